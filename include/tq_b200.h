@@ -1,0 +1,177 @@
+/*
+ * tq_b200.h -- C ABI of libtq_b200.so: the B200 (sm_100a) fake-quantization hot path.
+ *
+ * The reference (Qualcomm-AI-research/transformer-quantization) has no native/FFI boundary: its
+ * hot path is a chain of ATen ops inside Python classes.  This header is the boundary a native
+ * replacement binds to; every entry point names the reference code it replaces (file:line relative
+ * to the reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless a parameter says "host".  Tensors are contiguous,
+ *     row-major fp32 unless stated.
+ *   - `stream` is a cudaStream_t passed as void*.  Every call only enqueues work on that stream:
+ *     no allocation, no host synchronisation, no hidden global state -> CUDA-graph capturable.
+ *   - Workspaces are caller-owned, must be zero-initialised ONCE when allocated (the kernels leave
+ *     them zeroed again), and must not be shared by two streams at the same time.
+ *   - Return value: 0 = enqueued; <0 = TQ_E* argument error (nothing enqueued);
+ *     >0 = cudaError_t from the launch.
+ *   - Quantizer state stays on the device (the reference's `_delta`, `_zero_float`, `_signed`
+ *     buffers): kernels derive scale / zero_point / integer grid from it themselves, which removes
+ *     the `.item()` host syncs of quantizers.py:311-328.
+ */
+#ifndef TQ_B200_H
+#define TQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_OK 0
+#define TQ_EINVAL (-1)   /* bad argument (null pointer, negative size, n_bits out of range) */
+#define TQ_EALIGN (-2)   /* pointer alignment the entry point requires is not met */
+#define TQ_EWORKSPACE (-3) /* workspace too small */
+#define TQ_EUNSUPPORTED (-4)
+
+/* Quantizer state as the reference keeps it (quantizers.py:101-102, 308): raw `_delta`,
+ * `_zero_float` (asymmetric) or `_signed` (symmetric).  The kernels apply
+ *   scale      = max(delta, eps)            | exp(delta) for log_domain   (quantizers.py:142-147)
+ *   zero_point = clamp(round(zero_float), 0, 2^n-1)   | 0 for symmetric   (quantizers.py:149-153, 330-332)
+ *   [int_min, int_max] = [0, 2^n-1]                    asymmetric          (quantizers.py:131-140)
+ *                      = [-2^(n-1), 2^(n-1)-1] if *is_signed else [0, 2^n-1]   (quantizers.py:321-328)
+ * n_params = 1 (per-tensor) or C (per-axis / per-embedding-group / per-channel).  */
+typedef struct tq_qspec {
+    const float*   delta;       /* [n_params] */
+    const float*   zero_float;  /* [n_params]; NULL => symmetric quantizer */
+    const uint8_t* is_signed;   /* [1] (torch.bool); used only when zero_float == NULL */
+    int32_t        n_bits;      /* 1..16 */
+    int32_t        log_domain;  /* 0: 'linear', 1: 'log' scale_domain */
+    float          eps;         /* quantizer.eps, default 1e-8 */
+} tq_qspec;
+
+/* ---- library info ------------------------------------------------------------------------- */
+int         tq_version(void);              /* ABI version, currently 1 */
+const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
+int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
+
+/* ---- quantize -> round -> clamp -> dequantize ------------------------------------------------
+ * a1+a2: AsymmetricUniformQuantizer.forward / SymmetricUniformQuantizer (quantizers.py:172-211).
+ *   x_int = clamp(rint(x / scale) + zero_point, int_min, int_max);  y = scale * (x_int - zero_point)
+ * IEEE division, round-half-to-even, NaN propagates.  y must not alias x partially (y == x is
+ * allowed).  Per-tensor: q.n_params == 1. */
+int tq_qdq_f32(const float* x, float* y, int64_t n, tq_qspec q, void* stream);
+
+/* Per-axis variant: x viewed as [outer, C, inner]; parameter c applies to x[:, c, :].
+ *   per-embedding / PEG activations (B,T,d), axis=2 -> outer=B*T, C=d, inner=1   (quantizers.py:213-217)
+ *   per-channel weights (C_out, ...)              -> outer=1, C=C_out, inner=rest (quantizers.py:219-232) */
+int tq_qdq_axis_f32(const float* x, float* y, int64_t outer, int64_t C, int64_t inner,
+                    tq_qspec q, void* stream);
+
+/* to_integer_forward (quantizers.py:172-187): integer grid only.  Any of the outputs may be NULL.
+ *   x_int_f32 : fp32 integers, exactly what the reference returns
+ *   x_ctr_bf16: (x_int - zero_point) as bf16 (exact for n_bits <= 8) -- operand format of
+ *               tq_linear_qdq_bf16 */
+int tq_quant_int_f32(const float* x, float* x_int_f32, void* x_ctr_bf16,
+                     int64_t outer, int64_t C, int64_t inner, tq_qspec q, void* stream);
+
+/* ---- range estimation: min / max ------------------------------------------------------------
+ * a6-a8: torch.min / torch.max of CurrentMinMax / AllMinMax / RunningMinMax estimators
+ * (range_estimators.py:142-143,159-160,206-207).  One pass over x.  out = {min, max}; NaN
+ * propagates like torch.  ws: tq_minmax_workspace_bytes() bytes, zeroed once. */
+size_t tq_minmax_workspace_bytes(int64_t C);
+int tq_minmax_f32(const float* x, int64_t n, float* out_min_max, void* ws, size_t ws_bytes,
+                  void* stream);
+
+/* Per-axis min/max without the reference's transpose copy (range_estimators.py:82-85,115-116,
+ * 118-120,129-130,178-181,196-197): x viewed as [outer, C, inner] -> mn[C], mx[C]. */
+int tq_minmax_axis_f32(const float* x, int64_t outer, int64_t C, int64_t inner,
+                       float* mn, float* mx, void* ws, size_t ws_bytes, void* stream);
+
+/* Per-embedding-group statistics (range_estimators.py:87-112, 183-193): groups are contiguous
+ * blocks of C/n_groups dims of the (optionally range-sorted) hidden dims.  `ranges` (NULL = no
+ * permutation) is the per-dim range vector of the FP32 pass; the sort is stable (ties by index;
+ * the reference's torch.argsort leaves ties implementation-defined).  Replaces the reference's
+ * dense CxC permutation-matrix matmul by a gather on the [C] vectors (bit-identical).
+ * Returns TQ_EINVAL unless C % n_groups == 0 (reference: AssertionError, :89/:185). */
+int tq_group_minmax_f32(const float* mn, const float* mx, int64_t C, int32_t n_groups,
+                        const float* ranges, float* mn_out, float* mx_out, void* stream);
+
+/* FP32 "ranges" pass for the permutation (range_estimators.py:68-80): ranges = mx - mn; when
+ * `first` == 0 the reference's 0.1*r + 0.9*r re-rounding (lines 78-79) is applied. */
+int tq_dim_ranges_f32(const float* mn, const float* mx, int64_t C, int32_t first, float* ranges,
+                      void* stream);
+
+/* Estimator state update on the device (no host sync):
+ *   mode 0 current_minmax : cur = new                              (range_estimators.py:109-116,142-143)
+ *   mode 1 running_minmax : cur = first ? new : (1-m)*new + m*cur  (range_estimators.py:205-214)
+ *   mode 2 allminmax      : cur = first ? new : min/max(cur, new)  (range_estimators.py:162-167)
+ * `momentum` is the python double; (1 - momentum) and momentum are rounded to fp32 like torch does. */
+int tq_range_update_f32(const float* new_min, const float* new_max, float* cur_min, float* cur_max,
+                        int64_t k, int32_t mode, double momentum, int32_t first, void* stream);
+
+/* ---- set_quant_range on the device ------------------------------------------------------------
+ * a4: AsymmetricUniformQuantizer.set_quant_range (quantizers.py:234-282):
+ *   x_min = min(x_min, 0); x_max = max(x_max, eps); delta = (x_max - x_min) / (2^n - 1);
+ *   zero_float = -x_min / delta; log-domain: delta = log(delta). */
+int tq_set_range_asym_f32(const float* x_min, const float* x_max, int64_t k, int32_t n_bits,
+                          float eps, int32_t log_domain, float* delta, float* zero_float,
+                          void* stream);
+/* a5: SymmetricUniformQuantizer.set_quant_range (quantizers.py:334-344):
+ *   signed = any(min(x_min,0) < 0); delta = max(|x_min|, x_max) / int_max(signed). */
+int tq_set_range_sym_f32(const float* x_min, const float* x_max, int64_t k, int32_t n_bits,
+                         float eps, int32_t log_domain, float* delta, uint8_t* is_signed,
+                         void* stream);
+
+/* ---- MSE range estimator --------------------------------------------------------------------
+ * a9: MSE_Estimator.loss_fx (range_estimators.py:248-256) for a whole table of candidate
+ * quantizers in ONE read of x:   loss_accum[c] += sum_i (x_i - QDQ_c(x_i))^2,  c in [0, n_cand).
+ * The candidate table is built by the host exactly like MSE_Estimator.quantize (:287-294) builds
+ * its temporary quantizer: cand = {scale, zero_point, int_min, int_max} x n_cand, fp32, laid out
+ * as four consecutive arrays of n_cand.  Serves the 1-D grid (:356-376), the 2-D grid (:378-420)
+ * and -- with n_cand == 1 -- the golden-section objective (:296-327).
+ * Squared errors are fp32, block partials fp32, cross-block accumulation fp64 in a fixed order
+ * (deterministic).  ws: tq_mse_workspace_bytes(n_cand) bytes. */
+size_t tq_mse_workspace_bytes(int32_t n_cand);
+int tq_mse_sse_f32(const float* x, int64_t n, const float* cand, int32_t n_cand,
+                   double* loss_accum, void* ws, size_t ws_bytes, void* stream);
+
+/* argmin over the accumulated losses (np.argmin / unravel_index, range_estimators.py:370,406-408:
+ * first minimum in C order) and gather of the winning range:
+ *   xmin_out[0] = cand_xmin[idx], xmax_out[0] = cand_xmax[idx], idx_out[0] = idx. */
+int tq_mse_argmin_f64(const double* loss, int32_t n_cand, const float* cand_xmin,
+                      const float* cand_xmax, float* xmin_out, float* xmax_out, int32_t* idx_out,
+                      void* stream);
+
+/* ---- hijacked nn.Linear ---------------------------------------------------------------------
+ * a11: QuantizationHijacker.forward for QuantLinear (hijacker.py:66-116, autoquant_utils.py:16-21):
+ *     y = act_quant( act_fn( x @ Wq.T + bias ) )
+ * as one TMA-fed tcgen05 GEMM with a fused epilogue.  Operands are the INTEGER grids of the
+ * fake-quantized tensors carried in bf16 (exact for |v| <= 256):
+ *     a_ctr [M, K]  = x_int - zero_point of the input activation (tq_quant_int_f32 output)
+ *     w_ctr [N, K]  = w_int of the weight (symmetric: zero_point 0)
+ * fp32 accumulation in TMEM; epilogue: v = acc * (a_scale * w_scale[n]) + bias[n]; act_fn;
+ * then the output quantizer `out_q` (n_params 1 or N, i.e. per-tensor or per-column/PEG), written
+ * as fp32 `y` (may be NULL) and/or the bf16 centred integer grid `y_ctr` (may be NULL).
+ * If out_q.delta == NULL the epilogue stops after act_fn (FP32Acts / calibration pass) and, when
+ * `tile_minmax` != NULL, the per-tensor min/max of the pre-quantization output is reduced into
+ * tile_minmax[2] (calibration: range before quantize, quantization_manager.py:99-106).
+ * k_split == 3: A holds three bf16 planes [M, 3K] (hi|mid|lo split of an arbitrary fp32 tensor,
+ * a_scale = 1) -> fp32-accurate product for inputs that are not on a per-tensor grid.
+ * act_fn: 0 none, 1 GELU (erf), 2 ReLU, 3 Tanh.   Requires K % 64 == 0, N % 16 == 0. */
+size_t tq_linear_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias,
+                       float* y, void* y_ctr_bf16, int64_t M, int64_t N, int64_t K, int32_t k_split,
+                       const float* a_scale, const float* w_scale, int32_t w_scale_per_row,
+                       int32_t act_fn, tq_qspec out_q, int64_t out_q_params, float* tile_minmax,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* hi|mid|lo bf16 split of an fp32 tensor [M, K] -> [M, 3K] (x == hi + mid + lo to 2^-24 rel.). */
+int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQ_B200_H */

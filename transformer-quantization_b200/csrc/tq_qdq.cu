@@ -1,0 +1,278 @@
+// Quantize -> round -> clamp -> dequantize kernels.
+// Replaces the 6-pass ATen chain of AsymmetricUniformQuantizer.forward / to_integer_forward
+// (reference quantization/quantizers.py:172-211) by ONE pass: 4 B read + 4 B written per element.
+//
+// HBM-bound elementwise work.  Layout / mapping (B200: 148 SMs, 4 CTAs x 256 threads resident per
+// SM, 4 independent 128-bit loads in flight per thread = 64 KB in flight per SM):
+//   * per-tensor: grid-stride over float4 vectors, quantizer parameters resolved once per thread
+//     from the device-resident `_delta/_zero_float/_signed` buffers (no host sync).
+//   * per-embedding / per-embedding-group (x viewed [rows, C], inner == 1): the resolved per-dim
+//     {scale, zero_point} table is staged in shared memory once per CTA and indexed by hidden dim;
+//     the column of each vector is tracked incrementally (no 64-bit modulo in the loop).
+//   * per-channel weights (inner > 1): one row (channel) per CTA iteration, scalar parameters.
+#include "tq_common.cuh"
+#include <cuda_bf16.h>
+
+namespace tq {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+enum OutMode { OUT_QDQ = 0, OUT_INT = 1 };
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int MODE>
+__device__ __forceinline__ void emit_vec(const float4& v, const QP& p0, const QP& p1, const QP& p2,
+                                         const QP& p3, float4* y, float4* yint, uint2* yctr,
+                                         int64_t idx) {
+    float4 qi;
+    qi.x = quant_int(v.x, p0);
+    qi.y = quant_int(v.y, p1);
+    qi.z = quant_int(v.z, p2);
+    qi.w = quant_int(v.w, p3);
+    if (MODE == OUT_QDQ) {
+        float4 o;
+        o.x = dequant(qi.x, p0);
+        o.y = dequant(qi.y, p1);
+        o.z = dequant(qi.z, p2);
+        o.w = dequant(qi.w, p3);
+        st_stream(y + idx, o);
+    } else {
+        if (yint != nullptr) st_stream(yint + idx, qi);
+        if (yctr != nullptr) {
+            uint2 c;
+            c.x = pack_bf16x2(__fsub_rn(qi.x, p0.zp), __fsub_rn(qi.y, p1.zp));
+            c.y = pack_bf16x2(__fsub_rn(qi.z, p2.zp), __fsub_rn(qi.w, p3.zp));
+            yctr[idx] = c;
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void emit_scalar(float v, const QP& p, float* y, float* yint,
+                                            __nv_bfloat16* yctr, int64_t i) {
+    const float qi = quant_int(v, p);
+    if (MODE == OUT_QDQ) {
+        y[i] = dequant(qi, p);
+    } else {
+        if (yint != nullptr) yint[i] = qi;
+        if (yctr != nullptr) yctr[i] = __float2bfloat16_rn(__fsub_rn(qi, p.zp));
+    }
+}
+
+// ---- per-tensor ---------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+qdq_tensor_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yint,
+                      __nv_bfloat16* __restrict__ yctr, int64_t n, tq_qspec q) {
+    float lo, hi;
+    grid_of(q, lo, hi);
+    const QP p = resolve(q, 0, lo, hi);
+    const int64_t nvec = n >> 2;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    float4* yv = reinterpret_cast<float4*>(y);
+    float4* yiv = reinterpret_cast<float4*>(yint);
+    uint2* ycv = reinterpret_cast<uint2*>(yctr);
+    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
+    for (int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x; base < nvec;
+         base += stride) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) v[u] = ld_stream(xv + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) emit_vec<MODE>(v[u], p, p, p, p, yv, yiv, ycv, idx);
+        }
+    }
+    // ragged tail (n % 4 elements)
+    if (blockIdx.x == 0) {
+        const int64_t i = (nvec << 2) + threadIdx.x;
+        if (i < n) emit_scalar<MODE>(x[i], p, y, yint, yctr, i);
+    }
+}
+
+// generic scalar kernel: any alignment, any [outer, C, inner] view (C == 1: per-tensor)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+qdq_generic_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yint,
+                   __nv_bfloat16* __restrict__ yctr, int64_t n, int64_t C, int64_t inner,
+                   tq_qspec q) {
+    float lo, hi;
+    grid_of(q, lo, hi);
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        const int64_t c = (C == 1) ? 0 : (i / inner) % C;
+        const QP p = resolve(q, c, lo, hi);
+        emit_scalar<MODE>(x[i], p, y, yint, yctr, i);
+    }
+}
+
+// ---- per-embedding / per-embedding-group: x viewed [rows, C], parameters indexed by column ------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+qdq_cols_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yint,
+                    __nv_bfloat16* __restrict__ yctr, int64_t nvec, int32_t C, tq_qspec q) {
+    extern __shared__ __align__(16) float tab[];   // [C] scale | [C] zero_point, indexed by hidden dim
+    float lo, hi;
+    grid_of(q, lo, hi);
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+        const QP p = resolve(q, c, lo, hi);
+        tab[c] = p.scale;
+        tab[C + c] = p.zp;
+    }
+    __syncthreads();
+    const int32_t CV = C >> 2;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    float4* yv = reinterpret_cast<float4*>(y);
+    float4* yiv = reinterpret_cast<float4*>(yint);
+    uint2* ycv = reinterpret_cast<uint2*>(yctr);
+    const float4* sv = reinterpret_cast<const float4*>(tab);
+    const float4* zv = reinterpret_cast<const float4*>(tab + C);
+
+    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
+    int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x;
+    int32_t col0 = (int32_t)(base % CV);                 // vector column of the first access
+    const int32_t step = (int32_t)(stride % CV);
+    int32_t off[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) off[u] = (u * kThreads) % CV;
+
+    for (; base < nvec; base += stride) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) v[u] = ld_stream(xv + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) {
+                int32_t cv = col0 + off[u];
+                cv -= (cv >= CV) ? CV : 0;
+                const float4 s = sv[cv];
+                const float4 z = zv[cv];
+                const QP p0{s.x, z.x, lo, hi}, p1{s.y, z.y, lo, hi}, p2{s.z, z.z, lo, hi},
+                    p3{s.w, z.w, lo, hi};
+                emit_vec<MODE>(v[u], p0, p1, p2, p3, yv, yiv, ycv, idx);
+            }
+        }
+        col0 += step;
+        col0 -= (col0 >= CV) ? CV : 0;
+    }
+}
+
+// ---- per-channel rows: x viewed [rows = outer*C, inner], one parameter per row ------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+qdq_rows_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yint,
+                    __nv_bfloat16* __restrict__ yctr, int64_t rows, int64_t C, int64_t inner,
+                    tq_qspec q) {
+    float lo, hi;
+    grid_of(q, lo, hi);
+    const int64_t ivec = inner >> 2;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const QP p = resolve(q, r % C, lo, hi);
+        const float4* xv = reinterpret_cast<const float4*>(x + r * inner);
+        float4* yv = reinterpret_cast<float4*>(y + r * inner);
+        float4* yiv = yint ? reinterpret_cast<float4*>(yint + r * inner) : nullptr;
+        uint2* ycv = yctr ? reinterpret_cast<uint2*>(yctr + r * inner) : nullptr;
+        for (int64_t i = threadIdx.x; i < ivec; i += kThreads) {
+            const float4 v = ld_stream(xv + i);
+            emit_vec<MODE>(v, p, p, p, p, yv, yiv, ycv, i);
+        }
+    }
+}
+
+static int grid_for(int64_t work_items, int per_block, int ctas_per_sm) {
+    int64_t blocks = (work_items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <int MODE>
+static int launch_any(const float* x, float* y, float* yint, __nv_bfloat16* yctr, int64_t outer,
+                      int64_t C, int64_t inner, tq_qspec q, cudaStream_t st) {
+    const int64_t n = outer * C * inner;
+    if (n == 0) return TQ_OK;
+    const bool al = aligned16(x) && (MODE == OUT_QDQ ? aligned16(y)
+                                                     : ((yint == nullptr || aligned16(yint)) &&
+                                                        (yctr == nullptr ||
+                                                         (reinterpret_cast<uintptr_t>(yctr) & 7u) == 0)));
+    if (C == 1) {
+        if (al) {
+            const int grid = grid_for((n >> 2) + 1, kThreads * kUnroll, 4);
+            qdq_tensor_vec_kernel<MODE><<<grid, kThreads, 0, st>>>(x, y, yint, yctr, n, q);
+        } else {
+            qdq_generic_kernel<MODE><<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(x, y, yint, yctr, n,
+                                                                                   1, 1, q);
+        }
+        return launch_status();
+    }
+    if (inner == 1 && al && (C & 3) == 0 && C * 8 <= 200 * 1024) {
+        const size_t smem = (size_t)C * 8;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(qdq_cols_vec_kernel<MODE>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        const int grid = grid_for(n >> 2, kThreads * kUnroll, 4);
+        qdq_cols_vec_kernel<MODE><<<grid, kThreads, smem, st>>>(x, y, yint, yctr, n >> 2, (int32_t)C, q);
+        return launch_status();
+    }
+    if (inner > 1 && al && (inner & 3) == 0) {
+        const int64_t rows = outer * C;
+        const int grid = (int)(rows < (int64_t)sm_count() * 16 ? rows : (int64_t)sm_count() * 16);
+        qdq_rows_vec_kernel<MODE><<<grid, kThreads, 0, st>>>(x, y, yint, yctr, rows, C, inner, q);
+        return launch_status();
+    }
+    qdq_generic_kernel<MODE><<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(x, y, yint, yctr, n, C, inner,
+                                                                           q);
+    return launch_status();
+}
+
+}  // namespace tq
+
+extern "C" {
+
+int tq_qdq_f32(const float* x, float* y, int64_t n, tq_qspec q, void* stream) {
+    if (n < 0 || (n > 0 && (x == nullptr || y == nullptr))) return TQ_EINVAL;
+    if (int e = tq::check_qspec(q)) return e;
+    return tq::launch_any<tq::OUT_QDQ>(x, y, nullptr, nullptr, 1, 1, n, q, (cudaStream_t)stream);
+}
+
+int tq_qdq_axis_f32(const float* x, float* y, int64_t outer, int64_t C, int64_t inner, tq_qspec q,
+                    void* stream) {
+    if (outer < 0 || C < 1 || inner < 0) return TQ_EINVAL;
+    if (outer * C * inner > 0 && (x == nullptr || y == nullptr)) return TQ_EINVAL;
+    if (int e = tq::check_qspec(q)) return e;
+    return tq::launch_any<tq::OUT_QDQ>(x, y, nullptr, nullptr, outer, C, inner, q,
+                                       (cudaStream_t)stream);
+}
+
+int tq_quant_int_f32(const float* x, float* x_int_f32, void* x_ctr_bf16, int64_t outer, int64_t C,
+                     int64_t inner, tq_qspec q, void* stream) {
+    if (outer < 0 || C < 1 || inner < 0) return TQ_EINVAL;
+    if (outer * C * inner > 0 && x == nullptr) return TQ_EINVAL;
+    if (x_int_f32 == nullptr && x_ctr_bf16 == nullptr) return TQ_EINVAL;
+    if (int e = tq::check_qspec(q)) return e;
+    if (C == 1) {  // per-tensor: fold everything into one flat run
+        return tq::launch_any<tq::OUT_INT>(x, nullptr, x_int_f32, (__nv_bfloat16*)x_ctr_bf16, 1, 1,
+                                           outer * inner, q, (cudaStream_t)stream);
+    }
+    return tq::launch_any<tq::OUT_INT>(x, nullptr, x_int_f32, (__nv_bfloat16*)x_ctr_bf16, outer, C,
+                                       inner, q, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+"""ctypes binding of libtq_b200.so (C ABI: include/tq_b200.h) for PyTorch CUDA tensors.
+
+This is the ONLY arithmetic back-end of the package: there is no CPU / eager fallback.  If the
+shared library is missing, or a tensor is not on a CUDA device, the call raises immediately.
+
+PyTorch is plumbing here: it owns device memory (caching allocator), the current stream and the
+tensors' metadata; the binding only unwraps ``data_ptr()`` / ``cuda_stream`` and forwards them.
+Nothing in this module allocates inside a C call or synchronises the host, so every op can be
+captured in a CUDA graph (outputs are allocated with ``torch.empty`` before the call).
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get('TQ_B200_LIB', os.path.join(_HERE, 'lib', 'libtq_b200.so'))
+
+_c_f32p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+
+
+class QSpec(ctypes.Structure):
+    """struct tq_qspec (include/tq_b200.h)."""
+    _fields_ = [
+        ('delta', ctypes.c_void_p),
+        ('zero_float', ctypes.c_void_p),
+        ('is_signed', ctypes.c_void_p),
+        ('n_bits', ctypes.c_int32),
+        ('log_domain', ctypes.c_int32),
+        ('eps', ctypes.c_float),
+    ]
+
+
+class TQError(RuntimeError):
+    pass
+
+
+ACT_FN = {'none': 0, 'gelu': 1, 'relu': 2, 'tanh': 3}
+
+# exported symbol -> (restype, argtypes); also used by the CPU-side export test
+SIGNATURES = {
+    'tq_version': (ctypes.c_int, []),
+    'tq_error_string': (ctypes.c_char_p, [ctypes.c_int]),
+    'tq_device_sm_count': (ctypes.c_int, []),
+    'tq_qdq_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, QSpec, ctypes.c_void_p]),
+    'tq_qdq_axis_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i64, _i64, QSpec, ctypes.c_void_p]),
+    'tq_quant_int_f32': (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_void_p, _i64, _i64, _i64, QSpec,
+                                        ctypes.c_void_p]),
+    'tq_minmax_workspace_bytes': (ctypes.c_size_t, [_i64]),
+    'tq_minmax_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, ctypes.c_void_p, ctypes.c_size_t,
+                                     ctypes.c_void_p]),
+    'tq_minmax_axis_f32': (ctypes.c_int, [_c_f32p, _i64, _i64, _i64, _c_f32p, _c_f32p, ctypes.c_void_p,
+                                          ctypes.c_size_t, ctypes.c_void_p]),
+    'tq_group_minmax_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i32, _c_f32p, _c_f32p, _c_f32p,
+                                           ctypes.c_void_p]),
+    'tq_dim_ranges_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i32, _c_f32p, ctypes.c_void_p]),
+    'tq_range_update_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, _i64, _i32,
+                                           ctypes.c_double, _i32, ctypes.c_void_p]),
+    'tq_set_range_asym_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i32, ctypes.c_float, _i32,
+                                             _c_f32p, _c_f32p, ctypes.c_void_p]),
+    'tq_set_range_sym_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i32, ctypes.c_float, _i32,
+                                            _c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
+    'tq_mse_workspace_bytes': (ctypes.c_size_t, [_i32]),
+    'tq_mse_sse_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i32, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_void_p]),
+    'tq_mse_argmin_f64': (ctypes.c_int, [ctypes.c_void_p, _i32, _c_f32p, _c_f32p, _c_f32p, _c_f32p,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
+    'tq_linear_workspace_bytes': (ctypes.c_size_t, [_i64, _i64, _i64]),
+    'tq_linear_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p,
+                                          ctypes.c_void_p, _i64, _i64, _i64, _i32, _c_f32p, _c_f32p,
+                                          _i32, _i32, QSpec, _i64, _c_f32p, ctypes.c_void_p,
+                                          ctypes.c_size_t, ctypes.c_void_p]),
+    'tq_split3_bf16': (ctypes.c_int, [_c_f32p, ctypes.c_void_p, _i64, _i64, ctypes.c_void_p]),
+}
+
+
+def load_library(path=None):
+    """dlopen the library and attach prototypes.  No CUDA call is made here."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise TQError(
+            f'tq_b200: {path} not found -- build it with transformer-quantization_b200/csrc/build.sh '
+            f'(or __graft_entry__.build()).  There is no CPU fallback.')
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)         # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TQError('tq_b200: CUDA tensors required (this build has no CPU path); got a '
+                          f'{t.device} tensor')
+
+
+class CudaOps:
+    """Tensor-level wrappers around the C ABI.  One instance per process (see ``ops()``)."""
+
+    def __init__(self, lib=None):
+        self.lib = lib or load_library()
+        self._ws = {}
+        self._lock = threading.Lock()
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _check(self, code):
+        if code != 0:
+            raise TQError(f'tq_b200 call failed ({code}): {self.lib.tq_error_string(code).decode()}')
+
+    def workspace(self, kind, nbytes, device):
+        """Zero-initialised scratch, cached per (kind, device, stream) and grown on demand."""
+        key = (kind, device.index, _stream())
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            with self._lock:
+                buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+                self._ws[key] = buf
+        return buf
+
+    @staticmethod
+    def spec(delta, zero_float, is_signed, n_bits, log_domain=False, eps=1e-8):
+        return QSpec(_ptr(delta), _ptr(zero_float), _ptr(is_signed), int(n_bits), int(bool(log_domain)),
+                     float(eps))
+
+    # -- QDQ ------------------------------------------------------------------------------------
+    def qdq(self, x, spec, outer=1, C=1, inner=None, out=None):
+        _chk_cuda(x)
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            raise TQError(f'tq_b200: fp32 tensors only, got {x.dtype}')
+        y = torch.empty_like(x) if out is None else out
+        n = x.numel()
+        if C == 1:
+            self._check(self.lib.tq_qdq_f32(x.data_ptr(), y.data_ptr(), n, spec, _stream()))
+        else:
+            self._check(self.lib.tq_qdq_axis_f32(x.data_ptr(), y.data_ptr(), outer, C, inner, spec, _stream()))
+        return y
+
+    def quant_int(self, x, spec, outer=1, C=1, inner=None, want_f32=True, want_bf16=False):
+        _chk_cuda(x)
+        x = x.contiguous()
+        n = x.numel()
+        yi = torch.empty_like(x) if want_f32 else None
+        yc = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+        if C == 1:
+            outer, inner = 1, n
+        self._check(self.lib.tq_quant_int_f32(x.data_ptr(), _ptr(yi), _ptr(yc), outer, C, inner, spec, _stream()))
+        return yi, yc
+
+    # -- min / max ------------------------------------------------------------------------------
+    def minmax(self, x):
+        """-> fp32 tensor [2] = (min, max) on the device."""
+        _chk_cuda(x)
+        x = x.contiguous()
+        if x.numel() == 0:
+            raise RuntimeError('min(): Expected reduction dim to be specified for input.numel() == 0')
+        out = torch.empty(2, dtype=torch.float32, device=x.device)
+        nb = self.lib.tq_minmax_workspace_bytes(1)
+        ws = self.workspace('mm', nb, x.device)
+        self._check(self.lib.tq_minmax_f32(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        return out
+
+    def minmax_axis(self, x, outer, C, inner):
+        """x viewed [outer, C, inner] -> (mn[C], mx[C])."""
+        _chk_cuda(x)
+        x = x.contiguous()
+        out = torch.empty(2, C, dtype=torch.float32, device=x.device)
+        nb = self.lib.tq_minmax_workspace_bytes(C)
+        ws = self.workspace('mm', nb, x.device)
+        self._check(self.lib.tq_minmax_axis_f32(x.data_ptr(), outer, C, inner, out[0].data_ptr(), out[1].data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _stream()))
+        return out[0], out[1]
+
+    def group_minmax(self, mn, mx, n_groups, ranges=None):
+        _chk_cuda(mn, mx, ranges)
+        C = mn.numel()
+        out = torch.empty(2, C, dtype=torch.float32, device=mn.device)
+        code = self.lib.tq_group_minmax_f32(mn.data_ptr(), mx.data_ptr(), C, int(n_groups), _ptr(ranges),
+                                            out[0].data_ptr(), out[1].data_ptr(), _stream())
+        self._check(code)
+        return out[0], out[1]
+
+    def dim_ranges(self, mn, mx, first):
+        _chk_cuda(mn, mx)
+        r = torch.empty_like(mn)
+        self._check(self.lib.tq_dim_ranges_f32(mn.data_ptr(), mx.data_ptr(), mn.numel(), int(bool(first)),
+                                               r.data_ptr(), _stream()))
+        return r
+
+    def range_update(self, new_min, new_max, cur_min, cur_max, mode, momentum=0.0, first=False):
+        """In-place update of (cur_min, cur_max); mode 0 current, 1 running EMA, 2 all-minmax."""
+        _chk_cuda(new_min, new_max, cur_min, cur_max)
+        self._check(self.lib.tq_range_update_f32(new_min.data_ptr(), new_max.data_ptr(), cur_min.data_ptr(),
+                                                 cur_max.data_ptr(), new_min.numel(), mode, float(momentum),
+                                                 int(bool(first)), _stream()))
+
+    # -- set_quant_range ------------------------------------------------------------------------
+    def set_range_asym(self, x_min, x_max, n_bits, eps, log_domain, delta, zero_float):
+        _chk_cuda(x_min, x_max, delta, zero_float)
+        self._check(self.lib.tq_set_range_asym_f32(x_min.data_ptr(), x_max.data_ptr(), x_min.numel(), int(n_bits),
+                                                   float(eps), int(bool(log_domain)), delta.data_ptr(),
+                                                   zero_float.data_ptr(), _stream()))
+
+    def set_range_sym(self, x_min, x_max, n_bits, eps, log_domain, delta, is_signed):
+        _chk_cuda(x_min, x_max, delta, is_signed)
+        self._check(self.lib.tq_set_range_sym_f32(x_min.data_ptr(), x_max.data_ptr(), x_min.numel(), int(n_bits),
+                                                  float(eps), int(bool(log_domain)), delta.data_ptr(),
+                                                  is_signed.data_ptr(), _stream()))
+
+    # -- MSE ------------------------------------------------------------------------------------
+    def mse_sse(self, x, cand, n_cand, loss_accum):
+        """loss_accum[c] += sum((x - QDQ_c(x))^2) for the candidate table ``cand`` [4, n_cand]."""
+        _chk_cuda(x, cand, loss_accum)
+        x = x.contiguous()
+        nb = self.lib.tq_mse_workspace_bytes(n_cand)
+        ws = self.workspace('mse', nb, x.device)
+        self._check(self.lib.tq_mse_sse_f32(x.data_ptr(), x.numel(), cand.data_ptr(), n_cand,
+                                            loss_accum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+
+    def mse_argmin(self, loss, cand_xmin, cand_xmax):
+        """-> (xmin[1], xmax[1], idx[1]) device tensors; first minimum of the flat loss array."""
+        _chk_cuda(loss, cand_xmin, cand_xmax)
+        out = torch.empty(2, dtype=torch.float32, device=loss.device)
+        idx = torch.empty(1, dtype=torch.int32, device=loss.device)
+        self._check(self.lib.tq_mse_argmin_f64(loss.data_ptr(), loss.numel(), cand_xmin.data_ptr(),
+                                               cand_xmax.data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(),
+                                               idx.data_ptr(), _stream()))
+        return out[0:1], out[1:2], idx
+
+    # -- fused linear -----------------------------------------------------------------------------
+    def split3(self, x2d):
+        _chk_cuda(x2d)
+        M, K = x2d.shape
+        out = torch.empty(M, 3 * K, dtype=torch.bfloat16, device=x2d.device)
+        self._check(self.lib.tq_split3_bf16(x2d.data_ptr(), out.data_ptr(), M, K, _stream()))
+        return out
+
+    def linear(self, a_ctr, w_ctr, bias, M, N, K, k_split, a_scale, w_scale, w_scale_per_row, act_fn,
+               out_spec, out_params, want_f32=True, want_ctr=False, tile_minmax=None):
+        _chk_cuda(a_ctr, w_ctr, bias, a_scale, w_scale)
+        dev = a_ctr.device
+        y = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
+        yc = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if want_ctr else None
+        nb = self.lib.tq_linear_workspace_bytes(M, N, K)
+        ws = self.workspace('lin', nb, dev)
+        spec = out_spec if out_spec is not None else QSpec(None, None, None, 8, 0, 1e-8)
+        self._check(self.lib.tq_linear_qdq_bf16(a_ctr.data_ptr(), w_ctr.data_ptr(), _ptr(bias), _ptr(y), _ptr(yc),
+                                                M, N, K, int(k_split), _ptr(a_scale), w_scale.data_ptr(),
+                                                int(bool(w_scale_per_row)), int(act_fn), spec, int(out_params),
+                                                _ptr(tile_minmax), ws.data_ptr(), ws.numel(), _stream()))
+        return y, yc
+
+
+_OPS = None
+
+
+def default_device():
+    """Device for quantizer state created from python floats (before any tensor was seen)."""
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def ops():
+    """The process-wide CUDA back-end.  Raises (never falls back) if it cannot be created."""
+    global _OPS
+    if _OPS is None:
+        if not torch.cuda.is_available():
+            raise TQError('tq_b200: no CUDA device visible -- the fake-quantization kernels are '
+                          'sm_100a only and there is no CPU fallback')
+        _OPS = CudaOps()
+    return _OPS

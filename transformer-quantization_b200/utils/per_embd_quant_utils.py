@@ -1,0 +1,68 @@
+"""Per-embedding / per-embedding-group (PEG) and mixed-precision switches for existing quantizer
+sites.  Mirror of the reference's utils/per_embd_quant_utils.py (same function names and
+``quant_dict`` value grammar): an int sets n_bits, 'fp32' disables the site, 'per_embd' quantizes
+per hidden dim, 'ngK' uses K contiguous groups of hidden dims, 'ngpK' K groups after sorting the
+dims by their dynamic range.
+
+With these settings the quantizer parameters become [d]-vectors with K distinct values; the QDQ
+kernel stages the resolved per-dim table in shared memory and indexes it by hidden dim
+(csrc/tq_qdq.cu, qdq_cols_vec_kernel), the statistics come from tq_minmax_axis_f32 +
+tq_group_minmax_f32.
+"""
+from quantization.base_quantized_classes import FP32Acts
+
+
+def set_act_quant_axis_and_groups(module, axis, n_groups, permute=False):
+    """Turn a per-tensor activation quantizer into a per-axis / per-group one (reference :54-68).
+    With ``permute`` the next FP32 pass only collects per-dim ranges for the group permutation."""
+    mgr = module.activation_quantizer if hasattr(module, 'activation_quantizer') else module
+    for owner in (mgr, mgr.quantizer, mgr.range_estimator):
+        owner.axis = axis
+    for owner in (mgr, mgr.range_estimator):
+        owner.n_groups = n_groups
+    if permute:
+        mgr.range_estimator.per_group_range_estimation = True
+    return mgr
+
+
+def _hijack_act_quant(module, value):
+    if value is None:
+        return
+    if isinstance(value, int):
+        module.activation_quantizer.quantizer.n_bits = value
+    elif value == 'fp32':
+        module.activation_quantizer = FP32Acts()
+    elif value == 'per_embd':
+        set_act_quant_axis_and_groups(module, axis=2, n_groups=None)
+    elif value.startswith('ngp'):
+        set_act_quant_axis_and_groups(module, axis=2, n_groups=int(value[3:]), permute=True)
+    elif value.startswith('ng'):
+        set_act_quant_axis_and_groups(module, axis=2, n_groups=int(value[2:]), permute=False)
+    else:
+        raise NotImplementedError(f'Unknown value "{value}" in quant_dict')
+
+
+def _hijack_weight_quant(module, value):
+    if value is None:
+        return
+    if isinstance(value, int):
+        module.weight_quantizer.quantizer.n_bits = value
+    elif value == 'fp32':
+        module.weight_quantizer = FP32Acts()
+    else:
+        raise NotImplementedError(f'Unknown value "{value}" in quant_dict')
+
+
+def hijack_act_quant(quant_dict, name, m):
+    _hijack_act_quant(m, quant_dict.get(name, None))
+
+
+def hijack_weight_quant(quant_dict, name, m):
+    _hijack_weight_quant(m, quant_dict.get(name, None))
+
+
+def hijack_act_quant_modules(quant_dict, name, m):
+    value = quant_dict.get(name, None)
+    for sub in m.modules():
+        if hasattr(sub, 'activation_quantizer'):
+            _hijack_act_quant(sub, value)
