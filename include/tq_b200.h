@@ -153,18 +153,21 @@ int tq_mse_argmin_f64(const double* loss, int32_t n_cand, const float* cand_xmin
  *     a_ctr [M, K]  = x_int - zero_point of the input activation (tq_quant_int_f32 output)
  *     w_ctr [N, K]  = w_int of the weight (symmetric: zero_point 0)
  * fp32 accumulation in TMEM; epilogue: v = acc * (a_scale * w_scale[n]) + bias[n]; act_fn;
+ * a_scale / w_scale[n] are resolved from the operand quantizers `a_q` (per-tensor; delta == NULL:
+ * scale 1) and `w_q` (w_q_params = 1 per-tensor or N per output channel);
  * then the output quantizer `out_q` (n_params 1 or N, i.e. per-tensor or per-column/PEG), written
  * as fp32 `y` (may be NULL) and/or the bf16 centred integer grid `y_ctr` (may be NULL).
  * If out_q.delta == NULL the epilogue stops after act_fn (FP32Acts / calibration pass) and, when
  * `tile_minmax` != NULL, the per-tensor min/max of the pre-quantization output is reduced into
  * tile_minmax[2] (calibration: range before quantize, quantization_manager.py:99-106).
  * k_split == 3: A holds three bf16 planes [M, 3K] (hi|mid|lo split of an arbitrary fp32 tensor,
- * a_scale = 1) -> fp32-accurate product for inputs that are not on a per-tensor grid.
- * act_fn: 0 none, 1 GELU (erf), 2 ReLU, 3 Tanh.   Requires K % 64 == 0, N % 16 == 0. */
+ * a_q.delta = NULL) -> fp32-accurate product for inputs that are not on a per-tensor grid.
+ * act_fn: 0 none, 1 GELU (erf), 2 ReLU, 3 Tanh.   Requires K % 64 == 0, N % 8 == 0,
+ * 16-byte aligned operands; otherwise TQ_EUNSUPPORTED / TQ_EALIGN (callers use a library GEMM then). */
 size_t tq_linear_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias,
                        float* y, void* y_ctr_bf16, int64_t M, int64_t N, int64_t K, int32_t k_split,
-                       const float* a_scale, const float* w_scale, int32_t w_scale_per_row,
+                       tq_qspec a_q, tq_qspec w_q, int64_t w_q_params,
                        int32_t act_fn, tq_qspec out_q, int64_t out_q_params, float* tile_minmax,
                        void* ws, size_t ws_bytes, void* stream);
 

@@ -95,3 +95,31 @@ for kind, opt in [('symmetric_uniform', 'grid'), ('asymmetric_uniform', 'grid')]
 
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'kernel_bench.json'), 'w'), indent=1)
+
+# ---- fused linear (tcgen05) ---------------------------------------------------------------------
+try:
+    tf_peak = peaks.get('bf16_tflops', 1590.0)
+    for (M, N, K, act) in [(4096, 768, 768, 0), (4096, 2304, 768, 0), (4096, 3072, 768, 1), (4096, 768, 3072, 0),
+                           (8192, 128, 512, 0), (8192, 512, 128, 2), (16384, 4096, 4096, 0)]:
+        a = torch.randint(-255, 256, (M, K), device=dev).to(torch.bfloat16)
+        w = torch.randint(-128, 128, (N, K), device=dev).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        d = torch.tensor([0.02], device=dev); z = torch.tensor([128.0], device=dev)
+        od = torch.tensor([50.0], device=dev); oz = torch.tensor([120.0], device=dev)
+        a_spec = ops.spec(d, z, None, 8); o_spec = ops.spec(od, oz, None, 8)
+        ws = torch.tensor([0.001], device=dev); sg = torch.tensor(True, device=dev)
+        w_spec = ops.spec(ws, None, sg, 8)
+        fn = lambda: ops.linear(a, w, bias, M, N, K, 1, a_spec, w_spec, 1, act, o_spec, 1)
+        t = timeit(fn, iters=10, warm=3, flush=True)
+        fl = 2.0 * M * N * K
+        r = dict(kernel='linear_qdq_bf16', shape=[M, N, K], act=act, ms_median=t[0], ms_best=t[1],
+                 tflops_median=fl / t[0] / 1e9, tflops_best=fl / t[1] / 1e9, frac_of_measured_bf16_peak=fl / t[0] / 1e9 / tf_peak)
+        res.append(r)
+        print(json.dumps(r), flush=True)
+        t2 = timeit(lambda: torch.matmul(a, w.T), iters=10, warm=3, flush=True)
+        r = dict(kernel='cublas_bf16_matmul(reference point)', shape=[M, N, K], ms_median=t2[0], tflops_median=fl / t2[0] / 1e9)
+        res.append(r)
+        print(json.dumps(r), flush=True)
+except Exception as e:  # noqa
+    print('linear bench failed:', repr(e), flush=True)
+json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'kernel_bench.json'), 'w'), indent=1)

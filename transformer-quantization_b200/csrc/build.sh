@@ -11,6 +11,6 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=f
        -Xcompiler -fPIC -Xcompiler -O2 -shared -Xptxas -v "$@")
 SRC_EXIST=()
 for s in "${SRCS[@]}"; do [ -f "$s" ] && SRC_EXIST+=("$s"); done
-"$NVCC" "${FLAGS[@]}" -o "$OUT/libtq_b200.so" "${SRC_EXIST[@]}" -lcuda 2> "$OUT/ptxas.log" || { cat "$OUT/ptxas.log"; exit 1; }
+"$NVCC" "${FLAGS[@]}" -o "$OUT/libtq_b200.so" "${SRC_EXIST[@]}" 2> "$OUT/ptxas.log" || { cat "$OUT/ptxas.log"; exit 1; }
 grep -E "error|warning" "$OUT/ptxas.log" | grep -v "ptxas info" || true
 echo "built $OUT/libtq_b200.so"

@@ -1,30 +1,147 @@
 """QuantLinear data path.
 
-``linear``      -- the plain op of QuantLinear.run_forward (reference autoquant_utils.py:20-21).
+``linear``      -- the plain op of QuantLinear.run_forward (reference autoquant_utils.py:20-21);
+                   only reached when fusion does not apply (e.g. weights not quantized).
 ``try_fused``   -- GEMM + bias + activation fn + output QDQ as ONE tcgen05 kernel
-                   (tq_linear_qdq_bf16) when the layer state allows it; returns None otherwise.
+                   (tq_linear_qdq_bf16); returns None when the layer state is not supported.
 
 Operand carriers.  A fake-quantized tensor is ``scale * (x_int - zero_point)``; for n_bits <= 8 the
 centred integer ``x_int - zero_point`` (|v| <= 255) and the weight grid are exact in bf16, so the
 GEMM runs on the integer grids with fp32 accumulation in TMEM and the scales are applied once in
 the epilogue -- more exact than the reference's fp32 GEMM on dequantized values.  The activation's
 grid is recovered exactly from the fp32 tensor (``rint(x / scale)``) using the tag the producing
-quantizer attached (``_tq_grid``); inputs without a per-tensor 8-bit tag (FP32 activations,
-per-embedding-group inputs whose scale varies along K, 16-bit activations) take the hi|mid|lo
-bf16 split path (three bf16 planes, fp32-accurate).
+quantizer attached (``_tq_grid``, invalidated by in-place edits through the tensor version
+counter); inputs without a per-tensor <= 8-bit tag (FP32 activations, per-embedding-group inputs
+whose scale varies along K, 16-bit activations) take the hi|mid|lo bf16 split path (three bf16
+planes, fp32-accurate product).
 """
 import torch
+from torch import nn
 from torch.nn import functional as F
 
 import tq_native
 
-_STATE = {'enabled': True}
+ENABLED = True          # tests flip this to compare against the unfused path
+
+_ACT_CODES = ((nn.GELU, 1), (nn.ReLU, 2), (nn.Tanh, 3))
+
+
+class GridTag:
+    """What a per-tensor quantizer knows about the tensor it just produced."""
+    __slots__ = ('quantizer', 'version', 'ctr')
+
+    def __init__(self, quantizer, tensor):
+        self.quantizer = quantizer
+        self.version = tensor._version
+        self.ctr = None          # bf16 centred integer grid, filled lazily / by a fused producer
+
+
+def tag_output(quantizer, y):
+    """Called by the quantizers after a per-tensor QDQ with n_bits <= 8."""
+    y._tq_grid = GridTag(quantizer, y)
+    return y
+
+
+def _valid_tag(x):
+    tag = getattr(x, '_tq_grid', None)
+    if tag is None or tag.version != x._version or not tag.quantizer.is_initialized:
+        return None
+    return tag
 
 
 def linear(x, weight, bias):
-    """Plain (unfused) linear used during calibration / when fusion is not applicable."""
+    """Plain (unfused) linear: library GEMM."""
     return F.linear(x.contiguous(), weight.contiguous(), bias=bias)
 
 
-def try_fused(layer, x, weight, bias):
+def _act_code(fn):
+    if fn is None:
+        return 0
+    for cls, code in _ACT_CODES:
+        if isinstance(fn, cls):
+            if cls is nn.GELU and getattr(fn, 'approximate', 'none') != 'none':
+                return None
+            return code
     return None
+
+
+def _weight_grid(layer, weight_q):
+    """bf16 integer grid of the (cached) fake-quantized weight + its quantizer spec."""
+    mgr = layer.weight_quantizer
+    qz = getattr(mgr, 'quantizer', None)
+    if qz is None or not qz.is_initialized or qz.n_bits > 8 or qz.axis is not None:
+        return None
+    cache = getattr(layer, '_tq_wgrid', None)
+    if cache is not None and cache[0] is weight_q:
+        return cache[1], cache[2], cache[3]
+    w = layer.weight.detach()
+    N = w.shape[0]
+    k = qz.delta.numel()
+    if k not in (1, N):
+        return None
+    spec = qz._spec()
+    _, w_ctr = tq_native.ops().quant_int(w, spec, 1, k, w.numel() // k if k > 1 else None,
+                                         want_f32=False, want_bf16=True)
+    layer._tq_wgrid = (weight_q, w_ctr, spec, k)
+    return w_ctr, spec, k
+
+
+def try_fused(layer, x, weight, bias):
+    """Fused QuantLinear forward or None.  ``weight`` is what get_params() returned."""
+    if not ENABLED or layer.training or not layer._quant_w or not x.is_cuda or x.dtype != torch.float32:
+        return None
+    act = _act_code(layer.activation_function)
+    if act is None:
+        return None
+    N, K = layer.weight.shape
+    if K % 64 != 0 or N % 8 != 0 or x.shape[-1] != K or x.numel() == 0:
+        return None
+    wg = _weight_grid(layer, weight)
+    if wg is None:
+        return None
+    w_ctr, w_spec, w_params = wg
+
+    # ---- output quantizer state ----
+    mgr = layer.activation_quantizer
+    out_spec, out_params, calibrate = None, 1, False
+    if layer._quant_a and hasattr(mgr, 'quantizer'):
+        if mgr.range_estimator is not None and mgr.range_estimator.per_group_range_estimation:
+            calibrate = True                       # FP32 ranges pass: manager handles it, no QDQ
+        elif mgr._updates_ranges():
+            calibrate = True                       # range is needed before quantizing: two steps
+        else:
+            qz = mgr.quantizer
+            if not qz.is_initialized:
+                return None
+            k = qz.delta.numel()
+            if qz.axis is not None and k > 1:
+                if qz.axis != x.dim() - 1 or k != N:
+                    return None
+                qz._adjust_params_per_axis(x)      # keep the reference's [1,..,C] parameter view
+                out_params = N
+            elif k != 1:
+                return None
+            out_spec = qz._spec()
+
+    # ---- input operand ----
+    ops = tq_native.ops()
+    x2 = x.contiguous().view(-1, K)
+    M = x2.shape[0]
+    tag = _valid_tag(x)
+    a_spec = None
+    if tag is not None and tag.quantizer.n_bits <= 8 and tag.quantizer.delta.numel() == 1:
+        a_spec = tag.quantizer._spec()
+        if tag.ctr is None:
+            _, tag.ctr = ops.quant_int(x2, a_spec, want_f32=False, want_bf16=True)
+        a_ctr, k_split = tag.ctr.view(M, K), 1
+    else:
+        a_ctr, k_split = ops.split3(x2), 3
+
+    y, _ = ops.linear(a_ctr, w_ctr, bias, M, N, K, k_split, a_spec, w_spec, w_params, act, out_spec,
+                      out_params, want_f32=True, want_ctr=False)
+    y = y.view(*x.shape[:-1], N)
+    if calibrate:
+        return mgr(y)                              # estimator update + set_quant_range + QDQ kernels
+    if out_spec is not None and out_params == 1 and mgr.quantizer.n_bits <= 8:
+        tag_output(mgr.quantizer, y)
+    return y

@@ -21,6 +21,7 @@ from torch import nn
 from torch.autograd import Function
 
 import tq_native
+from quantization import fused_linear
 
 
 class RoundStraightThrough(Function):
@@ -208,7 +209,12 @@ class AsymmetricUniformQuantizer(QuantizerBase):
         """Quantize-dequantize ``x_float`` (reference quantizers.py:189-211)."""
         spec = self._spec()
         outer, C, inner = self._layout(x_float)
-        return tq_native.ops().qdq(x_float, spec, outer, C, inner)
+        y = tq_native.ops().qdq(x_float, spec, outer, C, inner)
+        if C == 1 and self.n_bits <= 8:
+            # remember which grid y lives on: a following QuantLinear feeds the integer grid to
+            # the tensor cores (quantization/fused_linear.py)
+            fused_linear.tag_output(self, y)
+        return y
 
     def _adjust_params_per_axis(self, x_float):
         """Keep the reference's parameter shape [1,..,C,..,1] (quantizers.py:213-217)."""

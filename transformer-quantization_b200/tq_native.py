@@ -70,8 +70,8 @@ SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_void_p]),
     'tq_linear_workspace_bytes': (ctypes.c_size_t, [_i64, _i64, _i64]),
     'tq_linear_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p,
-                                          ctypes.c_void_p, _i64, _i64, _i64, _i32, _c_f32p, _c_f32p,
-                                          _i32, _i32, QSpec, _i64, _c_f32p, ctypes.c_void_p,
+                                          ctypes.c_void_p, _i64, _i64, _i64, _i32, QSpec, QSpec, _i64,
+                                          _i32, QSpec, _i64, _c_f32p, ctypes.c_void_p,
                                           ctypes.c_size_t, ctypes.c_void_p]),
     'tq_split3_bf16': (ctypes.c_int, [_c_f32p, ctypes.c_void_p, _i64, _i64, ctypes.c_void_p]),
 }
@@ -143,6 +143,8 @@ class CudaOps:
             raise TQError(f'tq_b200: fp32 tensors only, got {x.dtype}')
         y = torch.empty_like(x) if out is None else out
         n = x.numel()
+        if n == 0:
+            return y
         if C == 1:
             self._check(self.lib.tq_qdq_f32(x.data_ptr(), y.data_ptr(), n, spec, _stream()))
         else:
@@ -155,6 +157,8 @@ class CudaOps:
         n = x.numel()
         yi = torch.empty_like(x) if want_f32 else None
         yc = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+        if n == 0:
+            return yi, yc
         if C == 1:
             outer, inner = 1, n
         self._check(self.lib.tq_quant_int_f32(x.data_ptr(), _ptr(yi), _ptr(yc), outer, C, inner, spec, _stream()))
@@ -248,19 +252,20 @@ class CudaOps:
         self._check(self.lib.tq_split3_bf16(x2d.data_ptr(), out.data_ptr(), M, K, _stream()))
         return out
 
-    def linear(self, a_ctr, w_ctr, bias, M, N, K, k_split, a_scale, w_scale, w_scale_per_row, act_fn,
+    def linear(self, a_ctr, w_ctr, bias, M, N, K, k_split, a_spec, w_spec, w_params, act_fn,
                out_spec, out_params, want_f32=True, want_ctr=False, tile_minmax=None):
-        _chk_cuda(a_ctr, w_ctr, bias, a_scale, w_scale)
+        """tq_linear_qdq_bf16: [M, k_split*K] x [N, K]^T -> (y fp32 [M, N] | None, y_ctr bf16 | None)."""
+        _chk_cuda(a_ctr, w_ctr, bias)
         dev = a_ctr.device
         y = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
         yc = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if want_ctr else None
-        nb = self.lib.tq_linear_workspace_bytes(M, N, K)
-        ws = self.workspace('lin', nb, dev)
-        spec = out_spec if out_spec is not None else QSpec(None, None, None, 8, 0, 1e-8)
-        self._check(self.lib.tq_linear_qdq_bf16(a_ctr.data_ptr(), w_ctr.data_ptr(), _ptr(bias), _ptr(y), _ptr(yc),
-                                                M, N, K, int(k_split), _ptr(a_scale), w_scale.data_ptr(),
-                                                int(bool(w_scale_per_row)), int(act_fn), spec, int(out_params),
-                                                _ptr(tile_minmax), ws.data_ptr(), ws.numel(), _stream()))
+        null = QSpec(None, None, None, 8, 0, 1e-8)
+        code = self.lib.tq_linear_qdq_bf16(
+            a_ctr.data_ptr(), w_ctr.data_ptr(), _ptr(bias), _ptr(y), _ptr(yc), M, N, K, int(k_split),
+            a_spec if a_spec is not None else null, w_spec if w_spec is not None else null, int(w_params),
+            int(act_fn), out_spec if out_spec is not None else null, int(out_params), _ptr(tile_minmax),
+            None, 0, _stream())
+        self._check(code)
         return y, yc
 
 
