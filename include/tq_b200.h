@@ -57,6 +57,12 @@ int         tq_version(void);              /* ABI version, currently 1 */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
 
+/* Device self-test of the division-free quotient used by every quantizing kernel (csrc/
+ * tq_common.cuh, tq::div_rn): blocks*256*iters adversarial (x, scale) pairs are compared bit for
+ * bit with the IEEE division instruction.  mismatches[0] += #quotient mismatches,
+ * mismatches[1] += #integer-grid mismatches (device uint64[2], caller-zeroed). */
+int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mismatches, void* stream);
+
 /* ---- quantize -> round -> clamp -> dequantize ------------------------------------------------
  * a1+a2: AsymmetricUniformQuantizer.forward / SymmetricUniformQuantizer (quantizers.py:172-211).
  *   x_int = clamp(rint(x / scale) + zero_point, int_min, int_max);  y = scale * (x_int - zero_point)

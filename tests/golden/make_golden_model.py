@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""Model-level golden outputs: the UNMODIFIED reference ``models/quantized_bert.py`` +
+``quantization/*`` (from /root/reference) run on CPU through the HF-4.1 compatibility shim
+(tests/hf41_shim.py) on a tiny BERT.  Run in the build container only:
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_model.py
+
+Writes tests/golden/bert_tiny.npz: weights, token ids and, per configuration, the logits, the
+final hidden states and every activation quantizer's (delta, zero_float) after calibration.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TESTS = os.path.dirname(HERE)
+REF = os.environ.get('TQ_REFERENCE', '/root/reference')
+sys.dont_write_bytecode = True
+sys.path.insert(0, TESTS)
+
+
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def import_reference_model(package_root):
+    """import ``models.quantized_bert`` from the reference with ``quantization`` / ``utils``
+    resolved under ``package_root`` (the reference itself, or this repo's package)."""
+    import hf41_shim
+    hf41_shim.install()
+    for k in [k for k in sys.modules if k.split('.')[0] in ('quantization', 'utils', 'models')]:
+        del sys.modules[k]
+    sys.path.insert(0, package_root)
+    try:
+        import quantization  # noqa: F401
+        if package_root == REF:
+            # the reference's utils/__init__ drags in datasets / click glue: expose only what the
+            # model files use
+            u = types.ModuleType('utils')
+            u.__path__ = [os.path.join(REF, 'utils')]
+            sys.modules['utils'] = u
+            tb = load_by_path('utils.tb_utils', os.path.join(REF, 'utils', 'tb_utils.py'))
+            pe = load_by_path('utils.per_embd_quant_utils', os.path.join(REF, 'utils', 'per_embd_quant_utils.py'))
+            for n in ('_tb_advance_global_step', '_tb_advance_token_counters', '_tb_hist'):
+                setattr(u, n, getattr(tb, n))
+            for n in ('set_act_quant_axis_and_groups', 'hijack_act_quant', 'hijack_weight_quant',
+                      'hijack_act_quant_modules'):
+                setattr(u, n, getattr(pe, n))
+        else:
+            import utils  # noqa: F401
+        m = types.ModuleType('models')
+        m.__path__ = [os.path.join(REF, 'models')]
+        sys.modules['models'] = m
+        qb = load_by_path('models.quantized_bert', os.path.join(REF, 'models', 'quantized_bert.py'))
+    finally:
+        sys.path.remove(package_root)
+    return qb
+
+
+CONFIGS = {
+    # name: (weight method, act method, n_bits, n_bits_act, act estimator, quant_dict-style PEG spec)
+    'w8a8_asym': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
+                      act_range_method='running_minmax', peg=None),
+    'w8a8_sym': dict(method='symmetric_uniform', act_method='symmetric_uniform', n_bits=8, n_bits_act=8,
+                     act_range_method='running_minmax', peg=None),
+    'w4a8_asym': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=4, n_bits_act=8,
+                      act_range_method='running_minmax', peg=None),
+    'w8a8_peg4': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
+                      act_range_method='running_minmax', peg=('ng', 4)),
+    'w8a8_pegp4': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
+                       act_range_method='current_minmax', peg=('ngp', 4)),
+    'w8a8_mse': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
+                     act_range_method='MSE', peg=None),
+}
+
+
+def peg_sites(model):
+    """the sites main.py:378-434 switches to per-embedding(-group) quantization"""
+    E = model.bert.embeddings
+    sites = [E.sum_input_token_type_embd_act_quantizer, E.sum_pos_embd_act_quantizer, E.LayerNorm]
+    for L in model.bert.encoder.layer:
+        A, S, O = L.attention.self, L.attention.output, L.output
+        sites += [A.query, A.key, A.value, A.context_act_quantizer, S.dense, S.res_act_quantizer,
+                  S.LayerNorm, O.dense, O.res_act_quantizer, O.LayerNorm]
+    return sites
+
+
+def run_config(qb, name, cfg, hf_model, batches):
+    """quantize -> (FP32 ranges pass) -> calibrate on batches[:-1] -> fix -> eval batches[-1]"""
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators, RangeEstimatorBase
+    from utils import set_act_quant_axis_and_groups
+
+    qparams = dict(method=QMethods[cfg['method']], act_method=QMethods[cfg['act_method']],
+                   n_bits=cfg['n_bits'], n_bits_act=cfg['n_bits_act'], per_channel_weights=False,
+                   percentile=None, quant_setup='all',
+                   weight_range_method=RangeEstimators.current_minmax, weight_range_options={},
+                   act_range_method=RangeEstimators[cfg['act_range_method']], act_range_options={},
+                   quant_dict={})
+    model = qb.QuantizedBertForSequenceClassification(hf_model, **qparams)
+    model.eval()
+    model.set_quant_state(weight_quant=True, act_quant=True)
+    if cfg['peg']:
+        kind, k = cfg['peg']
+        for s in peg_sites(model):
+            set_act_quant_axis_and_groups(s, axis=2, n_groups=k, permute=(kind == 'ngp'))
+        if kind == 'ngp':           # main.py:519-537: FP32 pass to collect per-dim ranges
+            model.full_precision()
+            for b in batches[:-1]:
+                model(input_ids=b, attention_mask=torch.ones_like(b))
+            model.set_quant_state(weight_quant=True, act_quant=True)
+            for m in model.modules():
+                if isinstance(m, RangeEstimatorBase):
+                    m.per_group_range_estimation = False
+    with torch.no_grad():
+        for b in batches[:-1]:
+            model(input_ids=b, attention_mask=torch.ones_like(b))
+        model.fix_ranges()
+        out = model(input_ids=batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+        hidden = model.bert(batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+    res = {f'{name}.logits': out.logits.numpy().copy(),
+           f'{name}.last_hidden': hidden.last_hidden_state.numpy().copy(),
+           f'{name}.pooled': hidden.pooler_output.numpy().copy()}
+    i = 0
+    for mname, m in model.named_modules():
+        q = getattr(m, 'quantizer', None)
+        if q is not None and mname.endswith('activation_quantizer') and q.is_initialized:
+            res[f'{name}.q{i}.delta'] = q._delta.detach().numpy().reshape(-1).copy()
+            if getattr(q, '_zero_float', None) is not None:
+                res[f'{name}.q{i}.zero_float'] = q._zero_float.detach().numpy().reshape(-1).copy()
+            res[f'{name}.q{i}.name'] = np.array(mname)
+            i += 1
+    res[f'{name}.n_act_quantizers'] = np.array(i)
+    return res, model
+
+
+def make_hf_model():
+    import hf41_shim
+    cfg = hf41_shim.TinyBertConfig()
+    m = hf41_shim.BertForSequenceClassification(cfg)
+    hf41_shim.init_weights(m, seed=0)
+    hf41_shim.perturb(m, seed=1)
+    m.eval()
+    return m
+
+
+def make_batches(n=3, B=4, T=32, vocab=1000):
+    g = torch.Generator().manual_seed(1234)
+    return [torch.randint(0, vocab, (B, T), generator=g) for _ in range(n)]
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    qb = import_reference_model(REF)
+    hf = make_hf_model()
+    batches = make_batches()
+    out = {'ids': np.stack([b.numpy() for b in batches])}
+    for k, v in hf.state_dict().items():
+        out['w.' + k] = v.numpy().copy()
+    for name, cfg in CONFIGS.items():
+        res, _ = run_config(qb, name, cfg, hf, batches)
+        out.update(res)
+        print(name, 'logits', res[f'{name}.logits'][0], 'act quantizers', int(res[f'{name}.n_act_quantizers']))
+    np.savez_compressed(os.path.join(HERE, 'bert_tiny.npz'), **out)
+    print('bert_tiny.npz', os.path.getsize(os.path.join(HERE, 'bert_tiny.npz')))

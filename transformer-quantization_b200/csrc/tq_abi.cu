@@ -1,7 +1,69 @@
 // Library-info entry points of the C ABI (include/tq_b200.h).
 #include "tq_common.cuh"
 
+namespace tq {
+
+__device__ __forceinline__ uint64_t splitmix(uint64_t& st) {
+    uint64_t z = (st += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// reference formulation with the division instruction and rintf (what tq::quant_int must equal)
+__device__ __forceinline__ float quant_int_ref(float x, float s, float zp, float lo, float hi) {
+    float q = __fadd_rn(rintf(__fdiv_rn(x, s)), zp);
+    q = q < lo ? lo : q;
+    q = q > hi ? hi : q;
+    return q;
+}
+
+// Brute-force check of the division-free quotient (tq::div_rn) and of tq::quant_int against the
+// IEEE division instruction on adversarial inputs: x near (k + 1/2) * s ties, random x, random s.
+__global__ void selftest_div_kernel(uint64_t seed, int iters, unsigned long long* out) {
+    uint64_t st = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1B54A32D192ED03ULL);
+    unsigned long long bad_div = 0, bad_q = 0;
+    for (int it = 0; it < iters; ++it) {
+        const uint64_t r0 = splitmix(st), r1 = splitmix(st);
+        // scale: random significand, exponent so that s in ~[1e-8, 1e4]
+        const uint32_t sexp = 100u + (uint32_t)(r0 % 41u);
+        const float s = __uint_as_float((sexp << 23) | (uint32_t)((r0 >> 16) & 0x7fffffu));
+        const int n_bits = 2 + (int)((r0 >> 40) % 15u);
+        const float hi = (float)(1u << n_bits) - 1.0f;
+        const float zp = (float)((r0 >> 48) % (uint32_t)(hi + 1.0f));
+        const QP p = make_qp(s, zp, 0.0f, hi);
+        float x;
+        const uint32_t mode = (uint32_t)(r1 & 3u);
+        if (mode == 0) {                          // fully random finite float
+            uint32_t b = (uint32_t)(r1 >> 32);
+            if (((b >> 23) & 0xffu) == 0xffu) b &= ~(1u << 30);
+            x = __uint_as_float(b);
+        } else {                                  // near a rounding tie of the integer grid
+            const int k = (int)((r1 >> 8) % 140001u) - 70000;
+            const float frac = mode == 1 ? 0.5f : (mode == 2 ? 0.0f : 0.25f + 0.5f * (float)((r1 >> 40) & 1u));
+            x = __fmul_rn((float)k + frac, s);
+            const int ulps = (int)((r1 >> 44) % 9u) - 4;
+            x = __uint_as_float(__float_as_uint(x) + (uint32_t)ulps);
+        }
+        const float a = div_rn(x, p), b = __fdiv_rn(x, s);
+        if (fabsf(b) < 4194304.0f && __float_as_uint(a) != __float_as_uint(b) && !(a == 0.0f && b == 0.0f)) ++bad_div;
+        const float qa = quant_int(x, p), qb = quant_int_ref(x, s, zp, 0.0f, hi);
+        if (!(qa == qb) && !(qa != qa && qb != qb)) ++bad_q;
+    }
+    if (bad_div) atomicAdd(out, bad_div);
+    if (bad_q) atomicAdd(out + 1, bad_q);
+}
+
+}  // namespace tq
+
 extern "C" {
+
+int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mismatches, void* stream) {
+    if (mismatches == nullptr || blocks < 1 || iters < 1) return TQ_EINVAL;
+    tq::selftest_div_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(seed, iters,
+                                                                     (unsigned long long*)mismatches);
+    return tq::launch_status();
+}
 
 int tq_version(void) { return 1; }
 

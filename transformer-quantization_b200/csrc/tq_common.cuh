@@ -14,6 +14,8 @@ namespace tq {
 // ---- resolved quantizer parameters ----------------------------------------------------------
 struct QP {
     float scale, zp, lo, hi;
+    float rcp;     // RN(1 / scale)
+    int exact;     // 1: use the IEEE division instruction (see div_rn)
 };
 
 // integer grid of the quantizer (quantizers.py:131-140, 321-328)
@@ -28,27 +30,66 @@ __device__ __forceinline__ void grid_of(const tq_qspec& q, float& lo, float& hi)
     }
 }
 
+__device__ __forceinline__ QP make_qp(float scale, float zp, float lo, float hi) {
+    QP p;
+    p.scale = scale;
+    p.zp = zp;
+    p.lo = lo;
+    p.hi = hi;
+    p.rcp = __frcp_rn(scale);
+    // Markstein's correction (div_rn) is proven for a correctly rounded reciprocal of a NORMAL
+    // divisor whose significand is not all ones; anything else takes the division instruction.
+    const uint32_t b = __float_as_uint(scale);
+    const uint32_t ex = (b >> 23) & 0xffu;
+    p.exact = ((b & 0x7fffffu) == 0x7fffffu) || ex == 0u || ex >= 0xfeu || ex <= 2u ? 1 : 0;
+    return p;
+}
+
 // scale / zero_point of parameter slot i (quantizers.py:142-153, 330-332)
 __device__ __forceinline__ QP resolve(const tq_qspec& q, int64_t i, float lo, float hi) {
-    QP p;
     const float d = __ldg(q.delta + i);
-    p.scale = q.log_domain ? expf(d) : (d < q.eps ? q.eps : d);   // torch.clamp(min=eps) keeps NaN
+    const float scale = q.log_domain ? expf(d) : (d < q.eps ? q.eps : d);   // torch.clamp(min=eps) keeps NaN
+    float zp = 0.0f;
     if (q.zero_float != nullptr) {
         float z = rintf(__ldg(q.zero_float + i));
         z = z < lo ? lo : z;
         z = z > hi ? hi : z;
-        p.zp = z;
-    } else {
-        p.zp = 0.0f;
+        zp = z;
     }
-    p.lo = lo;
-    p.hi = hi;
-    return p;
+    return make_qp(scale, zp, lo, hi);
+}
+
+// RN(x / s) without the division instruction.  The reference computes round(x / scale) with a true
+// IEEE division (quantizers.py:184) and the integer must be bit-exact, so a reciprocal multiply is
+// not enough: q0 = RN(x*r) can be 2 ulp off.  Two FMA residual corrections with r = RN(1/s)
+// (Markstein 1990; Muller et al., Handbook of FP Arithmetic, thm. on division by FMA iterations):
+//   q1 = RN(q0 + (x - q0*s)*r) is a faithful quotient, q2 = RN(q1 + (x - q1*s)*r) == RN(x/s).
+// The residuals are exact (FMA).  Outside |q| < 2^22 (or NaN/inf) q0 is returned: those values are
+// clamped to the grid edge (<= 2^16) no matter how they round, and inf - inf must not appear.
+// Verified bit-for-bit against __fdiv_rn on the GPU by tq_selftest_div (tests/test_gpu_parity.py).
+// This keeps the XU pipe (MUFU.RCP, 16 lanes/SM) out of the per-element path.
+__device__ __forceinline__ float div_rn(float x, const QP& p) {
+    if (p.exact) return __fdiv_rn(x, p.scale);
+    const float q0 = __fmul_rn(x, p.rcp);
+    const float e0 = __fmaf_rn(-q0, p.scale, x);
+    const float q1 = __fmaf_rn(e0, p.rcp, q0);
+    const float e1 = __fmaf_rn(-q1, p.scale, x);
+    const float q2 = __fmaf_rn(e1, p.rcp, q1);
+    return fabsf(q0) < 4194304.0f ? q2 : q0;
+}
+
+// round-half-to-even == torch.round for |v| < 2^22 via the 1.5 * 2^23 constant (two FADDs on the
+// FMA pipe instead of FRND on the XU pipe); larger |v|, inf and NaN pass through to the clamp.
+__device__ __forceinline__ float rint_even(float v) {
+    return __fsub_rn(__fadd_rn(v, 12582912.0f), 12582912.0f);
 }
 
 // clamp(rint(x / scale) + zp, lo, hi)  -- quantizers.py:184-185.  NaN propagates (torch.clamp).
 __device__ __forceinline__ float quant_int(float x, const QP& p) {
-    float q = __fadd_rn(rintf(__fdiv_rn(x, p.scale)), p.zp);
+    const float d = div_rn(x, p);
+    // |d| >= 2^22: rint_even would return a non-integer for 2^22 <= |d| < 2^23 -- irrelevant, the
+    // clamp maps all of them to the grid edge
+    float q = __fadd_rn(rint_even(d), p.zp);
     q = q < p.lo ? p.lo : q;
     q = q > p.hi ? p.hi : q;
     return q;

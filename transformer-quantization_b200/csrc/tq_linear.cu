@@ -8,7 +8,7 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4-6 stage smem ring
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32
 //                              accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2-5   epilogue       tcgen05.ld 32x32b.x32 -> acc * (s_a * s_w[n]) + bias[n] -> act_fn
+//   warps 2-9   epilogue       tcgen05.ld 32x32b.x32 -> acc * (s_a * s_w[n]) + bias[n] -> act_fn
 //                              -> per-tensor or per-column (PEG / fused-QKV) QDQ -> fp32 and/or
 //                              bf16 centred-integer output (operand format of the next GEMM)
 //
@@ -25,8 +25,8 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 B: one SWIZZLE_128B span
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;   // 6 warps: TMA, MMA, 4 x epilogue
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;   // 10 warps: TMA, MMA, 8 x epilogue (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 
 template <int BN>
@@ -35,7 +35,7 @@ struct Cfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN > 192) ? 4 : (BN > 128 ? 5 : 6);
-    static constexpr int kParamBytes = 4 * BN * 4;                  // colscale | bias | qscale | qzp
+    static constexpr int kParamBytes = 5 * BN * 4;                  // colscale | bias | qscale | qzp | qrcp
     static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kBarBytes + 1024;  // + align slack
 };
@@ -179,7 +179,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
-                mbar_init(tempty_bar(s), 4);      // one arrival per epilogue warp
+                mbar_init(tempty_bar(s), 8);      // one arrival per epilogue warp
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -242,13 +242,15 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int et = threadIdx.x - 64;                       // 0..127
+        // ===================== epilogue (warps 2..9) =====================
+        const int et = threadIdx.x - 64;                       // 0..255
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                      // which half of the 32-column chunks
         float* colscale = params;
         float* cbias = params + BN;
         float* qscale = params + 2 * BN;
         float* qzp = params + 3 * BN;
+        float* qrcp = params + 4 * BN;
         const bool has_q = ep.out_q.delta != nullptr;
         float qlo = 0.0f, qhi = 0.0f;
         if (has_q) grid_of(ep.out_q, qlo, qhi);
@@ -265,10 +267,11 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         float run_min = __int_as_float(0x7f800000), run_max = __int_as_float(0xff800000);
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's parameter reads done
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's parameter reads done
+            int need_exact = 0;
             for (int j = et; j < BN; j += kEpiThreads) {
                 const int64_t n = n0 + j;
-                float cs = 0.0f, b = 0.0f, qs = 1.0f, qz = 0.0f;
+                float cs = 0.0f, b = 0.0f, qs = 1.0f, qz = 0.0f, qr = 1.0f;
                 if (n < N) {
                     const float ws = ep.w_q.delta != nullptr
                                          ? resolve(ep.w_q, ep.w_q_params > 1 ? n : 0, wlo, whi).scale
@@ -279,20 +282,32 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const QP p = resolve(ep.out_q, ep.out_q_params > 1 ? n : 0, qlo, qhi);
                         qs = p.scale;
                         qz = p.zp;
+                        qr = p.rcp;
+                        need_exact |= p.exact;
                     }
                 }
                 colscale[j] = cs;
                 cbias[j] = b;
                 qscale[j] = qs;
                 qzp[j] = qz;
+                qrcp[j] = qr;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // barrier + OR-reduction over the 256 epilogue threads (named barrier 1)
+            int exact;
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t"
+                "setp.ne.b32 p, %1, 0;\n\t"
+                "bar.red.or.pred q, 1, 256, p;\n\t"
+                "selp.u32 %0, 1, 0, q;\n\t}"
+                : "=r"(exact)
+                : "r"(need_exact)
+                : "memory");
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int64_t row = m0 + quarter * 32 + lane;
             const bool row_ok = row < M;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
                 float o[32];
@@ -314,7 +329,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (has_q) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const QP p{qscale[c0 + j], qzp[c0 + j], qlo, qhi};
+                        const QP p{qscale[c0 + j], qzp[c0 + j], qlo, qhi, qrcp[c0 + j], exact};
                         const float qi = quant_int(o[j], p);
                         v[j] = __float_as_uint(__fsub_rn(qi, p.zp));      // centred integer
                         o[j] = __fmul_rn(p.scale, __uint_as_float(v[j]));  // scale * (x_int - zp)

@@ -23,8 +23,8 @@ mse_sse_kernel(const float* __restrict__ x, int64_t n, int64_t per_cta, int vec_
                const float* __restrict__ cand, int32_t n_cand, double* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                                   // [kSliceMax]
-    float4* ctab = reinterpret_cast<float4*>(smem_raw + (size_t)kSliceMax * 4);          // [kCandChunk]
-    double* wpart = reinterpret_cast<double*>(smem_raw + (size_t)kSliceMax * 4 + kCandChunk * 16);  // [16][kCandChunk]
+    QP* ctab = reinterpret_cast<QP*>(smem_raw + (size_t)kSliceMax * 4);                   // [kCandChunk]
+    double* wpart = reinterpret_cast<double*>(smem_raw + (size_t)kSliceMax * 4 + kCandChunk * sizeof(QP));  // [16][kCandChunk]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t begin = (int64_t)blockIdx.x * per_cta;
@@ -54,12 +54,11 @@ mse_sse_kernel(const float* __restrict__ x, int64_t n, int64_t per_cta, int vec_
         for (int c0 = 0; c0 < n_cand; c0 += kCandChunk) {
             const int cn = (n_cand - c0) < kCandChunk ? (n_cand - c0) : kCandChunk;
             if (tid < cn)
-                ctab[tid] = make_float4(cand[c0 + tid], cand[n_cand + c0 + tid],
-                                        cand[2 * n_cand + c0 + tid], cand[3 * n_cand + c0 + tid]);
+                ctab[tid] = make_qp(cand[c0 + tid], cand[n_cand + c0 + tid], cand[2 * n_cand + c0 + tid],
+                                    cand[3 * n_cand + c0 + tid]);
             __syncthreads();
             for (int c = 0; c < cn; ++c) {
-                const float4 t = ctab[c];
-                const QP p{t.x, t.y, t.z, t.w};
+                const QP p = ctab[c];
                 float acc0 = 0.0f, acc1 = 0.0f;
                 int i = tid;
                 for (; i + kMThreads < nv; i += 2 * kMThreads) {
@@ -157,7 +156,7 @@ mse_argmin_kernel(const double* __restrict__ loss, int32_t n, const float* __res
 }
 
 static size_t mse_smem_bytes() {
-    return (size_t)kSliceMax * 4 + (size_t)kCandChunk * 16 + (size_t)(kMThreads / 32) * kCandChunk * 8;
+    return (size_t)kSliceMax * 4 + (size_t)kCandChunk * sizeof(QP) + (size_t)(kMThreads / 32) * kCandChunk * 8;
 }
 
 }  // namespace tq

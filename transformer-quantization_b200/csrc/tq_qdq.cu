@@ -120,15 +120,18 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, 4)
 qdq_cols_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yint,
                     __nv_bfloat16* __restrict__ yctr, int64_t nvec, int32_t C, tq_qspec q) {
-    extern __shared__ __align__(16) float tab[];   // [C] scale | [C] zero_point, indexed by hidden dim
+    extern __shared__ __align__(16) float tab[];   // [C] scale | [C] zero_point | [C] 1/scale, by hidden dim
     float lo, hi;
     grid_of(q, lo, hi);
+    int need_exact = 0;
     for (int c = threadIdx.x; c < C; c += kThreads) {
         const QP p = resolve(q, c, lo, hi);
         tab[c] = p.scale;
         tab[C + c] = p.zp;
+        tab[2 * C + c] = p.rcp;
+        need_exact |= p.exact;
     }
-    __syncthreads();
+    const int exact = __syncthreads_or(need_exact);   // rare: any column needing the IEEE divide
     const int32_t CV = C >> 2;
     const float4* xv = reinterpret_cast<const float4*>(x);
     float4* yv = reinterpret_cast<float4*>(y);
@@ -136,6 +139,7 @@ qdq_cols_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
     uint2* ycv = reinterpret_cast<uint2*>(yctr);
     const float4* sv = reinterpret_cast<const float4*>(tab);
     const float4* zv = reinterpret_cast<const float4*>(tab + C);
+    const float4* rv = reinterpret_cast<const float4*>(tab + 2 * C);
 
     const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
     int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x;
@@ -160,8 +164,9 @@ qdq_cols_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
                 cv -= (cv >= CV) ? CV : 0;
                 const float4 s = sv[cv];
                 const float4 z = zv[cv];
-                const QP p0{s.x, z.x, lo, hi}, p1{s.y, z.y, lo, hi}, p2{s.z, z.z, lo, hi},
-                    p3{s.w, z.w, lo, hi};
+                const float4 r = rv[cv];
+                const QP p0{s.x, z.x, lo, hi, r.x, exact}, p1{s.y, z.y, lo, hi, r.y, exact},
+                    p2{s.z, z.z, lo, hi, r.z, exact}, p3{s.w, z.w, lo, hi, r.w, exact};
                 emit_vec<MODE>(v[u], p0, p1, p2, p3, yv, yiv, ycv, idx);
             }
         }
@@ -219,8 +224,8 @@ static int launch_any(const float* x, float* y, float* yint, __nv_bfloat16* yctr
         }
         return launch_status();
     }
-    if (inner == 1 && al && (C & 3) == 0 && C * 8 <= 200 * 1024) {
-        const size_t smem = (size_t)C * 8;
+    if (inner == 1 && al && (C & 3) == 0 && C * 12 <= 200 * 1024) {
+        const size_t smem = (size_t)C * 12;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(qdq_cols_vec_kernel<MODE>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,

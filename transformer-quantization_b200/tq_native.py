@@ -45,6 +45,7 @@ SIGNATURES = {
     'tq_version': (ctypes.c_int, []),
     'tq_error_string': (ctypes.c_char_p, [ctypes.c_int]),
     'tq_device_sm_count': (ctypes.c_int, []),
+    'tq_selftest_div': (ctypes.c_int, [ctypes.c_uint64, _i32, _i32, ctypes.c_void_p, ctypes.c_void_p]),
     'tq_qdq_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, QSpec, ctypes.c_void_p]),
     'tq_qdq_axis_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i64, _i64, QSpec, ctypes.c_void_p]),
     'tq_quant_int_f32': (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_void_p, _i64, _i64, _i64, QSpec,
@@ -114,11 +115,27 @@ class CudaOps:
         self.lib = lib or load_library()
         self._ws = {}
         self._lock = threading.Lock()
+        self.launches = 0            # kernels of this library enqueued so far (bench.py: gpu_launches)
+        self.profile = None          # list -> every call appends (name, work, start_event, end_event)
 
     # -- helpers --------------------------------------------------------------------------------
     def _check(self, code):
         if code != 0:
             raise TQError(f'tq_b200 call failed ({code}): {self.lib.tq_error_string(code).decode()}')
+
+    def _run(self, name, work, kernels, fn, *args):
+        """Call one C entry point.  ``work`` = algorithmic bytes (or flops) of the call, ``kernels``
+        = how many kernels it enqueues.  With ``self.profile`` set, CUDA events bracket the call on
+        the launching stream (used by bench.py's roofline pass; never during graph capture)."""
+        if self.profile is None:
+            self._check(fn(*args))
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._check(fn(*args))
+            e1.record()
+            self.profile.append((name, work, e0, e1))
+        self.launches += kernels
 
     def workspace(self, kind, nbytes, device):
         """Zero-initialised scratch, cached per (kind, device, stream) and grown on demand."""
@@ -146,9 +163,10 @@ class CudaOps:
         if n == 0:
             return y
         if C == 1:
-            self._check(self.lib.tq_qdq_f32(x.data_ptr(), y.data_ptr(), n, spec, _stream()))
+            self._run('qdq_tensor', 8 * n, 1, self.lib.tq_qdq_f32, x.data_ptr(), y.data_ptr(), n, spec, _stream())
         else:
-            self._check(self.lib.tq_qdq_axis_f32(x.data_ptr(), y.data_ptr(), outer, C, inner, spec, _stream()))
+            self._run('qdq_axis', 8 * n, 1, self.lib.tq_qdq_axis_f32, x.data_ptr(), y.data_ptr(), outer, C, inner, spec,
+                      _stream())
         return y
 
     def quant_int(self, x, spec, outer=1, C=1, inner=None, want_f32=True, want_bf16=False):
@@ -161,7 +179,8 @@ class CudaOps:
             return yi, yc
         if C == 1:
             outer, inner = 1, n
-        self._check(self.lib.tq_quant_int_f32(x.data_ptr(), _ptr(yi), _ptr(yc), outer, C, inner, spec, _stream()))
+        self._run('quant_int', (4 + (4 if want_f32 else 0) + (2 if want_bf16 else 0)) * n, 1, self.lib.tq_quant_int_f32,
+                  x.data_ptr(), _ptr(yi), _ptr(yc), outer, C, inner, spec, _stream())
         return yi, yc
 
     # -- min / max ------------------------------------------------------------------------------
@@ -174,7 +193,8 @@ class CudaOps:
         out = torch.empty(2, dtype=torch.float32, device=x.device)
         nb = self.lib.tq_minmax_workspace_bytes(1)
         ws = self.workspace('mm', nb, x.device)
-        self._check(self.lib.tq_minmax_f32(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        self._run('minmax_tensor', 4 * x.numel(), 1, self.lib.tq_minmax_f32, x.data_ptr(), x.numel(), out.data_ptr(),
+                  ws.data_ptr(), ws.numel(), _stream())
         return out
 
     def minmax_axis(self, x, outer, C, inner):
@@ -184,45 +204,44 @@ class CudaOps:
         out = torch.empty(2, C, dtype=torch.float32, device=x.device)
         nb = self.lib.tq_minmax_workspace_bytes(C)
         ws = self.workspace('mm', nb, x.device)
-        self._check(self.lib.tq_minmax_axis_f32(x.data_ptr(), outer, C, inner, out[0].data_ptr(), out[1].data_ptr(),
-                                                ws.data_ptr(), ws.numel(), _stream()))
+        self._run('minmax_axis', 4 * x.numel(), 1, self.lib.tq_minmax_axis_f32, x.data_ptr(), outer, C, inner,
+                  out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
         return out[0], out[1]
 
     def group_minmax(self, mn, mx, n_groups, ranges=None):
         _chk_cuda(mn, mx, ranges)
         C = mn.numel()
         out = torch.empty(2, C, dtype=torch.float32, device=mn.device)
-        code = self.lib.tq_group_minmax_f32(mn.data_ptr(), mx.data_ptr(), C, int(n_groups), _ptr(ranges),
-                                            out[0].data_ptr(), out[1].data_ptr(), _stream())
-        self._check(code)
+        self._run('group_minmax', 16 * C, 1, self.lib.tq_group_minmax_f32, mn.data_ptr(), mx.data_ptr(), C,
+                  int(n_groups), _ptr(ranges), out[0].data_ptr(), out[1].data_ptr(), _stream())
         return out[0], out[1]
 
     def dim_ranges(self, mn, mx, first):
         _chk_cuda(mn, mx)
         r = torch.empty_like(mn)
-        self._check(self.lib.tq_dim_ranges_f32(mn.data_ptr(), mx.data_ptr(), mn.numel(), int(bool(first)),
-                                               r.data_ptr(), _stream()))
+        self._run('dim_ranges', 12 * mn.numel(), 1, self.lib.tq_dim_ranges_f32, mn.data_ptr(), mx.data_ptr(),
+                  mn.numel(), int(bool(first)), r.data_ptr(), _stream())
         return r
 
     def range_update(self, new_min, new_max, cur_min, cur_max, mode, momentum=0.0, first=False):
         """In-place update of (cur_min, cur_max); mode 0 current, 1 running EMA, 2 all-minmax."""
         _chk_cuda(new_min, new_max, cur_min, cur_max)
-        self._check(self.lib.tq_range_update_f32(new_min.data_ptr(), new_max.data_ptr(), cur_min.data_ptr(),
-                                                 cur_max.data_ptr(), new_min.numel(), mode, float(momentum),
-                                                 int(bool(first)), _stream()))
+        self._run('range_update', 16 * new_min.numel(), 1, self.lib.tq_range_update_f32, new_min.data_ptr(),
+                  new_max.data_ptr(), cur_min.data_ptr(), cur_max.data_ptr(), new_min.numel(), mode,
+                  float(momentum), int(bool(first)), _stream())
 
     # -- set_quant_range ------------------------------------------------------------------------
     def set_range_asym(self, x_min, x_max, n_bits, eps, log_domain, delta, zero_float):
         _chk_cuda(x_min, x_max, delta, zero_float)
-        self._check(self.lib.tq_set_range_asym_f32(x_min.data_ptr(), x_max.data_ptr(), x_min.numel(), int(n_bits),
-                                                   float(eps), int(bool(log_domain)), delta.data_ptr(),
-                                                   zero_float.data_ptr(), _stream()))
+        self._run('set_range', 16 * x_min.numel(), 1, self.lib.tq_set_range_asym_f32, x_min.data_ptr(),
+                  x_max.data_ptr(), x_min.numel(), int(n_bits), float(eps), int(bool(log_domain)),
+                  delta.data_ptr(), zero_float.data_ptr(), _stream())
 
     def set_range_sym(self, x_min, x_max, n_bits, eps, log_domain, delta, is_signed):
         _chk_cuda(x_min, x_max, delta, is_signed)
-        self._check(self.lib.tq_set_range_sym_f32(x_min.data_ptr(), x_max.data_ptr(), x_min.numel(), int(n_bits),
-                                                  float(eps), int(bool(log_domain)), delta.data_ptr(),
-                                                  is_signed.data_ptr(), _stream()))
+        self._run('set_range', 12 * x_min.numel(), 1, self.lib.tq_set_range_sym_f32, x_min.data_ptr(),
+                  x_max.data_ptr(), x_min.numel(), int(n_bits), float(eps), int(bool(log_domain)),
+                  delta.data_ptr(), is_signed.data_ptr(), _stream())
 
     # -- MSE ------------------------------------------------------------------------------------
     def mse_sse(self, x, cand, n_cand, loss_accum):
@@ -231,17 +250,17 @@ class CudaOps:
         x = x.contiguous()
         nb = self.lib.tq_mse_workspace_bytes(n_cand)
         ws = self.workspace('mse', nb, x.device)
-        self._check(self.lib.tq_mse_sse_f32(x.data_ptr(), x.numel(), cand.data_ptr(), n_cand,
-                                            loss_accum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        self._run('mse_sse', 4 * x.numel(), 2, self.lib.tq_mse_sse_f32, x.data_ptr(), x.numel(), cand.data_ptr(),
+                  n_cand, loss_accum.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
 
     def mse_argmin(self, loss, cand_xmin, cand_xmax):
         """-> (xmin[1], xmax[1], idx[1]) device tensors; first minimum of the flat loss array."""
         _chk_cuda(loss, cand_xmin, cand_xmax)
         out = torch.empty(2, dtype=torch.float32, device=loss.device)
         idx = torch.empty(1, dtype=torch.int32, device=loss.device)
-        self._check(self.lib.tq_mse_argmin_f64(loss.data_ptr(), loss.numel(), cand_xmin.data_ptr(),
-                                               cand_xmax.data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(),
-                                               idx.data_ptr(), _stream()))
+        self._run('mse_argmin', 8 * loss.numel(), 1, self.lib.tq_mse_argmin_f64, loss.data_ptr(), loss.numel(),
+                  cand_xmin.data_ptr(), cand_xmax.data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(),
+                  idx.data_ptr(), _stream())
         return out[0:1], out[1:2], idx
 
     # -- fused linear -----------------------------------------------------------------------------
@@ -249,7 +268,7 @@ class CudaOps:
         _chk_cuda(x2d)
         M, K = x2d.shape
         out = torch.empty(M, 3 * K, dtype=torch.bfloat16, device=x2d.device)
-        self._check(self.lib.tq_split3_bf16(x2d.data_ptr(), out.data_ptr(), M, K, _stream()))
+        self._run('split3', 10 * M * K, 1, self.lib.tq_split3_bf16, x2d.data_ptr(), out.data_ptr(), M, K, _stream())
         return out
 
     def linear(self, a_ctr, w_ctr, bias, M, N, K, k_split, a_spec, w_spec, w_params, act_fn,
@@ -260,12 +279,11 @@ class CudaOps:
         y = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
         yc = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if want_ctr else None
         null = QSpec(None, None, None, 8, 0, 1e-8)
-        code = self.lib.tq_linear_qdq_bf16(
-            a_ctr.data_ptr(), w_ctr.data_ptr(), _ptr(bias), _ptr(y), _ptr(yc), M, N, K, int(k_split),
-            a_spec if a_spec is not None else null, w_spec if w_spec is not None else null, int(w_params),
-            int(act_fn), out_spec if out_spec is not None else null, int(out_params), _ptr(tile_minmax),
-            None, 0, _stream())
-        self._check(code)
+        self._run('linear_qdq', 2 * M * N * K * int(k_split), 1, self.lib.tq_linear_qdq_bf16,
+                  a_ctr.data_ptr(), w_ctr.data_ptr(), _ptr(bias), _ptr(y), _ptr(yc), M, N, K, int(k_split),
+                  a_spec if a_spec is not None else null, w_spec if w_spec is not None else null, int(w_params),
+                  int(act_fn), out_spec if out_spec is not None else null, int(out_params), _ptr(tile_minmax),
+                  None, 0, _stream())
         return y, yc
 
 
