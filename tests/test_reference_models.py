@@ -1,0 +1,64 @@
+"""Drop-in check: the reference's own ``models/quantized_bert.py`` -- UNCHANGED, loaded from the
+reference checkout -- runs on top of THIS repo's ``quantization`` / ``utils`` packages and reproduces
+the golden outputs it produced on top of the reference's packages.
+
+Needs the reference checkout (build container only; skipped on the GPU box, where /root/reference
+does not exist).  Arithmetic back-end: the CPU oracle injected through the test fixture, the
+library ops (matmul, layer_norm, ...) are the same torch CPU calls in both runs, so the logits must
+be identical.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import tq_native
+from conftest import GOLDEN, PKG
+
+REF = os.environ.get('TQ_REFERENCE', '/root/reference')
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'models')),
+                                reason='reference checkout not present')
+
+
+def _gm():
+    spec = importlib.util.spec_from_file_location('make_golden_model', os.path.join(GOLDEN, 'make_golden_model.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture()
+def drop_in(monkeypatch):
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    saved = {k: v for k, v in sys.modules.items() if k.split('.')[0] in ('quantization', 'utils', 'models')}
+    gm = _gm()
+    qb = gm.import_reference_model(PKG)           # reference model file + THIS package
+    yield gm, qb
+    for k in [k for k in sys.modules if k.split('.')[0] in ('quantization', 'utils', 'models')]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+
+
+@pytest.mark.parametrize('name', ['w8a8_asym', 'w8a8_sym', 'w4a8_asym', 'w8a8_peg4', 'w8a8_pegp4'])
+def test_reference_model_file_runs_unchanged_on_this_package(drop_in, name):
+    gm, qb = drop_in
+    assert qb.__file__.startswith(REF)
+    import quantization
+    assert quantization.__file__.startswith(PKG)
+    G = np.load(os.path.join(GOLDEN, 'bert_tiny.npz'))
+    torch.set_grad_enabled(False)
+    try:
+        res, model = gm.run_config(qb, name, gm.CONFIGS[name], gm.make_hf_model(), gm.make_batches())
+    finally:
+        torch.set_grad_enabled(True)
+    assert np.array_equal(res[f'{name}.logits'], G[f'{name}.logits'])
+    assert np.array_equal(res[f'{name}.last_hidden'], G[f'{name}.last_hidden'])
+    n = int(G[f'{name}.n_act_quantizers'])
+    assert int(res[f'{name}.n_act_quantizers']) == n
+    for i in range(n):
+        assert np.array_equal(res[f'{name}.q{i}.delta'], G[f'{name}.q{i}.delta']), str(G[f'{name}.q{i}.name'])
