@@ -59,8 +59,10 @@ int         tq_device_sm_count(void);      /* SM count of the current device (14
 
 /* Device self-test of the division-free quotient used by every quantizing kernel (csrc/
  * tq_common.cuh, tq::div_rn): blocks*256*iters adversarial (x, scale) pairs are compared bit for
- * bit with the IEEE division instruction.  mismatches[0] += #quotient mismatches,
- * mismatches[1] += #integer-grid mismatches (device uint64[2], caller-zeroed). */
+ * bit with the IEEE division instruction.  mismatches[0] += #quotient mismatches with
+ * 2^-60 <= |x/s| < 2^22, mismatches[1] += #integer-grid mismatches (both must stay 0),
+ * mismatches[2] += #quotient mismatches below 2^-60 (residual underflow; they round to 0 either
+ * way).  Device uint64[3], caller-zeroed. */
 int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mismatches, void* stream);
 
 /* ---- quantize -> round -> clamp -> dequantize ------------------------------------------------

@@ -22,7 +22,7 @@ __device__ __forceinline__ float quant_int_ref(float x, float s, float zp, float
 // IEEE division instruction on adversarial inputs: x near (k + 1/2) * s ties, random x, random s.
 __global__ void selftest_div_kernel(uint64_t seed, int iters, unsigned long long* out) {
     uint64_t st = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1B54A32D192ED03ULL);
-    unsigned long long bad_div = 0, bad_q = 0;
+    unsigned long long bad_div = 0, bad_q = 0, bad_tiny = 0;
     for (int it = 0; it < iters; ++it) {
         const uint64_t r0 = splitmix(st), r1 = splitmix(st);
         // scale: random significand, exponent so that s in ~[1e-8, 1e4]
@@ -46,12 +46,17 @@ __global__ void selftest_div_kernel(uint64_t seed, int iters, unsigned long long
             x = __uint_as_float(__float_as_uint(x) + (uint32_t)ulps);
         }
         const float a = div_rn(x, p), b = __fdiv_rn(x, s);
-        if (fabsf(b) < 4194304.0f && __float_as_uint(a) != __float_as_uint(b) && !(a == 0.0f && b == 0.0f)) ++bad_div;
+        if (fabsf(b) < 4194304.0f && __float_as_uint(a) != __float_as_uint(b) && !(a == 0.0f && b == 0.0f)) {
+            // below 2^-60 the FMA residuals can underflow; such quotients round to integer 0 anyway
+            if (fabsf(b) >= 8.67361737988e-19f) ++bad_div;
+            else ++bad_tiny;
+        }
         const float qa = quant_int(x, p), qb = quant_int_ref(x, s, zp, 0.0f, hi);
         if (!(qa == qb) && !(qa != qa && qb != qb)) ++bad_q;
     }
     if (bad_div) atomicAdd(out, bad_div);
     if (bad_q) atomicAdd(out + 1, bad_q);
+    if (bad_tiny) atomicAdd(out + 2, bad_tiny);
 }
 
 }  // namespace tq

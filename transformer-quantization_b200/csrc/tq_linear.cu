@@ -34,10 +34,11 @@ struct Cfg {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN > 192) ? 4 : (BN > 128 ? 5 : 6);
+    static constexpr int kStages = (BN > 192) ? 3 : (BN > 128 ? 4 : (BN > 64 ? 5 : 6));
     static constexpr int kParamBytes = 5 * BN * 4;                  // colscale | bias | qscale | qzp | qrcp
+    static constexpr int kStoreBytes = 8 * 4096;                    // per-epilogue-warp 32x32 fp32 transpose tile
     static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kBarBytes + 1024;  // + align slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kParamBytes + kBarBytes + 1024;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -151,15 +152,16 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;       // SWIZZLE_128B: 1024 B alignment
     unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
-    float* params = reinterpret_cast<float*>(base_ptr + C::kStages * C::kStageBytes);
-    const uint32_t bar0 = base + C::kStages * C::kStageBytes + C::kParamBytes;
+    unsigned char* store_stage = base_ptr + C::kStages * C::kStageBytes;
+    float* params = reinterpret_cast<float*>(store_stage + C::kStoreBytes);
+    const uint32_t bar0 = base + C::kStages * C::kStageBytes + C::kStoreBytes + C::kParamBytes;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (C::kStages + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 2 + s); };
     const uint32_t tmem_slot = bar0 + 8u * (2 * C::kStages + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-        base_ptr + C::kStages * C::kStageBytes + C::kParamBytes + 8 * (2 * C::kStages + 4));
+        base_ptr + C::kStages * C::kStageBytes + C::kStoreBytes + C::kParamBytes + 8 * (2 * C::kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
@@ -335,43 +337,52 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         o[j] = __fmul_rn(p.scale, __uint_as_float(v[j]));  // scale * (x_int - zp)
                     }
                 }
-                if (row_ok) {
-                    const int64_t col = n0 + c0;
-                    if (col + 32 <= N && (N & 3) == 0) {
-                        if (ep.y != nullptr) {
-                            float4* dst = reinterpret_cast<float4*>(ep.y + row * N + col);
+                // ---- coalesced stores: 32x32 transpose through this warp's private smem tile ----
+                // registers hold one ROW per lane; a direct store would touch 32 different 128 B lines
+                // per instruction.  Swizzled 16-byte chunks keep both smem phases conflict free.
+                {
+                    float4* stg = reinterpret_cast<float4*>(store_stage + (warp - 2) * 4096);
+                    const int64_t grow0 = m0 + quarter * 32;
+                    const int64_t gcol0 = n0 + c0;
+                    if (ep.y != nullptr) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                        }
-                        if (ep.y_ctr != nullptr && (N & 7) == 0) {
-                            uint4* dst = reinterpret_cast<uint4*>(ep.y_ctr + row * N + col);
+                        for (int c = 0; c < 8; ++c)
+                            stg[lane * 8 + (c ^ (lane & 7))] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                        __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 w;
-                                __nv_bfloat162 h;
-                                h = __floats2bfloat162_rn(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
-                                w.x = *reinterpret_cast<uint32_t*>(&h);
-                                h = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                                w.y = *reinterpret_cast<uint32_t*>(&h);
-                                h = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                                w.z = *reinterpret_cast<uint32_t*>(&h);
-                                h = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                                w.w = *reinterpret_cast<uint32_t*>(&h);
-                                dst[j] = w;
-                            }
-                        } else if (ep.y_ctr != nullptr) {
-                            for (int j = 0; j < 32; ++j)
-                                ep.y_ctr[row * N + col + j] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + (lane >> 3), ch = lane & 7;
+                            const float4 val = stg[r * 8 + (ch ^ (r & 7))];
+                            const int64_t grow = grow0 + r, gcol = gcol0 + ch * 4;
+                            if (grow < M && gcol < N) *reinterpret_cast<float4*>(ep.y + grow * N + gcol) = val;
                         }
-                    } else {
-                        for (int j = 0; j < 32; ++j) {
-                            if (col + j < N) {
-                                if (ep.y != nullptr) ep.y[row * N + col + j] = o[j];
-                                if (ep.y_ctr != nullptr)
-                                    ep.y_ctr[row * N + col + j] = __float2bfloat16_rn(__uint_as_float(v[j]));
-                            }
+                        __syncwarp();
+                    }
+                    if (ep.y_ctr != nullptr) {
+                        uint4* s2 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint4 w;
+                            __nv_bfloat162 h;
+                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1]));
+                            w.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+                            w.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+                            w.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+                            w.w = *reinterpret_cast<uint32_t*>(&h);
+                            s2[lane * 4 + (c ^ ((lane >> 1) & 3))] = w;
                         }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = i * 8 + (lane >> 2), ch = lane & 3;
+                            const uint4 val = s2[r * 4 + (ch ^ ((r >> 1) & 3))];
+                            const int64_t grow = grow0 + r, gcol = gcol0 + ch * 8;
+                            if (grow < M && gcol < N) *reinterpret_cast<uint4*>(ep.y_ctr + grow * N + gcol) = val;
+                        }
+                        __syncwarp();
                     }
                 }
             }
