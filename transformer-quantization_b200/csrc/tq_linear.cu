@@ -107,6 +107,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row atoms 1024 B apart
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -131,6 +141,35 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+    if (ACT == 1) return (v * 0.5f) * (1.0f + erff(v * 0.70710678118654752440f));   // nn.GELU (erf form)
+    if (ACT == 2) return v > 0.0f ? v : (v != v ? v : 0.0f);                         // nn.ReLU
+    if (ACT == 3) return tanhf(v);                                                   // nn.Tanh
+    return v;
+}
+
+// 16 accumulators of one row -> scale, bias, activation, optional output quantizer.  One compact,
+// branch-free body per (activation, quantized?) pair so the executed path is contiguous in the
+// instruction cache.  On return o[] holds the fp32 outputs, v[] the centred integers (if HASQ).
+template <int ACT, bool HASQ>
+__device__ __forceinline__ void epi_math16(uint32_t (&v)[16], float (&o)[16], const float* colscale,
+                                           const float* cbias, const float* qscale, const float* qzp,
+                                           const float* qrcp, float qlo, float qhi) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float f = act_fn<ACT>(__uint_as_float(v[j]) * colscale[j] + cbias[j]);
+        if (HASQ) {
+            const QP p{qscale[j], qzp[j], qlo, qhi, qrcp[j], 0};
+            const float qi = quant_int(f, p);
+            const float ctr = __fsub_rn(qi, p.zp);               // centred integer
+            v[j] = __float_as_uint(ctr);
+            f = __fmul_rn(p.scale, ctr);                         // scale * (x_int - zp)
+        }
+        o[j] = f;
+    }
+}
+
 struct EpiArgs {
     const float* bias;      // [N] or null
     float* y;               // [M, N] fp32 or null
@@ -142,7 +181,10 @@ struct EpiArgs {
     int64_t out_q_params;   // 1 or N
     int act_fn;
     float* tile_minmax;     // optional calibration side reduction (ordered-int encoded, 2 words)
+    long long* trace;       // optional: clock64 timeline of CTA 0 (16 slots), for tools/trace_linear.py
 };
+
+#define TQ_TRACE(slot) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[slot] = clock64(); } while (0)
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -169,6 +211,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int kb_per_pass = (int)(K / BK);
     const int num_kb = kb_per_pass * k_split;
 
+    if (threadIdx.x == 0) TQ_TRACE(0);
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -195,6 +238,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (threadIdx.x == 0) TQ_TRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -204,6 +248,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int32_t m0 = (int32_t)((t / n_tiles) * BM), n0 = (int32_t)((t % n_tiles) * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    if (kb == 0) TQ_TRACE(2);
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), C::kStageBytes);
                     const uint32_t sa = base + stage * C::kStageBytes;
@@ -211,6 +256,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tma_load_2d(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BK, n0, full_bar(stage));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
+                TQ_TRACE(3);
             }
         }
     } else if (warp == 1) {
@@ -227,6 +273,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
+                    if (kb == 0) TQ_TRACE(4);
+                    if (kb == 1) TQ_TRACE(5);
                     tc_fence_after();
                     const uint32_t sa = base + stage * C::kStageBytes;
                     const uint64_t adesc = make_desc_sw128(sa), bdesc = make_desc_sw128(sa + C::kABytes);
@@ -240,6 +288,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
                 tc_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
+                TQ_TRACE(6);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -304,88 +353,111 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 : "=r"(exact)
                 : "r"(need_exact)
                 : "memory");
+            if (et == 0) TQ_TRACE(7);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            if (et == 0) TQ_TRACE(8);
             const int64_t row = m0 + quarter * 32 + lane;
             const bool row_ok = row < M;
+            const int64_t grow0 = m0 + quarter * 32;
+            float4* stg = reinterpret_cast<float4*>(store_stage + (warp - 2) * 4096);
+            // Each warp of a pair owns one half of the tile's columns and walks it 16 columns at a
+            // time: the loop body (16 elements) stays small enough for the instruction cache -- a
+            // fully unrolled 32-wide body (~60 KB of SASS) made instruction fetch the top stall.
 #pragma unroll 1
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                float o[32];
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                float o[16];
+                if (has_q && exact) {
+                    // rare (a column scale outside div_rn's proven domain): IEEE divide, one element
+                    // at a time through a compact loop
+#pragma unroll 1
+                    for (int j = 0; j < 16; ++j) {
+                        float f = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = __uint_as_float(v[j]) * colscale[c0 + j] + cbias[c0 + j];
-                    f = apply_act(f, ep.act_fn);
-                    o[j] = f;
+                        for (int k = 0; k < 16; ++k)
+                            if (k == j) f = __uint_as_float(v[k]);
+                        f = apply_act(f * colscale[c0 + j] + cbias[c0 + j], ep.act_fn);
+                        const QP p{qscale[c0 + j], qzp[c0 + j], qlo, qhi, qrcp[c0 + j], 1};
+                        const float ctr = __fsub_rn(quant_int(f, p), p.zp);
+                        f = __fmul_rn(p.scale, ctr);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (k == j) {
+                                v[k] = __float_as_uint(ctr);
+                                o[k] = f;
+                            }
+                    }
+                } else {
+                    const float *cs = colscale + c0, *cb = cbias + c0, *qs = qscale + c0, *qz = qzp + c0,
+                                *qr = qrcp + c0;
+                    switch (ep.act_fn * 2 + (has_q ? 1 : 0)) {      // warp-uniform
+                        case 0: epi_math16<0, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        case 1: epi_math16<0, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        case 2: epi_math16<1, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        case 3: epi_math16<1, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        case 4: epi_math16<2, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        case 5: epi_math16<2, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        case 6: epi_math16<3, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        default: epi_math16<3, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                    }
                 }
                 if (ep.tile_minmax != nullptr && row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         if (n0 + c0 + j < N) {
                             run_min = fminf(run_min, o[j]);
                             run_max = fmaxf(run_max, o[j]);
                         }
                     }
                 }
-                if (has_q) {
+                // ---- coalesced stores: 32 x 16 transpose through this warp's private smem tile ----
+                // registers hold one ROW per lane; a direct store would touch 32 different lines per
+                // instruction.  Swizzled 16-byte chunks keep both smem phases bank-conflict free.
+                const int64_t gcol0 = n0 + c0;
+                if (ep.y != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const QP p{qscale[c0 + j], qzp[c0 + j], qlo, qhi, qrcp[c0 + j], exact};
-                        const float qi = quant_int(o[j], p);
-                        v[j] = __float_as_uint(__fsub_rn(qi, p.zp));      // centred integer
-                        o[j] = __fmul_rn(p.scale, __uint_as_float(v[j]));  // scale * (x_int - zp)
+                    for (int c = 0; c < 4; ++c)
+                        stg[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = i * 8 + (lane >> 2), ch = lane & 3;
+                        const float4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+                        const int64_t grow = grow0 + r, gcol = gcol0 + ch * 4;
+                        if (grow < M && gcol < N) *reinterpret_cast<float4*>(ep.y + grow * N + gcol) = val;
                     }
+                    __syncwarp();
                 }
-                // ---- coalesced stores: 32x32 transpose through this warp's private smem tile ----
-                // registers hold one ROW per lane; a direct store would touch 32 different 128 B lines
-                // per instruction.  Swizzled 16-byte chunks keep both smem phases conflict free.
-                {
-                    float4* stg = reinterpret_cast<float4*>(store_stage + (warp - 2) * 4096);
-                    const int64_t grow0 = m0 + quarter * 32;
-                    const int64_t gcol0 = n0 + c0;
-                    if (ep.y != nullptr) {
+                if (ep.y_ctr != nullptr) {
+                    uint4* s2 = reinterpret_cast<uint4*>(stg);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            stg[lane * 8 + (c ^ (lane & 7))] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = i * 4 + (lane >> 3), ch = lane & 7;
-                            const float4 val = stg[r * 8 + (ch ^ (r & 7))];
-                            const int64_t grow = grow0 + r, gcol = gcol0 + ch * 4;
-                            if (grow < M && gcol < N) *reinterpret_cast<float4*>(ep.y + grow * N + gcol) = val;
-                        }
-                        __syncwarp();
+                    for (int c = 0; c < 2; ++c) {
+                        uint4 w;
+                        __nv_bfloat162 h;
+                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1]));
+                        w.x = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+                        w.y = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+                        w.z = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+                        w.w = *reinterpret_cast<uint32_t*>(&h);
+                        s2[lane * 2 + (c ^ ((lane >> 2) & 1))] = w;
                     }
-                    if (ep.y_ctr != nullptr) {
-                        uint4* s2 = reinterpret_cast<uint4*>(stg);
+                    __syncwarp();
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint4 w;
-                            __nv_bfloat162 h;
-                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1]));
-                            w.x = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
-                            w.y = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
-                            w.z = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
-                            w.w = *reinterpret_cast<uint32_t*>(&h);
-                            s2[lane * 4 + (c ^ ((lane >> 1) & 3))] = w;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = i * 8 + (lane >> 2), ch = lane & 3;
-                            const uint4 val = s2[r * 4 + (ch ^ ((r >> 1) & 3))];
-                            const int64_t grow = grow0 + r, gcol = gcol0 + ch * 8;
-                            if (grow < M && gcol < N) *reinterpret_cast<uint4*>(ep.y_ctr + grow * N + gcol) = val;
-                        }
-                        __syncwarp();
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = i * 16 + (lane >> 1), ch = lane & 1;
+                        const uint4 val = s2[r * 2 + (ch ^ ((r >> 2) & 1))];
+                        const int64_t grow = grow0 + r, gcol = gcol0 + ch * 8;
+                        if (grow < M && gcol < N) *reinterpret_cast<uint4*>(ep.y_ctr + grow * N + gcol) = val;
                     }
+                    __syncwarp();
                 }
             }
+            if (et == 0) TQ_TRACE(9);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -404,6 +476,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TQ_TRACE(10);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)kTmemCols)
@@ -517,8 +590,6 @@ int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
                        tq_qspec w_q, int64_t w_q_params, int32_t act_fn, tq_qspec out_q, int64_t out_q_params,
                        float* tile_minmax, void* ws, size_t ws_bytes, void* stream) {
     using namespace tq::gemm;
-    (void)ws;
-    (void)ws_bytes;
     if (a_ctr_bf16 == nullptr || w_ctr_bf16 == nullptr || (y == nullptr && y_ctr_bf16 == nullptr)) return TQ_EINVAL;
     if (M < 1 || N < 1 || K < 1 || (k_split != 1 && k_split != 3)) return TQ_EINVAL;
     if (K % BK != 0 || N % 8 != 0) return TQ_EUNSUPPORTED;
@@ -541,6 +612,7 @@ int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
     ep.out_q_params = out_q_params;
     ep.act_fn = act_fn;
     ep.tile_minmax = tile_minmax;
+    ep.trace = (ws != nullptr && ws_bytes >= 16 * sizeof(long long)) ? reinterpret_cast<long long*>(ws) : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pick_bn(M, N)) {
         case 256: return launch<256>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
