@@ -179,6 +179,49 @@ int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
                        int32_t act_fn, tq_qspec out_q, int64_t out_q_params, float* tile_minmax,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* Same GEMM with the residual branch of the encoder blocks fused into the epilogue (reference
+ * models/quantized_bert.py:238-245 attention output, :264-277 FFN output):
+ *     g = dequant(out_q(x @ Wq.T + bias));  y = out2_q(g + res_scale * res_ctr)
+ * res_ctr [M, N] is the centred bf16 grid of the residual input (the block input), res_q its
+ * per-tensor quantizer, out2_q the residual-sum quantizer (1 or N parameters).  y / y_ctr as above. */
+int tq_linear_res_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias,
+                           float* y, void* y_ctr_bf16, int64_t M, int64_t N, int64_t K,
+                           tq_qspec a_q, tq_qspec w_q, int64_t w_q_params,
+                           tq_qspec out_q, int64_t out_q_params, const void* res_ctr_bf16,
+                           tq_qspec res_q, tq_qspec out2_q, int64_t out2_q_params, void* stream);
+
+/* ---- fused encoder blocks --------------------------------------------
+ * All tensors are centred integer grids in bf16 (x_int - zero_point; dequantized value = scale*ctr).
+ *
+ * Self-attention core of one layer (reference models/quantized_bert.py:153-213):
+ *   scores = Q K^T -> s_q QDQ -> / sqrt(head_dim) + mask -> softmax -> p_q QDQ -> P V -> c_q QDQ
+ * qkv_ctr [B*T, 3*H*head_dim] (Q | K | V column blocks, head h at columns h*head_dim..), output
+ * c_ctr [B*T, H*head_dim].  One CTA per (batch, head), both products on tcgen05 with exact integer
+ * operands; scores / probabilities stay in TMEM / shared memory.  q_q, k_q, v_q: per-tensor
+ * quantizers of the three projections (scales); mask [B, T] additive fp32 or NULL.
+ * Supported: T == 128, head_dim == 64 (else TQ_EUNSUPPORTED: callers use the unfused path). */
+int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B, int32_t T, int32_t H,
+                          int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q,
+                          tq_qspec p_q, tq_qspec c_q, const float* mask, void* stream);
+
+/* QuantLayerNorm over a quantized input (reference autoquant_utils.py:55-66 applied to the output of
+ * a residual quantizer): x = in_scale * x_ctr; y = LayerNorm(x; gamma_q, beta, eps); out_q QDQ.
+ * gamma_q is the fake-quantized LayerNorm weight.  in_q / out_q: 1 or D parameters.  out_f32 optional.
+ * One warp per row; requires D % 256 == 0, D <= 1024. */
+int tq_ln_qdq_bf16(const void* x_ctr_bf16, tq_qspec in_q, int64_t in_q_params, const float* gamma_q,
+                   const float* beta, float eps, tq_qspec out_q, int64_t out_q_params,
+                   void* out_ctr_bf16, float* out_f32, int64_t M, int32_t D, void* stream);
+
+/* Embedding block (reference models/quantized_bert.py:59-88): e_tok QDQ(word[id] + type[tt]) ->
+ * e_pos QDQ(. + pos[p]) -> LayerNorm -> out_q QDQ.  Tables are the fake-quantized embedding weights
+ * (fp32).  type_ids / pos_ids may be NULL (all zero / row % T). */
+int tq_embed_ln_qdq_bf16(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int64_t T,
+                         const float* word_q, const float* type_q, const float* pos_q,
+                         tq_qspec e_tok, int64_t e_tok_params, tq_qspec e_pos, int64_t e_pos_params,
+                         const float* gamma_q, const float* beta, float eps, tq_qspec out_q,
+                         int64_t out_q_params, void* out_ctr_bf16, float* out_f32, int64_t M, int32_t D,
+                         void* stream);
+
 /* hi|mid|lo bf16 split of an fp32 tensor [M, K] -> [M, 3K] (x == hi + mid + lo to 2^-24 rel.). */
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream);
 

@@ -1,0 +1,217 @@
+"""Fused encoder kernels and the fused inference engine (GPU).
+
+* tq_linear_res_qdq_bf16 : bit-exact vs the oracle (integer GEMM is exact, epilogue is the same
+  fp32 operation chain as the reference's dense -> QDQ -> + residual -> QDQ).
+* tq_ln_qdq_bf16 / tq_embed_ln_qdq_bf16 / tq_attention_qdq_bf16 : compared with the module-level
+  formulation (library LayerNorm / softmax in fp32 + oracle QDQ).  LayerNorm statistics, exp and the
+  softmax sum are evaluated in a different order than the library does, so a value that lands within
+  ~1e-6 of a rounding boundary may move to the neighbouring integer: the bar is max |d(int)| <= 1 and
+  < 0.5 % (LayerNorm) / 1 % (attention) of the integers differ.
+* FusedBertEngine vs the module path (engine.bert model, one kernel per site) on the same weights
+  and ranges: logits within 3 output steps, < 3 % of last-hidden integers differ.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import tq_native
+import parity_cases as P
+from oracle import fakequant_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def T_(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def asym_spec(ops, xmin, xmax, n_bits=8):
+    d, z = O.asym_set_quant_range(xmin, xmax, n_bits)
+    dt, zt = T_(np.atleast_1d(d)), T_(np.atleast_1d(z))
+    return ops.spec(dt, zt, None, n_bits), (dt, zt), (d, z)
+
+
+def flips(a, b, max_rate):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = np.abs(a - b)
+    assert d.max() <= 1.0, f'max integer difference {d.max()}'
+    rate = (d > 0).mean()
+    assert rate <= max_rate, f'{rate:.5f} of the integers differ'
+    return rate
+
+
+def test_linear_residual_epilogue_exact():
+    ops = tq_native.ops()
+    M, N, K = 384, 256, 192
+    rs = np.random.RandomState(0)
+    a = rs.randint(-255, 256, size=(M, K)).astype(np.float32)
+    w = rs.randint(-128, 128, size=(N, K)).astype(np.float32)
+    r = rs.randint(-200, 201, size=(M, N)).astype(np.float32)
+    bias = (rs.randn(N) * 0.3).astype(np.float32)
+    a_sp, a_keep, (a_d, a_z) = asym_spec(ops, -2.0, 3.0)
+    r_sp, r_keep, (r_d, r_z) = asym_spec(ops, -4.0, 4.0)
+    w_d, w_signed = O.sym_set_quant_range(-0.08, 0.09, 8)
+    wd_t, ws_t = T_(np.atleast_1d(w_d)), torch.tensor(bool(w_signed), device=DEV)
+    w_sp = ops.spec(wd_t, None, ws_t, 8)
+    acc = (a.astype(np.float64) @ w.astype(np.float64).T).astype(np.float32)
+    pre = (acc * np.float32(O.scale_of(a_d) * O.scale_of(w_d)) + bias).astype(np.float32)
+    g_sp, g_keep, (g_d, g_z) = asym_spec(ops, float(pre.min()), float(pre.max()))
+    g = O.qdq_asym(pre, g_d, g_z, 8)
+    res = (np.float32(O.scale_of(r_d)) * r).astype(np.float32)
+    tot = (g + res).astype(np.float32)
+    u_sp, u_keep, (u_d, u_z) = asym_spec(ops, float(tot.min()) * 0.9, float(tot.max()) * 0.9)
+    ref_int = O.qdq_asym(tot, u_d, u_z, 8, return_int=True) - O.asym_zero_point(u_z, 8)
+    ref = O.qdq_asym(tot, u_d, u_z, 8)
+    y, yc = ops.linear_res(T_(a).to(torch.bfloat16), T_(w).to(torch.bfloat16), T_(bias), M, N, K, a_sp, w_sp, 1,
+                           g_sp, 1, T_(r).to(torch.bfloat16), r_sp, u_sp, 1, want_f32=True)
+    torch.cuda.synchronize()
+    P.assert_same(yc.float(), ref_int, 'residual epilogue centred integers')
+    P.assert_same(y, ref, 'residual epilogue dequantized output')
+
+
+@pytest.mark.parametrize('D', [256, 768, 1024])
+def test_ln_qdq_kernel(D):
+    ops = tq_native.ops()
+    M = 200
+    rs = np.random.RandomState(D)
+    ctr = rs.randint(-120, 130, size=(M, D)).astype(np.float32)
+    gamma = (1 + 0.1 * rs.randn(D)).astype(np.float32)
+    beta = (0.05 * rs.randn(D)).astype(np.float32)
+    in_sp, in_keep, (in_d, in_z) = asym_spec(ops, -3.0, 3.2)
+    x = (np.float32(O.scale_of(in_d)) * ctr).astype(np.float32)
+    ref_ln = F.layer_norm(torch.from_numpy(x), (D,), torch.from_numpy(gamma), torch.from_numpy(beta), 1e-12).numpy()
+    out_sp, out_keep, (o_d, o_z) = asym_spec(ops, float(ref_ln.min()), float(ref_ln.max()))
+    ref_int = O.qdq_asym(ref_ln, o_d, o_z, 8, return_int=True) - O.asym_zero_point(o_z, 8)
+    out, f32 = ops.ln_qdq(T_(ctr).to(torch.bfloat16), in_sp, 1, T_(gamma), T_(beta), 1e-12, out_sp, 1, want_f32=True)
+    torch.cuda.synchronize()
+    flips(out.float().cpu().numpy(), ref_int, 5e-3)
+    assert torch.equal(f32, out.float() * float(O.scale_of(o_d)))
+
+
+def test_embed_ln_qdq_kernel():
+    ops = tq_native.ops()
+    B, Tn, D, V = 3, 128, 256, 500
+    rs = np.random.RandomState(5)
+    word = (rs.randn(V, D) * 0.02).astype(np.float32)
+    pos = (rs.randn(Tn, D) * 0.02).astype(np.float32)
+    typ = (rs.randn(2, D) * 0.02).astype(np.float32)
+    ids = rs.randint(0, V, size=(B, Tn))
+    tt = rs.randint(0, 2, size=(B, Tn))
+    gamma = (1 + 0.1 * rs.randn(D)).astype(np.float32)
+    beta = (0.05 * rs.randn(D)).astype(np.float32)
+    e0 = word[ids] + typ[tt]
+    s0, k0, (d0, z0) = asym_spec(ops, float(e0.min()), float(e0.max()))
+    e0q = O.qdq_asym(e0.astype(np.float32), d0, z0, 8)
+    e1 = (e0q + pos[np.arange(Tn)][None]).astype(np.float32)
+    s1, k1, (d1, z1) = asym_spec(ops, float(e1.min()), float(e1.max()))
+    e1q = O.qdq_asym(e1, d1, z1, 8)
+    ln = F.layer_norm(torch.from_numpy(e1q), (D,), torch.from_numpy(gamma), torch.from_numpy(beta), 1e-12).numpy()
+    s2, k2, (d2, z2) = asym_spec(ops, float(ln.min()), float(ln.max()))
+    ref_int = O.qdq_asym(ln, d2, z2, 8, return_int=True) - O.asym_zero_point(z2, 8)
+    out, _ = ops.embed_ln_qdq(T_(ids.reshape(-1)), T_(tt.reshape(-1)), None, Tn, T_(word), T_(typ), T_(pos), s0, 1,
+                              s1, 1, T_(gamma), T_(beta), 1e-12, s2, 1)
+    torch.cuda.synchronize()
+    flips(out.float().cpu().numpy().reshape(B, Tn, D), ref_int, 5e-3)
+
+
+@pytest.mark.parametrize('use_mask', [False, True])
+def test_attention_kernel(use_mask):
+    ops = tq_native.ops()
+    B, H, Tn, hd = 2, 4, 128, 64
+    D = H * hd
+    rs = np.random.RandomState(11)
+    qkv = rs.randint(-40, 41, size=(B * Tn, 3 * D)).astype(np.float32)
+    sq, _, (dq, zq) = asym_spec(ops, -1.9, 2.0)
+    sk, _, (dk, zk) = asym_spec(ops, -2.1, 2.0)
+    sv, _, (dv, zv) = asym_spec(ops, -2.5, 2.4)
+    fq, fk, fv = (np.float32(O.scale_of(d)) for d in (dq, dk, dv))
+    mask = None
+    if use_mask:
+        m = np.ones((B, Tn), np.float32)
+        m[0, 100:] = 0
+        m[1, 64:70] = 0
+        mask = ((1.0 - m) * -10000.0).astype(np.float32)
+    q = qkv[:, :D].reshape(B, Tn, H, hd).transpose(0, 2, 1, 3)
+    k = qkv[:, D:2 * D].reshape(B, Tn, H, hd).transpose(0, 2, 1, 3)
+    v = qkv[:, 2 * D:].reshape(B, Tn, H, hd).transpose(0, 2, 1, 3)
+    s_int = np.einsum('bhqd,bhkd->bhqk', q.astype(np.float64), k.astype(np.float64)).astype(np.float32)
+    scores = (s_int * np.float32(fq * fk)).astype(np.float32)
+    ss, _, (ds, zs) = asym_spec(ops, float(scores.min()), float(scores.max()))
+    t = O.qdq_asym(scores, ds, zs, 8)
+    t = (t * np.float32(1.0 / math.sqrt(hd))).astype(np.float32)
+    if mask is not None:
+        t = (t + mask[:, None, None, :]).astype(np.float32)
+    probs = torch.softmax(torch.from_numpy(t), dim=-1).numpy()
+    sp, _, (dp, zp) = asym_spec(ops, 0.0, float(probs.max()))
+    p_int = O.qdq_asym(probs, dp, zp, 8, return_int=True) - O.asym_zero_point(zp, 8)
+    o_int = np.einsum('bhqk,bhkd->bhqd', p_int.astype(np.float64), v.astype(np.float64)).astype(np.float32)
+    ctx = (o_int * np.float32(np.float32(O.scale_of(dp)) * fv)).astype(np.float32)
+    sc, _, (dc, zc) = asym_spec(ops, float(ctx.min()), float(ctx.max()))
+    c_int = O.qdq_asym(ctx, dc, zc, 8, return_int=True) - O.asym_zero_point(zc, 8)
+    ref = c_int.transpose(0, 2, 1, 3).reshape(B * Tn, D)
+    out = ops.attention(T_(qkv).to(torch.bfloat16), B, Tn, H, hd, sq, sk, sv, ss, sp, sc,
+                        T_(mask) if mask is not None else None)
+    torch.cuda.synchronize()
+    flips(out.float().cpu().numpy(), ref, 1e-2)
+
+
+def _model(device, n_bits=8, seed=0):
+    from engine.bert import BertConfig, QuantBertForSequenceClassification
+    from quantization.quantizers import QMethods
+    cfg = BertConfig(vocab_size=2000, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                     intermediate_size=512, max_position_embeddings=128)
+    m = QuantBertForSequenceClassification(cfg, method=QMethods.symmetric_uniform,
+                                           act_method=QMethods.asymmetric_uniform, n_bits=n_bits, n_bits_act=8)
+    m.init_weights(seed=seed, std=0.05)
+    g = torch.Generator().manual_seed(1)
+    for mod in m.modules():                      # non-trivial biases / LayerNorm parameters
+        if isinstance(mod, torch.nn.Linear):
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.05
+        elif isinstance(mod, torch.nn.LayerNorm):
+            mod.weight.data = 1 + torch.randn(mod.weight.shape, generator=g) * 0.1
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.05
+    return m.to(device).eval()
+
+
+@pytest.mark.parametrize('n_bits,use_mask', [(8, False), (4, True)])
+def test_engine_matches_module_path(n_bits, use_mask):
+    from engine.fused import FusedBertEngine
+    B, Tn = 4, 128
+    model = _model(DEV, n_bits)
+    g = torch.Generator().manual_seed(3)
+    ids = [torch.randint(0, 2000, (B, Tn), generator=g).to(DEV) for _ in range(3)]
+    mask = torch.ones(B, Tn, dtype=torch.int64, device=DEV)
+    if use_mask:
+        mask[1, 90:] = 0
+        mask[3, 17:23] = 0
+    model.set_quant_state(True, True)
+    with torch.no_grad():
+        for b in ids[:2]:
+            model(b, mask)
+        model.fix_ranges()
+        ref_logits = model(ids[2], mask)
+        ref_hidden = model.encode(ids[2], mask)
+    eng = FusedBertEngine(model, B, Tn)
+    logits = eng(ids[2], mask)
+    torch.cuda.synchronize()
+    cls_step = float(model.classifier.activation_quantizer.quantizer.scale)
+    assert (logits - ref_logits).abs().max().item() <= 3 * cls_step + 1e-6
+    z = model.layers[-1].z.activation_quantizer.quantizer
+    zs = float(z.scale)
+    dh = ((eng.hidden_states() - ref_hidden).abs() / zs).cpu().numpy()
+    assert dh.max() <= 4.5 and (dh > 0.5).mean() < 0.03, (dh.max(), (dh > 0.5).mean())
+    # the engine is deterministic and graph-capturable
+    l0 = eng.ops.launches
+    graph = torch.cuda.CUDAGraph()
+    static_ids = ids[2].clone()
+    with torch.cuda.graph(graph):
+        out = eng(static_ids, mask)
+    n_launch = eng.ops.launches - l0
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, logits)
+    assert n_launch == 1 + 7 * 2 + 2

@@ -1,0 +1,582 @@
+// Fused encoder blocks around the quantizer sites (pulled forward
+// because 24 + 36 of the 161 activation-quantizer sites of a BERT-base forward sit in them):
+//
+//   tq_attention_qdq_bf16 : QK^T -> QDQ(scores) -> /sqrt(d) + mask -> softmax -> QDQ(probs) -> PV ->
+//                           QDQ(context)      (reference models/quantized_bert.py:153-213)
+//                           one CTA per (batch, head); both GEMMs on tcgen05 with exact integer
+//                           operands (bf16 carriers), scores/probs never leave the SM.
+//   tq_ln_qdq_bf16        : LayerNorm with fake-quantized gamma over a quantized input + output QDQ
+//                           (reference autoquant_utils.py:55-66 after the residual quantizer)
+//   tq_embed_ln_qdq_bf16  : word + token-type -> QDQ -> + position -> QDQ -> LayerNorm -> QDQ
+//                           (reference models/quantized_bert.py:59-88)
+//
+// All three read / write the CENTRED INTEGER GRID of the fake-quantized tensors in bf16
+// (x_int - zero_point, exact for n_bits <= 8): 2 B per element instead of the 4 B fp32 tensor the
+// reference materialises at every site, and exactly the operand format of tq_linear_qdq_bf16.
+// The dequantized fp32 value the reference would have produced is scale * ctr, recomputed on the fly.
+#include "tq_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+
+namespace tq {
+namespace fused {
+
+// ---------------------------------------------------------------------------------------------------
+// shared small helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16_lo(uint32_t pair) { return __uint_as_float(pair << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t pair) { return __uint_as_float(pair & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct ColQ {              // quantizer with 1 or C parameter slots
+    tq_qspec q;
+    int64_t params;
+    float lo, hi;
+    QP p0;                 // resolved once when per-tensor
+    __device__ __forceinline__ void init() {
+        grid_of(q, lo, hi);
+        p0 = resolve(q, 0, lo, hi);
+    }
+    __device__ __forceinline__ QP at(int64_t c) const { return params > 1 ? resolve(q, c, lo, hi) : p0; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm (+ optional embedding prologue) : one warp per row, D % 256 == 0, D <= 1024
+// ---------------------------------------------------------------------------------------------------
+constexpr int kLnWarps = 8;
+constexpr int kLnMaxIter = 4;    // D / 256
+
+struct LnArgs {
+    // input: either a quantized tensor (x_ctr + in_q) or the embedding prologue (ids != null)
+    const __nv_bfloat16* x_ctr;
+    ColQ in_q;
+    const int64_t* ids;          // [M] token ids            -- embedding prologue
+    const int64_t* type_ids;     // [M] or null (all zero)
+    const int64_t* pos_ids;      // [M] or null (position = row % T)
+    int64_t T;
+    const float* word;           // [V, D] fake-quantized tables
+    const float* type_tab;       // [2, D]
+    const float* pos_tab;        // [P, D]
+    ColQ e_tok, e_pos;           // quantizers of the two embedding sums
+    // LayerNorm
+    const float* gamma_q;        // [D] fake-quantized weight
+    const float* beta;           // [D]
+    float eps;
+    ColQ out_q;
+    __nv_bfloat16* out_ctr;      // [M, D]
+    float* out_f32;              // optional [M, D]
+    int64_t M;
+    int32_t D;
+};
+
+template <bool EMBED>
+__global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
+    if (row >= a.M) return;
+    const int iters = a.D >> 8;                       // 8 elements per lane per iteration
+    float v[kLnMaxIter][8];
+    ColQ in_q = a.in_q, e_tok = a.e_tok, e_pos = a.e_pos, out_q = a.out_q;
+    out_q.init();
+    if (EMBED) {
+        e_tok.init();
+        e_pos.init();
+        const int64_t id = a.ids[row];
+        const int64_t tt = a.type_ids != nullptr ? a.type_ids[row] : 0;
+        const int64_t pp = a.pos_ids != nullptr ? a.pos_ids[row] : (row % a.T);
+#pragma unroll
+        for (int it = 0; it < kLnMaxIter; ++it) {
+            if (it < iters) {
+                const int c = (it * 32 + lane) * 8;
+                const float4* w = reinterpret_cast<const float4*>(a.word + id * a.D + c);
+                const float4* t = reinterpret_cast<const float4*>(a.type_tab + tt * a.D + c);
+                const float4* p = reinterpret_cast<const float4*>(a.pos_tab + pp * a.D + c);
+                const float4 w0 = w[0], w1 = w[1], t0 = t[0], t1 = t[1], p0 = p[0], p1 = p[1];
+                const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float ts[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                const float ps[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float e = qdq(__fadd_rn(ws[j], ts[j]), e_tok.at(c + j));      // quantized_bert.py:78-79
+                    e = qdq(__fadd_rn(e, ps[j]), e_pos.at(c + j));                // :83-84
+                    v[it][j] = e;
+                }
+            }
+        }
+    } else {
+        in_q.init();
+#pragma unroll
+        for (int it = 0; it < kLnMaxIter; ++it) {
+            if (it < iters) {
+                const int c = (it * 32 + lane) * 8;
+                const uint4 raw = *reinterpret_cast<const uint4*>(a.x_ctr + row * a.D + c);
+                const uint32_t pr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[it][2 * j] = __fmul_rn(in_q.at(c + 2 * j).scale, bf16_lo(pr[j]));          // scale * ctr
+                    v[it][2 * j + 1] = __fmul_rn(in_q.at(c + 2 * j + 1).scale, bf16_hi(pr[j]));
+                }
+            }
+        }
+    }
+    // mean / variance over the row (fp32, two passes: the values are in registers)
+    float s = 0.0f;
+#pragma unroll
+    for (int it = 0; it < kLnMaxIter; ++it)
+        if (it < iters)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[it][j];
+    s = warp_sum(s);
+    const float mean = s / (float)a.D;
+    float ss = 0.0f;
+#pragma unroll
+    for (int it = 0; it < kLnMaxIter; ++it)
+        if (it < iters)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[it][j] - mean;
+                ss += d * d;
+            }
+    ss = warp_sum(ss);
+    const float rstd = 1.0f / sqrtf(ss / (float)a.D + a.eps);
+#pragma unroll
+    for (int it = 0; it < kLnMaxIter; ++it) {
+        if (it < iters) {
+            const int c = (it * 32 + lane) * 8;
+            const float4* g = reinterpret_cast<const float4*>(a.gamma_q + c);
+            const float4* b = reinterpret_cast<const float4*>(a.beta + c);
+            const float4 g0 = g[0], g1 = g[1], b0 = b[0], b1 = b[1];
+            const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float ctr[8], deq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float y = (v[it][j] - mean) * rstd * gs[j] + bs[j];
+                const QP p = out_q.at(c + j);
+                ctr[j] = __fsub_rn(quant_int(y, p), p.zp);
+                deq[j] = __fmul_rn(p.scale, ctr[j]);
+            }
+            uint4 o;
+            o.x = pack2(ctr[0], ctr[1]);
+            o.y = pack2(ctr[2], ctr[3]);
+            o.z = pack2(ctr[4], ctr[5]);
+            o.w = pack2(ctr[6], ctr[7]);
+            *reinterpret_cast<uint4*>(a.out_ctr + row * a.D + c) = o;
+            if (a.out_f32 != nullptr) {
+                float4* of = reinterpret_cast<float4*>(a.out_f32 + row * a.D + c);
+                of[0] = make_float4(deq[0], deq[1], deq[2], deq[3]);
+                of[1] = make_float4(deq[4], deq[5], deq[6], deq[7]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention: T = 128 keys/queries per (batch, head), head_dim = 64
+// ---------------------------------------------------------------------------------------------------
+constexpr int AT = 128, AD = 64;
+constexpr int kAttnThreads = 192;       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 softmax / epilogue
+constexpr int kAttnTmemCols = 256;      // S: [0,128)  O: [128,192)
+constexpr int kAttnSmem = 16384 * 3 + 32768 + 512 + 64 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("tq_attention: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// K-major SWIZZLE_128B operand (rows of 128 B, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// MN-major SWIZZLE_128B operand: 64 MN-elements (128 B) contiguous per K row, 8-row atoms 1024 B
+// apart along K (stride byte offset); a single 64-wide MN block (leading byte offset unused)
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+struct AttnArgs {
+    int32_t B, H;                 // batch, heads; rows of qkv = B * AT, columns = 3 * H * AD
+    tq_qspec q_q, k_q, v_q;       // per-tensor quantizers of the Q / K / V projections (scales only)
+    tq_qspec s_q, p_q, c_q;       // scores / probs / context quantizers (per-tensor)
+    const float* mask;            // [B, AT] additive mask (0 / -10000) or null
+    __nv_bfloat16* c_ctr;         // [B * AT, H * AD] centred context grid
+    float inv_sqrt_d;             // 1 / sqrt(head_dim)
+};
+
+__device__ __forceinline__ float scale_of(const tq_qspec& q) {
+    float lo, hi;
+    grid_of(q, lo, hi);
+    return resolve(q, 0, lo, hi).scale;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* bp = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t sQ = base, sK = base + 16384, sV = base + 32768, sP = base + 49152;
+    unsigned char* pP = bp + 49152;
+    float* smask = reinterpret_cast<float*>(bp + 49152 + 32768);
+    const uint32_t bar0 = base + 49152 + 32768 + 512;
+    const uint32_t bar_qk = bar0, bar_v = bar0 + 8, bar_s = bar0 + 16, bar_p = bar0 + 24, bar_o = bar0 + 32;
+    const uint32_t tmem_slot = bar0 + 40;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bp + 49152 + 32768 + 512 + 40);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const int32_t dmodel = a.H * AD;
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(bar_qk, 1);
+            mbar_init(bar_v, 1);
+            mbar_init(bar_s, 1);
+            mbar_init(bar_p, 128);
+            mbar_init(bar_o, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)kAttnTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int r = threadIdx.x - 64;
+        smask[r] = a.mask != nullptr ? a.mask[(int64_t)b * AT + r] : 0.0f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_qk, 32768);
+            tma_load_2d(sQ, &map_qkv, h * AD, b * AT, bar_qk);
+            tma_load_2d(sK, &map_qkv, dmodel + h * AD, b * AT, bar_qk);
+            mbar_expect_tx(bar_v, 16384);
+            tma_load_2d(sV, &map_qkv, 2 * dmodel + h * AD, b * AT, bar_v);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // S[q, k] = sum_d Q[q, d] * K[k, d]      (both operands K-major, K = head_dim)
+            mbar_wait(bar_qk, 0);
+            tc_fence_after();
+            constexpr uint32_t id1 = idesc_bf16(128, 128, 0);
+#pragma unroll
+            for (int k = 0; k < AD / 16; ++k)
+                tc_mma(tmem, desc_k_sw128(sQ) + (uint64_t)(2 * k), desc_k_sw128(sK) + (uint64_t)(2 * k), id1, k != 0);
+            tc_commit(bar_s);
+            // O[q, d] = sum_k P[q, k] * V[k, d]      (A = P K-major over keys; B = V MN-major)
+            mbar_wait(bar_p, 0);
+            mbar_wait(bar_v, 0);
+            tc_fence_after();
+            constexpr uint32_t id2 = idesc_bf16(128, 64, 1);
+#pragma unroll
+            for (int k = 0; k < AT / 16; ++k) {
+                const uint64_t ad = desc_k_sw128(sP + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3));
+                const uint64_t bd = desc_mn_sw128(sV + k * 2048);
+                tc_mma(tmem + 128, ad, bd, id2, k != 0);
+            }
+            tc_commit(bar_o);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;                      // query index == TMEM lane
+        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        float lo, hi;
+        grid_of(a.s_q, lo, hi);
+        const QP qs = resolve(a.s_q, 0, lo, hi);
+        grid_of(a.p_q, lo, hi);
+        const QP qp = resolve(a.p_q, 0, lo, hi);
+        grid_of(a.c_q, lo, hi);
+        const QP qc = resolve(a.c_q, 0, lo, hi);
+        const float sqk = scale_of(a.q_q) * scale_of(a.k_q);
+        const float spv = qp.scale * scale_of(a.v_q);
+
+        mbar_wait(bar_s, 0);
+        tc_fence_after();
+        // pass 1: scores -> QDQ -> / sqrt(d) + mask, written back to TMEM; row max
+        float vmax = __int_as_float(0xff800000);
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float t = qdq(__fmul_rn(__uint_as_float(v[j]), sqk), qs);       // quantized_bert.py:153-154
+                t = __fadd_rn(__fmul_rn(t, a.inv_sqrt_d), smask[c0 + j]);       // :190-194
+                vmax = fmaxf(vmax, t);
+                v[j] = __float_as_uint(t);
+            }
+            tmem_st16(trow + c0, v);
+        }
+        // pass 2: exp(t - max), row sum
+        float vsum = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float e = expf(__uint_as_float(v[j]) - vmax);
+                vsum += e;
+                v[j] = __float_as_uint(e);
+            }
+            tmem_st16(trow + c0, v);
+        }
+        // pass 3: probs -> QDQ -> centred integers into the swizzled K-major A tile
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+            float c[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float pr = __fdiv_rn(__uint_as_float(v[j]), vsum);          // softmax, :197
+                c[j] = __fsub_rn(quant_int(pr, qp), qp.zp);                       // :198
+            }
+            const int halfk = c0 >> 6;                       // which 64-key swizzle span
+            const int ch0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this row piece
+            uint4* prow = reinterpret_cast<uint4*>(pP + halfk * 16384 + row * 128);
+            uint4 w0, w1;
+            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
+            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
+            prow[(ch0) ^ (row & 7)] = w0;
+            prow[(ch0 + 1) ^ (row & 7)] = w1;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
+        tc_fence_before();
+        mbar_arrive(bar_p);
+
+        // context: O * (s_p * s_v) -> QDQ -> centred bf16, coalesced through the (now free) P tile
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        uint4* stg = reinterpret_cast<uint4*>(pP + (warp - 2) * 4096);     // 32 rows x 128 B per warp
+#pragma unroll 1
+        for (int c0 = 0; c0 < AD; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + 128 + c0, v);
+            float c[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                c[j] = __fsub_rn(quant_int(__fmul_rn(__uint_as_float(v[j]), spv), qc), qc.zp);   // :201-213
+            uint4 w0, w1;
+            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
+            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
+            const int ch0 = c0 >> 3;
+            stg[lane * 8 + ((ch0) ^ (lane & 7))] = w0;
+            stg[lane * 8 + ((ch0 + 1) ^ (lane & 7))] = w1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3), ch = lane & 7;
+            const uint4 val = stg[r * 8 + (ch ^ (r & 7))];
+            const int64_t grow = (int64_t)b * AT + quarter * 32 + r;
+            *reinterpret_cast<uint4*>(a.c_ctr + grow * dmodel + h * AD + ch * 8) = val;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kAttnTmemCols)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace fused
+}  // namespace tq
+
+extern "C" {
+
+int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B, int32_t T, int32_t H,
+                          int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q, tq_qspec p_q,
+                          tq_qspec c_q, const float* mask, void* stream) {
+    using namespace tq::fused;
+    if (qkv_ctr_bf16 == nullptr || c_ctr_bf16 == nullptr || B < 1 || H < 1) return TQ_EINVAL;
+    if (T != AT || head_dim != AD) return TQ_EUNSUPPORTED;
+    if (!tq::aligned16(qkv_ctr_bf16) || !tq::aligned16(c_ctr_bf16)) return TQ_EALIGN;
+    const tq_qspec* all[6] = {&q_q, &k_q, &v_q, &s_q, &p_q, &c_q};
+    for (int i = 0; i < 6; ++i)
+        if (int e = tq::check_qspec(*all[i])) return e;
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) return TQ_EUNSUPPORTED;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)(3 * H * AD), (cuuint64_t)B * AT};
+    const cuuint64_t strides[1] = {(cuuint64_t)(3 * H * AD) * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)AD, (cuuint32_t)AT};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv_ctr_bf16), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return TQ_EINVAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    AttnArgs a;
+    a.B = B;
+    a.H = H;
+    a.q_q = q_q; a.k_q = k_q; a.v_q = v_q; a.s_q = s_q; a.p_q = p_q; a.c_q = c_q;
+    a.mask = mask;
+    a.c_ctr = reinterpret_cast<__nv_bfloat16*>(c_ctr_bf16);
+    a.inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
+    attention_kernel<<<B * H, kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(map, a);
+    return tq::launch_status();
+}
+
+static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {
+    using namespace tq::fused;
+    if (a.M < 1 || a.D < 256 || (a.D & 255) != 0 || a.D > 256 * kLnMaxIter) return TQ_EUNSUPPORTED;
+    if (a.gamma_q == nullptr || a.beta == nullptr || a.out_ctr == nullptr) return TQ_EINVAL;
+    if (int e = tq::check_qspec(a.out_q.q)) return e;
+    const unsigned grid = (unsigned)((a.M + kLnWarps - 1) / kLnWarps);
+    if (embed) ln_qdq_kernel<true><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(a);
+    else ln_qdq_kernel<false><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(a);
+    return tq::launch_status();
+}
+
+int tq_ln_qdq_bf16(const void* x_ctr_bf16, tq_qspec in_q, int64_t in_q_params, const float* gamma_q,
+                   const float* beta, float eps, tq_qspec out_q, int64_t out_q_params, void* out_ctr_bf16,
+                   float* out_f32, int64_t M, int32_t D, void* stream) {
+    tq::fused::LnArgs a = {};
+    if (x_ctr_bf16 == nullptr) return TQ_EINVAL;
+    if (int e = tq::check_qspec(in_q)) return e;
+    a.x_ctr = reinterpret_cast<const __nv_bfloat16*>(x_ctr_bf16);
+    a.in_q.q = in_q;
+    a.in_q.params = in_q_params;
+    a.gamma_q = gamma_q;
+    a.beta = beta;
+    a.eps = eps;
+    a.out_q.q = out_q;
+    a.out_q.params = out_q_params;
+    a.out_ctr = reinterpret_cast<__nv_bfloat16*>(out_ctr_bf16);
+    a.out_f32 = out_f32;
+    a.M = M;
+    a.D = D;
+    return ln_common(a, false, stream);
+}
+
+int tq_embed_ln_qdq_bf16(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int64_t T,
+                         const float* word_q, const float* type_q, const float* pos_q, tq_qspec e_tok,
+                         int64_t e_tok_params, tq_qspec e_pos, int64_t e_pos_params, const float* gamma_q,
+                         const float* beta, float eps, tq_qspec out_q, int64_t out_q_params, void* out_ctr_bf16,
+                         float* out_f32, int64_t M, int32_t D, void* stream) {
+    tq::fused::LnArgs a = {};
+    if (ids == nullptr || word_q == nullptr || type_q == nullptr || pos_q == nullptr || T < 1) return TQ_EINVAL;
+    if (int e = tq::check_qspec(e_tok)) return e;
+    if (int e = tq::check_qspec(e_pos)) return e;
+    a.ids = ids;
+    a.type_ids = type_ids;
+    a.pos_ids = pos_ids;
+    a.T = T;
+    a.word = word_q;
+    a.type_tab = type_q;
+    a.pos_tab = pos_q;
+    a.e_tok.q = e_tok;
+    a.e_tok.params = e_tok_params;
+    a.e_pos.q = e_pos;
+    a.e_pos.params = e_pos_params;
+    a.gamma_q = gamma_q;
+    a.beta = beta;
+    a.eps = eps;
+    a.out_q.q = out_q;
+    a.out_q.params = out_q_params;
+    a.out_ctr = reinterpret_cast<__nv_bfloat16*>(out_ctr_bf16);
+    a.out_f32 = out_f32;
+    a.M = M;
+    a.D = D;
+    return ln_common(a, true, stream);
+}
+
+}  // extern "C"

@@ -35,7 +35,7 @@ struct Cfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN > 192) ? 3 : (BN > 128 ? 4 : (BN > 64 ? 5 : 6));
-    static constexpr int kParamBytes = 5 * BN * 4;                  // colscale | bias | qscale | qzp | qrcp
+    static constexpr int kParamBytes = 8 * BN * 4;    // colscale | bias | qscale | qzp | qrcp | q2scale | q2zp | q2rcp
     static constexpr int kStoreBytes = 8 * 4096;                    // per-epilogue-warp 32x32 fp32 transpose tile
     static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kParamBytes + kBarBytes + 1024;
@@ -182,6 +182,12 @@ struct EpiArgs {
     int act_fn;
     float* tile_minmax;     // optional calibration side reduction (ordered-int encoded, 2 words)
     long long* trace;       // optional: clock64 timeline of CTA 0 (16 slots), for tools/trace_linear.py
+    // residual branch (attention-output / FFN-output blocks of the encoder, reference
+    // models/quantized_bert.py:238-245, 264-277):  y = Q2( dequant(Q1(linear)) + res_scale * res_ctr )
+    const __nv_bfloat16* res_ctr;   // [M, N] centred integer grid of the residual input, or null
+    tq_qspec res_q;                 // its (per-tensor) quantizer
+    tq_qspec out2_q;                // quantizer of the residual sum
+    int64_t out2_params;            // 1 or N
 };
 
 #define TQ_TRACE(slot) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[slot] = clock64(); } while (0)
@@ -302,7 +308,18 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         float* qscale = params + 2 * BN;
         float* qzp = params + 3 * BN;
         float* qrcp = params + 4 * BN;
+        float* q2scale = params + 5 * BN;
+        float* q2zp = params + 6 * BN;
+        float* q2rcp = params + 7 * BN;
         const bool has_q = ep.out_q.delta != nullptr;
+        const bool has_res = ep.res_ctr != nullptr;
+        float q2lo = 0.0f, q2hi = 0.0f, res_scale = 1.0f;
+        if (has_res) {
+            grid_of(ep.out2_q, q2lo, q2hi);
+            float lo, hi;
+            grid_of(ep.res_q, lo, hi);
+            res_scale = resolve(ep.res_q, 0, lo, hi).scale;
+        }
         float qlo = 0.0f, qhi = 0.0f;
         if (has_q) grid_of(ep.out_q, qlo, qhi);
         float a_scale = 1.0f;
@@ -342,6 +359,19 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 qscale[j] = qs;
                 qzp[j] = qz;
                 qrcp[j] = qr;
+                if (has_res) {
+                    float s2 = 1.0f, z2 = 0.0f, r2 = 1.0f;
+                    if (n < N) {
+                        const QP p2 = resolve(ep.out2_q, ep.out2_params > 1 ? n : 0, q2lo, q2hi);
+                        s2 = p2.scale;
+                        z2 = p2.zp;
+                        r2 = p2.rcp;
+                        need_exact |= p2.exact;
+                    }
+                    q2scale[j] = s2;
+                    q2zp[j] = z2;
+                    q2rcp[j] = r2;
+                }
             }
             // barrier + OR-reduction over the 256 epilogue threads (named barrier 1)
             int exact;
@@ -410,6 +440,36 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             run_min = fminf(run_min, o[j]);
                             run_max = fmaxf(run_max, o[j]);
                         }
+                    }
+                }
+                if (has_res) {
+                    // residual rows: coalesced 32 B pieces -> swizzled smem -> one row per lane
+                    uint4* s2 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = i * 16 + (lane >> 1), ch = lane & 1;
+                        const int64_t grow = grow0 + r, gcol = n0 + c0 + ch * 8;
+                        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                        if (grow < M && gcol < N) val = *reinterpret_cast<const uint4*>(ep.res_ctr + grow * N + gcol);
+                        s2[r * 2 + (ch ^ ((r >> 2) & 1))] = val;
+                    }
+                    __syncwarp();
+                    uint32_t rw[8];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint4 t4 = s2[lane * 2 + (c ^ ((lane >> 2) & 1))];
+                        rw[4 * c] = t4.x; rw[4 * c + 1] = t4.y; rw[4 * c + 2] = t4.z; rw[4 * c + 3] = t4.w;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t pair = rw[j >> 1];
+                        const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));   // bf16 -> fp32
+                        const float sum = __fadd_rn(o[j], __fmul_rn(res_scale, rc));
+                        const QP p2{q2scale[c0 + j], q2zp[c0 + j], q2lo, q2hi, q2rcp[c0 + j], exact};
+                        const float ctr = __fsub_rn(quant_int(sum, p2), p2.zp);
+                        v[j] = __float_as_uint(ctr);
+                        o[j] = __fmul_rn(p2.scale, ctr);
                     }
                 }
                 // ---- coalesced stores: 32 x 16 transpose through this warp's private smem tile ----
@@ -585,11 +645,19 @@ extern "C" {
 
 size_t tq_linear_workspace_bytes(int64_t, int64_t, int64_t) { return 256; }
 
-int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, float* y,
+static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, float* y,
                        void* y_ctr_bf16, int64_t M, int64_t N, int64_t K, int32_t k_split, tq_qspec a_q,
                        tq_qspec w_q, int64_t w_q_params, int32_t act_fn, tq_qspec out_q, int64_t out_q_params,
+                       const void* res_ctr_bf16, tq_qspec res_q, tq_qspec out2_q, int64_t out2_q_params,
                        float* tile_minmax, void* ws, size_t ws_bytes, void* stream) {
     using namespace tq::gemm;
+    if (res_ctr_bf16 != nullptr) {
+        if (out_q.delta == nullptr || res_q.delta == nullptr) return TQ_EINVAL;
+        if (int e = tq::check_qspec(out2_q)) return e;
+        if (int e = tq::check_qspec(res_q)) return e;
+        if (out2_q_params != 1 && out2_q_params != N) return TQ_EINVAL;
+        if (!tq::aligned16(res_ctr_bf16)) return TQ_EALIGN;
+    }
     if (a_ctr_bf16 == nullptr || w_ctr_bf16 == nullptr || (y == nullptr && y_ctr_bf16 == nullptr)) return TQ_EINVAL;
     if (M < 1 || N < 1 || K < 1 || (k_split != 1 && k_split != 3)) return TQ_EINVAL;
     if (K % BK != 0 || N % 8 != 0) return TQ_EUNSUPPORTED;
@@ -613,6 +681,10 @@ int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
     ep.act_fn = act_fn;
     ep.tile_minmax = tile_minmax;
     ep.trace = (ws != nullptr && ws_bytes >= 16 * sizeof(long long)) ? reinterpret_cast<long long*>(ws) : nullptr;
+    ep.res_ctr = reinterpret_cast<const __nv_bfloat16*>(res_ctr_bf16);
+    ep.res_q = res_q;
+    ep.out2_q = out2_q;
+    ep.out2_params = out2_q_params;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pick_bn(M, N)) {
         case 256: return launch<256>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
@@ -620,6 +692,26 @@ int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
         case 128: return launch<128>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
         default: return launch<64>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
     }
+}
+
+int tq_linear_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, float* y,
+                       void* y_ctr_bf16, int64_t M, int64_t N, int64_t K, int32_t k_split, tq_qspec a_q,
+                       tq_qspec w_q, int64_t w_q_params, int32_t act_fn, tq_qspec out_q, int64_t out_q_params,
+                       float* tile_minmax, void* ws, size_t ws_bytes, void* stream) {
+    tq_qspec none;
+    none.delta = nullptr; none.zero_float = nullptr; none.is_signed = nullptr;
+    none.n_bits = 8; none.log_domain = 0; none.eps = 1e-8f;
+    return linear_impl(a_ctr_bf16, w_ctr_bf16, bias, y, y_ctr_bf16, M, N, K, k_split, a_q, w_q, w_q_params, act_fn,
+                       out_q, out_q_params, nullptr, none, none, 1, tile_minmax, ws, ws_bytes, stream);
+}
+
+int tq_linear_res_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, float* y,
+                           void* y_ctr_bf16, int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q,
+                           int64_t w_q_params, tq_qspec out_q, int64_t out_q_params, const void* res_ctr_bf16,
+                           tq_qspec res_q, tq_qspec out2_q, int64_t out2_q_params, void* stream) {
+    if (res_ctr_bf16 == nullptr) return TQ_EINVAL;
+    return linear_impl(a_ctr_bf16, w_ctr_bf16, bias, y, y_ctr_bf16, M, N, K, 1, a_q, w_q, w_q_params, 0, out_q,
+                       out_q_params, res_ctr_bf16, res_q, out2_q, out2_q_params, nullptr, nullptr, 0, stream);
 }
 
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream) {

@@ -1,0 +1,226 @@
+"""Fused fixed-range inference engine for the quantized BERT encoder.
+
+Built FROM a calibrated ``engine.bert.QuantBertForSequenceClassification`` (ranges fixed, eval
+mode): it reads the fake-quantized weights and the per-site quantizer buffers of that model and
+runs the same forward -- the same 161 quantizer sites in the same order -- as 7 kernels per encoder
+layer, every tensor between them carried as the centred integer grid in bf16 (2 B / element):
+
+    embeddings : tq_embed_ln_qdq_bf16                       (3 sites)
+    per layer  : tq_linear_qdq_bf16   fused Q|K|V GEMM, per-column output quantizers      (3 sites)
+                 tq_attention_qdq_bf16 scores / probs / context                            (3 sites)
+                 tq_linear_res_qdq_bf16 attention-output dense + residual                   (2 sites)
+                 tq_ln_qdq_bf16                                                             (1 site)
+                 tq_linear_qdq_bf16   FFN-in + GELU                                          (1 site)
+                 tq_linear_res_qdq_bf16 FFN-out dense + residual                            (2 sites)
+                 tq_ln_qdq_bf16                                                             (1 site)
+    head       : pooler (tanh) and classifier through tq_linear_qdq_bf16                   (2 sites)
+
+The module-level path (quantization.* classes, one kernel per site + library ops) stays the
+reference-facing API and the calibration path; this engine is what the throughput benchmark runs.
+Supported: per-tensor quantizers with n_bits <= 8 at every site, seq 128, head_dim 64, hidden % 256
+== 0.  Anything else raises ``UnsupportedByEngine`` and callers keep using the module path.
+"""
+import torch
+from torch import nn
+
+import tq_native
+from quantization.base_quantized_classes import FP32Acts
+
+
+class UnsupportedByEngine(RuntimeError):
+    pass
+
+
+def _mgr(module):
+    m = module.activation_quantizer
+    if isinstance(m, FP32Acts) or not module._quant_a:
+        raise UnsupportedByEngine('every activation site must be quantized')
+    q = m.quantizer
+    if not q.is_initialized or q.n_bits > 8 or q.delta.numel() != 1 or q.axis is not None:
+        raise UnsupportedByEngine('engine needs initialised per-tensor <= 8-bit activation quantizers')
+    return q
+
+
+class _Site:
+    """per-tensor quantizer -> tq_qspec (keeps the buffers alive)"""
+
+    def __init__(self, quantizer):
+        self.q = quantizer
+        self.spec = quantizer._spec()
+
+
+class _ColSite:
+    """several per-tensor quantizers side by side along the output columns -> one [N] spec"""
+
+    def __init__(self, quantizers, widths):
+        ops = tq_native.ops()
+        sym = [q.symmetric for q in quantizers]
+        if any(sym) and not all(sym):
+            raise UnsupportedByEngine('mixed symmetric / asymmetric quantizers in one fused GEMM')
+        self.delta = torch.cat([q.delta.reshape(1).expand(w) for q, w in zip(quantizers, widths)]).contiguous()
+        q0 = quantizers[0]
+        if all(sym):
+            flags = [bool(q.signed) for q in quantizers]
+            if len(set(flags)) != 1:
+                raise UnsupportedByEngine('symmetric quantizers with different signedness in one fused GEMM')
+            self.zero_float = None
+            self.spec = ops.spec(self.delta, None, q0._signed, q0.n_bits, q0.scale_domain == 'log', q0.eps)
+        else:
+            self.zero_float = torch.cat([q.zero_float.reshape(1).expand(w)
+                                         for q, w in zip(quantizers, widths)]).contiguous()
+            self.spec = ops.spec(self.delta, self.zero_float, None, q0.n_bits, q0.scale_domain == 'log', q0.eps)
+        if len({(q.n_bits, q.scale_domain, q.eps) for q in quantizers}) != 1:
+            raise UnsupportedByEngine('fused sites must share n_bits / scale_domain / eps')
+        self.n = int(sum(widths))
+
+
+class _Weight:
+    """bf16 integer grid of one or more fake-quantized Linear weights stacked along N"""
+
+    def __init__(self, layers, pad_to=None):
+        ops = tq_native.ops()
+        grids, deltas, biases = [], [], []
+        q0 = None
+        for lin in layers:
+            if not lin._quant_w:
+                raise UnsupportedByEngine('weights must be quantized')
+            qz = lin.weight_quantizer.quantizer
+            if not qz.is_initialized or qz.n_bits > 8 or not qz.symmetric or qz.delta.numel() != 1:
+                raise UnsupportedByEngine('engine needs per-tensor symmetric <= 8-bit weight quantizers')
+            q0 = q0 or qz
+            if bool(qz.signed) != bool(q0.signed) or qz.n_bits != q0.n_bits:
+                raise UnsupportedByEngine('stacked weights must share the integer grid')
+            w = lin.weight.detach()
+            _, g = ops.quant_int(w, qz._spec(), want_f32=False, want_bf16=True)
+            grids.append(g)
+            deltas.append(qz.delta.reshape(1).expand(w.shape[0]))
+            biases.append(lin.bias.detach() if lin.bias is not None else torch.zeros(w.shape[0], device=w.device))
+        self.grid = torch.cat(grids).contiguous()
+        self.delta = torch.cat(deltas).contiguous()
+        self.bias = torch.cat(biases).contiguous().float()
+        if pad_to is not None and self.grid.shape[0] < pad_to:
+            n, k = self.grid.shape
+            self.grid = torch.cat([self.grid, torch.zeros(pad_to - n, k, dtype=self.grid.dtype, device=self.grid.device)])
+            self.delta = torch.cat([self.delta, self.delta[-1:].expand(pad_to - n)]).contiguous()
+            self.bias = torch.cat([self.bias, torch.zeros(pad_to - n, device=self.bias.device)])
+        self.N, self.K = self.grid.shape
+        self._signed = q0._signed
+        self.spec = ops.spec(self.delta, None, self._signed, q0.n_bits, q0.scale_domain == 'log', q0.eps)
+
+
+def _ln_params(ln):
+    """(fake-quantized gamma, beta, eps) of a QuantLayerNorm in eval mode"""
+    w, b = ln.get_params()
+    return w.detach().float().contiguous(), b.detach().float().contiguous(), float(ln.eps)
+
+
+class FusedBertEngine:
+    def __init__(self, model, batch, seq):
+        if model.training:
+            raise UnsupportedByEngine('engine runs the eval forward')
+        cfg = model.config
+        self.B, self.T, self.D, self.H = batch, seq, cfg.hidden_size, cfg.num_attention_heads
+        self.hd = self.D // self.H
+        if seq != 128 or self.hd != 64 or self.D % 256 != 0:
+            raise UnsupportedByEngine('engine supports seq 128, head_dim 64, hidden % 256 == 0')
+        self.num_labels = cfg.num_labels
+        self.ops = tq_native.ops()
+        dev = next(model.parameters()).device
+        self.dev = dev
+        E = model.embeddings
+        if E.roberta_positions:
+            raise UnsupportedByEngine('RoBERTa position ids: use the module path')
+        with torch.no_grad():
+            self.word_q = E.word.get_params()[0].detach().float().contiguous()
+            self.pos_q = E.position.get_params()[0].detach().float().contiguous()
+            self.type_q = E.token_type.get_params()[0].detach().float().contiguous()
+            self.e_tok, self.e_pos = _Site(_mgr(E.e_tok)), _Site(_mgr(E.e_pos))
+            self.e_gamma, self.e_beta, self.e_eps = _ln_params(E.norm)
+            self.e_out = _Site(_mgr(E.norm))
+            self.layers = []
+            for L in model.layers:
+                d = {}
+                d['wqkv'] = _Weight([L.query, L.key, L.value])
+                d['qkv_out'] = _ColSite([_mgr(L.query), _mgr(L.key), _mgr(L.value)], [self.D] * 3)
+                d['q'], d['k'], d['v'] = _Site(_mgr(L.query)), _Site(_mgr(L.key)), _Site(_mgr(L.value))
+                d['s'], d['p'], d['c'] = _Site(_mgr(L.s)), _Site(_mgr(L.p)), _Site(_mgr(L.c))
+                d['wg'], d['g'], d['u'] = _Weight([L.g]), _Site(_mgr(L.g)), _Site(_mgr(L.u))
+                d['ln1'] = _ln_params(L.x)
+                d['x'] = _Site(_mgr(L.x))
+                if not isinstance(L.ffn_in.activation_function, nn.GELU):
+                    raise UnsupportedByEngine('FFN activation must be nn.GELU')
+                d['wf'], d['f'] = _Weight([L.ffn_in]), _Site(_mgr(L.ffn_in))
+                d['wh'], d['h'], d['y'] = _Weight([L.h]), _Site(_mgr(L.h)), _Site(_mgr(L.y))
+                d['ln2'] = _ln_params(L.z)
+                d['z'] = _Site(_mgr(L.z))
+                self.layers.append(d)
+            self.w_pool, self.pool_out = _Weight([model.pooler]), _Site(_mgr(model.pooler))
+            self.w_cls, self.cls_out = _Weight([model.classifier], pad_to=8), _Site(_mgr(model.classifier))
+        M, D = batch * seq, self.D
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.x = torch.empty(M, D, **bf)
+        self.qkv = torch.empty(M, 3 * D, **bf)
+        self.c = torch.empty(M, D, **bf)
+        self.u = torch.empty(M, D, **bf)
+        self.a = torch.empty(M, D, **bf)
+        self.f = torch.empty(M, cfg.intermediate_size, **bf)
+        self.yb = torch.empty(M, D, **bf)
+        self.M = M
+
+    def _linear(self, a_ctr, a_site, w, act, out_spec, out_params, out_ctr=None, want_f32=False, M=None):
+        M = a_ctr.shape[0] if M is None else M
+        ops = self.ops
+        dev = a_ctr.device
+        y = torch.empty(M, w.N, dtype=torch.float32, device=dev) if want_f32 else None
+        yc = out_ctr if out_ctr is not None else (None if want_f32 else torch.empty(M, w.N, dtype=torch.bfloat16, device=dev))
+        null = tq_native.QSpec(None, None, None, 8, 0, 1e-8)
+        ops._run('linear_qdq', 2 * M * w.N * w.K, 1, ops.lib.tq_linear_qdq_bf16, a_ctr.data_ptr(), w.grid.data_ptr(),
+                 w.bias.data_ptr(), tq_native._ptr(y), tq_native._ptr(yc), M, w.N, w.K, 1, a_site.spec, w.spec, w.N,
+                 int(act), out_spec if out_spec is not None else null, int(out_params), None, None, 0,
+                 tq_native._stream())
+        return y, yc
+
+    @torch.no_grad()
+    def forward(self, input_ids, attention_mask=None, token_type_ids=None):
+        ops = self.ops
+        B, T, D, H = self.B, self.T, self.D, self.H
+        assert tuple(input_ids.shape) == (B, T)
+        mask = None
+        if attention_mask is not None:
+            mask = ((1.0 - attention_mask.to(torch.float32)) * -10000.0).contiguous()
+        ids = input_ids.reshape(-1).contiguous()
+        tt = token_type_ids.reshape(-1).contiguous() if token_type_ids is not None else None
+        x = self.x
+        ops.embed_ln_qdq(ids, tt, None, T, self.word_q, self.type_q, self.pos_q, self.e_tok.spec, 1,
+                         self.e_pos.spec, 1, self.e_gamma, self.e_beta, self.e_eps, self.e_out.spec, 1, out_ctr=x)
+        x_site = self.e_out
+        for d in self.layers:
+            self._linear(x, x_site, d['wqkv'], 0, d['qkv_out'].spec, d['qkv_out'].n, out_ctr=self.qkv)
+            ops.attention(self.qkv, B, T, H, self.hd, d['q'].spec, d['k'].spec, d['v'].spec, d['s'].spec,
+                          d['p'].spec, d['c'].spec, mask, out_ctr=self.c)
+            w = d['wg']
+            ops.linear_res(self.c, w.grid, w.bias, self.M, w.N, w.K, d['c'].spec, w.spec, w.N, d['g'].spec, 1,
+                           x, x_site.spec, d['u'].spec, 1, out_ctr=self.u)
+            g1, b1, e1 = d['ln1']
+            ops.ln_qdq(self.u, d['u'].spec, 1, g1, b1, e1, d['x'].spec, 1, out_ctr=self.a)
+            self._linear(self.a, d['x'], d['wf'], 1, d['f'].spec, 1, out_ctr=self.f)
+            w = d['wh']
+            ops.linear_res(self.f, w.grid, w.bias, self.M, w.N, w.K, d['f'].spec, w.spec, w.N, d['h'].spec, 1,
+                           self.a, d['x'].spec, d['y'].spec, 1, out_ctr=self.yb)
+            g2, b2, e2 = d['ln2']
+            ops.ln_qdq(self.yb, d['y'].spec, 1, g2, b2, e2, d['z'].spec, 1, out_ctr=x)
+            x_site = d['z']
+        first = x.view(B, T, D)[:, 0].contiguous()                       # pooler input: first token
+        _, pooled = self._linear(first, x_site, self.w_pool, 3, self.pool_out.spec, 1)
+        logits, _ = self._linear(pooled, self.pool_out, self.w_cls, 0, self.cls_out.spec, 1, want_f32=True)
+        logits = logits[:, :self.num_labels]
+        if self.num_labels == 1:
+            logits = torch.clamp(logits, 0.0, 5.0)
+        return logits
+
+    __call__ = forward
+
+    def hidden_states(self):
+        """dequantized output of the last encoder block of the most recent forward (for tests)"""
+        z = self.layers[-1]['z'].q
+        return (self.x.float() * z.scale.reshape(())).view(self.B, self.T, self.D)

@@ -74,6 +74,16 @@ SIGNATURES = {
                                           ctypes.c_void_p, _i64, _i64, _i64, _i32, QSpec, QSpec, _i64,
                                           _i32, QSpec, _i64, _c_f32p, ctypes.c_void_p,
                                           ctypes.c_size_t, ctypes.c_void_p]),
+    'tq_linear_res_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p, ctypes.c_void_p,
+                                              _i64, _i64, _i64, QSpec, QSpec, _i64, QSpec, _i64, ctypes.c_void_p,
+                                              QSpec, QSpec, _i64, ctypes.c_void_p]),
+    'tq_attention_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _i32, QSpec, QSpec,
+                                             QSpec, QSpec, QSpec, QSpec, _c_f32p, ctypes.c_void_p]),
+    'tq_ln_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, QSpec, _i64, _c_f32p, _c_f32p, ctypes.c_float, QSpec, _i64,
+                                      ctypes.c_void_p, _c_f32p, _i64, _i32, ctypes.c_void_p]),
+    'tq_embed_ln_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _i64, _c_f32p, _c_f32p,
+                                            _c_f32p, QSpec, _i64, QSpec, _i64, _c_f32p, _c_f32p, ctypes.c_float,
+                                            QSpec, _i64, ctypes.c_void_p, _c_f32p, _i64, _i32, ctypes.c_void_p]),
     'tq_split3_bf16': (ctypes.c_int, [_c_f32p, ctypes.c_void_p, _i64, _i64, ctypes.c_void_p]),
 }
 
@@ -285,6 +295,54 @@ class CudaOps:
                   int(act_fn), out_spec if out_spec is not None else null, int(out_params), _ptr(tile_minmax),
                   None, 0, _stream())
         return y, yc
+
+
+    # -- fused encoder blocks -----------------------------------------------------------------------
+    def linear_res(self, a_ctr, w_ctr, bias, M, N, K, a_spec, w_spec, w_params, out_spec, out_params,
+                   res_ctr, res_spec, out2_spec, out2_params, out_ctr=None, want_f32=False):
+        """tq_linear_res_qdq_bf16 -> (y fp32 | None, y_ctr bf16 [M, N])"""
+        _chk_cuda(a_ctr, w_ctr, bias, res_ctr)
+        dev = a_ctr.device
+        y = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
+        yc = out_ctr if out_ctr is not None else torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_res_qdq_bf16, a_ctr.data_ptr(),
+                  w_ctr.data_ptr(), _ptr(bias), _ptr(y), yc.data_ptr(), M, N, K, a_spec, w_spec, int(w_params),
+                  out_spec, int(out_params), res_ctr.data_ptr(), res_spec, out2_spec, int(out2_params), _stream())
+        return y, yc
+
+    def attention(self, qkv_ctr, B, T, H, head_dim, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec, mask=None,
+                  out_ctr=None):
+        """tq_attention_qdq_bf16: qkv_ctr [B*T, 3*H*hd] -> context grid [B*T, H*hd] (bf16)"""
+        _chk_cuda(qkv_ctr, mask)
+        c = out_ctr if out_ctr is not None else torch.empty(B * T, H * head_dim, dtype=torch.bfloat16,
+                                                            device=qkv_ctr.device)
+        work = 4 * B * H * T * T * head_dim
+        self._run('attention', work, 1, self.lib.tq_attention_qdq_bf16, qkv_ctr.data_ptr(), c.data_ptr(), B, T, H,
+                  head_dim, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec, _ptr(mask), _stream())
+        return c
+
+    def ln_qdq(self, x_ctr, in_spec, in_params, gamma_q, beta, eps, out_spec, out_params, out_ctr=None,
+               want_f32=False):
+        _chk_cuda(x_ctr, gamma_q, beta)
+        M, D = x_ctr.shape
+        o = out_ctr if out_ctr is not None else torch.empty(M, D, dtype=torch.bfloat16, device=x_ctr.device)
+        f = torch.empty(M, D, dtype=torch.float32, device=x_ctr.device) if want_f32 else None
+        self._run('ln_qdq', 4 * M * D, 1, self.lib.tq_ln_qdq_bf16, x_ctr.data_ptr(), in_spec, int(in_params),
+                  gamma_q.data_ptr(), beta.data_ptr(), float(eps), out_spec, int(out_params), o.data_ptr(), _ptr(f),
+                  M, D, _stream())
+        return o, f
+
+    def embed_ln_qdq(self, ids, type_ids, pos_ids, T, word_q, type_q, pos_q, e_tok, e_tok_params, e_pos,
+                     e_pos_params, gamma_q, beta, eps, out_spec, out_params, out_ctr=None, want_f32=False):
+        _chk_cuda(ids, word_q, type_q, pos_q, gamma_q, beta)
+        M, D = ids.numel(), word_q.shape[1]
+        o = out_ctr if out_ctr is not None else torch.empty(M, D, dtype=torch.bfloat16, device=ids.device)
+        f = torch.empty(M, D, dtype=torch.float32, device=ids.device) if want_f32 else None
+        self._run('embed_ln_qdq', 14 * M * D, 1, self.lib.tq_embed_ln_qdq_bf16, ids.data_ptr(), _ptr(type_ids),
+                  _ptr(pos_ids), int(T), word_q.data_ptr(), type_q.data_ptr(), pos_q.data_ptr(), e_tok,
+                  int(e_tok_params), e_pos, int(e_pos_params), gamma_q.data_ptr(), beta.data_ptr(), float(eps),
+                  out_spec, int(out_params), o.data_ptr(), _ptr(f), M, D, _stream())
+        return o, f
 
 
 _OPS = None
