@@ -125,9 +125,16 @@ def test_attention_kernel(use_mask):
     D = H * hd
     rs = np.random.RandomState(11)
     qkv = rs.randint(-40, 41, size=(B * Tn, 3 * D)).astype(np.float32)
-    sq, _, (dq, zq) = asym_spec(ops, -1.9, 2.0)
-    sk, _, (dk, zk) = asym_spec(ops, -2.1, 2.0)
-    sv, _, (dv, zv) = asym_spec(ops, -2.5, 2.4)
+    keep = []            # the specs hold raw device pointers: keep their tensors alive
+
+    def spec(lo, hi):
+        sp_, k_, dz = asym_spec(ops, lo, hi)
+        keep.append(k_)
+        return sp_, dz
+
+    sq, (dq, zq) = spec(-1.9, 2.0)
+    sk, (dk, zk) = spec(-2.1, 2.0)
+    sv, (dv, zv) = spec(-2.5, 2.4)
     fq, fk, fv = (np.float32(O.scale_of(d)) for d in (dq, dk, dv))
     mask = None
     if use_mask:
@@ -140,17 +147,17 @@ def test_attention_kernel(use_mask):
     v = qkv[:, 2 * D:].reshape(B, Tn, H, hd).transpose(0, 2, 1, 3)
     s_int = np.einsum('bhqd,bhkd->bhqk', q.astype(np.float64), k.astype(np.float64)).astype(np.float32)
     scores = (s_int * np.float32(fq * fk)).astype(np.float32)
-    ss, _, (ds, zs) = asym_spec(ops, float(scores.min()), float(scores.max()))
+    ss, (ds, zs) = spec(float(scores.min()), float(scores.max()))
     t = O.qdq_asym(scores, ds, zs, 8)
     t = (t * np.float32(1.0 / math.sqrt(hd))).astype(np.float32)
     if mask is not None:
         t = (t + mask[:, None, None, :]).astype(np.float32)
     probs = torch.softmax(torch.from_numpy(t), dim=-1).numpy()
-    sp, _, (dp, zp) = asym_spec(ops, 0.0, float(probs.max()))
+    sp, (dp, zp) = spec(0.0, float(probs.max()))
     p_int = O.qdq_asym(probs, dp, zp, 8, return_int=True) - O.asym_zero_point(zp, 8)
     o_int = np.einsum('bhqk,bhkd->bhqd', p_int.astype(np.float64), v.astype(np.float64)).astype(np.float32)
     ctx = (o_int * np.float32(np.float32(O.scale_of(dp)) * fv)).astype(np.float32)
-    sc, _, (dc, zc) = asym_spec(ops, float(ctx.min()), float(ctx.max()))
+    sc, (dc, zc) = spec(float(ctx.min()), float(ctx.max()))
     c_int = O.qdq_asym(ctx, dc, zc, 8, return_int=True) - O.asym_zero_point(zc, 8)
     ref = c_int.transpose(0, 2, 1, 3).reshape(B * Tn, D)
     out = ops.attention(T_(qkv).to(torch.bfloat16), B, Tn, H, hd, sq, sk, sv, ss, sp, sc,
@@ -195,9 +202,32 @@ def test_engine_matches_module_path(n_bits, use_mask):
         model.fix_ranges()
         ref_logits = model(ids[2], mask)
         ref_hidden = model.encode(ids[2], mask)
+    # per-site outputs of the module path (hooks) vs the engine's buffers, in execution order
+    taps = {}
+    hooks = []
+
+    def tap(name, mod):
+        hooks.append(mod.register_forward_hook(lambda m, i, o, name=name: taps.__setitem__(name, o.detach().clone())))
+
+    tap('emb', model.embeddings.norm)
+    for li, L in enumerate(model.layers):
+        for nm in ('query', 'key', 'value', 'c', 'u', 'x', 'ffn_in', 'y', 'z'):
+            tap(f'{li}.{nm}', getattr(L, nm))
+    with torch.no_grad():
+        model(ids[2], mask)
+    for h_ in hooks:
+        h_.remove()
     eng = FusedBertEngine(model, B, Tn)
-    logits = eng(ids[2], mask)
+    trace = {}
+    logits = eng(ids[2], mask, trace=trace)
     torch.cuda.synchronize()
+    report = []
+    for name, ref_t in taps.items():
+        got = trace[name]
+        d = ((got - ref_t.reshape(got.shape)).abs() / trace[name + '.step']).cpu().numpy()
+        report.append((name, float(d.max()), float((d > 0.5).mean())))
+    bad = [r for r in report if r[1] > 6.5 or r[2] > 0.05]
+    assert not bad, f'first diverging sites (name, max steps, frac differing): {bad[:4]}\nall: {report}'
     cls_step = float(model.classifier.activation_quantizer.quantizer.scale)
     assert (logits - ref_logits).abs().max().item() <= 3 * cls_step + 1e-6
     z = model.layers[-1].z.activation_quantizer.quantizer

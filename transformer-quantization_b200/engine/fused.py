@@ -181,8 +181,18 @@ class FusedBertEngine:
         return y, yc
 
     @torch.no_grad()
-    def forward(self, input_ids, attention_mask=None, token_type_ids=None):
+    def forward(self, input_ids, attention_mask=None, token_type_ids=None, trace=None):
+        """``trace`` (tests): dict that receives the dequantized output of every block site, under the
+        names of the module path, plus ``<name>.step`` = its quantization step."""
         ops = self.ops
+
+        def rec(name, ctr, site, cols=None):
+            if trace is not None:
+                t = ctr if cols is None else ctr[:, cols[0]:cols[1]]
+                sc = site.q.scale.reshape(())
+                trace[name] = (t.float() * sc).view(self.B, self.T, -1).clone()
+                trace[name + '.step'] = float(sc)
+
         B, T, D, H = self.B, self.T, self.D, self.H
         assert tuple(input_ids.shape) == (B, T)
         mask = None
@@ -194,22 +204,32 @@ class FusedBertEngine:
         ops.embed_ln_qdq(ids, tt, None, T, self.word_q, self.type_q, self.pos_q, self.e_tok.spec, 1,
                          self.e_pos.spec, 1, self.e_gamma, self.e_beta, self.e_eps, self.e_out.spec, 1, out_ctr=x)
         x_site = self.e_out
-        for d in self.layers:
+        rec('emb', x, x_site)
+        for li, d in enumerate(self.layers):
             self._linear(x, x_site, d['wqkv'], 0, d['qkv_out'].spec, d['qkv_out'].n, out_ctr=self.qkv)
+            rec(f'{li}.query', self.qkv, d['q'], (0, D))
+            rec(f'{li}.key', self.qkv, d['k'], (D, 2 * D))
+            rec(f'{li}.value', self.qkv, d['v'], (2 * D, 3 * D))
             ops.attention(self.qkv, B, T, H, self.hd, d['q'].spec, d['k'].spec, d['v'].spec, d['s'].spec,
                           d['p'].spec, d['c'].spec, mask, out_ctr=self.c)
+            rec(f'{li}.c', self.c, d['c'])
             w = d['wg']
             ops.linear_res(self.c, w.grid, w.bias, self.M, w.N, w.K, d['c'].spec, w.spec, w.N, d['g'].spec, 1,
                            x, x_site.spec, d['u'].spec, 1, out_ctr=self.u)
             g1, b1, e1 = d['ln1']
+            rec(f'{li}.u', self.u, d['u'])
             ops.ln_qdq(self.u, d['u'].spec, 1, g1, b1, e1, d['x'].spec, 1, out_ctr=self.a)
+            rec(f'{li}.x', self.a, d['x'])
             self._linear(self.a, d['x'], d['wf'], 1, d['f'].spec, 1, out_ctr=self.f)
+            rec(f'{li}.ffn_in', self.f, d['f'])
             w = d['wh']
             ops.linear_res(self.f, w.grid, w.bias, self.M, w.N, w.K, d['f'].spec, w.spec, w.N, d['h'].spec, 1,
                            self.a, d['x'].spec, d['y'].spec, 1, out_ctr=self.yb)
             g2, b2, e2 = d['ln2']
+            rec(f'{li}.y', self.yb, d['y'])
             ops.ln_qdq(self.yb, d['y'].spec, 1, g2, b2, e2, d['z'].spec, 1, out_ctr=x)
             x_site = d['z']
+            rec(f'{li}.z', x, x_site)
         first = x.view(B, T, D)[:, 0].contiguous()                       # pooler input: first token
         _, pooled = self._linear(first, x_site, self.w_pool, 3, self.pool_out.spec, 1)
         logits, _ = self._linear(pooled, self.pool_out, self.w_cls, 0, self.cls_out.spec, 1, want_f32=True)
