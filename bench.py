@@ -300,7 +300,9 @@ def run_ours(args):
         with torch.cuda.graph(graph):
             static_logits = forward(static_ids, mask_dev)
         launches_per_step = ops.launches - l0
-        module_logits = model(ids_dev, mask_dev)
+        graph.replay()
+        torch.cuda.synchronize()
+        module_logits = model(ids_dev, mask_dev)       # one kernel per site: cross-check of the engine
         engine_vs_module = float((static_logits - module_logits).abs().max())
         logits_host = torch.empty(static_logits.shape, dtype=static_logits.dtype).pin_memory()
 

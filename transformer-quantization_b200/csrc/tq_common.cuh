@@ -68,8 +68,13 @@ __device__ __forceinline__ QP resolve(const tq_qspec& q, int64_t i, float lo, fl
 // clamped to the grid edge (<= 2^16) no matter how they round, and inf - inf must not appear.
 // Verified bit-for-bit against __fdiv_rn on the GPU by tq_selftest_div (tests/test_gpu_parity.py).
 // This keeps the XU pipe (MUFU.RCP, 16 lanes/SM) out of the per-element path.
-__device__ __forceinline__ float div_rn(float x, const QP& p) {
-    if (p.exact) return __fdiv_rn(x, p.scale);
+//
+// FAST is a COMPILE-TIME switch: a per-element run-time test of p.exact puts a branch (BSSY/BSYNC)
+// between the independent element chains and stops ptxas from interleaving them (measured: 4-5x
+// slower epilogues).  Kernels evaluate `p.exact` once (it is uniform) and pick the instantiation.
+template <bool FAST>
+__device__ __forceinline__ float div_rn_t(float x, const QP& p) {
+    if (!FAST) return __fdiv_rn(x, p.scale);
     const float q0 = __fmul_rn(x, p.rcp);
     const float e0 = __fmaf_rn(-q0, p.scale, x);
     const float q1 = __fmaf_rn(e0, p.rcp, q0);
@@ -85,8 +90,9 @@ __device__ __forceinline__ float rint_even(float v) {
 }
 
 // clamp(rint(x / scale) + zp, lo, hi)  -- quantizers.py:184-185.  NaN propagates (torch.clamp).
-__device__ __forceinline__ float quant_int(float x, const QP& p) {
-    const float d = div_rn(x, p);
+template <bool FAST>
+__device__ __forceinline__ float quant_int_t(float x, const QP& p) {
+    const float d = div_rn_t<FAST>(x, p);
     // |d| >= 2^22: rint_even would return a non-integer for 2^22 <= |d| < 2^23 -- irrelevant, the
     // clamp maps all of them to the grid edge
     float q = __fadd_rn(rint_even(d), p.zp);
@@ -97,6 +103,14 @@ __device__ __forceinline__ float quant_int(float x, const QP& p) {
 // scale * (x_int - zp)  -- quantizers.py:209
 __device__ __forceinline__ float dequant(float xi, const QP& p) {
     return __fmul_rn(p.scale, __fsub_rn(xi, p.zp));
+}
+template <bool FAST>
+__device__ __forceinline__ float qdq_t(float x, const QP& p) { return dequant(quant_int_t<FAST>(x, p), p); }
+
+// run-time dispatch (cold paths only: scalar tails, generic fallbacks)
+__device__ __forceinline__ float div_rn(float x, const QP& p) { return p.exact ? div_rn_t<false>(x, p) : div_rn_t<true>(x, p); }
+__device__ __forceinline__ float quant_int(float x, const QP& p) {
+    return p.exact ? quant_int_t<false>(x, p) : quant_int_t<true>(x, p);
 }
 __device__ __forceinline__ float qdq(float x, const QP& p) { return dequant(quant_int(x, p), p); }
 

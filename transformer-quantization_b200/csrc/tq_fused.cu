@@ -42,6 +42,9 @@ struct ColQ {              // quantizer with 1 or C parameter slots
         p0 = resolve(q, 0, lo, hi);
     }
     __device__ __forceinline__ QP at(int64_t c) const { return params > 1 ? resolve(q, c, lo, hi) : p0; }
+    // PT (compile time): the caller has established params == 1 -> no per-element branch
+    template <bool PT>
+    __device__ __forceinline__ QP get(int64_t c) const { return PT ? p0 : at(c); }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -73,18 +76,12 @@ struct LnArgs {
     int32_t D;
 };
 
-template <bool EMBED>
-__global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
-    if (row >= a.M) return;
+template <bool EMBED, bool FAST>
+__device__ __forceinline__ void ln_row(const LnArgs& a, int64_t row, int lane, ColQ& in_q, ColQ& e_tok, ColQ& e_pos,
+                                       ColQ& out_q) {
     const int iters = a.D >> 8;                       // 8 elements per lane per iteration
     float v[kLnMaxIter][8];
-    ColQ in_q = a.in_q, e_tok = a.e_tok, e_pos = a.e_pos, out_q = a.out_q;
-    out_q.init();
     if (EMBED) {
-        e_tok.init();
-        e_pos.init();
         const int64_t id = a.ids[row];
         const int64_t tt = a.type_ids != nullptr ? a.type_ids[row] : 0;
         const int64_t pp = a.pos_ids != nullptr ? a.pos_ids[row] : (row % a.T);
@@ -101,14 +98,13 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
                 const float ps[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float e = qdq(__fadd_rn(ws[j], ts[j]), e_tok.at(c + j));      // quantized_bert.py:78-79
-                    e = qdq(__fadd_rn(e, ps[j]), e_pos.at(c + j));                // :83-84
+                    float e = qdq_t<FAST>(__fadd_rn(ws[j], ts[j]), e_tok.get<FAST>(c + j));      // quantized_bert.py:78-79
+                    e = qdq_t<FAST>(__fadd_rn(e, ps[j]), e_pos.get<FAST>(c + j));                // :83-84
                     v[it][j] = e;
                 }
             }
         }
     } else {
-        in_q.init();
 #pragma unroll
         for (int it = 0; it < kLnMaxIter; ++it) {
             if (it < iters) {
@@ -117,8 +113,8 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
                 const uint32_t pr[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    v[it][2 * j] = __fmul_rn(in_q.at(c + 2 * j).scale, bf16_lo(pr[j]));          // scale * ctr
-                    v[it][2 * j + 1] = __fmul_rn(in_q.at(c + 2 * j + 1).scale, bf16_hi(pr[j]));
+                    v[it][2 * j] = __fmul_rn(in_q.get<FAST>(c + 2 * j).scale, bf16_lo(pr[j]));          // scale * ctr
+                    v[it][2 * j + 1] = __fmul_rn(in_q.get<FAST>(c + 2 * j + 1).scale, bf16_hi(pr[j]));
                 }
             }
         }
@@ -156,8 +152,8 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float y = (v[it][j] - mean) * rstd * gs[j] + bs[j];
-                const QP p = out_q.at(c + j);
-                ctr[j] = __fsub_rn(quant_int(y, p), p.zp);
+                const QP p = out_q.get<FAST>(c + j);
+                ctr[j] = __fsub_rn(quant_int_t<FAST>(y, p), p.zp);
                 deq[j] = __fmul_rn(p.scale, ctr[j]);
             }
             uint4 o;
@@ -173,6 +169,28 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
             }
         }
     }
+}
+
+template <bool EMBED>
+__global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
+    if (row >= a.M) return;
+    ColQ in_q = a.in_q, e_tok = a.e_tok, e_pos = a.e_pos, out_q = a.out_q;
+    out_q.init();
+    // FAST (division-free quotient) only when every quantizer involved is per-tensor and inside
+    // div_rn's proven domain; otherwise the IEEE-divide instantiation (always valid)
+    bool fast = out_q.params == 1 && !out_q.p0.exact;
+    if (EMBED) {
+        e_tok.init();
+        e_pos.init();
+        fast = fast && e_tok.params == 1 && !e_tok.p0.exact && e_pos.params == 1 && !e_pos.p0.exact;
+    } else {
+        in_q.init();
+        fast = fast && in_q.params == 1;
+    }
+    if (fast) ln_row<EMBED, true>(a, row, lane, in_q, e_tok, e_pos, out_q);
+    else ln_row<EMBED, false>(a, row, lane, in_q, e_tok, e_pos, out_q);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -279,6 +297,96 @@ __device__ __forceinline__ float scale_of(const tq_qspec& q) {
     return resolve(q, 0, lo, hi).scale;
 }
 
+// per-row work of the softmax / epilogue warps (one query row per thread)
+template <bool FAST>
+__device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const QP& qp, const QP& qc, float sqk,
+                                          float spv, uint32_t trow, int row, int quarter, int lane, int warp, int b,
+                                          int h, int32_t dmodel, const float* smask, unsigned char* pP, uint32_t bar_s,
+                                          uint32_t bar_p, uint32_t bar_o) {
+        mbar_wait(bar_s, 0);
+        tc_fence_after();
+        // pass 1: scores -> QDQ -> / sqrt(d) + mask, written back to TMEM; row max
+        float vmax = __int_as_float(0xff800000);
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float t = qdq_t<FAST>(__fmul_rn(__uint_as_float(v[j]), sqk), qs);       // quantized_bert.py:153-154
+                t = __fadd_rn(__fmul_rn(t, a.inv_sqrt_d), smask[c0 + j]);       // :190-194
+                vmax = fmaxf(vmax, t);
+                v[j] = __float_as_uint(t);
+            }
+            tmem_st16(trow + c0, v);
+        }
+        // pass 2: exp(t - max), row sum
+        float vsum = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float e = expf(__uint_as_float(v[j]) - vmax);
+                vsum += e;
+                v[j] = __float_as_uint(e);
+            }
+            tmem_st16(trow + c0, v);
+        }
+        // pass 3: probs -> QDQ -> centred integers into the swizzled K-major A tile
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c0, v);
+            float c[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float pr = __fdiv_rn(__uint_as_float(v[j]), vsum);          // softmax, :197
+                c[j] = __fsub_rn(quant_int_t<FAST>(pr, qp), qp.zp);                       // :198
+            }
+            const int halfk = c0 >> 6;                       // which 64-key swizzle span
+            const int ch0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this row piece
+            uint4* prow = reinterpret_cast<uint4*>(pP + halfk * 16384 + row * 128);
+            uint4 w0, w1;
+            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
+            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
+            prow[(ch0) ^ (row & 7)] = w0;
+            prow[(ch0 + 1) ^ (row & 7)] = w1;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
+        tc_fence_before();
+        mbar_arrive(bar_p);
+
+        // context: O * (s_p * s_v) -> QDQ -> centred bf16, coalesced through the (now free) P tile
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        uint4* stg = reinterpret_cast<uint4*>(pP + (warp - 2) * 4096);     // 32 rows x 128 B per warp
+#pragma unroll 1
+        for (int c0 = 0; c0 < AD; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + 128 + c0, v);
+            float c[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                c[j] = __fsub_rn(quant_int_t<FAST>(__fmul_rn(__uint_as_float(v[j]), spv), qc), qc.zp);   // :201-213
+            uint4 w0, w1;
+            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
+            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
+            const int ch0 = c0 >> 3;
+            stg[lane * 8 + ((ch0) ^ (lane & 7))] = w0;
+            stg[lane * 8 + ((ch0 + 1) ^ (lane & 7))] = w1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3), ch = lane & 7;
+            const uint4 val = stg[r * 8 + (ch ^ (r & 7))];
+            const int64_t grow = (int64_t)b * AT + quarter * 32 + r;
+            *reinterpret_cast<uint4*>(a.c_ctr + grow * dmodel + h * AD + ch * 8) = val;
+        }
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
     extern __shared__ unsigned char smem_dyn[];
@@ -366,88 +474,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
         const float sqk = scale_of(a.q_q) * scale_of(a.k_q);
         const float spv = qp.scale * scale_of(a.v_q);
 
-        mbar_wait(bar_s, 0);
-        tc_fence_after();
-        // pass 1: scores -> QDQ -> / sqrt(d) + mask, written back to TMEM; row max
-        float vmax = __int_as_float(0xff800000);
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float t = qdq(__fmul_rn(__uint_as_float(v[j]), sqk), qs);       // quantized_bert.py:153-154
-                t = __fadd_rn(__fmul_rn(t, a.inv_sqrt_d), smask[c0 + j]);       // :190-194
-                vmax = fmaxf(vmax, t);
-                v[j] = __float_as_uint(t);
-            }
-            tmem_st16(trow + c0, v);
-        }
-        // pass 2: exp(t - max), row sum
-        float vsum = 0.0f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float e = expf(__uint_as_float(v[j]) - vmax);
-                vsum += e;
-                v[j] = __float_as_uint(e);
-            }
-            tmem_st16(trow + c0, v);
-        }
-        // pass 3: probs -> QDQ -> centred integers into the swizzled K-major A tile
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
-            float c[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float pr = __fdiv_rn(__uint_as_float(v[j]), vsum);          // softmax, :197
-                c[j] = __fsub_rn(quant_int(pr, qp), qp.zp);                       // :198
-            }
-            const int halfk = c0 >> 6;                       // which 64-key swizzle span
-            const int ch0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this row piece
-            uint4* prow = reinterpret_cast<uint4*>(pP + halfk * 16384 + row * 128);
-            uint4 w0, w1;
-            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
-            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
-            prow[(ch0) ^ (row & 7)] = w0;
-            prow[(ch0 + 1) ^ (row & 7)] = w1;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
-        tc_fence_before();
-        mbar_arrive(bar_p);
-
-        // context: O * (s_p * s_v) -> QDQ -> centred bf16, coalesced through the (now free) P tile
-        mbar_wait(bar_o, 0);
-        tc_fence_after();
-        uint4* stg = reinterpret_cast<uint4*>(pP + (warp - 2) * 4096);     // 32 rows x 128 B per warp
-#pragma unroll 1
-        for (int c0 = 0; c0 < AD; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + 128 + c0, v);
-            float c[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                c[j] = __fsub_rn(quant_int(__fmul_rn(__uint_as_float(v[j]), spv), qc), qc.zp);   // :201-213
-            uint4 w0, w1;
-            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
-            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
-            const int ch0 = c0 >> 3;
-            stg[lane * 8 + ((ch0) ^ (lane & 7))] = w0;
-            stg[lane * 8 + ((ch0 + 1) ^ (lane & 7))] = w1;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + (lane >> 3), ch = lane & 7;
-            const uint4 val = stg[r * 8 + (ch ^ (r & 7))];
-            const int64_t grow = (int64_t)b * AT + quarter * 32 + r;
-            *reinterpret_cast<uint4*>(a.c_ctr + grow * dmodel + h * AD + ch * 8) = val;
-        }
+        if (qs.exact | qp.exact | qc.exact)
+            attn_rows<false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, bar_s, bar_p, bar_o);
+        else
+            attn_rows<true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, bar_s, bar_p, bar_o);
     }
     tc_fence_before();
     __syncthreads();

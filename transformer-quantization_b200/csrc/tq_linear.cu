@@ -161,7 +161,7 @@ __device__ __forceinline__ void epi_math16(uint32_t (&v)[16], float (&o)[16], co
         float f = act_fn<ACT>(__uint_as_float(v[j]) * colscale[j] + cbias[j]);
         if (HASQ) {
             const QP p{qscale[j], qzp[j], qlo, qhi, qrcp[j], 0};
-            const float qi = quant_int(f, p);
+            const float qi = quant_int_t<true>(f, p);
             const float ctr = __fsub_rn(qi, p.zp);               // centred integer
             v[j] = __float_as_uint(ctr);
             f = __fmul_rn(p.scale, ctr);                         // scale * (x_int - zp)
@@ -410,7 +410,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             if (k == j) f = __uint_as_float(v[k]);
                         f = apply_act(f * colscale[c0 + j] + cbias[c0 + j], ep.act_fn);
                         const QP p{qscale[c0 + j], qzp[c0 + j], qlo, qhi, qrcp[c0 + j], 1};
-                        const float ctr = __fsub_rn(quant_int(f, p), p.zp);
+                        const float ctr = __fsub_rn(quant_int_t<false>(f, p), p.zp);
                         f = __fmul_rn(p.scale, ctr);
 #pragma unroll
                         for (int k = 0; k < 16; ++k)
@@ -461,15 +461,28 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         rw[4 * c] = t4.x; rw[4 * c + 1] = t4.y; rw[4 * c + 2] = t4.z; rw[4 * c + 3] = t4.w;
                     }
                     __syncwarp();
+                    if (exact) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t pair = rw[j >> 1];
-                        const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));   // bf16 -> fp32
-                        const float sum = __fadd_rn(o[j], __fmul_rn(res_scale, rc));
-                        const QP p2{q2scale[c0 + j], q2zp[c0 + j], q2lo, q2hi, q2rcp[c0 + j], exact};
-                        const float ctr = __fsub_rn(quant_int(sum, p2), p2.zp);
-                        v[j] = __float_as_uint(ctr);
-                        o[j] = __fmul_rn(p2.scale, ctr);
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t pair = rw[j >> 1];
+                            const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));
+                            const float sum = __fadd_rn(o[j], __fmul_rn(res_scale, rc));
+                            const QP p2{q2scale[c0 + j], q2zp[c0 + j], q2lo, q2hi, q2rcp[c0 + j], 1};
+                            const float ctr = __fsub_rn(quant_int_t<false>(sum, p2), p2.zp);
+                            v[j] = __float_as_uint(ctr);
+                            o[j] = __fmul_rn(p2.scale, ctr);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t pair = rw[j >> 1];
+                            const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));   // bf16 -> fp32
+                            const float sum = __fadd_rn(o[j], __fmul_rn(res_scale, rc));
+                            const QP p2{q2scale[c0 + j], q2zp[c0 + j], q2lo, q2hi, q2rcp[c0 + j], 0};
+                            const float ctr = __fsub_rn(quant_int_t<true>(sum, p2), p2.zp);
+                            v[j] = __float_as_uint(ctr);
+                            o[j] = __fmul_rn(p2.scale, ctr);
+                        }
                     }
                 }
                 // ---- coalesced stores: 32 x 16 transpose through this warp's private smem tile ----

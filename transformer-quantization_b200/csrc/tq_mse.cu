@@ -18,6 +18,32 @@ constexpr int kMThreads = 512;
 constexpr int kSliceMax = 40960;          // floats staged per CTA iteration (160 KB)
 constexpr int kCandChunk = 128;           // candidates per block-reduction round
 
+template <bool FAST>
+__device__ __forceinline__ void sse_slice(const float4* __restrict__ xs4, int nv, int tid, const QP& p, float& acc0,
+                                          float& acc1) {
+    int i = tid;
+    for (; i + kMThreads < nv; i += 2 * kMThreads) {
+        const float4 a = xs4[i], b = xs4[i + kMThreads];
+        float d;
+        d = __fsub_rn(a.x, qdq_t<FAST>(a.x, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        d = __fsub_rn(b.x, qdq_t<FAST>(b.x, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
+        d = __fsub_rn(a.y, qdq_t<FAST>(a.y, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        d = __fsub_rn(b.y, qdq_t<FAST>(b.y, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
+        d = __fsub_rn(a.z, qdq_t<FAST>(a.z, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        d = __fsub_rn(b.z, qdq_t<FAST>(b.z, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
+        d = __fsub_rn(a.w, qdq_t<FAST>(a.w, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        d = __fsub_rn(b.w, qdq_t<FAST>(b.w, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
+    }
+    if (i < nv) {
+        const float4 a = xs4[i];
+        float d;
+        d = __fsub_rn(a.x, qdq_t<FAST>(a.x, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        d = __fsub_rn(a.y, qdq_t<FAST>(a.y, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        d = __fsub_rn(a.z, qdq_t<FAST>(a.z, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        d = __fsub_rn(a.w, qdq_t<FAST>(a.w, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+    }
+}
+
 __global__ void __launch_bounds__(kMThreads, 1)
 mse_sse_kernel(const float* __restrict__ x, int64_t n, int64_t per_cta, int vec_ok,
                const float* __restrict__ cand, int32_t n_cand, double* __restrict__ partial) {
@@ -60,27 +86,8 @@ mse_sse_kernel(const float* __restrict__ x, int64_t n, int64_t per_cta, int vec_
             for (int c = 0; c < cn; ++c) {
                 const QP p = ctab[c];
                 float acc0 = 0.0f, acc1 = 0.0f;
-                int i = tid;
-                for (; i + kMThreads < nv; i += 2 * kMThreads) {
-                    const float4 a = xs4[i], b = xs4[i + kMThreads];
-                    float d;
-                    d = __fsub_rn(a.x, qdq(a.x, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                    d = __fsub_rn(b.x, qdq(b.x, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
-                    d = __fsub_rn(a.y, qdq(a.y, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                    d = __fsub_rn(b.y, qdq(b.y, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
-                    d = __fsub_rn(a.z, qdq(a.z, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                    d = __fsub_rn(b.z, qdq(b.z, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
-                    d = __fsub_rn(a.w, qdq(a.w, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                    d = __fsub_rn(b.w, qdq(b.w, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
-                }
-                if (i < nv) {
-                    const float4 a = xs4[i];
-                    float d;
-                    d = __fsub_rn(a.x, qdq(a.x, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                    d = __fsub_rn(a.y, qdq(a.y, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                    d = __fsub_rn(a.z, qdq(a.z, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                    d = __fsub_rn(a.w, qdq(a.w, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-                }
+                if (p.exact) sse_slice<false>(xs4, nv, tid, p, acc0, acc1);      // uniform per candidate
+                else sse_slice<true>(xs4, nv, tid, p, acc0, acc1);
                 const double w = warp_sum((double)acc0 + (double)acc1);
                 if (lane == 0) wpart[wid * kCandChunk + c] = w;
             }

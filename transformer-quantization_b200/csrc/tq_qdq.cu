@@ -25,15 +25,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int MODE>
+template <int MODE, bool FAST>
 __device__ __forceinline__ void emit_vec(const float4& v, const QP& p0, const QP& p1, const QP& p2,
                                          const QP& p3, float4* y, float4* yint, uint2* yctr,
                                          int64_t idx) {
     float4 qi;
-    qi.x = quant_int(v.x, p0);
-    qi.y = quant_int(v.y, p1);
-    qi.z = quant_int(v.z, p2);
-    qi.w = quant_int(v.w, p3);
+    qi.x = quant_int_t<FAST>(v.x, p0);
+    qi.y = quant_int_t<FAST>(v.y, p1);
+    qi.z = quant_int_t<FAST>(v.z, p2);
+    qi.w = quant_int_t<FAST>(v.w, p3);
     if (MODE == OUT_QDQ) {
         float4 o;
         o.x = dequant(qi.x, p0);
@@ -65,6 +65,26 @@ __device__ __forceinline__ void emit_scalar(float v, const QP& p, float* y, floa
 }
 
 // ---- per-tensor ---------------------------------------------------------------------------------
+template <int MODE, bool FAST>
+__device__ __forceinline__ void tensor_body(const float4* __restrict__ xv, float4* __restrict__ yv,
+                                            float4* __restrict__ yiv, uint2* __restrict__ ycv, int64_t nvec,
+                                            const QP& p) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
+    for (int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x; base < nvec; base += stride) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) v[u] = ld_stream(xv + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) emit_vec<MODE, FAST>(v[u], p, p, p, p, yv, yiv, ycv, idx);
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 4)
 qdq_tensor_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yint,
@@ -77,21 +97,8 @@ qdq_tensor_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float*
     float4* yv = reinterpret_cast<float4*>(y);
     float4* yiv = reinterpret_cast<float4*>(yint);
     uint2* ycv = reinterpret_cast<uint2*>(yctr);
-    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
-    for (int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x; base < nvec;
-         base += stride) {
-        float4 v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int64_t idx = base + (int64_t)u * kThreads;
-            if (idx < nvec) v[u] = ld_stream(xv + idx);
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int64_t idx = base + (int64_t)u * kThreads;
-            if (idx < nvec) emit_vec<MODE>(v[u], p, p, p, p, yv, yiv, ycv, idx);
-        }
-    }
+    if (p.exact) tensor_body<MODE, false>(xv, yv, yiv, ycv, nvec, p);     // uniform; see tq::div_rn_t
+    else tensor_body<MODE, true>(xv, yv, yiv, ycv, nvec, p);
     // ragged tail (n % 4 elements)
     if (blockIdx.x == 0) {
         const int64_t i = (nvec << 2) + threadIdx.x;
@@ -116,6 +123,44 @@ qdq_generic_kernel(const float* __restrict__ x, float* __restrict__ y, float* __
 }
 
 // ---- per-embedding / per-embedding-group: x viewed [rows, C], parameters indexed by column ------
+template <int MODE, bool FAST>
+__device__ __forceinline__ void cols_body(const float4* __restrict__ xv, float4* __restrict__ yv,
+                                          float4* __restrict__ yiv, uint2* __restrict__ ycv, int64_t nvec, int32_t CV,
+                                          const float4* sv, const float4* zv, const float4* rv, float lo, float hi) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
+    int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x;
+    int32_t col0 = (int32_t)(base % CV);                 // vector column of the first access
+    const int32_t step = (int32_t)(stride % CV);
+    int32_t off[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) off[u] = (u * kThreads) % CV;
+
+    for (; base < nvec; base += stride) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) v[u] = ld_stream(xv + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) {
+                int32_t cv = col0 + off[u];
+                cv -= (cv >= CV) ? CV : 0;
+                const float4 s = sv[cv];
+                const float4 z = zv[cv];
+                const float4 r = rv[cv];
+                const QP p0{s.x, z.x, lo, hi, r.x, 0}, p1{s.y, z.y, lo, hi, r.y, 0}, p2{s.z, z.z, lo, hi, r.z, 0},
+                    p3{s.w, z.w, lo, hi, r.w, 0};
+                emit_vec<MODE, FAST>(v[u], p0, p1, p2, p3, yv, yiv, ycv, idx);
+            }
+        }
+        col0 += step;
+        col0 -= (col0 >= CV) ? CV : 0;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 4)
 qdq_cols_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yint,
@@ -141,38 +186,8 @@ qdq_cols_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
     const float4* zv = reinterpret_cast<const float4*>(tab + C);
     const float4* rv = reinterpret_cast<const float4*>(tab + 2 * C);
 
-    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
-    int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x;
-    int32_t col0 = (int32_t)(base % CV);                 // vector column of the first access
-    const int32_t step = (int32_t)(stride % CV);
-    int32_t off[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) off[u] = (u * kThreads) % CV;
-
-    for (; base < nvec; base += stride) {
-        float4 v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int64_t idx = base + (int64_t)u * kThreads;
-            if (idx < nvec) v[u] = ld_stream(xv + idx);
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int64_t idx = base + (int64_t)u * kThreads;
-            if (idx < nvec) {
-                int32_t cv = col0 + off[u];
-                cv -= (cv >= CV) ? CV : 0;
-                const float4 s = sv[cv];
-                const float4 z = zv[cv];
-                const float4 r = rv[cv];
-                const QP p0{s.x, z.x, lo, hi, r.x, exact}, p1{s.y, z.y, lo, hi, r.y, exact},
-                    p2{s.z, z.z, lo, hi, r.z, exact}, p3{s.w, z.w, lo, hi, r.w, exact};
-                emit_vec<MODE>(v[u], p0, p1, p2, p3, yv, yiv, ycv, idx);
-            }
-        }
-        col0 += step;
-        col0 -= (col0 >= CV) ? CV : 0;
-    }
+    if (exact) cols_body<MODE, false>(xv, yv, yiv, ycv, nvec, CV, sv, zv, rv, lo, hi);
+    else cols_body<MODE, true>(xv, yv, yiv, ycv, nvec, CV, sv, zv, rv, lo, hi);
 }
 
 // ---- per-channel rows: x viewed [rows = outer*C, inner], one parameter per row ------------------
@@ -190,9 +205,12 @@ qdq_rows_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
         float4* yv = reinterpret_cast<float4*>(y + r * inner);
         float4* yiv = yint ? reinterpret_cast<float4*>(yint + r * inner) : nullptr;
         uint2* ycv = yctr ? reinterpret_cast<uint2*>(yctr + r * inner) : nullptr;
-        for (int64_t i = threadIdx.x; i < ivec; i += kThreads) {
-            const float4 v = ld_stream(xv + i);
-            emit_vec<MODE>(v, p, p, p, p, yv, yiv, ycv, i);
+        if (p.exact) {
+            for (int64_t i = threadIdx.x; i < ivec; i += kThreads)
+                emit_vec<MODE, false>(ld_stream(xv + i), p, p, p, p, yv, yiv, ycv, i);
+        } else {
+            for (int64_t i = threadIdx.x; i < ivec; i += kThreads)
+                emit_vec<MODE, true>(ld_stream(xv + i), p, p, p, p, yv, yiv, ycv, i);
         }
     }
 }
