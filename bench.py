@@ -122,9 +122,25 @@ def synthetic_ids(seed, n_batches=1):
     return [torch.randint(0, 30522, (BATCH, SEQ), generator=g) for _ in range(n_batches)]
 
 
-def host_threads():
-    """threads the CPU arm uses: every hardware thread of the host, as torch's intra-op pool"""
+def usable_cpus():
+    """hardware threads this process may actually use (affinity mask and cgroup CPU quota)"""
     n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def host_threads():
+    """threads the CPU arm uses: every hardware thread the host grants this process"""
+    n = usable_cpus()
     torch.set_num_threads(n)
     return n
 
@@ -193,6 +209,49 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def profile_graphs(forward, ids_dev, mask_dev, ops, reps=20):
+    """Per-kernel-class device time of one step UNDER THE SAME CONDITIONS AS THE TIMED REGION: the
+    calls of one forward are recorded (the fused engine's buffers are persistent, so the pointers
+    stay valid), every class of kernel is re-captured into its own CUDA graph and that graph is
+    replayed ``reps`` times between two CUDA events.  Class times add up to ~ the step time."""
+    calls = []
+    orig = ops._run
+
+    def record(name, work, kernels, fn, *args):
+        calls.append((name, work, fn, args))
+        return orig(name, work, kernels, fn, *args)
+
+    ops._run = record
+    try:
+        with torch.no_grad():
+            forward(ids_dev, mask_dev)
+    finally:
+        ops._run = orig
+    torch.cuda.synchronize()
+    out = {}
+    import tq_native
+    for cls in sorted({c[0] for c in calls}):
+        mine = [c for c in calls if c[0] == cls]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = tq_native._stream()
+            for _, _, fn, args in mine:
+                rc = fn(*(args[:-1] + (st,)))
+                assert rc == 0, rc
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out[cls] = {'seconds': e0.elapsed_time(e1) * 1e-3 / reps, 'work': float(sum(c[1] for c in mine)),
+                    'launches': len(mine)}
+    return out
+
+
 def profile_live(model, ids_dev, mask_dev, ops, reps=10):
     """Per-kernel device time of one step, measured live with CUDA events on the launching stream.
     During one eager forward every call of this library is, right after it ran, re-issued ``reps``
@@ -354,7 +413,7 @@ def run_ours(args):
 
         # ---- roofline of the dominant kernel (eager pass, events on the launching stream) ----
         torch.cuda.synchronize()
-        prof = profile_live(forward, ids_dev, mask_dev, ops)
+        prof = (profile_graphs if forward is not model else profile_live)(forward, ids_dev, mask_dev, ops)
         qdq_gbs = qdq_hbm_probe(ops)
 
     tokens = BATCH * SEQ * world

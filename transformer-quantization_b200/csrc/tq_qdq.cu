@@ -12,6 +12,7 @@
 //   * per-channel weights (inner > 1): one row (channel) per CTA iteration, scalar parameters.
 #include "tq_common.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace tq {
 
@@ -103,6 +104,107 @@ qdq_tensor_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float*
     if (blockIdx.x == 0) {
         const int64_t i = (nvec << 2) + threadIdx.x;
         if (i < n) emit_scalar<MODE>(x[i], p, y, yint, yctr, i);
+    }
+}
+
+// ---- per-tensor, bulk-copy staged (TMA engine, shared-memory ring) --------------------------------
+// For tensors much larger than L2 the memory-level parallelism of the LDG kernel is capped by its
+// register budget (4 x 16 B per thread).  Here the copy engine moves 16 KB tiles global -> shared
+// memory (cp.async.bulk + mbarrier complete_tx) and back (cp.async.bulk shared -> global, bulk
+// groups); threads only touch shared memory.  One elected thread issues both directions, a ring of
+// kBulkStages tiles keeps (stages - 1) loads and the stores in flight per CTA, two CTAs per SM.
+constexpr int kBulkThreads = 256;
+constexpr int kBulkTileVec = 1024;                 // float4 per tile (16 KB)
+constexpr int kBulkStages = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool FAST>
+__device__ __forceinline__ void bulk_compute(float4* tile, int nvec_tile, const QP& p) {
+#pragma unroll
+    for (int u = 0; u < kBulkTileVec / kBulkThreads; ++u) {
+        const int i = u * kBulkThreads + threadIdx.x;
+        if (i < nvec_tile) {
+            float4 v = tile[i];
+            v.x = qdq_t<FAST>(v.x, p);
+            v.y = qdq_t<FAST>(v.y, p);
+            v.z = qdq_t<FAST>(v.z, p);
+            v.w = qdq_t<FAST>(v.w, p);
+            tile[i] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBulkThreads, 2)
+qdq_tensor_bulk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, tq_qspec q) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    float4* ring = reinterpret_cast<float4*>(bulk_smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bulk_smem + (size_t)kBulkStages * kBulkTileVec * 16);
+    float lo, hi;
+    grid_of(q, lo, hi);
+    const QP p = resolve(q, 0, lo, hi);
+    const int64_t nvec = n >> 2;
+    const int64_t tiles = (nvec + kBulkTileVec - 1) / kBulkTileVec;
+    const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBulkStages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + s)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto tile_vecs = [&](int64_t i) -> int {      // i-th tile of this CTA
+        const int64_t t = blockIdx.x + i * gridDim.x;
+        const int64_t left = nvec - t * kBulkTileVec;
+        return (int)(left < kBulkTileVec ? left : kBulkTileVec);
+    };
+    auto issue_load = [&](int64_t i) {
+        const int s = (int)(i % kBulkStages);
+        const int64_t t = blockIdx.x + i * gridDim.x;
+        const uint32_t bytes = (uint32_t)tile_vecs(i) * 16u;
+        const uint32_t bar = smem_addr(bars + s);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(ring + (size_t)s * kBulkTileVec)), "l"(x + t * kBulkTileVec * 4), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (threadIdx.x == 0)
+        for (int64_t i = 0; i < kBulkStages - 1 && i < my_tiles; ++i) issue_load(i);
+
+    for (int64_t i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i % kBulkStages);
+        const uint32_t parity = (uint32_t)((i / kBulkStages) & 1);
+        const uint32_t bar = smem_addr(bars + s);
+        uint32_t done = 0;
+        while (!done)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        float4* tile = ring + (size_t)s * kBulkTileVec;
+        const int nv = tile_vecs(i);
+        if (p.exact) bulk_compute<false>(tile, nv, p);
+        else bulk_compute<true>(tile, nv, p);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // smem writes -> visible to the copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int64_t t = blockIdx.x + i * gridDim.x;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(y + t * kBulkTileVec * 4), "r"(smem_addr(tile)), "r"((uint32_t)nv * 16u)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the buffer of tile i-1 is re-used by tile i + stages - 1: its store must have been read
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (i + kBulkStages - 1 < my_tiles) issue_load(i + kBulkStages - 1);
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // ragged tail (n % 4 elements)
+    if (blockIdx.x == 0) {
+        const int64_t i = (nvec << 2) + threadIdx.x;
+        if (i < n) emit_scalar<OUT_QDQ>(x[i], p, y, nullptr, nullptr, i);
     }
 }
 
@@ -215,6 +317,17 @@ qdq_rows_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
     }
 }
 
+// per-tensor QDQ switches from the LDG kernel to the bulk-copy staged kernel at this many elements
+// (TQ_QDQ_BULK_MIN overrides; 0 disables the LDG kernel, a huge value disables the bulk kernel)
+static int64_t qdq_bulk_threshold() {
+    static int64_t thr = -1;
+    if (thr < 0) {
+        const char* e = getenv("TQ_QDQ_BULK_MIN");
+        thr = e != nullptr ? atoll(e) : (int64_t)8 * 1024 * 1024;
+    }
+    return thr;
+}
+
 static int grid_for(int64_t work_items, int per_block, int ctas_per_sm) {
     int64_t blocks = (work_items + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
@@ -233,6 +346,20 @@ static int launch_any(const float* x, float* y, float* yint, __nv_bfloat16* yctr
                                                         (yctr == nullptr ||
                                                          (reinterpret_cast<uintptr_t>(yctr) & 7u) == 0)));
     if (C == 1) {
+        if (MODE == OUT_QDQ && al && x != y && n >= qdq_bulk_threshold()) {
+            const size_t smem = (size_t)kBulkStages * kBulkTileVec * 16 + kBulkStages * 8;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e = cudaFuncSetAttribute(qdq_tensor_bulk_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                attr_set = true;
+            }
+            const int64_t tiles = ((n >> 2) + kBulkTileVec - 1) / kBulkTileVec;
+            const int64_t cap = (int64_t)sm_count() * 2;
+            qdq_tensor_bulk_kernel<<<(int)(tiles < cap ? tiles : cap), kBulkThreads, smem, st>>>(x, y, n, q);
+            return launch_status();
+        }
         if (al) {
             const int grid = grid_for((n >> 2) + 1, kThreads * kUnroll, 4);
             qdq_tensor_vec_kernel<MODE><<<grid, kThreads, 0, st>>>(x, y, yint, yctr, n, q);
