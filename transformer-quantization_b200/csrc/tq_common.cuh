@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/tq_b200.h"
 
 #define TQ_SM_COUNT_FALLBACK 148
@@ -175,6 +176,15 @@ inline int sm_count() {
     return cached;
 }
 
+inline bool pdl_enabled() {          // TQ_PDL=0 switches programmatic dependent launch off
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TQ_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int check_qspec(const tq_qspec& q) {
@@ -182,6 +192,31 @@ inline int check_qspec(const tq_qspec& q) {
     if (q.n_bits < 1 || q.n_bits > 16) return TQ_EINVAL;
     if (q.zero_float == nullptr && q.is_signed == nullptr) return TQ_EINVAL;
     return TQ_OK;
+}
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// The fused engine is a chain of ~90 short kernels per forward (7 per encoder layer).  Each kernel
+// releases its dependents immediately (pdl_trigger) and blocks before its first dependent global
+// access (pdl_wait) until the previous kernel has completed and flushed: the next kernel's launch
+// latency, barrier init, TMEM allocation and descriptor prefetch overlap the current kernel's tail.
+// Both instructions are no-ops when the kernel was launched without the PDL attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    return e == cudaSuccess ? TQ_OK : (int)e;
 }
 
 inline int launch_status() {

@@ -175,6 +175,8 @@ template <bool EMBED>
 __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
+    pdl_trigger();
+    pdl_wait();
     if (row >= a.M) return;
     ColQ in_q = a.in_q, e_tok = a.e_tok, e_pos = a.e_pos, out_q = a.out_q;
     out_q.init();
@@ -197,9 +199,9 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
 // attention: T = 128 keys/queries per (batch, head), head_dim = 64
 // ---------------------------------------------------------------------------------------------------
 constexpr int AT = 128, AD = 64;
-constexpr int kAttnThreads = 192;       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 softmax / epilogue
+constexpr int kAttnThreads = 320;       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-9 softmax / epilogue
 constexpr int kAttnTmemCols = 256;      // S: [0,128)  O: [128,192)
-constexpr int kAttnSmem = 16384 * 3 + 32768 + 512 + 64 + 1024;
+constexpr int kAttnSmem = 16384 * 3 + 32768 + 512 + 2048 + 64 + 1024;   // Q K V | P | mask | max/sum exchange | barriers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -266,6 +268,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 // K-major SWIZZLE_128B operand (rows of 128 B, 8-row atoms 1024 B apart)
 __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -297,94 +307,118 @@ __device__ __forceinline__ float scale_of(const tq_qspec& q) {
     return resolve(q, 0, lo, hi).scale;
 }
 
-// per-row work of the softmax / epilogue warps (one query row per thread)
+// exact RN(e / d) for a per-thread divisor: Markstein corrections with r = RN(1/d) (see tq::div_rn_t);
+// the one divisor class the proof excludes (all-ones significand) takes the IEEE instruction
+__device__ __forceinline__ float div_by(float e, float d, float r, bool ieee) {
+    if (ieee) return __fdiv_rn(e, d);
+    const float q0 = __fmul_rn(e, r);
+    const float q1 = __fmaf_rn(__fmaf_rn(-q0, d, e), r, q0);
+    return __fmaf_rn(__fmaf_rn(-q1, d, e), r, q1);
+}
+
+// per-row work of the softmax / epilogue warps: TWO threads per query row (warps w and w+4 of the
+// eight share a TMEM lane quarter), each owns one 64-key half of the row = one swizzle span of P
 template <bool FAST>
 __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const QP& qp, const QP& qc, float sqk,
                                           float spv, uint32_t trow, int row, int quarter, int lane, int warp, int b,
-                                          int h, int32_t dmodel, const float* smask, unsigned char* pP, uint32_t bar_s,
-                                          uint32_t bar_p, uint32_t bar_o) {
-        mbar_wait(bar_s, 0);
-        tc_fence_after();
-        // pass 1: scores -> QDQ -> / sqrt(d) + mask, written back to TMEM; row max
-        float vmax = __int_as_float(0xff800000);
+                                          int h, int32_t dmodel, const float* smask, unsigned char* pP, float* xchg,
+                                          uint32_t bar_s, uint32_t bar_p, uint32_t bar_o) {
+    const int hs = (warp - 2) >> 2;                 // which half of the keys / of the context columns
+    const int k0 = hs * 64;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    // pass 1: scores -> QDQ -> / sqrt(d) + mask, written back to TMEM; row max
+    float vmax = __int_as_float(0xff800000);
 #pragma unroll 1
-        for (int c0 = 0; c0 < AT; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
+    for (int c0 = k0; c0 < k0 + 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float t = qdq_t<FAST>(__fmul_rn(__uint_as_float(v[j]), sqk), qs);       // quantized_bert.py:153-154
-                t = __fadd_rn(__fmul_rn(t, a.inv_sqrt_d), smask[c0 + j]);       // :190-194
-                vmax = fmaxf(vmax, t);
-                v[j] = __float_as_uint(t);
-            }
-            tmem_st16(trow + c0, v);
+        for (int j = 0; j < 16; ++j) {
+            float t = qdq_t<FAST>(__fmul_rn(__uint_as_float(v[j]), sqk), qs);       // quantized_bert.py:153-154
+            t = __fadd_rn(__fmul_rn(t, a.inv_sqrt_d), smask[c0 + j]);               // :190-194
+            vmax = fmaxf(vmax, t);
+            v[j] = __float_as_uint(t);
         }
-        // pass 2: exp(t - max), row sum
-        float vsum = 0.0f;
+        tmem_st16_nowait(trow + c0, v);
+    }
+    xchg[hs * AT + row] = vmax;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    vmax = fmaxf(vmax, xchg[(hs ^ 1) * AT + row]);
+    // pass 2: exp(t - max), row sum
+    float vsum = 0.0f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < AT; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
+    for (int c0 = k0; c0 < k0 + 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float e = expf(__uint_as_float(v[j]) - vmax);
-                vsum += e;
-                v[j] = __float_as_uint(e);
-            }
-            tmem_st16(trow + c0, v);
+        for (int j = 0; j < 16; ++j) {
+            const float e = expf(__uint_as_float(v[j]) - vmax);
+            vsum += e;
+            v[j] = __float_as_uint(e);
         }
-        // pass 3: probs -> QDQ -> centred integers into the swizzled K-major A tile
+        tmem_st16_nowait(trow + c0, v);
+    }
+    xchg[2 * AT + hs * AT + row] = vsum;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // both threads of a row add the two partial sums in the same order (low half + high half)
+    vsum = xchg[2 * AT + row] + xchg[3 * AT + row];
+    const float rsum = __frcp_rn(vsum);
+    const bool ieee = (__float_as_uint(vsum) & 0x7fffffu) == 0x7fffffu;
+    // pass 3: probs -> QDQ -> centred integers into this thread's swizzle span of the K-major A tile
+    uint4* prow = reinterpret_cast<uint4*>(pP + hs * 16384 + row * 128);
 #pragma unroll 1
-        for (int c0 = 0; c0 < AT; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
-            float c[16];
+    for (int c0 = k0; c0 < k0 + 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c0, v);
+        float c[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float pr = __fdiv_rn(__uint_as_float(v[j]), vsum);          // softmax, :197
-                c[j] = __fsub_rn(quant_int_t<FAST>(pr, qp), qp.zp);                       // :198
-            }
-            const int halfk = c0 >> 6;                       // which 64-key swizzle span
-            const int ch0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this row piece
-            uint4* prow = reinterpret_cast<uint4*>(pP + halfk * 16384 + row * 128);
-            uint4 w0, w1;
-            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
-            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
-            prow[(ch0) ^ (row & 7)] = w0;
-            prow[(ch0 + 1) ^ (row & 7)] = w1;
+        for (int j = 0; j < 16; ++j) {
+            const float pr = div_by(__uint_as_float(v[j]), vsum, rsum, ieee);       // softmax, :197
+            c[j] = __fsub_rn(quant_int_t<FAST>(pr, qp), qp.zp);                     // :198
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
-        tc_fence_before();
-        mbar_arrive(bar_p);
+        const int ch0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this row piece
+        uint4 w0, w1;
+        w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
+        w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
+        prow[(ch0) ^ (row & 7)] = w0;
+        prow[(ch0 + 1) ^ (row & 7)] = w1;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
+    tc_fence_before();
+    mbar_arrive(bar_p);
 
-        // context: O * (s_p * s_v) -> QDQ -> centred bf16, coalesced through the (now free) P tile
-        mbar_wait(bar_o, 0);
-        tc_fence_after();
-        uint4* stg = reinterpret_cast<uint4*>(pP + (warp - 2) * 4096);     // 32 rows x 128 B per warp
+    // context: O * (s_p * s_v) -> QDQ -> centred bf16; this thread owns 32 of the 64 head dims;
+    // coalesced through the (now free) P tile: 32 rows x 64 B per warp
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    uint4* stg = reinterpret_cast<uint4*>(pP + (warp - 2) * 2048);
 #pragma unroll 1
-        for (int c0 = 0; c0 < AD; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + 128 + c0, v);
-            float c[16];
+    for (int i = 0; i < 2; ++i) {
+        const int c0 = hs * 32 + i * 16;
+        uint32_t v[16];
+        tmem_ld16(trow + 128 + c0, v);
+        float c[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                c[j] = __fsub_rn(quant_int_t<FAST>(__fmul_rn(__uint_as_float(v[j]), spv), qc), qc.zp);   // :201-213
-            uint4 w0, w1;
-            w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
-            w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
-            const int ch0 = c0 >> 3;
-            stg[lane * 8 + ((ch0) ^ (lane & 7))] = w0;
-            stg[lane * 8 + ((ch0 + 1) ^ (lane & 7))] = w1;
-        }
-        __syncwarp();
+        for (int j = 0; j < 16; ++j)
+            c[j] = __fsub_rn(quant_int_t<FAST>(__fmul_rn(__uint_as_float(v[j]), spv), qc), qc.zp);   // :201-213
+        uint4 w0, w1;
+        w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
+        w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
+        const int ch0 = i * 2;                           // 4 chunks of 16 B per staged row
+        stg[lane * 4 + ((ch0) ^ ((lane >> 1) & 3))] = w0;
+        stg[lane * 4 + ((ch0 + 1) ^ ((lane >> 1) & 3))] = w1;
+    }
+    __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + (lane >> 3), ch = lane & 7;
-            const uint4 val = stg[r * 8 + (ch ^ (r & 7))];
-            const int64_t grow = (int64_t)b * AT + quarter * 32 + r;
-            *reinterpret_cast<uint4*>(a.c_ctr + grow * dmodel + h * AD + ch * 8) = val;
-        }
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2), ch = lane & 3;
+        const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+        const int64_t grow = (int64_t)b * AT + quarter * 32 + r;
+        *reinterpret_cast<uint4*>(a.c_ctr + grow * dmodel + h * AD + hs * 32 + ch * 8) = val;
+    }
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -395,10 +429,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
     const uint32_t sQ = base, sK = base + 16384, sV = base + 32768, sP = base + 49152;
     unsigned char* pP = bp + 49152;
     float* smask = reinterpret_cast<float*>(bp + 49152 + 32768);
-    const uint32_t bar0 = base + 49152 + 32768 + 512;
+    float* xchg = reinterpret_cast<float*>(bp + 49152 + 32768 + 512);
+    const uint32_t bar0 = base + 49152 + 32768 + 512 + 2048;
     const uint32_t bar_qk = bar0, bar_v = bar0 + 8, bar_s = bar0 + 16, bar_p = bar0 + 24, bar_o = bar0 + 32;
     const uint32_t tmem_slot = bar0 + 40;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bp + 49152 + 32768 + 512 + 40);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bp + 49152 + 32768 + 512 + 2048 + 40);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
@@ -410,7 +445,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
             mbar_init(bar_qk, 1);
             mbar_init(bar_v, 1);
             mbar_init(bar_s, 1);
-            mbar_init(bar_p, 128);
+            mbar_init(bar_p, 256);
             mbar_init(bar_o, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -420,7 +455,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
         const int r = threadIdx.x - 64;
         smask[r] = a.mask != nullptr ? a.mask[(int64_t)b * AT + r] : 0.0f;
     }
@@ -428,6 +463,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -475,9 +512,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
         const float spv = qp.scale * scale_of(a.v_q);
 
         if (qs.exact | qp.exact | qc.exact)
-            attn_rows<false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, bar_s, bar_p, bar_o);
+            attn_rows<false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o);
         else
-            attn_rows<true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, bar_s, bar_p, bar_o);
+            attn_rows<true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o);
     }
     tc_fence_before();
     __syncthreads();
@@ -541,8 +578,7 @@ int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B,
     a.mask = mask;
     a.c_ctr = reinterpret_cast<__nv_bfloat16*>(c_ctr_bf16);
     a.inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
-    attention_kernel<<<B * H, kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(map, a);
-    return tq::launch_status();
+    return tq::launch_pdl(attention_kernel, dim3(B * H), dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, map, a);
 }
 
 static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {
@@ -551,9 +587,8 @@ static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {
     if (a.gamma_q == nullptr || a.beta == nullptr || a.out_ctr == nullptr) return TQ_EINVAL;
     if (int e = tq::check_qspec(a.out_q.q)) return e;
     const unsigned grid = (unsigned)((a.M + kLnWarps - 1) / kLnWarps);
-    if (embed) ln_qdq_kernel<true><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(a);
-    else ln_qdq_kernel<false><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(a);
-    return tq::launch_status();
+    if (embed) return tq::launch_pdl(ln_qdq_kernel<true>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, a);
+    return tq::launch_pdl(ln_qdq_kernel<false>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, a);
 }
 
 int tq_ln_qdq_bf16(const void* x_ctr_bf16, tq_qspec in_q, int64_t in_q_params, const float* gamma_q,

@@ -244,6 +244,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();                       // A / residual tiles are produced by the previous kernel
     if (threadIdx.x == 0) TQ_TRACE(1);
 
     if (warp == 0) {
@@ -626,8 +628,8 @@ static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K,
     }
     const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    linear_qdq_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(map_a, map_w, M, N, K, k_split, ep);
-    return launch_status();
+    return launch_pdl(linear_qdq_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, map_a, map_w, M, N, K,
+                      k_split, ep);
 }
 
 // tile width: fewest, fullest waves over the SMs (tile time ~ BN + fixed per-tile overhead)
