@@ -335,7 +335,8 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         tmem_ld16(trow + c0, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float t = qdq_t<FAST>(__fmul_rn(__uint_as_float(v[j]), sqk), qs);       // quantized_bert.py:153-154
+            float t = FAST ? dequant(quant_int_finite(__fmul_rn(__uint_as_float(v[j]), sqk), qs), qs)
+                           : qdq_t<false>(__fmul_rn(__uint_as_float(v[j]), sqk), qs);   // quantized_bert.py:153-154
             t = __fadd_rn(__fmul_rn(t, a.inv_sqrt_d), smask[c0 + j]);               // :190-194
             vmax = fmaxf(vmax, t);
             v[j] = __float_as_uint(t);
@@ -377,7 +378,7 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float pr = div_by(__uint_as_float(v[j]), vsum, rsum, ieee);       // softmax, :197
-            c[j] = __fsub_rn(quant_int_t<FAST>(pr, qp), qp.zp);                     // :198
+            c[j] = __fsub_rn(FAST ? quant_int_finite(pr, qp) : quant_int_t<false>(pr, qp), qp.zp);   // :198
         }
         const int ch0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this row piece
         uint4 w0, w1;
@@ -403,7 +404,10 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         float c[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            c[j] = __fsub_rn(quant_int_t<FAST>(__fmul_rn(__uint_as_float(v[j]), spv), qc), qc.zp);   // :201-213
+            {
+            const float cv = __fmul_rn(__uint_as_float(v[j]), spv);
+            c[j] = __fsub_rn(FAST ? quant_int_finite(cv, qc) : quant_int_t<false>(cv, qc), qc.zp);   // :201-213
+        }
         uint4 w0, w1;
         w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
         w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
@@ -569,6 +573,7 @@ int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B,
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
         if (e != cudaSuccess) return (int)e;
+        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     AttnArgs a;
@@ -587,6 +592,12 @@ static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {
     if (a.gamma_q == nullptr || a.beta == nullptr || a.out_ctr == nullptr) return TQ_EINVAL;
     if (int e = tq::check_qspec(a.out_q.q)) return e;
     const unsigned grid = (unsigned)((a.M + kLnWarps - 1) / kLnWarps);
+    static bool carve_set = false;
+    if (!carve_set) {   // same shared-memory carveout as the GEMMs around it: no SM reconfiguration between kernels
+        cudaFuncSetAttribute(ln_qdq_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(ln_qdq_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
     if (embed) return tq::launch_pdl(ln_qdq_kernel<true>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, a);
     return tq::launch_pdl(ln_qdq_kernel<false>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, a);
 }

@@ -25,8 +25,9 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 B: one SWIZZLE_128B span
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 320;   // 10 warps: TMA, MMA, 8 x epilogue (two per TMEM lane quarter)
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 12;    // three per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31)
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, 12 x epilogue
+constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 
 template <int BN>
@@ -36,7 +37,7 @@ struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN > 192) ? 3 : (BN > 128 ? 4 : (BN > 64 ? 5 : 6));
     static constexpr int kParamBytes = 8 * BN * 4;    // colscale | bias | qscale | qzp | qrcp | q2scale | q2zp | q2rcp
-    static constexpr int kStoreBytes = 8 * 4096;                    // per-epilogue-warp 32x32 fp32 transpose tile
+    static constexpr int kStoreBytes = kEpiWarps * 2048;            // per-epilogue-warp 32x16 fp32 transpose tile
     static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kParamBytes + kBarBytes + 1024;
 };
@@ -161,7 +162,7 @@ __device__ __forceinline__ void epi_math16(uint32_t (&v)[16], float (&o)[16], co
         float f = act_fn<ACT>(__uint_as_float(v[j]) * colscale[j] + cbias[j]);
         if (HASQ) {
             const QP p{qscale[j], qzp[j], qlo, qhi, qrcp[j], 0};
-            const float qi = quant_int_t<true>(f, p);
+            const float qi = quant_int_finite(f, p);
             const float ctr = __fsub_rn(qi, p.zp);               // centred integer
             v[j] = __float_as_uint(ctr);
             f = __fmul_rn(p.scale, ctr);                         // scale * (x_int - zp)
@@ -230,7 +231,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
-                mbar_init(tempty_bar(s), 8);      // one arrival per epilogue warp
+                mbar_init(tempty_bar(s), kEpiWarps);      // one arrival per epilogue warp
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -302,9 +303,9 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
-        const int et = threadIdx.x - 64;                       // 0..255
+        const int et = threadIdx.x - 64;                       // 0..383
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                      // which half of the 32-column chunks
+        const int third = (warp - 2) >> 2;                     // 0..2: which of the quarter's three warps
         float* colscale = params;
         float* cbias = params + BN;
         float* qscale = params + 2 * BN;
@@ -337,7 +338,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         float run_min = __int_as_float(0x7f800000), run_max = __int_as_float(0xff800000);
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's parameter reads done
+            asm volatile("bar.sync 1, 384;" ::: "memory");      // previous tile's parameter reads done
             int need_exact = 0;
             for (int j = et; j < BN; j += kEpiThreads) {
                 const int64_t n = n0 + j;
@@ -375,12 +376,12 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     q2rcp[j] = r2;
                 }
             }
-            // barrier + OR-reduction over the 256 epilogue threads (named barrier 1)
+            // barrier + OR-reduction over the 384 epilogue threads (named barrier 1)
             int exact;
             asm volatile(
                 "{\n\t.reg .pred p, q;\n\t"
                 "setp.ne.b32 p, %1, 0;\n\t"
-                "bar.red.or.pred q, 1, 256, p;\n\t"
+                "bar.red.or.pred q, 1, 384, p;\n\t"
                 "selp.u32 %0, 1, 0, q;\n\t}"
                 : "=r"(exact)
                 : "r"(need_exact)
@@ -392,12 +393,12 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int64_t row = m0 + quarter * 32 + lane;
             const bool row_ok = row < M;
             const int64_t grow0 = m0 + quarter * 32;
-            float4* stg = reinterpret_cast<float4*>(store_stage + (warp - 2) * 4096);
-            // Each warp of a pair owns one half of the tile's columns and walks it 16 columns at a
-            // time: the loop body (16 elements) stays small enough for the instruction cache -- a
-            // fully unrolled 32-wide body (~60 KB of SASS) made instruction fetch the top stall.
+            float4* stg = reinterpret_cast<float4*>(store_stage + (warp - 2) * 2048);
+            // The three warps of a lane quarter take the tile's 16-column slices round robin: the loop
+            // body (16 elements) stays small enough for the instruction cache -- a fully unrolled
+            // 32-wide body (~60 KB of SASS) made instruction fetch the top stall.
 #pragma unroll 1
-            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+            for (int c0 = third * 16; c0 < BN; c0 += 48) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
                 float o[16];
@@ -481,7 +482,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));   // bf16 -> fp32
                             const float sum = __fadd_rn(o[j], __fmul_rn(res_scale, rc));
                             const QP p2{q2scale[c0 + j], q2zp[c0 + j], q2lo, q2hi, q2rcp[c0 + j], 0};
-                            const float ctr = __fsub_rn(quant_int_t<true>(sum, p2), p2.zp);
+                            const float ctr = __fsub_rn(quant_int_finite(sum, p2), p2.zp);
                             v[j] = __float_as_uint(ctr);
                             o[j] = __fmul_rn(p2.scale, ctr);
                         }
