@@ -113,6 +113,72 @@ __device__ __forceinline__ float quant_int_finite(float x, const QP& p) {
     return fminf(fmaxf(__fadd_rn(rint_even(q2), p.zp), p.lo), p.hi);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two IEEE round-to-nearest fp32
+// operations per issue slot).  The quantizer chain is FMA-pipe bound in every kernel of this library
+// (~12 FP32 instructions per element); processing elements in pairs halves the issue slots.  Each
+// component is rounded exactly like the scalar instruction, so results are bit-identical.
+struct QP2 {
+    float2 scale, nscale, rcp, zp, nzp;   // per-component parameters (nscale = -scale, nzp = -zp)
+    float lo, hi;
+};
+__device__ __forceinline__ QP2 pair_of(const QP& a, const QP& b) {
+    QP2 p;
+    p.scale = make_float2(a.scale, b.scale);
+    p.nscale = make_float2(-a.scale, -b.scale);
+    p.rcp = make_float2(a.rcp, b.rcp);
+    p.zp = make_float2(a.zp, b.zp);
+    p.nzp = make_float2(-a.zp, -b.zp);
+    p.lo = a.lo;
+    p.hi = a.hi;
+    return p;
+}
+__device__ __forceinline__ QP2 pair_of(const QP& a) { return pair_of(a, a); }
+
+__device__ __forceinline__ float clamp_nan(float q, float lo, float hi) {   // torch.clamp: NaN propagates
+    q = q < lo ? lo : q;
+    return q > hi ? hi : q;
+}
+
+// RN(x / scale) for both components, division-free (see div_rn_t)
+__device__ __forceinline__ float2 quot2(float2 x, const QP2& p) {
+    const float2 q0 = __fmul2_rn(x, p.rcp);
+    const float2 q1 = __ffma2_rn(__ffma2_rn(q0, p.nscale, x), p.rcp, q0);
+    return __ffma2_rn(__ffma2_rn(q1, p.nscale, x), p.rcp, q1);
+}
+__device__ __forceinline__ float2 rint2_plus(float2 q, float2 zp) {          // rint_even(q) + zp
+    const float2 M = make_float2(12582912.0f, 12582912.0f), nM = make_float2(-12582912.0f, -12582912.0f);
+    return __fadd2_rn(__fadd2_rn(__fadd2_rn(q, M), nM), zp);
+}
+
+// clamp(rint(x / scale) + zp, lo, hi) for a pair; FAST as in quant_int_t
+template <bool FAST>
+__device__ __forceinline__ float2 quant_int2_t(float2 x, const QP2& p) {
+    float2 q;
+    if (FAST) {
+        const float2 q0 = __fmul2_rn(x, p.rcp);
+        float2 q2 = quot2(x, p);
+        q2.x = fabsf(q0.x) < 4194304.0f ? q2.x : q0.x;       // inf / NaN / huge: see div_rn_t
+        q2.y = fabsf(q0.y) < 4194304.0f ? q2.y : q0.y;
+        q = rint2_plus(q2, p.zp);
+    } else {
+        q = rint2_plus(make_float2(__fdiv_rn(x.x, p.scale.x), __fdiv_rn(x.y, p.scale.y)), p.zp);
+    }
+    q.x = clamp_nan(q.x, p.lo, p.hi);
+    q.y = clamp_nan(q.y, p.lo, p.hi);
+    return q;
+}
+// finite inputs only (GEMM / attention epilogues), see quant_int_finite
+__device__ __forceinline__ float2 quant_int2_finite(float2 x, const QP2& p) {
+    float2 q = rint2_plus(quot2(x, p), p.zp);
+    q.x = fminf(fmaxf(q.x, p.lo), p.hi);
+    q.y = fminf(fmaxf(q.y, p.lo), p.hi);
+    return q;
+}
+__device__ __forceinline__ float2 centre2(float2 xi, const QP2& p) { return __fadd2_rn(xi, p.nzp); }       // x_int - zp
+__device__ __forceinline__ float2 dequant2(float2 xi, const QP2& p) { return __fmul2_rn(p.scale, centre2(xi, p)); }
+template <bool FAST>
+__device__ __forceinline__ float2 qdq2_t(float2 x, const QP2& p) { return dequant2(quant_int2_t<FAST>(x, p), p); }
+
 // scale * (x_int - zp)  -- quantizers.py:209
 __device__ __forceinline__ float dequant(float xi, const QP& p) {
     return __fmul_rn(p.scale, __fsub_rn(xi, p.zp));

@@ -149,12 +149,26 @@ __device__ __forceinline__ void ln_row(const LnArgs& a, int64_t row, int lane, C
             const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
             const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float ctr[8], deq[8];
+            if (FAST) {
+                const QP2 p2 = pair_of(out_q.p0);
+                const float2 nmean = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float y = (v[it][j] - mean) * rstd * gs[j] + bs[j];
-                const QP p = out_q.get<FAST>(c + j);
-                ctr[j] = __fsub_rn(quant_int_t<FAST>(y, p), p.zp);
-                deq[j] = __fmul_rn(p.scale, ctr[j]);
+                for (int j = 0; j < 8; j += 2) {
+                    float2 y = __fmul2_rn(__fadd2_rn(make_float2(v[it][j], v[it][j + 1]), nmean), rs2);
+                    y = __fadd2_rn(__fmul2_rn(y, make_float2(gs[j], gs[j + 1])), make_float2(bs[j], bs[j + 1]));
+                    const float2 ci = centre2(quant_int2_t<true>(y, p2), p2);
+                    const float2 dq = __fmul2_rn(p2.scale, ci);
+                    ctr[j] = ci.x; ctr[j + 1] = ci.y;
+                    deq[j] = dq.x; deq[j + 1] = dq.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float y = (v[it][j] - mean) * rstd * gs[j] + bs[j];
+                    const QP p = out_q.get<FAST>(c + j);
+                    ctr[j] = __fsub_rn(quant_int_t<FAST>(y, p), p.zp);
+                    deq[j] = __fmul_rn(p.scale, ctr[j]);
+                }
             }
             uint4 o;
             o.x = pack2(ctr[0], ctr[1]);
@@ -325,6 +339,8 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
                                           uint32_t bar_s, uint32_t bar_p, uint32_t bar_o) {
     const int hs = (warp - 2) >> 2;                 // which half of the keys / of the context columns
     const int k0 = hs * 64;
+    const QP2 qs2 = pair_of(qs), qp2 = pair_of(qp), qc2 = pair_of(qc);
+    const float2 sqk2 = make_float2(sqk, sqk), inv2 = make_float2(a.inv_sqrt_d, a.inv_sqrt_d), spv2 = make_float2(spv, spv);
     mbar_wait(bar_s, 0);
     tc_fence_after();
     // pass 1: scores -> QDQ -> / sqrt(d) + mask, written back to TMEM; row max
@@ -334,12 +350,15 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         uint32_t v[16];
         tmem_ld16(trow + c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float t = FAST ? dequant(quant_int_finite(__fmul_rn(__uint_as_float(v[j]), sqk), qs), qs)
-                           : qdq_t<false>(__fmul_rn(__uint_as_float(v[j]), sqk), qs);   // quantized_bert.py:153-154
-            t = __fadd_rn(__fmul_rn(t, a.inv_sqrt_d), smask[c0 + j]);               // :190-194
-            vmax = fmaxf(vmax, t);
-            v[j] = __float_as_uint(t);
+        for (int j = 0; j < 16; j += 2) {
+            const float2 sc = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sqk2);
+            float2 t;                                                               // quantized_bert.py:153-154
+            if (FAST) t = dequant2(quant_int2_finite(sc, qs2), qs2);
+            else t = make_float2(qdq_t<false>(sc.x, qs), qdq_t<false>(sc.y, qs));
+            t = __fadd2_rn(__fmul2_rn(t, inv2), *reinterpret_cast<const float2*>(smask + c0 + j));   // :190-194
+            vmax = fmaxf(vmax, fmaxf(t.x, t.y));
+            v[j] = __float_as_uint(t.x);
+            v[j + 1] = __float_as_uint(t.y);
         }
         tmem_st16_nowait(trow + c0, v);
     }
@@ -368,6 +387,7 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
     vsum = xchg[2 * AT + row] + xchg[3 * AT + row];
     const float rsum = __frcp_rn(vsum);
     const bool ieee = (__float_as_uint(vsum) & 0x7fffffu) == 0x7fffffu;
+    const float2 r2 = make_float2(rsum, rsum), nd2 = make_float2(-vsum, -vsum);
     // pass 3: probs -> QDQ -> centred integers into this thread's swizzle span of the K-major A tile
     uint4* prow = reinterpret_cast<uint4*>(pP + hs * 16384 + row * 128);
 #pragma unroll 1
@@ -376,9 +396,21 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         tmem_ld16(trow + c0, v);
         float c[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float pr = div_by(__uint_as_float(v[j]), vsum, rsum, ieee);       // softmax, :197
-            c[j] = __fsub_rn(FAST ? quant_int_finite(pr, qp) : quant_int_t<false>(pr, qp), qp.zp);   // :198
+        for (int j = 0; j < 16; j += 2) {
+            const float2 e2 = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            float2 pr;                                                              // softmax, :197
+            if (ieee) {
+                pr = make_float2(__fdiv_rn(e2.x, vsum), __fdiv_rn(e2.y, vsum));
+            } else {                                                                // exact quotient, see div_by
+                const float2 q0 = __fmul2_rn(e2, r2);
+                const float2 q1 = __ffma2_rn(__ffma2_rn(q0, nd2, e2), r2, q0);
+                pr = __ffma2_rn(__ffma2_rn(q1, nd2, e2), r2, q1);
+            }
+            float2 ci;                                                              // :198
+            if (FAST) ci = centre2(quant_int2_finite(pr, qp2), qp2);
+            else ci = make_float2(__fsub_rn(quant_int_t<false>(pr.x, qp), qp.zp), __fsub_rn(quant_int_t<false>(pr.y, qp), qp.zp));
+            c[j] = ci.x;
+            c[j + 1] = ci.y;
         }
         const int ch0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this row piece
         uint4 w0, w1;
@@ -403,10 +435,13 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         tmem_ld16(trow + 128 + c0, v);
         float c[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            {
-            const float cv = __fmul_rn(__uint_as_float(v[j]), spv);
-            c[j] = __fsub_rn(FAST ? quant_int_finite(cv, qc) : quant_int_t<false>(cv, qc), qc.zp);   // :201-213
+        for (int j = 0; j < 16; j += 2) {                                           // :201-213
+            const float2 cv = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), spv2);
+            float2 ci;
+            if (FAST) ci = centre2(quant_int2_finite(cv, qc2), qc2);
+            else ci = make_float2(__fsub_rn(quant_int_t<false>(cv.x, qc), qc.zp), __fsub_rn(quant_int_t<false>(cv.y, qc), qc.zp));
+            c[j] = ci.x;
+            c[j + 1] = ci.y;
         }
         uint4 w0, w1;
         w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);

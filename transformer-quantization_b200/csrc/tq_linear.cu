@@ -36,7 +36,7 @@ struct Cfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN > 192) ? 3 : (BN > 128 ? 4 : (BN > 64 ? 5 : 6));
-    static constexpr int kParamBytes = 8 * BN * 4;    // colscale | bias | qscale | qzp | qrcp | q2scale | q2zp | q2rcp
+    static constexpr int kParamBytes = 12 * BN * 4;   // colscale | bias | {scale,-scale,1/scale,zp,-zp} x {out_q, out2_q}
     static constexpr int kStoreBytes = kEpiWarps * 2048;            // per-epilogue-warp 32x16 fp32 transpose tile
     static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kParamBytes + kBarBytes + 1024;
@@ -150,24 +150,46 @@ __device__ __forceinline__ float act_fn(float v) {
     return v;
 }
 
-// 16 accumulators of one row -> scale, bias, activation, optional output quantizer.  One compact,
-// branch-free body per (activation, quantized?) pair so the executed path is contiguous in the
-// instruction cache.  On return o[] holds the fp32 outputs, v[] the centred integers (if HASQ).
+// per-column epilogue parameters in shared memory (one float per column each)
+struct ColParams {
+    const float *cs, *cb;                         // s_a * s_w[n], bias[n]
+    const float *qs, *qns, *qr, *qz, *qnz;        // output quantizer: scale, -scale, 1/scale, zp, -zp
+};
+__device__ __forceinline__ QP2 qp2_at(const float* s, const float* ns, const float* r, const float* z, const float* nz,
+                                      int j, float lo, float hi) {
+    QP2 p;
+    p.scale = *reinterpret_cast<const float2*>(s + j);
+    p.nscale = *reinterpret_cast<const float2*>(ns + j);
+    p.rcp = *reinterpret_cast<const float2*>(r + j);
+    p.zp = *reinterpret_cast<const float2*>(z + j);
+    p.nzp = *reinterpret_cast<const float2*>(nz + j);
+    p.lo = lo;
+    p.hi = hi;
+    return p;
+}
+
+// 16 accumulators of one row -> scale, bias, activation, optional output quantizer, two columns per
+// instruction (FMUL2 / FADD2 / FFMA2).  One compact, branch-free body per (activation, quantized?)
+// pair so the executed path is contiguous in the instruction cache.  On return o[] holds the fp32
+// outputs, v[] the centred integers (if HASQ).
 template <int ACT, bool HASQ>
-__device__ __forceinline__ void epi_math16(uint32_t (&v)[16], float (&o)[16], const float* colscale,
-                                           const float* cbias, const float* qscale, const float* qzp,
-                                           const float* qrcp, float qlo, float qhi) {
+__device__ __forceinline__ void epi_math16(uint32_t (&v)[16], float (&o)[16], const ColParams& c, float qlo, float qhi) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        float f = act_fn<ACT>(__uint_as_float(v[j]) * colscale[j] + cbias[j]);
+    for (int j = 0; j < 16; j += 2) {
+        float2 f = __fadd2_rn(__fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                         *reinterpret_cast<const float2*>(c.cs + j)),
+                              *reinterpret_cast<const float2*>(c.cb + j));
+        f.x = act_fn<ACT>(f.x);
+        f.y = act_fn<ACT>(f.y);
         if (HASQ) {
-            const QP p{qscale[j], qzp[j], qlo, qhi, qrcp[j], 0};
-            const float qi = quant_int_finite(f, p);
-            const float ctr = __fsub_rn(qi, p.zp);               // centred integer
-            v[j] = __float_as_uint(ctr);
-            f = __fmul_rn(p.scale, ctr);                         // scale * (x_int - zp)
+            const QP2 p = qp2_at(c.qs, c.qns, c.qr, c.qz, c.qnz, j, qlo, qhi);
+            const float2 ctr = centre2(quant_int2_finite(f, p), p);          // centred integers
+            v[j] = __float_as_uint(ctr.x);
+            v[j + 1] = __float_as_uint(ctr.y);
+            f = __fmul2_rn(p.scale, ctr);                                    // scale * (x_int - zp)
         }
-        o[j] = f;
+        o[j] = f.x;
+        o[j + 1] = f.y;
     }
 }
 
@@ -311,9 +333,13 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         float* qscale = params + 2 * BN;
         float* qzp = params + 3 * BN;
         float* qrcp = params + 4 * BN;
-        float* q2scale = params + 5 * BN;
-        float* q2zp = params + 6 * BN;
-        float* q2rcp = params + 7 * BN;
+        float* qnscale = params + 5 * BN;
+        float* qnzp = params + 6 * BN;
+        float* q2scale = params + 7 * BN;
+        float* q2zp = params + 8 * BN;
+        float* q2rcp = params + 9 * BN;
+        float* q2nscale = params + 10 * BN;
+        float* q2nzp = params + 11 * BN;
         const bool has_q = ep.out_q.delta != nullptr;
         const bool has_res = ep.res_ctr != nullptr;
         float q2lo = 0.0f, q2hi = 0.0f, res_scale = 1.0f;
@@ -362,6 +388,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 qscale[j] = qs;
                 qzp[j] = qz;
                 qrcp[j] = qr;
+                qnscale[j] = -qs;
+                qnzp[j] = -qz;
                 if (has_res) {
                     float s2 = 1.0f, z2 = 0.0f, r2 = 1.0f;
                     if (n < N) {
@@ -374,6 +402,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     q2scale[j] = s2;
                     q2zp[j] = z2;
                     q2rcp[j] = r2;
+                    q2nscale[j] = -s2;
+                    q2nzp[j] = -z2;
                 }
             }
             // barrier + OR-reduction over the 384 epilogue threads (named barrier 1)
@@ -423,17 +453,17 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             }
                     }
                 } else {
-                    const float *cs = colscale + c0, *cb = cbias + c0, *qs = qscale + c0, *qz = qzp + c0,
-                                *qr = qrcp + c0;
+                    const ColParams cp{colscale + c0, cbias + c0, qscale + c0, qnscale + c0, qrcp + c0, qzp + c0,
+                                       qnzp + c0};
                     switch (ep.act_fn * 2 + (has_q ? 1 : 0)) {      // warp-uniform
-                        case 0: epi_math16<0, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
-                        case 1: epi_math16<0, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
-                        case 2: epi_math16<1, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
-                        case 3: epi_math16<1, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
-                        case 4: epi_math16<2, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
-                        case 5: epi_math16<2, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
-                        case 6: epi_math16<3, false>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
-                        default: epi_math16<3, true>(v, o, cs, cb, qs, qz, qr, qlo, qhi); break;
+                        case 0: epi_math16<0, false>(v, o, cp, qlo, qhi); break;
+                        case 1: epi_math16<0, true>(v, o, cp, qlo, qhi); break;
+                        case 2: epi_math16<1, false>(v, o, cp, qlo, qhi); break;
+                        case 3: epi_math16<1, true>(v, o, cp, qlo, qhi); break;
+                        case 4: epi_math16<2, false>(v, o, cp, qlo, qhi); break;
+                        case 5: epi_math16<2, true>(v, o, cp, qlo, qhi); break;
+                        case 6: epi_math16<3, false>(v, o, cp, qlo, qhi); break;
+                        default: epi_math16<3, true>(v, o, cp, qlo, qhi); break;
                     }
                 }
                 if (ep.tile_minmax != nullptr && row_ok) {
@@ -476,15 +506,19 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             o[j] = __fmul_rn(p2.scale, ctr);
                         }
                     } else {
+                        const float2 rs2 = make_float2(res_scale, res_scale);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < 16; j += 2) {
                             const uint32_t pair = rw[j >> 1];
-                            const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));   // bf16 -> fp32
-                            const float sum = __fadd_rn(o[j], __fmul_rn(res_scale, rc));
-                            const QP p2{q2scale[c0 + j], q2zp[c0 + j], q2lo, q2hi, q2rcp[c0 + j], 0};
-                            const float ctr = __fsub_rn(quant_int_finite(sum, p2), p2.zp);
-                            v[j] = __float_as_uint(ctr);
-                            o[j] = __fmul_rn(p2.scale, ctr);
+                            const float2 rc = make_float2(__uint_as_float(pair << 16), __uint_as_float(pair & 0xffff0000u));
+                            const float2 sum = __fadd2_rn(make_float2(o[j], o[j + 1]), __fmul2_rn(rs2, rc));
+                            const QP2 p2 = qp2_at(q2scale, q2nscale, q2rcp, q2zp, q2nzp, c0 + j, q2lo, q2hi);
+                            const float2 ctr = centre2(quant_int2_finite(sum, p2), p2);
+                            v[j] = __float_as_uint(ctr.x);
+                            v[j + 1] = __float_as_uint(ctr.y);
+                            const float2 dq = __fmul2_rn(p2.scale, ctr);
+                            o[j] = dq.x;
+                            o[j + 1] = dq.y;
                         }
                     }
                 }

@@ -19,29 +19,32 @@ constexpr int kSliceMax = 40960;          // floats staged per CTA iteration (16
 constexpr int kCandChunk = 128;           // candidates per block-reduction round
 
 template <bool FAST>
+__device__ __forceinline__ float2 sqerr2(float2 x, const QP2& p, float2 acc) {
+    const float2 y = qdq2_t<FAST>(x, p);
+    const float2 d = __fadd2_rn(x, make_float2(-y.x, -y.y));
+    return __fadd2_rn(acc, __fmul2_rn(d, d));
+}
+
+template <bool FAST>
 __device__ __forceinline__ void sse_slice(const float4* __restrict__ xs4, int nv, int tid, const QP& p, float& acc0,
                                           float& acc1) {
+    const QP2 p2 = pair_of(p);
+    float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
     int i = tid;
     for (; i + kMThreads < nv; i += 2 * kMThreads) {
         const float4 a = xs4[i], b = xs4[i + kMThreads];
-        float d;
-        d = __fsub_rn(a.x, qdq_t<FAST>(a.x, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-        d = __fsub_rn(b.x, qdq_t<FAST>(b.x, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
-        d = __fsub_rn(a.y, qdq_t<FAST>(a.y, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-        d = __fsub_rn(b.y, qdq_t<FAST>(b.y, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
-        d = __fsub_rn(a.z, qdq_t<FAST>(a.z, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-        d = __fsub_rn(b.z, qdq_t<FAST>(b.z, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
-        d = __fsub_rn(a.w, qdq_t<FAST>(a.w, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-        d = __fsub_rn(b.w, qdq_t<FAST>(b.w, p)); acc1 = __fadd_rn(acc1, __fmul_rn(d, d));
+        a0 = sqerr2<FAST>(make_float2(a.x, a.y), p2, a0);
+        a1 = sqerr2<FAST>(make_float2(a.z, a.w), p2, a1);
+        a2 = sqerr2<FAST>(make_float2(b.x, b.y), p2, a2);
+        a3 = sqerr2<FAST>(make_float2(b.z, b.w), p2, a3);
     }
     if (i < nv) {
         const float4 a = xs4[i];
-        float d;
-        d = __fsub_rn(a.x, qdq_t<FAST>(a.x, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-        d = __fsub_rn(a.y, qdq_t<FAST>(a.y, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-        d = __fsub_rn(a.z, qdq_t<FAST>(a.z, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
-        d = __fsub_rn(a.w, qdq_t<FAST>(a.w, p)); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        a0 = sqerr2<FAST>(make_float2(a.x, a.y), p2, a0);
+        a1 = sqerr2<FAST>(make_float2(a.z, a.w), p2, a1);
     }
+    acc0 = (a0.x + a0.y) + (a1.x + a1.y);
+    acc1 = (a2.x + a2.y) + (a3.x + a3.y);
 }
 
 __global__ void __launch_bounds__(kMThreads, 1)

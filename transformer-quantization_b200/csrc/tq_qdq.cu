@@ -27,27 +27,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 template <int MODE, bool FAST>
-__device__ __forceinline__ void emit_vec(const float4& v, const QP& p0, const QP& p1, const QP& p2,
-                                         const QP& p3, float4* y, float4* yint, uint2* yctr,
-                                         int64_t idx) {
-    float4 qi;
-    qi.x = quant_int_t<FAST>(v.x, p0);
-    qi.y = quant_int_t<FAST>(v.y, p1);
-    qi.z = quant_int_t<FAST>(v.z, p2);
-    qi.w = quant_int_t<FAST>(v.w, p3);
+__device__ __forceinline__ void emit_vec(const float4& v, const QP2& pa, const QP2& pb, float4* y, float4* yint,
+                                         uint2* yctr, int64_t idx) {
+    const float2 qa = quant_int2_t<FAST>(make_float2(v.x, v.y), pa);
+    const float2 qb = quant_int2_t<FAST>(make_float2(v.z, v.w), pb);
     if (MODE == OUT_QDQ) {
-        float4 o;
-        o.x = dequant(qi.x, p0);
-        o.y = dequant(qi.y, p1);
-        o.z = dequant(qi.z, p2);
-        o.w = dequant(qi.w, p3);
-        st_stream(y + idx, o);
+        const float2 oa = dequant2(qa, pa), ob = dequant2(qb, pb);
+        st_stream(y + idx, make_float4(oa.x, oa.y, ob.x, ob.y));
     } else {
-        if (yint != nullptr) st_stream(yint + idx, qi);
+        if (yint != nullptr) st_stream(yint + idx, make_float4(qa.x, qa.y, qb.x, qb.y));
         if (yctr != nullptr) {
+            const float2 ca = centre2(qa, pa), cb = centre2(qb, pb);
             uint2 c;
-            c.x = pack_bf16x2(__fsub_rn(qi.x, p0.zp), __fsub_rn(qi.y, p1.zp));
-            c.y = pack_bf16x2(__fsub_rn(qi.z, p2.zp), __fsub_rn(qi.w, p3.zp));
+            c.x = pack_bf16x2(ca.x, ca.y);
+            c.y = pack_bf16x2(cb.x, cb.y);
             yctr[idx] = c;
         }
     }
@@ -70,6 +63,7 @@ template <int MODE, bool FAST>
 __device__ __forceinline__ void tensor_body(const float4* __restrict__ xv, float4* __restrict__ yv,
                                             float4* __restrict__ yiv, uint2* __restrict__ ycv, int64_t nvec,
                                             const QP& p) {
+    const QP2 p2 = pair_of(p);
     const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
     for (int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x; base < nvec; base += stride) {
         float4 v[kUnroll];
@@ -81,7 +75,7 @@ __device__ __forceinline__ void tensor_body(const float4* __restrict__ xv, float
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int64_t idx = base + (int64_t)u * kThreads;
-            if (idx < nvec) emit_vec<MODE, FAST>(v[u], p, p, p, p, yv, yiv, ycv, idx);
+            if (idx < nvec) emit_vec<MODE, FAST>(v[u], p2, p2, yv, yiv, ycv, idx);
         }
     }
 }
@@ -121,16 +115,14 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 
 template <bool FAST>
 __device__ __forceinline__ void bulk_compute(float4* tile, int nvec_tile, const QP& p) {
+    const QP2 p2 = pair_of(p);
 #pragma unroll
     for (int u = 0; u < kBulkTileVec / kBulkThreads; ++u) {
         const int i = u * kBulkThreads + threadIdx.x;
         if (i < nvec_tile) {
-            float4 v = tile[i];
-            v.x = qdq_t<FAST>(v.x, p);
-            v.y = qdq_t<FAST>(v.y, p);
-            v.z = qdq_t<FAST>(v.z, p);
-            v.w = qdq_t<FAST>(v.w, p);
-            tile[i] = v;
+            const float4 v = tile[i];
+            const float2 a = qdq2_t<FAST>(make_float2(v.x, v.y), p2), b = qdq2_t<FAST>(make_float2(v.z, v.w), p2);
+            tile[i] = make_float4(a.x, a.y, b.x, b.y);
         }
     }
 }
@@ -253,9 +245,12 @@ __device__ __forceinline__ void cols_body(const float4* __restrict__ xv, float4*
                 const float4 s = sv[cv];
                 const float4 z = zv[cv];
                 const float4 r = rv[cv];
-                const QP p0{s.x, z.x, lo, hi, r.x, 0}, p1{s.y, z.y, lo, hi, r.y, 0}, p2{s.z, z.z, lo, hi, r.z, 0},
-                    p3{s.w, z.w, lo, hi, r.w, 0};
-                emit_vec<MODE, FAST>(v[u], p0, p1, p2, p3, yv, yiv, ycv, idx);
+                QP2 pa, pb;
+                pa.scale = make_float2(s.x, s.y); pa.nscale = make_float2(-s.x, -s.y); pa.rcp = make_float2(r.x, r.y);
+                pa.zp = make_float2(z.x, z.y); pa.nzp = make_float2(-z.x, -z.y); pa.lo = lo; pa.hi = hi;
+                pb.scale = make_float2(s.z, s.w); pb.nscale = make_float2(-s.z, -s.w); pb.rcp = make_float2(r.z, r.w);
+                pb.zp = make_float2(z.z, z.w); pb.nzp = make_float2(-z.z, -z.w); pb.lo = lo; pb.hi = hi;
+                emit_vec<MODE, FAST>(v[u], pa, pb, yv, yiv, ycv, idx);
             }
         }
         col0 += step;
@@ -307,12 +302,13 @@ qdq_rows_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
         float4* yv = reinterpret_cast<float4*>(y + r * inner);
         float4* yiv = yint ? reinterpret_cast<float4*>(yint + r * inner) : nullptr;
         uint2* ycv = yctr ? reinterpret_cast<uint2*>(yctr + r * inner) : nullptr;
+        const QP2 p2 = pair_of(p);
         if (p.exact) {
             for (int64_t i = threadIdx.x; i < ivec; i += kThreads)
-                emit_vec<MODE, false>(ld_stream(xv + i), p, p, p, p, yv, yiv, ycv, i);
+                emit_vec<MODE, false>(ld_stream(xv + i), p2, p2, yv, yiv, ycv, i);
         } else {
             for (int64_t i = threadIdx.x; i < ivec; i += kThreads)
-                emit_vec<MODE, true>(ld_stream(xv + i), p, p, p, p, yv, yiv, ycv, i);
+                emit_vec<MODE, true>(ld_stream(xv + i), p2, p2, yv, yiv, ycv, i);
         }
     }
 }
