@@ -35,7 +35,7 @@ struct Cfg {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN > 192) ? 3 : (BN > 128 ? 4 : (BN > 64 ? 5 : 6));
+    static constexpr int kStages = (BN > 192) ? 3 : (BN > 128 ? 4 : (BN > 96 ? 5 : 6));
     static constexpr int kParamBytes = 12 * BN * 4;   // colscale | bias | {scale,-scale,1/scale,zp,-zp} x {out_q, out2_q}
     static constexpr int kStoreBytes = kEpiWarps * 2048;            // per-epilogue-warp 32x16 fp32 transpose tile
     static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
@@ -667,19 +667,24 @@ static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K,
                       k_split, ep);
 }
 
-// tile width: fewest, fullest waves over the SMs (tile time ~ BN + fixed per-tile overhead)
-static int pick_bn(int64_t M, int64_t N) {
-    const int cands[4] = {256, 192, 128, 64};
+// Tile width.  Cycle model from the clock64 timeline of the kernel (tools/trace_linear.py): the main
+// loop is bound by L2->SM operand traffic (~70 B/clk/SM), the epilogue by FP32 issue (~75 cycles per
+// 16-column slice and warp-triple, x2 with GELU/tanh); with double-buffered TMEM a CTA that owns t
+// tiles takes  setup + main + (t-1) * max(main, epi) + epi.
+static int pick_bn(int64_t M, int64_t N, int64_t K, int k_split, int act_fn) {
+    const int cands[5] = {256, 192, 128, 96, 64};
     const int64_t m_tiles = (M + BM - 1) / BM;
     const int sms = sm_count();
     int best = 64;
     double best_cost = 1e30;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 5; ++i) {
         const int bn = cands[i];
         if (bn > 64 && N < bn) continue;                 // TMA box must fit inside the weight matrix
         const int64_t tiles = m_tiles * ((N + bn - 1) / bn);
-        const int64_t waves = (tiles + sms - 1) / sms;
-        const double cost = (double)waves * (bn + 24.0);
+        const double per_cta = (double)((tiles + sms - 1) / sms);
+        const double main_c = (double)(K / BK) * k_split * (16384.0 + bn * 128.0) / 70.0;
+        const double epi_c = (bn / 16.0 / 3.0) * (act_fn == 1 || act_fn == 3 ? 2400.0 : 1200.0);
+        const double cost = 800.0 + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
         if (cost < best_cost) {
             best_cost = cost;
             best = bn;
@@ -736,10 +741,11 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
     ep.out2_q = out2_q;
     ep.out2_params = out2_q_params;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (pick_bn(M, N)) {
+    switch (pick_bn(M, N, K, k_split, act_fn)) {
         case 256: return launch<256>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
         case 192: return launch<192>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
         case 128: return launch<128>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+        case 96: return launch<96>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
         default: return launch<64>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
     }
 }
