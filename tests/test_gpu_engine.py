@@ -58,8 +58,8 @@ def test_linear_residual_epilogue_exact():
     w_d, w_signed = O.sym_set_quant_range(-0.08, 0.09, 8)
     wd_t, ws_t = T_(np.atleast_1d(w_d)), torch.tensor(bool(w_signed), device=DEV)
     w_sp = ops.spec(wd_t, None, ws_t, 8)
-    acc = (a.astype(np.float64) @ w.astype(np.float64).T).astype(np.float32)
-    pre = (acc * np.float32(O.scale_of(a_d) * O.scale_of(w_d)) + bias).astype(np.float32)
+    acc = a.astype(np.float64) @ w.astype(np.float64).T
+    pre = (acc * np.float64(np.float32(O.scale_of(a_d) * O.scale_of(w_d))) + bias.astype(np.float64)).astype(np.float32)
     g_sp, g_keep, (g_d, g_z) = asym_spec(ops, float(pre.min()), float(pre.max()))
     g = O.qdq_asym(pre, g_d, g_z, 8)
     res = (np.float32(O.scale_of(r_d)) * r).astype(np.float32)

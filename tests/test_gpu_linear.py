@@ -57,8 +57,9 @@ def test_gemm_epilogue_exact(act, per_col):
     a_delta, a_zf = O.asym_set_quant_range(-3.1, 2.7, 8)
     w_delta, w_signed = O.sym_set_quant_range(-0.11, 0.09, 8)
     a_scale, w_scale = O.scale_of(a_delta), O.scale_of(w_delta)
-    acc = (a.astype(np.float64) @ w.astype(np.float64).T).astype(np.float32)
-    pre = (acc * np.float32(a_scale * w_scale) + bias).astype(np.float32)
+    acc = a.astype(np.float64) @ w.astype(np.float64).T                 # exact integers
+    # kernel contract: fma(acc, s_a * s_w, bias) -- one rounding (product exact in fp64, then one add)
+    pre = (acc * np.float64(np.float32(a_scale * w_scale)) + bias.astype(np.float64)).astype(np.float32)
     if act == 2:
         pre = np.maximum(pre, 0)
     if per_col:

@@ -407,7 +407,7 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
                 pr = __ffma2_rn(__ffma2_rn(q1, nd2, e2), r2, q1);
             }
             float2 ci;                                                              // :198
-            if (FAST) ci = centre2(quant_int2_finite(pr, qp2), qp2);
+            if (FAST) ci = quant_ctr2_finite(pr, qp2);
             else ci = make_float2(__fsub_rn(quant_int_t<false>(pr.x, qp), qp.zp), __fsub_rn(quant_int_t<false>(pr.y, qp), qp.zp));
             c[j] = ci.x;
             c[j + 1] = ci.y;
@@ -438,7 +438,7 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         for (int j = 0; j < 16; j += 2) {                                           // :201-213
             const float2 cv = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), spv2);
             float2 ci;
-            if (FAST) ci = centre2(quant_int2_finite(cv, qc2), qc2);
+            if (FAST) ci = quant_ctr2_finite(cv, qc2);
             else ci = make_float2(__fsub_rn(quant_int_t<false>(cv.x, qc), qc.zp), __fsub_rn(quant_int_t<false>(cv.y, qc), qc.zp));
             c[j] = ci.x;
             c[j + 1] = ci.y;

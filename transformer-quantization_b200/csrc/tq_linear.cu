@@ -176,14 +176,16 @@ template <int ACT, bool HASQ>
 __device__ __forceinline__ void epi_math16(uint32_t (&v)[16], float (&o)[16], const ColParams& c, float qlo, float qhi) {
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-        float2 f = __fadd2_rn(__fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
-                                         *reinterpret_cast<const float2*>(c.cs + j)),
-                              *reinterpret_cast<const float2*>(c.cb + j));
+        // acc * (s_a * s_w) + bias as ONE fused multiply-add per column (single rounding; ptxas
+        // contracts packed mul + add into FFMA2 anyway, so the fusion is made explicit and is part of
+        // the kernel's contract -- tests/test_gpu_linear.py checks against the fused formula)
+        float2 f = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                              *reinterpret_cast<const float2*>(c.cs + j), *reinterpret_cast<const float2*>(c.cb + j));
         f.x = act_fn<ACT>(f.x);
         f.y = act_fn<ACT>(f.y);
         if (HASQ) {
             const QP2 p = qp2_at(c.qs, c.qns, c.qr, c.qz, c.qnz, j, qlo, qhi);
-            const float2 ctr = centre2(quant_int2_finite(f, p), p);          // centred integers
+            const float2 ctr = quant_ctr2_finite(f, p);                      // centred integers x_int - zp
             v[j] = __float_as_uint(ctr.x);
             v[j + 1] = __float_as_uint(ctr.y);
             f = __fmul2_rn(p.scale, ctr);                                    // scale * (x_int - zp)
@@ -441,7 +443,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < 16; ++k)
                             if (k == j) f = __uint_as_float(v[k]);
-                        f = apply_act(f * colscale[c0 + j] + cbias[c0 + j], ep.act_fn);
+                        f = apply_act(__fmaf_rn(f, colscale[c0 + j], cbias[c0 + j]), ep.act_fn);
                         const QP p{qscale[c0 + j], qzp[c0 + j], qlo, qhi, qrcp[c0 + j], 1};
                         const float ctr = __fsub_rn(quant_int_t<false>(f, p), p.zp);
                         f = __fmul_rn(p.scale, ctr);
@@ -511,9 +513,12 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int j = 0; j < 16; j += 2) {
                             const uint32_t pair = rw[j >> 1];
                             const float2 rc = make_float2(__uint_as_float(pair << 16), __uint_as_float(pair & 0xffff0000u));
-                            const float2 sum = __fadd2_rn(make_float2(o[j], o[j + 1]), __fmul2_rn(rs2, rc));
+                            // residual value = fl(scale * ctr) as the reference materialises it: scalar
+                            // multiplies (a packed mul feeding a packed add would be contracted to FFMA2)
+                            const float2 sum = __fadd2_rn(make_float2(o[j], o[j + 1]),
+                                                          make_float2(__fmul_rn(rs2.x, rc.x), __fmul_rn(rs2.y, rc.y)));
                             const QP2 p2 = qp2_at(q2scale, q2nscale, q2rcp, q2zp, q2nzp, c0 + j, q2lo, q2hi);
-                            const float2 ctr = centre2(quant_int2_finite(sum, p2), p2);
+                            const float2 ctr = quant_ctr2_finite(sum, p2);
                             v[j] = __float_as_uint(ctr.x);
                             v[j + 1] = __float_as_uint(ctr.y);
                             const float2 dq = __fmul2_rn(p2.scale, ctr);
@@ -531,12 +536,17 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     for (int c = 0; c < 4; ++c)
                         stg[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
                     __syncwarp();
+                    float4 vals[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 4; ++i) {                 // all shared-memory reads first ...
                         const int r = i * 8 + (lane >> 2), ch = lane & 3;
-                        const float4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+                        vals[i] = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {                 // ... then the (predicated) global stores
+                        const int r = i * 8 + (lane >> 2), ch = lane & 3;
                         const int64_t grow = grow0 + r, gcol = gcol0 + ch * 4;
-                        if (grow < M && gcol < N) *reinterpret_cast<float4*>(ep.y + grow * N + gcol) = val;
+                        if (grow < M && gcol < N) *reinterpret_cast<float4*>(ep.y + grow * N + gcol) = vals[i];
                     }
                     __syncwarp();
                 }
@@ -557,12 +567,17 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         s2[lane * 2 + (c ^ ((lane >> 2) & 1))] = w;
                     }
                     __syncwarp();
+                    uint4 cv[2];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int r = i * 16 + (lane >> 1), ch = lane & 1;
-                        const uint4 val = s2[r * 2 + (ch ^ ((r >> 2) & 1))];
+                        cv[i] = s2[r * 2 + (ch ^ ((r >> 2) & 1))];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = i * 16 + (lane >> 1), ch = lane & 1;
                         const int64_t grow = grow0 + r, gcol = gcol0 + ch * 8;
-                        if (grow < M && gcol < N) *reinterpret_cast<uint4*>(ep.y_ctr + grow * N + gcol) = val;
+                        if (grow < M && gcol < N) *reinterpret_cast<uint4*>(ep.y_ctr + grow * N + gcol) = cv[i];
                     }
                     __syncwarp();
                 }
@@ -669,7 +684,7 @@ static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K,
 
 // Tile width.  Cycle model from the clock64 timeline of the kernel (tools/trace_linear.py): the main
 // loop is bound by L2->SM operand traffic (~70 B/clk/SM), the epilogue by FP32 issue (~75 cycles per
-// 16-column slice and warp-triple, x2 with GELU/tanh); with double-buffered TMEM a CTA that owns t
+// 16-column slice per warp: ~2.1 k cycles, ~3.4 k with GELU/tanh -- FMA-pipe and store bound); with double-buffered TMEM a CTA that owns t
 // tiles takes  setup + main + (t-1) * max(main, epi) + epi.
 static int pick_bn(int64_t M, int64_t N, int64_t K, int k_split, int act_fn) {
     const int cands[5] = {256, 192, 128, 96, 64};
@@ -683,7 +698,7 @@ static int pick_bn(int64_t M, int64_t N, int64_t K, int k_split, int act_fn) {
         const int64_t tiles = m_tiles * ((N + bn - 1) / bn);
         const double per_cta = (double)((tiles + sms - 1) / sms);
         const double main_c = (double)(K / BK) * k_split * (16384.0 + bn * 128.0) / 70.0;
-        const double epi_c = (bn / 16.0 / 3.0) * (act_fn == 1 || act_fn == 3 ? 2400.0 : 1200.0);
+        const double epi_c = (bn / 16.0 / 3.0) * (act_fn == 1 || act_fn == 3 ? 3400.0 : 2100.0);
         const double cost = 800.0 + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
         if (cost < best_cost) {
             best_cost = cost;
