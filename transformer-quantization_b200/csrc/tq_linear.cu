@@ -683,7 +683,7 @@ static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K,
 }
 
 // Tile width.  Cycle model from the clock64 timeline of the kernel (tools/trace_linear.py): the main
-// loop is bound by L2->SM operand traffic (~70 B/clk/SM), the epilogue by FP32 issue (~75 cycles per
+// loop advances one k-block per ~600 cycles whatever the tile width, the epilogue is bound by FP32 issue (~75 cycles per
 // 16-column slice per warp: ~2.1 k cycles, ~3.4 k with GELU/tanh -- FMA-pipe and store bound); with double-buffered TMEM a CTA that owns t
 // tiles takes  setup + main + (t-1) * max(main, epi) + epi.
 static int pick_bn(int64_t M, int64_t N, int64_t K, int k_split, int act_fn) {
@@ -697,7 +697,10 @@ static int pick_bn(int64_t M, int64_t N, int64_t K, int k_split, int act_fn) {
         if (bn > 64 && N < bn) continue;                 // TMA box must fit inside the weight matrix
         const int64_t tiles = m_tiles * ((N + bn - 1) / bn);
         const double per_cta = (double)((tiles + sms - 1) / sms);
-        const double main_c = (double)(K / BK) * k_split * (16384.0 + bn * 128.0) / 70.0;
+        // per 64-wide k-block: ~600 cycles of TMA->MMA hand-off latency (measured, independent of the
+        // tile width up to 192) or the MMA time itself (128 x bn x 64 MACs at 4096 MAC/clk)
+        const double mma_c = bn * 2.05;
+        const double main_c = (double)(K / BK) * k_split * (mma_c > 600.0 ? mma_c : 600.0);
         const double epi_c = (bn / 16.0 / 3.0) * (act_fn == 1 || act_fn == 3 ? 3400.0 : 2100.0);
         const double cost = 800.0 + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
         if (cost < best_cost) {
