@@ -320,6 +320,7 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
+        os.environ['NCCL_DEBUG'] = os.environ.get('TQ_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     import tq_native
     ops = tq_native.ops()
@@ -409,6 +410,7 @@ def run_ours(args):
         if rank != 0:
             if world > 1:
                 torch.distributed.barrier()
+                torch.distributed.destroy_process_group()
             return
 
         # ---- roofline of the dominant kernel (eager pass, events on the launching stream) ----
@@ -474,6 +476,7 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def main():

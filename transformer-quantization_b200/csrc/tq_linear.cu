@@ -142,9 +142,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+// erf with one code path (no range split -> no divergence between the elements of a warp):
+// Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 plus fp32 evaluation noise (~3e-7 total, the same
+// order as the spread between libm / Sleef / CUDA erff).  GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) then
+// carries an absolute error <= 1e-6 for |x| <= 6, far below the 8-bit output step that follows.
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float y = 1.0f - p * t * __expf(-ax * ax);
+    return copysignf(y, x);
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fn(float v) {
-    if (ACT == 1) return (v * 0.5f) * (1.0f + erff(v * 0.70710678118654752440f));   // nn.GELU (erf form)
+    if (ACT == 1) return (v * 0.5f) * (1.0f + erf_as(v * 0.70710678118654752440f));   // nn.GELU (erf form)
     if (ACT == 2) return v > 0.0f ? v : (v != v ? v : 0.0f);                         // nn.ReLU
     if (ACT == 3) return tanhf(v);                                                   // nn.Tanh
     return v;
