@@ -1,9 +1,10 @@
-"""QuantizedModule / QuantizedActivation / FP32Acts: per-module quantization switches.
+"""QuantizedModule / QuantizedActivation / FP32Acts: per-module quantization configuration and
+switches.
 
-Mirror of the reference's quantization/base_quantized_classes.py: same constructor keywords
-(reference :41-45), same flags (``_quant_w``, ``_quant_a``, ``cached_params``, ``caching``) and
-the same cache-invalidation points (``train(True)``, ``_apply`` i.e. .to()/.cuda(), the weight
-switches).  Pure control logic -- the arithmetic happens in the QuantizationManager kernels.
+Host-side mirror of the reference's quantization/base_quantized_classes.py: the constructor takes
+the reference's keywords (:41-45), the flags are the reference's (``_quant_w``, ``_quant_a``,
+``cached_params``, ``caching``) and the quantized-parameter cache is dropped at the same points
+(``train(True)``, ``_apply`` i.e. .to()/.cuda(), the weight switches).  Pure control logic.
 """
 from torch import nn
 
@@ -13,8 +14,8 @@ from quantization.range_estimators import RangeEstimators
 
 
 def _switch_initialized(method_name):
-    """module.apply() callback: call ``method_name`` on every *initialised* QuantizationManager
-    (un-initialised ones are skipped, reference :11-32 / quirk A.4-8)."""
+    """module.apply() callback calling ``method_name`` on every INITIALISED QuantizationManager
+    (un-initialised ones are skipped like in the reference, :11-32)."""
 
     def visit(layer):
         if isinstance(layer, QuantizationManager) and layer.quantizer.is_initialized:
@@ -30,9 +31,16 @@ _set_layer_estimate_ranges = _switch_initialized('estimate_ranges')
 _set_layer_estimate_ranges_train = _switch_initialized('estimate_ranges_train')
 
 
+def _apply_to_managers(visitor):
+    def method(self):
+        self.apply(visitor)
+
+    return method
+
+
 class QuantizedModule(nn.Module):
-    """Base of every module that owns quantizers: holds the quantization config, the weight /
-    activation on-off flags and the eval-time quantized-parameter cache."""
+    """Base of every module that owns quantizers: quantization config, weight / activation on-off
+    flags and the eval-time cache of fake-quantized parameters."""
 
     def __init__(self, *args, method=QMethods.asymmetric_uniform, act_method=None, n_bits=8,
                  n_bits_act=None, per_channel_weights=False, per_channel_acts=False, percentile=None,
@@ -41,27 +49,23 @@ class QuantizedModule(nn.Module):
                  scale_domain='linear', **kwargs):
         kwargs.pop('quant_dict', None)
         super().__init__(*args, **kwargs)
-
-        self.method = method
-        self.act_method = act_method or method
-        self.n_bits = n_bits
-        self.n_bits_act = n_bits_act or n_bits
-        self.per_channel_weights = per_channel_weights
-        self.per_channel_acts = per_channel_acts
-        self.percentile = percentile
-        self.weight_range_method = weight_range_method
-        self.weight_range_options = weight_range_options if weight_range_options else {}
-        self.act_range_method = act_range_method
-        self.act_range_options = act_range_options if act_range_options else {}
-        self.scale_domain = scale_domain
-
+        config = dict(
+            method=method, act_method=act_method or method,
+            n_bits=n_bits, n_bits_act=n_bits_act or n_bits,
+            per_channel_weights=per_channel_weights, per_channel_acts=per_channel_acts,
+            percentile=percentile,
+            weight_range_method=weight_range_method, weight_range_options=weight_range_options or {},
+            act_range_method=act_range_method, act_range_options=act_range_options or {},
+            scale_domain=scale_domain,
+        )
+        for name, value in config.items():
+            setattr(self, name, value)
         self.cached_params = None
         self._caching = True
         self.quant_params = None
-        self._quant_w = False
-        self._quant_a = False
+        self._quant_w = self._quant_a = False
 
-    # ---- cache control -------------------------------------------------------------------------
+    # ---- cache ---------------------------------------------------------------------------------
     @property
     def caching(self):
         return self._caching
@@ -72,17 +76,16 @@ class QuantizedModule(nn.Module):
         if not value:
             self.cached_params = None
 
-    def _drop_cache(self):
+    def _set_weight_quant(self, on):
         self.cached_params = None
+        self._quant_w = on
 
-    # ---- on / off switches ---------------------------------------------------------------------
+    # ---- on / off ------------------------------------------------------------------------------
     def quantized_weights(self):
-        self._drop_cache()
-        self._quant_w = True
+        self._set_weight_quant(True)
 
     def full_precision_weights(self):
-        self._drop_cache()
-        self._quant_w = False
+        self._set_weight_quant(False)
 
     def quantized_acts(self):
         self._quant_a = True
@@ -98,46 +101,37 @@ class QuantizedModule(nn.Module):
         self.full_precision_weights()
         self.full_precision_acts()
 
-    # ---- quantizer state switches (all initialised managers below this module) -----------------
-    def learn_ranges(self):
-        self.apply(_set_layer_learn_ranges)
-
-    def fix_ranges(self):
-        self.apply(_set_layer_fix_ranges)
-
-    def estimate_ranges(self):
-        self.apply(_set_layer_estimate_ranges)
-
-    def estimate_ranges_train(self):
-        self.apply(_set_layer_estimate_ranges_train)
+    # ---- state of every initialised manager below this module ----------------------------------
+    learn_ranges = _apply_to_managers(_set_layer_learn_ranges)
+    fix_ranges = _apply_to_managers(_set_layer_fix_ranges)
+    estimate_ranges = _apply_to_managers(_set_layer_estimate_ranges)
+    estimate_ranges_train = _apply_to_managers(_set_layer_estimate_ranges_train)
 
     def train(self, mode=True):
         super().train(mode)
         if mode:
-            self._drop_cache()
+            self.cached_params = None
         return self
 
     def _apply(self, *args, **kwargs):
-        self._drop_cache()
+        self.cached_params = None
         return super(QuantizedModule, self)._apply(*args, **kwargs)
 
     def extra_repr(self):
-        quant_state = 'weight_quant={}, act_quant={}'.format(self._quant_w, self._quant_a)
-        parent_repr = super().extra_repr()
-        return '{},\n{}'.format(parent_repr, quant_state) if parent_repr else quant_state
+        own = f'weight_quant={self._quant_w}, act_quant={self._quant_a}'
+        parent = super().extra_repr()
+        return f'{parent},\n{own}' if parent else own
 
 
 class QuantizedActivation(QuantizedModule):
-    """A stand-alone activation quantizer site (e.g. residual sums, attention scores)."""
+    """A stand-alone activation quantizer site (residual sums, attention scores, ...)."""
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.activation_quantizer = QuantizationManager(
-            qmethod=self.act_method,
+            qmethod=self.act_method, init=self.act_range_method,
             qparams=dict(n_bits=self.n_bits_act, scale_domain=self.scale_domain),
-            init=self.act_range_method,
-            init_params=self.act_range_options,
-        )
+            init_params=self.act_range_options)
 
     def quantize_activations(self, x):
         return self.activation_quantizer(x) if self._quant_a else x

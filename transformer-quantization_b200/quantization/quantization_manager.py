@@ -1,11 +1,14 @@
-"""QuantizationManager: one quantizer + one range estimator + the estimate/fix/learn state machine.
+"""QuantizationManager: one quantizer + one range estimator + the estimate / fix / learn state
+machine of a quantizer site.
 
-Mirror of the reference's quantization/quantization_manager.py (names, constructor signature,
-states and error behaviour identical).  ``forward`` enqueues at most four kernels and never
-synchronises the host:
+Host-side mirror of the reference's quantization/quantization_manager.py -- constructor signature,
+attribute names, states and error behaviour are the reference's (models/quantized_*.py and main.py
+poke at all of them); the data path is this library's:
 
-    estimate state : min/max reduction -> estimator update -> set_quant_range -> QDQ
-    fixed state    : QDQ only (one kernel; CUDA-graph capturable)
+    estimate state : min/max reduction -> estimator update -> set_quant_range -> QDQ   (4 kernels)
+    fixed state    : QDQ only                                                           (1 kernel)
+
+None of it synchronises the host, so a fixed-state forward is CUDA-graph capturable.
 """
 from enum import Enum
 
@@ -22,13 +25,33 @@ class Qstates(Enum):
     estimate_ranges_train = 3  # ranges are updated during train and fixed for eval
 
 
-class QuantizationManager(nn.Module):
-    """Quantization + range estimation for one tensor site.
+def _state_switch(target, precondition=None):
+    """method that moves the manager to ``target`` (after an optional hook)"""
 
-    Parameters (as in the reference, quantization_manager.py:19-40): ``qmethod`` (QMethods member),
-    ``init`` (RangeEstimators member), ``per_channel``, ``axis``, ``n_groups``, optional fixed
-    ``x_min`` / ``x_max``, ``qparams`` (kwargs of the quantizer, e.g. n_bits) and ``init_params``
-    (kwargs of the estimator).
+    def switch(self):
+        if precondition is not None:
+            precondition(self)
+        self.state = target
+
+    switch.__name__ = target.name
+    return switch
+
+
+def _require_initialized(mgr):
+    if not mgr.quantizer.is_initialized:
+        raise QuantizerNotInitializedError()
+
+
+class QuantizationManager(nn.Module):
+    """Quantization and range estimation of one tensor site.
+
+    qmethod     QMethods member: which quantizer class
+    init        RangeEstimators member: how the range is found
+    per_channel one grid per output channel (weights)
+    axis, n_groups  per-embedding / per-embedding-group activation quantization
+    x_min, x_max    optional fixed range: the manager starts in ``fix_ranges`` and owns no estimator
+    qparams     kwargs of the quantizer (n_bits, scale_domain, ...)
+    init_params kwargs of the estimator (momentum, num_candidates, opt_method, ...)
     """
 
     def __init__(self, qmethod=QMethods.symmetric_uniform, init=RangeEstimators.current_minmax,
@@ -36,45 +59,27 @@ class QuantizationManager(nn.Module):
                  init_params=None):
         super().__init__()
         self.state = Qstates.estimate_ranges
-        self.qmethod = qmethod
-        self.init = init
-        self.per_channel = per_channel
-        self.axis = axis
-        self.n_groups = n_groups
-        self.qparams = qparams if qparams else {}
-        self.init_params = init_params if init_params else {}
+        self.qmethod, self.init = qmethod, init
+        self.per_channel, self.axis, self.n_groups = per_channel, axis, n_groups
+        self.qparams = qparams or {}
+        self.init_params = init_params or {}
         self.range_estimator = None
+        self.quantizer = qmethod.cls(per_channel=per_channel, axis=axis, **qparams)
 
-        self.quantizer = self.qmethod.cls(per_channel=per_channel, axis=axis, **qparams)
-
-        if x_min is not None and x_max is not None:
-            # fixed, user-supplied range: no estimator is created (as in the reference)
+        fixed_range = x_min is not None and x_max is not None
+        if fixed_range:
             self.set_quant_range(x_min, x_max)
             self.state = Qstates.fix_ranges
         else:
-            self.range_estimator = self.init.cls(per_channel=self.per_channel, quantizer=self.quantizer,
-                                                 axis=self.axis, n_groups=self.n_groups,
-                                                 **self.init_params)
+            self.range_estimator = init.cls(per_channel=per_channel, quantizer=self.quantizer, axis=axis,
+                                            n_groups=n_groups, **self.init_params)
 
-    @property
-    def n_bits(self):
-        return self.quantizer.n_bits
+    n_bits = property(lambda self: self.quantizer.n_bits)
 
-    # ---- state switches ------------------------------------------------------------------------
-    def estimate_ranges(self):
-        self.state = Qstates.estimate_ranges
-
-    def fix_ranges(self):
-        if not self.quantizer.is_initialized:
-            raise QuantizerNotInitializedError()
-        self.state = Qstates.fix_ranges
-
-    def learn_ranges(self):
-        self.quantizer.make_range_trainable()
-        self.state = Qstates.learn_ranges
-
-    def estimate_ranges_train(self):
-        self.state = Qstates.estimate_ranges_train
+    estimate_ranges = _state_switch(Qstates.estimate_ranges)
+    estimate_ranges_train = _state_switch(Qstates.estimate_ranges_train)
+    fix_ranges = _state_switch(Qstates.fix_ranges, _require_initialized)
+    learn_ranges = _state_switch(Qstates.learn_ranges, lambda self: self.quantizer.make_range_trainable())
 
     def reset_ranges(self):
         self.range_estimator.reset()
@@ -82,21 +87,21 @@ class QuantizationManager(nn.Module):
         self.estimate_ranges()
 
     def _updates_ranges(self):
-        return self.state == Qstates.estimate_ranges or (
-            self.state == Qstates.estimate_ranges_train and self.training)
+        if self.state is Qstates.estimate_ranges:
+            return True
+        return self.state is Qstates.estimate_ranges_train and self.training
 
     def forward(self, x):
-        if self.range_estimator.per_group_range_estimation:
-            # FP32 pass that only records per-dim ranges for the PEG permutation
-            self.range_estimator(x)
+        est = self.range_estimator
+        if est.per_group_range_estimation:
+            est(x)                      # FP32 pass: only record per-dim ranges for the PEG permutation
             return x
         if self._updates_ranges():
-            cur_xmin, cur_xmax = self.range_estimator(x)     # per tensor, per axis or per channel
-            self.set_quant_range(cur_xmin, cur_xmax)
+            self.set_quant_range(*est(x))
         return self.quantizer(x)
 
     def set_quant_range(self, x_min, x_max):
         self.quantizer.set_quant_range(x_min, x_max)
 
     def extra_repr(self):
-        return 'state={}'.format(self.state.name)
+        return f'state={self.state.name}'
