@@ -45,6 +45,23 @@ def test_gemm_exact_no_epilogue(M, N, K):
     assert torch.equal(y.double(), ref), f'max |diff| = {(y.double() - ref).abs().max().item()}'
 
 
+@pytest.mark.parametrize('ctas', [1, 2])
+@pytest.mark.parametrize('bn', [256, 192, 128])
+@pytest.mark.parametrize('M,N,K', [(512, 768, 256), (300, 264, 128), (4096, 768, 768), (1000, 2304, 192)])
+def test_gemm_exact_forced_tile_shapes(monkeypatch, ctas, bn, M, N, K):
+    """every tile width, single CTA and CTA pair (tcgen05 cta_group::2), ragged M / N edges"""
+    monkeypatch.setenv('TQ_LINEAR_BN', str(bn))
+    monkeypatch.setenv('TQ_LINEAR_CTAS', str(ctas))
+    ops = tq_native.ops()
+    a, w = _grids(M, N, K, seed=7 * M + N + K + bn + ctas)
+    at = torch.from_numpy(a).to(DEV).to(torch.bfloat16)
+    wt = torch.from_numpy(w).to(DEV).to(torch.bfloat16)
+    y, _ = ops.linear(at, wt, None, M, N, K, 1, None, None, 1, 0, None, 1)
+    ref = torch.from_numpy(a).double().to(DEV) @ torch.from_numpy(w).double().to(DEV).T
+    torch.cuda.synchronize()
+    assert torch.equal(y.double(), ref), f'max |diff| = {(y.double() - ref).abs().max().item()}'
+
+
 @pytest.mark.parametrize('act', [0, 2])
 @pytest.mark.parametrize('per_col', [False, True])
 def test_gemm_epilogue_exact(act, per_col):

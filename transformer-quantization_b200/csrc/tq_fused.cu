@@ -618,7 +618,7 @@ int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B,
     a.mask = mask;
     a.c_ctr = reinterpret_cast<__nv_bfloat16*>(c_ctr_bf16);
     a.inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
-    return tq::launch_pdl(attention_kernel, dim3(B * H), dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, map, a);
+    return tq::launch_pdl(attention_kernel, dim3(B * H), dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, 1, map, a);
 }
 
 static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {
@@ -633,8 +633,8 @@ static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {
         cudaFuncSetAttribute(ln_qdq_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carve_set = true;
     }
-    if (embed) return tq::launch_pdl(ln_qdq_kernel<true>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, a);
-    return tq::launch_pdl(ln_qdq_kernel<false>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, a);
+    if (embed) return tq::launch_pdl(ln_qdq_kernel<true>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 1, a);
+    return tq::launch_pdl(ln_qdq_kernel<false>, dim3(grid), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 1, a);
 }
 
 int tq_ln_qdq_bf16(const void* x_ctr_bf16, tq_qspec in_q, int64_t in_q_params, const float* gamma_q,

@@ -5,12 +5,13 @@
 // six QDQ kernels.  Here the GEMM consumes the INTEGER grids of the fake-quantized operands carried
 // in bf16 (exact for |v| <= 256) on the 5th-gen tensor cores:
 //
-//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4-6 stage smem ring
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4-8 stage smem ring
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32
 //                              accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2-9   epilogue       tcgen05.ld 32x32b.x32 -> acc * (s_a * s_w[n]) + bias[n] -> act_fn
-//                              -> per-tensor or per-column (PEG / fused-QKV) QDQ -> fp32 and/or
-//                              bf16 centred-integer output (operand format of the next GEMM)
+//   warps 2-13  epilogue       tcgen05.ld 32x32b.x16 -> acc * (s_a * s_w[n]) + bias[n] -> act_fn
+//                              -> per-tensor or per-column (PEG / fused-QKV) QDQ [-> + residual -> QDQ]
+//                              -> fp32 and/or bf16 centred-integer output (operand format of the next
+//                              GEMM), one 32-byte row piece per lane (STG.256), no smem staging
 //
 // Persistent: grid = min(#tiles, #SMs); tile order keeps the A row-panel hot in L2.  Three
 // pipelines (smem full/empty, TMEM full/empty, tile loop) synchronised with mbarriers only.
@@ -30,16 +31,22 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, 12 x 
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 
-template <int BN>
+// CTAS = 2: a CTA PAIR (2-CTA cluster on one TPC) computes a 256 x BN tile with tcgen05 cta_group::2 --
+// each CTA stages its own 128 rows of A and HALF of the weight tile, so the L2 -> SM traffic per
+// flop (what bounds the main loop: ~43 B/clk/SM when every SM streams) drops by a third at BN = 256.
+template <int BN, int CTAS>
 struct Cfg {
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBRows = BN / CTAS;          // weight rows staged by this CTA
+    static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN > 192) ? 3 : (BN > 128 ? 4 : (BN > 96 ? 5 : 6));
-    static constexpr int kParamBytes = 12 * BN * 4;   // colscale | bias | {scale,-scale,1/scale,zp,-zp} x {out_q, out2_q}
-    static constexpr int kStoreBytes = kEpiWarps * 2048;            // per-epilogue-warp 32x16 fp32 transpose tile
+    static constexpr int kParamBytes = 12 * BN * 4;   // six float4 arrays per column pair (see "epilogue parameters")
+    // as many ring stages as fit beside the parameters (227 KB per CTA): the main loop is bound by
+    // the TMA -> MMA hand-off latency, so depth is what buys throughput
+    static constexpr int kStagesFit = (227 * 1024 - 1024 - kParamBytes - 256) / kStageBytes;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kParamBytes + kBarBytes + 1024;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kBarBytes + 1024;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -74,26 +81,72 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+template <int CTAS>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1,
                                             uint32_t bar) {
+    if (CTAS == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+            : "memory");
+    } else {
+        // data lands in THIS CTA's shared memory, the transaction bytes are counted on the LEADER's
+        // barrier (bit 24 of a shared::cluster address = CTA rank inside the pair)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same barrier of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(rank)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CTAS>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if (CTAS == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {                                          // the same barrier in BOTH CTAs of the pair
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(bar), "h"((uint16_t)3)
+            : "memory");
+    }
 }
+template <int CTAS>
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (CTAS == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -142,72 +195,110 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
-// erf with one code path (no range split -> no divergence between the elements of a warp):
-// Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 plus fp32 evaluation noise (~3e-7 total, the same
-// order as the spread between libm / Sleef / CUDA erff).  GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) then
-// carries an absolute error <= 1e-6 for |x| <= 6, far below the 8-bit output step that follows.
-__device__ __forceinline__ float erf_as(float x) {
-    const float ax = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float y = 1.0f - p * t * __expf(-ax * ax);
-    return copysignf(y, x);
+// GELU (erf form) for two columns with ONE code path: erf by Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7 plus fp32 evaluation noise, ~3e-7 total -- the same order as the spread between
+// libm / Sleef / CUDA erff), so GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) carries an absolute error
+// <= 1e-6 for |x| <= 6, far below the 8-bit output step that follows.  No range split -> no
+// divergence; the polynomial runs on packed FFMA2, only 1/d and exp2 use the XU pipe.
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
 }
-
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float2 gelu2(float2 x) {
+    const float2 z = __fmul2_rn(x, splat(0.70710678118654752440f));
+    const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+    const float2 d = __ffma2_rn(splat(0.3275911f), az, splat(1.0f));
+    const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    float2 p = __ffma2_rn(splat(-1.061405429f), t, splat(1.453152027f));     // -(a5 t + a4) ...
+    p = __ffma2_rn(p, t, splat(-1.421413741f));
+    p = __ffma2_rn(p, t, splat(0.284496736f));
+    p = __ffma2_rn(p, t, splat(-0.254829592f));                               // = -(polynomial)
+    const float2 npt = __fmul2_rn(p, t);
+    const float2 u = __fmul2_rn(__fmul2_rn(az, az), splat(-1.4426950408889634f));   // -z^2 log2 e
+    const float2 e = make_float2(ex2_approx(u.x), ex2_approx(u.y));
+    const float2 y = __ffma2_rn(npt, e, splat(1.0f));                         // erf(|z|)
+    const float2 erf = make_float2(copysignf(y.x, z.x), copysignf(y.y, z.y));
+    const float2 h = __fmul2_rn(x, splat(0.5f));
+    return __ffma2_rn(h, erf, h);
+}
 template <int ACT>
-__device__ __forceinline__ float act_fn(float v) {
-    if (ACT == 1) return (v * 0.5f) * (1.0f + erf_as(v * 0.70710678118654752440f));   // nn.GELU (erf form)
-    if (ACT == 2) return v > 0.0f ? v : (v != v ? v : 0.0f);                         // nn.ReLU
-    if (ACT == 3) return tanhf(v);                                                   // nn.Tanh
-    return v;
+__device__ __forceinline__ float2 act2(float2 f) {
+    if (ACT == 1) return gelu2(f);
+    return f;
 }
 
-// per-column epilogue parameters in shared memory (one float per column each)
-struct ColParams {
-    const float *cs, *cb;                         // s_a * s_w[n], bias[n]
-    const float *qs, *qns, *qr, *qz, *qnz;        // output quantizer: scale, -scale, 1/scale, zp, -zp
-};
-__device__ __forceinline__ QP2 qp2_at(const float* s, const float* ns, const float* r, const float* z, const float* nz,
-                                      int j, float lo, float hi) {
-    QP2 p;
-    p.scale = *reinterpret_cast<const float2*>(s + j);
-    p.nscale = *reinterpret_cast<const float2*>(ns + j);
-    p.rcp = *reinterpret_cast<const float2*>(r + j);
-    p.zp = *reinterpret_cast<const float2*>(z + j);
-    p.nzp = *reinterpret_cast<const float2*>(nz + j);
-    p.lo = lo;
-    p.hi = hi;
-    return p;
+// ---- 256-bit global access (LDG / STG.E.ENL2.256 on sm_100): 32 bytes = one full sector per lane.
+// The epilogue keeps one output ROW per lane (the TMEM layout); with 32-byte accesses a row-per-lane
+// load or store moves whole sectors, so no shared-memory transpose is needed for coalescing.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
 }
-
-// 16 accumulators of one row -> scale, bias, activation, optional output quantizer, two columns per
-// instruction (FMUL2 / FADD2 / FFMA2).  One compact, branch-free body per (activation, quantized?)
-// pair so the executed path is contiguous in the instruction cache.  On return o[] holds the fp32
-// outputs, v[] the centred integers (if HASQ).
-template <int ACT, bool HASQ>
-__device__ __forceinline__ void epi_math16(uint32_t (&v)[16], float (&o)[16], const ColParams& c, float qlo, float qhi) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-        // acc * (s_a * s_w) + bias as ONE fused multiply-add per column (single rounding; ptxas
-        // contracts packed mul + add into FFMA2 anyway, so the fusion is made explicit and is part of
-        // the kernel's contract -- tests/test_gpu_linear.py checks against the fused formula)
-        float2 f = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
-                              *reinterpret_cast<const float2*>(c.cs + j), *reinterpret_cast<const float2*>(c.cb + j));
-        f.x = act_fn<ACT>(f.x);
-        f.y = act_fn<ACT>(f.y);
-        if (HASQ) {
-            const QP2 p = qp2_at(c.qs, c.qns, c.qr, c.qz, c.qnz, j, qlo, qhi);
-            const float2 ctr = quant_ctr2_finite(f, p);                      // centred integers x_int - zp
-            v[j] = __float_as_uint(ctr.x);
-            v[j + 1] = __float_as_uint(ctr.y);
-            f = __fmul2_rn(p.scale, ctr);                                    // scale * (x_int - zp)
-        }
-        o[j] = f.x;
-        o[j + 1] = f.y;
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// 32 bytes of one row: `wide` (32-byte aligned row pieces) -> one 256-bit access, else two 128-bit
+// ones; `full` = false: only the first 16 bytes exist (ragged last column block, N % 16 == 8)
+__device__ __forceinline__ void ld_row32(const void* p, bool wide, bool full, uint32_t (&r)[8]) {
+    if (wide && full) {
+        ldg256(p, r);
+    } else {
+        const uint4 a = *reinterpret_cast<const uint4*>(p);
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        if (full) b = *(reinterpret_cast<const uint4*>(p) + 1);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+        r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
     }
+}
+__device__ __forceinline__ void st_row32(void* p, bool wide, bool full, const uint32_t (&r)[8]) {
+    if (wide && full) {
+        stg256(p, r);
+    } else {
+        *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]);
+        if (full) *(reinterpret_cast<uint4*>(p) + 1) = make_uint4(r[4], r[5], r[6], r[7]);
+    }
+}
+
+// ---- epilogue parameters -------------------------------------------------------------------------
+// Shared memory: six float4 arrays indexed by COLUMN PAIR jp (= column / 2), two columns per entry:
+//   P[0][jp] = {cs.x, cs.y, cb.x, cb.y}      acc scale s_a * s_w[n], bias[n]
+//   P[1][jp] = {s.x,  s.y,  -s.x, -s.y}      output quantizer scale
+//   P[2][jp] = {r.x,  r.y,  clo.x, clo.y}    RN(1/s), lower clamp bound lo - zp (centred domain)
+//   P[3][jp] = {chi.x, chi.y, chi2.x, chi2.y}  upper clamp bounds hi - zp of both quantizers
+//   P[4][jp] = {s2, -s2}, P[5][jp] = {r2, clo2}   quantizer of the residual sum
+// A per-tensor quantizer (the common case) is read once per tile into registers (QReg).
+__device__ __forceinline__ int pidx(int bn, int arr, int slot, int j) {       // float index
+    return ((arr * (bn >> 1) + (j >> 1)) << 2) + (slot << 1) + (j & 1);
+}
+struct QReg {
+    float2 s, ns, r, clo, chi;
+};
+
+// centred integers x_int - zp = clamp(rint(RN(x / s)), lo - zp, hi - zp) for two columns (finite x:
+// see quant_int_finite; every operand of the clamp is an integer below 2^24, so shifting the clamp
+// by zp is exact)
+__device__ __forceinline__ float2 ctr2(float2 x, const QReg& q) {
+    const float2 q0 = __fmul2_rn(x, q.r);
+    const float2 q1 = __ffma2_rn(__ffma2_rn(q0, q.ns, x), q.r, q0);
+    const float2 q2 = __ffma2_rn(__ffma2_rn(q1, q.ns, x), q.r, q1);
+    float2 k = __fadd2_rn(__fadd2_rn(q2, splat(12582912.0f)), splat(-12582912.0f));
+    k.x = fminf(fmaxf(k.x, q.clo.x), q.chi.x);
+    k.y = fminf(fmaxf(k.y, q.clo.y), q.chi.y);
+    return k;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float2 v) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 struct EpiArgs {
@@ -232,28 +323,224 @@ struct EpiArgs {
 
 #define TQ_TRACE(slot) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[slot] = clock64(); } while (0)
 
+
+// ---- epilogue of one accumulator tile ---------------------------------------------------------------
+// Fast path: activation ACT in {none, GELU}, an output quantizer whose scales are inside div_rn's
+// domain, optionally the residual add + second quantizer.  The three warps of a TMEM lane quarter take
+// the tile's 16-column slices round robin (c0 = third * 16, + 48, ...); a lane owns one output row:
+//   tcgen05.ld 16 columns -> FFMA2 (scale, bias) -> act -> centred integers (ctr2) [-> + residual ->
+//   ctr2] -> bf16 pack -> ONE 32-byte store per lane (and/or two for the fp32 output).
+// No shared-memory staging and no cross-lane traffic; the residual row piece of the NEXT slice is
+// requested before the math of the current one.
+template <int BN, int ACT, bool PERCOL, bool RES>
+__device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* params, uint32_t tmem_tile, int third,
+                                              int64_t row, bool row_ok, int64_t n0, int64_t N, float res_scale,
+                                              uint32_t tfull, uint32_t tphase) {
+    constexpr int HP = BN / 2;
+    const float4* P = reinterpret_cast<const float4*>(params);
+    QReg q1, q2;
+    if (!PERCOL) {
+        const float4 a = P[HP], b = P[2 * HP], c = P[3 * HP];
+        q1.s = make_float2(a.x, a.y); q1.ns = make_float2(a.z, a.w);
+        q1.r = make_float2(b.x, b.y); q1.clo = make_float2(b.z, b.w);
+        q1.chi = make_float2(c.x, c.y);
+        if (RES) {
+            const float4 d = P[4 * HP], e = P[5 * HP];
+            q2.s = make_float2(d.x, d.y); q2.ns = make_float2(d.z, d.w);
+            q2.r = make_float2(e.x, e.y); q2.clo = make_float2(e.z, e.w);
+            q2.chi = make_float2(c.z, c.w);
+        }
+    }
+    const bool wide_c = ((((uintptr_t)ep.y_ctr) | ((uintptr_t)ep.res_ctr)) & 31u) == 0 && (N & 15) == 0;
+    const bool wide_y = (((uintptr_t)ep.y) & 31u) == 0;
+    const __nv_bfloat16* res_row = RES ? ep.res_ctr + row * N + n0 : nullptr;
+    uint32_t rnext[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rnext[i] = 0u;
+    int c0 = third * 16;
+    if (RES && row_ok && n0 + c0 < N) ld_row32(res_row + c0, wide_c, n0 + c0 + 16 <= N, rnext);
+    mbar_wait(tfull, tphase);
+    tc_fence_after();
+    if (threadIdx.x == 64) TQ_TRACE(8);
+#pragma unroll 1
+    for (; c0 < BN; c0 += 48) {
+        const int64_t gcol = n0 + c0;
+        if (gcol >= N) break;                                    // warp-uniform
+        const bool full = gcol + 16 <= N;
+        uint32_t v[16];
+        tmem_ld16(tmem_tile + (uint32_t)c0, v);
+        uint32_t rw[8];
+        if (RES) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rw[i] = rnext[i];
+            const int cn = c0 + 48;
+            if (row_ok && cn < BN && n0 + cn < N) ld_row32(res_row + cn, wide_c, n0 + cn + 16 <= N, rnext);
+        }
+        float2 k[8];
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp) {
+            const int gp = (c0 >> 1) + jp;
+            const float4 p0 = P[gp];
+            float2 f = __ffma2_rn(make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])),
+                                  make_float2(p0.x, p0.y), make_float2(p0.z, p0.w));
+            f = act2<ACT>(f);
+            float4 pc;
+            if (PERCOL) {
+                const float4 a = P[HP + gp], b = P[2 * HP + gp];
+                pc = P[3 * HP + gp];
+                q1.s = make_float2(a.x, a.y); q1.ns = make_float2(a.z, a.w);
+                q1.r = make_float2(b.x, b.y); q1.clo = make_float2(b.z, b.w);
+                q1.chi = make_float2(pc.x, pc.y);
+            }
+            float2 c = ctr2(f, q1);
+            if (RES) {
+                if (PERCOL) {
+                    const float4 d = P[4 * HP + gp], e = P[5 * HP + gp];
+                    q2.s = make_float2(d.x, d.y); q2.ns = make_float2(d.z, d.w);
+                    q2.r = make_float2(e.x, e.y); q2.clo = make_float2(e.z, e.w);
+                    q2.chi = make_float2(pc.z, pc.w);
+                }
+                // dequantized linear output and residual value as the reference materialises them
+                // (fl(scale * ctr) each, then one add): SCALAR multiplies -- a packed multiply feeding
+                // a packed add would be contracted into FFMA2 by ptxas
+                const uint32_t pair = rw[jp];
+                const float2 sum = __fadd2_rn(
+                    make_float2(__fmul_rn(q1.s.x, c.x), __fmul_rn(q1.s.y, c.y)),
+                    make_float2(__fmul_rn(res_scale, __uint_as_float(pair << 16)),
+                                __fmul_rn(res_scale, __uint_as_float(pair & 0xffff0000u))));
+                c = ctr2(sum, q2);
+            }
+            k[jp] = c;
+        }
+        if (row_ok) {
+            if (ep.y_ctr != nullptr) {
+                uint32_t w[8];
+#pragma unroll
+                for (int jp = 0; jp < 8; ++jp) w[jp] = pack_bf16(k[jp]);
+                st_row32(ep.y_ctr + row * N + gcol, wide_c, full, w);
+            }
+            if (ep.y != nullptr) {
+                uint32_t w[16];
+#pragma unroll
+                for (int jp = 0; jp < 8; ++jp) {
+                    float2 s = RES ? q2.s : q1.s;
+                    if (PERCOL) {
+                        const float4 a = P[(RES ? 4 : 1) * HP + (c0 >> 1) + jp];
+                        s = make_float2(a.x, a.y);
+                    }
+                    const float2 o = __fmul2_rn(s, k[jp]);                  // scale * (x_int - zp)
+                    w[2 * jp] = __float_as_uint(o.x);
+                    w[2 * jp + 1] = __float_as_uint(o.y);
+                }
+                float* yr = ep.y + row * N + gcol;
+                st_row32(yr, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+                if (full) st_row32(yr + 8, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&w[8]));
+            }
+        }
+    }
+}
+
+// Generic path (cold): any activation, no output quantizer, scales that need the IEEE division
+// instruction, calibration min/max side reduction.  One element at a time through a compact loop;
+// NaN propagates through the clamp like torch.clamp.
 template <int BN>
+__device__ __forceinline__ void epi_tile_generic(const EpiArgs& ep, const float* params, uint32_t tmem_tile, int third,
+                                                 int64_t row, bool row_ok, int64_t n0, int64_t N, float res_scale,
+                                                 bool has_q, bool has_res, uint32_t tfull, uint32_t tphase,
+                                                 float& run_min, float& run_max) {
+    const bool wide_c = ((((uintptr_t)ep.y_ctr) | ((uintptr_t)ep.res_ctr)) & 31u) == 0 && (N & 15) == 0;
+    const bool wide_y = (((uintptr_t)ep.y) & 31u) == 0;
+    mbar_wait(tfull, tphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = third * 16; c0 < BN; c0 += 48) {
+        const int64_t gcol = n0 + c0;
+        if (gcol >= N) break;
+        const bool full = gcol + 16 <= N;
+        uint32_t v[16];
+        tmem_ld16(tmem_tile + (uint32_t)c0, v);
+        uint32_t rw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rw[i] = 0u;
+        if (has_res && row_ok) ld_row32(ep.res_ctr + row * N + gcol, wide_c, full, rw);
+        uint32_t o[16];
+#pragma unroll 1
+        for (int j = 0; j < 16; ++j) {
+            float acc = 0.0f;
+            uint32_t pair = 0u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i == j) {
+                    acc = __uint_as_float(v[i]);
+                    pair = rw[i >> 1];
+                }
+            const int col = c0 + j;
+            float f = apply_act(__fmaf_rn(acc, params[pidx(BN, 0, 0, col)], params[pidx(BN, 0, 1, col)]), ep.act_fn);
+            float c = f;
+            if (has_q) {
+                const float s = params[pidx(BN, 1, 0, col)];
+                c = clamp_nan(rint_even(__fdiv_rn(f, s)), params[pidx(BN, 2, 1, col)], params[pidx(BN, 3, 0, col)]);
+                f = __fmul_rn(s, c);
+            }
+            if (has_res) {
+                const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));
+                const float sum = __fadd_rn(f, __fmul_rn(res_scale, rc));
+                const float s2 = params[pidx(BN, 4, 0, col)];
+                c = clamp_nan(rint_even(__fdiv_rn(sum, s2)), params[pidx(BN, 5, 1, col)], params[pidx(BN, 3, 1, col)]);
+                f = __fmul_rn(s2, c);
+            }
+            if (ep.tile_minmax != nullptr && row_ok && gcol + j < N) {
+                run_min = fminf(run_min, f);
+                run_max = fmaxf(run_max, f);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i == j) {
+                    v[i] = __float_as_uint(c);
+                    o[i] = __float_as_uint(f);
+                }
+        }
+        if (row_ok) {
+            if (ep.y_ctr != nullptr) {
+                uint32_t w[8];
+#pragma unroll
+                for (int jp = 0; jp < 8; ++jp)
+                    w[jp] = pack_bf16(make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])));
+                st_row32(ep.y_ctr + row * N + gcol, wide_c, full, w);
+            }
+            if (ep.y != nullptr) {
+                float* yr = ep.y + row * N + gcol;
+                st_row32(yr, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
+                if (full) st_row32(yr + 8, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
+            }
+        }
+    }
+}
+
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                  int64_t M, int64_t N, int64_t K, int k_split, EpiArgs ep) {
-    using C = Cfg<BN>;
+                  int64_t M, int64_t N, int64_t K, int k_split, int ring, EpiArgs ep) {
+    using C = Cfg<BN, CTAS>;                          // ring: stages of the smem ring in use (<= C::kStages)
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;       // SWIZZLE_128B: 1024 B alignment
     unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
-    unsigned char* store_stage = base_ptr + C::kStages * C::kStageBytes;
-    float* params = reinterpret_cast<float*>(store_stage + C::kStoreBytes);
-    const uint32_t bar0 = base + C::kStages * C::kStageBytes + C::kStoreBytes + C::kParamBytes;
+    float* params = reinterpret_cast<float*>(base_ptr + C::kStages * C::kStageBytes);
+    const uint32_t bar0 = base + C::kStages * C::kStageBytes + C::kParamBytes;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (C::kStages + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 2 + s); };
     const uint32_t tmem_slot = bar0 + 8u * (2 * C::kStages + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-        base_ptr + C::kStages * C::kStageBytes + C::kStoreBytes + C::kParamBytes + 8 * (2 * C::kStages + 4));
+        base_ptr + C::kStages * C::kStageBytes + C::kParamBytes + 8 * (2 * C::kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+    // a work item is a (BM * CTAS) x BN tile; CTA `cta_rank` of the pair owns rows cta_rank*BM.. of it
+    const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const int64_t m_tiles = (M + BM * CTAS - 1) / (BM * CTAS), n_tiles = (N + BN - 1) / BN;
     const int64_t tiles = m_tiles * n_tiles;
+    const int64_t tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
     const int kb_per_pass = (int)(K / BK);
     const int num_kb = kb_per_pass * k_split;
 
@@ -270,18 +557,25 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
-                mbar_init(tempty_bar(s), kEpiWarps);      // one arrival per epilogue warp
+                mbar_init(tempty_bar(s), kEpiWarps * CTAS);   // one arrival per epilogue warp (of both CTAs)
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"((uint32_t)kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTAS == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"((uint32_t)kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {                                      // the same warp of both CTAs, same slot address
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"((uint32_t)kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs initialised
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_trigger();
@@ -293,29 +587,39 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int32_t m0 = (int32_t)((t / n_tiles) * BM), n0 = (int32_t)((t % n_tiles) * BN);
+            for (int64_t t = tile0; t < tiles; t += tile_step) {
+                const int32_t m0 = (int32_t)((t / n_tiles) * (BM * CTAS) + cta_rank * BM);
+                const int32_t n0 = (int32_t)((t % n_tiles) * BN + cta_rank * C::kBRows);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (kb == 0) TQ_TRACE(2);
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), C::kStageBytes);
+                    // the leader's barrier counts the bytes of both CTAs (the MMA issuer waits on it)
+                    if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CTAS);
                     const uint32_t sa = base + stage * C::kStageBytes;
-                    tma_load_2d(sa, &map_a, kb * BK, m0, full_bar(stage));
-                    tma_load_2d(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BK, n0, full_bar(stage));
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                    tma_load_2d<CTAS>(sa, &map_a, kb * BK, m0, full_bar(stage));
+                    tma_load_2d<CTAS>(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BK, n0, full_bar(stage));
+                    if (++stage == ring) { stage = 0; phase ^= 1u; }
                 }
                 TQ_TRACE(3);
+            }
+            if (CTAS == 2) {
+                // tail: every slot handed out has been consumed -- no multicast arrival may target
+                // this CTA's barriers after it has left
+                for (int s = 0; s < ring; ++s) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (++stage == ring) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+        if (lane == 0 && cta_rank == 0) {             // the pair's leader issues for both CTAs
+            constexpr uint32_t idesc = make_idesc(BM * CTAS, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int64_t t = tile0; t < tiles; t += tile_step) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -329,36 +633,25 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 B (16 bf16) inside the 128 B swizzle span: +2 in 16-byte units
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                        tc_mma_bf16<CTAS>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                     (uint32_t)((kb | k) != 0));
                     }
-                    tc_commit(empty_bar(stage));               // smem slot free once these MMAs retire
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                    tc_commit<CTAS>(empty_bar(stage));         // smem slot free once these MMAs retire
+                    if (++stage == ring) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
+                tc_commit<CTAS>(tfull_bar(acc));               // accumulator complete -> epilogue
                 TQ_TRACE(6);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..9) =====================
+        // ===================== epilogue (warps 2..13) =====================
         const int et = threadIdx.x - 64;                       // 0..383
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
         const int third = (warp - 2) >> 2;                     // 0..2: which of the quarter's three warps
-        float* colscale = params;
-        float* cbias = params + BN;
-        float* qscale = params + 2 * BN;
-        float* qzp = params + 3 * BN;
-        float* qrcp = params + 4 * BN;
-        float* qnscale = params + 5 * BN;
-        float* qnzp = params + 6 * BN;
-        float* q2scale = params + 7 * BN;
-        float* q2zp = params + 8 * BN;
-        float* q2rcp = params + 9 * BN;
-        float* q2nscale = params + 10 * BN;
-        float* q2nzp = params + 11 * BN;
         const bool has_q = ep.out_q.delta != nullptr;
         const bool has_res = ep.res_ctr != nullptr;
+        const bool percol = (has_q && ep.out_q_params > 1) || (has_res && ep.out2_params > 1);
         float q2lo = 0.0f, q2hi = 0.0f, res_scale = 1.0f;
         if (has_res) {
             grid_of(ep.out2_q, q2lo, q2hi);
@@ -379,13 +672,13 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         float run_min = __int_as_float(0x7f800000), run_max = __int_as_float(0xff800000);
-        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        for (int64_t t = tile0; t < tiles; t += tile_step) {
+            const int64_t m0 = (t / n_tiles) * (BM * CTAS) + cta_rank * BM, n0 = (t % n_tiles) * BN;
             asm volatile("bar.sync 1, 384;" ::: "memory");      // previous tile's parameter reads done
             int need_exact = 0;
             for (int j = et; j < BN; j += kEpiThreads) {
                 const int64_t n = n0 + j;
-                float cs = 0.0f, b = 0.0f, qs = 1.0f, qz = 0.0f, qr = 1.0f;
+                float cs = 0.0f, b = 0.0f, qs = 1.0f, qr = 1.0f, clo = 0.0f, chi = 0.0f;
                 if (n < N) {
                     const float ws = ep.w_q.delta != nullptr
                                          ? resolve(ep.w_q, ep.w_q_params > 1 ? n : 0, wlo, whi).scale
@@ -395,33 +688,33 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (has_q) {
                         const QP p = resolve(ep.out_q, ep.out_q_params > 1 ? n : 0, qlo, qhi);
                         qs = p.scale;
-                        qz = p.zp;
                         qr = p.rcp;
+                        clo = qlo - p.zp;                       // integers: exact
+                        chi = qhi - p.zp;
                         need_exact |= p.exact;
                     }
                 }
-                colscale[j] = cs;
-                cbias[j] = b;
-                qscale[j] = qs;
-                qzp[j] = qz;
-                qrcp[j] = qr;
-                qnscale[j] = -qs;
-                qnzp[j] = -qz;
-                if (has_res) {
-                    float s2 = 1.0f, z2 = 0.0f, r2 = 1.0f;
-                    if (n < N) {
-                        const QP p2 = resolve(ep.out2_q, ep.out2_params > 1 ? n : 0, q2lo, q2hi);
-                        s2 = p2.scale;
-                        z2 = p2.zp;
-                        r2 = p2.rcp;
-                        need_exact |= p2.exact;
-                    }
-                    q2scale[j] = s2;
-                    q2zp[j] = z2;
-                    q2rcp[j] = r2;
-                    q2nscale[j] = -s2;
-                    q2nzp[j] = -z2;
+                params[pidx(BN, 0, 0, j)] = cs;
+                params[pidx(BN, 0, 1, j)] = b;
+                params[pidx(BN, 1, 0, j)] = qs;
+                params[pidx(BN, 1, 1, j)] = -qs;
+                params[pidx(BN, 2, 0, j)] = qr;
+                params[pidx(BN, 2, 1, j)] = clo;
+                params[pidx(BN, 3, 0, j)] = chi;
+                float s2 = 1.0f, r2 = 1.0f, clo2 = 0.0f, chi2 = 0.0f;
+                if (has_res && n < N) {
+                    const QP p2 = resolve(ep.out2_q, ep.out2_params > 1 ? n : 0, q2lo, q2hi);
+                    s2 = p2.scale;
+                    r2 = p2.rcp;
+                    clo2 = q2lo - p2.zp;
+                    chi2 = q2hi - p2.zp;
+                    need_exact |= p2.exact;
                 }
+                params[pidx(BN, 3, 1, j)] = chi2;
+                params[pidx(BN, 4, 0, j)] = s2;
+                params[pidx(BN, 4, 1, j)] = -s2;
+                params[pidx(BN, 5, 0, j)] = r2;
+                params[pidx(BN, 5, 1, j)] = clo2;
             }
             // barrier + OR-reduction over the 384 epilogue threads (named barrier 1)
             int exact;
@@ -434,173 +727,31 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 : "r"(need_exact)
                 : "memory");
             if (et == 0) TQ_TRACE(7);
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            if (et == 0) TQ_TRACE(8);
             const int64_t row = m0 + quarter * 32 + lane;
             const bool row_ok = row < M;
-            const int64_t grow0 = m0 + quarter * 32;
-            float4* stg = reinterpret_cast<float4*>(store_stage + (warp - 2) * 2048);
-            // The three warps of a lane quarter take the tile's 16-column slices round robin: the loop
-            // body (16 elements) stays small enough for the instruction cache -- a fully unrolled
-            // 32-wide body (~60 KB of SASS) made instruction fetch the top stall.
-#pragma unroll 1
-            for (int c0 = third * 16; c0 < BN; c0 += 48) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                float o[16];
-                if (has_q && exact) {
-                    // rare (a column scale outside div_rn's proven domain): IEEE divide, one element
-                    // at a time through a compact loop
-#pragma unroll 1
-                    for (int j = 0; j < 16; ++j) {
-                        float f = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if (k == j) f = __uint_as_float(v[k]);
-                        f = apply_act(__fmaf_rn(f, colscale[c0 + j], cbias[c0 + j]), ep.act_fn);
-                        const QP p{qscale[c0 + j], qzp[c0 + j], qlo, qhi, qrcp[c0 + j], 1};
-                        const float ctr = __fsub_rn(quant_int_t<false>(f, p), p.zp);
-                        f = __fmul_rn(p.scale, ctr);
-#pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if (k == j) {
-                                v[k] = __float_as_uint(ctr);
-                                o[k] = f;
-                            }
-                    }
-                } else {
-                    const ColParams cp{colscale + c0, cbias + c0, qscale + c0, qnscale + c0, qrcp + c0, qzp + c0,
-                                       qnzp + c0};
-                    switch (ep.act_fn * 2 + (has_q ? 1 : 0)) {      // warp-uniform
-                        case 0: epi_math16<0, false>(v, o, cp, qlo, qhi); break;
-                        case 1: epi_math16<0, true>(v, o, cp, qlo, qhi); break;
-                        case 2: epi_math16<1, false>(v, o, cp, qlo, qhi); break;
-                        case 3: epi_math16<1, true>(v, o, cp, qlo, qhi); break;
-                        case 4: epi_math16<2, false>(v, o, cp, qlo, qhi); break;
-                        case 5: epi_math16<2, true>(v, o, cp, qlo, qhi); break;
-                        case 6: epi_math16<3, false>(v, o, cp, qlo, qhi); break;
-                        default: epi_math16<3, true>(v, o, cp, qlo, qhi); break;
-                    }
-                }
-                if (ep.tile_minmax != nullptr && row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (n0 + c0 + j < N) {
-                            run_min = fminf(run_min, o[j]);
-                            run_max = fmaxf(run_max, o[j]);
-                        }
-                    }
-                }
-                if (has_res) {
-                    // residual rows: coalesced 32 B pieces -> swizzled smem -> one row per lane
-                    uint4* s2 = reinterpret_cast<uint4*>(stg);
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int r = i * 16 + (lane >> 1), ch = lane & 1;
-                        const int64_t grow = grow0 + r, gcol = n0 + c0 + ch * 8;
-                        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                        if (grow < M && gcol < N) val = *reinterpret_cast<const uint4*>(ep.res_ctr + grow * N + gcol);
-                        s2[r * 2 + (ch ^ ((r >> 2) & 1))] = val;
-                    }
-                    __syncwarp();
-                    uint32_t rw[8];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint4 t4 = s2[lane * 2 + (c ^ ((lane >> 2) & 1))];
-                        rw[4 * c] = t4.x; rw[4 * c + 1] = t4.y; rw[4 * c + 2] = t4.z; rw[4 * c + 3] = t4.w;
-                    }
-                    __syncwarp();
-                    if (exact) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t pair = rw[j >> 1];
-                            const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));
-                            const float sum = __fadd_rn(o[j], __fmul_rn(res_scale, rc));
-                            const QP p2{q2scale[c0 + j], q2zp[c0 + j], q2lo, q2hi, q2rcp[c0 + j], 1};
-                            const float ctr = __fsub_rn(quant_int_t<false>(sum, p2), p2.zp);
-                            v[j] = __float_as_uint(ctr);
-                            o[j] = __fmul_rn(p2.scale, ctr);
-                        }
-                    } else {
-                        const float2 rs2 = make_float2(res_scale, res_scale);
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const uint32_t pair = rw[j >> 1];
-                            const float2 rc = make_float2(__uint_as_float(pair << 16), __uint_as_float(pair & 0xffff0000u));
-                            // residual value = fl(scale * ctr) as the reference materialises it: scalar
-                            // multiplies (a packed mul feeding a packed add would be contracted to FFMA2)
-                            const float2 sum = __fadd2_rn(make_float2(o[j], o[j + 1]),
-                                                          make_float2(__fmul_rn(rs2.x, rc.x), __fmul_rn(rs2.y, rc.y)));
-                            const QP2 p2 = qp2_at(q2scale, q2nscale, q2rcp, q2zp, q2nzp, c0 + j, q2lo, q2hi);
-                            const float2 ctr = quant_ctr2_finite(sum, p2);
-                            v[j] = __float_as_uint(ctr.x);
-                            v[j + 1] = __float_as_uint(ctr.y);
-                            const float2 dq = __fmul2_rn(p2.scale, ctr);
-                            o[j] = dq.x;
-                            o[j + 1] = dq.y;
-                        }
-                    }
-                }
-                // ---- coalesced stores: 32 x 16 transpose through this warp's private smem tile ----
-                // registers hold one ROW per lane; a direct store would touch 32 different lines per
-                // instruction.  Swizzled 16-byte chunks keep both smem phases bank-conflict free.
-                const int64_t gcol0 = n0 + c0;
-                if (ep.y != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        stg[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                    __syncwarp();
-                    float4 vals[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {                 // all shared-memory reads first ...
-                        const int r = i * 8 + (lane >> 2), ch = lane & 3;
-                        vals[i] = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {                 // ... then the (predicated) global stores
-                        const int r = i * 8 + (lane >> 2), ch = lane & 3;
-                        const int64_t grow = grow0 + r, gcol = gcol0 + ch * 4;
-                        if (grow < M && gcol < N) *reinterpret_cast<float4*>(ep.y + grow * N + gcol) = vals[i];
-                    }
-                    __syncwarp();
-                }
-                if (ep.y_ctr != nullptr) {
-                    uint4* s2 = reinterpret_cast<uint4*>(stg);
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint4 w;
-                        __nv_bfloat162 h;
-                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1]));
-                        w.x = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
-                        w.y = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
-                        w.z = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
-                        w.w = *reinterpret_cast<uint32_t*>(&h);
-                        s2[lane * 2 + (c ^ ((lane >> 2) & 1))] = w;
-                    }
-                    __syncwarp();
-                    uint4 cv[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int r = i * 16 + (lane >> 1), ch = lane & 1;
-                        cv[i] = s2[r * 2 + (ch ^ ((r >> 2) & 1))];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int r = i * 16 + (lane >> 1), ch = lane & 1;
-                        const int64_t grow = grow0 + r, gcol = gcol0 + ch * 8;
-                        if (grow < M && gcol < N) *reinterpret_cast<uint4*>(ep.y_ctr + grow * N + gcol) = cv[i];
-                    }
-                    __syncwarp();
-                }
+            const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t tf = tfull_bar(acc);
+            const bool fast = has_q && !exact && ep.tile_minmax == nullptr && ep.act_fn <= 1;
+            const int mode = !fast ? -1 : (has_res ? 4 : ep.act_fn * 2) + (percol ? 1 : 0);
+            switch (mode) {                                      // warp-uniform
+                case 0: epi_tile_fast<BN, 0, false, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
+                case 1: epi_tile_fast<BN, 0, true, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
+                case 2: epi_tile_fast<BN, 1, false, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
+                case 3: epi_tile_fast<BN, 1, true, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
+                case 4: epi_tile_fast<BN, 0, false, true>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
+                case 5: epi_tile_fast<BN, 0, true, true>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
+                default:
+                    epi_tile_generic<BN>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, has_q, has_res, tf,
+                                         acc_phase, run_min, run_max);
+                    break;
             }
             if (et == 0) TQ_TRACE(9);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_remote(tempty_bar(acc), 0u);      // the leader's barrier
+                else mbar_arrive(tempty_bar(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (ep.tile_minmax != nullptr) {
@@ -615,12 +766,17 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     // ---- teardown ----
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();
     if (threadIdx.x == 0) TQ_TRACE(10);
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)kTmemCols)
-                     : "memory");
+        if (CTAS == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)kTmemCols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)kTmemCols)
+                         : "memory");
     }
 }
 
@@ -675,52 +831,74 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
     return r == CUDA_SUCCESS ? TQ_OK : TQ_EINVAL;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K, int k_split, const EpiArgs& ep,
                   cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CTAS>;
     static_assert(C::kSmemBytes <= 227 * 1024, "shared memory budget");
     static_assert(2 * BN <= kTmemCols, "TMEM budget");
     CUtensorMap map_a, map_w;
     if (int e = make_map(&map_a, a, M, K * k_split, BM)) return e;
-    if (int e = make_map(&map_w, w, N, K, BN)) return e;
+    if (int e = make_map(&map_w, w, N, K, C::kBRows)) return e;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_qdq_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(linear_qdq_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    return launch_pdl(linear_qdq_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, map_a, map_w, M, N, K,
-                      k_split, ep);
+    const int64_t tiles = ((M + BM * CTAS - 1) / (BM * CTAS)) * ((N + BN - 1) / BN);
+    const int64_t slots = sm_count() / CTAS;                       // CTAs (pairs) resident at once
+    const int grid = (int)(tiles < slots ? tiles : slots) * CTAS;
+    int ring = C::kStages;
+    if (const char* e = getenv("TQ_LINEAR_STAGES")) {              // tuning aid (tools/mainloop_probe.py)
+        const int f = atoi(e);
+        if (f >= 1 && f < ring) ring = f;
+    }
+    return launch_pdl(linear_qdq_kernel<BN, CTAS>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, CTAS, map_a, map_w,
+                      M, N, K, k_split, ring, ep);
 }
 
-// Tile width.  Cycle model from the clock64 timeline of the kernel (tools/trace_linear.py): the main
-// loop advances one k-block per ~600 cycles whatever the tile width, the epilogue is bound by FP32 issue (~75 cycles per
-// 16-column slice per warp: ~2.1 k cycles, ~3.4 k with GELU/tanh -- FMA-pipe and store bound); with double-buffered TMEM a CTA that owns t
-// tiles takes  setup + main + (t-1) * max(main, epi) + epi.
-static int pick_bn(int64_t M, int64_t N, int64_t K, int k_split, int act_fn) {
+// Tile shape.  Cycle model from the clock64 timeline of the kernel (tools/trace_linear.py,
+// tools/sweep_linear.py): with every SM streaming operands the main loop is bound by the L2 -> SM
+// feed (~43 B/clk/SM) unless the tile is wide enough for the MMA itself (128 x bn x 64 MACs per CTA
+// at 4096 MAC/clk) to take longer; the epilogue costs ~0.9 k cycles per 16-column slice per warp
+// (1.4 k with GELU, 1.5 k with the residual branch).  With double-buffered TMEM a CTA that owns t
+// tiles takes  setup + main + (t-1) * max(main, epi) + epi.  CTA pairs (ctas = 2) stage half of the
+// weight tile each, which cuts the feed per flop.
+struct TileShape {
+    int bn, ctas;
+};
+static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act_fn, bool has_res) {
     const int cands[5] = {256, 192, 128, 96, 64};
-    const int64_t m_tiles = (M + BM - 1) / BM;
+    int force_bn = 0, force_ctas = 0;
+    if (const char* e = getenv("TQ_LINEAR_BN")) force_bn = atoi(e);          // tuning aids
+    if (const char* e = getenv("TQ_LINEAR_CTAS")) force_ctas = atoi(e);
     const int sms = sm_count();
-    int best = 64;
+    TileShape best = {64, 1};
     double best_cost = 1e30;
-    for (int i = 0; i < 5; ++i) {
-        const int bn = cands[i];
-        if (bn > 64 && N < bn) continue;                 // TMA box must fit inside the weight matrix
-        const int64_t tiles = m_tiles * ((N + bn - 1) / bn);
-        const double per_cta = (double)((tiles + sms - 1) / sms);
-        // per 64-wide k-block: ~600 cycles of TMA->MMA hand-off latency (measured, independent of the
-        // tile width up to 192) or the MMA time itself (128 x bn x 64 MACs at 4096 MAC/clk)
-        const double mma_c = bn * 2.05;
-        const double main_c = (double)(K / BK) * k_split * (mma_c > 600.0 ? mma_c : 600.0);
-        const double epi_c = (bn / 16.0 / 3.0) * (act_fn == 1 || act_fn == 3 ? 3400.0 : 2100.0);
-        const double cost = 800.0 + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
-        if (cost < best_cost) {
-            best_cost = cost;
-            best = bn;
+    for (int ctas = 1; ctas <= 2; ++ctas) {
+        if (force_ctas != 0 && ctas != force_ctas) continue;
+        for (int i = 0; i < 5; ++i) {
+            const int bn = cands[i];
+            if (force_bn != 0 && bn != force_bn && !(force_bn > N && bn == 64)) continue;
+            if (ctas == 2 && (bn < 128 || M < 2 * BM)) continue;
+            if (bn > 64 && N < bn) continue;             // TMA box must fit inside the weight matrix
+            const int64_t tiles = ((M + BM * ctas - 1) / (BM * ctas)) * ((N + bn - 1) / bn);
+            const int64_t slots = sms / ctas;
+            const double per_cta = (double)((tiles + slots - 1) / slots);
+            const double mma_c = bn * 2.05;
+            const double feed_c = (16384.0 + (bn / ctas) * 128.0) / 43.0;
+            double kb_c = mma_c > feed_c ? mma_c : feed_c;
+            if (kb_c < 450.0) kb_c = 450.0;              // TMA -> MMA hand-off latency floor
+            const double main_c = (double)(K / BK) * k_split * kb_c;
+            const double epi_c = (bn / 16.0 / 3.0) * (has_res ? 1500.0 : (act_fn == 1 || act_fn == 3 ? 1400.0 : 900.0));
+            const double cost = 1500.0 + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best.bn = bn;
+                best.ctas = ctas;
+            }
         }
     }
     return best;
@@ -774,12 +952,20 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
     ep.out2_q = out2_q;
     ep.out2_params = out2_q_params;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (pick_bn(M, N, K, k_split, act_fn)) {
-        case 256: return launch<256>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
-        case 192: return launch<192>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
-        case 128: return launch<128>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
-        case 96: return launch<96>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
-        default: return launch<64>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+    const TileShape ts = pick_tile(M, N, K, k_split, act_fn, res_ctr_bf16 != nullptr);
+    if (ts.ctas == 2) {
+        switch (ts.bn) {
+            case 256: return launch<256, 2>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+            case 192: return launch<192, 2>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+            default: return launch<128, 2>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+        }
+    }
+    switch (ts.bn) {
+        case 256: return launch<256, 1>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+        case 192: return launch<192, 1>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+        case 128: return launch<128, 1>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+        case 96: return launch<96, 1>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
+        default: return launch<64, 1>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
     }
 }
 
