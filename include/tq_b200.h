@@ -190,6 +190,23 @@ int tq_linear_res_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const
                            tq_qspec out_q, int64_t out_q_params, const void* res_ctr_bf16,
                            tq_qspec res_q, tq_qspec out2_q, int64_t out2_q_params, void* stream);
 
+/* Residual block with the LayerNorm fused into the GEMM epilogue (reference
+ * models/quantized_bert.py:238-245 / 264-277: dense -> QDQ -> + input -> QDQ -> QuantLayerNorm,
+ * autoquant_utils.py:55-66):
+ *     y = out2_q( dequant(out_q(x @ Wq.T + bias)) + res_scale * res_ctr )
+ *     z = ln_q( LayerNorm(y; ln_gamma_q, ln_beta, ln_eps) )
+ * Only z leaves the chip (z fp32 and / or z_ctr bf16 centred grid).  The CTAs that cover one 128-row
+ * panel form a thread-block cluster and exchange the row statistics through distributed shared
+ * memory (two-pass mean / variance in fp32).  out_q, out2_q and ln_q are per-tensor; the weight
+ * quantizer may be per-channel.  N must be a multiple of 128, 192 or 256 with at most 8 tiles per
+ * row panel, else TQ_EUNSUPPORTED (callers run tq_linear_res_qdq_bf16 + tq_ln_qdq_bf16). */
+int tq_linear_res_ln_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias,
+                              float* z, void* z_ctr_bf16, int64_t M, int64_t N, int64_t K,
+                              tq_qspec a_q, tq_qspec w_q, int64_t w_q_params, tq_qspec out_q,
+                              const void* res_ctr_bf16, tq_qspec res_q, tq_qspec out2_q,
+                              const float* ln_gamma_q, const float* ln_beta, float ln_eps,
+                              tq_qspec ln_q, void* stream);
+
 /* ---- fused encoder blocks --------------------------------------------
  * All tensors are centred integer grids in bf16 (x_int - zero_point; dequantized value = scale*ctr).
  *

@@ -74,6 +74,48 @@ def test_linear_residual_epilogue_exact():
     P.assert_same(y, ref, 'residual epilogue dequantized output')
 
 
+@pytest.mark.parametrize('M,N,K', [(384, 768, 192), (4096, 768, 768), (200, 1024, 256), (300, 256, 128), (128, 384, 3072)])
+def test_linear_residual_layernorm_fused(M, N, K):
+    """tq_linear_res_ln_qdq_bf16 (cluster kernel, row statistics through distributed shared memory) vs the
+    unfused chain tq_linear_res_qdq_bf16 + tq_ln_qdq_bf16 and vs the CPU formulation."""
+    ops = tq_native.ops()
+    rs = np.random.RandomState(M + N + K)
+    a = rs.randint(-255, 256, size=(M, K)).astype(np.float32)
+    w = rs.randint(-128, 128, size=(N, K)).astype(np.float32)
+    r = rs.randint(-200, 201, size=(M, N)).astype(np.float32)
+    bias = (rs.randn(N) * 0.3).astype(np.float32)
+    gamma = (1 + 0.1 * rs.randn(N)).astype(np.float32)
+    beta = (0.05 * rs.randn(N)).astype(np.float32)
+    a_sp, a_keep, (a_d, a_z) = asym_spec(ops, -2.0, 3.0)
+    r_sp, r_keep, (r_d, r_z) = asym_spec(ops, -4.0, 4.0)
+    w_d, w_signed = O.sym_set_quant_range(-0.08 * 8 / math.sqrt(K), 0.09 * 8 / math.sqrt(K), 8)
+    wd_t, ws_t = T_(np.atleast_1d(w_d)), torch.tensor(bool(w_signed), device=DEV)
+    w_sp = ops.spec(wd_t, None, ws_t, 8)
+    acc = a.astype(np.float64) @ w.astype(np.float64).T
+    pre = (acc * np.float64(np.float32(O.scale_of(a_d) * O.scale_of(w_d))) + bias.astype(np.float64)).astype(np.float32)
+    g_sp, g_keep, (g_d, g_z) = asym_spec(ops, float(pre.min()), float(pre.max()))
+    g = O.qdq_asym(pre, g_d, g_z, 8)
+    res = (np.float32(O.scale_of(r_d)) * r).astype(np.float32)
+    tot = (g + res).astype(np.float32)
+    u_sp, u_keep, (u_d, u_z) = asym_spec(ops, float(tot.min()) * 0.9, float(tot.max()) * 0.9)
+    u = O.qdq_asym(tot, u_d, u_z, 8)
+    ref_ln = F.layer_norm(torch.from_numpy(u), (N,), torch.from_numpy(gamma), torch.from_numpy(beta), 1e-12).numpy()
+    z_sp, z_keep, (z_d, z_z) = asym_spec(ops, float(ref_ln.min()), float(ref_ln.max()))
+    ref_int = O.qdq_asym(ref_ln, z_d, z_z, 8, return_int=True) - O.asym_zero_point(z_z, 8)
+    at, wt, bt, rt = T_(a).to(torch.bfloat16), T_(w).to(torch.bfloat16), T_(bias), T_(r).to(torch.bfloat16)
+    gt, bet = T_(gamma), T_(beta)
+    z, zc = ops.linear_res_ln(at, wt, bt, M, N, K, a_sp, w_sp, 1, g_sp, rt, r_sp, u_sp, gt, bet, 1e-12, z_sp,
+                              want_f32=True)
+    torch.cuda.synchronize()
+    flips(zc.float().cpu().numpy(), ref_int, 5e-3)                       # vs library LayerNorm on the CPU
+    if N % 256 == 0:                                                     # (the stand-alone LN kernel needs D % 256 == 0)
+        _, uc = ops.linear_res(at, wt, bt, M, N, K, a_sp, w_sp, 1, g_sp, 1, rt, r_sp, u_sp, 1)
+        zc2, _ = ops.ln_qdq(uc, u_sp, 1, gt, bet, 1e-12, z_sp, 1)
+        torch.cuda.synchronize()
+        flips(zc.float().cpu().numpy(), zc2.float().cpu().numpy(), 2e-3)     # vs the unfused kernels
+    assert torch.equal(z, zc.float() * float(O.scale_of(z_d)))
+
+
 @pytest.mark.parametrize('D', [256, 768, 1024])
 def test_ln_qdq_kernel(D):
     ops = tq_native.ops()
@@ -235,14 +277,24 @@ def test_engine_matches_module_path(n_bits, use_mask):
     zs = float(z.scale)
     dh = ((eng.hidden_states() - ref_hidden).abs() / zs).cpu().numpy()
     assert dh.max() <= 4.5 and (dh > 0.5).mean() < 0.05, (dh.max(), (dh > 0.5).mean())
-    # the engine is deterministic and graph-capturable
-    l0 = eng.ops.launches
-    graph = torch.cuda.CUDAGraph()
-    static_ids = ids[2].clone()
-    with torch.cuda.graph(graph):
-        out = eng(static_ids, mask)
-    n_launch = eng.ops.launches - l0
-    graph.replay()
-    torch.cuda.synchronize()
-    assert torch.equal(out, logits)
-    assert n_launch == 1 + 7 * 2 + 2
+    # the engine is deterministic and graph-capturable; without a trace request the two residual
+    # blocks of a layer run with the LayerNorm fused in (5 kernels per layer instead of 7)
+    for fuse, per_layer in ((True, 5), (False, 7)):
+        eng.fuse_ln = fuse
+        eager = eng(ids[2], mask)
+        torch.cuda.synchronize()
+        assert (eager - ref_logits).abs().max().item() <= 3 * cls_step + 1e-6
+        dh = ((eng.hidden_states() - ref_hidden).abs() / zs).cpu().numpy()
+        assert dh.max() <= 4.5 and (dh > 0.5).mean() < 0.05, (fuse, dh.max(), (dh > 0.5).mean())
+        if not fuse:
+            assert torch.equal(eager, logits)
+        l0 = eng.ops.launches
+        graph = torch.cuda.CUDAGraph()
+        static_ids = ids[2].clone()
+        with torch.cuda.graph(graph):
+            out = eng(static_ids, mask)
+        n_launch = eng.ops.launches - l0
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager)
+        assert n_launch == 1 + per_layer * 2 + 2

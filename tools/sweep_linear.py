@@ -39,8 +39,11 @@ def bench(fn, per_graph=20, replays=5):
 
 
 cases = [('qkv   2304x768 percol', 2304, 768, 0, True, False), ('attout 768x768 res', 768, 768, 0, False, True),
-         ('ffn_in 3072x768 gelu', 3072, 768, 1, False, False), ('ffnout 768x3072 res', 768, 3072, 0, False, True)]
+         ('ffn_in 3072x768 gelu', 3072, 768, 1, False, False), ('ffnout 768x3072 res', 768, 3072, 0, False, True),
+         ('attout 768x768 res+LN', 768, 768, 0, False, 'ln'), ('ffnout 768x3072 res+LN', 768, 3072, 0, False, 'ln')]
 combos = [(1, '256'), (1, '192'), (1, '128'), (1, '96'), (2, '256'), (2, '192'), (2, '128'), (None, None)]
+if os.environ.get('SWEEP_QUICK'):
+    combos = [(1, '256'), (1, '192'), (None, None)]
 print('%-24s' % 'case (ctas x bn)', ' '.join('%8s' % ('auto' if c is None else '%dx%s' % (c, b)) for c, b in combos))
 for name, N, K, act, percol, res in cases:
     a = torch.randint(-128, 128, (M, K), device=dev).to(torch.bfloat16)
@@ -50,7 +53,11 @@ for name, N, K, act, percol, res in cases:
     a_sp = spec(0.02, 128); w_sp = spec(0.001, None, True, N)
     o_sp = spec(0.05, 120, None, N if percol else 1); r_sp = spec(0.03, 128); o2_sp = spec(0.06, 125)
     yc = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    if res:
+    if res == 'ln':
+        gamma = torch.ones(N, device=dev); beta = torch.zeros(N, device=dev); ln_sp = spec(0.03, 120)
+        fn = lambda: ops.linear_res_ln(a, w, bias, M, N, K, a_sp, w_sp, N, o_sp, r, r_sp, o2_sp, gamma, beta, 1e-12,
+                                       ln_sp, out_ctr=yc)
+    elif res:
         fn = lambda: ops.linear_res(a, w, bias, M, N, K, a_sp, w_sp, N, o_sp, 1, r, r_sp, o2_sp, 1, out_ctr=yc)
     else:
         fn = lambda: ops.linear(a, w, bias, M, N, K, 1, a_sp, w_sp, N, act, o_sp, N if percol else 1,

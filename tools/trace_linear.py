@@ -27,3 +27,31 @@ for (M, N, K, act) in [(4096, 768, 768, 0), (4096, 3072, 768, 1), (4096, 768, 30
         torch.cuda.synchronize()
         t = trace.tolist()
         print((M, N, K, act), label, ' '.join(f'{n}={t[i] - t[0]}' for i, n in enumerate(names) if n in ('mma_done', 'epi_acc_ready', 'epi_done', 'teardown')))
+
+
+# residual + fused LayerNorm (cluster kernel): the timeline buffer is passed through TQ_LINEAR_TRACE_PTR
+names_ln = {4: 'first_full', 6: 'mma_issued', 8: 'acc_ready', 11: 'pass1_done', 12: 'stats_exchanged', 9: 'epi_done', 10: 'teardown'}
+for (M, N, K) in [(4096, 768, 768), (4096, 768, 3072)]:
+    a = torch.randint(-255, 256, (M, K), device=dev).to(torch.bfloat16)
+    w = torch.randint(-128, 128, (N, K), device=dev).to(torch.bfloat16)
+    r = torch.randint(-128, 128, (M, N), device=dev).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    gamma = torch.ones(N, device=dev); beta = torch.zeros(N, device=dev)
+    d = torch.tensor([0.02], device=dev); z = torch.tensor([128.0], device=dev)
+    od = torch.tensor([0.05], device=dev); oz = torch.tensor([120.0], device=dev)
+    ws_ = torch.tensor([0.001], device=dev); sg = torch.tensor(True, device=dev)
+    a_spec = ops.spec(d, z, None, 8); o_spec = ops.spec(od, oz, None, 8); w_spec = ops.spec(ws_, None, sg, 8)
+    yc = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    trace = torch.zeros(16, dtype=torch.int64, device=dev)
+    os.environ['TQ_LINEAR_TRACE_PTR'] = hex(trace.data_ptr())
+    for bn in (None, '256'):
+        if bn:
+            os.environ['TQ_LINEAR_BN'] = bn
+        for it in range(3):
+            ops.linear_res_ln(a, w, bias, M, N, K, a_spec, w_spec, 1, o_spec, r, a_spec, o_spec, gamma, beta, 1e-12, o_spec,
+                              out_ctr=yc)
+        torch.cuda.synchronize()
+        t = trace.tolist()
+        print((M, N, K), 'res+LN bn=%s' % (bn or 'auto'), ' '.join(f'{n}={t[i] - t[0]}' for i, n in names_ln.items()))
+    os.environ.pop('TQ_LINEAR_BN', None)
+    os.environ.pop('TQ_LINEAR_TRACE_PTR', None)

@@ -5,10 +5,10 @@
 // six QDQ kernels.  Here the GEMM consumes the INTEGER grids of the fake-quantized operands carried
 // in bf16 (exact for |v| <= 256) on the 5th-gen tensor cores:
 //
-//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4-8 stage smem ring
-//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32
+//   warp 12     TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4-8 stage smem ring
+//   warp 13     MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32
 //                              accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2-13  epilogue       tcgen05.ld 32x32b.x16 -> acc * (s_a * s_w[n]) + bias[n] -> act_fn
+//   warps 0-11  epilogue       tcgen05.ld 32x32b.x16 -> acc * (s_a * s_w[n]) + bias[n] -> act_fn
 //                              -> per-tensor or per-column (PEG / fused-QKV) QDQ [-> + residual -> QDQ]
 //                              -> fp32 and/or bf16 centred-integer output (operand format of the next
 //                              GEMM), one 32-byte row piece per lane (STG.256), no smem staging
@@ -27,7 +27,11 @@ constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 B: one SWIZZLE_128B span
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 12;    // three per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31)
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, 12 x epilogue
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // 12 x epilogue, then the TMA producer and the MMA issuer
+// The two single-lane roles sit in the HIGHEST warp ids: the warp scheduler favours higher ids, and an
+// issue-bound epilogue (GELU) sharing a scheduler with a low-id producer / MMA warp starved the main
+// loop of the next tile (measured: time per tile = main + epilogue instead of max(main, epilogue)).
+constexpr int kProdWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 
@@ -40,7 +44,8 @@ struct Cfg {
     static constexpr int kBRows = BN / CTAS;          // weight rows staged by this CTA
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kParamBytes = 12 * BN * 4;   // six float4 arrays per column pair (see "epilogue parameters")
+    static constexpr int kXchgFloats = 6 * BM + 2 * 8 * BM;       // LayerNorm row statistics (fused LN epilogue)
+    static constexpr int kParamBytes = 14 * BN * 4 + kXchgFloats * 4;   // seven float4 arrays per column pair + exchange
     // as many ring stages as fit beside the parameters (227 KB per CTA): the main loop is bound by
     // the TMA -> MMA hand-off latency, so depth is what buys throughput
     static constexpr int kStagesFit = (227 * 1024 - 1024 - kParamBytes - 256) / kStageBytes;
@@ -106,6 +111,20 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// store one float at the same shared-memory offset of CTA `rank` of the cluster (distributed smem)
+__device__ __forceinline__ void st_remote_f32(uint32_t local_addr, uint32_t rank, float v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.f32 [ra], %2;\n\t}"
+        ::"r"(local_addr), "r"(rank), "f"(v)
+        : "memory");
 }
 // arrive on the same barrier of CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
@@ -276,6 +295,7 @@ __device__ __forceinline__ void st_row32(void* p, bool wide, bool full, const ui
 //   P[2][jp] = {r.x,  r.y,  clo.x, clo.y}    RN(1/s), lower clamp bound lo - zp (centred domain)
 //   P[3][jp] = {chi.x, chi.y, chi2.x, chi2.y}  upper clamp bounds hi - zp of both quantizers
 //   P[4][jp] = {s2, -s2}, P[5][jp] = {r2, clo2}   quantizer of the residual sum
+//   P[6][jp] = {gamma.x, gamma.y, beta.x, beta.y}  LayerNorm weight (fake-quantized) and bias (fused LN)
 // A per-tensor quantizer (the common case) is read once per tile into registers (QReg).
 __device__ __forceinline__ int pidx(int bn, int arr, int slot, int j) {       // float index
     return ((arr * (bn >> 1) + (j >> 1)) << 2) + (slot << 1) + (j & 1);
@@ -313,12 +333,19 @@ struct EpiArgs {
     int act_fn;
     float* tile_minmax;     // optional calibration side reduction (ordered-int encoded, 2 words)
     long long* trace;       // optional: clock64 timeline of CTA 0 (16 slots), for tools/trace_linear.py
+    long long* trace_all;   // optional: {globaltimer start, end, smid, clock64 span} per CTA (tools/trace_ctas.py)
     // residual branch (attention-output / FFN-output blocks of the encoder, reference
     // models/quantized_bert.py:238-245, 264-277):  y = Q2( dequant(Q1(linear)) + res_scale * res_ctr )
     const __nv_bfloat16* res_ctr;   // [M, N] centred integer grid of the residual input, or null
     tq_qspec res_q;                 // its (per-tensor) quantizer
     tq_qspec out2_q;                // quantizer of the residual sum
     int64_t out2_params;            // 1 or N
+    // fused LayerNorm of the residual sum (reference models/quantized_bert.py:245, 277 -> QuantLayerNorm,
+    // autoquant_utils.py:55-66):  z = ln_q( LayerNorm(y; gamma_q, beta, eps) );  ln_gamma != null selects it
+    const float* ln_gamma;          // [N] fake-quantized LayerNorm weight
+    const float* ln_beta;           // [N]
+    float ln_eps;
+    tq_qspec ln_q;                  // per-tensor output quantizer
 };
 
 #define TQ_TRACE(slot) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[slot] = clock64(); } while (0)
@@ -361,7 +388,7 @@ __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* pa
     if (RES && row_ok && n0 + c0 < N) ld_row32(res_row + c0, wide_c, n0 + c0 + 16 <= N, rnext);
     mbar_wait(tfull, tphase);
     tc_fence_after();
-    if (threadIdx.x == 64) TQ_TRACE(8);
+    if (threadIdx.x == 0) TQ_TRACE(8);
 #pragma unroll 1
     for (; c0 < BN; c0 += 48) {
         const int64_t gcol = n0 + c0;
@@ -435,6 +462,202 @@ __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* pa
                 float* yr = ep.y + row * N + gcol;
                 st_row32(yr, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
                 if (full) st_row32(yr + 8, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&w[8]));
+            }
+        }
+    }
+}
+
+// centred integers for a pair, FAST (division-free, see ctr2) or with the IEEE division instruction
+template <bool FAST>
+__device__ __forceinline__ float2 ctr2_t(float2 x, const QReg& q) {
+    if (FAST) return ctr2(x, q);
+    float2 k;
+    k.x = fminf(fmaxf(rint_even(__fdiv_rn(x.x, q.s.x)), q.clo.x), q.chi.x);
+    k.y = fminf(fmaxf(rint_even(__fdiv_rn(x.y, q.s.y)), q.clo.y), q.chi.y);
+    return k;
+}
+
+// 8-column TMEM accesses (32 lanes x 8 words): the fused LayerNorm epilogue parks its packed
+// intermediate in the accumulator columns it has already consumed
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8_nowait(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Residual block with the LayerNorm fused in (one tile per CTA, the CTAs of a cluster cover the N
+// columns of their 128 rows).  Three compact loops over the warp's 16-column slices (a fully unrolled
+// body that kept the intermediate in registers was instruction-fetch bound: every instruction ran
+// once):
+//   loop 1   y = Q2( dequant(Q1(acc * cs + bias)) + res )  -> packed bf16 centred integers, parked in
+//            the first 8 of the 16 accumulator columns just read (TMEM); lane sum of scale * y
+//   loop 2   squared deviations from the LANE's own mean
+//   exchange lane partials -> smem (3 warps per row) -> every CTA of the cluster (distributed shared
+//            memory) -> one cluster barrier -> mean, variance by pairwise combination (Chan et al.):
+//            as accurate as a global two-pass variance
+//   loop 3   z = Q3( (v - mean) * rstd * gamma + beta ) -> bf16 grid / fp32
+// All three quantizers are per-tensor here (the host routes anything else to the unfused kernels).
+template <int BN, bool FAST>
+__device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params, uint32_t tmem_tile, int third, int quarter,
+                                                int lane, int64_t row, bool row_ok, int64_t n0, int64_t N,
+                                                float res_scale, uint32_t tfull, uint32_t tphase) {
+    constexpr int HP = BN / 2;
+    const float4* P = reinterpret_cast<const float4*>(params);
+    float* part = params + 14 * BN;                    // [2][3][BM] lane partials (sum | squared deviations)
+    float* xs = part + 6 * BM;                         // [8][BM][2] (sum, M2) of every CTA of the cluster
+    QReg q1, q2, q3;
+    {
+        const float4 a = P[HP], b = P[2 * HP], c = P[3 * HP], d = P[4 * HP], e = P[5 * HP];
+        q1.s = make_float2(a.x, a.y); q1.ns = make_float2(a.z, a.w);
+        q1.r = make_float2(b.x, b.y); q1.clo = make_float2(b.z, b.w);
+        q1.chi = make_float2(c.x, c.y);
+        q2.s = make_float2(d.x, d.y); q2.ns = make_float2(d.z, d.w);
+        q2.r = make_float2(e.x, e.y); q2.clo = make_float2(e.z, e.w);
+        q2.chi = make_float2(c.z, c.w);
+        float lo, hi;
+        grid_of(ep.ln_q, lo, hi);
+        const QP p3 = resolve(ep.ln_q, 0, lo, hi);
+        q3.s = splat(p3.scale); q3.ns = splat(-p3.scale); q3.r = splat(p3.rcp);
+        q3.clo = splat(lo - p3.zp); q3.chi = splat(hi - p3.zp);
+    }
+    const uint32_t cn = cluster_nctarank(), my = cluster_ctarank();
+    const int rl = quarter * 32 + lane;                // row inside the tile
+    const bool wide_c = ((((uintptr_t)ep.y_ctr) | ((uintptr_t)ep.res_ctr)) & 31u) == 0 && (N & 15) == 0;
+    const bool wide_y = (((uintptr_t)ep.y) & 31u) == 0;
+    const __nv_bfloat16* res_row = ep.res_ctr + row * N + n0;
+    uint32_t rnext[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rnext[i] = 0u;
+    if (row_ok) ld_row32(res_row + third * 16, wide_c, true, rnext);
+    mbar_wait(tfull, tphase);
+    tc_fence_after();
+    if (threadIdx.x == 0) TQ_TRACE(8);
+
+    // ---- loop 1 ----
+    float s = 0.0f;
+    int n_loc = 0;
+#pragma unroll 1
+    for (int c0 = third * 16; c0 < BN; c0 += 48) {
+        uint32_t v[16];
+        tmem_ld16(tmem_tile + (uint32_t)c0, v);
+        uint32_t rw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rw[j] = rnext[j];
+        if (row_ok && c0 + 48 < BN) ld_row32(res_row + c0 + 48, wide_c, true, rnext);
+        uint32_t kp[8];
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp) {
+            const float4 p0 = P[(c0 >> 1) + jp];
+            const float2 f = __ffma2_rn(make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])),
+                                        make_float2(p0.x, p0.y), make_float2(p0.z, p0.w));
+            const float2 c = ctr2_t<FAST>(f, q1);
+            const uint32_t pair = rw[jp];
+            const float2 sum = __fadd2_rn(
+                make_float2(__fmul_rn(q1.s.x, c.x), __fmul_rn(q1.s.y, c.y)),
+                make_float2(__fmul_rn(res_scale, __uint_as_float(pair << 16)),
+                            __fmul_rn(res_scale, __uint_as_float(pair & 0xffff0000u))));
+            const float2 k = ctr2_t<FAST>(sum, q2);
+            kp[jp] = pack_bf16(k);
+            s = __fadd_rn(s, __fmul_rn(q2.s.x, k.x));                       // LayerNorm input = scale * (x_int - zp)
+            s = __fadd_rn(s, __fmul_rn(q2.s.y, k.y));
+        }
+        tmem_st8_nowait(tmem_tile + (uint32_t)c0, kp);
+        n_loc += 16;
+    }
+    tmem_st_wait();
+    // ---- loop 2: squared deviations from the lane's own mean ----
+    const float m_loc = __fdiv_rn(s, (float)n_loc);
+    float m2 = 0.0f;
+#pragma unroll 1
+    for (int c0 = third * 16; c0 < BN; c0 += 48) {
+        uint32_t kp[8];
+        tmem_ld8(tmem_tile + (uint32_t)c0, kp);
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp) {
+            const float dx = __fsub_rn(__fmul_rn(q2.s.x, __uint_as_float(kp[jp] << 16)), m_loc);
+            const float dy = __fsub_rn(__fmul_rn(q2.s.y, __uint_as_float(kp[jp] & 0xffff0000u)), m_loc);
+            m2 = __fmaf_rn(dx, dx, m2);
+            m2 = __fmaf_rn(dy, dy, m2);
+        }
+    }
+    if (threadIdx.x == 0) TQ_TRACE(11);
+    // ---- exchange ----
+    part[third * BM + rl] = s;
+    part[(3 + third) * BM + rl] = m2;
+    asm volatile("bar.sync 1, 384;" ::: "memory");
+    if (third == 0) {
+        float S = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) S = __fadd_rn(S, part[t * BM + rl]);
+        const float mc = __fdiv_rn(S, (float)BN);
+        float M2c = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int n_t = 16 * ((BN - t * 16 + 47) / 48);                 // values held by a lane of warp-third t
+            const float dm = __fsub_rn(__fdiv_rn(part[t * BM + rl], (float)n_t), mc);
+            M2c = __fadd_rn(M2c, __fmaf_rn((float)n_t * dm, dm, part[(3 + t) * BM + rl]));
+        }
+        const uint32_t dst = smem_u32(xs + (my * BM + rl) * 2);
+        for (uint32_t r = 0; r < cn; ++r) {
+            st_remote_f32(dst, r, S);
+            st_remote_f32(dst + 4, r, M2c);
+        }
+    }
+    cluster_sync_all();
+    if (threadIdx.x == 0) TQ_TRACE(12);
+    float tot = 0.0f;
+    for (uint32_t r = 0; r < cn; ++r) tot = __fadd_rn(tot, xs[(r * BM + rl) * 2]);
+    const float mean = __fdiv_rn(tot, (float)N);
+    float M2 = 0.0f;
+    for (uint32_t r = 0; r < cn; ++r) {
+        const float dm = __fsub_rn(__fdiv_rn(xs[(r * BM + rl) * 2], (float)BN), mean);
+        M2 = __fadd_rn(M2, __fmaf_rn((float)BN * dm, dm, xs[(r * BM + rl) * 2 + 1]));
+    }
+    const float rstd = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(M2, (float)N), ep.ln_eps)));
+    // ---- loop 3: normalise, affine, output quantizer ----
+    const float2 nmean = splat(-mean), rstd2 = splat(rstd);
+#pragma unroll 1
+    for (int c0 = third * 16; c0 < BN; c0 += 48) {
+        uint32_t kp[8];
+        tmem_ld8(tmem_tile + (uint32_t)c0, kp);
+        float2 k3[8];
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp) {
+            const float2 v = make_float2(__fmul_rn(q2.s.x, __uint_as_float(kp[jp] << 16)),
+                                         __fmul_rn(q2.s.y, __uint_as_float(kp[jp] & 0xffff0000u)));
+            const float4 gb = P[6 * HP + (c0 >> 1) + jp];
+            float2 y = __fmul2_rn(__fadd2_rn(v, nmean), rstd2);
+            y = __ffma2_rn(y, make_float2(gb.x, gb.y), make_float2(gb.z, gb.w));
+            k3[jp] = ctr2_t<FAST>(y, q3);
+        }
+        if (row_ok) {
+            const int64_t gcol = n0 + c0;
+            if (ep.y_ctr != nullptr) {
+                uint32_t w[8];
+#pragma unroll
+                for (int jp = 0; jp < 8; ++jp) w[jp] = pack_bf16(k3[jp]);
+                st_row32(ep.y_ctr + row * N + gcol, wide_c, true, w);
+            }
+            if (ep.y != nullptr) {
+                uint32_t w[16];
+#pragma unroll
+                for (int jp = 0; jp < 8; ++jp) {
+                    const float2 o = __fmul2_rn(q3.s, k3[jp]);
+                    w[2 * jp] = __float_as_uint(o.x);
+                    w[2 * jp + 1] = __float_as_uint(o.y);
+                }
+                float* yr = ep.y + row * N + gcol;
+                st_row32(yr, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+                st_row32(yr + 8, wide_y, true, *reinterpret_cast<uint32_t(*)[8]>(&w[8]));
             }
         }
     }
@@ -517,7 +740,9 @@ __device__ __forceinline__ void epi_tile_generic(const EpiArgs& ep, const float*
     }
 }
 
-template <int BN, int CTAS>
+// LNF: residual block with the LayerNorm fused into the epilogue -- one tile per CTA, launched as
+// clusters of N / BN CTAs that exchange the row statistics through distributed shared memory.
+template <int BN, int CTAS, bool LNF>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   int64_t M, int64_t N, int64_t K, int k_split, int ring, EpiArgs ep) {
@@ -545,16 +770,39 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int num_kb = kb_per_pass * k_split;
 
     if (threadIdx.x == 0) TQ_TRACE(0);
-    if (warp == 0 && lane == 0) {
+    long long t_start_ns = 0, t_start_clk = 0;
+    if (ep.trace_all != nullptr && threadIdx.x == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
+        t_start_clk = clock64();
+    }
+    // producer state; a single CTA starts its first loads BEFORE the TMEM allocation / block barrier
+    // below (the first TMA round trip, ~1.5 k cycles, then overlaps the rest of the prologue)
+    int p_stage = 0, p_pre = 0;
+    uint32_t p_phase = 0;
+    if (warp == kProdWarp && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    }
-    if (warp == 1) {
-        if (lane == 0) {
-            for (int s = 0; s < C::kStages; ++s) {
-                mbar_init(full_bar(s), 1);
-                mbar_init(empty_bar(s), 1);
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (CTAS == 1 && tile0 < tiles) {             // (a pair must wait for the peer's barriers)
+            pdl_wait();                               // A is produced by the previous kernel
+            const int32_t m0 = (int32_t)((tile0 / n_tiles) * BM), n0 = (int32_t)((tile0 % n_tiles) * BN);
+            p_pre = num_kb < ring ? num_kb : ring;
+            for (int kb = 0; kb < p_pre; ++kb) {      // ring slots are free: no empty-barrier wait
+                mbar_expect_tx(full_bar(p_stage), C::kStageBytes);
+                const uint32_t sa = base + p_stage * C::kStageBytes;
+                tma_load_2d<1>(sa, &map_a, kb * BK, m0, full_bar(p_stage));
+                tma_load_2d<1>(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BK, n0, full_bar(p_stage));
+                if (++p_stage == ring) { p_stage = 0; p_phase ^= 1u; }
             }
+        }
+    }
+    if (warp == kMmaWarp) {
+        if (lane == 0) {
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
                 mbar_init(tempty_bar(s), kEpiWarps * CTAS);   // one arrival per epilogue warp (of both CTAs)
@@ -582,15 +830,15 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     pdl_wait();                       // A / residual tiles are produced by the previous kernel
     if (threadIdx.x == 0) TQ_TRACE(1);
 
-    if (warp == 0) {
+    if (warp == kProdWarp) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = p_stage;
+            uint32_t phase = p_phase;
             for (int64_t t = tile0; t < tiles; t += tile_step) {
                 const int32_t m0 = (int32_t)((t / n_tiles) * (BM * CTAS) + cta_rank * BM);
                 const int32_t n0 = (int32_t)((t % n_tiles) * BN + cta_rank * C::kBRows);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = (t == tile0 ? p_pre : 0); kb < num_kb; ++kb) {
                     if (kb == 0) TQ_TRACE(2);
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     // the leader's barrier counts the bytes of both CTAs (the MMA issuer waits on it)
@@ -611,7 +859,11 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
+        if (LNF) {                                    // the epilogue's cluster barrier counts every thread
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         if (lane == 0 && cta_rank == 0) {             // the pair's leader issues for both CTAs
             constexpr uint32_t idesc = make_idesc(BM * CTAS, BN);
@@ -644,11 +896,15 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
+        if (LNF) {
+            __syncwarp();
+            cluster_sync_all();
+        }
     } else {
-        // ===================== epilogue (warps 2..13) =====================
-        const int et = threadIdx.x - 64;                       // 0..383
+        // ===================== epilogue (warps 0..11) =====================
+        const int et = threadIdx.x;                            // 0..383
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
-        const int third = (warp - 2) >> 2;                     // 0..2: which of the quarter's three warps
+        const int third = warp >> 2;                           // 0..2: which of the quarter's three warps
         const bool has_q = ep.out_q.delta != nullptr;
         const bool has_res = ep.res_ctr != nullptr;
         const bool percol = (has_q && ep.out_q_params > 1) || (has_res && ep.out2_params > 1);
@@ -676,6 +932,11 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int64_t m0 = (t / n_tiles) * (BM * CTAS) + cta_rank * BM, n0 = (t % n_tiles) * BN;
             asm volatile("bar.sync 1, 384;" ::: "memory");      // previous tile's parameter reads done
             int need_exact = 0;
+            if (LNF) {
+                float lo, hi;
+                grid_of(ep.ln_q, lo, hi);
+                need_exact |= resolve(ep.ln_q, 0, lo, hi).exact;
+            }
             for (int j = et; j < BN; j += kEpiThreads) {
                 const int64_t n = n0 + j;
                 float cs = 0.0f, b = 0.0f, qs = 1.0f, qr = 1.0f, clo = 0.0f, chi = 0.0f;
@@ -715,6 +976,10 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 params[pidx(BN, 4, 1, j)] = -s2;
                 params[pidx(BN, 5, 0, j)] = r2;
                 params[pidx(BN, 5, 1, j)] = clo2;
+                if (LNF) {
+                    params[pidx(BN, 6, 0, j)] = n < N ? ep.ln_gamma[n] : 0.0f;
+                    params[pidx(BN, 6, 1, j)] = n < N ? ep.ln_beta[n] : 0.0f;
+                }
             }
             // barrier + OR-reduction over the 384 epilogue threads (named barrier 1)
             int exact;
@@ -733,6 +998,10 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t tf = tfull_bar(acc);
             const bool fast = has_q && !exact && ep.tile_minmax == nullptr && ep.act_fn <= 1;
             const int mode = !fast ? -1 : (has_res ? 4 : ep.act_fn * 2) + (percol ? 1 : 0);
+            if (LNF) {
+                if (exact) epi_tile_res_ln<BN, false>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, tf, acc_phase);
+                else epi_tile_res_ln<BN, true>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, tf, acc_phase);
+            } else
             switch (mode) {                                      // warp-uniform
                 case 0: epi_tile_fast<BN, 0, false, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
                 case 1: epi_tile_fast<BN, 0, true, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
@@ -768,7 +1037,18 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tc_fence_before();
     if (CTAS == 2) cluster_sync_all(); else __syncthreads();
     if (threadIdx.x == 0) TQ_TRACE(10);
-    if (warp == 1) {
+    if (ep.trace_all != nullptr && threadIdx.x == 0) {
+        long long t_end_ns;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long* o = ep.trace_all + 4 * (long long)blockIdx.x;
+        o[0] = t_start_ns;
+        o[1] = t_end_ns;
+        o[2] = (long long)smid;
+        o[3] = clock64() - t_start_clk;
+    }
+    if (warp == kMmaWarp) {
         if (CTAS == 1)
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                          "r"((uint32_t)kTmemCols)
@@ -831,7 +1111,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
     return r == CUDA_SUCCESS ? TQ_OK : TQ_EINVAL;
 }
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, bool LNF = false>
 static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K, int k_split, const EpiArgs& ep,
                   cudaStream_t st) {
     using C = Cfg<BN, CTAS>;
@@ -842,30 +1122,36 @@ static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K,
     if (int e = make_map(&map_w, w, N, K, C::kBRows)) return e;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_qdq_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(linear_qdq_kernel<BN, CTAS, LNF>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     const int64_t tiles = ((M + BM * CTAS - 1) / (BM * CTAS)) * ((N + BN - 1) / BN);
     const int64_t slots = sm_count() / CTAS;                       // CTAs (pairs) resident at once
-    const int grid = (int)(tiles < slots ? tiles : slots) * CTAS;
+    int grid = (int)(tiles < slots ? tiles : slots) * CTAS;
+    int cluster = CTAS;
+    if (LNF) {                                                     // one tile per CTA, a cluster per 128-row panel
+        cluster = (int)(N / BN);
+        grid = (int)tiles;
+    }
     int ring = C::kStages;
     if (const char* e = getenv("TQ_LINEAR_STAGES")) {              // tuning aid (tools/mainloop_probe.py)
         const int f = atoi(e);
         if (f >= 1 && f < ring) ring = f;
     }
-    return launch_pdl(linear_qdq_kernel<BN, CTAS>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, CTAS, map_a, map_w,
-                      M, N, K, k_split, ring, ep);
+    return launch_pdl(linear_qdq_kernel<BN, CTAS, LNF>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, cluster, map_a,
+                      map_w, M, N, K, k_split, ring, ep);
 }
 
-// Tile shape.  Cycle model from the clock64 timeline of the kernel (tools/trace_linear.py,
-// tools/sweep_linear.py): with every SM streaming operands the main loop is bound by the L2 -> SM
-// feed (~43 B/clk/SM) unless the tile is wide enough for the MMA itself (128 x bn x 64 MACs per CTA
-// at 4096 MAC/clk) to take longer; the epilogue costs ~0.9 k cycles per 16-column slice per warp
-// (1.4 k with GELU, 1.5 k with the residual branch).  With double-buffered TMEM a CTA that owns t
-// tiles takes  setup + main + (t-1) * max(main, epi) + epi.  CTA pairs (ctas = 2) stage half of the
-// weight tile each, which cuts the feed per flop.
+// Tile shape.  Cycle model from the clock64 timelines of the kernel (tools/mainloop_probe.py,
+// tools/trace_linear.py, tools/sweep_linear.py; every SM streaming operands):
+//   * one 64-wide k-block takes ~650 (bn = 64) ... ~820 (bn = 256) cycles for a single CTA and ~715
+//     for a CTA pair whatever bn -- a lone CTA needs ~530, the MMA itself 2 * bn;
+//   * first operands land ~3.5 k cycles after launch (pair: ~6 k, cluster barrier + peer hand-shake);
+//   * the epilogue costs ~0.9 k cycles per 16-column slice per warp (1.05 k with the residual branch,
+//     1.75 k with GELU).
+// With double-buffered TMEM a CTA that owns t tiles takes  setup + main + (t-1) * max(main, epi) + epi.
 struct TileShape {
     int bn, ctas;
 };
@@ -874,6 +1160,7 @@ static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act
     int force_bn = 0, force_ctas = 0;
     if (const char* e = getenv("TQ_LINEAR_BN")) force_bn = atoi(e);          // tuning aids
     if (const char* e = getenv("TQ_LINEAR_CTAS")) force_ctas = atoi(e);
+    if (force_ctas != 2) force_ctas = 1;      // CTA pairs measured no faster on any BERT GEMM: opt-in only
     const int sms = sm_count();
     TileShape best = {64, 1};
     double best_cost = 1e30;
@@ -887,13 +1174,11 @@ static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act
             const int64_t tiles = ((M + BM * ctas - 1) / (BM * ctas)) * ((N + bn - 1) / bn);
             const int64_t slots = sms / ctas;
             const double per_cta = (double)((tiles + slots - 1) / slots);
-            const double mma_c = bn * 2.05;
-            const double feed_c = (16384.0 + (bn / ctas) * 128.0) / 43.0;
-            double kb_c = mma_c > feed_c ? mma_c : feed_c;
-            if (kb_c < 450.0) kb_c = 450.0;              // TMA -> MMA hand-off latency floor
+            double kb_c = ctas == 2 ? 715.0 : 595.0 + 0.9 * bn;
+            if (kb_c < bn * 2.05) kb_c = bn * 2.05;
             const double main_c = (double)(K / BK) * k_split * kb_c;
-            const double epi_c = (bn / 16.0 / 3.0) * (has_res ? 1500.0 : (act_fn == 1 || act_fn == 3 ? 1400.0 : 900.0));
-            const double cost = 1500.0 + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
+            const double epi_c = (bn / 16.0 / 3.0) * (has_res ? 1050.0 : (act_fn == 1 || act_fn == 3 ? 1750.0 : 900.0));
+            const double cost = (ctas == 2 ? 6000.0 : 3500.0) + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
             if (cost < best_cost) {
                 best_cost = cost;
                 best.bn = bn;
@@ -915,7 +1200,8 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
                        void* y_ctr_bf16, int64_t M, int64_t N, int64_t K, int32_t k_split, tq_qspec a_q,
                        tq_qspec w_q, int64_t w_q_params, int32_t act_fn, tq_qspec out_q, int64_t out_q_params,
                        const void* res_ctr_bf16, tq_qspec res_q, tq_qspec out2_q, int64_t out2_q_params,
-                       float* tile_minmax, void* ws, size_t ws_bytes, void* stream) {
+                       float* tile_minmax, void* ws, size_t ws_bytes, void* stream, const float* ln_gamma = nullptr,
+                       const float* ln_beta = nullptr, float ln_eps = 0.0f, const tq_qspec* ln_q = nullptr) {
     using namespace tq::gemm;
     if (res_ctr_bf16 != nullptr) {
         if (out_q.delta == nullptr || res_q.delta == nullptr) return TQ_EINVAL;
@@ -946,12 +1232,54 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
     ep.out_q_params = out_q_params;
     ep.act_fn = act_fn;
     ep.tile_minmax = tile_minmax;
+    if (ws == nullptr) {
+        if (const char* e = getenv("TQ_LINEAR_TRACE_PTR")) {     // tools: device buffer of >= 16 int64 for the timeline
+            ws = reinterpret_cast<void*>(strtoull(e, nullptr, 0));
+            ws_bytes = ws != nullptr ? 16 * sizeof(long long) : 0;
+        }
+    }
     ep.trace = (ws != nullptr && ws_bytes >= 16 * sizeof(long long)) ? reinterpret_cast<long long*>(ws) : nullptr;
+    ep.trace_all = (ws != nullptr && ws_bytes >= (16 + 4 * 160) * sizeof(long long))
+                       ? reinterpret_cast<long long*>(ws) + 16
+                       : nullptr;
     ep.res_ctr = reinterpret_cast<const __nv_bfloat16*>(res_ctr_bf16);
     ep.res_q = res_q;
     ep.out2_q = out2_q;
     ep.out2_params = out2_q_params;
     cudaStream_t st = (cudaStream_t)stream;
+    ep.ln_gamma = ln_gamma;
+    ep.ln_beta = ln_beta;
+    ep.ln_eps = ln_eps;
+    ep.ln_q = ln_q != nullptr ? *ln_q : out_q;
+    if (ln_gamma != nullptr) {
+        // fused LayerNorm: clusters of N / bn CTAs, one tile each (see epi_tile_res_ln)
+        if (res_ctr_bf16 == nullptr || ln_beta == nullptr || ln_q == nullptr) return TQ_EINVAL;
+        if (int e = tq::check_qspec(*ln_q)) return e;
+        if (out_q_params != 1 || out2_q_params != 1 || k_split != 1 || (N & 15) != 0) return TQ_EUNSUPPORTED;
+        const int cands[3] = {256, 192, 128};
+        int best = 0;
+        double best_cost = 1e30;
+        int force_bn = 0;
+        if (const char* e = getenv("TQ_LINEAR_BN")) force_bn = atoi(e);
+        for (int i = 0; i < 3; ++i) {
+            const int bn = cands[i];
+            if (N % bn != 0 || N / bn > 8) continue;
+            if (force_bn != 0 && force_bn != bn && N % force_bn == 0 && N / force_bn <= 8 && force_bn >= 128) continue;
+            const int64_t tiles = ((M + BM - 1) / BM) * (N / bn);
+            const double waves = (double)((tiles + tq::sm_count() - 1) / tq::sm_count());
+            const double cost = waves * ((double)(K / BK) * (595.0 + 0.9 * bn) + (bn / 16.0 / 3.0) * 1600.0 + 4500.0);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = bn;
+            }
+        }
+        switch (best) {
+            case 256: return launch<256, 1, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+            case 192: return launch<192, 1, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+            case 128: return launch<128, 1, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+            default: return TQ_EUNSUPPORTED;
+        }
+    }
     const TileShape ts = pick_tile(M, N, K, k_split, act_fn, res_ctr_bf16 != nullptr);
     if (ts.ctas == 2) {
         switch (ts.bn) {
@@ -987,6 +1315,16 @@ int tq_linear_res_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const
     if (res_ctr_bf16 == nullptr) return TQ_EINVAL;
     return linear_impl(a_ctr_bf16, w_ctr_bf16, bias, y, y_ctr_bf16, M, N, K, 1, a_q, w_q, w_q_params, 0, out_q,
                        out_q_params, res_ctr_bf16, res_q, out2_q, out2_q_params, nullptr, nullptr, 0, stream);
+}
+
+int tq_linear_res_ln_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, float* z,
+                              void* z_ctr_bf16, int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q,
+                              int64_t w_q_params, tq_qspec out_q, const void* res_ctr_bf16, tq_qspec res_q,
+                              tq_qspec out2_q, const float* ln_gamma_q, const float* ln_beta, float ln_eps,
+                              tq_qspec ln_q, void* stream) {
+    if (res_ctr_bf16 == nullptr || ln_gamma_q == nullptr || ln_beta == nullptr) return TQ_EINVAL;
+    return linear_impl(a_ctr_bf16, w_ctr_bf16, bias, z, z_ctr_bf16, M, N, K, 1, a_q, w_q, w_q_params, 0, out_q, 1,
+                       res_ctr_bf16, res_q, out2_q, 1, nullptr, nullptr, 0, stream, ln_gamma_q, ln_beta, ln_eps, &ln_q);
 }
 
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream) {

@@ -2,24 +2,27 @@
 
 Built FROM a calibrated ``engine.bert.QuantBertForSequenceClassification`` (ranges fixed, eval
 mode): it reads the fake-quantized weights and the per-site quantizer buffers of that model and
-runs the same forward -- the same 161 quantizer sites in the same order -- as 7 kernels per encoder
+runs the same forward -- the same 161 quantizer sites in the same order -- as 5 kernels per encoder
 layer, every tensor between them carried as the centred integer grid in bf16 (2 B / element):
 
     embeddings : tq_embed_ln_qdq_bf16                       (3 sites)
     per layer  : tq_linear_qdq_bf16   fused Q|K|V GEMM, per-column output quantizers      (3 sites)
                  tq_attention_qdq_bf16 scores / probs / context                            (3 sites)
-                 tq_linear_res_qdq_bf16 attention-output dense + residual                   (2 sites)
-                 tq_ln_qdq_bf16                                                             (1 site)
+                 tq_linear_res_ln_qdq_bf16 attention-output dense + residual + LayerNorm    (3 sites)
                  tq_linear_qdq_bf16   FFN-in + GELU                                          (1 site)
-                 tq_linear_res_qdq_bf16 FFN-out dense + residual                            (2 sites)
-                 tq_ln_qdq_bf16                                                             (1 site)
+                 tq_linear_res_ln_qdq_bf16 FFN-out dense + residual + LayerNorm             (3 sites)
     head       : pooler (tanh) and classifier through tq_linear_qdq_bf16                   (2 sites)
+
+(``TQ_ENGINE_FUSE_LN=0`` or a ``trace`` request splits the two residual blocks back into
+tq_linear_res_qdq_bf16 + tq_ln_qdq_bf16: 7 kernels per layer.)
 
 The module-level path (quantization.* classes, one kernel per site + library ops) stays the
 reference-facing API and the calibration path; this engine is what the throughput benchmark runs.
 Supported: per-tensor quantizers with n_bits <= 8 at every site, seq 128, head_dim 64, hidden % 256
 == 0.  Anything else raises ``UnsupportedByEngine`` and callers keep using the module path.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -166,6 +169,8 @@ class FusedBertEngine:
         self.f = torch.empty(M, cfg.intermediate_size, **bf)
         self.yb = torch.empty(M, D, **bf)
         self.M = M
+        # residual blocks: LayerNorm fused into the GEMM epilogue (cluster kernel) unless switched off
+        self.fuse_ln = os.environ.get('TQ_ENGINE_FUSE_LN', '1') != '0' and D <= 2048
 
     def _linear(self, a_ctr, a_site, w, act, out_spec, out_params, out_ctr=None, want_f32=False, M=None):
         M = a_ctr.shape[0] if M is None else M
@@ -195,6 +200,8 @@ class FusedBertEngine:
 
         B, T, D, H = self.B, self.T, self.D, self.H
         assert tuple(input_ids.shape) == (B, T)
+        # the pre-LayerNorm sums (sites u / y) only exist in the unfused chain: tracing keeps it
+        fuse_ln = self.fuse_ln and trace is None
         mask = None
         if attention_mask is not None:
             mask = ((1.0 - attention_mask.to(torch.float32)) * -10000.0).contiguous()
@@ -214,20 +221,28 @@ class FusedBertEngine:
                           d['p'].spec, d['c'].spec, mask, out_ctr=self.c)
             rec(f'{li}.c', self.c, d['c'])
             w = d['wg']
-            ops.linear_res(self.c, w.grid, w.bias, self.M, w.N, w.K, d['c'].spec, w.spec, w.N, d['g'].spec, 1,
-                           x, x_site.spec, d['u'].spec, 1, out_ctr=self.u)
             g1, b1, e1 = d['ln1']
-            rec(f'{li}.u', self.u, d['u'])
-            ops.ln_qdq(self.u, d['u'].spec, 1, g1, b1, e1, d['x'].spec, 1, out_ctr=self.a)
+            if fuse_ln:      # dense + residual + LayerNorm in one cluster kernel: only the LN output leaves the chip
+                ops.linear_res_ln(self.c, w.grid, w.bias, self.M, w.N, w.K, d['c'].spec, w.spec, w.N, d['g'].spec,
+                                  x, x_site.spec, d['u'].spec, g1, b1, e1, d['x'].spec, out_ctr=self.a)
+            else:
+                ops.linear_res(self.c, w.grid, w.bias, self.M, w.N, w.K, d['c'].spec, w.spec, w.N, d['g'].spec, 1,
+                               x, x_site.spec, d['u'].spec, 1, out_ctr=self.u)
+                rec(f'{li}.u', self.u, d['u'])
+                ops.ln_qdq(self.u, d['u'].spec, 1, g1, b1, e1, d['x'].spec, 1, out_ctr=self.a)
             rec(f'{li}.x', self.a, d['x'])
             self._linear(self.a, d['x'], d['wf'], 1, d['f'].spec, 1, out_ctr=self.f)
             rec(f'{li}.ffn_in', self.f, d['f'])
             w = d['wh']
-            ops.linear_res(self.f, w.grid, w.bias, self.M, w.N, w.K, d['f'].spec, w.spec, w.N, d['h'].spec, 1,
-                           self.a, d['x'].spec, d['y'].spec, 1, out_ctr=self.yb)
             g2, b2, e2 = d['ln2']
-            rec(f'{li}.y', self.yb, d['y'])
-            ops.ln_qdq(self.yb, d['y'].spec, 1, g2, b2, e2, d['z'].spec, 1, out_ctr=x)
+            if fuse_ln:
+                ops.linear_res_ln(self.f, w.grid, w.bias, self.M, w.N, w.K, d['f'].spec, w.spec, w.N, d['h'].spec,
+                                  self.a, d['x'].spec, d['y'].spec, g2, b2, e2, d['z'].spec, out_ctr=x)
+            else:
+                ops.linear_res(self.f, w.grid, w.bias, self.M, w.N, w.K, d['f'].spec, w.spec, w.N, d['h'].spec, 1,
+                               self.a, d['x'].spec, d['y'].spec, 1, out_ctr=self.yb)
+                rec(f'{li}.y', self.yb, d['y'])
+                ops.ln_qdq(self.yb, d['y'].spec, 1, g2, b2, e2, d['z'].spec, 1, out_ctr=x)
             x_site = d['z']
             rec(f'{li}.z', x, x_site)
         first = x.view(B, T, D)[:, 0].contiguous()                       # pooler input: first token

@@ -77,6 +77,9 @@ SIGNATURES = {
     'tq_linear_res_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p, ctypes.c_void_p,
                                               _i64, _i64, _i64, QSpec, QSpec, _i64, QSpec, _i64, ctypes.c_void_p,
                                               QSpec, QSpec, _i64, ctypes.c_void_p]),
+    'tq_linear_res_ln_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p, ctypes.c_void_p,
+                                                 _i64, _i64, _i64, QSpec, QSpec, _i64, QSpec, ctypes.c_void_p, QSpec,
+                                                 QSpec, _c_f32p, _c_f32p, ctypes.c_float, QSpec, ctypes.c_void_p]),
     'tq_attention_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _i32, QSpec, QSpec,
                                              QSpec, QSpec, QSpec, QSpec, _c_f32p, ctypes.c_void_p]),
     'tq_ln_qdq_bf16': (ctypes.c_int, [ctypes.c_void_p, QSpec, _i64, _c_f32p, _c_f32p, ctypes.c_float, QSpec, _i64,
@@ -309,6 +312,20 @@ class CudaOps:
                   w_ctr.data_ptr(), _ptr(bias), _ptr(y), yc.data_ptr(), M, N, K, a_spec, w_spec, int(w_params),
                   out_spec, int(out_params), res_ctr.data_ptr(), res_spec, out2_spec, int(out2_params), _stream())
         return y, yc
+
+    def linear_res_ln(self, a_ctr, w_ctr, bias, M, N, K, a_spec, w_spec, w_params, out_spec, res_ctr, res_spec,
+                      out2_spec, gamma_q, beta, eps, ln_spec, out_ctr=None, want_f32=False):
+        """tq_linear_res_ln_qdq_bf16: residual block with the LayerNorm fused in -> (z fp32 | None, z_ctr bf16).
+        Raises TQError(TQ_EUNSUPPORTED) for shapes the cluster kernel does not cover."""
+        _chk_cuda(a_ctr, w_ctr, bias, res_ctr, gamma_q, beta)
+        dev = a_ctr.device
+        z = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
+        zc = out_ctr if out_ctr is not None else torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_res_ln_qdq_bf16, a_ctr.data_ptr(),
+                  w_ctr.data_ptr(), _ptr(bias), _ptr(z), zc.data_ptr(), M, N, K, a_spec, w_spec, int(w_params),
+                  out_spec, res_ctr.data_ptr(), res_spec, out2_spec, gamma_q.data_ptr(), beta.data_ptr(), float(eps),
+                  ln_spec, _stream())
+        return z, zc
 
     def attention(self, qkv_ctr, B, T, H, head_dim, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec, mask=None,
                   out_ctr=None):
