@@ -6,7 +6,9 @@
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_model.py
 
 Writes tests/golden/bert_tiny.npz: weights, token ids and, per configuration, the logits, the
-final hidden states and every activation quantizer's (delta, zero_float) after calibration.
+final hidden states and every activation quantizer's (delta, zero_float) after calibration; and
+tests/golden/roberta_tiny.npz: the same for ``models/quantized_roberta.py`` (TQ_GOLDEN_ONLY=roberta
+regenerates only that file).
 """
 import importlib.util
 import os
@@ -60,6 +62,7 @@ def import_reference_model(package_root):
         m.__path__ = [os.path.join(REF, 'models')]
         sys.modules['models'] = m
         qb = load_by_path('models.quantized_bert', os.path.join(REF, 'models', 'quantized_bert.py'))
+        qb.roberta = load_by_path('models.quantized_roberta', os.path.join(REF, 'models', 'quantized_roberta.py'))
     finally:
         sys.path.remove(package_root)
     return qb
@@ -79,6 +82,14 @@ CONFIGS = {
                        act_range_method='current_minmax', peg=('ngp', 4)),
     'w8a8_mse': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
                      act_range_method='MSE', peg=None),
+}
+
+# the reference's models/quantized_roberta.py (BASELINE config 5 family): running min-max and MSE ranges
+ROBERTA_CONFIGS = {
+    'roberta_w8a8': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
+                         act_range_method='running_minmax', peg=None),
+    'roberta_w8a8_mse': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
+                             act_range_method='MSE', peg=None),
 }
 
 
@@ -142,6 +153,99 @@ def run_config(qb, name, cfg, hf_model, batches):
     return res, model
 
 
+def run_roberta_config(qb, name, cfg, hf_model, batches):
+    """models/quantized_roberta.py: quantize -> calibrate on batches[:-1] -> fix -> eval batches[-1]"""
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators
+
+    qparams = dict(method=QMethods[cfg['method']], act_method=QMethods[cfg['act_method']],
+                   n_bits=cfg['n_bits'], n_bits_act=cfg['n_bits_act'], per_channel_weights=False,
+                   percentile=None, quant_setup='all',
+                   weight_range_method=RangeEstimators.current_minmax, weight_range_options={},
+                   act_range_method=RangeEstimators[cfg['act_range_method']], act_range_options={},
+                   quant_dict={})
+    model = qb.roberta.QuantizedRobertaForSequenceClassification(hf_model, **qparams)
+    model.eval()
+    model.set_quant_state(weight_quant=True, act_quant=True)
+    with torch.no_grad():
+        for b in batches[:-1]:
+            model(input_ids=b, attention_mask=torch.ones_like(b))
+        model.fix_ranges()
+        out = model(input_ids=batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+        hidden = model.roberta(batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+    res = {f'{name}.logits': out.logits.numpy().copy(),
+           f'{name}.last_hidden': hidden.last_hidden_state.numpy().copy()}
+    n = 0
+    for mname, m in model.named_modules():
+        q = getattr(m, 'quantizer', None)
+        if q is not None and mname.endswith('activation_quantizer') and q.is_initialized:
+            n += 1
+    res[f'{name}.n_act_quantizers'] = np.array(n)
+    return res, model
+
+
+MOBILEBERT_CONFIGS = {
+    # BASELINE config 4 family: 4-bit symmetric weights, 8-bit asymmetric activations
+    'mobilebert_w4a8': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=4, n_bits_act=8,
+                            act_range_method='running_minmax'),
+    'mobilebert_w8a8': dict(method='symmetric_uniform', act_method='asymmetric_uniform', n_bits=8, n_bits_act=8,
+                            act_range_method='running_minmax'),
+}
+
+
+def import_reference_mobilebert(qb):
+    """models/quantized_mobilebert.py from the reference, on whatever quantization / utils packages
+    ``import_reference_model`` has put in place"""
+    import hf41_shim
+    hf41_shim.install_mobilebert()
+    u = sys.modules['utils']
+    if not hasattr(u, 'DotDict'):
+        ut = load_by_path('utils.utils', os.path.join(REF, 'utils', 'utils.py'))
+        u.DotDict = ut.DotDict
+    return load_by_path('models.quantized_mobilebert', os.path.join(REF, 'models', 'quantized_mobilebert.py'))
+
+
+def run_mobilebert_config(qm, name, cfg, hf_model, batches):
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators
+
+    qparams = dict(method=QMethods[cfg['method']], act_method=QMethods[cfg['act_method']],
+                   n_bits=cfg['n_bits'], n_bits_act=cfg['n_bits_act'], per_channel_weights=False,
+                   percentile=None, quant_setup='all',
+                   weight_range_method=RangeEstimators.current_minmax, weight_range_options={},
+                   act_range_method=RangeEstimators[cfg['act_range_method']], act_range_options={},
+                   quant_dict={})
+    model = qm.QuantizedMobileBertForSequenceClassification(hf_model, **qparams)
+    model.eval()
+    model.set_quant_state(weight_quant=True, act_quant=True)
+    with torch.no_grad():
+        for b in batches[:-1]:
+            model(input_ids=b, attention_mask=torch.ones_like(b))
+        model.fix_ranges()
+        out = model(input_ids=batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+        hidden = model.mobilebert(batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+    n = sum(1 for mname, m in model.named_modules()
+            if getattr(m, 'quantizer', None) is not None and m.quantizer.is_initialized)
+    return {f'{name}.logits': out.logits.numpy().copy(),
+            f'{name}.last_hidden': hidden.last_hidden_state.numpy().copy(),
+            f'{name}.n_quantizers': np.array(n)}, model
+
+
+def make_hf_mobilebert():
+    import hf41_shim
+    return hf41_shim.make_tiny_mobilebert()
+
+
+def make_hf_roberta():
+    import hf41_shim
+    cfg = hf41_shim.TinyBertConfig(pad_token_id=1)
+    m = hf41_shim.RobertaForSequenceClassification(cfg)
+    hf41_shim.init_weights(m, seed=2)
+    hf41_shim.perturb(m, seed=3)
+    m.eval()
+    return m
+
+
 def make_hf_model():
     import hf41_shim
     cfg = hf41_shim.TinyBertConfig()
@@ -166,9 +270,30 @@ if __name__ == '__main__':
     out = {'ids': np.stack([b.numpy() for b in batches])}
     for k, v in hf.state_dict().items():
         out['w.' + k] = v.numpy().copy()
-    for name, cfg in CONFIGS.items():
+    for name, cfg in ({} if os.environ.get('TQ_GOLDEN_ONLY', '') in ('roberta', 'mobilebert') else CONFIGS).items():
         res, _ = run_config(qb, name, cfg, hf, batches)
         out.update(res)
         print(name, 'logits', res[f'{name}.logits'][0], 'act quantizers', int(res[f'{name}.n_act_quantizers']))
-    np.savez_compressed(os.path.join(HERE, 'bert_tiny.npz'), **out)
-    print('bert_tiny.npz', os.path.getsize(os.path.join(HERE, 'bert_tiny.npz')))
+    if os.environ.get('TQ_GOLDEN_ONLY', '') not in ('roberta', 'mobilebert'):
+        np.savez_compressed(os.path.join(HERE, 'bert_tiny.npz'), **out)
+        print('bert_tiny.npz', os.path.getsize(os.path.join(HERE, 'bert_tiny.npz')))
+    hr = make_hf_roberta()
+    outr = {'ids': np.stack([b.numpy() for b in batches])}
+    for k, v in hr.state_dict().items():
+        outr['w.' + k] = v.numpy().copy()
+    for name, cfg in ({} if os.environ.get('TQ_GOLDEN_ONLY', '') == 'mobilebert' else ROBERTA_CONFIGS).items():
+        res, _ = run_roberta_config(qb, name, cfg, hr, batches)
+        outr.update(res)
+        print(name, 'logits', res[f'{name}.logits'][0], 'act quantizers', int(res[f'{name}.n_act_quantizers']))
+    if os.environ.get('TQ_GOLDEN_ONLY', '') != 'mobilebert':
+        np.savez_compressed(os.path.join(HERE, 'roberta_tiny.npz'), **outr)
+        print('roberta_tiny.npz', os.path.getsize(os.path.join(HERE, 'roberta_tiny.npz')))
+    qm = import_reference_mobilebert(qb)
+    hm = make_hf_mobilebert()
+    outm = {'ids': np.stack([b.numpy() for b in batches])}
+    for name, cfg in MOBILEBERT_CONFIGS.items():
+        res, _ = run_mobilebert_config(qm, name, cfg, hm, batches)
+        outm.update(res)
+        print(name, 'logits', res[f'{name}.logits'][0], 'quantizers', int(res[f'{name}.n_quantizers']))
+    np.savez_compressed(os.path.join(HERE, 'mobilebert_tiny.npz'), **outm)
+    print('mobilebert_tiny.npz', os.path.getsize(os.path.join(HERE, 'mobilebert_tiny.npz')))

@@ -164,6 +164,82 @@ class BertForSequenceClassification(nn.Module):
         self.classifier = nn.Linear(c.hidden_size, c.num_labels)
 
 
+# ---- RoBERTa (reference models/quantized_roberta.py): same containers under the Roberta* type names
+# (the reference's ``specials`` tables match on the exact type), pad-aware position ids, and the
+# two-layer classification head.
+class RobertaSelfAttention(BertSelfAttention):
+    pass
+
+
+class RobertaSelfOutput(BertSelfOutput):
+    pass
+
+
+class RobertaAttention(BertAttention):
+    def __init__(self, c):
+        nn.Module.__init__(self)
+        self.self = RobertaSelfAttention(c)
+        self.output = RobertaSelfOutput(c)
+
+
+class RobertaLayer(BertLayer):
+    def __init__(self, c):
+        nn.Module.__init__(self)
+        self.chunk_size_feed_forward = 0
+        self.seq_len_dim = 1
+        self.is_decoder = False
+        self.add_cross_attention = False
+        self.attention = RobertaAttention(c)
+        self.intermediate = BertIntermediate(c)
+        self.output = BertOutput(c)
+
+
+class RobertaEncoder(BertEncoder):
+    def __init__(self, c):
+        nn.Module.__init__(self)
+        self.layer = nn.ModuleList([RobertaLayer(c) for _ in range(c.num_hidden_layers)])
+
+
+class RobertaEmbeddings(BertEmbeddings):
+    def __init__(self, c):
+        super().__init__(c)
+        self.padding_idx = c.pad_token_id
+
+
+class RobertaClassificationHead(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.dense = nn.Linear(c.hidden_size, c.hidden_size)
+        self.dropout = nn.Dropout(c.hidden_dropout_prob)
+        self.out_proj = nn.Linear(c.hidden_size, c.num_labels)
+
+    def forward(self, features, **kwargs):
+        x = features[:, 0, :]
+        x = self.dropout(x)
+        x = self.dense(x)
+        x = torch.tanh(x)
+        x = self.dropout(x)
+        return self.out_proj(x)
+
+
+class RobertaModel(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.config = c
+        self.embeddings = RobertaEmbeddings(c)
+        self.encoder = RobertaEncoder(c)
+        self.pooler = None                     # RobertaForSequenceClassification: add_pooling_layer=False
+
+
+class RobertaForSequenceClassification(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.config = c
+        self.num_labels = c.num_labels
+        self.roberta = RobertaModel(c)
+        self.classifier = RobertaClassificationHead(c)
+
+
 def init_weights(model, seed=0, std=0.02):
     """HF-style random init: normal(0, std) Linear / Embedding weights, zero biases, LN (1, 0)."""
     g = torch.Generator().manual_seed(seed)
@@ -211,3 +287,57 @@ def install():
 
     mu.ModuleUtilsMixin.get_extended_attention_mask = get_extended_attention_mask
     mu.ModuleUtilsMixin.get_head_mask = get_head_mask
+
+    import transformers.models.roberta.modeling_roberta as mr
+    mr.RobertaLayer = RobertaLayer
+    mr.RobertaSelfAttention = RobertaSelfAttention
+    mr.RobertaSelfOutput = RobertaSelfOutput
+
+
+def install_mobilebert():
+    """MobileBERT (reference models/quantized_mobilebert.py): the installed transformers still has the
+    building blocks the reference wraps (NoNorm, BottleneckLayer, FFNLayer, ...), but the container
+    forwards lost ``head_mask`` / ``output_attentions``.  Put the 4.1-style container forwards back."""
+    install()
+    import transformers.models.mobilebert.modeling_mobilebert as mm
+    from transformers.modeling_outputs import BaseModelOutput
+
+    def attention_forward(self, query_tensor, key_tensor, value_tensor, layer_input, attention_mask=None,
+                          head_mask=None, output_attentions=None):
+        self_outputs = self.self(query_tensor, key_tensor, value_tensor, attention_mask, head_mask, output_attentions)
+        attention_output = self.output(self_outputs[0], layer_input)
+        return (attention_output,) + tuple(self_outputs[1:])
+
+    def encoder_forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False,
+                        output_hidden_states=False, return_dict=True):
+        for i, layer_module in enumerate(self.layer):
+            layer_outputs = layer_module(hidden_states, attention_mask, head_mask[i] if head_mask else None,
+                                         output_attentions)
+            hidden_states = layer_outputs[0]
+        return BaseModelOutput(last_hidden_state=hidden_states, hidden_states=None, attentions=None)
+
+    mm.MobileBertAttention.forward = attention_forward
+    mm.MobileBertEncoder.forward = encoder_forward
+    return mm
+
+
+def make_tiny_mobilebert(seed=4):
+    """a 2-layer MobileBERT with every structural feature of the real one (bottlenecks, shared key/query
+    bottleneck, trigram embeddings, stacked FFNs, NoNorm), HF classes, seeded random weights"""
+    mm = install_mobilebert()
+    from transformers import MobileBertConfig
+    cfg = MobileBertConfig(vocab_size=1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=4,
+                           intermediate_size=128, embedding_size=32, intra_bottleneck_size=32,
+                           num_feedforward_networks=2, max_position_embeddings=64, trigram_input=True,
+                           use_bottleneck=True, key_query_shared_bottleneck=True, normalization_type='no_norm',
+                           classifier_activation=False, hidden_dropout_prob=0.0, num_labels=2)
+    torch.manual_seed(seed)
+    m = mm.MobileBertForSequenceClassification(cfg)
+    g = torch.Generator().manual_seed(seed)
+    for p_ in m.parameters():                   # explicit values: independent of HF's init code
+        p_.data = torch.randn(p_.shape, generator=g) * (0.05 if p_.dim() > 1 else 0.1) + (1.0 if p_.dim() == 1 and p_.shape[0] in (32, 128) and False else 0.0)
+    for mod in m.modules():
+        if isinstance(mod, mm.NoNorm):
+            mod.weight.data = 1.0 + 0.1 * torch.randn(mod.weight.shape, generator=g)
+            mod.bias.data = 0.05 * torch.randn(mod.bias.shape, generator=g)
+    return m.eval()

@@ -62,3 +62,45 @@ def test_reference_model_file_runs_unchanged_on_this_package(drop_in, name):
     assert int(res[f'{name}.n_act_quantizers']) == n
     for i in range(n):
         assert np.array_equal(res[f'{name}.q{i}.delta'], G[f'{name}.q{i}.delta']), str(G[f'{name}.q{i}.name'])
+
+
+@pytest.mark.parametrize('name', ['roberta_w8a8', 'roberta_w8a8_mse'])
+def test_reference_roberta_model_file_runs_unchanged_on_this_package(drop_in, name):
+    """models/quantized_roberta.py (BASELINE config 5 family; MSE-grid activation ranges in the second
+    case) -- unchanged reference file on this repo's quantization / utils packages."""
+    gm, qb = drop_in
+    assert qb.roberta.__file__.startswith(REF)
+    G = np.load(os.path.join(GOLDEN, 'roberta_tiny.npz'))
+    torch.set_grad_enabled(False)
+    try:
+        res, model = gm.run_roberta_config(qb, name, gm.ROBERTA_CONFIGS[name], gm.make_hf_roberta(), gm.make_batches())
+    finally:
+        torch.set_grad_enabled(True)
+    assert int(res[f'{name}.n_act_quantizers']) == int(G[f'{name}.n_act_quantizers'])
+    if name.endswith('_mse'):
+        # MSE losses are accumulated in a different (deterministic fp64) order than torch's blocked fp32
+        # sums: the selected grid candidate can differ by one on near-ties -> logits within 2 output steps
+        step = float(model.classifier.out_proj.activation_quantizer.quantizer.scale)
+        assert np.abs(res[f'{name}.logits'] - G[f'{name}.logits']).max() <= 2 * step + 1e-7
+    else:
+        assert np.array_equal(res[f'{name}.logits'], G[f'{name}.logits'])
+        assert np.array_equal(res[f'{name}.last_hidden'], G[f'{name}.last_hidden'])
+
+
+@pytest.mark.parametrize('name', ['mobilebert_w4a8', 'mobilebert_w8a8'])
+def test_reference_mobilebert_model_file_runs_unchanged_on_this_package(drop_in, name):
+    """models/quantized_mobilebert.py (BASELINE config 4 family: W4A8, QuantNoNorm, bottlenecks, stacked
+    FFNs) -- unchanged reference file, HF MobileBERT building blocks, this repo's quantization package."""
+    gm, qb = drop_in
+    qm = gm.import_reference_mobilebert(qb)
+    assert qm.__file__.startswith(REF)
+    G = np.load(os.path.join(GOLDEN, 'mobilebert_tiny.npz'))
+    torch.set_grad_enabled(False)
+    try:
+        res, model = gm.run_mobilebert_config(qm, name, gm.MOBILEBERT_CONFIGS[name], gm.make_hf_mobilebert(),
+                                              gm.make_batches())
+    finally:
+        torch.set_grad_enabled(True)
+    assert int(res[f'{name}.n_quantizers']) == int(G[f'{name}.n_quantizers'])
+    assert np.array_equal(res[f'{name}.logits'], G[f'{name}.logits'])
+    assert np.array_equal(res[f'{name}.last_hidden'], G[f'{name}.last_hidden'])

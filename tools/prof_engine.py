@@ -14,3 +14,8 @@ eng = FusedBertEngine(model, bench.BATCH, bench.SEQ)
 for _ in range(3):
     eng(ids, mask)
 torch.cuda.synchronize()
+# ncu --profile-from-start off: only this forward is captured (5 kernels per encoder layer)
+torch.cuda.profiler.start()
+eng(ids, mask)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()

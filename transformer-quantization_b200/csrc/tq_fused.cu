@@ -213,9 +213,14 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_qdq_kernel(LnArgs a) {
 // attention: T = 128 keys/queries per (batch, head), head_dim = 64
 // ---------------------------------------------------------------------------------------------------
 constexpr int AT = 128, AD = 64;
-constexpr int kAttnThreads = 320;       // warp 0 TMA, warp 1 MMA + TMEM, warps 2-9 softmax / epilogue
-constexpr int kAttnTmemCols = 256;      // S: [0,128)  O: [128,192)
-constexpr int kAttnSmem = 16384 * 3 + 32768 + 512 + 2048 + 64 + 1024;   // Q K V | P | mask | max/sum exchange | barriers
+// 8 warps, two threads per query row; thread 0 also issues the TMA loads and the MMAs, warp 0 owns the
+// TMEM allocation.  Resources are sized for THREE CTAs per SM (444 slots >= the 384 (batch, head)
+// pairs of BERT-base at batch 32: one wave): 128 TMEM columns (O reuses the first 64 columns of S once
+// the probabilities have left TMEM), ~52 KB shared memory (the P tile reuses the Q | K buffers once the
+// score MMA has retired), <= 85 registers.
+constexpr int kAttnThreads = 256;
+constexpr int kAttnTmemCols = 128;      // S: [0,128)  then O: [0,64)
+constexpr int kAttnSmem = 16384 * 3 + 512 + 2048 + 64 + 1024;   // Q K (later P) V | mask | max/sum exchange | barriers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -336,8 +341,9 @@ template <bool FAST>
 __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const QP& qp, const QP& qc, float sqk,
                                           float spv, uint32_t trow, int row, int quarter, int lane, int warp, int b,
                                           int h, int32_t dmodel, const float* smask, unsigned char* pP, float* xchg,
-                                          uint32_t bar_s, uint32_t bar_p, uint32_t bar_o) {
-    const int hs = (warp - 2) >> 2;                 // which half of the keys / of the context columns
+                                          uint32_t bar_s, uint32_t bar_p, uint32_t bar_o, uint32_t bar_v, uint32_t sP,
+                                          uint32_t sV, uint32_t tmem) {
+    const int hs = warp >> 2;                       // which half of the keys / of the context columns
     const int k0 = hs * 64;
     const QP2 qs2 = pair_of(qs), qp2 = pair_of(qp), qc2 = pair_of(qc);
     const float2 sqk2 = make_float2(sqk, sqk), inv2 = make_float2(a.inv_sqrt_d, a.inv_sqrt_d), spv2 = make_float2(spv, spv);
@@ -422,121 +428,117 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
     tc_fence_before();
     mbar_arrive(bar_p);
+    if (threadIdx.x == 0) {
+        // O[q, d] = sum_k P[q, k] * V[k, d]      (A = P K-major over keys; B = V MN-major); O overwrites
+        // the first 64 score columns: every thread has read its scores before arriving on bar_p
+        mbar_wait(bar_p, 0);
+        mbar_wait(bar_v, 0);
+        tc_fence_after();
+        constexpr uint32_t id2 = idesc_bf16(128, 64, 1);
+#pragma unroll
+        for (int k = 0; k < AT / 16; ++k) {
+            const uint64_t ad = desc_k_sw128(sP + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3));
+            const uint64_t bd = desc_mn_sw128(sV + k * 2048);
+            tc_mma(tmem, ad, bd, id2, k != 0);
+        }
+        tc_commit(bar_o);
+    }
+    __syncwarp();
 
-    // context: O * (s_p * s_v) -> QDQ -> centred bf16; this thread owns 32 of the 64 head dims;
-    // coalesced through the (now free) P tile: 32 rows x 64 B per warp
+    // context: O * (s_p * s_v) -> QDQ -> centred bf16; this thread owns 32 of the 64 head dims = 64
+    // contiguous bytes of its output row: two 32-byte stores
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    uint4* stg = reinterpret_cast<uint4*>(pP + (warp - 2) * 2048);
+    __nv_bfloat16* orow = a.c_ctr + ((int64_t)b * AT + row) * dmodel + h * AD + hs * 32;
+    const bool wide = ((((uintptr_t)a.c_ctr) & 31u) == 0) && ((dmodel & 15) == 0);
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
         const int c0 = hs * 32 + i * 16;
         uint32_t v[16];
-        tmem_ld16(trow + 128 + c0, v);
-        float c[16];
+        tmem_ld16(trow + c0, v);
+        uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {                                           // :201-213
             const float2 cv = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), spv2);
             float2 ci;
             if (FAST) ci = quant_ctr2_finite(cv, qc2);
             else ci = make_float2(__fsub_rn(quant_int_t<false>(cv.x, qc), qc.zp), __fsub_rn(quant_int_t<false>(cv.y, qc), qc.zp));
-            c[j] = ci.x;
-            c[j + 1] = ci.y;
+            w[j >> 1] = pack2(ci.x, ci.y);
         }
-        uint4 w0, w1;
-        w0.x = pack2(c[0], c[1]); w0.y = pack2(c[2], c[3]); w0.z = pack2(c[4], c[5]); w0.w = pack2(c[6], c[7]);
-        w1.x = pack2(c[8], c[9]); w1.y = pack2(c[10], c[11]); w1.z = pack2(c[12], c[13]); w1.w = pack2(c[14], c[15]);
-        const int ch0 = i * 2;                           // 4 chunks of 16 B per staged row
-        stg[lane * 4 + ((ch0) ^ ((lane >> 1) & 3))] = w0;
-        stg[lane * 4 + ((ch0 + 1) ^ ((lane >> 1) & 3))] = w1;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = i * 8 + (lane >> 2), ch = lane & 3;
-        const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
-        const int64_t grow = (int64_t)b * AT + quarter * 32 + r;
-        *reinterpret_cast<uint4*>(a.c_ctr + grow * dmodel + h * AD + hs * 32 + ch * 8) = val;
+        if (wide) {
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + i * 16), "r"(w[0]),
+                         "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                         : "memory");
+        } else {
+            *reinterpret_cast<uint4*>(orow + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(orow + i * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
     }
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__global__ void __launch_bounds__(kAttnThreads, 3)
 attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* bp = smem_dyn + (base - smem_u32(smem_dyn));
-    const uint32_t sQ = base, sK = base + 16384, sV = base + 32768, sP = base + 49152;
-    unsigned char* pP = bp + 49152;
-    float* smask = reinterpret_cast<float*>(bp + 49152 + 32768);
-    float* xchg = reinterpret_cast<float*>(bp + 49152 + 32768 + 512);
-    const uint32_t bar0 = base + 49152 + 32768 + 512 + 2048;
+    const uint32_t sQ = base, sK = base + 16384, sV = base + 32768;
+    const uint32_t sP = base;                          // P (2 x 16 KB K-major halves) reuses Q | K after the score MMA
+    unsigned char* pP = bp;
+    float* smask = reinterpret_cast<float*>(bp + 49152);
+    float* xchg = reinterpret_cast<float*>(bp + 49152 + 512);
+    const uint32_t bar0 = base + 49152 + 512 + 2048;
     const uint32_t bar_qk = bar0, bar_v = bar0 + 8, bar_s = bar0 + 16, bar_p = bar0 + 24, bar_o = bar0 + 32;
     const uint32_t tmem_slot = bar0 + 40;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bp + 49152 + 32768 + 512 + 2048 + 40);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bp + 49152 + 512 + 2048 + 40);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
     const int32_t dmodel = a.H * AD;
 
-    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
-    if (warp == 1) {
-        if (lane == 0) {
-            mbar_init(bar_qk, 1);
-            mbar_init(bar_v, 1);
-            mbar_init(bar_s, 1);
-            mbar_init(bar_p, 256);
-            mbar_init(bar_o, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        mbar_init(bar_qk, 1);
+        mbar_init(bar_v, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, kAttnThreads);
+        mbar_init(bar_o, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // the loads start before the TMEM allocation / block barrier below
+        pdl_wait();                                   // qkv is produced by the previous kernel
+        mbar_expect_tx(bar_qk, 32768);
+        tma_load_2d(sQ, &map_qkv, h * AD, b * AT, bar_qk);
+        tma_load_2d(sK, &map_qkv, dmodel + h * AD, b * AT, bar_qk);
+        mbar_expect_tx(bar_v, 16384);
+        tma_load_2d(sV, &map_qkv, 2 * dmodel + h * AD, b * AT, bar_v);
+    }
+    if (warp == 0) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                      "r"((uint32_t)kAttnTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2 && warp < 6) {
-        const int r = threadIdx.x - 64;
-        smask[r] = a.mask != nullptr ? a.mask[(int64_t)b * AT + r] : 0.0f;
-    }
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x < AT) smask[threadIdx.x] = a.mask != nullptr ? a.mask[(int64_t)b * AT + threadIdx.x] : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
-    pdl_trigger();
-    pdl_wait();
 
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(bar_qk, 32768);
-            tma_load_2d(sQ, &map_qkv, h * AD, b * AT, bar_qk);
-            tma_load_2d(sK, &map_qkv, dmodel + h * AD, b * AT, bar_qk);
-            mbar_expect_tx(bar_v, 16384);
-            tma_load_2d(sV, &map_qkv, 2 * dmodel + h * AD, b * AT, bar_v);
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // S[q, k] = sum_d Q[q, d] * K[k, d]      (both operands K-major, K = head_dim)
-            mbar_wait(bar_qk, 0);
-            tc_fence_after();
-            constexpr uint32_t id1 = idesc_bf16(128, 128, 0);
+    if (threadIdx.x == 0) {
+        // S[q, k] = sum_d Q[q, d] * K[k, d]      (both operands K-major, K = head_dim)
+        mbar_wait(bar_qk, 0);
+        tc_fence_after();
+        constexpr uint32_t id1 = idesc_bf16(128, 128, 0);
 #pragma unroll
-            for (int k = 0; k < AD / 16; ++k)
-                tc_mma(tmem, desc_k_sw128(sQ) + (uint64_t)(2 * k), desc_k_sw128(sK) + (uint64_t)(2 * k), id1, k != 0);
-            tc_commit(bar_s);
-            // O[q, d] = sum_k P[q, k] * V[k, d]      (A = P K-major over keys; B = V MN-major)
-            mbar_wait(bar_p, 0);
-            mbar_wait(bar_v, 0);
-            tc_fence_after();
-            constexpr uint32_t id2 = idesc_bf16(128, 64, 1);
-#pragma unroll
-            for (int k = 0; k < AT / 16; ++k) {
-                const uint64_t ad = desc_k_sw128(sP + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3));
-                const uint64_t bd = desc_mn_sw128(sV + k * 2048);
-                tc_mma(tmem + 128, ad, bd, id2, k != 0);
-            }
-            tc_commit(bar_o);
-        }
-    } else {
+        for (int k = 0; k < AD / 16; ++k)
+            tc_mma(tmem, desc_k_sw128(sQ) + (uint64_t)(2 * k), desc_k_sw128(sK) + (uint64_t)(2 * k), id1, k != 0);
+        tc_commit(bar_s);
+    }
+    __syncwarp();
+    {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;                      // query index == TMEM lane
         const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -551,13 +553,13 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
         const float spv = qp.scale * scale_of(a.v_q);
 
         if (qs.exact | qp.exact | qc.exact)
-            attn_rows<false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o);
+            attn_rows<false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
         else
-            attn_rows<true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o);
+            attn_rows<true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kAttnTmemCols)
                      : "memory");
     }
