@@ -341,7 +341,8 @@ def run_ours(args):
         # ---- the public forward: fused engine built from the calibrated model (module path if the
         #      configuration is outside the engine's support) ----
         from engine.fused import FusedBertEngine, UnsupportedByEngine
-        engine_kind = 'fused (engine/fused.py: 7 kernels per encoder layer, bf16 integer-grid carriers)'
+        engine_kind = ('fused (engine/fused.py: 5 kernels per encoder layer -- QKV GEMM, attention, attention-out GEMM + residual + '
+                       'LayerNorm, FFN-in GEMM + GELU, FFN-out GEMM + residual + LayerNorm -- bf16 integer-grid carriers)')
         try:
             forward = FusedBertEngine(model, BATCH, SEQ)
         except UnsupportedByEngine as e:
@@ -426,7 +427,7 @@ def run_ours(args):
     per_launch_s = st['seconds'] / st['launches']
     flops_kernels = ('linear_qdq', 'attention')
     if name in flops_kernels:
-        roof = {'kernel': 'tq_linear_qdq_bf16 / tq_linear_res_qdq_bf16 (tcgen05 GEMM + fused QDQ epilogue)'
+        roof = {'kernel': 'tq_linear_qdq_bf16 / tq_linear_res_ln_qdq_bf16 (tcgen05 GEMM + fused QDQ / residual / LayerNorm epilogue)'
                 if name == 'linear_qdq' else 'tq_attention_qdq_bf16', 'bound': 'tensor',
                 'achieved': st['work'] / st['seconds'] / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s'}
     else:
@@ -434,6 +435,14 @@ def run_ours(args):
                 'peak': hbm_peak, 'unit': 'GB/s'}
     roof['frac'] = roof['achieved'] / roof['peak']
     roof['traffic'] = None
+    try:                      # DRAM bytes per launch of that kernel class from the committed ncu --set full capture
+        with open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')) as f:
+            tr = json.load(f)
+        if name in tr:
+            roof['traffic'] = tr[name]['dram_bytes_per_launch']
+            roof['traffic_source'] = tr[name]['source']
+    except (OSError, ValueError, KeyError):
+        pass
     roof['peak_source'] = f'{peak_kind} (MEASURED_PEAKS.json)' if peak_kind == 'measured' else 'fallback (B200_PROFILING.md)'
     roof['launches_per_step'] = st['launches']
     roof['avg_launch_us'] = per_launch_s * 1e6
@@ -455,7 +464,8 @@ def run_ours(args):
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'seq_len': SEQ,
                    'parallelism': f'dp{world} (independent replicas)',
-                   'l2': 'per-step working set (0.34 GB bf16+fp32 weights, >2.6 GB activations) exceeds the 126 MB L2',
+                   'l2': 'per-step working set (0.17 GB bf16 weight grids + 0.09 GB fp32 embedding tables, 12 x 63 MB bf16 '
+                         'activations) exceeds the 126 MB L2; nothing is flushed between steps',
                    'cuda_graph': True, 'forward': engine_kind,
                    'max_abs_logit_diff_engine_vs_module_path': engine_vs_module},
         'e2e': {'value': e2e, 'unit': 'tokens/s', 'h2d_bytes_per_step': ids_host.numel() * ids_host.element_size(),
