@@ -207,6 +207,31 @@ int tq_linear_res_ln_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, co
                               const float* ln_gamma_q, const float* ln_beta, float ln_eps,
                               tq_qspec ln_q, void* stream);
 
+/* ---- 8-bit integer operand mode ---------------------------------------------------------------
+ * The same hijacked-linear / residual-block semantics as tq_linear_qdq_bf16 / tq_linear_res_ln_qdq_bf16
+ * with A, W and the residual carried as the quantizers' INTEGER grids x_int in one byte per element
+ * (unsigned for asymmetric / unsigned-symmetric quantizers, two's complement for signed-symmetric ones;
+ * n_bits <= 8) and multiplied on the int8 tensor cores (tcgen05 kind::i8, int32 accumulators: the
+ * integer GEMM is always exact).  The zero point of A is removed with the integer identity
+ *     sum_k (a_int - zp) * w[n,k] = acc[n] - zp * w_rowsum[n],      w_rowsum[n] = sum_k w_int[n,k]  (int32, [N]).
+ * Outputs: y fp32 and / or y_ctr_bf16 (centred grid, e.g. for tq_attention_*) and / or y_i8 (x_int
+ * bytes: the A operand / residual of the next block).  K % 128 == 0, N % 16 == 0. */
+int tq_linear_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
+                     float* y, void* y_ctr_bf16, void* y_i8, int64_t M, int64_t N, int64_t K,
+                     tq_qspec a_q, tq_qspec w_q, int64_t w_q_params, int32_t act_fn,
+                     tq_qspec out_q, int64_t out_q_params, void* stream);
+/* tq_linear_qdq_bf16 (bf16 centred operands) with the output written as x_int bytes: lets a bf16-operand
+ * GEMM feed an 8-bit-operand one (act_fn: 0 none, 1 GELU). */
+int tq_linear_qdq_bf16_o8(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, void* y_i8,
+                          int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q, int64_t w_q_params,
+                          int32_t act_fn, tq_qspec out_q, int64_t out_q_params, void* stream);
+int tq_linear_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
+                            float* z, void* z_ctr_bf16, void* z_i8, int64_t M, int64_t N, int64_t K,
+                            tq_qspec a_q, tq_qspec w_q, int64_t w_q_params, tq_qspec out_q,
+                            const void* res_i8, tq_qspec res_q, tq_qspec out2_q,
+                            const float* ln_gamma_q, const float* ln_beta, float ln_eps,
+                            tq_qspec ln_q, void* stream);
+
 /* ---- fused encoder blocks --------------------------------------------
  * All tensors are centred integer grids in bf16 (x_int - zero_point; dequantized value = scale*ctr).
  *
@@ -220,6 +245,11 @@ int tq_linear_res_ln_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, co
 int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B, int32_t T, int32_t H,
                           int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q,
                           tq_qspec p_q, tq_qspec c_q, const float* mask, void* stream);
+
+/* tq_attention_qdq_bf16 with the context written as x_int bytes (A operand of tq_linear_*_i8). */
+int tq_attention_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H,
+                        int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q,
+                        tq_qspec p_q, tq_qspec c_q, const float* mask, void* stream);
 
 /* QuantLayerNorm over a quantized input (reference autoquant_utils.py:55-66 applied to the output of
  * a residual quantizer): x = in_scale * x_ctr; y = LayerNorm(x; gamma_q, beta, eps); out_q QDQ.
@@ -241,6 +271,13 @@ int tq_embed_ln_qdq_bf16(const int64_t* ids, const int64_t* type_ids, const int6
 
 /* hi|mid|lo bf16 split of an fp32 tensor [M, K] -> [M, 3K] (x == hi + mid + lo to 2^-24 rel.). */
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream);
+
+/* tq_embed_ln_qdq_bf16 with the output written as x_int bytes (8-bit operand mode). */
+int tq_embed_ln_qdq_i8(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int64_t T,
+                       const float* word_q, const float* type_q, const float* pos_q, tq_qspec e_tok,
+                       int64_t e_tok_params, tq_qspec e_pos, int64_t e_pos_params, const float* gamma_q,
+                       const float* beta, float eps, tq_qspec out_q, int64_t out_q_params,
+                       void* out_i8, int64_t M, int32_t D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,86 @@ def test_linear_residual_layernorm_fused(M, N, K):
     assert torch.equal(z, zc.float() * float(O.scale_of(z_d)))
 
 
+def _i8_case(ops, M, N, K, seed, per_col=False):
+    rs = np.random.RandomState(seed)
+    a_int = rs.randint(0, 256, size=(M, K)).astype(np.float32)
+    w_int = rs.randint(-128, 128, size=(N, K)).astype(np.float32)
+    bias = (rs.randn(N) * 0.3).astype(np.float32)
+    a_sp, a_keep, (a_d, a_z) = asym_spec(ops, -2.0, 3.0)
+    zp_a = float(O.asym_zero_point(a_z, 8))
+    w_d, w_signed = O.sym_set_quant_range(-0.08 * 8 / math.sqrt(K), 0.09 * 8 / math.sqrt(K), 8)
+    wd_t, ws_t = T_(np.atleast_1d(w_d)), torch.tensor(bool(w_signed), device=DEV)
+    w_sp = ops.spec(wd_t, None, ws_t, 8)
+    a8 = T_(a_int).to(torch.uint8)
+    a_ctr = T_(a_int - zp_a).to(torch.bfloat16)
+    w8 = T_(w_int).to(torch.int8)
+    w_bf = T_(w_int).to(torch.bfloat16)
+    rowsum = T_(w_int).to(torch.int32).sum(dim=1, dtype=torch.int32).contiguous()
+    pre = ((a_int - zp_a).astype(np.float64) @ w_int.astype(np.float64).T
+           * np.float64(np.float32(O.scale_of(a_d) * O.scale_of(w_d))) + bias.astype(np.float64)).astype(np.float32)
+    keep = [a_keep, wd_t, ws_t]
+    return dict(a8=a8, a_ctr=a_ctr, w8=w8, w_bf=w_bf, rowsum=rowsum, bias=T_(bias), a_sp=a_sp, w_sp=w_sp, pre=pre,
+                keep=keep)
+
+
+@pytest.mark.parametrize('M,N,K,act', [(384, 256, 256, 0), (4096, 2304, 768, 0), (4096, 3072, 768, 1), (300, 272, 128, 0),
+                                       (32, 768, 768, 3), (32, 16, 768, 0)])
+def test_linear_i8_matches_bf16_path(M, N, K, act):
+    """8-bit operand mode (x_int bytes, tcgen05 kind::i8, int32 accumulators + zero-point correction) must
+    reproduce the bf16 centred-grid path bit for bit: both integer GEMMs are exact."""
+    ops = tq_native.ops()
+    cse = _i8_case(ops, M, N, K, seed=M + N + K + act)
+    o_sp, o_keep, (o_d, o_z) = asym_spec(ops, float(cse['pre'].min()), float(cse['pre'].max()))
+    zp_o = float(O.asym_zero_point(o_z, 8))
+    y_b, yc_b = ops.linear(cse['a_ctr'], cse['w_bf'], cse['bias'], M, N, K, 1, cse['a_sp'], cse['w_sp'], 1, act, o_sp, 1,
+                           want_f32=True, want_ctr=True)
+    yc_i = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    y8_i = torch.empty(M, N, dtype=torch.uint8, device=DEV)
+    y_i = ops.linear_i8(cse['a8'], cse['w8'], cse['rowsum'], cse['bias'], M, N, K, cse['a_sp'], cse['w_sp'], 1, act, o_sp, 1,
+                        want_f32=True, out_ctr=yc_i, out_i8=y8_i)
+    torch.cuda.synchronize()
+    assert torch.equal(y_i, y_b)
+    assert torch.equal(yc_i, yc_b)
+    assert torch.equal(y8_i.float(), yc_b.float() + zp_o)
+    if act <= 1 and N % 16 == 0:          # bf16 operands, byte output (feeds an 8-bit-operand GEMM)
+        y8_b = torch.empty(M, N, dtype=torch.uint8, device=DEV)
+        ops.linear_bf16_o8(cse['a_ctr'], cse['w_bf'], cse['bias'], M, N, K, cse['a_sp'], cse['w_sp'], 1, act, o_sp, 1, y8_b)
+        torch.cuda.synchronize()
+        assert torch.equal(y8_b, y8_i)
+    # no output quantizer (generic epilogue): fp32 result of the integer GEMM + scale + bias
+    y_b2, _ = ops.linear(cse['a_ctr'], cse['w_bf'], cse['bias'], M, N, K, 1, cse['a_sp'], cse['w_sp'], 1, 0, None, 1)
+    y_i2 = ops.linear_i8(cse['a8'], cse['w8'], cse['rowsum'], cse['bias'], M, N, K, cse['a_sp'], cse['w_sp'], 1, 0, None, 1,
+                         want_f32=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y_i2, y_b2)
+
+
+@pytest.mark.parametrize('M,N,K', [(384, 768, 256), (4096, 768, 3072), (200, 1024, 256)])
+def test_linear_residual_layernorm_i8_matches_bf16_path(M, N, K):
+    ops = tq_native.ops()
+    cse = _i8_case(ops, M, N, K, seed=M + N + K)
+    rs = np.random.RandomState(1)
+    r_int = rs.randint(0, 256, size=(M, N)).astype(np.float32)
+    gamma = (1 + 0.1 * rs.randn(N)).astype(np.float32)
+    beta = (0.05 * rs.randn(N)).astype(np.float32)
+    r_sp, r_keep, (r_d, r_z) = asym_spec(ops, -4.0, 4.0)
+    zp_r = float(O.asym_zero_point(r_z, 8))
+    g_sp, g_keep, _ = asym_spec(ops, float(cse['pre'].min()), float(cse['pre'].max()))
+    u_sp, u_keep, _ = asym_spec(ops, float(cse['pre'].min()) - 3.0, float(cse['pre'].max()) + 3.0)
+    z_sp, z_keep, (z_d, z_z) = asym_spec(ops, -4.0, 4.0)
+    zp_z = float(O.asym_zero_point(z_z, 8))
+    gt, bt = T_(gamma), T_(beta)
+    _, zc_b = ops.linear_res_ln(cse['a_ctr'], cse['w_bf'], cse['bias'], M, N, K, cse['a_sp'], cse['w_sp'], 1, g_sp,
+                                T_(r_int - zp_r).to(torch.bfloat16), r_sp, u_sp, gt, bt, 1e-12, z_sp)
+    z8 = torch.empty(M, N, dtype=torch.uint8, device=DEV)
+    zc_i = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_res_ln_i8(cse['a8'], cse['w8'], cse['rowsum'], cse['bias'], M, N, K, cse['a_sp'], cse['w_sp'], 1, g_sp,
+                         T_(r_int).to(torch.uint8), r_sp, u_sp, gt, bt, 1e-12, z_sp, z8, out_ctr=zc_i)
+    torch.cuda.synchronize()
+    assert torch.equal(z8.float(), zc_b.float() + zp_z)
+    assert torch.equal(zc_i, zc_b)
+
+
 @pytest.mark.parametrize('D', [256, 768, 1024])
 def test_ln_qdq_kernel(D):
     ops = tq_native.ops()
@@ -279,8 +359,17 @@ def test_engine_matches_module_path(n_bits, use_mask):
     assert dh.max() <= 4.5 and (dh > 0.5).mean() < 0.05, (dh.max(), (dh > 0.5).mean())
     # the engine is deterministic and graph-capturable; without a trace request the two residual
     # blocks of a layer run with the LayerNorm fused in (5 kernels per layer instead of 7)
-    for fuse, per_layer in ((True, 5), (False, 7)):
+    assert eng.i8, 'asymmetric 8-bit (and narrower) activation grids: the 8-bit operand mode must be active'
+    logits_i8 = eng(ids[2], mask)
+    hidden_i8 = eng.hidden_states()
+    eng.i8 = False
+    logits_bf = eng(ids[2], mask)
+    torch.cuda.synchronize()
+    assert torch.equal(logits_i8, logits_bf), 'int8 tensor-core path vs bf16 centred-grid path'
+    assert torch.equal(hidden_i8, eng.hidden_states())
+    for fuse, per_layer, i8 in ((True, 5, True), (True, 5, False), (False, 7, False)):
         eng.fuse_ln = fuse
+        eng.i8 = i8
         eager = eng(ids[2], mask)
         torch.cuda.synchronize()
         assert (eager - ref_logits).abs().max().item() <= 3 * cls_step + 1e-6

@@ -40,7 +40,11 @@ def bench(fn, per_graph=20, replays=5):
 
 cases = [('qkv   2304x768 percol', 2304, 768, 0, True, False), ('attout 768x768 res', 768, 768, 0, False, True),
          ('ffn_in 3072x768 gelu', 3072, 768, 1, False, False), ('ffnout 768x3072 res', 768, 3072, 0, False, True),
-         ('attout 768x768 res+LN', 768, 768, 0, False, 'ln'), ('ffnout 768x3072 res+LN', 768, 3072, 0, False, 'ln')]
+         ('attout 768x768 res+LN', 768, 768, 0, False, 'ln'), ('ffnout 768x3072 res+LN', 768, 3072, 0, False, 'ln'),
+         ('i8 qkv 2304x768 percol', 2304, 768, 0, True, 'i8'), ('i8 ffn_in 3072x768 gelu', 3072, 768, 1, False, 'i8'),
+         ('i8 attout 768x768 res+LN', 768, 768, 0, False, 'i8ln'), ('i8 ffnout 768x3072 res+LN', 768, 3072, 0, False, 'i8ln'),
+         ('i8 ffn_in 3072x768 plain u8', 3072, 768, 0, False, 'i8'), ('i8 ffn_in gelu bf16-out', 3072, 768, 1, False, 'i8bf'),
+         ('i8 ffn_in plain bf16-out', 3072, 768, 0, False, 'i8bf')]
 combos = [(1, '256'), (1, '192'), (1, '128'), (1, '96'), (2, '256'), (2, '192'), (2, '128'), (None, None)]
 if os.environ.get('SWEEP_QUICK'):
     combos = [(1, '256'), (1, '192'), (None, None)]
@@ -53,7 +57,21 @@ for name, N, K, act, percol, res in cases:
     a_sp = spec(0.02, 128); w_sp = spec(0.001, None, True, N)
     o_sp = spec(0.05, 120, None, N if percol else 1); r_sp = spec(0.03, 128); o2_sp = spec(0.06, 125)
     yc = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    if res == 'ln':
+    if res in ('i8', 'i8ln', 'i8bf'):
+        a8 = torch.randint(0, 256, (M, K), device=dev).to(torch.uint8)
+        w8 = torch.randint(-128, 128, (N, K), device=dev).to(torch.int8)
+        rsum = w8.to(torch.int32).sum(dim=1, dtype=torch.int32).contiguous()
+        r8 = torch.randint(0, 256, (M, N), device=dev).to(torch.uint8)
+        y8 = torch.empty(M, N, device=dev, dtype=torch.uint8)
+        gamma = torch.ones(N, device=dev); beta = torch.zeros(N, device=dev); ln_sp = spec(0.03, 120)
+        if res == 'i8ln':
+            fn = lambda: ops.linear_res_ln_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, N, o_sp, r8, r_sp, o2_sp, gamma, beta,
+                                              1e-12, ln_sp, y8)
+        elif percol or res == 'i8bf':
+            fn = lambda: ops.linear_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, N, act, o_sp, N if percol else 1, out_ctr=yc)
+        else:
+            fn = lambda: ops.linear_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, N, act, o_sp, 1, out_i8=y8)
+    elif res == 'ln':
         gamma = torch.ones(N, device=dev); beta = torch.zeros(N, device=dev); ln_sp = spec(0.03, 120)
         fn = lambda: ops.linear_res_ln(a, w, bias, M, N, K, a_sp, w_sp, N, o_sp, r, r_sp, o2_sp, gamma, beta, 1e-12,
                                        ln_sp, out_ctr=yc)

@@ -70,7 +70,8 @@ struct LnArgs {
     const float* beta;           // [D]
     float eps;
     ColQ out_q;
-    __nv_bfloat16* out_ctr;      // [M, D]
+    __nv_bfloat16* out_ctr;      // [M, D] centred grid (optional when out_u8 is given)
+    unsigned char* out_u8;       // optional [M, D] x_int bytes (8-bit operand mode of the GEMMs)
     float* out_f32;              // optional [M, D]
     int64_t M;
     int32_t D;
@@ -175,7 +176,17 @@ __device__ __forceinline__ void ln_row(const LnArgs& a, int64_t row, int lane, C
             o.y = pack2(ctr[2], ctr[3]);
             o.z = pack2(ctr[4], ctr[5]);
             o.w = pack2(ctr[6], ctr[7]);
-            *reinterpret_cast<uint4*>(a.out_ctr + row * a.D + c) = o;
+            if (a.out_ctr != nullptr) *reinterpret_cast<uint4*>(a.out_ctr + row * a.D + c) = o;
+            if (a.out_u8 != nullptr) {
+                uint32_t xi[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    xi[j] = __float_as_uint(__fadd_rn(ctr[j], __fadd_rn(out_q.get<FAST>(c + j).zp, 12582912.0f)));
+                uint2 o8;
+                o8.x = __byte_perm(__byte_perm(xi[0], xi[1], 0x0040), __byte_perm(xi[2], xi[3], 0x0040), 0x5410);
+                o8.y = __byte_perm(__byte_perm(xi[4], xi[5], 0x0040), __byte_perm(xi[6], xi[7], 0x0040), 0x5410);
+                *reinterpret_cast<uint2*>(a.out_u8 + row * a.D + c) = o8;
+            }
             if (a.out_f32 != nullptr) {
                 float4* of = reinterpret_cast<float4*>(a.out_f32 + row * a.D + c);
                 of[0] = make_float4(deq[0], deq[1], deq[2], deq[3]);
@@ -316,7 +327,8 @@ struct AttnArgs {
     tq_qspec q_q, k_q, v_q;       // per-tensor quantizers of the Q / K / V projections (scales only)
     tq_qspec s_q, p_q, c_q;       // scores / probs / context quantizers (per-tensor)
     const float* mask;            // [B, AT] additive mask (0 / -10000) or null
-    __nv_bfloat16* c_ctr;         // [B * AT, H * AD] centred context grid
+    __nv_bfloat16* c_ctr;         // [B * AT, H * AD] centred context grid (or null)
+    unsigned char* c_u8;          // [B * AT, H * AD] context x_int, one byte each (8-bit operand mode; or null)
     float inv_sqrt_d;             // 1 / sqrt(head_dim)
 };
 
@@ -449,14 +461,17 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
     // contiguous bytes of its output row: two 32-byte stores
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    __nv_bfloat16* orow = a.c_ctr + ((int64_t)b * AT + row) * dmodel + h * AD + hs * 32;
+    const int64_t ooff = ((int64_t)b * AT + row) * dmodel + h * AD + hs * 32;
+    __nv_bfloat16* orow = a.c_ctr + ooff;
     const bool wide = ((((uintptr_t)a.c_ctr) & 31u) == 0) && ((dmodel & 15) == 0);
+    uint32_t bytes[8];                                  // 32 context values as x_int bytes (8-bit operand mode)
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
         const int c0 = hs * 32 + i * 16;
         uint32_t v[16];
         tmem_ld16(trow + c0, v);
         uint32_t w[8];
+        uint32_t xi[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {                                           // :201-213
             const float2 cv = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), spv2);
@@ -464,7 +479,17 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
             if (FAST) ci = quant_ctr2_finite(cv, qc2);
             else ci = make_float2(__fsub_rn(quant_int_t<false>(cv.x, qc), qc.zp), __fsub_rn(quant_int_t<false>(cv.y, qc), qc.zp));
             w[j >> 1] = pack2(ci.x, ci.y);
+            // x_int bytes without F2I: v + 1.5 * 2^23 keeps the integer in the low mantissa bits
+            xi[j] = __float_as_uint(__fadd_rn(ci.x, __fadd_rn(qc.zp, 12582912.0f)));
+            xi[j + 1] = __float_as_uint(__fadd_rn(ci.y, __fadd_rn(qc.zp, 12582912.0f)));
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t packed = __byte_perm(__byte_perm(xi[4 * q], xi[4 * q + 1], 0x0040),
+                                                __byte_perm(xi[4 * q + 2], xi[4 * q + 3], 0x0040), 0x5410);
+            if (i == 0) bytes[q] = packed; else bytes[4 + q] = packed;
+        }
+        if (a.c_ctr == nullptr) continue;
         if (wide) {
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + i * 16), "r"(w[0]),
                          "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
@@ -472,6 +497,18 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         } else {
             *reinterpret_cast<uint4*>(orow + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(orow + i * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
+    if (a.c_u8 != nullptr) {
+        unsigned char* o8 = a.c_u8 + ooff;               // 32 bytes: one sector
+        if ((((uintptr_t)a.c_u8) & 31u) == 0 && (dmodel & 31) == 0) {
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o8), "r"(bytes[0]),
+                         "r"(bytes[1]), "r"(bytes[2]), "r"(bytes[3]), "r"(bytes[4]), "r"(bytes[5]), "r"(bytes[6]),
+                         "r"(bytes[7])
+                         : "memory");
+        } else {
+            *reinterpret_cast<uint4*>(o8) = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
+            *reinterpret_cast<uint4*>(o8 + 16) = make_uint4(bytes[4], bytes[5], bytes[6], bytes[7]);
         }
     }
 }
@@ -585,13 +622,14 @@ static EncodeTiledFn encode_fn() {
 
 extern "C" {
 
-int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B, int32_t T, int32_t H,
+static int attention_impl(const void* qkv_ctr_bf16, void* c_ctr_bf16, void* c_u8, int32_t B, int32_t T, int32_t H,
                           int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q, tq_qspec p_q,
                           tq_qspec c_q, const float* mask, void* stream) {
     using namespace tq::fused;
-    if (qkv_ctr_bf16 == nullptr || c_ctr_bf16 == nullptr || B < 1 || H < 1) return TQ_EINVAL;
+    if (qkv_ctr_bf16 == nullptr || (c_ctr_bf16 == nullptr && c_u8 == nullptr) || B < 1 || H < 1) return TQ_EINVAL;
     if (T != AT || head_dim != AD) return TQ_EUNSUPPORTED;
-    if (!tq::aligned16(qkv_ctr_bf16) || !tq::aligned16(c_ctr_bf16)) return TQ_EALIGN;
+    if (!tq::aligned16(qkv_ctr_bf16) || !tq::aligned16(c_ctr_bf16) || !tq::aligned16(c_u8)) return TQ_EALIGN;
+    if (c_u8 != nullptr && c_q.n_bits > 8) return TQ_EUNSUPPORTED;
     const tq_qspec* all[6] = {&q_q, &k_q, &v_q, &s_q, &p_q, &c_q};
     for (int i = 0; i < 6; ++i)
         if (int e = tq::check_qspec(*all[i])) return e;
@@ -619,14 +657,29 @@ int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B,
     a.q_q = q_q; a.k_q = k_q; a.v_q = v_q; a.s_q = s_q; a.p_q = p_q; a.c_q = c_q;
     a.mask = mask;
     a.c_ctr = reinterpret_cast<__nv_bfloat16*>(c_ctr_bf16);
+    a.c_u8 = reinterpret_cast<unsigned char*>(c_u8);
     a.inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
     return tq::launch_pdl(attention_kernel, dim3(B * H), dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, 1, map, a);
+}
+
+int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B, int32_t T, int32_t H,
+                          int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q, tq_qspec p_q,
+                          tq_qspec c_q, const float* mask, void* stream) {
+    if (c_ctr_bf16 == nullptr) return TQ_EINVAL;
+    return attention_impl(qkv_ctr_bf16, c_ctr_bf16, nullptr, B, T, H, head_dim, q_q, k_q, v_q, s_q, p_q, c_q, mask, stream);
+}
+
+int tq_attention_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H, int32_t head_dim,
+                        tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q, tq_qspec p_q, tq_qspec c_q,
+                        const float* mask, void* stream) {
+    if (c_i8 == nullptr) return TQ_EINVAL;
+    return attention_impl(qkv_ctr_bf16, nullptr, c_i8, B, T, H, head_dim, q_q, k_q, v_q, s_q, p_q, c_q, mask, stream);
 }
 
 static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {
     using namespace tq::fused;
     if (a.M < 1 || a.D < 256 || (a.D & 255) != 0 || a.D > 256 * kLnMaxIter) return TQ_EUNSUPPORTED;
-    if (a.gamma_q == nullptr || a.beta == nullptr || a.out_ctr == nullptr) return TQ_EINVAL;
+    if (a.gamma_q == nullptr || a.beta == nullptr || (a.out_ctr == nullptr && a.out_u8 == nullptr)) return TQ_EINVAL;
     if (int e = tq::check_qspec(a.out_q.q)) return e;
     const unsigned grid = (unsigned)((a.M + kLnWarps - 1) / kLnWarps);
     static bool carve_set = false;
@@ -660,12 +713,14 @@ int tq_ln_qdq_bf16(const void* x_ctr_bf16, tq_qspec in_q, int64_t in_q_params, c
     return ln_common(a, false, stream);
 }
 
-int tq_embed_ln_qdq_bf16(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int64_t T,
-                         const float* word_q, const float* type_q, const float* pos_q, tq_qspec e_tok,
-                         int64_t e_tok_params, tq_qspec e_pos, int64_t e_pos_params, const float* gamma_q,
-                         const float* beta, float eps, tq_qspec out_q, int64_t out_q_params, void* out_ctr_bf16,
-                         float* out_f32, int64_t M, int32_t D, void* stream) {
+static int embed_impl(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int64_t T,
+                      const float* word_q, const float* type_q, const float* pos_q, tq_qspec e_tok,
+                      int64_t e_tok_params, tq_qspec e_pos, int64_t e_pos_params, const float* gamma_q,
+                      const float* beta, float eps, tq_qspec out_q, int64_t out_q_params, void* out_ctr_bf16,
+                      void* out_u8, float* out_f32, int64_t M, int32_t D, void* stream) {
     tq::fused::LnArgs a = {};
+    a.out_u8 = reinterpret_cast<unsigned char*>(out_u8);
+    if (out_u8 != nullptr && out_q.n_bits > 8) return TQ_EUNSUPPORTED;
     if (ids == nullptr || word_q == nullptr || type_q == nullptr || pos_q == nullptr || T < 1) return TQ_EINVAL;
     if (int e = tq::check_qspec(e_tok)) return e;
     if (int e = tq::check_qspec(e_pos)) return e;
@@ -690,6 +745,26 @@ int tq_embed_ln_qdq_bf16(const int64_t* ids, const int64_t* type_ids, const int6
     a.M = M;
     a.D = D;
     return ln_common(a, true, stream);
+}
+
+int tq_embed_ln_qdq_bf16(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int64_t T,
+                         const float* word_q, const float* type_q, const float* pos_q, tq_qspec e_tok,
+                         int64_t e_tok_params, tq_qspec e_pos, int64_t e_pos_params, const float* gamma_q,
+                         const float* beta, float eps, tq_qspec out_q, int64_t out_q_params, void* out_ctr_bf16,
+                         float* out_f32, int64_t M, int32_t D, void* stream) {
+    if (out_ctr_bf16 == nullptr) return TQ_EINVAL;
+    return embed_impl(ids, type_ids, pos_ids, T, word_q, type_q, pos_q, e_tok, e_tok_params, e_pos, e_pos_params, gamma_q,
+                      beta, eps, out_q, out_q_params, out_ctr_bf16, nullptr, out_f32, M, D, stream);
+}
+
+int tq_embed_ln_qdq_i8(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int64_t T,
+                       const float* word_q, const float* type_q, const float* pos_q, tq_qspec e_tok,
+                       int64_t e_tok_params, tq_qspec e_pos, int64_t e_pos_params, const float* gamma_q,
+                       const float* beta, float eps, tq_qspec out_q, int64_t out_q_params, void* out_i8, int64_t M,
+                       int32_t D, void* stream) {
+    if (out_i8 == nullptr) return TQ_EINVAL;
+    return embed_impl(ids, type_ids, pos_ids, T, word_q, type_q, pos_q, e_tok, e_tok_params, e_pos, e_pos_params, gamma_q,
+                      beta, eps, out_q, out_q_params, nullptr, out_i8, nullptr, M, D, stream);
 }
 
 }  // extern "C"

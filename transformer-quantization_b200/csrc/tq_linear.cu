@@ -45,7 +45,7 @@ struct Cfg {
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kXchgFloats = 6 * BM + 2 * 8 * BM;       // LayerNorm row statistics (fused LN epilogue)
-    static constexpr int kParamBytes = 14 * BN * 4 + kXchgFloats * 4;   // seven float4 arrays per column pair + exchange
+    static constexpr int kParamBytes = 16 * BN * 4 + kXchgFloats * 4;   // eight float4 arrays per column pair + exchange
     // as many ring stages as fit beside the parameters (227 KB per CTA): the main loop is bound by
     // the TMA -> MMA hand-off latency, so depth is what buys throughput
     static constexpr int kStagesFit = (227 * 1024 - 1024 - kParamBytes - 256) / kStageBytes;
@@ -190,6 +190,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 8-bit integer operands (unsigned or two's complement), int32 accumulators: K = 32 per instruction
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row atoms 1024 B apart
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -288,6 +299,105 @@ __device__ __forceinline__ void st_row32(void* p, bool wide, bool full, const ui
     }
 }
 
+// ---- 8-bit integer operand mode (I8) ------------------------------------------------------------------
+// A and W are the quantizers' integer grids x_int / w_int in one byte per element (kind::i8 MMA,
+// int32 accumulators: always exact, twice the K per shared-memory byte and per MMA cycle).  The
+// zero point of A is taken out per output column with the exact integer identity
+//     sum_k (a_int - zp) * w[n,k]  =  acc[n] - zp * sum_k w[n,k]        (w row sums precomputed once).
+template <bool I8>
+__device__ __forceinline__ float2 acc_pair(uint32_t a, uint32_t b, const float4& corr) {
+    if (!I8) return make_float2(__uint_as_float(a), __uint_as_float(b));
+    return make_float2(__int2float_rn((int)a - __float_as_int(corr.x)), __int2float_rn((int)b - __float_as_int(corr.y)));
+}
+// residual row piece of 16 columns: bf16 centred grid (32 bytes) or 8-bit x_int (16 bytes)
+template <bool I8>
+__device__ __forceinline__ void ld_res16(const void* base, int64_t elem, bool wide, bool full, uint32_t (&r)[8]) {
+    if (!I8) {
+        ld_row32(reinterpret_cast<const __nv_bfloat16*>(base) + elem, wide, full, r);
+    } else {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(base) + elem;
+        if (full) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p);
+            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+        } else {
+            const uint2 a = *reinterpret_cast<const uint2*>(p);
+            r[0] = a.x; r[1] = a.y; r[2] = 0u; r[3] = 0u;
+        }
+    }
+}
+// columns 2 jp, 2 jp + 1 of that piece as centred values (x_int - zp)
+template <bool I8>
+__device__ __forceinline__ float2 res_pair(const uint32_t (&rw)[8], int jp, float res_zp) {
+    if (!I8) return make_float2(__uint_as_float(rw[jp] << 16), __uint_as_float(rw[jp] & 0xffff0000u));
+    // byte -> float without the conversion unit: 0x4B000000 | b is the float 2^23 + b; (2^23 + b) - (2^23 + zp)
+    // is exact.  One PRMT + one FADD per element (I2F / F2I run on the quarter-rate XU pipe).
+    const uint32_t w = rw[jp >> 1];
+    const float off = __fadd_rn(8388608.0f, res_zp);
+    const uint32_t lo = __byte_perm(w, 0x4B000000u, (jp & 1) ? 0x7652 : 0x7650);
+    const uint32_t hi = __byte_perm(w, 0x4B000000u, (jp & 1) ? 0x7653 : 0x7651);
+    return make_float2(__fsub_rn(__uint_as_float(lo), off), __fsub_rn(__uint_as_float(hi), off));
+}
+// Slice order of an epilogue warp.  bf16 outputs: 16-column slices third*16 + 48*it (a lane stores 32 bytes
+// per slice).  8-bit outputs: a 16-column slice is only 16 bytes, half a sector, so a warp takes PAIRS of
+// adjacent slices (third*32 + 96*(it/2) + 16*(it%2)), keeps the four packed words of the even one and
+// stores the 32 bytes of both with the odd one.
+template <bool I8>
+__device__ __forceinline__ int slice_col(int third, int it) {
+    return I8 ? third * 32 + 96 * (it >> 1) + 16 * (it & 1) : third * 16 + 48 * it;
+}
+// 16 centred integers -> x_int = k - (lo - zp) + lo, one byte each (two's complement low byte): four words
+__device__ __forceinline__ void pack_u8x16(uint32_t (&w)[4], const float2 (&k)[8], float2 clo0, const float4* Pclo,
+                                           bool percol, float lo) {
+    uint32_t b[16];
+    const float2 off0 = make_float2(__fsub_rn(__fadd_rn(lo, 12582912.0f), clo0.x), __fsub_rn(__fadd_rn(lo, 12582912.0f), clo0.y));
+#pragma unroll
+    for (int jp = 0; jp < 8; ++jp) {
+        float2 off = off0;
+        if (percol) off = make_float2(__fsub_rn(__fadd_rn(lo, 12582912.0f), Pclo[jp].z), __fsub_rn(__fadd_rn(lo, 12582912.0f), Pclo[jp].w));
+        const float2 t = __fadd2_rn(k[jp], off);       // v + 1.5 * 2^23 keeps v (two's complement) in the low mantissa bits
+        b[2 * jp] = __float_as_uint(t.x);
+        b[2 * jp + 1] = __float_as_uint(t.y);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        w[i] = __byte_perm(__byte_perm(b[4 * i], b[4 * i + 1], 0x0040), __byte_perm(b[4 * i + 2], b[4 * i + 3], 0x0040), 0x5410);
+}
+// store the slice pair: `it` even -> hold (store alone when there is no odd partner), odd -> 32 bytes
+__device__ __forceinline__ void st_u8_pair(unsigned char* row_ptr, int64_t gcol, int64_t N, int it, uint32_t (&held)[4],
+                                           const uint32_t (&w)[4], bool wide32) {
+    if ((it & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) held[i] = w[i];
+        if (gcol + 16 >= N) *reinterpret_cast<uint4*>(row_ptr + gcol) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if (wide32) {
+        const uint32_t r[8] = {held[0], held[1], held[2], held[3], w[0], w[1], w[2], w[3]};
+        stg256(row_ptr + gcol - 16, r);
+    } else {
+        *reinterpret_cast<uint4*>(row_ptr + gcol - 16) = make_uint4(held[0], held[1], held[2], held[3]);
+        *reinterpret_cast<uint4*>(row_ptr + gcol) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+__device__ __forceinline__ void st_u8x16(void* p, const float2 (&k)[8], float2 clo0, const float4* Pclo, bool percol,
+                                         float lo, bool full) {
+    // float integer -> byte without F2I: v + 1.5 * 2^23 keeps v (two's complement) in the low mantissa bits
+    uint32_t b[16];
+    const float2 off0 = make_float2(__fsub_rn(__fadd_rn(lo, 12582912.0f), clo0.x), __fsub_rn(__fadd_rn(lo, 12582912.0f), clo0.y));
+#pragma unroll
+    for (int jp = 0; jp < 8; ++jp) {
+        float2 off = off0;
+        if (percol) off = make_float2(__fsub_rn(__fadd_rn(lo, 12582912.0f), Pclo[jp].z), __fsub_rn(__fadd_rn(lo, 12582912.0f), Pclo[jp].w));
+        const float2 t = __fadd2_rn(k[jp], off);
+        b[2 * jp] = __float_as_uint(t.x);
+        b[2 * jp + 1] = __float_as_uint(t.y);
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        w[i] = __byte_perm(__byte_perm(b[4 * i], b[4 * i + 1], 0x0040), __byte_perm(b[4 * i + 2], b[4 * i + 3], 0x0040), 0x5410);
+    if (full) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+}
+
 // ---- epilogue parameters -------------------------------------------------------------------------
 // Shared memory: six float4 arrays indexed by COLUMN PAIR jp (= column / 2), two columns per entry:
 //   P[0][jp] = {cs.x, cs.y, cb.x, cb.y}      acc scale s_a * s_w[n], bias[n]
@@ -296,6 +406,7 @@ __device__ __forceinline__ void st_row32(void* p, bool wide, bool full, const ui
 //   P[3][jp] = {chi.x, chi.y, chi2.x, chi2.y}  upper clamp bounds hi - zp of both quantizers
 //   P[4][jp] = {s2, -s2}, P[5][jp] = {r2, clo2}   quantizer of the residual sum
 //   P[6][jp] = {gamma.x, gamma.y, beta.x, beta.y}  LayerNorm weight (fake-quantized) and bias (fused LN)
+//   P[7][jp] = {corr.x, corr.y, -, -}  int32 bits: zero point of A times the weight row sums (I8 mode)
 // A per-tensor quantizer (the common case) is read once per tile into registers (QReg).
 __device__ __forceinline__ int pidx(int bn, int arr, int slot, int j) {       // float index
     return ((arr * (bn >> 1) + (j >> 1)) << 2) + (slot << 1) + (j & 1);
@@ -342,6 +453,9 @@ struct EpiArgs {
     int64_t out2_params;            // 1 or N
     // fused LayerNorm of the residual sum (reference models/quantized_bert.py:245, 277 -> QuantLayerNorm,
     // autoquant_utils.py:55-66):  z = ln_q( LayerNorm(y; gamma_q, beta, eps) );  ln_gamma != null selects it
+    // 8-bit operand mode
+    void* y_u8;                     // [M, N] x_int of the output (unsigned or two's complement byte) or null
+    const int32_t* w_rowsum;        // [N] sum_k w_int[n, k]
     const float* ln_gamma;          // [N] fake-quantized LayerNorm weight
     const float* ln_beta;           // [N]
     float ln_eps;
@@ -359,10 +473,10 @@ struct EpiArgs {
 //   ctr2] -> bf16 pack -> ONE 32-byte store per lane (and/or two for the fp32 output).
 // No shared-memory staging and no cross-lane traffic; the residual row piece of the NEXT slice is
 // requested before the math of the current one.
-template <int BN, int ACT, bool PERCOL, bool RES>
+template <int BN, int ACT, bool PERCOL, bool RES, bool I8>
 __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* params, uint32_t tmem_tile, int third,
                                               int64_t row, bool row_ok, int64_t n0, int64_t N, float res_scale,
-                                              uint32_t tfull, uint32_t tphase) {
+                                              float res_zp, float qlo, uint32_t tfull, uint32_t tphase) {
     constexpr int HP = BN / 2;
     const float4* P = reinterpret_cast<const float4*>(params);
     QReg q1, q2;
@@ -380,17 +494,19 @@ __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* pa
     }
     const bool wide_c = ((((uintptr_t)ep.y_ctr) | ((uintptr_t)ep.res_ctr)) & 31u) == 0 && (N & 15) == 0;
     const bool wide_y = (((uintptr_t)ep.y) & 31u) == 0;
-    const __nv_bfloat16* res_row = RES ? ep.res_ctr + row * N + n0 : nullptr;
+    const int64_t res_base = row * N + n0;             // element offset of this lane's residual row piece
     uint32_t rnext[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rnext[i] = 0u;
-    int c0 = third * 16;
-    if (RES && row_ok && n0 + c0 < N) ld_row32(res_row + c0, wide_c, n0 + c0 + 16 <= N, rnext);
+    int c0 = slice_col<I8>(third, 0);
+    if (RES && row_ok && n0 + c0 < N) ld_res16<I8>(ep.res_ctr, res_base + c0, wide_c, n0 + c0 + 16 <= N, rnext);
     mbar_wait(tfull, tphase);
     tc_fence_after();
     if (threadIdx.x == 0) TQ_TRACE(8);
+    uint32_t held[4] = {0u, 0u, 0u, 0u};
+    const bool wide8 = I8 && ((((uintptr_t)ep.y_u8) & 31u) == 0) && (N & 31) == 0;
 #pragma unroll 1
-    for (; c0 < BN; c0 += 48) {
+    for (int it = 0; (c0 = slice_col<I8>(third, it)) < BN; ++it) {
         const int64_t gcol = n0 + c0;
         if (gcol >= N) break;                                    // warp-uniform
         const bool full = gcol + 16 <= N;
@@ -400,15 +516,15 @@ __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* pa
         if (RES) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) rw[i] = rnext[i];
-            const int cn = c0 + 48;
-            if (row_ok && cn < BN && n0 + cn < N) ld_row32(res_row + cn, wide_c, n0 + cn + 16 <= N, rnext);
+            const int cn = slice_col<I8>(third, it + 1);
+            if (row_ok && cn < BN && n0 + cn < N) ld_res16<I8>(ep.res_ctr, res_base + cn, wide_c, n0 + cn + 16 <= N, rnext);
         }
         float2 k[8];
 #pragma unroll
         for (int jp = 0; jp < 8; ++jp) {
             const int gp = (c0 >> 1) + jp;
             const float4 p0 = P[gp];
-            float2 f = __ffma2_rn(make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])),
+            float2 f = __ffma2_rn(acc_pair<I8>(v[2 * jp], v[2 * jp + 1], P[7 * HP + (I8 ? gp : 0)]),
                                   make_float2(p0.x, p0.y), make_float2(p0.z, p0.w));
             f = act2<ACT>(f);
             float4 pc;
@@ -430,16 +546,23 @@ __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* pa
                 // dequantized linear output and residual value as the reference materialises them
                 // (fl(scale * ctr) each, then one add): SCALAR multiplies -- a packed multiply feeding
                 // a packed add would be contracted into FFMA2 by ptxas
-                const uint32_t pair = rw[jp];
+                const float2 rc = res_pair<I8>(rw, jp, res_zp);
                 const float2 sum = __fadd2_rn(
                     make_float2(__fmul_rn(q1.s.x, c.x), __fmul_rn(q1.s.y, c.y)),
-                    make_float2(__fmul_rn(res_scale, __uint_as_float(pair << 16)),
-                                __fmul_rn(res_scale, __uint_as_float(pair & 0xffff0000u))));
+                    make_float2(__fmul_rn(res_scale, rc.x), __fmul_rn(res_scale, rc.y)));
                 c = ctr2(sum, q2);
             }
             k[jp] = c;
         }
         if (row_ok) {
+            if (ep.y_u8 != nullptr) {
+                uint32_t w8[4];
+                pack_u8x16(w8, k, RES ? q2.clo : q1.clo, P + (RES ? 5 : 2) * HP + (c0 >> 1), PERCOL, qlo);
+                unsigned char* o8 = reinterpret_cast<unsigned char*>(ep.y_u8) + row * N;
+                if (I8) st_u8_pair(o8, gcol, N, it, held, w8, wide8);            // paired slices: 32-byte stores
+                else if (full) *reinterpret_cast<uint4*>(o8 + gcol) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                else *reinterpret_cast<uint2*>(o8 + gcol) = make_uint2(w8[0], w8[1]);
+            }
             if (ep.y_ctr != nullptr) {
                 uint32_t w[8];
 #pragma unroll
@@ -506,15 +629,18 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 //            as accurate as a global two-pass variance
 //   loop 3   z = Q3( (v - mean) * rstd * gamma + beta ) -> bf16 grid / fp32
 // All three quantizers are per-tensor here (the host routes anything else to the unfused kernels).
-template <int BN, bool FAST>
+// (Both operand modes walk the slices in the paired order of slice_col<true>, so the fp32 row statistics
+// are summed in the same order and the two modes give bit-identical results.)
+template <int BN, bool FAST, bool I8>
 __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params, uint32_t tmem_tile, int third, int quarter,
                                                 int lane, int64_t row, bool row_ok, int64_t n0, int64_t N,
-                                                float res_scale, uint32_t tfull, uint32_t tphase) {
+                                                float res_scale, float res_zp, uint32_t tfull, uint32_t tphase) {
     constexpr int HP = BN / 2;
     const float4* P = reinterpret_cast<const float4*>(params);
-    float* part = params + 14 * BN;                    // [2][3][BM] lane partials (sum | squared deviations)
+    float* part = params + 16 * BN;                    // [2][3][BM] lane partials (sum | squared deviations)
     float* xs = part + 6 * BM;                         // [8][BM][2] (sum, M2) of every CTA of the cluster
     QReg q1, q2, q3;
+    float ln_lo = 0.0f;
     {
         const float4 a = P[HP], b = P[2 * HP], c = P[3 * HP], d = P[4 * HP], e = P[5 * HP];
         q1.s = make_float2(a.x, a.y); q1.ns = make_float2(a.z, a.w);
@@ -528,16 +654,17 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
         const QP p3 = resolve(ep.ln_q, 0, lo, hi);
         q3.s = splat(p3.scale); q3.ns = splat(-p3.scale); q3.r = splat(p3.rcp);
         q3.clo = splat(lo - p3.zp); q3.chi = splat(hi - p3.zp);
+        ln_lo = lo;
     }
     const uint32_t cn = cluster_nctarank(), my = cluster_ctarank();
     const int rl = quarter * 32 + lane;                // row inside the tile
     const bool wide_c = ((((uintptr_t)ep.y_ctr) | ((uintptr_t)ep.res_ctr)) & 31u) == 0 && (N & 15) == 0;
     const bool wide_y = (((uintptr_t)ep.y) & 31u) == 0;
-    const __nv_bfloat16* res_row = ep.res_ctr + row * N + n0;
+    const int64_t res_base = row * N + n0;
     uint32_t rnext[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rnext[i] = 0u;
-    if (row_ok) ld_row32(res_row + third * 16, wide_c, true, rnext);
+    if (row_ok) ld_res16<I8>(ep.res_ctr, res_base + slice_col<true>(third, 0), wide_c, true, rnext);
     mbar_wait(tfull, tphase);
     tc_fence_after();
     if (threadIdx.x == 0) TQ_TRACE(8);
@@ -546,25 +673,25 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
     float s = 0.0f;
     int n_loc = 0;
 #pragma unroll 1
-    for (int c0 = third * 16; c0 < BN; c0 += 48) {
+    for (int it = 0, c0; (c0 = slice_col<true>(third, it)) < BN; ++it) {
         uint32_t v[16];
         tmem_ld16(tmem_tile + (uint32_t)c0, v);
         uint32_t rw[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) rw[j] = rnext[j];
-        if (row_ok && c0 + 48 < BN) ld_row32(res_row + c0 + 48, wide_c, true, rnext);
+        const int cn = slice_col<true>(third, it + 1);
+        if (row_ok && cn < BN) ld_res16<I8>(ep.res_ctr, res_base + cn, wide_c, true, rnext);
         uint32_t kp[8];
 #pragma unroll
         for (int jp = 0; jp < 8; ++jp) {
             const float4 p0 = P[(c0 >> 1) + jp];
-            const float2 f = __ffma2_rn(make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])),
+            const float2 f = __ffma2_rn(acc_pair<I8>(v[2 * jp], v[2 * jp + 1], P[7 * HP + (I8 ? (c0 >> 1) + jp : 0)]),
                                         make_float2(p0.x, p0.y), make_float2(p0.z, p0.w));
             const float2 c = ctr2_t<FAST>(f, q1);
-            const uint32_t pair = rw[jp];
+            const float2 rc = res_pair<I8>(rw, jp, res_zp);
             const float2 sum = __fadd2_rn(
                 make_float2(__fmul_rn(q1.s.x, c.x), __fmul_rn(q1.s.y, c.y)),
-                make_float2(__fmul_rn(res_scale, __uint_as_float(pair << 16)),
-                            __fmul_rn(res_scale, __uint_as_float(pair & 0xffff0000u))));
+                make_float2(__fmul_rn(res_scale, rc.x), __fmul_rn(res_scale, rc.y)));
             const float2 k = ctr2_t<FAST>(sum, q2);
             kp[jp] = pack_bf16(k);
             s = __fadd_rn(s, __fmul_rn(q2.s.x, k.x));                       // LayerNorm input = scale * (x_int - zp)
@@ -578,7 +705,7 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
     const float m_loc = __fdiv_rn(s, (float)n_loc);
     float m2 = 0.0f;
 #pragma unroll 1
-    for (int c0 = third * 16; c0 < BN; c0 += 48) {
+    for (int it = 0, c0; (c0 = slice_col<true>(third, it)) < BN; ++it) {
         uint32_t kp[8];
         tmem_ld8(tmem_tile + (uint32_t)c0, kp);
 #pragma unroll
@@ -602,7 +729,8 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
         float M2c = 0.0f;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            const int n_t = 16 * ((BN - t * 16 + 47) / 48);                 // values held by a lane of warp-third t
+            // values held by a lane of warp-third t (see slice_col)
+            const int n_t = 16 * (2 * ((BN - t * 32) / 96) + (((BN - t * 32) % 96) >= 32 ? 2 : ((BN - t * 32) % 96) >= 16 ? 1 : 0));
             const float dm = __fsub_rn(__fdiv_rn(part[t * BM + rl], (float)n_t), mc);
             M2c = __fadd_rn(M2c, __fmaf_rn((float)n_t * dm, dm, part[(3 + t) * BM + rl]));
         }
@@ -625,8 +753,10 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
     const float rstd = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(M2, (float)N), ep.ln_eps)));
     // ---- loop 3: normalise, affine, output quantizer ----
     const float2 nmean = splat(-mean), rstd2 = splat(rstd);
+    uint32_t held[4] = {0u, 0u, 0u, 0u};
+    const bool wide8 = I8 && ((((uintptr_t)ep.y_u8) & 31u) == 0) && (N & 31) == 0;
 #pragma unroll 1
-    for (int c0 = third * 16; c0 < BN; c0 += 48) {
+    for (int it = 0, c0; (c0 = slice_col<true>(third, it)) < BN; ++it) {
         uint32_t kp[8];
         tmem_ld8(tmem_tile + (uint32_t)c0, kp);
         float2 k3[8];
@@ -641,6 +771,11 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
         }
         if (row_ok) {
             const int64_t gcol = n0 + c0;
+            if (I8 && ep.y_u8 != nullptr) {
+                uint32_t w8[4];
+                pack_u8x16(w8, k3, q3.clo, P, false, ln_lo);
+                st_u8_pair(reinterpret_cast<unsigned char*>(ep.y_u8) + row * N, gcol, N, it, held, w8, wide8);
+            }
             if (ep.y_ctr != nullptr) {
                 uint32_t w[8];
 #pragma unroll
@@ -666,11 +801,11 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
 // Generic path (cold): any activation, no output quantizer, scales that need the IEEE division
 // instruction, calibration min/max side reduction.  One element at a time through a compact loop;
 // NaN propagates through the clamp like torch.clamp.
-template <int BN>
+template <int BN, bool I8>
 __device__ __forceinline__ void epi_tile_generic(const EpiArgs& ep, const float* params, uint32_t tmem_tile, int third,
                                                  int64_t row, bool row_ok, int64_t n0, int64_t N, float res_scale,
-                                                 bool has_q, bool has_res, uint32_t tfull, uint32_t tphase,
-                                                 float& run_min, float& run_max) {
+                                                 float res_zp, float qlo, bool has_q, bool has_res, uint32_t tfull,
+                                                 uint32_t tphase, float& run_min, float& run_max) {
     const bool wide_c = ((((uintptr_t)ep.y_ctr) | ((uintptr_t)ep.res_ctr)) & 31u) == 0 && (N & 15) == 0;
     const bool wide_y = (((uintptr_t)ep.y) & 31u) == 0;
     mbar_wait(tfull, tphase);
@@ -685,17 +820,19 @@ __device__ __forceinline__ void epi_tile_generic(const EpiArgs& ep, const float*
         uint32_t rw[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rw[i] = 0u;
-        if (has_res && row_ok) ld_row32(ep.res_ctr + row * N + gcol, wide_c, full, rw);
+        if (has_res && row_ok) ld_res16<I8>(ep.res_ctr, row * N + gcol, wide_c, full, rw);
         uint32_t o[16];
 #pragma unroll 1
         for (int j = 0; j < 16; ++j) {
             float acc = 0.0f;
-            uint32_t pair = 0u;
+            float rc = 0.0f;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 if (i == j) {
-                    acc = __uint_as_float(v[i]);
-                    pair = rw[i >> 1];
+                    const float2 a2 = acc_pair<I8>(v[i], v[i], reinterpret_cast<const float4*>(params)[7 * (BN / 2) + (I8 ? (c0 + i) >> 1 : 0)]);
+                    acc = (i & 1) ? a2.y : a2.x;
+                    const float2 r2 = res_pair<I8>(rw, i >> 1, res_zp);
+                    rc = (i & 1) ? r2.y : r2.x;
                 }
             const int col = c0 + j;
             float f = apply_act(__fmaf_rn(acc, params[pidx(BN, 0, 0, col)], params[pidx(BN, 0, 1, col)]), ep.act_fn);
@@ -706,7 +843,6 @@ __device__ __forceinline__ void epi_tile_generic(const EpiArgs& ep, const float*
                 f = __fmul_rn(s, c);
             }
             if (has_res) {
-                const float rc = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));
                 const float sum = __fadd_rn(f, __fmul_rn(res_scale, rc));
                 const float s2 = params[pidx(BN, 4, 0, col)];
                 c = clamp_nan(rint_even(__fdiv_rn(sum, s2)), params[pidx(BN, 5, 1, col)], params[pidx(BN, 3, 1, col)]);
@@ -724,6 +860,13 @@ __device__ __forceinline__ void epi_tile_generic(const EpiArgs& ep, const float*
                 }
         }
         if (row_ok) {
+            if (I8 && ep.y_u8 != nullptr && has_q) {
+                float2 k[8];
+#pragma unroll
+                for (int jp = 0; jp < 8; ++jp) k[jp] = make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1]));
+                st_u8x16(reinterpret_cast<unsigned char*>(ep.y_u8) + row * N + gcol, k, make_float2(0.0f, 0.0f),
+                         reinterpret_cast<const float4*>(params) + (has_res ? 5 : 2) * (BN / 2) + (c0 >> 1), true, qlo, full);
+            }
             if (ep.y_ctr != nullptr) {
                 uint32_t w[8];
 #pragma unroll
@@ -742,7 +885,7 @@ __device__ __forceinline__ void epi_tile_generic(const EpiArgs& ep, const float*
 
 // LNF: residual block with the LayerNorm fused into the epilogue -- one tile per CTA, launched as
 // clusters of N / BN CTAs that exchange the row statistics through distributed shared memory.
-template <int BN, int CTAS, bool LNF>
+template <int BN, int CTAS, bool LNF, bool I8>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   int64_t M, int64_t N, int64_t K, int k_split, int ring, EpiArgs ep) {
@@ -766,7 +909,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int64_t m_tiles = (M + BM * CTAS - 1) / (BM * CTAS), n_tiles = (N + BN - 1) / BN;
     const int64_t tiles = m_tiles * n_tiles;
     const int64_t tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
-    const int kb_per_pass = (int)(K / BK);
+    constexpr int BKe = I8 ? 2 * BK : BK;             // elements per 128-byte k-block row
+    const int kb_per_pass = (int)(K / BKe);
     const int num_kb = kb_per_pass * k_split;
 
     if (threadIdx.x == 0) TQ_TRACE(0);
@@ -795,8 +939,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int kb = 0; kb < p_pre; ++kb) {      // ring slots are free: no empty-barrier wait
                 mbar_expect_tx(full_bar(p_stage), C::kStageBytes);
                 const uint32_t sa = base + p_stage * C::kStageBytes;
-                tma_load_2d<1>(sa, &map_a, kb * BK, m0, full_bar(p_stage));
-                tma_load_2d<1>(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BK, n0, full_bar(p_stage));
+                tma_load_2d<1>(sa, &map_a, kb * BKe, m0, full_bar(p_stage));
+                tma_load_2d<1>(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BKe, n0, full_bar(p_stage));
                 if (++p_stage == ring) { p_stage = 0; p_phase ^= 1u; }
             }
         }
@@ -844,8 +988,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     // the leader's barrier counts the bytes of both CTAs (the MMA issuer waits on it)
                     if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CTAS);
                     const uint32_t sa = base + stage * C::kStageBytes;
-                    tma_load_2d<CTAS>(sa, &map_a, kb * BK, m0, full_bar(stage));
-                    tma_load_2d<CTAS>(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BK, n0, full_bar(stage));
+                    tma_load_2d<CTAS>(sa, &map_a, kb * BKe, m0, full_bar(stage));
+                    tma_load_2d<CTAS>(sa + C::kABytes, &map_w, (kb % kb_per_pass) * BKe, n0, full_bar(stage));
                     if (++stage == ring) { stage = 0; phase ^= 1u; }
                 }
                 TQ_TRACE(3);
@@ -866,7 +1010,14 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         if (lane == 0 && cta_rank == 0) {             // the pair's leader issues for both CTAs
-            constexpr uint32_t idesc = make_idesc(BM * CTAS, BN);
+            uint32_t idesc = make_idesc(BM * CTAS, BN);
+            if (I8) {
+                // kind::i8: int32 accumulators; operand signedness from the quantizers (asymmetric grids
+                // are unsigned, symmetric ones carry a device-side `signed` flag)
+                const uint32_t a_s8 = (ep.a_q.zero_float == nullptr && ep.a_q.is_signed != nullptr && *ep.a_q.is_signed) ? 1u : 0u;
+                const uint32_t w_s8 = (ep.w_q.zero_float == nullptr && ep.w_q.is_signed != nullptr && *ep.w_q.is_signed) ? 1u : 0u;
+                idesc = (2u << 4) | (a_s8 << 7) | (w_s8 << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
+            }
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -885,8 +1036,10 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 B (16 bf16) inside the 128 B swizzle span: +2 in 16-byte units
-                        tc_mma_bf16<CTAS>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                    (uint32_t)((kb | k) != 0));
+                        if (I8) tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                          (uint32_t)((kb | k) != 0));
+                        else tc_mma_bf16<CTAS>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                               (uint32_t)((kb | k) != 0));
                     }
                     tc_commit<CTAS>(empty_bar(stage));         // smem slot free once these MMAs retire
                     if (++stage == ring) { stage = 0; phase ^= 1u; }
@@ -908,20 +1061,25 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const bool has_q = ep.out_q.delta != nullptr;
         const bool has_res = ep.res_ctr != nullptr;
         const bool percol = (has_q && ep.out_q_params > 1) || (has_res && ep.out2_params > 1);
-        float q2lo = 0.0f, q2hi = 0.0f, res_scale = 1.0f;
+        float q2lo = 0.0f, q2hi = 0.0f, res_scale = 1.0f, res_zp = 0.0f;
         if (has_res) {
             grid_of(ep.out2_q, q2lo, q2hi);
             float lo, hi;
             grid_of(ep.res_q, lo, hi);
-            res_scale = resolve(ep.res_q, 0, lo, hi).scale;
+            const QP rq = resolve(ep.res_q, 0, lo, hi);
+            res_scale = rq.scale;
+            res_zp = rq.zp;
         }
         float qlo = 0.0f, qhi = 0.0f;
         if (has_q) grid_of(ep.out_q, qlo, qhi);
         float a_scale = 1.0f;
+        int a_zp = 0;
         if (ep.a_q.delta != nullptr) {
             float lo, hi;
             grid_of(ep.a_q, lo, hi);
-            a_scale = resolve(ep.a_q, 0, lo, hi).scale;
+            const QP aq = resolve(ep.a_q, 0, lo, hi);
+            a_scale = aq.scale;
+            a_zp = (int)aq.zp;
         }
         float wlo = 0.0f, whi = 0.0f;
         if (ep.w_q.delta != nullptr) grid_of(ep.w_q, wlo, whi);
@@ -980,6 +1138,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     params[pidx(BN, 6, 0, j)] = n < N ? ep.ln_gamma[n] : 0.0f;
                     params[pidx(BN, 6, 1, j)] = n < N ? ep.ln_beta[n] : 0.0f;
                 }
+                if (I8) params[pidx(BN, 7, 0, j)] = __int_as_float(n < N ? a_zp * ep.w_rowsum[n] : 0);
             }
             // barrier + OR-reduction over the 384 epilogue threads (named barrier 1)
             int exact;
@@ -998,20 +1157,21 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t tf = tfull_bar(acc);
             const bool fast = has_q && !exact && ep.tile_minmax == nullptr && ep.act_fn <= 1;
             const int mode = !fast ? -1 : (has_res ? 4 : ep.act_fn * 2) + (percol ? 1 : 0);
+            const float out_lo = has_res ? q2lo : qlo;           // lower edge of the integer grid that is stored
             if (LNF) {
-                if (exact) epi_tile_res_ln<BN, false>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, tf, acc_phase);
-                else epi_tile_res_ln<BN, true>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, tf, acc_phase);
+                if (exact) epi_tile_res_ln<BN, false, I8>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, res_zp, tf, acc_phase);
+                else epi_tile_res_ln<BN, true, I8>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, res_zp, tf, acc_phase);
             } else
             switch (mode) {                                      // warp-uniform
-                case 0: epi_tile_fast<BN, 0, false, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
-                case 1: epi_tile_fast<BN, 0, true, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
-                case 2: epi_tile_fast<BN, 1, false, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
-                case 3: epi_tile_fast<BN, 1, true, false>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
-                case 4: epi_tile_fast<BN, 0, false, true>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
-                case 5: epi_tile_fast<BN, 0, true, true>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, tf, acc_phase); break;
+                case 0: epi_tile_fast<BN, 0, false, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
+                case 1: epi_tile_fast<BN, 0, true, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
+                case 2: epi_tile_fast<BN, 1, false, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
+                case 3: epi_tile_fast<BN, 1, true, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
+                case 4: epi_tile_fast<BN, 0, false, true, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
+                case 5: epi_tile_fast<BN, 0, true, true, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
                 default:
-                    epi_tile_generic<BN>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, has_q, has_res, tf,
-                                         acc_phase, run_min, run_max);
+                    epi_tile_generic<BN, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, has_q,
+                                             has_res, tf, acc_phase, run_min, run_max);
                     break;
             }
             if (et == 0) TQ_TRACE(9);
@@ -1097,32 +1257,32 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// row-major [rows, cols] bf16 -> 2-D tensor map with a [box_rows, 64] box, 128 B swizzle
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+// row-major [rows, cols] bf16 (or 8-bit) -> 2-D tensor map with a [box_rows, 128 bytes] box, 128 B swizzle
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows, bool i8 = false) {
     EncodeTiledFn enc = encode_fn();
     if (enc == nullptr) return TQ_EUNSUPPORTED;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * (i8 ? 1 : 2)};
+    const cuuint32_t box[2] = {(cuuint32_t)(i8 ? 2 * BK : BK), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(map, i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? TQ_OK : TQ_EINVAL;
 }
 
-template <int BN, int CTAS, bool LNF = false>
+template <int BN, int CTAS, bool LNF = false, bool I8 = false>
 static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K, int k_split, const EpiArgs& ep,
                   cudaStream_t st) {
     using C = Cfg<BN, CTAS>;
     static_assert(C::kSmemBytes <= 227 * 1024, "shared memory budget");
     static_assert(2 * BN <= kTmemCols, "TMEM budget");
     CUtensorMap map_a, map_w;
-    if (int e = make_map(&map_a, a, M, K * k_split, BM)) return e;
-    if (int e = make_map(&map_w, w, N, K, C::kBRows)) return e;
+    if (int e = make_map(&map_a, a, M, K * k_split, BM, I8)) return e;
+    if (int e = make_map(&map_w, w, N, K, C::kBRows, I8)) return e;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_qdq_kernel<BN, CTAS, LNF>,
+        cudaError_t e = cudaFuncSetAttribute(linear_qdq_kernel<BN, CTAS, LNF, I8>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
@@ -1140,7 +1300,7 @@ static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K,
         const int f = atoi(e);
         if (f >= 1 && f < ring) ring = f;
     }
-    return launch_pdl(linear_qdq_kernel<BN, CTAS, LNF>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, cluster, map_a,
+    return launch_pdl(linear_qdq_kernel<BN, CTAS, LNF, I8>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, cluster, map_a,
                       map_w, M, N, K, k_split, ring, ep);
 }
 
@@ -1155,7 +1315,7 @@ static int launch(const void* a, const void* w, int64_t M, int64_t N, int64_t K,
 struct TileShape {
     int bn, ctas;
 };
-static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act_fn, bool has_res) {
+static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act_fn, bool has_res, bool i8 = false) {
     const int cands[5] = {256, 192, 128, 96, 64};
     int force_bn = 0, force_ctas = 0;
     if (const char* e = getenv("TQ_LINEAR_BN")) force_bn = atoi(e);          // tuning aids
@@ -1176,7 +1336,7 @@ static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act
             const double per_cta = (double)((tiles + slots - 1) / slots);
             double kb_c = ctas == 2 ? 715.0 : 595.0 + 0.9 * bn;
             if (kb_c < bn * 2.05) kb_c = bn * 2.05;
-            const double main_c = (double)(K / BK) * k_split * kb_c;
+            const double main_c = (double)(K / (i8 ? 2 * BK : BK)) * k_split * kb_c;
             const double epi_c = (bn / 16.0 / 3.0) * (has_res ? 1050.0 : (act_fn == 1 || act_fn == 3 ? 1750.0 : 900.0));
             const double cost = (ctas == 2 ? 6000.0 : 3500.0) + main_c + (per_cta - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
             if (cost < best_cost) {
@@ -1201,8 +1361,16 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
                        tq_qspec w_q, int64_t w_q_params, int32_t act_fn, tq_qspec out_q, int64_t out_q_params,
                        const void* res_ctr_bf16, tq_qspec res_q, tq_qspec out2_q, int64_t out2_q_params,
                        float* tile_minmax, void* ws, size_t ws_bytes, void* stream, const float* ln_gamma = nullptr,
-                       const float* ln_beta = nullptr, float ln_eps = 0.0f, const tq_qspec* ln_q = nullptr) {
+                       const float* ln_beta = nullptr, float ln_eps = 0.0f, const tq_qspec* ln_q = nullptr,
+                       bool i8 = false, const int32_t* w_rowsum = nullptr, void* y_u8 = nullptr) {
     using namespace tq::gemm;
+    if (i8) {
+        // 8-bit operand mode: A / W / residual are x_int bytes; K in 128-element blocks; rows 16-byte aligned
+        if (w_rowsum == nullptr || a_q.delta == nullptr || w_q.delta == nullptr) return TQ_EINVAL;
+        if (a_q.n_bits > 8 || w_q.n_bits > 8 || (res_ctr_bf16 != nullptr && res_q.n_bits > 8)) return TQ_EUNSUPPORTED;
+        if (k_split != 1 || K % (2 * BK) != 0 || N % 16 != 0) return TQ_EUNSUPPORTED;
+        if (y_u8 != nullptr && (out_q.delta == nullptr || !tq::aligned16(y_u8))) return TQ_EINVAL;
+    }
     if (res_ctr_bf16 != nullptr) {
         if (out_q.delta == nullptr || res_q.delta == nullptr) return TQ_EINVAL;
         if (int e = tq::check_qspec(out2_q)) return e;
@@ -1210,7 +1378,7 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
         if (out2_q_params != 1 && out2_q_params != N) return TQ_EINVAL;
         if (!tq::aligned16(res_ctr_bf16)) return TQ_EALIGN;
     }
-    if (a_ctr_bf16 == nullptr || w_ctr_bf16 == nullptr || (y == nullptr && y_ctr_bf16 == nullptr)) return TQ_EINVAL;
+    if (a_ctr_bf16 == nullptr || w_ctr_bf16 == nullptr || (y == nullptr && y_ctr_bf16 == nullptr && y_u8 == nullptr)) return TQ_EINVAL;
     if (M < 1 || N < 1 || K < 1 || (k_split != 1 && k_split != 3)) return TQ_EINVAL;
     if (K % BK != 0 || N % 8 != 0) return TQ_EUNSUPPORTED;
     if (!tq::aligned16(a_ctr_bf16) || !tq::aligned16(w_ctr_bf16)) return TQ_EALIGN;
@@ -1247,6 +1415,8 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
     ep.out2_q = out2_q;
     ep.out2_params = out2_q_params;
     cudaStream_t st = (cudaStream_t)stream;
+    ep.y_u8 = y_u8;
+    ep.w_rowsum = w_rowsum;
     ep.ln_gamma = ln_gamma;
     ep.ln_beta = ln_beta;
     ep.ln_eps = ln_eps;
@@ -1267,10 +1437,18 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
             if (force_bn != 0 && force_bn != bn && N % force_bn == 0 && N / force_bn <= 8 && force_bn >= 128) continue;
             const int64_t tiles = ((M + BM - 1) / BM) * (N / bn);
             const double waves = (double)((tiles + tq::sm_count() - 1) / tq::sm_count());
-            const double cost = waves * ((double)(K / BK) * (595.0 + 0.9 * bn) + (bn / 16.0 / 3.0) * 1600.0 + 4500.0);
+            const double cost = waves * ((double)(K / (i8 ? 2 * BK : BK)) * (595.0 + 0.9 * bn) + (bn / 16.0 / 3.0) * 1600.0 + 4500.0);
             if (cost < best_cost) {
                 best_cost = cost;
                 best = bn;
+            }
+        }
+        if (i8) {
+            switch (best) {
+                case 256: return launch<256, 1, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+                case 192: return launch<192, 1, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+                case 128: return launch<128, 1, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+                default: return TQ_EUNSUPPORTED;
             }
         }
         switch (best) {
@@ -1280,7 +1458,16 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
             default: return TQ_EUNSUPPORTED;
         }
     }
-    const TileShape ts = pick_tile(M, N, K, k_split, act_fn, res_ctr_bf16 != nullptr);
+    const TileShape ts = pick_tile(M, N, K, k_split, act_fn, res_ctr_bf16 != nullptr, i8);
+    if (i8) {
+        switch (ts.bn) {
+            case 256: return launch<256, 1, false, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+            case 192: return launch<192, 1, false, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+            case 128: return launch<128, 1, false, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+            case 96: return launch<96, 1, false, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+            default: return launch<64, 1, false, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, 1, ep, st);
+        }
+    }
     if (ts.ctas == 2) {
         switch (ts.bn) {
             case 256: return launch<256, 2>(a_ctr_bf16, w_ctr_bf16, M, N, K, k_split, ep, st);
@@ -1325,6 +1512,38 @@ int tq_linear_res_ln_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, co
     if (res_ctr_bf16 == nullptr || ln_gamma_q == nullptr || ln_beta == nullptr) return TQ_EINVAL;
     return linear_impl(a_ctr_bf16, w_ctr_bf16, bias, z, z_ctr_bf16, M, N, K, 1, a_q, w_q, w_q_params, 0, out_q, 1,
                        res_ctr_bf16, res_q, out2_q, 1, nullptr, nullptr, 0, stream, ln_gamma_q, ln_beta, ln_eps, &ln_q);
+}
+
+int tq_linear_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias, float* y,
+                     void* y_ctr_bf16, void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q,
+                     int64_t w_q_params, int32_t act_fn, tq_qspec out_q, int64_t out_q_params, void* stream) {
+    tq_qspec none;
+    none.delta = nullptr; none.zero_float = nullptr; none.is_signed = nullptr;
+    none.n_bits = 8; none.log_domain = 0; none.eps = 1e-8f;
+    return linear_impl(a_i8, w_i8, bias, y, y_ctr_bf16, M, N, K, 1, a_q, w_q, w_q_params, act_fn, out_q, out_q_params,
+                       nullptr, none, none, 1, nullptr, nullptr, 0, stream, nullptr, nullptr, 0.0f, nullptr, true, w_rowsum,
+                       y_i8);
+}
+
+int tq_linear_qdq_bf16_o8(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, void* y_i8, int64_t M,
+                          int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q, int64_t w_q_params, int32_t act_fn,
+                          tq_qspec out_q, int64_t out_q_params, void* stream) {
+    tq_qspec none;
+    none.delta = nullptr; none.zero_float = nullptr; none.is_signed = nullptr;
+    none.n_bits = 8; none.log_domain = 0; none.eps = 1e-8f;
+    if (y_i8 == nullptr || out_q.delta == nullptr || out_q.n_bits > 8 || N % 16 != 0 || act_fn > 1) return TQ_EUNSUPPORTED;
+    return linear_impl(a_ctr_bf16, w_ctr_bf16, bias, nullptr, nullptr, M, N, K, 1, a_q, w_q, w_q_params, act_fn, out_q,
+                       out_q_params, nullptr, none, none, 1, nullptr, nullptr, 0, stream, nullptr, nullptr, 0.0f, nullptr,
+                       false, nullptr, y_i8);
+}
+
+int tq_linear_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias, float* z,
+                            void* z_ctr_bf16, void* z_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q,
+                            int64_t w_q_params, tq_qspec out_q, const void* res_i8, tq_qspec res_q, tq_qspec out2_q,
+                            const float* ln_gamma_q, const float* ln_beta, float ln_eps, tq_qspec ln_q, void* stream) {
+    if (res_i8 == nullptr || ln_gamma_q == nullptr || ln_beta == nullptr) return TQ_EINVAL;
+    return linear_impl(a_i8, w_i8, bias, z, z_ctr_bf16, M, N, K, 1, a_q, w_q, w_q_params, 0, out_q, 1, res_i8, res_q,
+                       out2_q, 1, nullptr, nullptr, 0, stream, ln_gamma_q, ln_beta, ln_eps, &ln_q, true, w_rowsum, z_i8);
 }
 
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream) {

@@ -44,6 +44,11 @@ def _mgr(module):
     return q
 
 
+def _unsigned_grid(q):
+    """integer grid [0, 2^n - 1]: asymmetric quantizers and symmetric ones over non-negative data"""
+    return (not q.symmetric) or (not bool(q.signed))
+
+
 class _Site:
     """per-tensor quantizer -> tq_qspec (keeps the buffers alive)"""
 
@@ -109,6 +114,11 @@ class _Weight:
         self.N, self.K = self.grid.shape
         self._signed = q0._signed
         self.spec = ops.spec(self.delta, None, self._signed, q0.n_bits, q0.scale_domain == 'log', q0.eps)
+        # 8-bit operand mode: the same integers, one byte each (two's complement when the grid is signed),
+        # and their row sums for the zero-point correction of the activations
+        gi = self.grid.to(torch.int32)
+        self.grid8 = (gi.to(torch.int8) if bool(q0.signed) else gi.to(torch.uint8)).contiguous()
+        self.rowsum = gi.sum(dim=1, dtype=torch.int32).contiguous()
 
 
 def _ln_params(ln):
@@ -158,7 +168,7 @@ class FusedBertEngine:
                 d['z'] = _Site(_mgr(L.z))
                 self.layers.append(d)
             self.w_pool, self.pool_out = _Weight([model.pooler]), _Site(_mgr(model.pooler))
-            self.w_cls, self.cls_out = _Weight([model.classifier], pad_to=8), _Site(_mgr(model.classifier))
+            self.w_cls, self.cls_out = _Weight([model.classifier], pad_to=16), _Site(_mgr(model.classifier))
         M, D = batch * seq, self.D
         bf = dict(dtype=torch.bfloat16, device=dev)
         self.x = torch.empty(M, D, **bf)
@@ -171,6 +181,22 @@ class FusedBertEngine:
         self.M = M
         # residual blocks: LayerNorm fused into the GEMM epilogue (cluster kernel) unless switched off
         self.fuse_ln = os.environ.get('TQ_ENGINE_FUSE_LN', '1') != '0' and D <= 2048
+        # 8-bit operand mode: activations travel as x_int bytes and every GEMM runs on the int8 tensor
+        # cores (exact int32 accumulation).  Needs unsigned activation grids (asymmetric quantizers, the
+        # BASELINE configuration) -- anything else keeps the bf16 carriers.
+        sites = [self.e_out, self.pool_out] + [d[k] for d in self.layers for k in ('c', 'x', 'f', 'z')]
+        self.i8 = (os.environ.get('TQ_ENGINE_I8', '1') != '0' and self.fuse_ln and D % 128 == 0
+                   and cfg.intermediate_size % 128 == 0 and all(_unsigned_grid(st.q) for st in sites))
+        if self.i8:
+            u8 = dict(dtype=torch.uint8, device=dev)
+            self.x8 = torch.empty(M, D, **u8)
+            self.c8 = torch.empty(M, D, **u8)
+            self.a8 = torch.empty(M, D, **u8)
+            self.f8 = torch.empty(M, cfg.intermediate_size, **u8)
+            self.first8 = torch.empty(batch, D, **u8)
+            self.pooled8 = torch.empty(batch, D, **u8)
+        self.ffn_in_bf16 = os.environ.get('TQ_ENGINE_FFN_IN_BF16', '1') != '0'
+        self._last_i8 = False
 
     def _linear(self, a_ctr, a_site, w, act, out_spec, out_params, out_ctr=None, want_f32=False, M=None):
         M = a_ctr.shape[0] if M is None else M
@@ -202,6 +228,9 @@ class FusedBertEngine:
         assert tuple(input_ids.shape) == (B, T)
         # the pre-LayerNorm sums (sites u / y) only exist in the unfused chain: tracing keeps it
         fuse_ln = self.fuse_ln and trace is None
+        self._last_i8 = self.i8 and fuse_ln
+        if self._last_i8:
+            return self._forward_i8(input_ids, attention_mask, token_type_ids)
         mask = None
         if attention_mask is not None:
             mask = ((1.0 - attention_mask.to(torch.float32)) * -10000.0).contiguous()
@@ -253,9 +282,61 @@ class FusedBertEngine:
             logits = torch.clamp(logits, 0.0, 5.0)
         return logits
 
+    def _forward_i8(self, input_ids, attention_mask, token_type_ids):
+        """the same chain with x_int byte carriers and int8 tensor-core GEMMs (5 kernels per layer)"""
+        ops = self.ops
+        B, T, D, H, M = self.B, self.T, self.D, self.H, self.M
+        mask = None
+        if attention_mask is not None:
+            mask = ((1.0 - attention_mask.to(torch.float32)) * -10000.0).contiguous()
+        ids = input_ids.reshape(-1).contiguous()
+        tt = token_type_ids.reshape(-1).contiguous() if token_type_ids is not None else None
+        x, c, a, f = self.x8, self.c8, self.a8, self.f8
+        ops.embed_ln_qdq_i8(ids, tt, None, T, self.word_q, self.type_q, self.pos_q, self.e_tok.spec, 1, self.e_pos.spec, 1,
+                            self.e_gamma, self.e_beta, self.e_eps, self.e_out.spec, 1, x)
+        x_site = self.e_out
+        for d in self.layers:
+            w = d['wqkv']
+            ops.linear_i8(x, w.grid8, w.rowsum, w.bias, M, w.N, w.K, x_site.spec, w.spec, w.N, 0, d['qkv_out'].spec,
+                          d['qkv_out'].n, out_ctr=self.qkv)
+            ops.attention_i8(self.qkv, B, T, H, self.hd, d['q'].spec, d['k'].spec, d['v'].spec, d['s'].spec, d['p'].spec,
+                             d['c'].spec, mask, c)
+            w = d['wg']
+            g1, b1, e1 = d['ln1']
+            # FFN-in (K = hidden, GELU epilogue) measured faster with bf16 operands: the block before it writes
+            # its output in both carrier formats
+            mixed = self.ffn_in_bf16
+            ops.linear_res_ln_i8(c, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['c'].spec, w.spec, w.N, d['g'].spec, x,
+                                 x_site.spec, d['u'].spec, g1, b1, e1, d['x'].spec, a, out_ctr=self.a if mixed else None)
+            w = d['wf']
+            if mixed:
+                ops.linear_bf16_o8(self.a, w.grid, w.bias, M, w.N, w.K, d['x'].spec, w.spec, w.N, 1, d['f'].spec, 1, f)
+            else:
+                ops.linear_i8(a, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['x'].spec, w.spec, w.N, 1, d['f'].spec, 1, out_i8=f)
+            w = d['wh']
+            g2, b2, e2 = d['ln2']
+            ops.linear_res_ln_i8(f, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['f'].spec, w.spec, w.N, d['h'].spec, a,
+                                 d['x'].spec, d['y'].spec, g2, b2, e2, d['z'].spec, x)
+            x_site = d['z']
+        self.first8.copy_(x.view(B, T, D)[:, 0])                         # pooler input: first token
+        w = self.w_pool
+        ops.linear_i8(self.first8, w.grid8, w.rowsum, w.bias, B, w.N, w.K, x_site.spec, w.spec, w.N, 3, self.pool_out.spec,
+                      1, out_i8=self.pooled8)
+        w = self.w_cls
+        logits = ops.linear_i8(self.pooled8, w.grid8, w.rowsum, w.bias, B, w.N, w.K, self.pool_out.spec, w.spec, w.N, 0,
+                               self.cls_out.spec, 1, want_f32=True)
+        logits = logits[:, :self.num_labels]
+        if self.num_labels == 1:
+            logits = torch.clamp(logits, 0.0, 5.0)
+        return logits
+
     __call__ = forward
 
     def hidden_states(self):
         """dequantized output of the last encoder block of the most recent forward (for tests)"""
         z = self.layers[-1]['z'].q
+        if self._last_i8:
+            zp = z.zero_point
+            zp = zp.reshape(()) if torch.is_tensor(zp) else zp
+            return ((self.x8.float() - zp) * z.scale.reshape(())).view(self.B, self.T, self.D)
         return (self.x.float() * z.scale.reshape(())).view(self.B, self.T, self.D)

@@ -88,6 +88,21 @@ SIGNATURES = {
                                             _c_f32p, QSpec, _i64, QSpec, _i64, _c_f32p, _c_f32p, ctypes.c_float,
                                             QSpec, _i64, ctypes.c_void_p, _c_f32p, _i64, _i32, ctypes.c_void_p]),
     'tq_split3_bf16': (ctypes.c_int, [_c_f32p, ctypes.c_void_p, _i64, _i64, ctypes.c_void_p]),
+    # ---- 8-bit integer operand mode
+    'tq_linear_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p,
+                                        ctypes.c_void_p, ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, _i64, _i32,
+                                        QSpec, _i64, ctypes.c_void_p]),
+    'tq_linear_qdq_bf16_o8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p, _i64, _i64, _i64,
+                                             QSpec, QSpec, _i64, _i32, QSpec, _i64, ctypes.c_void_p]),
+    'tq_linear_res_ln_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p,
+                                               ctypes.c_void_p, ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, _i64, QSpec,
+                                               ctypes.c_void_p, QSpec, QSpec, _c_f32p, _c_f32p, ctypes.c_float, QSpec,
+                                               ctypes.c_void_p]),
+    'tq_attention_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _i32, QSpec, QSpec,
+                                           QSpec, QSpec, QSpec, QSpec, _c_f32p, ctypes.c_void_p]),
+    'tq_embed_ln_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _i64, _c_f32p, _c_f32p,
+                                          _c_f32p, QSpec, _i64, QSpec, _i64, _c_f32p, _c_f32p, ctypes.c_float,
+                                          QSpec, _i64, ctypes.c_void_p, _i64, _i32, ctypes.c_void_p]),
 }
 
 
@@ -360,6 +375,54 @@ class CudaOps:
                   int(e_tok_params), e_pos, int(e_pos_params), gamma_q.data_ptr(), beta.data_ptr(), float(eps),
                   out_spec, int(out_params), o.data_ptr(), _ptr(f), M, D, _stream())
         return o, f
+
+    # -- 8-bit integer operand mode (x_int bytes, int8 tensor cores) ---------------------------------
+    def linear_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_spec, w_params, act_fn, out_spec, out_params,
+                  want_f32=False, out_ctr=None, out_i8=None):
+        """tq_linear_qdq_i8 -> (y fp32 | None); out_ctr (bf16 centred) / out_i8 (x_int bytes) are filled if given"""
+        _chk_cuda(a_i8, w_i8, w_rowsum, bias)
+        y = torch.empty(M, N, dtype=torch.float32, device=a_i8.device) if want_f32 else None
+        null = QSpec(None, None, None, 8, 0, 1e-8)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_qdq_i8, a_i8.data_ptr(), w_i8.data_ptr(),
+                  w_rowsum.data_ptr(), _ptr(bias), _ptr(y), _ptr(out_ctr), _ptr(out_i8), M, N, K, a_spec, w_spec,
+                  int(w_params), int(act_fn), out_spec if out_spec is not None else null, int(out_params), _stream())
+        return y
+
+    def linear_res_ln_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_spec, w_params, out_spec, res_i8, res_spec,
+                         out2_spec, gamma_q, beta, eps, ln_spec, out_i8, want_f32=False, out_ctr=None):
+        _chk_cuda(a_i8, w_i8, w_rowsum, bias, res_i8, gamma_q, beta, out_i8, out_ctr)
+        z = torch.empty(M, N, dtype=torch.float32, device=a_i8.device) if want_f32 else None
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_res_ln_qdq_i8, a_i8.data_ptr(), w_i8.data_ptr(),
+                  w_rowsum.data_ptr(), _ptr(bias), _ptr(z), _ptr(out_ctr), out_i8.data_ptr(), M, N, K, a_spec, w_spec, int(w_params),
+                  out_spec, res_i8.data_ptr(), res_spec, out2_spec, gamma_q.data_ptr(), beta.data_ptr(), float(eps),
+                  ln_spec, _stream())
+        return z
+
+    def linear_bf16_o8(self, a_ctr, w_ctr, bias, M, N, K, a_spec, w_spec, w_params, act_fn, out_spec, out_params, out_i8):
+        """tq_linear_qdq_bf16_o8: bf16 centred operands, x_int byte output"""
+        _chk_cuda(a_ctr, w_ctr, bias, out_i8)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_qdq_bf16_o8, a_ctr.data_ptr(), w_ctr.data_ptr(),
+                  _ptr(bias), out_i8.data_ptr(), M, N, K, a_spec, w_spec, int(w_params), int(act_fn), out_spec,
+                  int(out_params), _stream())
+        return out_i8
+
+    def attention_i8(self, qkv_ctr, B, T, H, head_dim, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec, mask, out_i8):
+        """tq_attention_qdq_i8: bf16 centred q|k|v in, context x_int bytes out"""
+        _chk_cuda(qkv_ctr, mask, out_i8)
+        self._run('attention', 4 * B * H * T * T * head_dim, 1, self.lib.tq_attention_qdq_i8, qkv_ctr.data_ptr(),
+                  out_i8.data_ptr(), B, T, H, head_dim, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec, _ptr(mask),
+                  _stream())
+        return out_i8
+
+    def embed_ln_qdq_i8(self, ids, type_ids, pos_ids, T, word_q, type_q, pos_q, e_tok, e_tok_params, e_pos,
+                        e_pos_params, gamma_q, beta, eps, out_spec, out_params, out_i8):
+        _chk_cuda(ids, word_q, type_q, pos_q, gamma_q, beta, out_i8)
+        M, D = ids.numel(), word_q.shape[1]
+        self._run('embed_ln_qdq', 14 * M * D, 1, self.lib.tq_embed_ln_qdq_i8, ids.data_ptr(), _ptr(type_ids),
+                  _ptr(pos_ids), int(T), word_q.data_ptr(), type_q.data_ptr(), pos_q.data_ptr(), e_tok,
+                  int(e_tok_params), e_pos, int(e_pos_params), gamma_q.data_ptr(), beta.data_ptr(), float(eps),
+                  out_spec, int(out_params), out_i8.data_ptr(), M, D, _stream())
+        return out_i8
 
 
 _OPS = None
