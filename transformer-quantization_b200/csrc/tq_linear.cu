@@ -2,12 +2,13 @@
 //     y = act_quant( act_fn( x @ Wq.T + bias ) )       (reference hijacker.py:66-116,
 //                                                        autoquant_utils.py:16-21)
 // The reference runs an fp32 cuBLAS SGEMM on dequantized tensors plus separate bias / activation /
-// six QDQ kernels.  Here the GEMM consumes the INTEGER grids of the fake-quantized operands carried
-// in bf16 (exact for |v| <= 256) on the 5th-gen tensor cores:
+// six QDQ kernels.  Here the GEMM consumes the INTEGER grids of the fake-quantized operands on the
+// 5th-gen tensor cores -- centred grids in bf16 (exact for |v| <= 256, kind::f16) or the raw 8-bit
+// grids x_int (kind::i8, int32 accumulators, zero point removed with the weight row sums):
 //
 //   warp 12     TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4-8 stage smem ring
-//   warp 13     MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32
-//                              accumulators in TMEM, double buffered (2 x BN columns)
+//   warp 13     MMA issuer     tcgen05.mma.cta_group::1, M=128 x N=BN x K=16 (bf16) / K=32 (int8),
+//                              fp32 / int32 accumulators in TMEM, double buffered (2 x BN columns)
 //   warps 0-11  epilogue       tcgen05.ld 32x32b.x16 -> acc * (s_a * s_w[n]) + bias[n] -> act_fn
 //                              -> per-tensor or per-column (PEG / fused-QKV) QDQ [-> + residual -> QDQ]
 //                              -> fp32 and/or bf16 centred-integer output (operand format of the next
