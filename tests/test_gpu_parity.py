@@ -254,3 +254,16 @@ def test_uninitialised_quantizer_raises():
     with pytest.raises(tq_native.TQError):
         q.set_quant_range(-1.0, 1.0)
         q(torch.zeros(4))               # CPU tensor: rejected, no fallback
+
+
+def test_percentile_on_device_matches_numpy():
+    """the percentile ranges are computed on the GPU (torch.sort + numpy's interpolation formula)"""
+    from quantization.range_estimators import CurrentMinMaxEstimator
+    rs = np.random.RandomState(3)
+    for n, q in [(98304, 0.01), (3145728, 0.1), (1000, 50.0), (777, 99.99)]:
+        x = (rs.randn(2, n) * 3).astype(np.float32)
+        ref = np.percentile(x, (q, 100 - q), axis=-1)
+        got = CurrentMinMaxEstimator._percentiles(torch.from_numpy(x).to('cuda'), (q, 100 - q))
+        for r, g in zip(ref, got):
+            assert g.is_cuda
+            assert np.array_equal(torch.Tensor(r).numpy(), g.cpu().numpy())

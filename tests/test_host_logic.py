@@ -42,3 +42,24 @@ def test_manager_api(case, golden):
 @pytest.mark.parametrize('case', golden_cases('linear'), ids=lambda c: c['name'])
 def test_quant_linear_api(case, golden):
     P.check_linear_case(case, golden.file('linear'), CPU, exact_gemm=True)
+
+
+def test_percentile_estimator_matches_numpy():
+    """CurrentMinMaxEstimator(percentile=...) evaluates np.percentile's 'linear' method where the tensor
+    lives (sort + numpy's own float32-difference / float64-interpolation formula); the reference calls
+    np.percentile on the host (range_estimators.py:121-140).  Bit-identical, NaN slices included."""
+    import numpy as np
+    import torch
+    from quantization.range_estimators import CurrentMinMaxEstimator
+    rs = np.random.RandomState(0)
+    for trial in range(200):
+        n, rows = int(rs.randint(1, 3000)), int(rs.randint(1, 5))
+        x = (rs.randn(rows, n) * rs.rand() * 10).astype(np.float32)
+        if trial % 9 == 0:
+            x[0, rs.randint(0, n)] = np.nan
+        q = float(rs.choice([0.0, 0.01, 0.1, 1.0, 5.0, 50.0, 99.9, 99.99, 100.0, rs.rand() * 100]))
+        with np.errstate(all='ignore'):
+            ref = np.percentile(x, (q, 100 - q), axis=-1)
+        got = CurrentMinMaxEstimator._percentiles(torch.from_numpy(x), (q, 100 - q))
+        for r, g in zip(ref, got):
+            assert np.array_equal(torch.Tensor(r).numpy(), g.numpy(), equal_nan=True), (n, q)

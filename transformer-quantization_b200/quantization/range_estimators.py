@@ -28,6 +28,8 @@ import copy
 from collections import namedtuple
 from enum import Enum
 
+import math
+
 import numpy as np
 import torch
 from scipy.optimize import minimize_scalar
@@ -120,15 +122,34 @@ class CurrentMinMaxEstimator(RangeEstimatorBase):
         mn, mx = self._axis_minmax(x)
         self.ranges = tq_native.ops().dim_ranges(mn, mx, first=self.ranges is None)
 
+    @staticmethod
+    def _percentiles(rows, qs):
+        """np.percentile(rows, qs, axis=-1) (method 'linear') evaluated ON THE DEVICE of ``rows``: sort +
+        numpy's own interpolation formula in float64 (numpy promotes float32 data x float64 weights to
+        float64, the reference then casts back with torch.Tensor(...)).  Returns len(qs) fp32 vectors."""
+        srt, _ = torch.sort(rows, dim=-1)
+        n = srt.shape[-1]
+        has_nan = torch.isnan(srt[:, -1])                       # numpy: any NaN in a slice -> NaN
+        out = []
+        for q in qs:
+            vi = (n - 1) * (q / 100.0)
+            lo = min(max(int(math.floor(vi)), 0), n - 1)
+            hi = min(lo + 1, n - 1)
+            g = vi - math.floor(vi)
+            d = (srt[:, hi] - srt[:, lo]).double()              # numpy: difference in the data's dtype ...
+            a, b = srt[:, lo].double(), srt[:, hi].double()      # ... interpolation in float64
+            r = b - d * (1.0 - g) if g >= 0.5 else a + d * g     # numpy _lerp
+            r = torch.where(has_nan, torch.full_like(r, float('nan')), r)
+            out.append(r.float())
+        return out
+
     def _percentile_minmax(self, x):
-        # host numpy path, exactly as the reference (:121-127, :133-140); off the hot path
+        # reference :121-127, :133-140 (np.percentile on the host); same numbers, computed where x lives
         if self.per_channel:
-            data = to_numpy(x.reshape(x.shape[0], -1))
-            lo, hi = np.percentile(data, (self.percentile, 100 - self.percentile), axis=-1)
-            return torch.Tensor(lo).to(x.device), torch.Tensor(hi).to(x.device)
-        lo, hi = np.percentile(to_numpy(x), (self.percentile, 100))
-        return (torch.Tensor(np.atleast_1d(lo)).to(x.device).detach(),
-                torch.Tensor(np.atleast_1d(hi)).to(x.device).detach())
+            lo, hi = self._percentiles(x.detach().reshape(x.shape[0], -1), (self.percentile, 100 - self.percentile))
+            return lo, hi
+        lo, hi = self._percentiles(x.detach().reshape(1, -1), (self.percentile, 100))
+        return lo, hi
 
     def forward(self, x):
         if self.per_group_range_estimation:
