@@ -205,7 +205,7 @@ def run_reference(args):
         'e2e': {'value': val, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -483,13 +483,36 @@ def run_ours(args):
                            'shape': '256Mi fp32 (1 GiB in, 1 GiB out)', 'bytes_per_elem': 8},
         'kernels': {k: {'ms_per_step': v['seconds'] * 1e3, 'launches': v['launches']} for k, v in prof.items()},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line at
+    communicator creation whenever NCCL_DEBUG >= VERSION): point fd 1 at stderr for the whole run and keep
+    the original stdout for the result line."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
