@@ -438,3 +438,152 @@ class MSEGolden(MSEGrid):
             xmin = np.array([-fr + sub.x], dtype=np.single)
         self.current_xmin, self.current_xmax = xmin, xmax
         return xmin, xmax
+
+
+# --------------------------------------------------------------------------------------
+# training-time path: straight-through backward, learnable ranges, AdaRound soft rounding
+# (SURVEY.md section 8(f) ranks 3-4).  Pinned by tests/golden/qat.npz (make_golden_qat.py: the
+# reference under torch autograd).
+# --------------------------------------------------------------------------------------
+def _param_sum(v, C, layout):
+    """sum_to_size of an elementwise gradient onto the parameter shape.  ``layout`` = (outer, C,
+    inner) view of the tensor; per-tensor parameters: C == 1.  fp64 accumulation (torch sums fp32 in a
+    blocked order; tests compare with a tolerance relative to the summed magnitudes)."""
+    v = np.asarray(v, np.float64)
+    if C == 1:
+        return np.array([v.sum()])
+    outer, C, inner = layout
+    return v.reshape(outer, C, inner).sum(axis=(0, 2))
+
+
+def qdq_backward(x, g, delta, zero_float, signed, n_bits, eps=1e-8, scale_domain='linear', axis=None,
+                 per_channel=False):
+    """Autograd of AsymmetricUniformQuantizer.forward / SymmetricUniformQuantizer.forward
+    (quantizers.py:142-153, 172-211) for the upstream gradient ``g``:
+
+      round_ste            identity gradient                              quantizers.py:12-20
+      clamp(u, lo, hi)     gradient where lo <= u <= hi (inclusive)        quantizers.py:185
+      x / scale            grad_x = h / s, grad_s += -h * ((x / s) / s)   quantizers.py:184
+      scale * (x_int - zp) h = g * s, grad_s += g * (x_int - zp)          quantizers.py:209
+      zero_point           used twice (:184 and :209): -sum(h) + sum(h * mask), then the
+                           clamp / round_ste of quantizers.py:149-153
+      scale                clamp(delta, min=eps): gradient where delta >= eps; exp(delta): * scale
+
+    Returns (grad_x, grad_delta[n_params], grad_zero_float[n_params] | None, mag) where ``mag`` =
+    (sum |terms| of grad_scale, sum |terms| of grad_zero_point) per parameter -- the scale of the
+    fp32 summation error, used as tolerance base by the tests."""
+    x, g = _f32(x), _f32(g)
+    delta = _f32(delta).reshape(-1)
+    C = delta.size
+    s_flat = scale_of(delta, eps, scale_domain)
+    asym = zero_float is not None
+    if asym:
+        zf = _f32(zero_float).reshape(-1)
+        zp_flat = asym_zero_point(zf, n_bits)
+        lo, hi = 0.0, asym_int_max(n_bits)
+    else:
+        zp_flat = np.zeros_like(s_flat)
+        lo, hi = sym_grid(n_bits, signed)
+    if C > 1:
+        if axis is not None:
+            layout = (int(np.prod(x.shape[:axis], dtype=np.int64)), C, int(np.prod(x.shape[axis + 1:], dtype=np.int64)))
+        elif per_channel:
+            layout = (1, C, x.size // C)
+        else:
+            layout = (x.size // C, C, 1)
+        s = _view_params(s_flat, x.ndim, axis, per_channel) if (axis is not None or per_channel) else s_flat
+        zp = _view_params(zp_flat, x.ndim, axis, per_channel) if (axis is not None or per_channel) else zp_flat
+    else:
+        layout = (1, 1, x.size)
+        s, zp = s_flat.reshape(()), zp_flat.reshape(())
+    t = (x / s).astype(F32)
+    u = (np.rint(t) + zp).astype(F32)
+    mask = (u >= F32(lo)) & (u <= F32(hi))
+    x_int = np.clip(u, F32(lo), F32(hi)).astype(F32)
+    w = (x_int - zp).astype(F32)
+    h = (g * s).astype(F32)                       # MulBackward (:209)
+    gs1 = (g * w).astype(F32)
+    hm = np.where(mask, h, F32(0)).astype(F32)    # ClampBackward (:185)
+    grad_x = (hm / s).astype(F32)                 # DivBackward, self (:184)
+    gs2 = (-hm * ((x / s).astype(F32) / s).astype(F32)).astype(F32)   # DivBackward, other
+    grad_scale = (_param_sum(gs1, C, layout).astype(F32) + _param_sum(gs2, C, layout).astype(F32)).astype(F32)
+    mag_s = _param_sum(np.abs(gs1), C, layout) + _param_sum(np.abs(gs2), C, layout)
+    if scale_domain == 'linear':
+        grad_delta = np.where(delta >= F32(eps), grad_scale, F32(0)).astype(F32)
+    else:
+        grad_delta = (grad_scale * s_flat).astype(F32)
+        mag_s = mag_s * s_flat
+    grad_zf, mag_z = None, None
+    if asym:
+        grad_zp = (_param_sum(-h, C, layout).astype(F32) + _param_sum(hm, C, layout).astype(F32)).astype(F32)
+        mag_z = _param_sum(np.abs(h), C, layout) + _param_sum(np.abs(hm), C, layout)
+        r = np.rint(zf)
+        grad_zf = np.where((r >= F32(lo)) & (r <= F32(hi)), grad_zp, F32(0)).astype(F32)
+    return grad_x, grad_delta, grad_zf, (mag_s, mag_z)
+
+
+ADAROUND_MODES = ('learned_sigmoid', 'learned_hard_sigmoid', 'sigmoid_temp_decay')
+ADAROUND_ZETA, ADAROUND_GAMMA = 1.1, -0.1          # adaround/quantizer.py:29,34 defaults
+
+
+def _sigmoid(a):
+    a = _f32(a)
+    return (F32(1) / (F32(1) + np.exp(-a))).astype(F32)
+
+
+def adaround_alpha_init(x, scale, mode, temperature=None):
+    """adaround/quantizer.py:54-71: alpha such that the soft target equals the rounding rest."""
+    t = (_f32(x) / _f32(scale)).astype(F32)
+    rest = (t - np.floor(t)).astype(F32)
+    if mode == 'learned_hard_sigmoid':                                     # hard_logit, :34-36
+        return (-np.log((F32(ADAROUND_ZETA) - rest) / (rest - F32(ADAROUND_GAMMA)))).astype(F32)
+    p = np.clip(rest, F32(1e-16), F32(1 - 1e-16))                          # logit, :24-26
+    a = (-np.log(F32(1) / p - F32(1))).astype(F32)
+    if mode == 'sigmoid_temp_decay':
+        a = (F32(temperature) * a).astype(F32)
+    return a
+
+
+def adaround_rest(alpha, mode, temperature=None):
+    """AdaRoundQuantizer.get_rest, adaround/quantizer.py:84-92."""
+    alpha = _f32(alpha)
+    if mode == 'learned_sigmoid':
+        return _sigmoid(alpha)
+    if mode == 'learned_hard_sigmoid':                                     # hard_sigmoid, :29-31
+        p = _sigmoid(alpha)
+        return np.clip(p * F32(ADAROUND_ZETA - ADAROUND_GAMMA) + F32(ADAROUND_GAMMA), F32(0), F32(1)).astype(F32)
+    return _sigmoid((alpha / F32(temperature)).astype(F32))
+
+
+def adaround_to_integer(x, alpha, scale, zp, lo, hi, mode, soft, temperature=None):
+    """AdaRoundQuantizer.to_integer_forward in a relaxation mode, adaround/quantizer.py:46-82:
+    floor(x / scale) + (soft target | alpha >= 0) [+ zero_point], clamped to the grid."""
+    t = (_f32(x) / _f32(scale)).astype(F32)
+    up = adaround_rest(alpha, mode, temperature) if soft else (_f32(alpha) >= 0).astype(F32)
+    u = (np.floor(t) + up).astype(F32)
+    u = (u + _f32(zp)).astype(F32)
+    return np.clip(u, F32(lo), F32(hi)).astype(F32), u
+
+
+def adaround_qdq(x, alpha, scale, zp, lo, hi, mode, soft, temperature=None):
+    x_int, _ = adaround_to_integer(x, alpha, scale, zp, lo, hi, mode, soft, temperature)
+    return dequantize(x_int, scale, zp)
+
+
+def adaround_grad_alpha(x, alpha, g, scale, zp, lo, hi, mode, temperature=None):
+    """d / d alpha of scale * (clamp(floor(x / scale) + rest(alpha) + zp, lo, hi) - zp) for the
+    upstream gradient g (soft targets)."""
+    _, u = adaround_to_integer(x, alpha, scale, zp, lo, hi, mode, True, temperature)
+    mask = (u >= F32(lo)) & (u <= F32(hi))
+    h = np.where(mask, (_f32(g) * _f32(scale)).astype(F32), F32(0))
+    alpha = _f32(alpha)
+    if mode == 'sigmoid_temp_decay':
+        p = _sigmoid((alpha / F32(temperature)).astype(F32))
+        d = (p * (F32(1) - p) / F32(temperature)).astype(F32)
+    else:
+        p = _sigmoid(alpha)
+        d = (p * (F32(1) - p)).astype(F32)
+        if mode == 'learned_hard_sigmoid':
+            v = p * F32(ADAROUND_ZETA - ADAROUND_GAMMA) + F32(ADAROUND_GAMMA)
+            d = np.where((v >= 0) & (v <= 1), d * F32(ADAROUND_ZETA - ADAROUND_GAMMA), F32(0)).astype(F32)
+    return (h * d).astype(F32)
