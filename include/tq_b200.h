@@ -279,6 +279,42 @@ int tq_embed_ln_qdq_i8(const int64_t* ids, const int64_t* type_ids, const int64_
                        const float* beta, float eps, tq_qspec out_q, int64_t out_q_params,
                        void* out_i8, int64_t M, int32_t D, void* stream);
 
+/* ---- training-time quantizer path -----------------------------------
+ * Straight-through backward of the fake quantizer with learnable ranges: autograd of
+ * AsymmetricUniformQuantizer.forward / SymmetricUniformQuantizer.forward (quantizers.py:172-211,
+ * round_ste :12-20, scale :142-147, zero_point :149-153; make_range_trainable :284-288, 346-349)
+ * for the upstream gradient grad_y, x viewed [outer, C, inner] as in tq_qdq_axis_f32:
+ *     u = rint(x / s) + zp;  in = (int_min <= u <= int_max);  h = grad_y * s
+ *     grad_x          = in ? h / s : 0
+ *     grad_scale[c]   = sum grad_y * (clamp(u) - zp)  -  sum (in ? h : 0) * ((x / s) / s)
+ *     grad_zp[c]      = sum (in ? 0 : -h)
+ *     grad_delta[c]   = delta >= eps ? grad_scale : 0          ('log' domain: grad_scale * s)
+ *     grad_zero_float = int_min <= rint(zero_float) <= int_max ? grad_zp : 0
+ * One pass: 12 B / element (the reference's autograd graph makes ~14 passes).  Any of grad_x,
+ * grad_delta[n_params], grad_zero_float[n_params] may be NULL; grad_zero_float is ignored for a
+ * symmetric quantizer.  Sums: fp32 per thread, fp64 across threads / CTAs in a fixed order
+ * (deterministic).  ws: tq_qdq_bwd_workspace_bytes() bytes, 16-byte aligned, zeroed once. */
+size_t tq_qdq_bwd_workspace_bytes(int64_t outer, int64_t C, int64_t inner);
+int tq_qdq_bwd_f32(const float* x, const float* grad_y, float* grad_x, float* grad_delta,
+                   float* grad_zero_float, int64_t outer, int64_t C, int64_t inner, tq_qspec q,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* AdaRound soft-rounding quantizer, AdaRoundQuantizer.to_integer_forward in a relaxation mode
+ * (quantization/adaround/quantizer.py:46-92).  mode: 0 learned_sigmoid, 1 learned_hard_sigmoid
+ * (zeta 1.1, gamma -0.1), 2 sigmoid_temp_decay (needs temperature > 0).  w viewed [outer, C, inner].
+ *   init : alpha such that the soft target equals the rounding rest x/s - floor(x/s)       (:54-71)
+ *   fwd  : x_int = clamp(floor(w / s) + (soft ? h(alpha) : alpha >= 0) + zp, int_min, int_max);
+ *          y = s * (x_int - zp).  y and / or x_int may be NULL                               (:73-82)
+ *   bwd  : grad_alpha = grad_y * s * [int_min <= u <= int_max] * h'(alpha)   (soft targets) */
+int tq_adaround_init_alpha_f32(const float* w, float* alpha, int64_t outer, int64_t C, int64_t inner,
+                               tq_qspec q, int32_t mode, float temperature, void* stream);
+int tq_adaround_fwd_f32(const float* w, const float* alpha, float* y, float* x_int, int64_t outer,
+                        int64_t C, int64_t inner, tq_qspec q, int32_t mode, int32_t soft_targets,
+                        float temperature, void* stream);
+int tq_adaround_bwd_f32(const float* w, const float* alpha, const float* grad_y, float* grad_alpha,
+                        int64_t outer, int64_t C, int64_t inner, tq_qspec q, int32_t mode,
+                        float temperature, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -457,7 +457,7 @@ def _param_sum(v, C, layout):
 
 
 def qdq_backward(x, g, delta, zero_float, signed, n_bits, eps=1e-8, scale_domain='linear', axis=None,
-                 per_channel=False):
+                 per_channel=False, layout=None):
     """Autograd of AsymmetricUniformQuantizer.forward / SymmetricUniformQuantizer.forward
     (quantizers.py:142-153, 172-211) for the upstream gradient ``g``:
 
@@ -484,7 +484,12 @@ def qdq_backward(x, g, delta, zero_float, signed, n_bits, eps=1e-8, scale_domain
     else:
         zp_flat = np.zeros_like(s_flat)
         lo, hi = sym_grid(n_bits, signed)
-    if C > 1:
+    shape = x.shape
+    if layout is not None:                      # explicit [outer, C, inner] view (the C ABI's convention)
+        layout = tuple(int(v) for v in layout)
+        x, g = x.reshape(layout), g.reshape(layout)
+        s, zp = (s_flat.reshape(1, C, 1), zp_flat.reshape(1, C, 1)) if C > 1 else (s_flat.reshape(()), zp_flat.reshape(()))
+    elif C > 1:
         if axis is not None:
             layout = (int(np.prod(x.shape[:axis], dtype=np.int64)), C, int(np.prod(x.shape[axis + 1:], dtype=np.int64)))
         elif per_channel:
@@ -504,7 +509,7 @@ def qdq_backward(x, g, delta, zero_float, signed, n_bits, eps=1e-8, scale_domain
     h = (g * s).astype(F32)                       # MulBackward (:209)
     gs1 = (g * w).astype(F32)
     hm = np.where(mask, h, F32(0)).astype(F32)    # ClampBackward (:185)
-    grad_x = (hm / s).astype(F32)                 # DivBackward, self (:184)
+    grad_x = (hm / s).astype(F32).reshape(shape)  # DivBackward, self (:184)
     gs2 = (-hm * ((x / s).astype(F32) / s).astype(F32)).astype(F32)   # DivBackward, other
     grad_scale = (_param_sum(gs1, C, layout).astype(F32) + _param_sum(gs2, C, layout).astype(F32)).astype(F32)
     mag_s = _param_sum(np.abs(gs1), C, layout) + _param_sum(np.abs(gs2), C, layout)
@@ -528,7 +533,8 @@ ADAROUND_ZETA, ADAROUND_GAMMA = 1.1, -0.1          # adaround/quantizer.py:29,34
 
 def _sigmoid(a):
     a = _f32(a)
-    return (F32(1) / (F32(1) + np.exp(-a))).astype(F32)
+    with np.errstate(over='ignore'):
+        return (F32(1) / (F32(1) + np.exp(-a))).astype(F32)
 
 
 def adaround_alpha_init(x, scale, mode, temperature=None):

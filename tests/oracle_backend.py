@@ -121,3 +121,39 @@ class OracleOps:
         idx = int(np.argmin(_np(loss)))
         return (cand_xmin[idx:idx + 1].clone(), cand_xmax[idx:idx + 1].clone(),
                 torch.tensor([idx], dtype=torch.int32))
+
+    # -- training-time path ---------------------------------------------------------------------
+    def qdq_bwd(self, x, grad_y, spec, n_params, outer=1, C=1, inner=None, want_x=True, want_delta=True,
+                want_zero_float=True):
+        n = x.numel()
+        if C == 1:
+            outer, inner = 1, n
+        dom = 'log' if spec.log_domain else 'linear'
+        signed = bool(_np(spec.is_signed)) if spec.zero_float is None else None
+        gx, gd, gz, _ = O.qdq_backward(_np(x), _np(grad_y), _np(spec.delta), _np(spec.zero_float), signed, spec.n_bits,
+                                       spec.eps, dom, layout=(outer, C, inner))
+        return (torch.from_numpy(gx.copy()) if want_x else None,
+                torch.from_numpy(gd.copy()) if want_delta else None,
+                torch.from_numpy(gz.copy()) if (want_zero_float and gz is not None) else None)
+
+    def _ada_grid(self, spec, outer, C, inner):
+        scale, zp, lo, hi = spec.resolve()
+        return self._bcast(scale, outer, C, inner), self._bcast(zp, outer, C, inner), lo, hi
+
+    def adaround_init_alpha(self, w, spec, outer, C, inner, mode, temperature=None):
+        s, _, _, _ = self._ada_grid(spec, outer, C, inner)
+        a = O.adaround_alpha_init(_np(w).reshape(outer, C, inner), s, mode, temperature)
+        return torch.from_numpy(a.reshape(tuple(w.shape)).copy())
+
+    def adaround_fwd(self, w, alpha, spec, outer, C, inner, mode, soft, temperature=None, want_int=False):
+        s, z, lo, hi = self._ada_grid(spec, outer, C, inner)
+        xi, _ = O.adaround_to_integer(_np(w).reshape(outer, C, inner), _np(alpha).reshape(outer, C, inner), s, z, lo,
+                                      hi, mode, soft, temperature)
+        out = xi if want_int else O.dequantize(xi, s, z)
+        return torch.from_numpy(out.reshape(tuple(w.shape)).copy())
+
+    def adaround_bwd(self, w, alpha, grad_y, spec, outer, C, inner, mode, temperature=None):
+        s, z, lo, hi = self._ada_grid(spec, outer, C, inner)
+        ga = O.adaround_grad_alpha(_np(w).reshape(outer, C, inner), _np(alpha).reshape(outer, C, inner),
+                                   _np(grad_y).reshape(outer, C, inner), s, z, lo, hi, mode, temperature)
+        return torch.from_numpy(ga.reshape(tuple(w.shape)).copy())

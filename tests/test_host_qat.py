@@ -1,0 +1,74 @@
+"""Training-time host logic on CPU (oracle injected as the arithmetic back-end, test-only): the
+autograd wiring of the quantizers (FakeQuantSTE), learnable ranges through the manager state machine
+and the AdaRound quantizer classes reproduce the reference under torch autograd (tests/golden/qat.npz)."""
+import numpy as np
+import pytest
+import torch
+
+import tq_native
+from oracle_backend import OracleOps
+from qat_cases import QAT_MANIFEST, check_backward_case
+
+CPU = torch.device('cpu')
+
+
+@pytest.fixture(autouse=True)
+def oracle_ops(monkeypatch):
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: CPU)
+
+
+@pytest.mark.parametrize('case', QAT_MANIFEST['backward'], ids=lambda c: c['name'])
+def test_backward_api(case):
+    check_backward_case(case, CPU)
+
+
+def test_learn_ranges_state():
+    """QuantizationManager.learn_ranges -> nn.Parameters that receive gradients (reference
+    quantization_manager.py:82-84, quantizers.py:284-288)"""
+    from quantization.quantization_manager import QuantizationManager, Qstates
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators
+    rs = np.random.RandomState(0)
+    x = torch.from_numpy((rs.randn(4, 16, 32) * 2).astype(np.float32))
+    for qm, names in ((QMethods.asymmetric_uniform, {'quantizer._delta', 'quantizer._zero_float'}),
+                      (QMethods.symmetric_uniform, {'quantizer._delta'})):
+        m = QuantizationManager(qmethod=qm, init=RangeEstimators.running_minmax, qparams=dict(n_bits=4))
+        m(x)
+        m.learn_ranges()
+        assert m.state is Qstates.learn_ranges
+        assert {n for n, _ in m.named_parameters()} == names
+        d0 = m.quantizer._delta.detach().clone()
+        y = m(x * 3)                      # learn_ranges: no estimator update
+        assert torch.equal(m.quantizer._delta.detach(), d0)
+        y.square().sum().backward()
+        for _, p in m.named_parameters():
+            assert p.grad is not None and p.grad.shape == p.shape and torch.isfinite(p.grad).all()
+        assert m.quantizer._delta.grad.abs().sum() > 0
+
+
+from qat_cases import check_adaround_case  # noqa: E402
+
+
+@pytest.mark.parametrize('case', QAT_MANIFEST['adaround'], ids=lambda c: c['name'])
+def test_adaround_quantizer_api(case):
+    check_adaround_case(case, CPU)
+
+
+from qat_cases import check_adaround_layer_case  # noqa: E402
+
+
+@pytest.mark.parametrize('case', QAT_MANIFEST['adaround_layer'], ids=lambda c: c['name'])
+def test_adaround_layer_loop(case):
+    check_adaround_layer_case(case, CPU)
+
+
+def test_temp_decay_schedules():
+    """every schedule starts at b_range[0], ends at b_range[1] and is monotone"""
+    from quantization.adaround.utils import AdaRoundTempDecayType, TempDecay
+    for kind in AdaRoundTempDecayType:
+        sched = TempDecay(100, b_range=(20.0, 2.0), rel_decay_start=0.2, decay_type=kind, decay_shape=2.0)
+        vals = [sched(t) for t in range(0, 101)]
+        assert vals[0] == 20.0 and vals[10] == 20.0
+        assert abs(vals[-1] - 2.0) < 1e-9, (kind, vals[-1])
+        assert all(a >= b - 1e-12 for a, b in zip(vals, vals[1:])), kind

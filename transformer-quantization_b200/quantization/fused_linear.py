@@ -80,8 +80,19 @@ def _weight_grid(layer, weight_q):
     if k not in (1, N):
         return None
     spec = qz._spec()
-    _, w_ctr = tq_native.ops().quant_int(w, spec, 1, k, w.numel() // k if k > 1 else None,
-                                         want_f32=False, want_bf16=True)
+    relaxed = getattr(qz, '_relaxed', None)
+    if relaxed is not None and relaxed():
+        # AdaRound quantizer (learned up / down rounding): the grid comes from its own forward
+        if qz.soft_targets:
+            return None                            # soft targets are not integers
+        with torch.no_grad():
+            w_int = qz.to_integer_forward(w)
+            if not qz.symmetric:
+                w_int = w_int - qz.zero_point
+        w_ctr = w_int.to(torch.bfloat16)
+    else:
+        _, w_ctr = tq_native.ops().quant_int(w, spec, 1, k, w.numel() // k if k > 1 else None,
+                                             want_f32=False, want_bf16=True)
     layer._tq_wgrid = (weight_q, w_ctr, spec, k)
     return w_ctr, spec, k
 
@@ -90,6 +101,10 @@ def try_fused(layer, x, weight, bias):
     """Fused QuantLinear forward or None.  ``weight`` is what get_params() returned."""
     if not ENABLED or layer.training or not layer._quant_w or not x.is_cuda or x.dtype != torch.float32:
         return None
+    if torch.is_grad_enabled() and x.requires_grad:
+        return None                                # the input is part of an autograd graph: three-step path
+    # (an eval-mode forward does not build a graph for the layer's own parameters; QAT runs in train()
+    # mode, AdaRound's soft targets are excluded in _weight_grid)
     act = _act_code(layer.activation_function)
     if act is None:
         return None

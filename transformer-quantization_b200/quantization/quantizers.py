@@ -52,6 +52,38 @@ round_ste_func = RoundStraightThrough.apply
 floor_ste_func = FloorStraightThrough.apply
 
 
+class FakeQuantSTE(Function):
+    """Quantize-dequantize with the reference's autograd semantics (quantizers.py:172-211 under
+    autograd: straight-through round :12-20, clamp masks, gradients of ``_delta`` / ``_zero_float``
+    once ``make_range_trainable`` turned them into parameters, :284-288 / :346-349).
+
+    forward  -> tq_qdq_f32 / tq_qdq_axis_f32 (one pass)
+    backward -> tq_qdq_bwd_f32: grad_x and the reduced range gradients in one pass over (x, grad_y)
+    """
+
+    @staticmethod
+    def forward(ctx, x, delta, zero_float, quantizer, layout):
+        outer, C, inner = layout
+        y = tq_native.ops().qdq(x, quantizer._spec(), outer, C, inner)
+        ctx.save_for_backward(x, delta, zero_float)
+        ctx.quantizer, ctx.layout = quantizer, layout
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, delta, zero_float = ctx.saved_tensors
+        qz = ctx.quantizer
+        outer, C, inner = ctx.layout
+        ops = tq_native.ops()
+        spec = ops.spec(delta, zero_float, None if zero_float is not None else qz._signed, qz.n_bits,
+                        qz.scale_domain == 'log', qz.eps)
+        need_x, need_d, need_z = ctx.needs_input_grad[:3]
+        gx, gd, gz = ops.qdq_bwd(x, grad_y, spec, delta.numel(), outer, C, inner, want_x=need_x,
+                                 want_delta=need_d, want_zero_float=need_z and zero_float is not None)
+        return (gx, gd.view_as(delta) if gd is not None else None,
+                gz.view_as(zero_float) if gz is not None else None, None, None)
+
+
 class QuantizerNotInitializedError(Exception):
     """Raised when a quantizer has not initialized (reference quantizers.py:368-372)."""
 
@@ -209,6 +241,10 @@ class AsymmetricUniformQuantizer(QuantizerBase):
         """Quantize-dequantize ``x_float`` (reference quantizers.py:189-211)."""
         spec = self._spec()
         outer, C, inner = self._layout(x_float)
+        if torch.is_grad_enabled() and (x_float.requires_grad or self._delta.requires_grad or
+                                        (self._zero_float is not None and self._zero_float.requires_grad)):
+            # training: the output joins the autograd graph (STE + learnable ranges)
+            return FakeQuantSTE.apply(x_float, self._delta, self._zero_float, self, (outer, C, inner))
         y = tq_native.ops().qdq(x_float, spec, outer, C, inner)
         if C == 1 and self.n_bits <= 8:
             # remember which grid y lives on: a following QuantLinear feeds the integer grid to

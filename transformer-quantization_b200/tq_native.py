@@ -103,7 +103,19 @@ SIGNATURES = {
     'tq_embed_ln_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _i64, _c_f32p, _c_f32p,
                                           _c_f32p, QSpec, _i64, QSpec, _i64, _c_f32p, _c_f32p, ctypes.c_float,
                                           QSpec, _i64, ctypes.c_void_p, _i64, _i32, ctypes.c_void_p]),
+    # ---- training-time path (STE backward with learnable ranges, AdaRound)
+    'tq_qdq_bwd_workspace_bytes': (ctypes.c_size_t, [_i64, _i64, _i64]),
+    'tq_qdq_bwd_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _i64, _i64, _i64, QSpec,
+                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    'tq_adaround_init_alpha_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i64, _i64, QSpec, _i32, ctypes.c_float,
+                                                  ctypes.c_void_p]),
+    'tq_adaround_fwd_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, _i64, _i64, _i64, QSpec, _i32, _i32,
+                                           ctypes.c_float, ctypes.c_void_p]),
+    'tq_adaround_bwd_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, _i64, _i64, _i64, QSpec, _i32,
+                                           ctypes.c_float, ctypes.c_void_p]),
 }
+
+ADAROUND_MODE = {'learned_sigmoid': 0, 'learned_hard_sigmoid': 1, 'sigmoid_temp_decay': 2}
 
 
 def load_library(path=None):
@@ -210,6 +222,53 @@ class CudaOps:
         self._run('quant_int', (4 + (4 if want_f32 else 0) + (2 if want_bf16 else 0)) * n, 1, self.lib.tq_quant_int_f32,
                   x.data_ptr(), _ptr(yi), _ptr(yc), outer, C, inner, spec, _stream())
         return yi, yc
+
+    # -- training-time path -----------------------------------------------------------------------
+    def qdq_bwd(self, x, grad_y, spec, n_params, outer=1, C=1, inner=None, want_x=True, want_delta=True,
+                want_zero_float=True):
+        """tq_qdq_bwd_f32 -> (grad_x | None, grad_delta[n_params] | None, grad_zero_float[n_params] | None)"""
+        _chk_cuda(x, grad_y)
+        x, grad_y = x.contiguous(), grad_y.contiguous()
+        if x.dtype != torch.float32 or grad_y.dtype != torch.float32:
+            raise TQError(f'tq_b200: fp32 tensors only, got {x.dtype} / {grad_y.dtype}')
+        n = x.numel()
+        if C == 1:
+            outer, inner = 1, n
+        gx = torch.empty_like(x) if want_x else None
+        gd = torch.empty(n_params, dtype=torch.float32, device=x.device) if want_delta else None
+        gz = torch.empty(n_params, dtype=torch.float32, device=x.device) if want_zero_float else None
+        nb = self.lib.tq_qdq_bwd_workspace_bytes(outer, C, inner)
+        ws = self.workspace('bwd', nb, x.device)
+        self._run('qdq_bwd', (12 if want_x else 8) * n, 1, self.lib.tq_qdq_bwd_f32, x.data_ptr(), grad_y.data_ptr(),
+                  _ptr(gx), _ptr(gd), _ptr(gz), outer, C, inner, spec, ws.data_ptr(), ws.numel(), _stream())
+        return gx, gd, gz
+
+    def adaround_init_alpha(self, w, spec, outer, C, inner, mode, temperature=None):
+        _chk_cuda(w)
+        w = w.contiguous()
+        alpha = torch.empty_like(w)
+        self._run('adaround', 8 * w.numel(), 1, self.lib.tq_adaround_init_alpha_f32, w.data_ptr(), alpha.data_ptr(),
+                  outer, C, inner, spec, ADAROUND_MODE[mode], float(temperature or 0.0), _stream())
+        return alpha
+
+    def adaround_fwd(self, w, alpha, spec, outer, C, inner, mode, soft, temperature=None, want_int=False):
+        """-> y (QDQ) or x_int (want_int) of the AdaRound quantizer in a relaxation mode"""
+        _chk_cuda(w, alpha)
+        w, alpha = w.contiguous(), alpha.contiguous()
+        out = torch.empty_like(w)
+        self._run('adaround', 12 * w.numel(), 1, self.lib.tq_adaround_fwd_f32, w.data_ptr(), alpha.data_ptr(),
+                  None if want_int else out.data_ptr(), out.data_ptr() if want_int else None, outer, C, inner, spec,
+                  ADAROUND_MODE[mode], int(bool(soft)), float(temperature or 0.0), _stream())
+        return out
+
+    def adaround_bwd(self, w, alpha, grad_y, spec, outer, C, inner, mode, temperature=None):
+        _chk_cuda(w, alpha, grad_y)
+        w, alpha, grad_y = w.contiguous(), alpha.contiguous(), grad_y.contiguous()
+        ga = torch.empty_like(w)
+        self._run('adaround', 16 * w.numel(), 1, self.lib.tq_adaround_bwd_f32, w.data_ptr(), alpha.data_ptr(),
+                  grad_y.data_ptr(), ga.data_ptr(), outer, C, inner, spec, ADAROUND_MODE[mode],
+                  float(temperature or 0.0), _stream())
+        return ga
 
     # -- min / max ------------------------------------------------------------------------------
     def minmax(self, x):
