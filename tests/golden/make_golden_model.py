@@ -8,7 +8,8 @@
 Writes tests/golden/bert_tiny.npz: weights, token ids and, per configuration, the logits, the
 final hidden states and every activation quantizer's (delta, zero_float) after calibration; and
 tests/golden/roberta_tiny.npz: the same for ``models/quantized_roberta.py`` (TQ_GOLDEN_ONLY=roberta
-regenerates only that file).
+regenerates only that file); tests/golden/bert_tiny_qat.npz (TQ_GOLDEN_ONLY=qat): loss and
+gradients of one training step with learnable ranges.
 """
 import importlib.util
 import os
@@ -231,6 +232,37 @@ def run_mobilebert_config(qm, name, cfg, hf_model, batches):
             f'{name}.n_quantizers': np.array(n)}, model
 
 
+QAT_CONFIGS = ('w8a8_asym', 'w4a8_asym', 'w8a8_sym')
+
+
+def run_qat_step(model, name, batch, labels, seed=77):
+    """one quantization-aware training step on a calibrated model with learnable ranges (README
+    `train-quantized --learn-ranges`; quantizers.py:284-288): loss and gradients"""
+    model.learn_ranges()
+    model.train()
+    model.zero_grad()
+    torch.manual_seed(seed)                       # dropout masks
+    with torch.enable_grad():
+        out = model(input_ids=batch, attention_mask=torch.ones_like(batch), labels=labels, return_dict=True)
+        out.loss.backward()
+    res = {f'{name}.qat.loss': out.loss.detach().numpy().copy(),
+           f'{name}.qat.logits': out.logits.detach().numpy().copy()}
+    n_q = 0
+    for pname, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        leaf = pname.split('.')[-1]
+        if leaf in ('_delta', '_zero_float'):
+            res[f'{name}.qat.grad.{pname}'] = p.grad.numpy().reshape(-1).copy()
+            n_q += 1
+        elif pname in ('classifier.weight', 'bert.pooler.dense_act.weight', 'bert.encoder.layer.0.attention.self.query.weight',
+                       'bert.encoder.layer.1.output.dense.weight', 'bert.embeddings.LayerNorm.weight',
+                       'bert.embeddings.position_embeddings.weight'):
+            res[f'{name}.qat.grad.{pname}'] = p.grad.numpy().copy()
+    res[f'{name}.qat.n_range_params'] = np.array(n_q)
+    return res
+
+
 def make_hf_mobilebert():
     import hf41_shim
     return hf41_shim.make_tiny_mobilebert()
@@ -261,12 +293,25 @@ def make_batches(n=3, B=4, T=32, vocab=1000):
     return [torch.randint(0, vocab, (B, T), generator=g) for _ in range(n)]
 
 
+def qat_labels(B=4):
+    return torch.tensor([0, 1, 1, 0][:B])
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_grad_enabled(False)
     qb = import_reference_model(REF)
     hf = make_hf_model()
     batches = make_batches()
+    if os.environ.get('TQ_GOLDEN_ONLY', '') == 'qat':
+        outq = {}
+        for name in QAT_CONFIGS:
+            _, model = run_config(qb, name, CONFIGS[name], hf, batches)
+            outq.update(run_qat_step(model, name, batches[-1], qat_labels()))
+            print(name, 'qat loss', float(outq[f'{name}.qat.loss']), 'range params', int(outq[f'{name}.qat.n_range_params']))
+        np.savez_compressed(os.path.join(HERE, 'bert_tiny_qat.npz'), **outq)
+        print('bert_tiny_qat.npz', os.path.getsize(os.path.join(HERE, 'bert_tiny_qat.npz')))
+        sys.exit(0)
     out = {'ids': np.stack([b.numpy() for b in batches])}
     for k, v in hf.state_dict().items():
         out['w.' + k] = v.numpy().copy()

@@ -213,3 +213,50 @@ def check_adaround_layer_case(case, device):
     got = np.array([res.loss_soft_before, res.loss_hard_before, res.loss_soft_after, res.loss_hard_after])
     np.testing.assert_allclose(got, g[f'{nm}.losses'], rtol=2e-2, atol=1e-6)
     assert layer.caching and not qz.soft_targets
+
+
+def check_training_step(device):
+    """A QuantLinear in training mode (weights through FakeQuantSTE, learnable ranges) against the same
+    computation written with torch ops (the reference's formulation) on `device`."""
+    import torch
+    from quantization.autoquant_utils import QuantLinear
+    from quantization.quantizers import QMethods
+    torch.manual_seed(0)
+    lin = QuantLinear(256, 192, method=QMethods.symmetric_uniform, act_method=QMethods.asymmetric_uniform, n_bits=4,
+                      n_bits_act=8).to(device)
+    x = torch.randn(8, 32, 256, device=device)
+    coef = torch.linspace(-1, 1, 192, device=device)
+    lin.quantized()
+    lin.eval()
+    with torch.no_grad():
+        lin(x)
+    lin.learn_ranges()
+    lin.train()
+    y = lin(x)
+    (y * coef).sum().backward()
+    wq, aq = lin.weight_quantizer.quantizer, lin.activation_quantizer.quantizer
+    assert isinstance(wq._delta, torch.nn.Parameter) and isinstance(aq._zero_float, torch.nn.Parameter)
+    # the reference's formulation in torch ops
+    w = lin.weight.detach().clone().requires_grad_(True)
+    dw = wq._delta.detach().clone().requires_grad_(True)
+    da = aq._delta.detach().clone().requires_grad_(True)
+    za = aq._zero_float.detach().clone().requires_grad_(True)
+
+    def ste(v):
+        return v + (torch.round(v) - v).detach()
+    sw = torch.clamp(dw, min=1e-8)
+    lo, hi = (-8.0, 7.0) if wq.signed else (0.0, 15.0)
+    wqq = sw * torch.clamp(ste(w / sw), lo, hi)
+    out = torch.nn.functional.linear(x, wqq, lin.bias.detach())
+    sa = torch.clamp(da, min=1e-8)
+    zp = torch.clamp(ste(za), 0, 255)
+    yq = sa * (torch.clamp(ste(out / sa) + zp, 0, 255) - zp)
+    (yq * coef).sum().backward()
+    step = float(sa.detach())
+    assert (y - yq).abs().max().item() <= step * 1.01          # GEMM summation order: at most one step
+    assert (y != yq).float().mean().item() < 5e-3
+    for got, want, name in ((lin.weight.grad, w.grad, 'weight'), (wq._delta.grad, dw.grad, 'w delta'),
+                            (aq._delta.grad, da.grad, 'a delta'), (aq._zero_float.grad, za.grad, 'a zero_float')):
+        err = (got - want.view_as(got)).abs().max().item()
+        ref = want.abs().max().item()
+        assert err <= 2e-2 * ref + 1e-6, f'{name}: {err} vs {ref}'

@@ -16,7 +16,8 @@ import torch
 
 import tq_native
 from oracle import fakequant_oracle as O
-from qat_cases import QAT_MANIFEST, check_adaround_case, check_backward_case, close_sum
+from qat_cases import (QAT_MANIFEST, check_adaround_case, check_adaround_layer_case, check_backward_case,
+                       check_training_step, close_sum)
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -78,7 +79,7 @@ def _check_vs_oracle(ops, shape, layout, n_bits, asym, signed=True, misalign=0, 
     if asym:
         close_sum(gz.cpu().numpy(), egz, mag_z, 'grad_zero_float')
     else:
-        assert gz is None or True
+        assert gz is None
 
 
 @pytest.mark.parametrize('n_bits', [8, 4])
@@ -151,13 +152,10 @@ def test_bwd_properties_full_size(ops, layout):
     # grad_x is grad_y (up to one rounding of g * s / s) inside the range and exactly 0 outside
     d = torch.tensor(delta, device=DEV)
     z = torch.tensor(zf, device=DEV)
-    spec = ops.spec(d, z, None, 8, False, 1e-8)
-    xi, _ = ops.quant_int(x.view(outer, C, inner), spec, outer, C, inner, want_f32=True)
     scale = d.clamp(min=1e-8).view(1, C, 1)
     zp = z.round().clamp(0, 255).view(1, C, 1)
     u = torch.round(x.view(outer, C, inner) / scale) + zp
     inside = ((u >= 0) & (u <= 255)).view(-1)
-    assert torch.equal(inside, ((xi.view(-1) > 0) & (xi.view(-1) < 255)) | (inside & ((xi.view(-1) == 0) | (xi.view(-1) == 255))))
     gx = a[0].view(-1)
     assert (gx[~inside] == 0).all()
     assert torch.allclose(gx[inside], g[inside], rtol=3e-7, atol=0)
@@ -186,45 +184,9 @@ def test_bwd_empty_and_errors(ops):
 
 
 def test_qat_training_step_matches_torch_autograd():
-    """A QuantLinear in training mode (weights through FakeQuantSTE, learnable ranges) against the same
-    computation written with torch ops (the reference's formulation) on the GPU."""
-    from quantization.autoquant_utils import QuantLinear
-    from quantization.quantizers import QMethods
-    torch.manual_seed(0)
-    lin = QuantLinear(256, 192, method=QMethods.symmetric_uniform, act_method=QMethods.asymmetric_uniform, n_bits=4,
-                      n_bits_act=8).to(DEV)
-    x = torch.randn(8, 32, 256, device=DEV)
-    lin.quantized()
-    lin.eval()
-    with torch.no_grad():
-        lin(x)
-    lin.learn_ranges()
-    lin.train()
-    y = lin(x)
-    loss = (y * torch.linspace(-1, 1, 192, device=DEV)).sum()
-    loss.backward()
-    wq, aq = lin.weight_quantizer.quantizer, lin.activation_quantizer.quantizer
-    # torch formulation
-    w = lin.weight.detach().clone().requires_grad_(True)
-    dw = wq._delta.detach().clone().requires_grad_(True)
-    da = aq._delta.detach().clone().requires_grad_(True)
-    za = aq._zero_float.detach().clone().requires_grad_(True)
+    check_training_step(DEV)
 
-    def ste(v):
-        return v + (torch.round(v) - v).detach()
-    sw = torch.clamp(dw, min=1e-8)
-    lo, hi = (-8.0, 7.0) if wq.signed else (0.0, 15.0)
-    wqq = sw * torch.clamp(ste(w / sw), lo, hi)
-    out = torch.nn.functional.linear(x, wqq, lin.bias)
-    sa = torch.clamp(da, min=1e-8)
-    zp = torch.clamp(ste(za), 0, 255)
-    yq = sa * (torch.clamp(ste(out / sa) + zp, 0, 255) - zp)
-    (yq * torch.linspace(-1, 1, 192, device=DEV)).sum().backward()
-    assert torch.allclose(y, yq, rtol=0, atol=float(sa) * 1.01)          # GEMM order: at most one step
-    frac = (y != yq).float().mean().item()
-    assert frac < 5e-3
-    for got, want, name in ((lin.weight.grad, w.grad, 'weight'), (wq._delta.grad, dw.grad, 'w delta'),
-                            (aq._delta.grad, da.grad, 'a delta'), (aq._zero_float.grad, za.grad, 'a zero_float')):
-        err = (got - want.view_as(got)).abs().max().item()
-        ref = want.abs().max().item()
-        assert err <= 2e-2 * ref + 1e-6, f'{name}: {err} vs {ref}'
+
+@pytest.mark.parametrize('case', QAT_MANIFEST['adaround_layer'], ids=lambda c: c['name'])
+def test_adaround_layer_loop(case):
+    check_adaround_layer_case(case, DEV)

@@ -72,3 +72,8 @@ def test_temp_decay_schedules():
         assert vals[0] == 20.0 and vals[10] == 20.0
         assert abs(vals[-1] - 2.0) < 1e-9, (kind, vals[-1])
         assert all(a >= b - 1e-12 for a, b in zip(vals, vals[1:])), kind
+
+
+def test_training_step_matches_torch_autograd():
+    from qat_cases import check_training_step
+    check_training_step(CPU)

@@ -104,3 +104,37 @@ def test_reference_mobilebert_model_file_runs_unchanged_on_this_package(drop_in,
     assert int(res[f'{name}.n_quantizers']) == int(G[f'{name}.n_quantizers'])
     assert np.array_equal(res[f'{name}.logits'], G[f'{name}.logits'])
     assert np.array_equal(res[f'{name}.last_hidden'], G[f'{name}.last_hidden'])
+
+
+@pytest.mark.parametrize('name', ['w8a8_asym', 'w4a8_asym', 'w8a8_sym'])
+def test_reference_model_qat_step_on_this_package(drop_in, name):
+    """One quantization-aware training step with learnable ranges: the unchanged
+    reference model file on this package's quantizers (FakeQuantSTE -> tq_qdq_bwd semantics, oracle back-end
+    here) vs the reference's autograd.  Forward, loss and weight gradients are the same fp32 chain ->
+    equal; range gradients are sums in a different order -> rtol 1e-3 relative to the largest one."""
+    gm, qb = drop_in
+    G = np.load(os.path.join(GOLDEN, 'bert_tiny_qat.npz'))
+    batches = gm.make_batches()
+    torch.set_grad_enabled(False)
+    try:
+        _, model = gm.run_config(qb, name, gm.CONFIGS[name], gm.make_hf_model(), batches)
+        res = gm.run_qat_step(model, name, batches[-1], gm.qat_labels())
+    finally:
+        torch.set_grad_enabled(True)
+    assert int(res[f'{name}.qat.n_range_params']) == int(G[f'{name}.qat.n_range_params'])
+    assert np.array_equal(res[f'{name}.qat.logits'], G[f'{name}.qat.logits'])
+    assert float(res[f'{name}.qat.loss']) == float(G[f'{name}.qat.loss'])
+    keys = [k for k in G.files if k.startswith(f'{name}.qat.grad.')]
+    assert keys and set(keys) == {k for k in res if k.startswith(f'{name}.qat.grad.')}
+    rng = [k for k in keys if k.split('.')[-1] in ('_delta', '_zero_float')]
+    for k in keys:
+        if k in rng:
+            continue
+        np.testing.assert_allclose(res[k], G[k], rtol=1e-4, atol=1e-6 * np.abs(G[k]).max(), err_msg=k)
+    for leaf in ('_delta', '_zero_float'):
+        sel = [k for k in rng if k.endswith(leaf)]
+        if not sel:
+            continue
+        top = max(np.abs(G[k]).max() for k in sel)
+        for k in sel:
+            assert np.abs(res[k] - G[k]).max() <= 1e-3 * top + 1e-3 * np.abs(G[k]).max(), k

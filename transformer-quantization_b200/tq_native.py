@@ -236,6 +236,7 @@ class CudaOps:
             outer, inner = 1, n
         gx = torch.empty_like(x) if want_x else None
         gd = torch.empty(n_params, dtype=torch.float32, device=x.device) if want_delta else None
+        want_zero_float = want_zero_float and bool(spec.zero_float)      # symmetric quantizer: no zero point
         gz = torch.empty(n_params, dtype=torch.float32, device=x.device) if want_zero_float else None
         nb = self.lib.tq_qdq_bwd_workspace_bytes(outer, C, inner)
         ws = self.workspace('bwd', nb, x.device)
