@@ -293,7 +293,8 @@ int tq_embed_ln_qdq_i8(const int64_t* ids, const int64_t* type_ids, const int64_
  * One pass: 12 B / element (the reference's autograd graph makes ~14 passes).  Any of grad_x,
  * grad_delta[n_params], grad_zero_float[n_params] may be NULL; grad_zero_float is ignored for a
  * symmetric quantizer.  Sums: fp32 per thread, fp64 across threads / CTAs in a fixed order
- * (deterministic).  ws: tq_qdq_bwd_workspace_bytes() bytes, 16-byte aligned, zeroed once. */
+ * (deterministic).  ws: tq_qdq_bwd_workspace_bytes() bytes, 16-byte aligned, zeroed once; one buffer
+ * (sized for the largest call) may serve all calls of a stream. */
 size_t tq_qdq_bwd_workspace_bytes(int64_t outer, int64_t C, int64_t inner);
 int tq_qdq_bwd_f32(const float* x, const float* grad_y, float* grad_x, float* grad_delta,
                    float* grad_zero_float, int64_t outer, int64_t C, int64_t inner, tq_qspec q,

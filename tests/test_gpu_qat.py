@@ -102,7 +102,7 @@ def test_bwd_cols_vs_oracle(ops, rows, C, asym):
 
 
 @pytest.mark.parametrize('outer,C,inner', [(1, 768, 3072), (1, 48, 64), (1, 5, 21), (3, 6, 20), (2, 6, 5), (1, 3072, 768),
-                                           (40, 30, 1), (1, 2, 4)])
+                                           (40, 30, 1), (1, 2, 4), (1, 3000, 772), (1, 297, 8), (1, 5000, 4)])
 @pytest.mark.parametrize('asym', [True, False])
 def test_bwd_rows_vs_oracle(ops, outer, C, inner, asym):
     """per-channel weights [C, inner] and generic [outer, C, inner] views"""
@@ -164,6 +164,17 @@ def test_bwd_properties_full_size(ops, layout):
     assert only_x[1] is None and only_x[2] is None and torch.equal(only_x[0], a[0])
     only_p = _run(ops, x, g, delta, zf, None, 8, layout, want_x=False)
     assert only_p[0] is None and torch.equal(only_p[1], a[1]) and torch.equal(only_p[2], a[2])
+
+
+def test_bwd_workspace_shared_between_variants(ops):
+    """one caller workspace serves every variant on a stream: the per-tensor kernel's partial sums must not
+    be mistaken for the column kernel's tickets (and vice versa), in any call order"""
+    for _ in range(2):
+        _check_vs_oracle(ops, (200003,), (1, 1, 200003), 8, True, seed=21)
+        _check_vs_oracle(ops, (64, 3072), (64, 3072, 1), 8, True, seed=22)
+        _check_vs_oracle(ops, (4096, 768), (4096, 768, 1), 8, False, seed=23)
+        _check_vs_oracle(ops, (1, 400, 64), (1, 400, 64), 4, True, seed=24)       # warp-per-row kernel
+        _check_vs_oracle(ops, (32 * 128 * 768,), (1, 1, 32 * 128 * 768), 8, True, seed=25)
 
 
 def test_bwd_empty_and_errors(ops):

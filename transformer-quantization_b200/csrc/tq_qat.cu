@@ -81,8 +81,14 @@ __device__ __forceinline__ bool last_cta(uint32_t* ticket, uint32_t total) {
     return is_last;
 }
 
-// workspace: bytes 0..15 header (word 0 = ticket), then double partials
-__host__ __device__ inline double* bwd_partials(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16); }
+// Workspace layout shared by all variants (the same caller buffer serves every call on a stream, so the
+// ticket words must never be used as partial-sum storage): bytes 0..1023 = 256 ticket words, zero when idle
+// (word 0: per-tensor kernel; word 4 + b: column block b of the column kernel), partial sums from byte 1024.
+constexpr size_t kBwdHeader = 1024;
+constexpr int64_t kBwdMaxColBlocks = 252;
+__host__ __device__ inline double* bwd_partials(void* ws) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kBwdHeader);
+}
 
 // ---- per-tensor ------------------------------------------------------------------------------------
 template <bool FAST>
@@ -175,34 +181,39 @@ qdq_bwd_tensor_kernel(const float* __restrict__ x, const float* __restrict__ g, 
 
 // ---- per-embedding / per-embedding-group: x viewed [rows, C]; CTA = 64 vector columns x 4 row lanes ---
 template <bool FAST>
+__device__ __forceinline__ void bwd_vec4(const float4& a, const float4& b, float4& o, const QP (&p)[4], float (&ds)[4],
+                                         float (&dz)[4]) {
+    bwd_elem<FAST>(a.x, b.x, p[0], o.x, ds[0], dz[0]);
+    bwd_elem<FAST>(a.y, b.y, p[1], o.y, ds[1], dz[1]);
+    bwd_elem<FAST>(a.z, b.z, p[2], o.z, ds[2], dz[2]);
+    bwd_elem<FAST>(a.w, b.w, p[3], o.w, ds[3], dz[3]);
+}
+
+constexpr int kColsInFlight = 4;      // rows in flight per thread: 8 x 128-bit loads (2 CTAs/SM -> 64 KB per SM)
+
+template <bool FAST>
 __device__ __forceinline__ void bwd_cols_body(const float4* __restrict__ xv, const float4* __restrict__ gv,
                                               float4* __restrict__ gxv, int64_t r0, int64_t r1, int32_t CV, int32_t vc,
                                               const QP (&p)[4], float (&ds)[4], float (&dz)[4]) {
     int64_t r = r0 + threadIdx.y;
-    for (; r + 4 < r1; r += 8) {                                 // two rows in flight per thread
-        const float4 a0 = ld_stream(xv + r * CV + vc), b0 = ld_stream(gv + r * CV + vc);
-        const float4 a1 = ld_stream(xv + (r + 4) * CV + vc), b1 = ld_stream(gv + (r + 4) * CV + vc);
-        float4 o0, o1;
-        bwd_elem<FAST>(a0.x, b0.x, p[0], o0.x, ds[0], dz[0]);
-        bwd_elem<FAST>(a0.y, b0.y, p[1], o0.y, ds[1], dz[1]);
-        bwd_elem<FAST>(a0.z, b0.z, p[2], o0.z, ds[2], dz[2]);
-        bwd_elem<FAST>(a0.w, b0.w, p[3], o0.w, ds[3], dz[3]);
-        bwd_elem<FAST>(a1.x, b1.x, p[0], o1.x, ds[0], dz[0]);
-        bwd_elem<FAST>(a1.y, b1.y, p[1], o1.y, ds[1], dz[1]);
-        bwd_elem<FAST>(a1.z, b1.z, p[2], o1.z, ds[2], dz[2]);
-        bwd_elem<FAST>(a1.w, b1.w, p[3], o1.w, ds[3], dz[3]);
-        if (gxv != nullptr) {
-            st_stream(gxv + r * CV + vc, o0);
-            st_stream(gxv + (r + 4) * CV + vc, o1);
+    for (; r + 4 * (kColsInFlight - 1) < r1; r += 4 * kColsInFlight) {
+        float4 a[kColsInFlight], b[kColsInFlight];
+#pragma unroll
+        for (int u = 0; u < kColsInFlight; ++u) {
+            a[u] = ld_stream(xv + (r + 4 * u) * CV + vc);
+            b[u] = ld_stream(gv + (r + 4 * u) * CV + vc);
+        }
+#pragma unroll
+        for (int u = 0; u < kColsInFlight; ++u) {
+            float4 o;
+            bwd_vec4<FAST>(a[u], b[u], o, p, ds, dz);
+            if (gxv != nullptr) st_stream(gxv + (r + 4 * u) * CV + vc, o);
         }
     }
     for (; r < r1; r += 4) {
         const float4 a0 = ld_stream(xv + r * CV + vc), b0 = ld_stream(gv + r * CV + vc);
         float4 o0;
-        bwd_elem<FAST>(a0.x, b0.x, p[0], o0.x, ds[0], dz[0]);
-        bwd_elem<FAST>(a0.y, b0.y, p[1], o0.y, ds[1], dz[1]);
-        bwd_elem<FAST>(a0.z, b0.z, p[2], o0.z, ds[2], dz[2]);
-        bwd_elem<FAST>(a0.w, b0.w, p[3], o0.w, ds[3], dz[3]);
+        bwd_vec4<FAST>(a0, b0, o0, p, ds, dz);
         if (gxv != nullptr) st_stream(gxv + r * CV + vc, o0);
     }
 }
@@ -242,7 +253,8 @@ qdq_bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ g, fl
         sdz[threadIdx.y][threadIdx.x][j] = dz[j];
     }
     __syncthreads();
-    double* part = bwd_partials(ws);                  // [slabs][C][2]
+    // partial sums of this CTA: [slab][C] pairs {d scale, d zero_point}
+    double2* part = reinterpret_cast<double2*>(bwd_partials(ws));
     if (threadIdx.y == 0 && active) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -252,23 +264,43 @@ qdq_bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ g, fl
                 a += (double)sds[y][threadIdx.x][j];
                 b += (double)sdz[y][threadIdx.x][j];
             }
-            const int64_t c = (int64_t)vc * 4 + j;
-            part[((int64_t)blockIdx.y * C + c) * 2] = a;
-            part[((int64_t)blockIdx.y * C + c) * 2 + 1] = b;
+            part[(int64_t)blockIdx.y * C + (int64_t)vc * 4 + j] = make_double2(a, b);
         }
     }
-    if (!last_cta(reinterpret_cast<uint32_t*>(ws), gridDim.x * gridDim.y)) return;
-    const int tid = threadIdx.y * 64 + threadIdx.x;
-    for (int64_t c = tid; c < C; c += 256) {
-        double a = 0.0, b = 0.0;
-        for (unsigned s = 0; s < gridDim.y; ++s) {
-            a += __ldcg(part + ((int64_t)s * C + c) * 2);
-            b += __ldcg(part + ((int64_t)s * C + c) * 2 + 1);
+    // the last CTA of this COLUMN BLOCK (one ticket per block of 256 columns) sums the slabs of its columns:
+    // the four row lanes take every fourth slab (independent 16-byte loads), then a fixed-order combine
+    if (!last_cta(reinterpret_cast<uint32_t*>(ws) + 4 + blockIdx.x, gridDim.y)) return;
+    __shared__ double2 fin[4][64][4];
+    if (active) {
+        double2 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = make_double2(0.0, 0.0);
+        for (unsigned sl = threadIdx.y; sl < gridDim.y; sl += 4) {
+            const double2* row = part + (int64_t)sl * C + (int64_t)vc * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 v = __ldcg(row + j);
+                acc[j].x += v.x;
+                acc[j].y += v.y;
+            }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fin[threadIdx.y][threadIdx.x][j] = acc[j];
+    }
+    __syncthreads();
+    if (active) {                                   // thread (x, y) finishes column 4 * vc + y
+        const int j = threadIdx.y;
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            a += fin[y][threadIdx.x][j].x;
+            b += fin[y][threadIdx.x][j].y;
+        }
+        const int64_t c = (int64_t)vc * 4 + j;
         if (grad_delta != nullptr) grad_delta[c] = delta_grad(q, c, (float)a);
         if (grad_zf != nullptr && q.zero_float != nullptr) grad_zf[c] = zf_grad(q, c, (float)b, lo, hi);
     }
-    if (tid == 0) *reinterpret_cast<uint32_t*>(ws) = 0u;
+    if (threadIdx.x == 0 && threadIdx.y == 0) reinterpret_cast<uint32_t*>(ws)[4 + blockIdx.x] = 0u;
 }
 
 // ---- general [outer, C, inner] (per-channel weights, odd shapes): one CTA per channel ---------------
@@ -323,9 +355,67 @@ qdq_bwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ g, fl
     }
 }
 
+// ---- per-channel weights [C, inner] with many channels: one WARP per channel row -------------------------
+// A BERT weight row is 768 - 3072 floats: a CTA per row leaves most threads idle and pays two block
+// reductions per 3 - 12 KB.  Here a warp streams its row with 4 x 2 independent 128-bit loads per lane and
+// reduces with shuffles only.
+template <bool FAST>
+__device__ __forceinline__ void bwd_row_warp(const float4* __restrict__ xv, const float4* __restrict__ gv,
+                                             float4* __restrict__ gxv, int iv, int lane, const QP& p, float& ds,
+                                             float& dz) {
+    for (int j0 = lane; j0 < iv; j0 += 32 * kBUnroll) {
+        float4 a[kBUnroll], b[kBUnroll];
+#pragma unroll
+        for (int u = 0; u < kBUnroll; ++u) {
+            const int j = j0 + 32 * u;
+            if (j < iv) {
+                a[u] = ld_stream(xv + j);
+                b[u] = ld_stream(gv + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBUnroll; ++u) {
+            const int j = j0 + 32 * u;
+            if (j < iv) {
+                float4 o;
+                bwd_elem<FAST>(a[u].x, b[u].x, p, o.x, ds, dz);
+                bwd_elem<FAST>(a[u].y, b[u].y, p, o.y, ds, dz);
+                bwd_elem<FAST>(a[u].z, b[u].z, p, o.z, ds, dz);
+                bwd_elem<FAST>(a[u].w, b[u].w, p, o.w, ds, dz);
+                if (gxv != nullptr) st_stream(gxv + j, o);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBThreads, 2)
+qdq_bwd_rowwarp_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gx, int64_t C,
+                       int64_t inner, tq_qspec q, float* __restrict__ grad_delta, float* __restrict__ grad_zf) {
+    float lo, hi;
+    grid_of(q, lo, hi);
+    const int lane = threadIdx.x & 31;
+    const int iv = (int)(inner >> 2);                 // inner <= 65536 (host dispatch)
+    const int64_t warps = (int64_t)gridDim.x * (kBThreads / 32);
+    for (int64_t c = (int64_t)blockIdx.x * (kBThreads / 32) + (threadIdx.x >> 5); c < C; c += warps) {
+        const QP p = resolve(q, c, lo, hi);
+        const float4* xv = reinterpret_cast<const float4*>(x + c * inner);
+        const float4* gv = reinterpret_cast<const float4*>(g + c * inner);
+        float4* gxv = gx != nullptr ? reinterpret_cast<float4*>(gx + c * inner) : nullptr;
+        float ds = 0.0f, dz = 0.0f;
+        if (p.exact) bwd_row_warp<false>(xv, gv, gxv, iv, lane, p, ds, dz);      // warp-uniform
+        else bwd_row_warp<true>(xv, gv, gxv, iv, lane, p, ds, dz);
+        const double a = warp_sum((double)ds), b = warp_sum((double)dz);
+        if (lane == 0) {
+            if (grad_delta != nullptr) grad_delta[c] = delta_grad(q, c, (float)a);
+            if (grad_zf != nullptr && q.zero_float != nullptr) grad_zf[c] = zf_grad(q, c, (float)b, lo, hi);
+        }
+    }
+}
+
 static int64_t bwd_cols_slabs(int64_t rows, int64_t C) {
+    // one wave: column blocks x slabs <= 2 resident CTAs per SM (a 297th CTA would run alone in a second wave)
     const int64_t col_blocks = ((C >> 2) + 63) / 64;
-    int64_t slabs = ((int64_t)sm_count() * 2 + col_blocks - 1) / col_blocks;      // ~2 CTAs per SM
+    int64_t slabs = ((int64_t)sm_count() * 2) / col_blocks;
     const int64_t max_slabs = (rows + 7) / 8;                                     // >= 8 rows per slab
     if (slabs > max_slabs) slabs = max_slabs;
     return slabs < 1 ? 1 : slabs;
@@ -430,9 +520,10 @@ extern "C" {
 
 size_t tq_qdq_bwd_workspace_bytes(int64_t outer, int64_t C, int64_t inner) {
     if (outer < 0 || C < 1 || inner < 0) return 0;
-    if (C == 1) return 16 + (size_t)tq::sm_count() * 3 * 2 * sizeof(double);
-    if (inner == 1 && (C & 3) == 0) return 16 + (size_t)tq::bwd_cols_slabs(outer, C) * (size_t)C * 2 * sizeof(double);
-    return 16;
+    if (C == 1) return tq::kBwdHeader + (size_t)tq::sm_count() * 3 * 2 * sizeof(double);
+    if (inner == 1 && (C & 3) == 0 && ((C >> 2) + 63) / 64 <= tq::kBwdMaxColBlocks)
+        return tq::kBwdHeader + (size_t)tq::bwd_cols_slabs(outer, C) * (size_t)C * 2 * sizeof(double);
+    return tq::kBwdHeader;
 }
 
 int tq_qdq_bwd_f32(const float* x, const float* grad_y, float* grad_x, float* grad_delta, float* grad_zero_float,
@@ -455,7 +546,7 @@ int tq_qdq_bwd_f32(const float* x, const float* grad_y, float* grad_x, float* gr
             x, grad_y, grad_x, n, al ? 1 : 0, q, grad_delta, grad_zero_float, ws);
         return tq::launch_status();
     }
-    if (inner == 1 && (C & 3) == 0 && al) {
+    if (inner == 1 && (C & 3) == 0 && al && ((C >> 2) + 63) / 64 <= tq::kBwdMaxColBlocks) {
         const int64_t slabs = tq::bwd_cols_slabs(outer, C);
         const int64_t rps = (outer + slabs - 1) / slabs;
         const dim3 grid((unsigned)(((C >> 2) + 63) / 64), (unsigned)((outer + rps - 1) / rps));
@@ -465,6 +556,12 @@ int tq_qdq_bwd_f32(const float* x, const float* grad_y, float* grad_x, float* gr
     }
     const int vec_ok = (al && (inner & 3) == 0) ? 1 : 0;
     const int64_t cap = (int64_t)tq::sm_count() * 8;
+    if (outer == 1 && vec_ok && C >= (int64_t)tq::sm_count() * 2 && inner <= 65536) {
+        const int64_t blocks = (C + 7) / 8, resident = (int64_t)tq::sm_count() * 2;      // persistent: one wave
+        tq::qdq_bwd_rowwarp_kernel<<<(int)(blocks < resident ? blocks : resident), tq::kBThreads, 0, st>>>(
+            x, grad_y, grad_x, C, inner, q, grad_delta, grad_zero_float);
+        return tq::launch_status();
+    }
     tq::qdq_bwd_rows_kernel<<<(int)(C < cap ? C : cap), tq::kBThreads, 0, st>>>(x, grad_y, grad_x, outer, C, inner,
                                                                                vec_ok, q, grad_delta, grad_zero_float);
     return tq::launch_status();
