@@ -22,6 +22,8 @@ def sigmoid(x):
 
 
 class BaseOption(Flag):
+    """Flag enum printed by member name, with the list_names() helper the option parsers use"""
+
     def __str__(self):
         return self.name
 
@@ -31,29 +33,21 @@ class BaseOption(Flag):
 
     @classmethod
     def list_names(cls):
-        return [m.name for m in cls]
+        return [member.name for member in cls]
 
 
-class AdaRoundActQuantMode(BaseOption):
-    no_act_quant = auto()       # activations stay FP32
-    post_adaround = auto()      # AdaRound on FP32 activations, activations quantized afterwards (default)
-
-
-class AdaRoundInitMode(BaseOption):
-    """How the weight grid is initialised before rounding is learned."""
-    range_estimator = auto()
-    mse = auto()
-    mse_out = auto()
-    mse_out_asym = auto()
-
-
-class AdaRoundLossType(BaseOption):
-    relaxation = auto()
-    temp_decay = auto()
+# activation handling while rounding is learned: none at all | FP32 during AdaRound, quantized afterwards
+AdaRoundActQuantMode = BaseOption('AdaRoundActQuantMode', 'no_act_quant post_adaround')
+# where the weight grid comes from: the layer's range estimator | MSE on the weights | MSE on the layer
+# output (with FP32 or quantized preceding layers)
+AdaRoundInitMode = BaseOption('AdaRoundInitMode', 'range_estimator mse mse_out mse_out_asym')
+# regulariser pushing h(alpha) to {0, 1} | annealed sigmoid temperature
+AdaRoundLossType = BaseOption('AdaRoundLossType', 'relaxation temp_decay')
+AdaRoundTempDecayType = BaseOption('AdaRoundTempDecayType', 'linear cosine sigmoid power exp log')
 
 
 class AdaRoundMode(BaseOption):
-    nearest = auto()
+    nearest = auto()                    # plain round-to-nearest (no learned rounding)
     learned_sigmoid = auto()
     learned_hard_sigmoid = auto()
     sigmoid_temp_decay = auto()
@@ -61,29 +55,32 @@ class AdaRoundMode(BaseOption):
 
     @classmethod
     def list_names(cls):
-        skip = (AdaRoundMode.nearest, AdaRoundMode.RELAXATION)
-        return [m.name for m in cls if m not in skip]
+        return [m.name for m in cls if m not in (cls.nearest, cls.RELAXATION)]
 
 
-MODE_TO_LOSS_TYPE = {
-    AdaRoundMode.learned_hard_sigmoid: AdaRoundLossType.relaxation,
-    AdaRoundMode.learned_sigmoid: AdaRoundLossType.relaxation,
-    AdaRoundMode.sigmoid_temp_decay: AdaRoundLossType.temp_decay,
+MODE_TO_LOSS_TYPE = {AdaRoundMode.sigmoid_temp_decay: AdaRoundLossType.temp_decay}
+MODE_TO_LOSS_TYPE.update({m: AdaRoundLossType.relaxation
+                          for m in (AdaRoundMode.learned_sigmoid, AdaRoundMode.learned_hard_sigmoid)})
+
+
+def _sigmoid_progress(u, k):
+    off = sigmoid(-k / 2)
+    return (sigmoid(k * (u - 0.5)) - off) / (1 - 2 * off)
+
+
+# progress p(u, shape) in [0, 1] for relative time u in [0, 1]: b(t) = b0 + (b1 - b0) * p
+_PROGRESS = {
+    'linear': lambda u, k: min(1.0, u),
+    'cosine': lambda u, k: 0.5 * (1 - math.cos(u * math.pi)),
+    'sigmoid': _sigmoid_progress,
+    'power': lambda u, k: u ** k,
+    'exp': lambda u, k: (1.0 - math.exp(-k * u)) / (1.0 - math.exp(-k)),
 }
 
 
-class AdaRoundTempDecayType(BaseOption):
-    linear = auto()
-    cosine = auto()
-    sigmoid = auto()
-    power = auto()
-    exp = auto()
-    log = auto()
-
-
 class TempDecay:
-    """Annealing schedule b(t) from ``b_range[0]`` to ``b_range[1]`` over ``t_max`` iterations, constant
-    before ``rel_decay_start * t_max`` (reference adaround/utils.py:93-133)."""
+    """Annealing schedule b(t): ``b_range[0]`` until ``rel_decay_start * t_max``, then down to ``b_range[1]``
+    at ``t_max`` along the chosen curve (same curves as the reference, adaround/utils.py:93-133)."""
 
     def __init__(self, t_max, b_range=(20.0, 2.0), rel_decay_start=0.0,
                  decay_type=AdaRoundTempDecayType.linear, decay_shape=1.0):
@@ -93,27 +90,17 @@ class TempDecay:
         self.decay_start = rel_decay_start * t_max
 
     def __call__(self, t):
-        if t < self.decay_start:
-            return self.start_b
         b0, b1, k = self.start_b, self.end_b, self.decay_shape
-        u = (t - self.decay_start) / (self.t_max - self.decay_start)       # relative progress in [0, 1]
-        kind = self.decay_type
-        T = AdaRoundTempDecayType
-        if kind == T.linear:
-            return b1 + (b0 - b1) * max(0.0, 1 - u)
-        if kind == T.cosine:
-            return b1 + 0.5 * (b0 - b1) * (1 + math.cos(u * math.pi))
-        if kind == T.sigmoid:
-            off = sigmoid(-k / 2)
-            return b0 + (b1 - b0) * (sigmoid(k * (u - 0.5)) - off) / (1 - 2 * off)
-        if kind == T.power:
-            return b1 + (b0 - b1) * (1 - u ** k)
-        if kind == T.exp:
-            return b0 + (b1 - b0) * (1.0 - math.exp(-k * u)) / (1.0 - math.exp(-k))
-        if kind == T.log:
-            hi, lo = math.exp(b1 / k), math.exp(b0 / k)
-            return k * math.log((hi - lo) * u + lo)
-        raise ValueError(f'Unknown temp decay type {kind}')
+        if t < self.decay_start:
+            return b0
+        u = (t - self.decay_start) / (self.t_max - self.decay_start)
+        name = self.decay_type.name if isinstance(self.decay_type, AdaRoundTempDecayType) else None
+        if name == 'log':                   # linear in exp(b / k)
+            lo, hi = math.exp(b0 / k), math.exp(b1 / k)
+            return k * math.log(lo + (hi - lo) * u)
+        if name not in _PROGRESS:
+            raise ValueError(f'Unknown temp decay type {self.decay_type}')
+        return b0 + (b1 - b0) * _PROGRESS[name](u, k)
 
 
 class CombinedLoss:
@@ -214,3 +201,24 @@ class LayerOutputMSE:
         for i in range(math.ceil(self.input.size(0) / bs)):
             loss += F.mse_loss(self.layer(self.input[i * bs:(i + 1) * bs]), self.exp_out[i * bs:(i + 1) * bs]).item()
         return loss
+
+
+class AdaRoundConfig(dict):
+    """option container with attribute access (missing options read as None, like utils.utils.DotDict)"""
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+    def __getattr__(self, key):
+        return self.get(key)
+
+
+DEFAULT_ADAROUND_CONFIG = AdaRoundConfig(
+    # which layers, how many calibration samples, how the grid is initialised
+    layers=('all',), num_samples=1024, init=AdaRoundInitMode.range_estimator,
+    # relaxation and its optimiser
+    round_mode=AdaRoundMode.learned_hard_sigmoid, asym=True, include_act_func=True, lr=1e-3, iters=1000,
+    # regulariser weight and annealing of its exponent
+    weight=0.01, annealing=(20, 2), decay_type=AdaRoundTempDecayType.cosine, decay_shape=1.0, decay_start=0.0,
+    warmup=0.2,
+    act_quant_mode=AdaRoundActQuantMode.post_adaround,
+)

@@ -77,84 +77,100 @@ class QuantEmbedding(QuantizationHijacker, nn.Embedding):
                            scale_grad_by_freq=self.scale_grad_by_freq, sparse=self.sparse)
 
 
+# ---- model conversion ----------------------------------------------------------------------------------
+# Rules (the reference's, autoquant_utils.py:88-241): a layer whose exact type is in ``module_map`` becomes its
+# hijacked twin with a cloned weight / bias; inside a Sequential / ModuleList it also absorbs the first activation
+# module found LATER in the same container (not necessarily adjacent, quirk A.4-10) and the walk continues one (or
+# two) positions further; ``specials`` maps user types to factories; parameter-free pooling layers get a
+# QuantizedActivationWrapper, optionally sharing the previous layer's activation quantizer; anything else is
+# deep-copied and converted child by child.
 module_map = {nn.Linear: QuantLinear, nn.LayerNorm: QuantLayerNorm, nn.Embedding: QuantEmbedding}
-
 non_param_modules = (_AdaptiveAvgPoolNd, _AvgPoolNd)
+
+# constructor arguments that re-create a layer of each convertible type
+_CTOR_FIELDS = {
+    nn.Linear: ('in_features', 'out_features'),
+    nn.LayerNorm: ('normalized_shape', 'eps'),
+    nn.Embedding: ('num_embeddings', 'embedding_dim', 'padding_idx', 'max_norm', 'norm_type', 'scale_grad_by_freq',
+                   'sparse'),
+}
+
+
+def _ctor_args(module, base):
+    kwargs = {f: getattr(module, f) for f in _CTOR_FIELDS[base]}
+    if base is nn.Linear:
+        kwargs['bias'] = module.bias is not None
+    return kwargs
+
+
+def get_linear_args(module):
+    return _ctor_args(module, nn.Linear)
+
+
+def get_layernorm_args(module):
+    return _ctor_args(module, nn.LayerNorm)
+
+
+def get_embedding_args(module):
+    return _ctor_args(module, nn.Embedding)
+
+
+def get_module_args(mod, act):
+    for base in _CTOR_FIELDS:
+        if isinstance(mod, base):
+            return dict(_ctor_args(mod, base), activation=act)
+    raise ValueError
 
 
 def get_act(module, i):
-    """first activation module after position i in the Sequential (not necessarily adjacent)."""
+    """(activation module, its index): the first activation after position ``i`` of the container"""
     for j in range(i + 1, len(module)):
         if isinstance(module[j], tuple(activations_list)):
             return module[j], j
     return None, None
 
 
-def get_linear_args(module):
-    return dict(in_features=module.in_features, out_features=module.out_features,
-                bias=module.bias is not None)
-
-
-def get_layernorm_args(module):
-    return dict(normalized_shape=module.normalized_shape, eps=module.eps)
-
-
-def get_embedding_args(module):
-    return dict(num_embeddings=module.num_embeddings, embedding_dim=module.embedding_dim,
-                padding_idx=module.padding_idx, max_norm=module.max_norm, norm_type=module.norm_type,
-                scale_grad_by_freq=module.scale_grad_by_freq, sparse=module.sparse)
-
-
-_ARG_GETTERS = ((nn.Linear, get_linear_args), (nn.LayerNorm, get_layernorm_args),
-                (nn.Embedding, get_embedding_args))
-
-
-def get_module_args(mod, act):
-    for typ, getter in _ARG_GETTERS:
-        if isinstance(mod, typ):
-            kwargs = getter(mod)
-            kwargs['activation'] = act
-            return kwargs
-    raise ValueError
+def _hijacked_twin(src, act, quant_params, clone):
+    twin = module_map[type(src)](**get_module_args(src, act), **quant_params)
+    twin.weight.data = src.weight.data.clone() if clone else src.weight.data
+    if getattr(src, 'bias', None) is not None:
+        twin.bias.data = src.bias.data.clone() if clone else src.bias.data
+    return twin
 
 
 def quant_module(module, i, **quant_params):
-    """Convert module[i] (+ the activation it is fused with); returns (new_module, next_index)."""
+    """Convert ``module[i]`` together with the activation it absorbs -> (new layer, index to continue at)"""
     act, _ = get_act(module, i)
-    src = module[i]
-    new_module = module_map[type(src)](**get_module_args(src, act), **quant_params)
-    new_module.weight.data = src.weight.data.clone()
-    if src.bias is not None:
-        new_module.bias.data = src.bias.data.clone()
-    return new_module, i + int(bool(act)) + 1
+    return _hijacked_twin(module[i], act, quant_params, clone=True), i + (2 if act else 1)
 
 
 def quantize_sequence(model, specials=None, tie_activation_quantizers=False, **quant_params):
-    specials = specials or dict()
-    out = []
-    i = 0
+    """converted layers of an indexable container, as a python list"""
+    specials = specials or {}
+    converted, i = [], 0
     while i < len(model):
-        m = model[i]
-        if isinstance(m, QuantizedModule):
-            out.append(m)
-        elif type(m) in module_map:
-            new_module, i = quant_module(model, i, **quant_params)
-            out.append(new_module)
+        layer, kind = model[i], type(model[i])
+        if kind in module_map and not isinstance(layer, QuantizedModule):
+            twin, i = quant_module(model, i, **quant_params)
+            converted.append(twin)
             continue
-        elif type(m) in specials:
-            out.append(specials[type(m)](m, **quant_params))
-        elif isinstance(m, non_param_modules):
-            input_quantizer = None
-            if out and isinstance(out[-1], QuantizedModule) and tie_activation_quantizers:
-                input_quantizer = out[-1].activation_quantizer
-                warnings.warn(f'Tying input quantizer {i}^th layer of type {type(out[-1])} to the '
-                              f'quantized {type(m)} following it')
-            out.append(QuantizedActivationWrapper(m, tie_activation_quantizers=tie_activation_quantizers,
-                                                  input_quantizer=input_quantizer, **quant_params))
+        if isinstance(layer, QuantizedModule):
+            new = layer
+        elif kind in specials:
+            new = specials[kind](layer, **quant_params)
+        elif isinstance(layer, non_param_modules):
+            shared = None
+            if tie_activation_quantizers and converted and isinstance(converted[-1], QuantizedModule):
+                shared = converted[-1].activation_quantizer
+                warnings.warn(f'Tying input quantizer {i}^th layer of type {type(converted[-1])} to the '
+                              f'quantized {kind} following it')
+            new = QuantizedActivationWrapper(layer, tie_activation_quantizers=tie_activation_quantizers,
+                                             input_quantizer=shared, **quant_params)
         else:
-            out.append(quantize_model(m, specials=specials, **quant_params))
+            new = quantize_model(layer, specials=specials, **quant_params)
+        converted.append(new)
         i += 1
-    return out
+    return converted
 
 
 def quantize_sequential(model, specials=None, tie_activation_quantizers=False, **quant_params):
@@ -166,27 +182,20 @@ def quantize_module_list(model, specials=None, tie_activation_quantizers=False, 
 
 
 def quantize_model(model, specials=None, tie_activation_quantizers=False, **quant_params):
-    specials = specials or dict()
-
+    specials = specials or {}
+    kind = type(model)
     if isinstance(model, nn.Sequential):
         return quantize_sequential(model, specials, tie_activation_quantizers, **quant_params)
-    if type(model) in specials:
-        return specials[type(model)](model, **quant_params)
+    if kind in specials:
+        return specials[kind](model, **quant_params)
     if isinstance(model, non_param_modules):
         return QuantizedActivationWrapper(model, **quant_params)
-    if type(model) in module_map:
-        # exact type match only: subclasses of Linear / LayerNorm / Embedding are left to the
-        # generic branch below
-        quant_model = module_map[type(model)](**get_module_args(model, None), **quant_params)
-        quant_model.weight.data = model.weight.data
-        if getattr(model, 'bias', None) is not None:
-            quant_model.bias.data = model.bias.data
-        return quant_model
-
-    # unknown container: copy it and convert its children in place
-    quant_model = copy.deepcopy(model)
-    for name, module in quant_model._modules.items():
-        new_model = quantize_model(module, specials=specials, **quant_params)
-        if new_model is not None:
-            setattr(quant_model, name, new_model)
-    return quant_model
+    if kind in module_map:          # exact type only: subclasses of Linear / LayerNorm / Embedding fall through
+        return _hijacked_twin(model, None, quant_params, clone=False)
+    # any other container: convert the children of a deep copy
+    twin = copy.deepcopy(model)
+    for name, child in twin._modules.items():
+        new_child = quantize_model(child, specials=specials, **quant_params)
+        if new_child is not None:
+            setattr(twin, name, new_child)
+    return twin

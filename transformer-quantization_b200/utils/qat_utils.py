@@ -1,4 +1,10 @@
-"""Quantization-aware-training set-up (mirror of the reference's utils/qat_utils.py)."""
+"""Quantization-aware-training set-up: calibrate, then choose how every quantizer's range behaves while
+the weights train (the reference's utils/qat_utils.py entry point, same name and arguments).
+
+  qat.learn_ranges           ranges become nn.Parameters; their gradients come from tq_qdq_bwd_f32
+  otherwise                  ranges keep following the data in train mode (estimate_ranges_train), except
+                             the kinds frozen by qat.fix_weight_ranges / qat.fix_act_ranges
+"""
 import logging
 
 from utils.utils import pass_data_for_range_estimation
@@ -8,23 +14,19 @@ logger.setLevel('INFO')
 
 
 def prepare_model_for_quantization(config, model, loader):
-    """Calibrate on training data, then put every quantizer in the state QAT asked for: learnable ranges
-    (``_delta`` / ``_zero_float`` become parameters, gradients from tq_qdq_bwd_f32) or ranges that keep
-    updating in train mode, optionally frozen per kind (reference qat_utils.py:14-45)."""
-    pass_data_for_range_estimation(loader=loader, model=model, act_quant=config.quant.act_quant,
-                                   weight_quant=config.quant.weight_quant,
-                                   max_num_batches=config.act_quant.num_batches,
-                                   cross_entropy_layer=config.act_quant.cross_entropy_layer)
-    if config.qat.learn_ranges:
+    quant, qat, act = config.quant, config.qat, config.act_quant
+    pass_data_for_range_estimation(loader=loader, model=model, act_quant=quant.act_quant,
+                                   weight_quant=quant.weight_quant, max_num_batches=act.num_batches,
+                                   cross_entropy_layer=act.cross_entropy_layer)
+    if qat.learn_ranges:
         logger.info('Make quantizers learnable')
         model.learn_ranges()
     else:
-        logger.info(f'Fix quantizer ranges to fixW={config.qat.fix_weight_ranges} and '
-                    f'fixA={config.qat.fix_act_ranges}')
+        logger.info(f'Fix quantizer ranges to fixW={qat.fix_weight_ranges} and fixA={qat.fix_act_ranges}')
         model.estimate_ranges_train()
-        if config.qat.fix_weight_ranges:
-            model.fix_weight_ranges()
-        if config.qat.fix_act_ranges:
-            model.fix_act_ranges()
-    model.set_quant_state(config.quant.weight_quant, config.quant.act_quant)
+        for frozen, freeze in ((qat.fix_weight_ranges, model.fix_weight_ranges),
+                               (qat.fix_act_ranges, model.fix_act_ranges)):
+            if frozen:
+                freeze()
+    model.set_quant_state(quant.weight_quant, quant.act_quant)
     return model
