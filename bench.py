@@ -312,6 +312,33 @@ def qdq_hbm_probe(ops, n=256 * 1024 * 1024, iters=10):
     return 8.0 * n / statistics.median(ts) / 1e9
 
 
+def qdq_bwd_probe(ops, n=128 * 1024 * 1024, iters=10):
+    """straight-through backward with learnable-range gradients (tq_qdq_bwd_f32) on 512 MiB fp32 tensors
+    (> L2): achieved HBM GB/s at 12 B / element (x read, grad_y read, grad_x written).  None if it cannot run:
+    a side measurement must not take the headline line down."""
+    try:
+        x = torch.randn(n, device='cuda') * 3
+        g = torch.randn(n, device='cuda')
+        d, z = torch.full((1,), 0.03, device='cuda'), torch.full((1,), 120.3, device='cuda')
+        spec = ops.spec(d, z, None, 8)
+        for _ in range(3):
+            ops.qdq_bwd(x, g, spec, 1)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.qdq_bwd(x, g, spec, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        del x, g
+        return 12.0 * n / statistics.median(ts) / 1e9
+    except Exception as e:                                  # noqa: BLE001
+        print(f'bench.py: qdq_bwd_probe failed: {e!r}', file=sys.stderr)
+        return None
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -418,6 +445,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         prof = (profile_graphs if forward is not model else profile_live)(forward, ids_dev, mask_dev, ops)
         qdq_gbs = qdq_hbm_probe(ops)
+        bwd_gbs = qdq_bwd_probe(ops)
 
     tokens = BATCH * SEQ * world
     value = tokens * args.steps / t_dev
@@ -481,6 +509,9 @@ def run_ours(args):
                             'frac': value / world / (hbm_peak * 1e9 / QDQ_BYTES_PER_TOKEN)},
         'qdq_standalone': {'gbs': qdq_gbs, 'frac_of_measured_hbm': qdq_gbs / hbm_peak,
                            'shape': '256Mi fp32 (1 GiB in, 1 GiB out)', 'bytes_per_elem': 8},
+        'qat_backward_standalone': {'gbs': bwd_gbs, 'frac_of_measured_hbm': bwd_gbs / hbm_peak if bwd_gbs else None,
+                                    'shape': '128Mi fp32 (x, grad_y in; grad_x + range gradients out)',
+                                    'bytes_per_elem': 12},
         'kernels': {k: {'ms_per_step': v['seconds'] * 1e3, 'launches': v['launches']} for k, v in prof.items()},
     }
     emit(line)
