@@ -65,6 +65,13 @@ int         tq_device_sm_count(void);      /* SM count of the current device (14
  * way).  Device uint64[3], caller-zeroed. */
 int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mismatches, void* stream);
 
+/* Copy-bandwidth probe with this library's streaming access pattern (128-bit grid-stride loop of the
+ * quant-dequant kernels, no arithmetic): the attainable ceiling of an 8 B / element kernel on the device at
+ * hand.  flags: bit 0 = loads bypass L1 (ld.global.L1::no_allocate), bit 1 = stores bypass L1, bit 2 =
+ * persistent grid (<= 4 CTAs per SM, grid-stride) instead of one 16 KB chunk per CTA.  n % 4 == 0,
+ * 16-byte aligned pointers. */
+int tq_probe_copy_f32(const float* x, float* y, int64_t n, int32_t flags, void* stream);
+
 /* ---- quantize -> round -> clamp -> dequantize ------------------------------------------------
  * a1+a2: AsymmetricUniformQuantizer.forward / SymmetricUniformQuantizer (quantizers.py:172-211).
  *   x_int = clamp(rint(x / scale) + zero_point, int_min, int_max);  y = scale * (x_int - zero_point)

@@ -74,7 +74,8 @@ def _asym(ops, xmin, xmax, n_bits, dev=DEV):
 
 
 @pytest.mark.parametrize('shape', [(32, 128, 768), (8, 12, 128, 128), (1000003,), (5,), (4, 7, 13),
-                                   (8 * 1024 * 1024 + 4096 + 13,)])     # last: bulk-copy staged kernel, ragged
+                                   (8 * 1024 * 1024 + 4096 + 13,),      # bulk-copy staged kernel, ragged
+                                   (20 * 1024 * 1024 + 4096 + 13,)])    # one-chunk-per-CTA kernel, ragged
 @pytest.mark.parametrize('n_bits', [8, 4])
 def test_qdq_tensor_vs_oracle(ops, shape, n_bits):
     rs = np.random.RandomState(1234)

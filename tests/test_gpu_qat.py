@@ -84,7 +84,7 @@ def _check_vs_oracle(ops, shape, layout, n_bits, asym, signed=True, misalign=0, 
 
 @pytest.mark.parametrize('n_bits', [8, 4])
 @pytest.mark.parametrize('asym', [True, False])
-@pytest.mark.parametrize('n', [32 * 128 * 768, 1000003, 5, 1, 4096 + 3])
+@pytest.mark.parametrize('n', [32 * 128 * 768, 1000003, 5, 1, 4096 + 3, 20 * 1024 * 1024 + 7])   # last: one-chunk-per-CTA kernel
 def test_bwd_tensor_vs_oracle(ops, n, asym, n_bits):
     _check_vs_oracle(ops, (n,), (1, 1, n), n_bits, asym, seed=n % 97)
 
@@ -131,7 +131,7 @@ def test_bwd_log_domain(ops):
 
 
 # ---- 3. properties at full size --------------------------------------------------------------------
-@pytest.mark.parametrize('layout', [(1, 1, 32 * 128 * 3072), (32 * 128, 768, 1), (1, 3072, 768)])
+@pytest.mark.parametrize('layout', [(1, 1, 32 * 128 * 3072), (32 * 128, 768, 1), (1, 3072, 768), (1, 1, 64 * 1024 * 1024)])
 def test_bwd_properties_full_size(ops, layout):
     outer, C, inner = layout
     n = outer * C * inner

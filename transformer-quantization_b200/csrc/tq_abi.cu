@@ -59,9 +59,54 @@ __global__ void selftest_div_kernel(uint64_t seed, int iters, unsigned long long
     if (bad_tiny) atomicAdd(out + 2, bad_tiny);
 }
 
+// ---- copy-bandwidth probe with this library's access patterns ---------------------------------------------
+// What an 8 B / element streaming kernel of this library can reach at most on the device at hand: the same
+// 128-bit grid-stride loop as the quant-dequant kernels without the arithmetic.  flags select the cache policy
+// of the loads / stores and persistent (grid-stride, <= 4 CTAs per SM) vs one 16 KB chunk per CTA.
+template <bool LD_NA, bool ST_NA>
+__global__ void __launch_bounds__(256, 4)
+probe_copy_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t nvec) {
+    const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+    for (int64_t base = (int64_t)blockIdx.x * 256 * 4 + threadIdx.x; base < nvec; base += stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t idx = base + (int64_t)u * 256;
+            if (idx < nvec) v[u] = LD_NA ? ld_stream(x + idx) : x[idx];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t idx = base + (int64_t)u * 256;
+            if (idx < nvec) {
+                if (ST_NA) st_stream(y + idx, v[u]);
+                else y[idx] = v[u];
+            }
+        }
+    }
+}
+
 }  // namespace tq
 
 extern "C" {
+
+int tq_probe_copy_f32(const float* x, float* y, int64_t n, int32_t flags, void* stream) {
+    if (x == nullptr || y == nullptr || n < 0 || (n & 3) != 0 || !tq::aligned16(x) || !tq::aligned16(y)) return TQ_EINVAL;
+    const int64_t nvec = n >> 2;
+    if (nvec == 0) return TQ_OK;
+    const int64_t chunks = (nvec + 1023) / 1024;
+    const int64_t cap = (int64_t)tq::sm_count() * 4;
+    const int grid = (int)((flags & 4) && chunks > cap ? cap : chunks);
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    float4* yv = reinterpret_cast<float4*>(y);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (flags & 3) {
+        case 0: tq::probe_copy_kernel<false, false><<<grid, 256, 0, st>>>(xv, yv, nvec); break;
+        case 1: tq::probe_copy_kernel<true, false><<<grid, 256, 0, st>>>(xv, yv, nvec); break;
+        case 2: tq::probe_copy_kernel<false, true><<<grid, 256, 0, st>>>(xv, yv, nvec); break;
+        default: tq::probe_copy_kernel<true, true><<<grid, 256, 0, st>>>(xv, yv, nvec); break;
+    }
+    return tq::launch_status();
+}
 
 int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mismatches, void* stream) {
     if (mismatches == nullptr || blocks < 1 || iters < 1) return TQ_EINVAL;

@@ -179,6 +179,93 @@ qdq_bwd_tensor_kernel(const float* __restrict__ x, const float* __restrict__ g, 
     }
 }
 
+// Non-persistent variant for tensors far larger than L2: every CTA streams kBwdSpan consecutive 16 KB chunks of
+// x and grad_y and retires; CTAs that retire and get replaced one by one keep reads and writes mixed, whereas
+// the CTAs of a persistent grid fall into lock step (arithmetic-free probe tq_probe_copy_f32: 6.8 vs 6.0 TB/s).
+// One chunk per CTA was tried and lost (4.6 TB/s): a ticket atomic + two block reductions per 16 KB cost more
+// than the access pattern gains.  One partial pair per CTA; the last
+// CTA sums them in a fixed order.
+constexpr int kBwdSpan = 8;
+constexpr int64_t kBwdSpanMinDefault = 6144;            // CTAs: measured 6.17 vs 5.54 TB/s at 8192 CTAs (256 Mi elements),
+                                                        // 5.41 vs 5.78 at 2048 (64 Mi): only very large tensors gain
+__global__ void __launch_bounds__(kBThreads, 3)
+qdq_bwd_span_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gx, int64_t n,
+                    tq_qspec q, float* __restrict__ grad_delta, float* __restrict__ grad_zf, void* ws) {
+    __shared__ double sm[32];
+    const int64_t nvec = n >> 2;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const float4* gv = reinterpret_cast<const float4*>(g);
+    float4* gxv = reinterpret_cast<float4*>(gx);
+    float lo, hi;
+    grid_of(q, lo, hi);
+    const QP p = resolve(q, 0, lo, hi);
+    float ds = 0.0f, dz = 0.0f;
+    const int64_t first = (int64_t)blockIdx.x * kBwdSpan * kBThreads * kBUnroll + threadIdx.x;
+    for (int c = 0; c < kBwdSpan; ++c) {
+        const int64_t base = first + (int64_t)c * kBThreads * kBUnroll;
+        if (base - threadIdx.x >= nvec) break;
+        float4 a[kBUnroll], b[kBUnroll];
+#pragma unroll
+        for (int u = 0; u < kBUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kBThreads;
+            if (idx < nvec) {
+                a[u] = ld_stream(xv + idx);
+                b[u] = ld_stream(gv + idx);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kBThreads;
+            if (idx < nvec) {
+                float4 o;
+                if (p.exact) {
+                    bwd_elem<false>(a[u].x, b[u].x, p, o.x, ds, dz);
+                    bwd_elem<false>(a[u].y, b[u].y, p, o.y, ds, dz);
+                    bwd_elem<false>(a[u].z, b[u].z, p, o.z, ds, dz);
+                    bwd_elem<false>(a[u].w, b[u].w, p, o.w, ds, dz);
+                } else {
+                    bwd_elem<true>(a[u].x, b[u].x, p, o.x, ds, dz);
+                    bwd_elem<true>(a[u].y, b[u].y, p, o.y, ds, dz);
+                    bwd_elem<true>(a[u].z, b[u].z, p, o.z, ds, dz);
+                    bwd_elem<true>(a[u].w, b[u].w, p, o.w, ds, dz);
+                }
+                if (gxv != nullptr) st_stream(gxv + idx, o);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {                                        // ragged tail (n % 4 elements)
+        const int64_t i = (nvec << 2) + threadIdx.x;
+        if (p.exact) bwd_scalar_range<false>(x, g, gx, i, n, kBThreads, p, ds, dz);
+        else bwd_scalar_range<true>(x, g, gx, i, n, kBThreads, p, ds, dz);
+    }
+    double2* part = reinterpret_cast<double2*>(bwd_partials(ws));
+    const double bs = block_sum((double)ds, sm);
+    const double bz = block_sum((double)dz, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = make_double2(bs, bz);
+    if (!last_cta(reinterpret_cast<uint32_t*>(ws), gridDim.x)) return;
+    double as = 0.0, az = 0.0;
+    for (unsigned i0 = threadIdx.x; i0 < gridDim.x; i0 += kBThreads * 8) {      // 8 independent L2 loads in flight
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const unsigned i = i0 + u * kBThreads;
+            v[u] = i < gridDim.x ? __ldcg(part + i) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            as += v[u].x;
+            az += v[u].y;
+        }
+    }
+    as = block_sum(as, sm);
+    az = block_sum(az, sm);
+    if (threadIdx.x == 0) {
+        if (grad_delta != nullptr) grad_delta[0] = delta_grad(q, 0, (float)as);
+        if (grad_zf != nullptr && q.zero_float != nullptr) grad_zf[0] = zf_grad(q, 0, (float)az, lo, hi);
+        *reinterpret_cast<uint32_t*>(ws) = 0u;
+    }
+}
+
 // ---- per-embedding / per-embedding-group: x viewed [rows, C]; CTA = 64 vector columns x 4 row lanes ---
 template <bool FAST>
 __device__ __forceinline__ void bwd_vec4(const float4& a, const float4& b, float4& o, const QP (&p)[4], float (&ds)[4],
@@ -420,6 +507,24 @@ static int64_t bwd_cols_slabs(int64_t rows, int64_t C) {
     if (slabs > max_slabs) slabs = max_slabs;
     return slabs < 1 ? 1 : slabs;
 }
+// the non-persistent span kernel takes over at this many CTAs (TQ_BWD_SPAN_MIN overrides; 0 = always)
+static int64_t bwd_span_min() {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char* e = getenv("TQ_BWD_SPAN_MIN");
+        v = e != nullptr ? atoll(e) : kBwdSpanMinDefault;
+    }
+    return v;
+}
+static int64_t bwd_spans(int64_t n) {
+    const int64_t per_cta = (int64_t)kBwdSpan * kBThreads * kBUnroll;
+    return ((n >> 2) + per_cta - 1) / per_cta;
+}
+static bool bwd_use_spans(int64_t n) {
+    const int64_t c = bwd_spans(n);
+    return c >= bwd_span_min() && c > 0 && c < 0x7fffffff;
+}
+
 static int bwd_tensor_grid(int64_t n) {
     int64_t blocks = ((n >> 2) + kBThreads * kBUnroll) / (kBThreads * kBUnroll);
     const int64_t cap = (int64_t)sm_count() * 3;
@@ -520,7 +625,11 @@ extern "C" {
 
 size_t tq_qdq_bwd_workspace_bytes(int64_t outer, int64_t C, int64_t inner) {
     if (outer < 0 || C < 1 || inner < 0) return 0;
-    if (C == 1) return tq::kBwdHeader + (size_t)tq::sm_count() * 3 * 2 * sizeof(double);
+    if (C == 1) {
+        const int64_t n = outer * inner;
+        const size_t ctas = tq::bwd_use_spans(n) ? (size_t)tq::bwd_spans(n) : (size_t)tq::sm_count() * 3;
+        return tq::kBwdHeader + ctas * 2 * sizeof(double);
+    }
     if (inner == 1 && (C & 3) == 0 && ((C >> 2) + 63) / 64 <= tq::kBwdMaxColBlocks)
         return tq::kBwdHeader + (size_t)tq::bwd_cols_slabs(outer, C) * (size_t)C * 2 * sizeof(double);
     return tq::kBwdHeader;
@@ -542,6 +651,11 @@ int tq_qdq_bwd_f32(const float* x, const float* grad_y, float* grad_x, float* gr
     if ((reinterpret_cast<uintptr_t>(ws) & 15u) != 0) return TQ_EALIGN;
     const bool al = tq::aligned16(x) && tq::aligned16(grad_y) && (grad_x == nullptr || tq::aligned16(grad_x));
     if (C == 1) {
+        if (al && tq::bwd_use_spans(n)) {
+            tq::qdq_bwd_span_kernel<<<(int)tq::bwd_spans(n), tq::kBThreads, 0, st>>>(x, grad_y, grad_x, n, q, grad_delta,
+                                                                                grad_zero_float, ws);
+            return tq::launch_status();
+        }
         tq::qdq_bwd_tensor_kernel<<<tq::bwd_tensor_grid(n), tq::kBThreads, 0, st>>>(
             x, grad_y, grad_x, n, al ? 1 : 0, q, grad_delta, grad_zero_float, ws);
         return tq::launch_status();

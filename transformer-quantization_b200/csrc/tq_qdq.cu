@@ -59,21 +59,21 @@ __device__ __forceinline__ void emit_scalar(float v, const QP& p, float* y, floa
 }
 
 // ---- per-tensor ---------------------------------------------------------------------------------
-template <int MODE, bool FAST>
+template <int MODE, bool FAST, int U = kUnroll>
 __device__ __forceinline__ void tensor_body(const float4* __restrict__ xv, float4* __restrict__ yv,
                                             float4* __restrict__ yiv, uint2* __restrict__ ycv, int64_t nvec,
                                             const QP& p) {
     const QP2 p2 = pair_of(p);
-    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
-    for (int64_t base = (int64_t)blockIdx.x * kThreads * kUnroll + threadIdx.x; base < nvec; base += stride) {
-        float4 v[kUnroll];
+    const int64_t stride = (int64_t)gridDim.x * kThreads * U;
+    for (int64_t base = (int64_t)blockIdx.x * kThreads * U + threadIdx.x; base < nvec; base += stride) {
+        float4 v[U];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t idx = base + (int64_t)u * kThreads;
             if (idx < nvec) v[u] = ld_stream(xv + idx);
         }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t idx = base + (int64_t)u * kThreads;
             if (idx < nvec) emit_vec<MODE, FAST>(v[u], p2, p2, yv, yiv, ycv, idx);
         }
@@ -98,6 +98,47 @@ qdq_tensor_vec_kernel(const float* __restrict__ x, float* __restrict__ y, float*
     if (blockIdx.x == 0) {
         const int64_t i = (nvec << 2) + threadIdx.x;
         if (i < n) emit_scalar<MODE>(x[i], p, y, yint, yctr, i);
+    }
+}
+
+// One 16 KB chunk per CTA, as many CTAs as chunks (no grid-stride loop).  Measured with the arithmetic-free
+// probe (tq_probe_copy_f32, profiles/r1_copy_probe.json): the same 128-bit accesses reach 6.8 TB/s this way
+// and 6.0 TB/s from a persistent grid-stride grid, whose CTAs fall into lock step (all reading, then all
+// writing); CTAs that retire and get replaced one by one keep reads and writes mixed.  The data loads are
+// issued before the quantizer parameters are resolved (two dependent L2 round trips per CTA otherwise).
+constexpr int kChunkVec = kThreads * kUnroll;        // float4 per CTA
+__global__ void __launch_bounds__(kThreads, 4)
+qdq_tensor_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, tq_qspec q) {
+    const int64_t nvec = n >> 2;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    float4* yv = reinterpret_cast<float4*>(y);
+    const int64_t base = (int64_t)blockIdx.x * kChunkVec + threadIdx.x;
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const int64_t idx = base + (int64_t)u * kThreads;
+        if (idx < nvec) v[u] = ld_stream(xv + idx);
+    }
+    float lo, hi;
+    grid_of(q, lo, hi);
+    const QP p = resolve(q, 0, lo, hi);
+    const QP2 p2 = pair_of(p);
+    if (p.exact) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) emit_vec<OUT_QDQ, false>(v[u], p2, p2, yv, nullptr, nullptr, idx);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kThreads;
+            if (idx < nvec) emit_vec<OUT_QDQ, true>(v[u], p2, p2, yv, nullptr, nullptr, idx);
+        }
+    }
+    if (blockIdx.x == 0) {                               // ragged tail (n % 4 elements)
+        const int64_t i = (nvec << 2) + threadIdx.x;
+        if (i < n) emit_scalar<OUT_QDQ>(x[i], p, y, nullptr, nullptr, i);
     }
 }
 
@@ -324,6 +365,29 @@ static int64_t qdq_bulk_threshold() {
     return thr;
 }
 
+// TQ_QDQ_VARIANT = ldg | bulk | chunk forces one per-tensor QDQ kernel for every size (tuning / profiling);
+// unset: the size policy in launch_any
+static int qdq_forced_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TQ_QDQ_VARIANT");
+        v = 0;
+        if (e != nullptr) v = e[0] == 'l' ? 1 : (e[0] == 'b' ? 3 : (e[0] == 'c' ? 4 : 0));
+    }
+    return v;
+}
+
+// the one-chunk-per-CTA kernel is the default at every size (measured faster from 3 M to 256 M elements,
+// profiles/r1_qdq_variants.json); TQ_QDQ_CHUNK_MIN = minimum number of chunks for it
+static int64_t qdq_chunk_min_ctas() {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char* e = getenv("TQ_QDQ_CHUNK_MIN");
+        v = e != nullptr ? atoll(e) : 1;
+    }
+    return v;
+}
+
 static int grid_for(int64_t work_items, int per_block, int ctas_per_sm) {
     int64_t blocks = (work_items + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
@@ -342,7 +406,15 @@ static int launch_any(const float* x, float* y, float* yint, __nv_bfloat16* yctr
                                                         (yctr == nullptr ||
                                                          (reinterpret_cast<uintptr_t>(yctr) & 7u) == 0)));
     if (C == 1) {
-        if (MODE == OUT_QDQ && al && x != y && n >= qdq_bulk_threshold()) {
+        const int forced = MODE == OUT_QDQ && al ? qdq_forced_variant() : 0;
+        // one-chunk CTAs beat every persistent variant (LDG grid-stride, bulk-copy ring) at all measured sizes
+        const int64_t chunks = ((n >> 2) + kChunkVec - 1) / kChunkVec;
+        if (MODE == OUT_QDQ && al && (forced == 4 || (forced == 0 && chunks >= qdq_chunk_min_ctas())) && chunks > 0 &&
+            chunks < 0x7fffffff) {
+            qdq_tensor_chunk_kernel<<<(int)chunks, kThreads, 0, st>>>(x, y, n, q);
+            return launch_status();
+        }
+        if (MODE == OUT_QDQ && al && x != y && forced != 1 && (forced == 3 || n >= qdq_bulk_threshold())) {
             const size_t smem = (size_t)kBulkStages * kBulkTileVec * 16 + kBulkStages * 8;
             static bool attr_set = false;
             if (!attr_set) {

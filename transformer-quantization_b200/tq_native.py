@@ -46,6 +46,7 @@ SIGNATURES = {
     'tq_error_string': (ctypes.c_char_p, [ctypes.c_int]),
     'tq_device_sm_count': (ctypes.c_int, []),
     'tq_selftest_div': (ctypes.c_int, [ctypes.c_uint64, _i32, _i32, ctypes.c_void_p, ctypes.c_void_p]),
+    'tq_probe_copy_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i32, ctypes.c_void_p]),
     'tq_qdq_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, QSpec, ctypes.c_void_p]),
     'tq_qdq_axis_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i64, _i64, QSpec, ctypes.c_void_p]),
     'tq_quant_int_f32': (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_void_p, _i64, _i64, _i64, QSpec,
