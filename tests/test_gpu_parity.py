@@ -268,3 +268,17 @@ def test_percentile_on_device_matches_numpy():
         for r, g in zip(ref, got):
             assert g.is_cuda
             assert np.array_equal(torch.Tensor(r).numpy(), g.cpu().numpy())
+
+
+def test_copy_probe_copies(ops):
+    """tq_probe_copy_f32 (bandwidth probe with the library's streaming access pattern): every flag combination
+    copies exactly; argument errors are reported"""
+    x = torch.randn(1 << 20, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    for flags in range(8):
+        y = torch.zeros_like(x)
+        assert ops.lib.tq_probe_copy_f32(x.data_ptr(), y.data_ptr(), x.numel(), flags, st) == 0
+        assert torch.equal(x, y)
+    y = torch.zeros_like(x)
+    assert ops.lib.tq_probe_copy_f32(x.data_ptr(), y.data_ptr(), 1002, 0, st) == -1        # n % 4 != 0
+    assert ops.lib.tq_probe_copy_f32(None, y.data_ptr(), 1000, 0, st) == -1
