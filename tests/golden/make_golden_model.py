@@ -9,7 +9,8 @@ Writes tests/golden/bert_tiny.npz: weights, token ids and, per configuration, th
 final hidden states and every activation quantizer's (delta, zero_float) after calibration; and
 tests/golden/roberta_tiny.npz: the same for ``models/quantized_roberta.py`` (TQ_GOLDEN_ONLY=roberta
 regenerates only that file); tests/golden/bert_tiny_qat.npz (TQ_GOLDEN_ONLY=qat): loss and
-gradients of one training step with learnable ranges.
+gradients of one training step with learnable ranges; tests/golden/bert_tiny_pegp.npz (TQ_GOLDEN_ONLY=pegp): the
+range-permuted PEG configuration with main.py's FP32 ranges pass (activation quantizers on).
 """
 import importlib.util
 import os
@@ -105,8 +106,12 @@ def peg_sites(model):
     return sites
 
 
-def run_config(qb, name, cfg, hf_model, batches):
-    """quantize -> (FP32 ranges pass) -> calibrate on batches[:-1] -> fix -> eval batches[-1]"""
+def run_config(qb, name, cfg, hf_model, batches, main_py_ranges_pass=False):
+    """quantize -> (FP32 ranges pass) -> calibrate on batches[:-1] -> fix -> eval batches[-1].
+    ``main_py_ranges_pass``: run the FP32 pass exactly like main.py:519-530 does -- weights FP32, activation
+    quantizers ON (pass_data_for_range_estimation(act_quant=True, weight_quant=False)), so the managers are
+    invoked and record the per-dim ranges; without it (the protocol of bert_tiny.npz) the quantizers are off
+    during that pass, no ranges are recorded and the groups are formed without permutation."""
     from quantization.quantizers import QMethods
     from quantization.range_estimators import RangeEstimators, RangeEstimatorBase
     from utils import set_act_quant_axis_and_groups
@@ -126,6 +131,8 @@ def run_config(qb, name, cfg, hf_model, batches):
             set_act_quant_axis_and_groups(s, axis=2, n_groups=k, permute=(kind == 'ngp'))
         if kind == 'ngp':           # main.py:519-537: FP32 pass to collect per-dim ranges
             model.full_precision()
+            if main_py_ranges_pass:
+                model.set_quant_state(weight_quant=False, act_quant=True)
             for b in batches[:-1]:
                 model(input_ids=b, attention_mask=torch.ones_like(b))
             model.set_quant_state(weight_quant=True, act_quant=True)
@@ -303,6 +310,17 @@ if __name__ == '__main__':
     qb = import_reference_model(REF)
     hf = make_hf_model()
     batches = make_batches()
+    if os.environ.get('TQ_GOLDEN_ONLY', '') == 'pegp':
+        outp = {}
+        for name in ('w8a8_pegp4',):
+            res, model = run_config(qb, name, CONFIGS[name], hf, batches, main_py_ranges_pass=True)
+            outp.update(res)
+            n_perm = sum(1 for m in model.modules() if getattr(m, 'ranges', None) is not None)
+            outp[f'{name}.n_range_vectors'] = np.array(n_perm)
+            print(name, 'logits', res[f'{name}.logits'][0], 'estimators with permutation ranges', n_perm)
+        np.savez_compressed(os.path.join(HERE, 'bert_tiny_pegp.npz'), **outp)
+        print('bert_tiny_pegp.npz', os.path.getsize(os.path.join(HERE, 'bert_tiny_pegp.npz')))
+        sys.exit(0)
     if os.environ.get('TQ_GOLDEN_ONLY', '') == 'qat':
         outq = {}
         for name in QAT_CONFIGS:

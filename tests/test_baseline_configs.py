@@ -1,0 +1,72 @@
+"""Every BASELINE.json configuration as a named recipe (engine/configs.py) driven end to end on CPU at tiny
+dimensions with the oracle arithmetic back-end: build -> [FP32 ranges pass] -> calibrate -> fix -> eval.
+Checks the plumbing each configuration adds on top of the per-site parity tests: symmetric activations
+(config 1), per-embedding-group ranges with permutation (config 3), MobileBERT W4A8 (config 4), RoBERTa positions
++ MSE grid ranges (config 5)."""
+import numpy as np
+import pytest
+import torch
+
+import tq_native
+from oracle_backend import OracleOps
+
+
+@pytest.fixture(autouse=True)
+def oracle_ops(monkeypatch):
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+
+
+def _run(name, **kw):
+    from engine import configs
+    model, recipe = configs.build(name, 'cpu', tiny=True, **kw)
+    batches = configs.synthetic_batches(model, recipe, 3, batch=2, seq=16)
+    configs.calibrate(model, recipe, batches[:2])
+    with torch.no_grad():
+        mask = torch.ones_like(batches[2])
+        y1 = model(batches[2], mask)
+        y2 = model(batches[2], mask)
+    assert y1.shape == (2, 2) and torch.isfinite(y1).all() and torch.equal(y1, y2)
+    return model, recipe, y1
+
+
+def _managers(model):
+    from quantization.quantization_manager import QuantizationManager
+    return [m for m in model.modules() if isinstance(m, QuantizationManager)]
+
+
+@pytest.mark.parametrize('name', ['bert_w8a8_sym', 'bert_w8a8_asym', 'mobilebert_w4a8'])
+def test_per_tensor_configs(name):
+    from quantization.quantization_manager import Qstates
+    from quantization.quantizers import SymmetricUniformQuantizer
+    model, recipe, _ = _run(name)
+    mgrs = [m for m in _managers(model) if m.quantizer.is_initialized]
+    assert mgrs and all(m.state is Qstates.fix_ranges for m in mgrs)
+    assert all(m.quantizer._delta.numel() == 1 for m in mgrs)
+    if name == 'bert_w8a8_sym':
+        assert all(isinstance(m.quantizer, SymmetricUniformQuantizer) for m in mgrs)
+    if name == 'mobilebert_w4a8':
+        assert {m.quantizer.n_bits for m in mgrs} == {4, 8}
+
+
+def test_peg_config():
+    """config 3: the PEG sites carry per-dim parameters with exactly K = 6 distinct groups, the others stay per-tensor"""
+    model, recipe, _ = _run('bert_w8a8_peg')
+    peg = [s.activation_quantizer for s in model.peg_sites()]
+    assert len(peg) == 3 + 10 * len(model.layers)
+    for mgr in peg:
+        d = mgr.quantizer._delta.detach().numpy().reshape(-1)
+        assert d.size == model.config.hidden_size and mgr.n_groups == 6
+        assert len(np.unique(d)) <= 6
+        assert mgr.range_estimator.ranges is not None          # permutation ranges were collected
+    others = [m for m in _managers(model) if m.quantizer.is_initialized and all(m is not p for p in peg)]
+    assert others and all(m.quantizer._delta.numel() == 1 for m in others)
+
+
+def test_roberta_mse_config():
+    """config 5: RoBERTa position ids (offset by the padding id) and MSE-grid activation ranges"""
+    from quantization.range_estimators import OptMethod
+    model, recipe, _ = _run('roberta_w8a8_mse', act_range_options=dict(opt_method=OptMethod.grid, num_candidates=4))
+    assert model.embeddings.roberta_positions and model.config.pad_token_id == 1
+    est = model.layers[0].query.activation_quantizer.range_estimator
+    assert type(est).__name__ == 'MSE_Estimator' and est.loss_array is not None

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Run one BASELINE.json configuration (engine/configs.py) on cuda:0: build the random-init model, calibrate on
+two synthetic batches (incl. the FP32 ranges pass for the PEG permutation), fix the ranges, capture the eval
+forward in a CUDA graph and time it with CUDA events.  One JSON line per configuration.
+
+    python tools/run_config.py [--config NAME | --all] [--steps 20] [--warmup 3] [--no-graph]
+
+BERT-base per-tensor asymmetric (config 2) goes through the fused engine exactly like bench.py; every other
+configuration runs the module path (one kernel per quantizer site, fused QuantLinear) today -- see DESIGN.md
+section 10 for what is planned for them."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'transformer-quantization_b200'))
+
+from engine import configs  # noqa: E402
+import tq_native  # noqa: E402
+
+
+def run(name, steps, warmup, use_graph=True):
+    dev = torch.device('cuda', 0)
+    ops = tq_native.ops()
+    model, recipe = configs.build(name, dev)
+    batches = configs.synthetic_batches(model, recipe, 3)
+    t0 = time.perf_counter()
+    configs.calibrate(model, recipe, batches[:2])
+    torch.cuda.synchronize()
+    t_cal = time.perf_counter() - t0
+    ids = batches[2].to(dev)
+    mask = torch.ones_like(ids)
+    forward, kind = model, 'module path'
+    if recipe.family == 'bert' and recipe.peg is None:
+        from engine.fused import FusedBertEngine, UnsupportedByEngine
+        try:
+            forward, kind = FusedBertEngine(model, recipe.batch, recipe.seq), 'fused engine'
+        except UnsupportedByEngine as e:
+            kind = f'module path ({e})'
+    with torch.no_grad():
+        for _ in range(2):
+            ref = forward(ids, mask)
+        torch.cuda.synchronize()
+        l0 = ops.launches
+        if use_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = forward(ids, mask)
+            step = graph.replay
+        else:
+            def step():
+                return forward(ids, mask)
+            out = step()
+        launches = ops.launches - l0
+        for _ in range(max(warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return dict(config=name, forward=kind, batch=recipe.batch, seq=recipe.seq, ms_per_step=ms,
+                tokens_per_s=recipe.batch * recipe.seq / ms * 1e3, library_launches_per_step=launches,
+                calibration_s=t_cal, cuda_graph=use_graph, logits_finite=bool(torch.isfinite(out).all()),
+                graph_equals_eager=bool(torch.equal(out, ref)) if use_graph else None)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--config', default='bert_w8a8_asym', choices=sorted(configs.RECIPES))
+    ap.add_argument('--all', action='store_true')
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--no-graph', action='store_true')
+    a = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit('tools/run_config.py: no CUDA device -- the product path has no CPU fallback')
+    for name in (sorted(configs.RECIPES) if a.all else [a.config]):
+        print(json.dumps(run(name, a.steps, a.warmup, not a.no_graph)), flush=True)
