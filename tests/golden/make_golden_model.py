@@ -10,7 +10,8 @@ final hidden states and every activation quantizer's (delta, zero_float) after c
 tests/golden/roberta_tiny.npz: the same for ``models/quantized_roberta.py`` (TQ_GOLDEN_ONLY=roberta
 regenerates only that file); tests/golden/bert_tiny_qat.npz (TQ_GOLDEN_ONLY=qat): loss and
 gradients of one training step with learnable ranges; tests/golden/bert_tiny_pegp.npz (TQ_GOLDEN_ONLY=pegp): the
-range-permuted PEG configuration with main.py's FP32 ranges pass (activation quantizers on).
+range-permuted PEG configuration with main.py's FP32 ranges pass (activation quantizers on);
+tests/golden/bert_tiny_quant_dict.npz (TQ_GOLDEN_ONLY=quant_dict): mixed-precision / per-site `quant_dict` recipes.
 """
 import importlib.util
 import os
@@ -239,6 +240,71 @@ def run_mobilebert_config(qm, name, cfg, hf_model, batches):
             f'{name}.n_quantizers': np.array(n)}, model
 
 
+# mixed-precision / per-site control through `quant_dict` (reference README.md:160-173, main.py:442-498)
+QUANT_DICTS = {
+    'mp16_ffn': {'y': 16, 'h': 16, 'x': 16},                                  # README: MP-PTQ, 16-bit FFN sites
+    'peg_ffn': {'y': 'ng4', 'h': 'ng4', 'x': 'ng4'},                          # README: PEG on the FFN sites only
+    # every value kind; the all-modules key (L0) on a layer without FP32 sites (the reference cannot re-bit them)
+    'mixed': {'s1': 'fp32', 'p1': 6, 'c': 'per_embd', 'g1': 12, 'u': 'ng2', 'z1': 'fp32', 'e': 16, 'Et': 4,
+              'L0': 12, 'P': 16, 'C': 'fp32', 'wC': 'fp32'},
+}
+
+
+def wire_quant_dict(model, quant_dict, utils_mod):
+    """what main.py:442-498 does with --quant-dict (layer count taken from the model instead of the literal 12)"""
+    hijack_act_quant, hijack_weight_quant = utils_mod.hijack_act_quant, utils_mod.hijack_weight_quant
+    hijack_act_quant_modules = utils_mod.hijack_act_quant_modules
+    E = model.bert.embeddings
+    hijack_act_quant(quant_dict, 'e', E.sum_input_token_type_embd_act_quantizer)
+    hijack_act_quant(quant_dict, 'e', E.sum_pos_embd_act_quantizer)
+    hijack_weight_quant(quant_dict, 'Et', E.word_embeddings)
+    for i, L in enumerate(model.bert.encoder.layer):
+        A, S, O = L.attention.self, L.attention.output, L.output
+        for key, site in (('s', A.attn_scores_act_quantizer), ('p', A.attn_probs_act_quantizer),
+                          ('c', A.context_act_quantizer), ('g', S.dense), ('u', S.res_act_quantizer),
+                          ('x', S.LayerNorm), ('h', O.dense), ('y', O.res_act_quantizer), ('z', O.LayerNorm)):
+            hijack_act_quant(quant_dict, f'{key}{i}', site)
+            hijack_act_quant(quant_dict, key, site)
+        hijack_act_quant_modules(quant_dict, f'L{i}', L)
+        hijack_act_quant_modules(quant_dict, 'L', L)
+    hijack_act_quant(quant_dict, 'P', model.bert.pooler.dense_act[0])
+    hijack_act_quant(quant_dict, 'C', model.classifier)
+    hijack_act_quant(quant_dict, 'wP', model.bert.pooler.dense_act[0])
+    hijack_weight_quant(quant_dict, 'wC', model.classifier)
+
+
+def run_quant_dict_config(qb, name, quant_dict, hf_model, batches):
+    """W8A8 asymmetric running-minmax model with per-site overrides: quantize -> wire -> calibrate -> fix -> eval"""
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators
+    import utils as utils_mod
+    qparams = dict(method=QMethods.symmetric_uniform, act_method=QMethods.asymmetric_uniform, n_bits=8, n_bits_act=8,
+                   per_channel_weights=False, percentile=None, quant_setup='all',
+                   weight_range_method=RangeEstimators.current_minmax, weight_range_options={},
+                   act_range_method=RangeEstimators.running_minmax, act_range_options={}, quant_dict={})
+    model = qb.QuantizedBertForSequenceClassification(hf_model, **qparams)
+    model.eval()
+    wire_quant_dict(model, quant_dict, utils_mod)
+    model.set_quant_state(weight_quant=True, act_quant=True)
+    with torch.no_grad():
+        for b in batches[:-1]:
+            model(input_ids=b, attention_mask=torch.ones_like(b))
+        model.fix_ranges()
+        out = model(input_ids=batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+        hidden = model.bert(batches[-1], attention_mask=torch.ones_like(batches[-1]), return_dict=True)
+    res = {f'{name}.logits': out.logits.numpy().copy(), f'{name}.last_hidden': hidden.last_hidden_state.numpy().copy()}
+    n = 0
+    for mname, m in model.named_modules():
+        q = getattr(m, 'quantizer', None)
+        if q is not None and mname.endswith('activation_quantizer') and q.is_initialized:
+            res[f'{name}.q{n}.delta'] = q._delta.detach().numpy().reshape(-1).copy()
+            res[f'{name}.q{n}.n_bits'] = np.array(q.n_bits)
+            res[f'{name}.q{n}.name'] = np.array(mname)
+            n += 1
+    res[f'{name}.n_act_quantizers'] = np.array(n)
+    return res, model
+
+
 QAT_CONFIGS = ('w8a8_asym', 'w4a8_asym', 'w8a8_sym')
 
 
@@ -310,6 +376,15 @@ if __name__ == '__main__':
     qb = import_reference_model(REF)
     hf = make_hf_model()
     batches = make_batches()
+    if os.environ.get('TQ_GOLDEN_ONLY', '') == 'quant_dict':
+        outd = {}
+        for name, qd in QUANT_DICTS.items():
+            res, _ = run_quant_dict_config(qb, name, qd, hf, batches)
+            outd.update(res)
+            print(name, 'logits', res[f'{name}.logits'][0], 'act quantizers', int(res[f'{name}.n_act_quantizers']))
+        np.savez_compressed(os.path.join(HERE, 'bert_tiny_quant_dict.npz'), **outd)
+        print('bert_tiny_quant_dict.npz', os.path.getsize(os.path.join(HERE, 'bert_tiny_quant_dict.npz')))
+        sys.exit(0)
     if os.environ.get('TQ_GOLDEN_ONLY', '') == 'pegp':
         outp = {}
         for name in ('w8a8_pegp4',):

@@ -20,7 +20,8 @@ from torch import nn
 from quantization.autoquant_utils import QuantEmbedding, QuantLayerNorm, QuantLinear
 from quantization.base_quantized_classes import QuantizedActivation
 from quantization.base_quantized_model import QuantizedModel
-from utils.per_embd_quant_utils import set_act_quant_axis_and_groups
+from utils.per_embd_quant_utils import (hijack_act_quant, hijack_act_quant_modules, hijack_weight_quant,
+                                        set_act_quant_axis_and_groups)
 
 
 class BertConfig:
@@ -165,6 +166,30 @@ class QuantBertForSequenceClassification(QuantizedModel):
     def set_per_embedding_groups(self, n_groups, permute=False):
         for s in self.peg_sites():
             set_act_quant_axis_and_groups(s, axis=2, n_groups=n_groups, permute=permute)
+
+    def apply_quant_dict(self, quant_dict):
+        """Mixed-precision / per-site control with the reference's ``--quant-dict`` grammar (main.py:442-498,
+        README.md:160-173): keys are the site letters of this module's docstring, optionally followed by a layer
+        index (``'x'`` = every layer, ``'x3'`` = layer 3), ``L`` / ``L<i>`` = every activation quantizer of the
+        layer(s), ``Et`` / ``wC`` = weight quantizers of the token embedding / classifier; values: an int (bits),
+        ``'fp32'``, ``'per_embd'``, ``'ng<K>'``, ``'ngp<K>'``.  Call before calibration.  E.g. the paper's
+        MP-PTQ recipe is ``{'y': 16, 'h': 16, 'x': 16}``, PEG on the FFN sites ``{'y': 'ng6', 'h': 'ng6', 'x': 'ng6'}``."""
+        E = self.embeddings
+        for site in (E.e_tok, E.e_pos):
+            hijack_act_quant(quant_dict, 'e', site)
+        hijack_weight_quant(quant_dict, 'Et', E.word)
+        for i, L in enumerate(self.layers):
+            for letter in 'spcguxhyz':                       # same order as the reference applies them
+                site = getattr(L, letter)
+                hijack_act_quant(quant_dict, f'{letter}{i}', site)
+                hijack_act_quant(quant_dict, letter, site)
+            hijack_act_quant_modules(quant_dict, f'L{i}', L)
+            hijack_act_quant_modules(quant_dict, 'L', L)
+        hijack_act_quant(quant_dict, 'P', self.pooler)
+        hijack_act_quant(quant_dict, 'C', self.classifier)
+        hijack_act_quant(quant_dict, 'wP', self.pooler)      # sic: the reference routes 'wP' to the ACTIVATION quantizer
+        hijack_weight_quant(quant_dict, 'wC', self.classifier)
+        return self
 
     def load_hf_state_dict(self, sd):
         """weights stored under HuggingFace BertForSequenceClassification names"""
