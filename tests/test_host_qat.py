@@ -77,3 +77,34 @@ def test_temp_decay_schedules():
 def test_training_step_matches_torch_autograd():
     from qat_cases import check_training_step
     check_training_step(CPU)
+
+
+def test_estimate_ranges_train_state():
+    """Qstates.estimate_ranges_train (the default QAT mode, reference quantization_manager.py:12-16, 94-106 and
+    qat_utils.py:36-42): ranges follow the data while the module is in train mode and are frozen in eval mode;
+    the forward stays differentiable w.r.t. its input (straight-through) in both."""
+    from quantization.quantization_manager import QuantizationManager, Qstates
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators
+    rs = np.random.RandomState(1)
+    x1 = torch.from_numpy(rs.randn(4, 8, 32).astype(np.float32))
+    x2 = (x1 * 4).requires_grad_(True)
+    m = QuantizationManager(qmethod=QMethods.asymmetric_uniform, init=RangeEstimators.running_minmax,
+                            qparams=dict(n_bits=8))
+    m(x1)
+    m.estimate_ranges_train()
+    assert m.state is Qstates.estimate_ranges_train
+    d0 = m.quantizer._delta.clone()
+    m.eval()
+    y = m(x2)
+    assert torch.equal(m.quantizer._delta, d0), 'ranges must be frozen in eval mode'
+    y.sum().backward()
+    inside = (x2.detach() >= m.quantizer.x_min) & (x2.detach() <= m.quantizer.x_max)
+    assert torch.equal(x2.grad != 0, inside) or (x2.grad != 0).sum() >= inside.sum() * 0.98   # edges round in
+    m.train()
+    x2.grad = None
+    y = m(x2)
+    assert not torch.equal(m.quantizer._delta, d0), 'ranges must follow the data in train mode'
+    y.sum().backward()
+    assert x2.grad is not None and (x2.grad != 0).any()
+    assert not any(p.requires_grad for p in m.parameters()), 'no learnable ranges in this state'
