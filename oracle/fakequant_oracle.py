@@ -8,7 +8,10 @@ fails loudly when the CUDA library is missing.
 Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the unmodified reference
 (``/root/reference/quantization/*``) in the build container, runs it on seeded inputs and stores
 the outputs under ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function in
-this file against those vectors (bit-exact for integers / ranges, == for fp32 results).
+this file against those vectors (bit-exact for integers / ranges, == for fp32 results);
+``tests/test_oracle_qat.py`` does the same for the training-time functions (``tests/golden/qat.npz``), and
+``tests/test_oracle_vs_reference_live.py`` compares against the reference imported in place on random inputs
+(build container only).
 
 Every function cites the reference file:line (paths relative to the reference checkout) whose
 arithmetic it restates.  All math is IEEE fp32 (numpy float32), matching torch CPU fp32:

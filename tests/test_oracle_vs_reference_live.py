@@ -101,3 +101,93 @@ def test_forward_and_backward_match_reference(ref_quantizers, c):
     if zf is not None:
         tol_z = 4e-6 * np.asarray(mag_z).reshape(-1) + 1e-30
         assert (np.abs(gz - zf.grad.numpy().reshape(-1)) <= tol_z).all()
+
+
+@pytest.fixture(scope='module')
+def ref_estimators(ref_quantizers):
+    """the reference's quantization.range_estimators (imported like ref_quantizers, private copy)"""
+    saved = {k: v for k, v in sys.modules.items() if k == 'quantization' or k.startswith('quantization.')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        mod = importlib.import_module('quantization.range_estimators')
+        qmod = importlib.import_module('quantization.quantizers')
+        assert mod.__file__.startswith(REF)
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == 'quantization' or k.startswith('quantization.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return mod, qmod
+
+
+est_case = st.fixed_dictionaries(dict(
+    B=st.integers(1, 4), T=st.integers(1, 6), groups=st.sampled_from([1, 2, 3, 4, 6]), per_group=st.integers(1, 4),
+    seed=st.integers(0, 2 ** 31 - 1), kind=st.sampled_from(['current', 'running']), n_batches=st.integers(1, 3),
+    mode=st.sampled_from(['tensor', 'axis', 'groups', 'groups_permuted', 'channel']), momentum=st.sampled_from([0.9, 0.5])))
+
+
+@settings(**SETTINGS)
+@given(c=est_case)
+def test_minmax_estimators_match_reference(ref_estimators, c):
+    R, Q = ref_estimators
+    d = c['groups'] * c['per_group']
+    rs = np.random.RandomState(c['seed'])
+    scales = (0.5 + 3 * rs.rand(d)).astype(np.float32)          # distinct per-dim ranges: a well-defined permutation
+    batches = [(rs.randn(c['B'], c['T'], d) * scales).astype(np.float32) for _ in range(c['n_batches'])]
+    mode = c['mode']
+    if c['kind'] == 'running' and mode == 'groups_permuted':
+        mode = 'groups'                       # the running estimator has no permutation (quirk A.4-7)
+    kw = dict(axis=2 if mode in ('axis', 'groups', 'groups_permuted') else None,
+              n_groups=c['groups'] if mode.startswith('groups') else None, per_channel=mode == 'channel')
+    qz = Q.AsymmetricUniformQuantizer(n_bits=8)
+    if c['kind'] == 'current':
+        ref = R.CurrentMinMaxEstimator(quantizer=qz, **kw)
+        mine = O.CurrentMinMax(**kw)
+    else:
+        ref = R.RunningMinMaxEstimator(quantizer=qz, momentum=c['momentum'], **kw)
+        mine = O.RunningMinMax(momentum=c['momentum'], **kw)
+    if mode == 'groups_permuted':
+        ref.per_group_range_estimation = mine.per_group_range_estimation = True
+        for b in batches:
+            ref(torch.from_numpy(b))
+            mine(b)
+        assert np.array_equal(ref.ranges.numpy(), mine.ranges)
+        ref.per_group_range_estimation = mine.per_group_range_estimation = False
+    for b in batches:
+        rmn, rmx = ref(torch.from_numpy(b))
+        omn, omx = mine(b)
+        assert np.array_equal(np.asarray(rmn.numpy(), np.float32).reshape(-1), np.asarray(omn, np.float32).reshape(-1))
+        assert np.array_equal(np.asarray(rmx.numpy(), np.float32).reshape(-1), np.asarray(omx, np.float32).reshape(-1))
+
+
+mse_case = st.fixed_dictionaries(dict(
+    seed=st.integers(0, 2 ** 31 - 1), n=st.integers(16, 400), n_bits=st.sampled_from([2, 4, 8]), sym=st.booleans(),
+    one_sided=st.booleans(), cands=st.sampled_from([5, 20]), n_batches=st.integers(1, 2)))
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(c=mse_case)
+def test_mse_grid_matches_reference(ref_estimators, c):
+    R, Q = ref_estimators
+    rs = np.random.RandomState(c['seed'])
+    batches = [(rs.randn(c['n']) * 2).astype(np.float32) for _ in range(c['n_batches'])]
+    if c['one_sided']:
+        batches = [np.abs(b) for b in batches]
+    qz = (Q.SymmetricUniformQuantizer if c['sym'] else Q.AsymmetricUniformQuantizer)(n_bits=c['n_bits'])
+    ref = R.MSE_Estimator(quantizer=qz, opt_method=R.OptMethod.grid, num_candidates=c['cands'])
+    mine = O.MSEGrid(c['n_bits'], c['sym'], num_candidates=c['cands'])
+    for b in batches:
+        rmn, rmx = ref(torch.from_numpy(b))
+        omn, omx = mine(b)
+    la, lb = np.asarray(ref.loss_array, np.float64), np.asarray(mine.loss_array, np.float64)
+    assert la.shape == lb.shape
+    fin = np.isfinite(la)
+    assert np.array_equal(fin, np.isfinite(lb))
+    np.testing.assert_allclose(lb[fin], la[fin], rtol=2e-5)
+    # the selected range is the argmin of those losses: equal unless two candidates tie within the summation tolerance
+    srt = np.sort(la[fin])
+    if len(srt) < 2 or srt[1] - srt[0] > 1e-4 * max(srt[0], 1e-12):
+        assert np.array_equal(np.asarray(rmn).reshape(-1), np.asarray(omn).reshape(-1))
+        assert np.array_equal(np.asarray(rmx).reshape(-1), np.asarray(omx).reshape(-1))
