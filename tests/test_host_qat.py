@@ -108,3 +108,28 @@ def test_estimate_ranges_train_state():
     y.sum().backward()
     assert x2.grad is not None and (x2.grad != 0).any()
     assert not any(p.requires_grad for p in m.parameters()), 'no learnable ranges in this state'
+
+
+def test_backward_uses_the_range_of_its_own_forward():
+    """One quantizer serving two tensors in a forward (QuantNoNorm quantizes weight, then bias, with the same
+    weight quantizer; reference quantized_mobilebert.py:64-68) while its range is being estimated: the range
+    buffers are rewritten in place by the second call, the backward of the FIRST call must still use the range
+    it quantized with (the reference allocates new range tensors per set_quant_range)."""
+    from quantization.quantization_manager import QuantizationManager
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators
+    rs = np.random.RandomState(2)
+    for qm in (QMethods.asymmetric_uniform, QMethods.symmetric_uniform):
+        w = torch.from_numpy((rs.randn(64) * 1.0).astype(np.float32)).requires_grad_(True)
+        b = torch.from_numpy((rs.rand(64) * 0.05).astype(np.float32)).requires_grad_(True)   # much smaller, one-sided
+        m = QuantizationManager(qmethod=qm, init=RangeEstimators.current_minmax, qparams=dict(n_bits=4))
+        m.quantizer.set_quant_range(-0.5, 0.5)          # pre-allocates the buffers that get rewritten in place
+        wq = m(w)                                       # range <- w
+        d_w = m.quantizer._delta.detach().clone()
+        bq = m(b)                                       # range <- b, same buffers
+        assert not torch.equal(m.quantizer._delta, d_w)
+        (wq.sum() + bq.sum()).backward()
+        # STE: every w lies inside its own [min, max] range -> gradient 1 everywhere; with the bias's (tiny) range
+        # almost every element of w would be clamped -> gradient 0
+        assert torch.equal(w.grad, torch.ones_like(w)), 'backward of the first call used the range of the second call'
+        assert torch.equal(b.grad, torch.ones_like(b))

@@ -62,20 +62,30 @@ class FakeQuantSTE(Function):
     """
 
     @staticmethod
+    def _frozen(t):
+        """Range buffers are rewritten IN PLACE by the next set_quant_range of the same quantizer (stable
+        addresses for CUDA graphs), e.g. when one quantizer serves two tensors in a forward (QuantNoNorm:
+        weight, then bias) or when ranges keep following the data in train mode.  The reference allocates new
+        tensors there, so each autograd node keeps the range it quantized with: do the same with a copy.
+        Learnable ranges (requires_grad) are never rewritten by an estimator and must stay the graph's leaves."""
+        return t if (t is None or t.requires_grad) else t.clone()
+
+    @staticmethod
     def forward(ctx, x, delta, zero_float, quantizer, layout):
         outer, C, inner = layout
         y = tq_native.ops().qdq(x, quantizer._spec(), outer, C, inner)
-        ctx.save_for_backward(x, delta, zero_float)
+        ctx.save_for_backward(x, FakeQuantSTE._frozen(delta), FakeQuantSTE._frozen(zero_float),
+                              FakeQuantSTE._frozen(getattr(quantizer, '_signed', None)))
         ctx.quantizer, ctx.layout = quantizer, layout
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
-        x, delta, zero_float = ctx.saved_tensors
+        x, delta, zero_float, is_signed = ctx.saved_tensors
         qz = ctx.quantizer
         outer, C, inner = ctx.layout
         ops = tq_native.ops()
-        spec = ops.spec(delta, zero_float, None if zero_float is not None else qz._signed, qz.n_bits,
+        spec = ops.spec(delta, zero_float, None if zero_float is not None else is_signed, qz.n_bits,
                         qz.scale_domain == 'log', qz.eps)
         need_x, need_d, need_z = ctx.needs_input_grad[:3]
         gx, gd, gz = ops.qdq_bwd(x, grad_y, spec, delta.numel(), outer, C, inner, want_x=need_x,
