@@ -95,6 +95,9 @@ class _Weight:
             qz = lin.weight_quantizer.quantizer
             if not qz.is_initialized or qz.n_bits > 8 or not qz.symmetric or qz.delta.numel() != 1:
                 raise UnsupportedByEngine('engine needs per-tensor symmetric <= 8-bit weight quantizers')
+            relaxed = getattr(qz, '_relaxed', None)
+            if relaxed is not None and relaxed():
+                raise UnsupportedByEngine('AdaRound-rounded weights (learned up / down rounding): use the module path')
             q0 = q0 or qz
             if bool(qz.signed) != bool(q0.signed) or qz.n_bits != q0.n_bits:
                 raise UnsupportedByEngine('stacked weights must share the integer grid')

@@ -82,17 +82,12 @@ def _weight_grid(layer, weight_q):
     spec = qz._spec()
     relaxed = getattr(qz, '_relaxed', None)
     if relaxed is not None and relaxed():
-        # AdaRound quantizer (learned up / down rounding): the grid comes from its own forward
-        if qz.soft_targets:
-            return None                            # soft targets are not integers
-        with torch.no_grad():
-            w_int = qz.to_integer_forward(w)
-            if not qz.symmetric:
-                w_int = w_int - qz.zero_point
-        w_ctr = w_int.to(torch.bfloat16)
-    else:
-        _, w_ctr = tq_native.ops().quant_int(w, spec, 1, k, w.numel() // k if k > 1 else None,
-                                             want_f32=False, want_bf16=True)
+        # AdaRound quantizer in a relaxation mode (learned up / down rounding, soft or hard targets): its grid is
+        # not round-to-nearest, so tq_quant_int_f32 does not apply -- the layer runs the three-step path (the
+        # AdaRound forward kernel quantizes the weight, then the library GEMM)
+        return None
+    _, w_ctr = tq_native.ops().quant_int(w, spec, 1, k, w.numel() // k if k > 1 else None,
+                                         want_f32=False, want_bf16=True)
     layer._tq_wgrid = (weight_q, w_ctr, spec, k)
     return w_ctr, spec, k
 
