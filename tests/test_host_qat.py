@@ -133,3 +133,30 @@ def test_backward_uses_the_range_of_its_own_forward():
         # almost every element of w would be clamped -> gradient 0
         assert torch.equal(w.grad, torch.ones_like(w)), 'backward of the first call used the range of the second call'
         assert torch.equal(b.grad, torch.ones_like(b))
+
+
+def test_fused_engine_refuses_adaround_weights():
+    """the fused engine quantizes weights round-to-nearest: a model whose weights carry learned (AdaRound)
+    rounding must be refused (callers then keep the module path), never silently re-rounded"""
+    from engine.bert import BertConfig, QuantBertForSequenceClassification
+    from engine.fused import FusedBertEngine, UnsupportedByEngine
+    from quantization.adaround.adaround import _adaround_quantizer_like
+    from quantization.adaround.utils import AdaRoundMode
+    from quantization.quantizers import QMethods
+    cfg = BertConfig(vocab_size=300, hidden_size=256, num_hidden_layers=1, num_attention_heads=4,
+                     intermediate_size=256, max_position_embeddings=128)
+    model = QuantBertForSequenceClassification(cfg, method=QMethods.symmetric_uniform,
+                                               act_method=QMethods.asymmetric_uniform, n_bits=8, n_bits_act=8)
+    model.init_weights(seed=0).eval()
+    model.set_quant_state(True, True)
+    ids = torch.randint(0, 300, (1, 128), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        model(ids, torch.ones_like(ids))
+    model.fix_ranges()
+    FusedBertEngine(model, 1, 128)                          # plain model: accepted
+    lin = model.layers[0].ffn_in
+    q = _adaround_quantizer_like(lin.weight_quantizer.quantizer)
+    q.round_mode = AdaRoundMode.learned_hard_sigmoid
+    lin.weight_quantizer.quantizer = q
+    with pytest.raises(UnsupportedByEngine):
+        FusedBertEngine(model, 1, 128)
