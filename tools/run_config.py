@@ -66,11 +66,16 @@ def run(name, steps, warmup, use_graph=True):
             step()
         e1.record()
         torch.cuda.synchronize()
+        # cross-check of whatever ran against the module path (one kernel per quantizer site)
+        module_logits = model(ids, mask)
+        out_step = float(model.classifier.activation_quantizer.quantizer.scale.reshape(-1)[0])
+        vs_module = float((out.float() - module_logits.float()).abs().max())
     ms = e0.elapsed_time(e1) / steps
     return dict(config=name, forward=kind, batch=recipe.batch, seq=recipe.seq, ms_per_step=ms,
                 tokens_per_s=recipe.batch * recipe.seq / ms * 1e3, library_launches_per_step=launches,
                 calibration_s=t_cal, cuda_graph=use_graph, logits_finite=bool(torch.isfinite(out).all()),
-                graph_equals_eager=bool(torch.equal(out, ref)) if use_graph else None)
+                graph_equals_eager=bool(torch.equal(out, ref)) if use_graph else None,
+                max_abs_logit_diff_vs_module_path=vs_module, logit_quantization_step=out_step)
 
 
 if __name__ == '__main__':
