@@ -70,3 +70,18 @@ def test_roberta_mse_config():
     assert model.embeddings.roberta_positions and model.config.pad_token_id == 1
     est = model.layers[0].query.activation_quantizer.range_estimator
     assert type(est).__name__ == 'MSE_Estimator' and est.loss_array is not None
+
+
+@pytest.mark.parametrize('name', ['bert_w8a8_peg', 'mobilebert_w4a8'])
+def test_run_config_tool_dry_run(name):
+    """tools/run_config.py end to end on CPU (tiny dimensions, oracle back-end, wall-clock timing): the control
+    flow a GPU run takes, minus the CUDA graph and the fused engine"""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location('run_config', os.path.join(ROOT, 'tools', 'run_config.py'))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    r = tool.run(name, steps=1, warmup=1, device='cpu', tiny=True, batch=2, seq=16)
+    assert r['config'] == name and r['forward'] == 'module path' and r['logits_finite']
+    assert r['max_abs_logit_diff_vs_module_path'] == 0.0 and r['tokens_per_s'] > 0

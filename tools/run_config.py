@@ -24,19 +24,26 @@ from engine import configs  # noqa: E402
 import tq_native  # noqa: E402
 
 
-def run(name, steps, warmup, use_graph=True):
-    dev = torch.device('cuda', 0)
+def run(name, steps, warmup, use_graph=True, device='cuda:0', tiny=False, batch=None, seq=None):
+    """``device`` / ``tiny`` / ``batch`` / ``seq`` exist for the CPU dry run of this tool in the test-suite (oracle
+    back-end injected by the test, wall-clock timing); on a GPU the defaults are the BASELINE shapes."""
+    dev = torch.device(device)
+    on_gpu = dev.type == 'cuda'
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+    use_graph = use_graph and on_gpu
     ops = tq_native.ops()
-    model, recipe = configs.build(name, dev)
+    model, recipe = configs.build(name, dev, tiny=tiny)
+    if batch or seq:
+        recipe = recipe._replace(batch=batch or recipe.batch, seq=seq or recipe.seq)
     batches = configs.synthetic_batches(model, recipe, 3)
     t0 = time.perf_counter()
     configs.calibrate(model, recipe, batches[:2])
-    torch.cuda.synchronize()
+    sync()
     t_cal = time.perf_counter() - t0
     ids = batches[2].to(dev)
     mask = torch.ones_like(ids)
     forward, kind = model, 'module path'
-    if recipe.family == 'bert' and recipe.peg is None:
+    if on_gpu and recipe.family == 'bert' and recipe.peg is None:
         from engine.fused import FusedBertEngine, UnsupportedByEngine
         try:
             forward, kind = FusedBertEngine(model, recipe.batch, recipe.seq), 'fused engine'
@@ -45,8 +52,8 @@ def run(name, steps, warmup, use_graph=True):
     with torch.no_grad():
         for _ in range(2):
             ref = forward(ids, mask)
-        torch.cuda.synchronize()
-        l0 = ops.launches
+        sync()
+        l0 = getattr(ops, 'launches', 0)
         if use_graph:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -56,21 +63,26 @@ def run(name, steps, warmup, use_graph=True):
             def step():
                 return forward(ids, mask)
             out = step()
-        launches = ops.launches - l0
+        launches = getattr(ops, 'launches', 0) - l0
         for _ in range(max(warmup, 3)):
             step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        sync()
+        if on_gpu:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             step()
-        e1.record()
-        torch.cuda.synchronize()
+        if on_gpu:
+            e1.record()
+            sync()
+            ms = e0.elapsed_time(e1) / steps
+        else:
+            ms = (time.perf_counter() - t0) * 1e3 / steps
         # cross-check of whatever ran against the module path (one kernel per quantizer site)
         module_logits = model(ids, mask)
         out_step = float(model.classifier.activation_quantizer.quantizer.scale.reshape(-1)[0])
         vs_module = float((out.float() - module_logits.float()).abs().max())
-    ms = e0.elapsed_time(e1) / steps
     return dict(config=name, forward=kind, batch=recipe.batch, seq=recipe.seq, ms_per_step=ms,
                 tokens_per_s=recipe.batch * recipe.seq / ms * 1e3, library_launches_per_step=launches,
                 calibration_s=t_cal, cuda_graph=use_graph, logits_finite=bool(torch.isfinite(out).all()),
