@@ -175,6 +175,31 @@ def cpu_baseline(threads, budget_s=20.0):
     return rows * SEQ / statistics.median(ts), rows, logits
 
 
+def cpu_qdq_baseline(threads, n=16 * 1024 * 1024, passes=5):
+    """the reference's quantize-dequantize chain on the host cores (oracle.bert_oracle.Site: one torch CPU op per
+    step of quantizers.py:142-153, 184-185, 209 -- six passes + temporaries), fixed range, on a 64 MiB fp32 tensor:
+    algorithmic GB/s at 8 B / element, next to `qdq_standalone`.  None if it cannot run."""
+    try:
+        from oracle.bert_oracle import Site
+        x = torch.randn(n, generator=torch.Generator().manual_seed(1234)) * 3
+        site = Site(n_bits=8, symmetric=False, estimator='current_minmax')
+        with torch.no_grad():
+            site(x)                              # estimates the range
+            site.fixed = True
+            site(x)                              # warm-up
+            ts = []
+            for _ in range(passes):
+                t0 = time.perf_counter()
+                site(x)
+                ts.append(time.perf_counter() - t0)
+        return {'gbs': 8.0 * n / statistics.median(ts) / 1e9, 'cores': threads, 'kind': 'port',
+                'sample': f'{passes} fixed-range passes over {n} fp32 elements (oracle/bert_oracle.py Site: the '
+                          'reference op chain on torch CPU)'}
+    except Exception as e:                                  # noqa: BLE001
+        print(f'bench.py: cpu_qdq_baseline failed: {e!r}', file=sys.stderr)
+        return None
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -476,7 +501,7 @@ def run_ours(args):
     roof['avg_launch_us'] = per_launch_s * 1e6
     roof['share_of_library_kernel_time'] = st['seconds'] / sum(v['seconds'] for v in prof.values())
 
-    cpu = None
+    cpu = cpu_qdq = None
     if world == 1:
         threads = host_threads()
         cpu_val, rows, cpu_logits = cpu_baseline(threads)
@@ -484,6 +509,7 @@ def run_ours(args):
                'sample': f'1 full-batch calibration forward + 2 timed fixed-range forwards of the first {rows} of '
                          'the 32 sequences (oracle/bert_oracle.py, torch CPU, reference op chain)',
                'logit_max_abs_diff_vs_gpu': float((cpu_logits - static_logits[:rows].float().cpu()).abs().max())}
+        cpu_qdq = cpu_qdq_baseline(threads)
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps,
@@ -508,7 +534,7 @@ def run_ours(args):
                             'tokens_per_s_at_peak_per_gpu': hbm_peak * 1e9 / QDQ_BYTES_PER_TOKEN,
                             'frac': value / world / (hbm_peak * 1e9 / QDQ_BYTES_PER_TOKEN)},
         'qdq_standalone': {'gbs': qdq_gbs, 'frac_of_measured_hbm': qdq_gbs / hbm_peak,
-                           'shape': '256Mi fp32 (1 GiB in, 1 GiB out)', 'bytes_per_elem': 8},
+                           'shape': '256Mi fp32 (1 GiB in, 1 GiB out)', 'bytes_per_elem': 8, 'cpu_baseline': cpu_qdq},
         'qat_backward_standalone': {'gbs': bwd_gbs, 'frac_of_measured_hbm': bwd_gbs / hbm_peak if bwd_gbs else None,
                                     'shape': '128Mi fp32 (x, grad_y in; grad_x + range gradients out)',
                                     'bytes_per_elem': 12},
