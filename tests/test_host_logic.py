@@ -63,3 +63,24 @@ def test_percentile_estimator_matches_numpy():
         got = CurrentMinMaxEstimator._percentiles(torch.from_numpy(x), (q, 100 - q))
         for r, g in zip(ref, got):
             assert np.array_equal(torch.Tensor(r).numpy(), g.numpy(), equal_nan=True), (n, q)
+
+
+def test_grid_tag_is_bound_to_the_range_that_produced_the_tensor():
+    """A fused QuantLinear recovers the integer grid of its input from the tag the producing quantizer attached.
+    The quantizer's range buffers are rewritten in place by its next set_quant_range, so a tag must stop being
+    valid when that happens (or when the tensor is edited in place)."""
+    from quantization import fused_linear
+    from quantization.quantizers import QMethods
+    for qm in (QMethods.asymmetric_uniform, QMethods.symmetric_uniform):
+        q = qm.cls(n_bits=8)
+        q.set_quant_range(-1.0, 1.0)
+        x = torch.linspace(-1, 1, 64)
+        y = q(x)
+        tag = fused_linear._valid_tag(y)
+        assert tag is not None and tag.quantizer is q
+        q.set_quant_range(-2.0, 2.0)                    # new range, same buffers
+        assert fused_linear._valid_tag(y) is None
+        y2 = q(x)
+        assert fused_linear._valid_tag(y2) is not None
+        y2 += 1.0                                       # in-place edit (the reference's models do this)
+        assert fused_linear._valid_tag(y2) is None

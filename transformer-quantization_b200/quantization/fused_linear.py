@@ -28,11 +28,14 @@ _ACT_CODES = ((nn.GELU, 1), (nn.ReLU, 2), (nn.Tanh, 3))
 
 class GridTag:
     """What a per-tensor quantizer knows about the tensor it just produced."""
-    __slots__ = ('quantizer', 'version', 'ctr')
+    __slots__ = ('quantizer', 'version', 'epoch', 'ctr')
 
     def __init__(self, quantizer, tensor):
         self.quantizer = quantizer
         self.version = tensor._version
+        # the quantizer's range buffers are rewritten in place by its next set_quant_range: the tag is only
+        # good for the range that produced the tensor
+        self.epoch = getattr(quantizer, '_range_epoch', 0)
         self.ctr = None          # bf16 centred integer grid, filled lazily / by a fused producer
 
 
@@ -46,6 +49,8 @@ def _valid_tag(x):
     tag = getattr(x, '_tq_grid', None)
     if tag is None or tag.version != x._version or not tag.quantizer.is_initialized:
         return None
+    if getattr(tag.quantizer, '_range_epoch', 0) != tag.epoch:
+        return None              # the producing quantizer has been given a new range since
     return tag
 
 

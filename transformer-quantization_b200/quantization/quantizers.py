@@ -315,6 +315,7 @@ class AsymmetricUniformQuantizer(QuantizerBase):
                                        delta, zero_float)
         self._delta = delta
         self._zero_float = zero_float
+        self._range_epoch = getattr(self, '_range_epoch', 0) + 1     # invalidates grid tags of earlier outputs
 
     def make_range_trainable(self):
         if self.delta not in self.parameters():
@@ -370,6 +371,7 @@ class SymmetricUniformQuantizer(AsymmetricUniformQuantizer):
                                       delta, signed)
         self._delta = delta
         self._signed = signed
+        self._range_epoch = getattr(self, '_range_epoch', 0) + 1
 
     def make_range_trainable(self):
         if self.delta not in self.parameters():
