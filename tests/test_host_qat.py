@@ -195,3 +195,27 @@ def test_mse_per_channel_weights(case):
     else:
         np.testing.assert_allclose(mx.numpy().reshape(-1), g[f'{nm}.xmax'], rtol=2e-3)
         np.testing.assert_allclose(mn.numpy().reshape(-1), g[f'{nm}.xmin'], rtol=2e-3)
+
+
+@pytest.mark.parametrize('case', QAT_MANIFEST['cross_entropy'], ids=lambda c: c['name'])
+def test_cross_entropy_estimator(case):
+    """CrossEntropyEstimator on logits (reference range_estimators.py:493-502): accumulated loss arrays rtol 1e-5,
+    selected range equal unless two candidates tie within that tolerance"""
+    from qat_cases import qat_file
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import OptMethod, RangeEstimators
+    g, nm = qat_file(), case['name']
+    qm = QMethods.symmetric_uniform if case['kind'] == 'sym' else QMethods.asymmetric_uniform
+    est = RangeEstimators.cross_entropy.cls(quantizer=qm.cls(n_bits=case['n_bits']), opt_method=OptMethod.grid,
+                                            num_candidates=case['num_candidates'])
+    for i in range(case['n_batches']):
+        mn, mx = est(torch.from_numpy(g[f'{nm}.x{i}']))
+        loss, ref = np.asarray(est.loss_array, np.float64), g[f'{nm}.b{i}.loss']
+        fin = np.isfinite(ref)
+        assert loss.shape == ref.shape and np.array_equal(fin, np.isfinite(loss))
+        np.testing.assert_allclose(loss[fin], ref[fin], rtol=1e-5)
+        if not (np.array_equal(mn.numpy().reshape(-1), g[f'{nm}.b{i}.xmin']) and
+                np.array_equal(mx.numpy().reshape(-1), g[f'{nm}.b{i}.xmax'])):
+            mine = int(np.argmin(loss[0]))
+            ref_min = float(ref[0].min())
+            assert abs(float(ref[0].reshape(-1)[mine]) - ref_min) <= 1e-5 * abs(ref_min)
