@@ -191,3 +191,32 @@ def test_mse_grid_matches_reference(ref_estimators, c):
     if len(srt) < 2 or srt[1] - srt[0] > 1e-4 * max(srt[0], 1e-12):
         assert np.array_equal(np.asarray(rmn).reshape(-1), np.asarray(omn).reshape(-1))
         assert np.array_equal(np.asarray(rmx).reshape(-1), np.asarray(omx).reshape(-1))
+
+
+pct_case = st.fixed_dictionaries(dict(
+    seed=st.integers(0, 2 ** 31 - 1), rows=st.integers(1, 6), cols=st.integers(1, 300), per_channel=st.booleans(),
+    pct=st.sampled_from([0.001, 0.01, 0.1, 1.0, 5.0, 25.0, 50.0])))
+
+
+@settings(**SETTINGS)
+@given(c=pct_case)
+def test_percentile_estimator_matches_reference(ref_estimators, c, monkeypatch):
+    """CurrentMinMaxEstimator(percentile=p): the reference calls np.percentile on the host
+    (range_estimators.py:121-127, 133-140; per-tensor: (p, 100), per-channel: (p, 100 - p)); this package's class
+    evaluates the same interpolation where the tensor lives.  Whole estimator forward, reference in place vs this
+    package's class (oracle back-end for its kernels) -- equal."""
+    import tq_native
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    from quantization.range_estimators import CurrentMinMaxEstimator as Mine
+    R, Q = ref_estimators
+    rs = np.random.RandomState(c['seed'])
+    x = (rs.randn(c['rows'], c['cols']) * (1 + 3 * rs.rand())).astype(np.float32)
+    ref = R.CurrentMinMaxEstimator(quantizer=Q.AsymmetricUniformQuantizer(n_bits=8), per_channel=c['per_channel'],
+                                   percentile=c['pct'])
+    mine = Mine(per_channel=c['per_channel'], percentile=c['pct'])
+    rmn, rmx = ref(torch.from_numpy(x))
+    omn, omx = mine(torch.from_numpy(x))
+    assert np.array_equal(rmn.numpy().reshape(-1), omn.numpy().reshape(-1))
+    assert np.array_equal(rmx.numpy().reshape(-1), omx.numpy().reshape(-1))
