@@ -85,3 +85,33 @@ def test_run_config_tool_dry_run(name):
     r = tool.run(name, steps=1, warmup=1, device='cpu', tiny=True, batch=2, seq=16)
     assert r['config'] == name and r['forward'] == 'module path' and r['logits_finite']
     assert r['max_abs_logit_diff_vs_module_path'] == 0.0 and r['tokens_per_s'] > 0
+
+
+def test_quant_options_to_model():
+    """utils.quant_options: reference option names -> config -> make_qparams -> a quantized model (W4 per-channel
+    MSE weights, A8 running min-max with momentum) that calibrates and runs"""
+    from engine.bert import BertConfig, QuantBertForSequenceClassification
+    from quantization.range_estimators import OptMethod, RangeEstimators
+    from utils.quant_options import make_qparams, quant_config
+    cfg = quant_config(n_bits=4, n_bits_act=8, qmethod_act='asymmetric_uniform', per_channel=True,
+                       weight_quant_method='MSE', num_candidates=10, act_momentum=0.5)
+    qp = make_qparams(cfg)
+    assert qp['weight_range_method'] is RangeEstimators.MSE and qp['weight_range_options'] == dict(
+        opt_method=OptMethod.grid, num_candidates=10)
+    assert qp['act_range_options'] == dict(momentum=0.5) and qp['per_channel_weights'] and qp['n_bits'] == 4
+    with pytest.raises(ValueError):
+        quant_config(act_num_candidates=5)                     # only valid with the MSE activation estimator
+    with pytest.raises(TypeError):
+        quant_config(nbits=4)
+    model = QuantBertForSequenceClassification(
+        BertConfig(vocab_size=100, hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=32,
+                   max_position_embeddings=16), **qp)
+    model.init_weights(seed=0).eval()
+    model.set_quant_state(cfg.quant.weight_quant, cfg.quant.act_quant)
+    ids = torch.randint(0, 100, (2, 8), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        model(ids, torch.ones_like(ids))
+        model.fix_ranges()
+        y = model(ids, torch.ones_like(ids))
+    assert torch.isfinite(y).all()
+    assert model.layers[0].query.weight_quantizer.quantizer._delta.numel() == 32       # per-channel ranges

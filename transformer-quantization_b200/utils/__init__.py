@@ -9,6 +9,7 @@ from utils.per_embd_quant_utils import (
     set_act_quant_axis_and_groups,
 )
 from utils.qat_utils import prepare_model_for_quantization
+from utils.quant_options import make_qparams, quant_config
 from utils.tb_utils import _tb_advance_global_step, _tb_advance_token_counters, _tb_hist
 from utils.utils import (
     seed_all,
