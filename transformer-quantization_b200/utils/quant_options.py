@@ -5,7 +5,6 @@ reference's utils/quant_click_options.py for programmatic callers (the click dec
 DotDicts with the reference's option names and defaults (quant_click_options.py:50-108, 134-198, 200-229,
 231-352; ``--qmethod`` is a required option there, here it defaults to ``symmetric_uniform``); ``make_qparams(config)`` turns them into the keyword arguments every ``Quantized*`` class of this
 package takes (reference :356-380)."""
-from quantization.adaround.utils import DEFAULT_ADAROUND_CONFIG, AdaRoundConfig
 from quantization.quantizers import QMethods
 from quantization.range_estimators import OptMethod, RangeEstimators
 from utils.utils import DotDict
@@ -44,6 +43,8 @@ def quant_config(**overrides):
     config.act_quant = DotDict(quant_method=a['act_quant_method'], cross_entropy_layer=a['cross_entropy_layer'],
                                num_batches=a['num_est_batches'], options=options)
     config.qat = DotDict(pick(_QAT_DEFAULTS))
+    # imported here: quantization.adaround.utils itself imports utils.utils (package import cycle otherwise)
+    from quantization.adaround.utils import DEFAULT_ADAROUND_CONFIG, AdaRoundConfig
     config.adaround = AdaRoundConfig(DEFAULT_ADAROUND_CONFIG)
     config.adaround.update(overrides.get('adaround') or {})
     return config
