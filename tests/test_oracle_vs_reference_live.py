@@ -220,3 +220,88 @@ def test_percentile_estimator_matches_reference(ref_estimators, c, monkeypatch):
     omn, omx = mine(torch.from_numpy(x))
     assert np.array_equal(rmn.numpy().reshape(-1), omn.numpy().reshape(-1))
     assert np.array_equal(rmx.numpy().reshape(-1), omx.numpy().reshape(-1))
+
+
+# ---- model conversion (quantize_model / quantize_sequential / quantize_module_list) ---------------------------
+@pytest.fixture(scope='module')
+def ref_autoquant(ref_quantizers):
+    saved = {k: v for k, v in sys.modules.items() if k == 'quantization' or k.startswith('quantization.')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        mod = importlib.import_module('quantization.autoquant_utils')
+        qmod = importlib.import_module('quantization.quantizers')
+        assert mod.__file__.startswith(REF)
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == 'quantization' or k.startswith('quantization.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return mod, qmod
+
+
+def _nets():
+    from torch import nn
+
+    class Block(nn.Module):                      # an unknown container: converted child by child
+        def __init__(self):
+            super().__init__()
+            self.emb = nn.Embedding(20, 8)
+            self.body = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 16), nn.GELU(), nn.LayerNorm(16))
+            self.heads = nn.ModuleList([nn.Linear(16, 4), nn.Linear(16, 4)])
+
+        def forward(self, ids):
+            h = self.body(self.emb(ids))
+            return self.heads[0](h) + self.heads[1](h)
+
+    torch.manual_seed(11)
+    return {
+        'mlp': (nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 16), nn.GELU(), nn.LayerNorm(16),
+                              nn.Linear(16, 4)), 'float'),
+        # the first Linear absorbs the Tanh two positions later and the walk resumes AFTER the next position:
+        # the second Linear is skipped (reference autoquant_utils.py:94-105, 143-150 -- quirk A.4-10)
+        'skip': (nn.Sequential(nn.Linear(8, 8), nn.Linear(8, 8), nn.Tanh(), nn.Linear(8, 4)), 'float'),
+        'pool_tied': (nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.AdaptiveAvgPool1d(4)), 'float'),
+        'block': (Block(), 'ids'),
+    }
+
+
+def _tree(m):
+    return [(n, type(s).__name__) for n, s in m.named_modules()]
+
+
+@pytest.mark.parametrize('name', ['mlp', 'skip', 'pool_tied', 'block'])
+@pytest.mark.parametrize('tie', [False, True])
+def test_model_conversion_matches_reference(ref_autoquant, name, tie, monkeypatch):
+    import copy
+    import tq_native
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    import quantization.autoquant_utils as mine_mod
+    from quantization.quantizers import QMethods as MineQ
+    R, RQ = ref_autoquant
+    net, kind = _nets()[name]
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randint(0, 20, (3, 6), generator=g) if kind == 'ids' else torch.randn(3, 6, 8, generator=g)
+          for _ in range(3)]
+    outs = []
+    for mod, Q in ((R, RQ.QMethods), (mine_mod, MineQ)):
+        qnet = mod.quantize_model(copy.deepcopy(net), tie_activation_quantizers=tie, method=Q.symmetric_uniform,
+                                  act_method=Q.asymmetric_uniform, n_bits=4, n_bits_act=8)
+        qnet.eval()
+        for m in qnet.modules():
+            if hasattr(m, 'quantized'):
+                m.quantized()
+        with torch.no_grad():
+            ys = [qnet(x) for x in xs[:2]]
+            for m in qnet.modules():
+                if hasattr(m, 'fix_ranges') and hasattr(m, 'quantized'):
+                    m.fix_ranges()
+            ys.append(qnet(xs[2]))
+        outs.append((_tree(qnet), [y.numpy().copy() for y in ys]))
+    (tree_r, ys_r), (tree_m, ys_m) = outs
+    assert tree_r == tree_m                              # same module names, same class names
+    for a, b in zip(ys_r, ys_m):
+        assert np.array_equal(a, b)
