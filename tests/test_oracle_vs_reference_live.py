@@ -305,3 +305,65 @@ def test_model_conversion_matches_reference(ref_autoquant, name, tie, monkeypatc
     assert tree_r == tree_m                              # same module names, same class names
     for a, b in zip(ys_r, ys_m):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('layer', ['linear_relu', 'layernorm', 'embedding'])
+def test_hijacked_layers_match_reference(ref_autoquant, layer, monkeypatch):
+    """QuantLinear / QuantLayerNorm / QuantEmbedding through their life cycle (reference hijacker.py:66-116):
+    estimate -> fix -> eval with the weight cache, activation dumps (``activation_save_target``), cache reset on
+    train() and with ``caching = False``, weight / activation switches.  Outputs and dumps equal."""
+    import tq_native
+    from torch import nn
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    import quantization.autoquant_utils as mine_mod
+    from quantization.quantizers import QMethods as MineQ
+    R, RQ = ref_autoquant
+    g = torch.Generator().manual_seed(9)
+    if layer == 'embedding':
+        xs = [torch.randint(0, 30, (4, 7), generator=g) for _ in range(4)]
+    else:
+        xs = [torch.randn(4, 7, 12, generator=g) * (1 + i) for i in range(4)]
+    results = []
+    for mod, Q in ((R, RQ.QMethods), (mine_mod, MineQ)):
+        torch.manual_seed(21)
+        kw = dict(method=Q.symmetric_uniform, act_method=Q.asymmetric_uniform, n_bits=4, n_bits_act=8)
+        if layer == 'linear_relu':
+            m = mod.QuantLinear(12, 10, activation=nn.ReLU(), **kw)
+        elif layer == 'layernorm':
+            m = mod.QuantLayerNorm(12, **kw)
+            m.weight.data = 1 + 0.1 * torch.randn(12, generator=torch.Generator().manual_seed(3))
+        else:
+            m = mod.QuantEmbedding(30, 12, **kw)
+        m.eval()
+        log = []
+        with torch.no_grad():
+            log.append(m(xs[0]))                                   # FP32
+            m.quantized()
+            log.append(m(xs[0]))                                   # estimate ranges
+            log.append(m(xs[1]))
+            m.fix_ranges()
+            dump = {}
+            m.activation_save_target, m.activation_save_name = dump, 'site'
+            log.append(m(xs[2]))
+            m.activation_save_target = None
+            cached = m.cached_params is not None
+            m.train()
+            assert m.cached_params is None
+            m.eval()
+            m.caching = False
+            log.append(m(xs[3]))
+            assert m.cached_params is None
+            m.full_precision_acts()
+            log.append(m(xs[3]))
+            m.quantized_acts()
+            m.full_precision_weights()
+            log.append(m(xs[3]))
+        results.append(([y.numpy().copy() for y in log], {k: np.array(v) for k, v in dump.items()}, cached))
+    (ys_r, dump_r, c_r), (ys_m, dump_m, c_m) = results
+    assert c_r == c_m and set(dump_r) == set(dump_m) and dump_r
+    for k in dump_r:
+        assert np.array_equal(dump_r[k], dump_m[k]), k
+    for i, (a, b) in enumerate(zip(ys_r, ys_m)):
+        assert np.array_equal(a, b), f'step {i}'
