@@ -367,3 +367,54 @@ def test_hijacked_layers_match_reference(ref_autoquant, layer, monkeypatch):
         assert np.array_equal(dump_r[k], dump_m[k]), k
     for i, (a, b) in enumerate(zip(ys_r, ys_m)):
         assert np.array_equal(a, b), f'step {i}'
+
+
+def test_error_behaviour_matches_reference(ref_estimators, monkeypatch):
+    """the exceptions SURVEY.md section 8(b) lists: same exception class (by name) from the reference and from this
+    package for the same misuse"""
+    import tq_native
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    import quantization.quantization_manager as mine_mgr
+    import quantization.quantizers as mine_q
+    import quantization.range_estimators as mine_est
+    R, RQ = ref_estimators
+    saved = {k: v for k, v in sys.modules.items() if k == 'quantization' or k.startswith('quantization.')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        ref_mgr = importlib.import_module('quantization.quantization_manager')
+        ref_q = importlib.import_module('quantization.quantizers')
+        ref_est = importlib.import_module('quantization.range_estimators')
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == 'quantization' or k.startswith('quantization.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    x = torch.randn(2, 3, 12, generator=torch.Generator().manual_seed(0))
+
+    def cases(Q, E, M):
+        A, S = Q.QMethods.asymmetric_uniform, Q.QMethods.symmetric_uniform
+        yield 'delta before init', lambda: A.cls(n_bits=8).delta
+        yield 'zero_float before init', lambda: A.cls(n_bits=8).zero_float
+        yield 'signed before init', lambda: S.cls(n_bits=8).signed
+        yield 'fix_ranges before init', lambda: M.QuantizationManager(qmethod=A, qparams=dict(n_bits=8)).fix_ranges()
+        yield 'vector range on per-tensor quantizer', lambda: A.cls(n_bits=8).set_quant_range(
+            torch.tensor([-1.0, -2.0]), torch.tensor([1.0, 2.0]))
+        yield 'groups do not divide the dim', lambda: M.QuantizationManager(
+            qmethod=A, init=E.RangeEstimators.current_minmax, axis=2, n_groups=5, qparams=dict(n_bits=8))(x)
+        yield 'MSE without data', lambda: E.RangeEstimators.MSE.cls(quantizer=A.cls(n_bits=8)).optimization_method
+        yield 'MSE without quantizer', lambda: E.RangeEstimators.MSE.cls()
+
+    for (what, ref_call), (_, mine_call) in zip(cases(ref_q, ref_est, ref_mgr), cases(mine_q, mine_est, mine_mgr)):
+        names = []
+        for call in (ref_call, mine_call):
+            try:
+                call()
+                names.append(None)
+            except Exception as e:                         # noqa: BLE001
+                names.append(type(e).__name__)
+        assert names[0] is not None, f'{what}: the reference raised nothing'
+        assert names[0] == names[1], f'{what}: reference {names[0]}, this package {names[1]}'
