@@ -34,3 +34,28 @@ def test_no_cpu_fallback():
         pytest.skip('CPU-only check')
     with pytest.raises(tq_native.TQError):
         tq_native.ops()
+
+
+def test_product_code_never_imports_the_oracle():
+    """the CPU oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may
+    import it -- nothing under the package or tools/ does (a product path routed through it would void parity)"""
+    import ast
+    import os
+    from conftest import PKG, ROOT
+    offenders = []
+    for top in (PKG, os.path.join(ROOT, 'tools')):
+        for dirpath, _, files in os.walk(top):
+            for f in files:
+                if not f.endswith('.py'):
+                    continue
+                path = os.path.join(dirpath, f)
+                tree = ast.parse(open(path).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom) and node.module:
+                        names = [node.module]
+                    if any(n == 'oracle' or n.startswith('oracle.') or n == 'oracle_backend' for n in names):
+                        offenders.append(path)
+    assert not offenders, offenders
