@@ -16,6 +16,9 @@ Our arm prints ONE JSON line with
               H2D and D2H inside the timed region, one host sync per step
   roofline    the dominant kernel of the step, timed live with CUDA events in an eager pass
   cpu_baseline  oracle port (oracle/bert_oracle.py) on the host cores, bounded sample (rank 0, N=1)
+  qdq_standalone  second half of BASELINE's metric: the standalone quant-dequant kernel on a 1 GiB fp32 tensor, GB/s at
+              8 B / element, with `cpu_baseline` = the reference's six-pass chain on the host cores (oracle port)
+  qat_backward_standalone  tq_qdq_bwd_f32 (straight-through backward + range gradients) on 512 MiB tensors, 12 B / element
 The reference arm times the same oracle port -- the reference's algorithm on the host CPU with all
 host threads -- on the same config and prints the same line with "impl": "reference".
 """
