@@ -418,3 +418,80 @@ def test_error_behaviour_matches_reference(ref_estimators, monkeypatch):
                 names.append(type(e).__name__)
         assert names[0] is not None, f'{what}: the reference raised nothing'
         assert names[0] == names[1], f'{what}: reference {names[0]}, this package {names[1]}'
+
+
+def test_calibration_loop_and_model_switches_match_reference(ref_autoquant, monkeypatch):
+    """utils.pass_data_for_range_estimation (reference utils/utils.py:47-79) + the QuantizedModel bulk switches
+    (base_quantized_model.py:15-113) on a small model: batches consumed, quantizer states and outputs equal."""
+    import importlib.util
+    import types
+    import tq_native
+    from torch import nn
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    import quantization.autoquant_utils as mine_auto
+    import quantization.base_quantized_model as mine_model
+    import quantization.quantization_manager as mine_mgr
+    from quantization.quantizers import QMethods as MineQ
+    from utils.utils import pass_data_for_range_estimation as mine_pass
+    R, RQ = ref_autoquant
+    # reference side: base_quantized_model + utils/utils.py loaded from the checkout (utils/__init__ needs the CLI stack)
+    saved = {k: v for k, v in sys.modules.items() if k.split('.')[0] in ('quantization', 'utils')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        ref_model = importlib.import_module('quantization.base_quantized_model')
+        ref_mgr = importlib.import_module('quantization.quantization_manager')
+        pkg = types.ModuleType('utils')
+        pkg.__path__ = []
+        sys.modules['utils'] = pkg
+        spec = importlib.util.spec_from_file_location('utils.utils', os.path.join(REF, 'utils', 'utils.py'))
+        ref_utils = importlib.util.module_from_spec(spec)
+        sys.modules['utils.utils'] = ref_utils
+        spec.loader.exec_module(ref_utils)
+        ref_auto = importlib.import_module('quantization.autoquant_utils')
+        ref_Q = importlib.import_module('quantization.quantizers').QMethods
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.split('.')[0] in ('quantization', 'utils')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+    def make(auto, model_mod, Q):
+        class Net(model_mod.QuantizedModel):
+            def __init__(self):
+                super().__init__()
+                kw = dict(method=Q.symmetric_uniform, act_method=Q.asymmetric_uniform, n_bits=8, n_bits_act=8)
+                self.fc1 = auto.QuantLinear(6, 10, activation=nn.GELU(), **kw)
+                self.fc2 = auto.QuantLinear(10, 3, **kw)
+
+            def forward(self, x):
+                return self.fc2(self.fc1(x))
+        torch.manual_seed(31)
+        return Net()
+
+    g = torch.Generator().manual_seed(2)
+    loader = [(torch.randn(5, 6, generator=g) * (i + 1), torch.zeros(5)) for i in range(4)]
+    outs = []
+    for auto, model_mod, mgr_mod, Q, pass_fn in ((ref_auto, ref_model, ref_mgr, ref_Q, ref_utils.pass_data_for_range_estimation),
+                                                 (mine_auto, mine_model, mine_mgr, MineQ, mine_pass)):
+        net = make(auto, model_mod, Q)
+        with torch.no_grad():
+            pass_fn(loader=loader, model=net, act_quant=True, weight_quant=True, max_num_batches=3)
+            states0 = [m.state.name for m in net.modules() if isinstance(m, mgr_mod.QuantizationManager)]
+            net.fix_act_ranges()
+            states1 = [m.state.name for m in net.modules() if isinstance(m, mgr_mod.QuantizationManager)]
+            y_q = net(loader[3][0])
+            net.full_precision_acts()
+            y_w = net(loader[3][0])
+            net.set_quant_state(weight_quant=False, act_quant=True)
+            y_a = net(loader[3][0])
+            net.reset_act_ranges()
+            states2 = [m.state.name for m in net.modules() if isinstance(m, mgr_mod.QuantizationManager)]
+        assert not net.training
+        outs.append((states0, states1, states2, [t.numpy().copy() for t in (y_q, y_w, y_a)]))
+    assert outs[0][:3] == outs[1][:3]
+    for a, b in zip(outs[0][3], outs[1][3]):
+        assert np.array_equal(a, b)
