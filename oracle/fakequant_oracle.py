@@ -596,3 +596,31 @@ def adaround_grad_alpha(x, alpha, g, scale, zp, lo, hi, mode, temperature=None):
             v = p * F32(ADAROUND_ZETA - ADAROUND_GAMMA) + F32(ADAROUND_GAMMA)
             d = np.where((v >= 0) & (v <= 1), d * F32(ADAROUND_ZETA - ADAROUND_GAMMA), F32(0)).astype(F32)
     return (h * d).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# grouped integer GEMM for per-embedding-group (PEG) activations -- the formulation planned for the fused
+# engine; checker for that kernel, exercised today by tests/test_oracle_qat.py
+# --------------------------------------------------------------------------------------
+def peg_linear_exact(x_int, zp, scale, w_int, w_scale, bias, n_groups, order=None):
+    """y[m, n] = sum_k  scale[k] * (x_int[m, k] - zp[k]) * w_scale[n] * w_int[n, k]  + bias[n]
+    for an activation quantized per embedding group (scale / zp constant inside each of the ``n_groups``
+    groups of -- optionally range-permuted -- hidden dims) and a symmetric weight grid, computed the way an
+    integer tensor-core kernel would: one exact integer accumulator per group,
+        acc_g[m, n] = sum_{k in g} x_int[m, k] * w_int[n, k],     rowsum_g[n] = sum_{k in g} w_int[n, k]
+        y = w_scale[n] * sum_g  s_g * (acc_g - zp_g * rowsum_g)  + bias
+    (int64 here; int32 suffices on the device: |acc_g| <= 255 * 127 * K).  Returns float64."""
+    x_int = np.asarray(x_int, np.int64)
+    w_int = np.asarray(w_int, np.int64)
+    K = x_int.shape[1]
+    order = np.arange(K) if order is None else np.asarray(order)
+    gs = K // n_groups
+    y = np.zeros((x_int.shape[0], w_int.shape[0]), np.float64)
+    for g in range(n_groups):
+        cols = order[g * gs:(g + 1) * gs]
+        s_g, z_g = float(scale[cols[0]]), int(zp[cols[0]])
+        assert np.all(scale[cols] == scale[cols[0]]) and np.all(zp[cols] == zp[cols[0]])
+        acc = x_int[:, cols] @ w_int[:, cols].T
+        rowsum = w_int[:, cols].sum(1)
+        y += s_g * (acc - z_g * rowsum[None, :]).astype(np.float64)
+    return y * np.asarray(w_scale, np.float64).reshape(1, -1) + np.asarray(bias, np.float64).reshape(1, -1)

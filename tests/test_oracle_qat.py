@@ -62,3 +62,29 @@ def test_adaround(case):
     assert np.array_equal(O.dequantize(xi, scale, zp), a['y_hard1'])
     ga = O.adaround_grad_alpha(w, a['alpha1'], a['g'], scale, zp, lo, hi, mode, temp)
     np.testing.assert_allclose(ga, a['grad_alpha1'], rtol=2e-5, atol=1e-7 * step)
+
+
+@pytest.mark.parametrize('permute', [False, True])
+def test_peg_grouped_integer_gemm_is_the_dequantized_matmul(permute):
+    """The grouped integer GEMM planned for PEG activations in the fused engine (oracle.peg_linear_exact) equals
+    the reference's formulation -- F.linear on the dequantized tensors -- evaluated in float64, to float64
+    round-off: per-group integer accumulators + one scale per group lose nothing (the reference's fp32 GEMM on
+    dequantized values is the less exact of the two)."""
+    rs = np.random.RandomState(7)
+    M, K, N, G = 24, 96, 20, 6
+    x = (rs.randn(M, K) * (0.5 + 3 * rs.rand(K))).astype(np.float32)
+    mn, mx = O.minmax_axis(x.reshape(1, M, K), 2)
+    order = O.stable_order((mx - mn).astype(np.float32)) if permute else None
+    gmn, gmx = O.group_minmax(mn, mx, G, order)
+    delta, zf = O.asym_set_quant_range(gmn, gmx, 8)
+    scale, zp = O.scale_of(delta), O.asym_zero_point(zf, 8)
+    x_int = O.qdq_asym(x.reshape(1, M, K), delta, zf, 8, axis=2, return_int=True).reshape(M, K)
+    w = (rs.randn(N, K) * 0.05).astype(np.float32)
+    wd, signed = O.sym_set_quant_range(w.min(), w.max(), 8)
+    w_int = O.qdq_sym(w, wd, signed, 8, return_int=True)
+    bias = rs.randn(N).astype(np.float32)
+    y = O.peg_linear_exact(x_int, zp, scale, w_int, np.full(N, O.scale_of(wd)), bias, G, order)
+    xq = O.dequantize(x_int, scale.reshape(1, K), zp.reshape(1, K)).astype(np.float64)
+    wq = O.dequantize(w_int, O.scale_of(wd), np.float32(0)).astype(np.float64)
+    ref = xq @ wq.T + bias.astype(np.float64)
+    np.testing.assert_allclose(y, ref, rtol=1e-6, atol=1e-6 * np.abs(ref).max())
