@@ -495,3 +495,50 @@ def test_calibration_loop_and_model_switches_match_reference(ref_autoquant, monk
     assert outs[0][:3] == outs[1][:3]
     for a, b in zip(outs[0][3], outs[1][3]):
         assert np.array_equal(a, b)
+
+
+def test_state_dicts_interchange_with_the_reference(ref_estimators, monkeypatch):
+    """calibrated QuantizationManagers expose the same state_dict (keys, dtypes, shapes, values) as the reference's:
+    checkpoints written by one side load on the other"""
+    import tq_native
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    import quantization.quantization_manager as mine_mgr
+    import quantization.quantizers as mine_q
+    import quantization.range_estimators as mine_est
+    saved = {k: v for k, v in sys.modules.items() if k == 'quantization' or k.startswith('quantization.')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        ref_mgr = importlib.import_module('quantization.quantization_manager')
+        ref_q = importlib.import_module('quantization.quantizers')
+        ref_est = importlib.import_module('quantization.range_estimators')
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == 'quantization' or k.startswith('quantization.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    g = torch.Generator().manual_seed(4)
+    x3 = torch.randn(3, 5, 12, generator=g)
+    w2 = torch.randn(6, 10, generator=g) * 0.1
+    cases = [('asym tensor', 'asymmetric_uniform', 'running_minmax', {}, x3),
+             ('sym tensor', 'symmetric_uniform', 'current_minmax', {}, x3),
+             ('asym per-embedding groups', 'asymmetric_uniform', 'current_minmax', dict(axis=2, n_groups=3), x3),
+             ('sym per-channel', 'symmetric_uniform', 'current_minmax', dict(per_channel=True), w2),
+             ('asym per-channel', 'asymmetric_uniform', 'allminmax', dict(per_channel=True), w2)]
+    for what, qm, est, kw, data in cases:
+        sds = []
+        for M, Q, E in ((ref_mgr, ref_q, ref_est), (mine_mgr, mine_q, mine_est)):
+            m = M.QuantizationManager(qmethod=Q.QMethods[qm], init=E.RangeEstimators[est], qparams=dict(n_bits=8), **kw)
+            with torch.no_grad():
+                m(data)
+                m(data * 1.5)
+            sds.append(m.state_dict())
+        ref_sd, mine_sd = sds
+        assert list(ref_sd) == list(mine_sd), what
+        for k in ref_sd:
+            a, b = ref_sd[k], mine_sd[k]
+            assert a.dtype == b.dtype and tuple(a.shape) == tuple(b.shape), f'{what}: {k}'
+            assert torch.equal(a, b), f'{what}: {k}'
