@@ -25,32 +25,38 @@ def set_act_quant_axis_and_groups(module, axis, n_groups, permute=False):
     return mgr
 
 
-def _hijack_act_quant(module, value):
+def _parse_groups(value):
+    """'per_embd' | 'ng<K>' | 'ngp<K>'  ->  (n_groups | None, permute) or None if ``value`` is not a PEG spec"""
+    if value == 'per_embd':
+        return None, False
+    for prefix, permute in (('ngp', True), ('ng', False)):          # 'ngp' first: 'ng' is its prefix
+        if value.startswith(prefix):
+            return int(value[len(prefix):]), permute
+    return None
+
+
+def _hijack(module, attr, value, allow_groups):
+    """apply one ``quant_dict`` value to ``module.<attr>`` (the activation or the weight QuantizationManager)"""
     if value is None:
         return
     if isinstance(value, int):
-        module.activation_quantizer.quantizer.n_bits = value
-    elif value == 'fp32':
-        module.activation_quantizer = FP32Acts()
-    elif value == 'per_embd':
-        set_act_quant_axis_and_groups(module, axis=2, n_groups=None)
-    elif value.startswith('ngp'):
-        set_act_quant_axis_and_groups(module, axis=2, n_groups=int(value[3:]), permute=True)
-    elif value.startswith('ng'):
-        set_act_quant_axis_and_groups(module, axis=2, n_groups=int(value[2:]), permute=False)
-    else:
+        getattr(module, attr).quantizer.n_bits = value
+        return
+    if value == 'fp32':
+        setattr(module, attr, FP32Acts())
+        return
+    groups = _parse_groups(value) if allow_groups else None
+    if groups is None:
         raise NotImplementedError(f'Unknown value "{value}" in quant_dict')
+    set_act_quant_axis_and_groups(module, axis=2, n_groups=groups[0], permute=groups[1])
+
+
+def _hijack_act_quant(module, value):
+    _hijack(module, 'activation_quantizer', value, allow_groups=True)
 
 
 def _hijack_weight_quant(module, value):
-    if value is None:
-        return
-    if isinstance(value, int):
-        module.weight_quantizer.quantizer.n_bits = value
-    elif value == 'fp32':
-        module.weight_quantizer = FP32Acts()
-    else:
-        raise NotImplementedError(f'Unknown value "{value}" in quant_dict')
+    _hijack(module, 'weight_quantizer', value, allow_groups=False)
 
 
 def hijack_act_quant(quant_dict, name, m):
@@ -62,6 +68,7 @@ def hijack_weight_quant(quant_dict, name, m):
 
 
 def hijack_act_quant_modules(quant_dict, name, m):
+    """the same value for every module below ``m`` that owns an activation quantizer"""
     value = quant_dict.get(name, None)
     for sub in m.modules():
         if hasattr(sub, 'activation_quantizer'):
