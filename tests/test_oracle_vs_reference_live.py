@@ -43,7 +43,11 @@ case = st.fixed_dictionaries(dict(
     shape=shapes, n_bits=st.integers(2, 12), asym=st.booleans(), seed=st.integers(0, 2 ** 31 - 1),
     lo=st.floats(-8, 1), hi=st.floats(-1, 8), scale=st.sampled_from([1e-3, 0.1, 1.0, 30.0]),
     log=st.booleans(), layout=st.sampled_from(['tensor', 'axis', 'channel'])))
-SETTINGS = dict(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+# derandomize: the same examples on every run (a test-suite that draws new inputs each time can turn red by chance)
+# (exploration: TQ_HYPOTHESIS_RANDOM=1 TQ_HYPOTHESIS_EXAMPLES=5000 pytest tests/test_oracle_vs_reference_live.py)
+_RANDOM = os.environ.get('TQ_HYPOTHESIS_RANDOM') == '1'
+SETTINGS = dict(max_examples=int(os.environ.get('TQ_HYPOTHESIS_EXAMPLES', 150)), deadline=None,
+                derandomize=not _RANDOM, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 
 
 def _build(ref, c):
@@ -139,6 +143,9 @@ def test_minmax_estimators_match_reference(ref_estimators, c):
     mode = c['mode']
     if c['kind'] == 'running' and mode == 'groups_permuted':
         mode = 'groups'                       # the running estimator has no permutation (quirk A.4-7)
+    if mode == 'groups_permuted' and c['B'] * c['T'] < 2:
+        mode = 'groups'                       # one sample per dim: every range is 0, the permutation is all ties and
+        #                                       torch.argsort leaves their order implementation-defined (quirk A.4-11)
     kw = dict(axis=2 if mode in ('axis', 'groups', 'groups_permuted') else None,
               n_groups=c['groups'] if mode.startswith('groups') else None, per_channel=mode == 'channel')
     qz = Q.AsymmetricUniformQuantizer(n_bits=8)
@@ -167,7 +174,7 @@ mse_case = st.fixed_dictionaries(dict(
     one_sided=st.booleans(), cands=st.sampled_from([5, 20]), n_batches=st.integers(1, 2)))
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@settings(**dict(SETTINGS, max_examples=max(40, SETTINGS['max_examples'] // 4)))
 @given(c=mse_case)
 def test_mse_grid_matches_reference(ref_estimators, c):
     R, Q = ref_estimators
