@@ -549,3 +549,72 @@ def test_state_dicts_interchange_with_the_reference(ref_estimators, monkeypatch)
             a, b = ref_sd[k], mine_sd[k]
             assert a.dtype == b.dtype and tuple(a.shape) == tuple(b.shape), f'{what}: {k}'
             assert torch.equal(a, b), f'{what}: {k}'
+
+
+mgr_case = st.fixed_dictionaries(dict(
+    seed=st.integers(0, 2 ** 31 - 1), asym=st.booleans(), n_bits=st.sampled_from([2, 4, 8, 16]),
+    est=st.sampled_from(['current_minmax', 'running_minmax', 'allminmax']), layout=st.sampled_from(['tensor', 'axis', 'groups', 'channel']),
+    groups=st.sampled_from([1, 2, 4]), per_group=st.integers(1, 3), rows=st.integers(2, 5), n_batches=st.integers(1, 3),
+    log=st.booleans()))
+
+
+@settings(**SETTINGS)
+@given(c=mgr_case)
+def test_quantization_manager_flow_matches_reference(ref_estimators, c, monkeypatch):
+    """QuantizationManager end to end on random configurations: estimate over several batches -> fix_ranges ->
+    quantize a new batch; the reference in place vs this package's classes (oracle back-end for the kernels).
+    Outputs equal (scale_domain='log': within one grid step, libm vs numpy expf on the scale)."""
+    import tq_native
+    from oracle_backend import OracleOps
+    monkeypatch.setattr(tq_native, '_OPS', OracleOps())
+    monkeypatch.setattr(tq_native, 'default_device', lambda: torch.device('cpu'))
+    import quantization.quantization_manager as mine_mgr
+    import quantization.quantizers as mine_q
+    import quantization.range_estimators as mine_est
+    R, Q = ref_estimators
+    saved = {k: v for k, v in sys.modules.items() if k == 'quantization' or k.startswith('quantization.')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        ref_mgr = importlib.import_module('quantization.quantization_manager')
+        ref_q = importlib.import_module('quantization.quantizers')
+        ref_est = importlib.import_module('quantization.range_estimators')
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == 'quantization' or k.startswith('quantization.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    layout = c['layout']
+    if not c['asym'] and layout in ('axis', 'groups'):
+        layout = 'tensor'                      # symmetric quantizer: no per-axis mode (quirk A.4-1)
+    if c['est'] == 'allminmax' and layout in ('axis', 'groups'):
+        layout = 'tensor'                      # the all-min-max estimator ignores `axis` (quirk A.4-7)
+    d = c['groups'] * c['per_group']
+    rs = np.random.RandomState(c['seed'])
+    sc = (0.5 + 3 * rs.rand(d)).astype(np.float32)
+    batches = [(rs.randn(c['rows'], 3, d) * sc * (1 + 0.3 * i)).astype(np.float32) for i in range(c['n_batches'] + 1)]
+    kw = dict(per_channel=layout == 'channel', axis=2 if layout in ('axis', 'groups') else None,
+              n_groups=c['groups'] if layout == 'groups' else None)
+    qparams = dict(n_bits=c['n_bits'], scale_domain='log' if c['log'] else 'linear')
+    outs = []
+    for M, QQ, E in ((ref_mgr, ref_q, ref_est), (mine_mgr, mine_q, mine_est)):
+        qm = QQ.QMethods.asymmetric_uniform if c['asym'] else QQ.QMethods.symmetric_uniform
+        m = M.QuantizationManager(qmethod=qm, init=E.RangeEstimators[c['est']], qparams=dict(qparams), **kw)
+        ys = []
+        with torch.no_grad():
+            for b in batches[:-1]:
+                ys.append(m(torch.from_numpy(b)).numpy().copy())
+            m.fix_ranges()
+            ys.append(m(torch.from_numpy(batches[-1])).numpy().copy())
+        outs.append((ys, m.quantizer._delta.detach().numpy().reshape(-1).copy()))
+    (ys_r, d_r), (ys_m, d_m) = outs
+    if c['log']:
+        np.testing.assert_allclose(d_m, d_r, rtol=1e-6, atol=1e-7)
+        step = float(np.exp(d_r).max())
+        for a, b in zip(ys_r, ys_m):
+            assert np.abs(a - b).max() <= step * 1.0001
+        return
+    assert np.array_equal(d_r, d_m)
+    for a, b in zip(ys_r, ys_m):
+        assert np.array_equal(a, b)
