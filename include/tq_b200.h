@@ -53,7 +53,8 @@ typedef struct tq_qspec {
 } tq_qspec;
 
 /* ---- library info ------------------------------------------------------------------------- */
-int         tq_version(void);              /* ABI version, currently 1 */
+int         tq_version(void);              /* ABI version: 1 = inference path; 2 (current) adds the training-time
+                                              * entry points (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32 */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
 

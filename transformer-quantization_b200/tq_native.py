@@ -116,6 +116,7 @@ SIGNATURES = {
                                            ctypes.c_float, ctypes.c_void_p]),
 }
 
+ABI_VERSION = 2          # tq_version() of the library this binding was written against
 ADAROUND_MODE = {'learned_sigmoid': 0, 'learned_hard_sigmoid': 1, 'sigmoid_temp_decay': 2}
 
 
@@ -127,6 +128,9 @@ def load_library(path=None):
             f'tq_b200: {path} not found -- build it with transformer-quantization_b200/csrc/build.sh '
             f'(or __graft_entry__.build()).  There is no CPU fallback.')
     lib = ctypes.CDLL(path)
+    if lib.tq_version() < ABI_VERSION:
+        raise TQError(f'tq_b200: {path} implements ABI version {lib.tq_version()}, this binding needs {ABI_VERSION} '
+                      f'-- rebuild it with transformer-quantization_b200/csrc/build.sh')
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)         # AttributeError if the .so does not export it
         fn.restype = res
