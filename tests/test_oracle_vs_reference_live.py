@@ -618,3 +618,86 @@ def test_quantization_manager_flow_matches_reference(ref_estimators, c, monkeypa
     assert np.array_equal(d_r, d_m)
     for a, b in zip(ys_r, ys_m):
         assert np.array_equal(a, b)
+
+
+ada_case = st.fixed_dictionaries(dict(
+    seed=st.integers(0, 2 ** 31 - 1), rows=st.integers(1, 6), cols=st.integers(1, 24), asym=st.booleans(),
+    per_channel=st.booleans(), n_bits=st.sampled_from([2, 3, 4, 8]),
+    mode=st.sampled_from(['learned_sigmoid', 'learned_hard_sigmoid', 'sigmoid_temp_decay']),
+    temperature=st.sampled_from([0.5, 1.0, 2.5, 20.0]), shrink=st.sampled_from([0.5, 0.8, 1.0])))
+
+
+@settings(**SETTINGS)
+@given(c=ada_case)
+def test_adaround_quantizer_matches_reference(ref_quantizers, c):
+    """AdaRoundQuantizer in the relaxation modes (reference quantization/adaround/quantizer.py:46-92), oracle vs the
+    reference in place on random weights / grids / alpha: alpha initialisation, soft and hard forward, d / d alpha."""
+    saved = {k: v for k, v in sys.modules.items() if k.split('.')[0] in ('quantization', 'utils')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        import importlib.util
+        import types
+        pkg = types.ModuleType('utils')
+        pkg.__path__ = []
+        sys.modules['utils'] = pkg
+        spec = importlib.util.spec_from_file_location('utils.utils', os.path.join(REF, 'utils', 'utils.py'))
+        sub = importlib.util.module_from_spec(spec)
+        sys.modules['utils.utils'] = sub
+        spec.loader.exec_module(sub)
+        aq = importlib.import_module('quantization.adaround.quantizer')
+        au = importlib.import_module('quantization.adaround.utils')
+        rq = importlib.import_module('quantization.quantizers')
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.split('.')[0] in ('quantization', 'utils')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    rs = np.random.RandomState(c['seed'])
+    w = (rs.randn(c['rows'], c['cols']) * 0.05).astype(np.float32)
+    base = rq.AsymmetricUniformQuantizer if c['asym'] else rq.SymmetricUniformQuantizer
+    q = aq.ADAROUND_QUANTIZER_MAP[base](n_bits=c['n_bits'], per_channel=c['per_channel'])
+    if c['per_channel']:
+        q.set_quant_range(torch.from_numpy(w.min(1) * c['shrink']), torch.from_numpy(w.max(1) * c['shrink']))
+    else:
+        q.set_quant_range(float(w.min()) * c['shrink'], float(w.max()) * c['shrink'])
+    q.round_mode = au.AdaRoundMode[c['mode']]
+    q.temperature = c['temperature']
+    q.soft_targets = True
+    wt = torch.from_numpy(w)
+    y0 = q(wt)
+    scale = O.scale_of(q._delta.detach().numpy().reshape(-1))
+    if c['asym']:
+        zp = O.asym_zero_point(q._zero_float.detach().numpy().reshape(-1), c['n_bits'])
+        lo, hi = 0.0, O.asym_int_max(c['n_bits'])
+    else:
+        zp = np.zeros_like(scale)
+        lo, hi = O.sym_grid(c['n_bits'], bool(q.signed))
+    shp = (-1, 1) if c['per_channel'] else ()
+    scale, zp = scale.reshape(shp), zp.reshape(shp)
+    step = float(np.max(scale))
+    ytol = 4e-6 * step * max(abs(lo), hi, 1.0)
+    temp = c['temperature']
+    a0 = O.adaround_alpha_init(w, scale, c['mode'], temp)
+    ref_a0 = q.alpha.detach().numpy()
+    fin = np.isfinite(ref_a0)
+    assert np.array_equal(fin, np.isfinite(a0))
+    np.testing.assert_allclose(a0[fin], ref_a0[fin], rtol=5e-5, atol=5e-5 * max(temp, 1.0))
+    np.testing.assert_allclose(O.adaround_qdq(w, np.where(fin, ref_a0, 0), scale, zp, lo, hi, c['mode'], True, temp)[fin],
+                               y0.detach().numpy()[fin], rtol=0, atol=ytol)
+    alpha1 = (np.where(fin, ref_a0, 0) + rs.randn(*w.shape) * 1.5).astype(np.float32)
+    with torch.no_grad():
+        q.alpha.copy_(torch.from_numpy(alpha1))
+    g = rs.randn(*w.shape).astype(np.float32)
+    y1 = q(wt)
+    y1.backward(torch.from_numpy(g))
+    np.testing.assert_allclose(O.adaround_qdq(w, alpha1, scale, zp, lo, hi, c['mode'], True, temp), y1.detach().numpy(),
+                               rtol=0, atol=ytol)
+    ga = O.adaround_grad_alpha(w, alpha1, g, scale, zp, lo, hi, c['mode'], temp)
+    np.testing.assert_allclose(ga, q.alpha.grad.numpy(), rtol=5e-5, atol=2e-7 * step)
+    q.soft_targets = False
+    with torch.no_grad():
+        xi = q.to_integer_forward(wt).numpy()
+    mine, _ = O.adaround_to_integer(w, alpha1, scale, zp, lo, hi, c['mode'], False, temp)
+    assert np.array_equal(mine, xi)
