@@ -19,8 +19,16 @@ Our arm prints ONE JSON line with
   qdq_standalone  second half of BASELINE's metric: the standalone quant-dequant kernel on a 1 GiB fp32 tensor, GB/s at
               8 B / element, with `cpu_baseline` = the reference's six-pass chain on the host cores (oracle port)
   qat_backward_standalone  tq_qdq_bwd_f32 (straight-through backward + range gradients) on 512 MiB tensors, 12 B / element
-The reference arm times the same oracle port -- the reference's algorithm on the host CPU with all
-host threads -- on the same config and prints the same line with "impl": "reference".
+  calibration  BASELINE config 5 at every N: RoBERTa-base W8A8, MSE (grid, 100 candidates) activation ranges, one
+              B=32 calibration batch PER RANK, estimator statistics all-reduced over NCCL inside
+              quantization/_dist.calibration_sync() -- tokens/s, collective calls and bytes, ranks identical?
+  other_configs  (N = 1) BASELINE configs 3 and 4 through tools/run_config.py: BERT-base PEG (K = 6, range-permuted)
+              and MobileBERT W4A8 B=64, CUDA-graphed eval forward, tokens/s
+The reference arm runs the UNMODIFIED reference (baseline/_ref, tools/install_reference.sh) through its own
+public API on the host CPU with all host threads (baseline/reference_arm.py; the oracle port only if that copy is
+absent) on the same config and prints the same line with "impl": "reference".
+
+    python bench.py --config bert_w8a8_peg | mobilebert_w4a8 | roberta_w8a8_mse     one of the other configs as the line
 """
 import argparse
 import json
@@ -43,15 +51,20 @@ BATCH, SEQ = 32, 128
 METRIC = 'tokens/sec W8A8 BERT-base seq128 b32'
 WORKLOAD = ('BERT-base W8A8 per-tensor asymmetric (W8 sym current_minmax / A8 asym running_minmax, '
             'fixed ranges), seq 128 batch 32 per GPU, eval forward')
+DTYPE = ('u8 / s8 integer-grid operands with int32 accumulation (QKV, attention-out, FFN-out GEMMs), bf16 integer-grid '
+         'operands with fp32 accumulation (FFN-in GEMM, attention products) -- all exact; quantize / dequantize / LayerNorm / '
+         'softmax / GELU arithmetic in fp32')
 QDQ_BYTES_PER_TOKEN = 1.3456e6     # algorithmic QDQ traffic per token
 
 
 def peaks():
+    """(HBM GB/s, bf16 TFLOP/s burst, bf16 TFLOP/s sustained, source).  The timed region of this benchmark is tens of
+    milliseconds at full clocks -- the BURST figure is the denominator for its kernels."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         d = json.load(open(path))
-        return d['hbm_gbs'], d['bf16_tflops_sustained'], 'measured'
-    return 6650.0, 1400.0, 'fallback'
+        return d['hbm_gbs'], d['bf16_tflops'], d['bf16_tflops_sustained'], 'measured'
+    return 6650.0, 1590.0, 1400.0, 'fallback'
 
 
 class ClockSampler:
@@ -148,34 +161,47 @@ def host_threads():
     return n
 
 
-def cpu_forward_setup(sample_batch=BATCH):
+def cpu_forward_setup():
+    """The reference's CPU implementation of the workload, calibrated on the benchmark batch with fixed ranges:
+    the UNMODIFIED reference from baseline/_ref (kind "reference") when tools/install_reference.sh has installed
+    it, else the oracle port (kind "port").  -> (forward(ids, mask), ids, mask, calibration seconds, kind, what)"""
     from oracle.bert_oracle import OracleBert, random_bert_state_dict
     sd = random_bert_state_dict(seed=0)
-    m = OracleBert(sd, n_layers=12, n_heads=12, n_bits=8, n_bits_act=8, sym_acts=False)
     ids = synthetic_ids(1234)[0]
     mask = torch.ones_like(ids)
+    m, kind, what = None, 'port', 'oracle/bert_oracle.py: the reference op chain on torch CPU'
+    try:
+        from baseline import reference_arm
+        if reference_arm.available():
+            m = reference_arm.ReferenceBert(sd)
+            kind = 'reference'
+            what = ('unmodified reference (baseline/_ref: models/quantized_bert.py + quantization/*, its own public API; '
+                    'HF-4.1 container shim tests/hf41_shim.py)')
+    except Exception as e:                                  # noqa: BLE001
+        print(f'bench.py: reference arm unavailable ({e!r}); timing the oracle port', file=sys.stderr)
+        m = None
+    if m is None:
+        m = OracleBert(sd, n_layers=12, n_heads=12, n_bits=8, n_bits_act=8, sym_acts=False)
     with torch.no_grad():
         t0 = time.perf_counter()
         m(ids, mask)                 # calibration forward on the full batch (also caches the weights)
         t_cal = time.perf_counter() - t0
         m.fix_ranges()
-    return m, ids, mask, t_cal
+    return m, ids, mask, t_cal, kind, what
 
 
-def cpu_baseline(threads, budget_s=20.0):
-    """oracle port of the reference path on the host cores: calibrate on the full batch, fix the
-    ranges, then time fixed-range forwards of a bounded sample (the first rows of the same batch)."""
-    m, ids, mask, t_cal = cpu_forward_setup()
-    rows = BATCH
-    while rows > 1 and 2 * t_cal * rows / BATCH > budget_s:
-        rows //= 2
+def cpu_baseline(threads, n_timed=5):
+    """the reference on the host cores: calibrate on the full batch, fix the ranges, then the MEDIAN of
+    ``n_timed`` fixed-range forwards of the SAME full batch (B=32, T=128) after one warm-up forward."""
+    m, ids, mask, t_cal, kind, what = cpu_forward_setup()
     with torch.no_grad():
+        logits = m(ids, mask)        # warm-up
         ts = []
-        for _ in range(2):
+        for _ in range(n_timed):
             t0 = time.perf_counter()
-            logits = m(ids[:rows], mask[:rows])
+            logits = m(ids, mask)
             ts.append(time.perf_counter() - t0)
-    return rows * SEQ / statistics.median(ts), rows, logits
+    return BATCH * SEQ / statistics.median(ts), n_timed, logits, kind, what
 
 
 def cpu_qdq_baseline(threads, n=16 * 1024 * 1024, passes=5):
@@ -208,28 +234,37 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    m, ids, mask, t_cal = cpu_forward_setup()
-    rows = BATCH                     # bounded sample: keep the whole run within a few minutes
-    while rows > 1 and (args.steps + args.warmup) * t_cal * rows / BATCH > 150.0:
-        rows //= 2
+    m, ids, mask, t_cal, kind, what = cpu_forward_setup()
+    # every step is one forward of the SAME full batch (B=32, T=128) at every N; only if the host is so slow that
+    # the whole run would exceed ~5 minutes are the steps cut short (and the line says so)
+    steps, warmup = args.steps, args.warmup
     with torch.no_grad():
-        for _ in range(args.warmup):
-            m(ids[:rows], mask[:rows])
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            m(ids[:rows], mask[:rows])
-        dt = time.perf_counter() - t0
+        m(ids, mask)
+        t_fwd = time.perf_counter() - t0
+        budget = 300.0
+        if (steps + warmup) * t_fwd > budget:
+            steps = max(5, int(budget / t_fwd) - 1)
+            warmup = 1
+        for _ in range(max(warmup - 1, 0)):
+            m(ids, mask)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            m(ids, mask)
+            ts.append(time.perf_counter() - t0)
+    dt = sum(ts)
     # the CPU path does not shard: N "GPUs" of the reference arm are still one host
-    val = args.steps * rows * SEQ / dt
+    val = steps * BATCH * SEQ / dt
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'tokens/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': dt / steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': BATCH, 'seq_len': SEQ, 'parallelism': 'host-cpu'},
-        'cpu_baseline': {'value': val, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{args.steps} fixed-range forwards of the first {rows} of the 32 sequences '
-                                   '(T=128) after one full-batch calibration forward (oracle/bert_oracle.py: '
-                                   'the reference op chain on torch CPU)'},
+        'cpu_baseline': {'value': val, 'unit': 'tokens/s', 'cores': threads, 'kind': kind,
+                         'sample': f'{steps} fixed-range forwards of the full batch (32 x 128 tokens) after one '
+                                   f'full-batch calibration forward; median {statistics.median(ts) * 1e3:.0f} ms per forward; {what}',
+                         'steps_requested': args.steps},
         'e2e': {'value': val, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -367,6 +402,132 @@ def qdq_bwd_probe(ops, n=128 * 1024 * 1024, iters=10):
         return None
 
 
+def calibration_leg(dev, rank, world):
+    """BASELINE config 5 (every rank calls this): RoBERTa-base W8A8, MSE range estimation on the activations
+    (grid search, 100 candidates; the asymmetric two-sided sites take the reference's 2-D grid), ONE calibration
+    batch of 32 x 128 tokens PER RANK through ``utils.pass_data_for_range_estimation`` -- the loop that opts into
+    quantization/_dist.calibration_sync(): every estimator update all-reduces its statistics over NCCL, so all
+    ranks end with the ranges of the global batch.  Timed on the device, max over ranks; a first untimed pass on
+    the same model (ranges reset afterwards) takes module loading / allocator warm-up out of the number."""
+    from engine import configs
+    from quantization import _dist
+    from utils.utils import pass_data_for_range_estimation
+    import torch.distributed as dist
+    model, recipe = configs.build('roberta_w8a8_mse', dev)
+    ids = configs.synthetic_batches(model, recipe, 1, seed=4321 + rank)[0]
+    loader = [{'input_ids': ids, 'attention_mask': torch.ones_like(ids)}]
+
+    def one_pass():
+        with torch.no_grad():
+            pass_data_for_range_estimation(loader, model, act_quant=True, weight_quant=True, max_num_batches=1)
+
+    one_pass()                                     # warm-up (also fills the weight caches: weights calibrate once)
+    model.reset_act_ranges()
+    model.estimate_act_ranges()
+    _dist.stats(reset=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    secs = e0.elapsed_time(e1) * 1e-3
+    model.fix_ranges()
+    st = _dist.stats()
+    deltas = torch.cat([m.quantizer._delta.reshape(-1).float() for m in model.act_quantizers()])
+    identical = True
+    if world > 1:
+        t = torch.tensor([secs, wall], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs, wall = t.tolist()
+        gathered = [torch.empty_like(deltas) for _ in range(world)]
+        dist.all_gather(gathered, deltas)
+        identical = all(torch.equal(gathered[0], g) for g in gathered)
+    tokens = recipe.batch * recipe.seq * world
+    return {'workload': 'RoBERTa-base W8A8, activation ranges by MSE grid search (100 candidates), weights current_minmax; '
+                        'one 32 x 128 calibration batch per rank, statistics all-reduced inside the estimators',
+            'tokens_per_s': tokens / secs, 'seconds': secs, 'host_wall_seconds': wall, 'n_gpus': world,
+            'global_calibration_tokens': tokens, 'sites': len(model.act_quantizers()),
+            'allreduce_calls': st['calls'], 'allreduce_bytes': st['bytes'],
+            'collective': 'NCCL all-reduce (MAX on packed [-min, max]; SUM on fp64 loss arrays)' if world > 1 else 'none (one rank)',
+            'ranks_identical': bool(identical)}
+
+
+def other_config_legs(steps, warmup):
+    """BASELINE configs 3 and 4 on this GPU (N = 1 only): tools/run_config.py -- build, calibrate on two synthetic
+    batches (incl. the FP32 ranges pass for the PEG permutation), fix ranges, CUDA-graphed eval forward."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import run_config
+    out = {}
+    for name in ('bert_w8a8_peg', 'mobilebert_w4a8'):
+        try:
+            out[name] = run_config.run(name, steps, warmup)
+        except Exception as e:                              # noqa: BLE001  (a side leg must not take the headline down)
+            out[name] = {'error': repr(e)}
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_other_config(args):
+    """`--config NAME`: one of BASELINE configs 3 / 4 / 5 as the line of this run (single GPU unless it is the
+    calibration config, which shards over the ranks).  Same keys as the headline line where they apply."""
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    hbm_peak, tf_peak, tf_sustained, peak_kind = peaks()
+    if args.config == 'roberta_w8a8_mse':
+        if world > 1:
+            os.environ['NCCL_DEBUG'] = os.environ.get('TQ_NCCL_DEBUG', 'INFO')
+            torch.distributed.init_process_group('nccl', device_id=dev)
+        with ClockSampler(local) as clk:
+            c = calibration_leg(dev, rank, world)
+        if rank == 0:
+            emit({'metric': 'calibration tokens/sec RoBERTa-base W8A8 MSE range estimation', 'value': c['tokens_per_s'],
+                  'unit': 'tokens/s', 'n_gpus': world, 'steps': 1, 'warmup': 1, 'ms_per_step': c['seconds'] * 1e3,
+                  'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (MSE losses fp64)',
+                  'data': 'synthetic', 'config': {'workload': c['workload'], 'global_batch': 32 * world, 'seq_len': SEQ,
+                                                  'parallelism': f'dp{world} (calibration batches sharded, statistics all-reduced)'},
+                  'clocks': clk.summary(), 'calibration': c})
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import run_config
+    import tq_native
+    ops = tq_native.ops()
+    with ClockSampler(local) as clk:
+        r = run_config.run(args.config, args.steps, max(args.warmup, 3), profile=True)
+    prof = r.pop('kernel_profile', None) or {}
+    roof = None
+    if prof:
+        name, st = max(prof.items(), key=lambda kv: kv[1]['seconds'])
+        tensor = name in ('linear_qdq', 'attention')
+        ach = st['work'] / st['seconds'] / (1e12 if tensor else 1e9)
+        roof = {'kernel': name, 'bound': 'tensor' if tensor else 'hbm', 'achieved': ach, 'peak': tf_peak if tensor else hbm_peak,
+                'unit': 'TFLOP/s' if tensor else 'GB/s', 'frac': ach / (tf_peak if tensor else hbm_peak), 'traffic': None,
+                'launches_per_step': st['launches'], 'avg_launch_us': st['seconds'] / st['launches'] * 1e6,
+                'share_of_library_kernel_time': st['seconds'] / sum(v['seconds'] for v in prof.values()),
+                'peak_source': f'{peak_kind} (MEASURED_PEAKS.json)'}
+    emit({'metric': f'tokens/sec {args.config} seq{r["seq"]} b{r["batch"]}', 'value': r['tokens_per_s'], 'unit': 'tokens/s',
+          'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': r['ms_per_step'],
+          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'integer-grid tensor-core GEMMs, fp32 QDQ',
+          'data': 'synthetic', 'config': {'workload': args.config, 'global_batch': r['batch'], 'seq_len': r['seq'],
+                                          'forward': r['forward'], 'cuda_graph': r['cuda_graph']},
+          'gpu_launches': r['library_launches_per_step'] * args.steps, 'clocks': clk.summary(), 'roofline': roof,
+          'kernels': {k: {'ms_per_step': v['seconds'] * 1e3, 'launches': v['launches']} for k, v in prof.items()},
+          'detail': r})
+    del ops
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -375,18 +536,20 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
-        os.environ['NCCL_DEBUG'] = os.environ.get('TQ_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+        # NCCL's INFO log (communicator size, transports, NVLS) is the evidence that the ranks really talk: leave it
+        # on.  It goes to stderr -- fd 1 is redirected for the whole run (_guard_stdout), stdout carries one JSON line.
+        os.environ['NCCL_DEBUG'] = os.environ.get('TQ_NCCL_DEBUG', 'INFO')
         dist.init_process_group('nccl', device_id=dev)
     import tq_native
     ops = tq_native.ops()
-    hbm_peak, tf_peak, peak_kind = peaks()
+    hbm_peak, tf_peak, tf_sustained, peak_kind = peaks()
 
     model = build_model(dev)
     ids_host = synthetic_ids(1234 + rank)[0].pin_memory()
     mask_dev = torch.ones(BATCH, SEQ, dtype=torch.int64, device=dev)
     ids_dev = ids_host.to(dev)
     with torch.no_grad():
-        os.environ['TQ_DIST_CALIBRATION'] = '0'       # replicas calibrate on their own batch
+        # replicas calibrate on their own batch: no collective (the reduction is opt-in, quantization/_dist.py)
         model(ids_dev, mask_dev)                      # calibration batch: ranges + weight cache
         model.fix_ranges()
         for _ in range(2):
@@ -463,11 +626,20 @@ def run_ours(args):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             t_dev, t_e2e = t.tolist()
 
-        if rank != 0:
-            if world > 1:
-                torch.distributed.barrier()
-                torch.distributed.destroy_process_group()
-            return
+    # ---- BASELINE config 5: sharded calibration with the cross-rank all-reduce (every rank takes part) ----
+    calib = None
+    if os.environ.get('TQ_BENCH_CALIBRATION', '1') != '0':
+        try:
+            calib = calibration_leg(dev, rank, world)
+        except Exception as e:                              # noqa: BLE001
+            calib = {'error': repr(e)}
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+
+    with torch.no_grad():
 
         # ---- roofline of the dominant kernel (eager pass, events on the launching stream) ----
         torch.cuda.synchronize()
@@ -483,16 +655,25 @@ def run_ours(args):
     per_launch_s = st['seconds'] / st['launches']
     flops_kernels = ('linear_qdq', 'attention')
     if name in flops_kernels:
-        roof = {'kernel': 'tq_linear_qdq_bf16 / tq_linear_res_ln_qdq_bf16 (tcgen05 GEMM + fused QDQ / residual / LayerNorm epilogue)'
-                if name == 'linear_qdq' else 'tq_attention_qdq_bf16', 'bound': 'tensor',
-                'achieved': st['work'] / st['seconds'] / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s'}
+        roof = {'kernel': 'tq_linear_qdq_i8 / tq_linear_res_ln_qdq_i8 / tq_linear_qdq_bf16_o8 (tcgen05 GEMM + fused QDQ / GELU / residual / '
+                          'LayerNorm epilogue)' if name == 'linear_qdq' else 'tq_attention_qdq_i8', 'bound': 'tensor',
+                'achieved': st['work'] / st['seconds'] / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                'peak_kind': 'bf16 dense BURST (cuBLAS 8192^3, best of 10) -- the timed region is tens of ms at full clocks',
+                'frac_of_sustained_bf16_peak': st['work'] / st['seconds'] / 1e12 / tf_sustained}
+        if name == 'linear_qdq' and getattr(forward, 'i8', False):
+            # 2/3 of the GEMM flops of a layer run as kind::i8 (QKV, attention-out, FFN-out), whose pipe rate is 2x
+            # bf16 (tools/mainloop_probe_i8.py: 133 cycles per M128 x N256 x K32 MMA alone = K16 bf16): flop-weighted peak
+            share_i8 = forward.i8_flop_share()
+            roof['i8_flop_share'] = share_i8
+            roof['peak_i8_weighted'] = tf_peak / (1.0 - share_i8 / 2.0)
+            roof['frac_of_i8_weighted_peak'] = roof['achieved'] / roof['peak_i8_weighted']
     else:
         roof = {'kernel': name, 'bound': 'hbm', 'achieved': st['work'] / st['seconds'] / 1e9,
                 'peak': hbm_peak, 'unit': 'GB/s'}
     roof['frac'] = roof['achieved'] / roof['peak']
     roof['traffic'] = None
     try:                      # DRAM bytes per launch of that kernel class from the committed ncu --set full capture
-        with open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
             tr = json.load(f)
         if name in tr:
             roof['traffic'] = tr[name]['dram_bytes_per_launch']
@@ -504,20 +685,23 @@ def run_ours(args):
     roof['avg_launch_us'] = per_launch_s * 1e6
     roof['share_of_library_kernel_time'] = st['seconds'] / sum(v['seconds'] for v in prof.values())
 
-    cpu = cpu_qdq = None
+    cpu = cpu_qdq = others = None
     if world == 1:
+        others = other_config_legs(10, 3) if os.environ.get('TQ_BENCH_OTHER_CONFIGS', '1') != '0' else None
         threads = host_threads()
-        cpu_val, rows, cpu_logits = cpu_baseline(threads)
-        cpu = {'value': cpu_val, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
-               'sample': f'1 full-batch calibration forward + 2 timed fixed-range forwards of the first {rows} of '
-                         'the 32 sequences (oracle/bert_oracle.py, torch CPU, reference op chain)',
-               'logit_max_abs_diff_vs_gpu': float((cpu_logits - static_logits[:rows].float().cpu()).abs().max())}
+        cpu_val, n_timed, cpu_logits, cpu_kind, cpu_what = cpu_baseline(threads)
+        cls_step = float(model.classifier.activation_quantizer.quantizer.scale.reshape(-1)[0])
+        cpu = {'value': cpu_val, 'unit': 'tokens/s', 'cores': threads, 'kind': cpu_kind,
+               'sample': f'1 full-batch calibration forward, 1 warm-up, median of {n_timed} timed fixed-range forwards of the '
+                         f'full batch (32 x 128 tokens); {cpu_what}',
+               'logit_max_abs_diff_vs_gpu': float((cpu_logits - static_logits.float().cpu()).abs().max()),
+               'logit_diff_vs_gpu_in_classifier_steps': float((cpu_logits - static_logits.float().cpu()).abs().max()) / cls_step}
         cpu_qdq = cpu_qdq_baseline(threads)
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16 integer-grid operands, fp32 accumulate / fp32 QDQ',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPE,
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'seq_len': SEQ,
                    'parallelism': f'dp{world} (independent replicas)',
@@ -542,6 +726,8 @@ def run_ours(args):
                                     'shape': '128Mi fp32 (x, grad_y in; grad_x + range gradients out)',
                                     'bytes_per_elem': 12},
         'kernels': {k: {'ms_per_step': v['seconds'] * 1e3, 'launches': v['launches']} for k, v in prof.items()},
+        'calibration': calib,
+        'other_configs': others,
     }
     emit(line)
     if world > 1:
@@ -578,9 +764,14 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='bert_w8a8_asym',
+                    choices=['bert_w8a8_asym', 'bert_w8a8_peg', 'mobilebert_w4a8', 'roberta_w8a8_mse'],
+                    help='BASELINE configuration (default: the headline, configs[1]); the others print their own line')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config != 'bert_w8a8_asym':
+        run_other_config(args)
     else:
         run_ours(args)
 

@@ -33,6 +33,7 @@ class Site:
         self.delta = self.zero_float = None
         self.signed = None
         self.fixed = False
+        self.record = None          # (dict, key): tools/parity_fullsize.py captures the site's output
 
     def _set_range(self, x_min, x_max):
         x_min = torch.min(x_min, torch.zeros_like(x_min))                      # quantizers.py:258
@@ -66,15 +67,19 @@ class Site:
             zero_point = torch.clamp(torch.round(self.zero_float), int_min, int_max)   # :151-152
         x_int = torch.round(x / scale) + zero_point                            # :184
         x_int = torch.clamp(x_int, int_min, int_max)                           # :185
-        return scale * (x_int - zero_point)                                    # :209
+        y = scale * (x_int - zero_point)                                       # :209
+        if self.record is not None:
+            self.record[0][self.record[1]] = y
+        return y
 
 
 class OracleBert:
     """Functional BERT-for-sequence-classification over a HuggingFace-named state dict."""
 
     def __init__(self, sd, n_layers, n_heads, n_bits=8, n_bits_act=8, sym_acts=False, eps_ln=1e-12,
-                 act_estimator='running_minmax'):
+                 act_estimator='running_minmax', device=None):
         self.sd = {k: v.float() for k, v in sd.items()}
+        self.device = device        # None: host CPU (the baseline); a CUDA device runs the same op chain on cuBLAS
         self.L, self.H = n_layers, n_heads
         self.n_bits, self.eps_ln = n_bits, eps_ln
         mk = lambda: Site(n_bits_act, sym_acts, act_estimator)
@@ -112,7 +117,7 @@ class OracleBert:
         e = F.embedding(ids, self._w('bert.embeddings.word_embeddings.weight')) + \
             F.embedding(tt, self._w('bert.embeddings.token_type_embeddings.weight'))
         e = A['e_tok'](e)
-        e = e + F.embedding(torch.arange(T).unsqueeze(0), self._w('bert.embeddings.position_embeddings.weight'))
+        e = e + F.embedding(torch.arange(T, device=self.device).unsqueeze(0), self._w('bert.embeddings.position_embeddings.weight'))
         e = A['e_pos'](e)
         h = A['e_ln'](self._ln(e, 'bert.embeddings.LayerNorm'))
         ext = None if mask is None else (1.0 - mask[:, None, None, :].float()) * -10000.0

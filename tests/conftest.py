@@ -23,6 +23,21 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a machine without a GPU (or without the built library) skips the gpu-marked tests
+    instead of failing them; on a GPU box with the library they always run -- and fail loudly if the CUDA
+    path is broken."""
+    import torch
+    lib = os.path.join(PKG, 'lib', 'libtq_b200.so')
+    if torch.cuda.is_available() and os.path.exists(os.environ.get('TQ_B200_LIB', lib)):
+        return
+    why = 'no CUDA device visible' if not torch.cuda.is_available() else f'{lib} not built'
+    skip = pytest.mark.skip(reason=f'gpu test: {why}')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
 class Golden:
     def __init__(self):
         with open(os.path.join(GOLDEN, 'manifest.json')) as f:

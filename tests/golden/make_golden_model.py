@@ -23,9 +23,10 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 TESTS = os.path.dirname(HERE)
-REF = os.environ.get('TQ_REFERENCE', '/root/reference')
 sys.dont_write_bytecode = True
 sys.path.insert(0, TESTS)
+from reference_path import reference_root  # noqa: E402
+REF = reference_root()
 
 
 def load_by_path(name, path):

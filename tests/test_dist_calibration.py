@@ -73,8 +73,11 @@ def _worker(rank, world, port, q):
     try:
         B = _batches()
         shard = slice(rank * 4, rank * 4 + 4)           # batch dim 8 split over 2 ranks
-        res = _calibrate(_make_managers(), B, shard)
-        q.put((rank, res))
+        from quantization import _dist
+        local = _calibrate(_make_managers(), B, shard)  # outside calibration_sync(): rank-local, no collective
+        with _dist.calibration_sync():
+            res = _calibrate(_make_managers(), B, shard)
+        q.put((rank, res, local, _dist.stats()))
     finally:
         dist.destroy_process_group()
 
@@ -89,7 +92,13 @@ def test_two_rank_calibration_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=240) for _ in range(2))
+    raw = [q.get(timeout=240) for _ in range(2)]
+    got = {r[0]: r[1] for r in raw}
+    local = {r[0]: r[2] for r in raw}
+    # opt-in: without the context the estimators never reduce (the two shards give different ranges) ...
+    assert not np.array_equal(local[0]['running'], local[1]['running'])
+    # ... and inside it every estimator update issued collectives
+    assert all(r[3]['calls'] > 0 and r[3]['bytes'] > 0 for r in raw)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

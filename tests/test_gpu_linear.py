@@ -135,6 +135,7 @@ def test_unsupported_shapes_are_rejected():
 
 
 @pytest.mark.parametrize('act', [None, nn.GELU, nn.ReLU, nn.Tanh])
+@torch.no_grad()                       # the fused kernel is the inference path: it declines while autograd records
 def test_quant_linear_fused_vs_unfused(act):
     """QuantLinear through the module API: fused tcgen05 path vs the three-step path (library fp32
     GEMM + activation + QDQ kernel).  <= 1 output step, < 0.2 % of elements differ."""
@@ -176,3 +177,26 @@ def test_quant_linear_fused_vs_unfused(act):
         fused_linear.ENABLED = True
     d = (y_s - y_su).abs()
     assert d.max().item() <= step * 1.001 and (d > step * 1e-3).float().mean().item() < 2e-3
+
+
+def test_fused_linear_declines_while_autograd_records():
+    """eval-mode forward with grad enabled (sensitivity / Fisher passes, eval-mode fine-tuning): the output must
+    carry a grad_fn that reaches the weight -- the fused kernel would cut the graph silently."""
+    from quantization.autoquant_utils import QuantLinear
+    from quantization.quantizers import QMethods
+    torch.manual_seed(0)
+    lin = QuantLinear(128, 64, bias=True, method=QMethods.symmetric_uniform, act_method=QMethods.asymmetric_uniform,
+                      n_bits=8, n_bits_act=8).to(DEV)
+    lin.quantized()
+    lin.eval()
+    x = torch.randn(4, 16, 128, device=DEV)
+    with torch.no_grad():
+        lin(x)
+    lin.fix_ranges()
+    lin.cached_params = None
+    y = lin(x)
+    assert y.grad_fn is not None
+    y.sum().backward()
+    assert lin.weight.grad is not None and lin.weight.grad.abs().sum().item() > 0
+    with torch.no_grad():
+        assert lin(x).grad_fn is None

@@ -58,3 +58,19 @@ def test_mobilebert_caller_matches_reference_cpu(name, monkeypatch):
     assert n == int(G[f'{name}.n_quantizers'])
     assert np.array_equal(logits.numpy(), G[f'{name}.logits'])
     assert np.array_equal(hidden.numpy(), G[f'{name}.last_hidden'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', list(CONFIGS))
+def test_mobilebert_caller_matches_reference_gpu(name):
+    """the same caller on the CUDA back-end (QuantNoNorm's uncached weight / bias QDQs, W4 grids, ReLU and
+    bottleneck GEMMs on tcgen05): GEMM tolerance of DESIGN.md section 3"""
+    model, logits, hidden = run(name, 'cuda')
+    n = sum(1 for m in model.modules() if getattr(m, 'quantizer', None) is not None and m.quantizer.is_initialized)
+    assert n == int(G[f'{name}.n_quantizers'])
+    ref_logits, ref_hidden = G[f'{name}.logits'], G[f'{name}.last_hidden']
+    step = float(model.classifier.activation_quantizer.quantizer.delta.max())
+    assert np.abs(logits.cpu().numpy() - ref_logits).max() <= 3 * step + 1e-6
+    hstep = float((ref_hidden.max() - ref_hidden.min()) / 255.0)
+    dh = np.abs(hidden.cpu().numpy() - ref_hidden)
+    assert dh.max() <= 6 * hstep and (dh > 0.5 * hstep).mean() < 0.05

@@ -14,7 +14,8 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 
 from oracle import fakequant_oracle as O
 
-REF = os.environ.get('TQ_REFERENCE', '/root/reference')
+from reference_path import reference_root
+REF = reference_root()
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'quantization')),
                                 reason='reference checkout not present')
 

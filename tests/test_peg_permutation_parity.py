@@ -22,7 +22,8 @@ from conftest import GOLDEN, PKG
 GP = np.load(os.path.join(GOLDEN, 'bert_tiny_pegp.npz'))
 GW = np.load(os.path.join(GOLDEN, 'bert_tiny.npz'))
 NAME = 'w8a8_pegp4'
-REF = os.environ.get('TQ_REFERENCE', '/root/reference')
+from reference_path import reference_root
+REF = reference_root()
 
 
 @pytest.fixture()

@@ -18,7 +18,8 @@ from conftest import GOLDEN, PKG
 
 G = np.load(os.path.join(GOLDEN, 'bert_tiny_quant_dict.npz'))
 GW = np.load(os.path.join(GOLDEN, 'bert_tiny.npz'))
-REF = os.environ.get('TQ_REFERENCE', '/root/reference')
+from reference_path import reference_root
+REF = reference_root()
 NAMES = ['mp16_ffn', 'peg_ffn', 'mixed']
 
 

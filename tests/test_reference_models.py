@@ -18,7 +18,8 @@ import torch
 import tq_native
 from conftest import GOLDEN, PKG
 
-REF = os.environ.get('TQ_REFERENCE', '/root/reference')
+from reference_path import reference_root
+REF = reference_root()
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'models')),
                                 reason='reference checkout not present')
 

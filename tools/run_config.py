@@ -24,7 +24,37 @@ from engine import configs  # noqa: E402
 import tq_native  # noqa: E402
 
 
-def run(name, steps, warmup, use_graph=True, device='cuda:0', tiny=False, batch=None, seq=None):
+def _profile_live(forward, ids, mask, ops, reps=5):
+    """per-kernel-class device time of one eager forward: every call of the library is re-issued `reps` times
+    between two CUDA events right after it ran (the kernels are idempotent) -- kernel time, not launch overhead"""
+    orig = ops._run
+    agg = {}
+
+    def timed(name, work, kernels, fn, *args):
+        orig(name, work, kernels, fn, *args)
+        fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn(*args)
+        e1.record()
+        a = agg.setdefault(name, [[], 0.0, 0])
+        a[0].append((e0, e1))
+        a[1] += work
+        a[2] += 1
+
+    ops._run = timed
+    try:
+        with torch.no_grad():
+            forward(ids, mask)
+        torch.cuda.synchronize()
+    finally:
+        ops._run = orig
+    return {k: {'seconds': sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / reps, 'work': work, 'launches': n}
+            for k, (evs, work, n) in agg.items()}
+
+
+def run(name, steps, warmup, use_graph=True, device='cuda:0', tiny=False, batch=None, seq=None, profile=False):
     """``device`` / ``tiny`` / ``batch`` / ``seq`` exist for the CPU dry run of this tool in the test-suite (oracle
     back-end injected by the test, wall-clock timing); on a GPU the defaults are the BASELINE shapes."""
     dev = torch.device(device)
@@ -83,7 +113,11 @@ def run(name, steps, warmup, use_graph=True, device='cuda:0', tiny=False, batch=
         module_logits = model(ids, mask)
         out_step = float(model.classifier.activation_quantizer.quantizer.scale.reshape(-1)[0])
         vs_module = float((out.float() - module_logits.float()).abs().max())
-    return dict(config=name, forward=kind, batch=recipe.batch, seq=recipe.seq, ms_per_step=ms,
+        prof = None
+        if profile and on_gpu:
+            prof = _profile_live(forward, ids, mask, ops)
+    extra = {'kernel_profile': prof} if prof is not None else {}
+    return dict(extra, config=name, forward=kind, batch=recipe.batch, seq=recipe.seq, ms_per_step=ms,
                 tokens_per_s=recipe.batch * recipe.seq / ms * 1e3, library_launches_per_step=launches,
                 calibration_s=t_cal, cuda_graph=use_graph, logits_finite=bool(torch.isfinite(out).all()),
                 graph_equals_eager=bool(torch.equal(out, ref)) if use_graph else None,

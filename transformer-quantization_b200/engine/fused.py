@@ -335,6 +335,20 @@ class FusedBertEngine:
 
     __call__ = forward
 
+    def i8_flop_share(self):
+        """share of the GEMM flops of one forward that runs on kind::i8 (bench.py: flop-weighted tensor peak)"""
+        if not self.i8:
+            return 0.0
+        i8 = bf = 0
+        for d in self.layers:
+            for key in ('wqkv', 'wg', 'wh'):
+                i8 += d[key].N * d[key].K
+            if self.ffn_in_bf16:
+                bf += d['wf'].N * d['wf'].K
+            else:
+                i8 += d['wf'].N * d['wf'].K
+        return i8 / float(i8 + bf)
+
     def hidden_states(self):
         """dequantized output of the last encoder block of the most recent forward (for tests)"""
         z = self.layers[-1]['z'].q

@@ -97,14 +97,27 @@ def _weight_grid(layer, weight_q):
     return w_ctr, spec, k
 
 
+def _wants_grad(layer, weight, bias):
+    if weight.requires_grad or (bias is not None and bias.requires_grad) or layer.weight.requires_grad:
+        return True
+    for mgr in (layer.weight_quantizer, layer.activation_quantizer):
+        qz = getattr(mgr, 'quantizer', None)
+        for name in ('_delta', '_zero_float'):
+            t = getattr(qz, name, None) if qz is not None else None
+            if torch.is_tensor(t) and t.requires_grad:
+                return True
+    return False
+
+
 def try_fused(layer, x, weight, bias):
     """Fused QuantLinear forward or None.  ``weight`` is what get_params() returned."""
     if not ENABLED or layer.training or not layer._quant_w or not x.is_cuda or x.dtype != torch.float32:
         return None
-    if torch.is_grad_enabled() and x.requires_grad:
-        return None                                # the input is part of an autograd graph: three-step path
-    # (an eval-mode forward does not build a graph for the layer's own parameters; QAT runs in train()
-    # mode, AdaRound's soft targets are excluded in _weight_grid)
+    if torch.is_grad_enabled() and (x.requires_grad or _wants_grad(layer, weight, bias)):
+        # the input, the layer's parameters or a learnable range is part of an autograd graph (eval-mode
+        # fine-tuning, sensitivity / Fisher passes, a first layer behind frozen embeddings): the fused kernel
+        # returns a tensor without grad_fn, so the three-step path must build the graph like the reference does
+        return None
     act = _act_code(layer.activation_function)
     if act is None:
         return None

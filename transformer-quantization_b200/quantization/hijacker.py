@@ -19,6 +19,7 @@ import copy
 
 from torch import nn
 
+from quantization import _dist
 from quantization.base_quantized_classes import QuantizedModule
 from quantization.quantization_manager import QuantizationManager
 from quantization.range_estimators import RangeEstimators
@@ -73,7 +74,8 @@ class QuantizationHijacker(QuantizedModule):
             return self.cached_params
         weight, bias = self.get_weight_bias()
         if self._quant_w:
-            weight = self.weight_quantizer(weight)
+            with _dist.local():                   # weights are replicated: their estimators never all-reduce
+                weight = self.weight_quantizer(weight)
         if use_cache and self._caching and self.cached_params is None:
             # the kernel output is already a fresh fp32 device tensor; copy only what aliases the
             # parameters so later in-place edits of them do not leak into the cache

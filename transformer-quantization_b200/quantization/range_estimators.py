@@ -411,12 +411,13 @@ class MSE_Estimator(RangeEstimatorBase):
         data = data.detach()
         t = self._grid_tables(data.device)
         rows = data.reshape(len(data), -1) if self.per_channel else data.reshape(1, -1)
+        batch = torch.zeros(rows.shape[0], t['n'], dtype=torch.float64, device=data.device)
+        for ch in range(rows.shape[0]):
+            tq_native.ops().mse_sse(rows[ch], t['cand'], t['n'], batch[ch])
+        batch = _dist.allreduce_sum(batch)          # ONE collective for all channels
         for ch in range(rows.shape[0]):
             flat = self._loss_dev[ch].view(-1)
-            batch = torch.zeros(t['n'], dtype=torch.float64, device=data.device)
-            tq_native.ops().mse_sse(rows[ch], t['cand'], t['n'], batch)
-            batch = _dist.allreduce_sum(batch)
-            flat[t['lead']:] += batch
+            flat[t['lead']:] += batch[ch]
             xmin, xmax, _ = tq_native.ops().mse_argmin(flat, t['cxmin'], t['cxmax'])
             self.current_xmin[ch:ch + 1] = xmin
             self.current_xmax[ch:ch + 1] = xmax

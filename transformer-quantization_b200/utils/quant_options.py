@@ -5,6 +5,8 @@ reference's utils/quant_click_options.py for programmatic callers (the click dec
 DotDicts with the reference's option names and defaults (quant_click_options.py:50-108, 134-198, 200-229,
 231-352; ``--qmethod`` is a required option there, here it defaults to ``symmetric_uniform``); ``make_qparams(config)`` turns them into the keyword arguments every ``Quantized*`` class of this
 package takes (reference :356-380)."""
+import copy
+
 from quantization.quantizers import QMethods
 from quantization.range_estimators import OptMethod, RangeEstimators
 from utils.utils import DotDict
@@ -24,7 +26,7 @@ def quant_config(**overrides):
     unknown = set(overrides) - known
     if unknown:
         raise TypeError(f'unknown quantization option(s): {sorted(unknown)}')
-    pick = lambda defaults: {k: overrides.get(k, v) for k, v in defaults.items()}     # noqa: E731
+    pick = lambda defaults: {k: overrides.get(k, copy.deepcopy(v)) for k, v in defaults.items()}     # noqa: E731 (own copy of mutable defaults)
     config = DotDict()
     config.quant = DotDict(pick(_QUANT_DEFAULTS))
     config.quant.qmethod_act = config.quant.qmethod_act or config.quant.qmethod
