@@ -92,7 +92,7 @@ def test_engine_stages_teacher_forced(setup):
             kind = ('attention' if stage.startswith('attention') else
                     'layernorm' if ('ln_' in stage or 'embed' in stage) else 'gemm')
             worst[kind] = max(worst.get(kind, 0.0), rate)
-            assert mx <= 1.0 + 1e-6, (li, stage, mx)
+            assert mx <= 1.001, (li, stage, mx)          # one step (the ratio itself is computed in floating point)
             assert rate <= BUDGET[kind], (li, stage, rate)
     assert set(worst) == {'gemm', 'layernorm', 'attention'}
 

@@ -446,6 +446,7 @@ struct EpiArgs {
     float* tile_minmax;     // optional calibration side reduction (ordered-int encoded, 2 words)
     long long* trace;       // optional: clock64 timeline of CTA 0 (16 slots), for tools/trace_linear.py
     long long* trace_all;   // optional: {globaltimer start, end, smid, clock64 span} per CTA (tools/trace_ctas.py)
+    long long* trace_tiles; // optional: per-tile clock64 stamps of CTA 0, [8 tiles][8 slots] (tools/trace_tiles.py)
     // residual branch (attention-output / FFN-output blocks of the encoder, reference
     // models/quantized_bert.py:238-245, 264-277):  y = Q2( dequant(Q1(linear)) + res_scale * res_ctr )
     const __nv_bfloat16* res_ctr;   // [M, N] centred integer grid of the residual input, or null
@@ -464,6 +465,10 @@ struct EpiArgs {
 };
 
 #define TQ_TRACE(slot) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[slot] = clock64(); } while (0)
+// per-tile stamps of CTA 0: slot 0 params start, 1 params done, 2 accumulator ready, 3 epilogue done,
+// 4 MMA got a free accumulator, 5 first operands landed, 6 MMAs issued, 7 producer issued its last load
+#define TQ_TTRACE(tile_no, slot) do { if (ep.trace_tiles != nullptr && blockIdx.x == 0 && (tile_no) < 8) \
+        ep.trace_tiles[(tile_no) * 8 + (slot)] = clock64(); } while (0)
 
 
 // ---- epilogue of one accumulator tile ---------------------------------------------------------------
@@ -477,7 +482,7 @@ struct EpiArgs {
 template <int BN, int ACT, bool PERCOL, bool RES, bool I8>
 __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* params, uint32_t tmem_tile, int third,
                                               int64_t row, bool row_ok, int64_t n0, int64_t N, float res_scale,
-                                              float res_zp, float qlo, uint32_t tfull, uint32_t tphase) {
+                                              float res_zp, float qlo, uint32_t tfull, uint32_t tphase, int tno) {
     constexpr int HP = BN / 2;
     const float4* P = reinterpret_cast<const float4*>(params);
     QReg q1, q2;
@@ -504,6 +509,7 @@ __device__ __forceinline__ void epi_tile_fast(const EpiArgs& ep, const float* pa
     mbar_wait(tfull, tphase);
     tc_fence_after();
     if (threadIdx.x == 0) TQ_TRACE(8);
+    if (threadIdx.x == 0) TQ_TTRACE(tno, 2);
     uint32_t held[4] = {0u, 0u, 0u, 0u};
     const bool wide8 = I8 && ((((uintptr_t)ep.y_u8) & 31u) == 0) && (N & 31) == 0;
 #pragma unroll 1
@@ -635,7 +641,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <int BN, bool FAST, bool I8>
 __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params, uint32_t tmem_tile, int third, int quarter,
                                                 int lane, int64_t row, bool row_ok, int64_t n0, int64_t N,
-                                                float res_scale, float res_zp, uint32_t tfull, uint32_t tphase) {
+                                                float res_scale, float res_zp, uint32_t tfull, uint32_t tphase, int tno) {
     constexpr int HP = BN / 2;
     const float4* P = reinterpret_cast<const float4*>(params);
     float* part = params + 16 * BN;                    // [2][3][BM] lane partials (sum | squared deviations)
@@ -669,6 +675,7 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
     mbar_wait(tfull, tphase);
     tc_fence_after();
     if (threadIdx.x == 0) TQ_TRACE(8);
+    if (threadIdx.x == 0) TQ_TTRACE(tno, 2);
 
     // ---- loop 1 ----
     float s = 0.0f;
@@ -980,7 +987,8 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (lane == 0) {
             int stage = p_stage;
             uint32_t phase = p_phase;
-            for (int64_t t = tile0; t < tiles; t += tile_step) {
+            int tno = 0;
+            for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
                 const int32_t m0 = (int32_t)((t / n_tiles) * (BM * CTAS) + cta_rank * BM);
                 const int32_t n0 = (int32_t)((t % n_tiles) * BN + cta_rank * C::kBRows);
                 for (int kb = (t == tile0 ? p_pre : 0); kb < num_kb; ++kb) {
@@ -994,6 +1002,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (++stage == ring) { stage = 0; phase ^= 1u; }
                 }
                 TQ_TRACE(3);
+                TQ_TTRACE(tno, 7);
             }
             if (CTAS == 2) {
                 // tail: every slot handed out has been consumed -- no multicast arrival may target
@@ -1023,13 +1032,16 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t t = tile0; t < tiles; t += tile_step) {
+            int tno = 0;
+            for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
+                TQ_TTRACE(tno, 4);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     if (kb == 0) TQ_TRACE(4);
+                    if (kb == 0) TQ_TTRACE(tno, 5);
                     if (kb == 1) TQ_TRACE(5);
                     tc_fence_after();
                     const uint32_t sa = base + stage * C::kStageBytes;
@@ -1047,6 +1059,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 tc_commit<CTAS>(tfull_bar(acc));               // accumulator complete -> epilogue
                 TQ_TRACE(6);
+                TQ_TTRACE(tno, 6);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -1087,9 +1100,11 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         float run_min = __int_as_float(0x7f800000), run_max = __int_as_float(0xff800000);
-        for (int64_t t = tile0; t < tiles; t += tile_step) {
+        int tno = 0;
+        for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
             const int64_t m0 = (t / n_tiles) * (BM * CTAS) + cta_rank * BM, n0 = (t % n_tiles) * BN;
             asm volatile("bar.sync 1, 384;" ::: "memory");      // previous tile's parameter reads done
+            if (et == 0) TQ_TTRACE(tno, 0);
             int need_exact = 0;
             if (LNF) {
                 float lo, hi;
@@ -1152,6 +1167,7 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 : "r"(need_exact)
                 : "memory");
             if (et == 0) TQ_TRACE(7);
+            if (et == 0) TQ_TTRACE(tno, 1);
             const int64_t row = m0 + quarter * 32 + lane;
             const bool row_ok = row < M;
             const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
@@ -1160,22 +1176,23 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int mode = !fast ? -1 : (has_res ? 4 : ep.act_fn * 2) + (percol ? 1 : 0);
             const float out_lo = has_res ? q2lo : qlo;           // lower edge of the integer grid that is stored
             if (LNF) {
-                if (exact) epi_tile_res_ln<BN, false, I8>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, res_zp, tf, acc_phase);
-                else epi_tile_res_ln<BN, true, I8>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, res_zp, tf, acc_phase);
+                if (exact) epi_tile_res_ln<BN, false, I8>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, res_zp, tf, acc_phase, tno);
+                else epi_tile_res_ln<BN, true, I8>(ep, params, tmem_tile, third, quarter, lane, row, row_ok, n0, N, res_scale, res_zp, tf, acc_phase, tno);
             } else
             switch (mode) {                                      // warp-uniform
-                case 0: epi_tile_fast<BN, 0, false, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
-                case 1: epi_tile_fast<BN, 0, true, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
-                case 2: epi_tile_fast<BN, 1, false, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
-                case 3: epi_tile_fast<BN, 1, true, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
-                case 4: epi_tile_fast<BN, 0, false, true, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
-                case 5: epi_tile_fast<BN, 0, true, true, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase); break;
+                case 0: epi_tile_fast<BN, 0, false, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase, tno); break;
+                case 1: epi_tile_fast<BN, 0, true, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase, tno); break;
+                case 2: epi_tile_fast<BN, 1, false, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase, tno); break;
+                case 3: epi_tile_fast<BN, 1, true, false, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase, tno); break;
+                case 4: epi_tile_fast<BN, 0, false, true, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase, tno); break;
+                case 5: epi_tile_fast<BN, 0, true, true, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, tf, acc_phase, tno); break;
                 default:
                     epi_tile_generic<BN, I8>(ep, params, tmem_tile, third, row, row_ok, n0, N, res_scale, res_zp, out_lo, has_q,
                                              has_res, tf, acc_phase, run_min, run_max);
                     break;
             }
             if (et == 0) TQ_TRACE(9);
+            if (et == 0) TQ_TTRACE(tno, 3);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -1411,6 +1428,9 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
     ep.trace_all = (ws != nullptr && ws_bytes >= (16 + 4 * 160) * sizeof(long long))
                        ? reinterpret_cast<long long*>(ws) + 16
                        : nullptr;
+    ep.trace_tiles = nullptr;
+    if (const char* e = getenv("TQ_LINEAR_TRACE_TILES"))          // tools/trace_tiles.py: device buffer of 64 int64
+        ep.trace_tiles = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
     ep.res_ctr = reinterpret_cast<const __nv_bfloat16*>(res_ctr_bf16);
     ep.res_q = res_q;
     ep.out2_q = out2_q;
