@@ -53,8 +53,9 @@ typedef struct tq_qspec {
 } tq_qspec;
 
 /* ---- library info ------------------------------------------------------------------------- */
-int         tq_version(void);              /* ABI version: 1 = inference path; 2 (current) adds the training-time
-                                              * entry points (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32 */
+int         tq_version(void);              /* ABI version: 1 = inference path; 2 adds the training-time entry points
+                                              * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 (current) adds
+                                              * tq_linear_seg_qdq_i8 */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
 
@@ -205,7 +206,8 @@ int tq_linear_res_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const
  *     z = ln_q( LayerNorm(y; ln_gamma_q, ln_beta, ln_eps) )
  * Only z leaves the chip (z fp32 and / or z_ctr bf16 centred grid).  The CTAs that cover one 128-row
  * panel form a thread-block cluster and exchange the row statistics through distributed shared
- * memory (two-pass mean / variance in fp32).  out_q, out2_q and ln_q are per-tensor; the weight
+ * memory (exact integer sums of the centred integers -> mean / variance in fp64, rounded once: independent of
+ * the tiling and of the summation order).  out_q, out2_q and ln_q are per-tensor; the weight
  * quantizer may be per-channel.  N must be a multiple of 128, 192 or 256 with at most 8 tiles per
  * row panel, else TQ_EUNSUPPORTED (callers run tq_linear_res_qdq_bf16 + tq_ln_qdq_bf16). */
 int tq_linear_res_ln_qdq_bf16(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias,
@@ -233,6 +235,17 @@ int tq_linear_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum
 int tq_linear_qdq_bf16_o8(const void* a_ctr_bf16, const void* w_ctr_bf16, const float* bias, void* y_i8,
                           int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q, int64_t w_q_params,
                           int32_t act_fn, tq_qspec out_q, int64_t out_q_params, void* stream);
+/* The engine form of tq_linear_qdq_i8: the weight and output quantizers are given per SEGMENT of output columns
+ * (w_q and out_q carry nseg parameter slots; segment j covers columns [j * N / nseg, (j + 1) * N / nseg)) -- one
+ * segment for a plain hijacked nn.Linear, three for the fused Q | K | V projection (reference
+ * models/quantized_bert.py:135-151: three QuantLinear, each with its own per-tensor quantizers).  Same arithmetic
+ * as tq_linear_qdq_i8 (bit-identical outputs), leaner kernel: a parameter warp resolves the quantizers once and
+ * streams {bias, zero-point correction} per tile, the epilogue has no per-tile set-up and no run-time format
+ * switches.  Exactly one of y_ctr_bf16 / y_i8; act_fn 0 (none) or 1 (GELU); K % 128 == 0, (N / nseg) a multiple of
+ * 128, 192 or 256, outputs 32-byte aligned; else TQ_EUNSUPPORTED / TQ_EALIGN (callers use tq_linear_qdq_i8). */
+int tq_linear_seg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
+                         void* y_ctr_bf16, void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q,
+                         tq_qspec w_q, tq_qspec out_q, int32_t nseg, int32_t act_fn, void* stream);
 int tq_linear_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
                             float* z, void* z_ctr_bf16, void* z_i8, int64_t M, int64_t N, int64_t K,
                             tq_qspec a_q, tq_qspec w_q, int64_t w_q_params, tq_qspec out_q,

@@ -387,3 +387,82 @@ def test_engine_matches_module_path(n_bits, use_mask):
         torch.cuda.synchronize()
         assert torch.equal(out, eager)
         assert n_launch == 1 + per_layer * 2 + 2
+
+
+# ---- lean int8 kernels (tq_linear_seg_qdq_i8, lean form of tq_linear_res_ln_qdq_i8) ------------------------------
+@pytest.mark.parametrize('M,N,K,nseg,act', [(4096, 2304, 768, 3, 0), (4096, 3072, 768, 1, 1), (384, 768, 256, 3, 0),
+                                            (300, 384, 128, 1, 1), (200, 576, 384, 3, 1), (128, 256, 3072, 1, 0)])
+def test_linear_seg_i8_matches_general_kernel(M, N, K, nseg, act):
+    """per-segment quantizers + parameter warp + 32-column epilogue slices: same operation chain as the general
+    int8 kernel with per-column parameters -> bit-identical bytes / bf16 grids"""
+    ops = tq_native.ops()
+    cse = _i8_case(ops, M, N, K, seed=M + N + K + nseg)
+    seg = N // nseg
+    pre = cse['pre']
+    # per-segment output quantizers (asymmetric) and per-segment weight scales
+    o_d = np.zeros(nseg, np.float32)
+    o_z = np.zeros(nseg, np.float32)
+    for j in range(nseg):
+        blk = pre[:, j * seg:(j + 1) * seg]
+        d, z = O.asym_set_quant_range(float(blk.min()) * (1 + 0.1 * j), float(blk.max()), 8)
+        o_d[j], o_z[j] = d, z
+    od_t, oz_t = T_(o_d), T_(o_z)
+    o_seg = ops.spec(od_t, oz_t, None, 8)
+    od_c, oz_c = T_(np.repeat(o_d, seg)), T_(np.repeat(o_z, seg))
+    o_col = ops.spec(od_c, oz_c, None, 8)
+    w_d0 = float(cse['keep'][1].cpu()[0])
+    w_seg_d = T_(np.array([w_d0 * (1 + 0.25 * j) for j in range(nseg)], np.float32))
+    w_seg = ops.spec(w_seg_d, None, cse['keep'][2], 8)
+    w_col_d = T_(np.repeat(w_seg_d.cpu().numpy(), seg))
+    w_col = ops.spec(w_col_d, None, cse['keep'][2], 8)
+    ref8 = torch.empty(M, N, dtype=torch.uint8, device=DEV)
+    refc = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_i8(cse['a8'], cse['w8'], cse['rowsum'], cse['bias'], M, N, K, cse['a_sp'], w_col, N, act, o_col, N,
+                  out_ctr=refc, out_i8=ref8)
+    got8 = torch.empty(M, N, dtype=torch.uint8, device=DEV)
+    gotc = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_seg_i8(cse['a8'], cse['w8'], cse['rowsum'], cse['bias'], M, N, K, cse['a_sp'], w_seg, o_seg, nseg, act, out_i8=got8)
+    ops.linear_seg_i8(cse['a8'], cse['w8'], cse['rowsum'], cse['bias'], M, N, K, cse['a_sp'], w_seg, o_seg, nseg, act, out_ctr=gotc)
+    torch.cuda.synchronize()
+    assert torch.equal(got8, ref8)
+    assert torch.equal(gotc, refc)
+
+
+@pytest.mark.parametrize('M,N,K', [(4096, 768, 768), (4096, 768, 3072), (384, 768, 256), (200, 1024, 256), (130, 256, 128)])
+def test_linear_residual_layernorm_lean_matches_general_kernel(M, N, K, monkeypatch):
+    """lean fused residual + LayerNorm kernel vs the general one (TQ_LINEAR_LEAN=0): the row statistics come from
+    exact integer sums in both, so the outputs are bit-identical whatever the tiling; and vs the unfused chain"""
+    ops = tq_native.ops()
+    cse = _i8_case(ops, M, N, K, seed=M + N + K)
+    rs = np.random.RandomState(2)
+    r_int = rs.randint(0, 256, size=(M, N)).astype(np.float32)
+    gamma = (1 + 0.1 * rs.randn(N)).astype(np.float32)
+    beta = (0.05 * rs.randn(N)).astype(np.float32)
+    r_sp, r_keep, (r_d, r_z) = asym_spec(ops, -4.0, 4.0)
+    zp_r = float(O.asym_zero_point(r_z, 8))
+    g_sp, g_keep, _ = asym_spec(ops, float(cse['pre'].min()), float(cse['pre'].max()))
+    u_sp, u_keep, _ = asym_spec(ops, float(cse['pre'].min()) - 3.0, float(cse['pre'].max()) + 3.0)
+    z_sp, z_keep, (z_d, z_z) = asym_spec(ops, -4.0, 4.0)
+    gt, bt = T_(gamma), T_(beta)
+    r8 = T_(r_int).to(torch.uint8)
+
+    def run():
+        z8 = torch.empty(M, N, dtype=torch.uint8, device=DEV)
+        zc = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.linear_res_ln_i8(cse['a8'], cse['w8'], cse['rowsum'], cse['bias'], M, N, K, cse['a_sp'], cse['w_sp'], 1, g_sp,
+                             r8, r_sp, u_sp, gt, bt, 1e-12, z_sp, z8, out_ctr=zc)
+        torch.cuda.synchronize()
+        return z8, zc
+
+    monkeypatch.setenv('TQ_LINEAR_LEAN', '1')
+    z8_l, zc_l = run()
+    monkeypatch.setenv('TQ_LINEAR_LEAN', '0')
+    z8_g, zc_g = run()
+    assert torch.equal(z8_l, z8_g)
+    assert torch.equal(zc_l, zc_g)
+    if N % 256 == 0:          # the unfused chain (GEMM + residual kernel, then the stand-alone LayerNorm kernel): same statistics
+        _, uc = ops.linear_res(cse['a_ctr'], cse['w_bf'], cse['bias'], M, N, K, cse['a_sp'], cse['w_sp'], 1, g_sp, 1,
+                               T_(r_int - zp_r).to(torch.bfloat16), r_sp, u_sp, 1)
+        zc2, _ = ops.ln_qdq(uc, u_sp, 1, gt, bt, 1e-12, z_sp, 1)
+        torch.cuda.synchronize()
+        assert torch.equal(zc2, zc_l)

@@ -115,7 +115,7 @@ int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mism
     return tq::launch_status();
 }
 
-int tq_version(void) { return 2; }
+int tq_version(void) { return 3; }
 
 const char* tq_error_string(int code) {
     switch (code) {

@@ -250,6 +250,21 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// LayerNorm statistics of a row of a fake-quantized tensor x_i = s * k_i from the EXACT integer sums S1 = sum k_i,
+// S2 = sum k_i^2 (k = centred integers, |k| <= 2^8): mean = s * S1 / n, var = s^2 * (S2 - S1^2 / n) / n evaluated
+// in fp64 and rounded once.  Independent of the summation order and of how a row is tiled over threads / CTAs,
+// so the fused GEMM epilogues (any tile width, bf16 or int8 operands) and the stand-alone LayerNorm kernel give
+// bit-identical results; closer to the true statistics than any fp32 summation.
+__device__ __forceinline__ void ln_stats_from_sums(long long S1, long long S2, int64_t n, float s, float eps, float& mean,
+                                                   float& rstd) {
+    const double m = (double)S1 / (double)n;
+    double var = ((double)S2 - (double)S1 * m) / (double)n;
+    var = var < 0.0 ? 0.0 : var;
+    mean = (float)((double)s * m);
+    const float varf = (float)((double)s * (double)s * var);
+    rstd = __fdiv_rn(1.0f, sqrtf(__fadd_rn(varf, eps)));
+}
+
 inline int sm_count() {
     static int cached = 0;
     if (cached == 0) {

@@ -120,26 +120,56 @@ __device__ __forceinline__ void ln_row(const LnArgs& a, int64_t row, int lane, C
             }
         }
     }
-    // mean / variance over the row (fp32, two passes: the values are in registers)
-    float s = 0.0f;
+    float mean, rstd;
+    if (!EMBED && FAST) {
+        // per-tensor quantized input x = s * k: statistics from the exact integer sums of k (see ln_stats_from_sums),
+        // bit-identical to the fused GEMM + LayerNorm epilogues whatever their tiling
+        const float sc = in_q.p0.scale;
+        float f1 = 0.0f, f2 = 0.0f;                    // <= 32 values per lane: exact in fp32
 #pragma unroll
-    for (int it = 0; it < kLnMaxIter; ++it)
-        if (it < iters)
+        for (int it = 0; it < kLnMaxIter; ++it) {
+            if (it < iters) {
+                const int c = (it * 32 + lane) * 8;
+                const uint4 raw = *reinterpret_cast<const uint4*>(a.x_ctr + row * a.D + c);
+                const uint32_t pr[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s += v[it][j];
-    s = warp_sum(s);
-    const float mean = s / (float)a.D;
-    float ss = 0.0f;
-#pragma unroll
-    for (int it = 0; it < kLnMaxIter; ++it)
-        if (it < iters)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = v[it][j] - mean;
-                ss += d * d;
+                for (int j = 0; j < 4; ++j) {
+                    const float k0 = bf16_lo(pr[j]), k1 = bf16_hi(pr[j]);
+                    f1 = __fadd_rn(f1, __fadd_rn(k0, k1));
+                    f2 = __fmaf_rn(k0, k0, f2);
+                    f2 = __fmaf_rn(k1, k1, f2);
+                }
             }
-    ss = warp_sum(ss);
-    const float rstd = 1.0f / sqrtf(ss / (float)a.D + a.eps);
+        }
+        int i1 = __float2int_rn(f1), i2 = __float2int_rn(f2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            i1 += __shfl_xor_sync(0xffffffffu, i1, o);
+            i2 += __shfl_xor_sync(0xffffffffu, i2, o);
+        }
+        ln_stats_from_sums((long long)i1, (long long)i2, (int64_t)a.D, sc, a.eps, mean, rstd);
+    } else {
+        // mean / variance over the row (fp32, two passes: the values are in registers)
+        float s = 0.0f;
+#pragma unroll
+        for (int it = 0; it < kLnMaxIter; ++it)
+            if (it < iters)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += v[it][j];
+        s = warp_sum(s);
+        mean = s / (float)a.D;
+        float ss = 0.0f;
+#pragma unroll
+        for (int it = 0; it < kLnMaxIter; ++it)
+            if (it < iters)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = v[it][j] - mean;
+                    ss += d * d;
+                }
+        ss = warp_sum(ss);
+        rstd = 1.0f / sqrtf(ss / (float)a.D + a.eps);
+    }
 #pragma unroll
     for (int it = 0; it < kLnMaxIter; ++it) {
         if (it < iters) {
@@ -156,7 +186,7 @@ __device__ __forceinline__ void ln_row(const LnArgs& a, int64_t row, int lane, C
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {
                     float2 y = __fmul2_rn(__fadd2_rn(make_float2(v[it][j], v[it][j + 1]), nmean), rs2);
-                    y = __fadd2_rn(__fmul2_rn(y, make_float2(gs[j], gs[j + 1])), make_float2(bs[j], bs[j + 1]));
+                    y = __ffma2_rn(y, make_float2(gs[j], gs[j + 1]), make_float2(bs[j], bs[j + 1]));    // as the fused epilogues
                     const float2 ci = centre2(quant_int2_t<true>(y, p2), p2);
                     const float2 dq = __fmul2_rn(p2.scale, ci);
                     ctr[j] = ci.x; ctr[j + 1] = ci.y;

@@ -678,8 +678,7 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
     if (threadIdx.x == 0) TQ_TTRACE(tno, 2);
 
     // ---- loop 1 ----
-    float s = 0.0f;
-    int n_loc = 0;
+    float S1 = 0.0f, S2 = 0.0f;           // sum k, sum k^2 of this lane's centred integers: exact in fp32 (< 2^24)
 #pragma unroll 1
     for (int it = 0, c0; (c0 = slice_col<true>(third, it)) < BN; ++it) {
         uint32_t v[16];
@@ -702,63 +701,42 @@ __device__ __forceinline__ void epi_tile_res_ln(const EpiArgs& ep, float* params
                 make_float2(__fmul_rn(res_scale, rc.x), __fmul_rn(res_scale, rc.y)));
             const float2 k = ctr2_t<FAST>(sum, q2);
             kp[jp] = pack_bf16(k);
-            s = __fadd_rn(s, __fmul_rn(q2.s.x, k.x));                       // LayerNorm input = scale * (x_int - zp)
-            s = __fadd_rn(s, __fmul_rn(q2.s.y, k.y));
+            S1 = __fadd_rn(S1, __fadd_rn(k.x, k.y));
+            S2 = __fmaf_rn(k.x, k.x, S2);
+            S2 = __fmaf_rn(k.y, k.y, S2);
         }
         tmem_st8_nowait(tmem_tile + (uint32_t)c0, kp);
-        n_loc += 16;
     }
     tmem_st_wait();
-    // ---- loop 2: squared deviations from the lane's own mean ----
-    const float m_loc = __fdiv_rn(s, (float)n_loc);
-    float m2 = 0.0f;
-#pragma unroll 1
-    for (int it = 0, c0; (c0 = slice_col<true>(third, it)) < BN; ++it) {
-        uint32_t kp[8];
-        tmem_ld8(tmem_tile + (uint32_t)c0, kp);
-#pragma unroll
-        for (int jp = 0; jp < 8; ++jp) {
-            const float dx = __fsub_rn(__fmul_rn(q2.s.x, __uint_as_float(kp[jp] << 16)), m_loc);
-            const float dy = __fsub_rn(__fmul_rn(q2.s.y, __uint_as_float(kp[jp] & 0xffff0000u)), m_loc);
-            m2 = __fmaf_rn(dx, dx, m2);
-            m2 = __fmaf_rn(dy, dy, m2);
-        }
-    }
     if (threadIdx.x == 0) TQ_TRACE(11);
-    // ---- exchange ----
-    part[third * BM + rl] = s;
-    part[(3 + third) * BM + rl] = m2;
+    // ---- exchange: exact integer sums (see ln_stats_from_sums) ----
+    int* parti = reinterpret_cast<int*>(part);
+    int* xsi = reinterpret_cast<int*>(xs);
+    parti[third * BM + rl] = __float2int_rn(S1);
+    parti[(3 + third) * BM + rl] = __float2int_rn(S2);
     asm volatile("bar.sync 1, 384;" ::: "memory");
     if (third == 0) {
-        float S = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) S = __fadd_rn(S, part[t * BM + rl]);
-        const float mc = __fdiv_rn(S, (float)BN);
-        float M2c = 0.0f;
+        int t1 = 0, t2 = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            // values held by a lane of warp-third t (see slice_col)
-            const int n_t = 16 * (2 * ((BN - t * 32) / 96) + (((BN - t * 32) % 96) >= 32 ? 2 : ((BN - t * 32) % 96) >= 16 ? 1 : 0));
-            const float dm = __fsub_rn(__fdiv_rn(part[t * BM + rl], (float)n_t), mc);
-            M2c = __fadd_rn(M2c, __fmaf_rn((float)n_t * dm, dm, part[(3 + t) * BM + rl]));
+            t1 += parti[t * BM + rl];
+            t2 += parti[(3 + t) * BM + rl];
         }
-        const uint32_t dst = smem_u32(xs + (my * BM + rl) * 2);
+        const uint32_t dst = smem_u32(xsi + (my * BM + rl) * 2);
         for (uint32_t r = 0; r < cn; ++r) {
-            st_remote_f32(dst, r, S);
-            st_remote_f32(dst + 4, r, M2c);
+            st_remote_f32(dst, r, __int_as_float(t1));
+            st_remote_f32(dst + 4, r, __int_as_float(t2));
         }
     }
     cluster_sync_all();
     if (threadIdx.x == 0) TQ_TRACE(12);
-    float tot = 0.0f;
-    for (uint32_t r = 0; r < cn; ++r) tot = __fadd_rn(tot, xs[(r * BM + rl) * 2]);
-    const float mean = __fdiv_rn(tot, (float)N);
-    float M2 = 0.0f;
+    long long T1 = 0, T2 = 0;
     for (uint32_t r = 0; r < cn; ++r) {
-        const float dm = __fsub_rn(__fdiv_rn(xs[(r * BM + rl) * 2], (float)BN), mean);
-        M2 = __fadd_rn(M2, __fmaf_rn((float)BN * dm, dm, xs[(r * BM + rl) * 2 + 1]));
+        T1 += xsi[(r * BM + rl) * 2];
+        T2 += xsi[(r * BM + rl) * 2 + 1];
     }
-    const float rstd = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(M2, (float)N), ep.ln_eps)));
+    float mean, rstd;
+    ln_stats_from_sums(T1, T2, N, q2.s.x, ep.ln_eps, mean, rstd);
     // ---- loop 3: normalise, affine, output quantizer ----
     const float2 nmean = splat(-mean), rstd2 = splat(rstd);
     uint32_t held[4] = {0u, 0u, 0u, 0u};
@@ -1238,6 +1216,556 @@ linear_qdq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 }
 
+// =====================================================================================================
+// LEAN int8 kernels (the fused engine's hot path).  Same TMA -> tcgen05 kind::i8 -> TMEM pipeline as
+// linear_qdq_kernel; what is different is everything around the accumulators.  The per-tile timelines
+// and the ncu source view of the general kernel (profiles/r2_trace_tiles.txt, r2_ncu_engine_layer0.json)
+// showed the int8 GEMMs to be bound by their EPILOGUE, not by the tensor pipe: ~2.5 k cycles of
+// per-tile parameter set-up (dependent global loads behind a block barrier), ~9 k cycles per 128 x 256
+// tile in an epilogue loop that reloaded spilled address registers before every TMEM load and kept
+// run-time output-format branches in the loop, against a 3-4.6 k cycle main loop.  Here:
+//   * quantizer parameters are per SEGMENT of output columns (1 segment, or 3 for the fused Q|K|V GEMM):
+//     resolved once per CTA by a dedicated parameter warp, which also streams the per-column {bias,
+//     zero-point correction} pairs of the NEXT tile into a double-buffered shared-memory table while the
+//     epilogue warps work on the current one (mbarrier hand-off, no block barrier per tile);
+//   * 8 epilogue warps (two per TMEM lane quarter) with up to 168 registers each take 32-column slices:
+//     one tcgen05.ld.x32 per slice, the next slice's load in flight during the arithmetic of the current
+//     one, output format and activation fixed at compile time, one 32-byte (u8) or two 32-byte (bf16)
+//     row pieces per store;
+//   * the fused LayerNorm takes its row statistics from EXACT integer sums (sum k, sum k^2 of the centred
+//     integers k, |k| <= 255), so they do not depend on the summation order or the tiling: two passes
+//     over the tile instead of three, and bit-identical to the general kernels.
+// Arithmetic per element is the same operation chain as the general kernel (bit-identical outputs).
+// =====================================================================================================
+namespace lean {
+
+constexpr int kEpiWarps = 8;
+constexpr int kProdWarp = 8, kMmaWarp = 9, kParWarp = 10;
+constexpr int kThreads = 32 * 11;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kMaxSeg = 4;
+constexpr int kSegFloats = 24;
+
+template <int BN, bool LNF>
+struct Cfg {
+    static constexpr int kABytes = BM * 128;
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kColBytes = 2 * (BN / 2) * 16;                 // 2 x float4 {bias.x, bias.y, corr.x, corr.y} per column pair
+    static constexpr int kLnBytes = LNF ? (BN / 2) * 16 + 2 * BM * 8 + 8 * BM * 8 : 0;   // gamma|beta pairs, half partials, cluster partials
+    static constexpr int kSegBytes = kMaxSeg * kSegFloats * 4;
+    static constexpr int kParamBytes = kColBytes + kLnBytes + kSegBytes;
+    static constexpr int kStagesFit = (227 * 1024 - 1024 - kParamBytes - 256) / kStageBytes;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr int kBarBytes = (2 * kStages + 8) * 8 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kBarBytes + 1024;
+};
+
+struct Args {
+    const float* bias;              // [N] or null
+    const int32_t* w_rowsum;        // [N]
+    tq_qspec a_q;                   // per-tensor input quantizer
+    tq_qspec w_q, out_q;            // nseg parameter slots each
+    int64_t seg_width;              // columns per segment (N / nseg)
+    int32_t nseg;
+    void* y_u8;                     // [M, N] x_int bytes          (exactly one of the two outputs ...
+    __nv_bfloat16* y_ctr;           // [M, N] centred bf16 grid     ... unless LNF, where y_ctr is optional)
+    const unsigned char* res_u8;    // LNF: residual x_int bytes [M, N]
+    tq_qspec res_q, out2_q, ln_q;   // LNF: per-tensor
+    const float* ln_gamma;
+    const float* ln_beta;
+    float ln_eps;
+    long long* trace;
+    long long* trace_tiles;
+};
+
+#define TQL_TRACE(slot) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[slot] = clock64(); } while (0)
+#define TQL_TTRACE(tile_no, slot) do { if (ep.trace_tiles != nullptr && blockIdx.x == 0 && (tile_no) < 8) \
+        ep.trace_tiles[(tile_no) * 8 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// tcgen05.wait::ld, then "touch" the destination registers: the compiler may not use them before the wait
+template <int NV>
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&v)[NV]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < NV; ++i) asm volatile("" : "+r"(v[i]));
+}
+
+// resolved per-tensor quantizer -> QReg (clamp bounds in the centred domain)
+__device__ __forceinline__ QReg qreg_of(float s, float r, float clo, float chi) {
+    QReg q;
+    q.s = splat(s); q.ns = splat(-s); q.r = splat(r); q.clo = splat(clo); q.chi = splat(chi);
+    return q;
+}
+// 16 float bit patterns (x_int + 1.5 * 2^23: the integer sits in the low mantissa byte) -> 4 packed words
+__device__ __forceinline__ void pack_bytes16(uint32_t (&w)[4], const uint32_t (&b)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        w[i] = __byte_perm(__byte_perm(b[4 * i], b[4 * i + 1], 0x0040), __byte_perm(b[4 * i + 2], b[4 * i + 3], 0x0040), 0x5410);
+}
+
+// ---- plain epilogue: y = Q(act(acc * cs + bias)) for one 128 x BN accumulator tile ---------------------
+// segment parameters sg[]: 0 cs, 1 s, 2 r, 3 clo, 4 chi, 5 (lo - clo) + 1.5 * 2^23, 6 exact flag
+template <int BN, int ACT, bool FAST, bool OUT8>
+__device__ __forceinline__ void epi_plain(const Args& ep, const float4* __restrict__ Pcol, const float* __restrict__ sg,
+                                          uint32_t tmem_tile, int half, int64_t row, bool row_ok, int64_t n0, int64_t N) {
+    constexpr int NIT = BN / 64;
+    const QReg q = qreg_of(sg[1], sg[2], sg[3], sg[4]);
+    const float2 cs2 = splat(sg[0]), off2 = splat(sg[5]);
+    unsigned char* o8 = OUT8 ? reinterpret_cast<unsigned char*>(ep.y_u8) + row * N + n0 : nullptr;
+    __nv_bfloat16* oc = OUT8 ? nullptr : ep.y_ctr + row * N + n0;
+    uint32_t va[32], vb[32];
+    tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32), va);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        uint32_t (&v)[32] = (it & 1) ? vb : va;
+        uint32_t (&vn)[32] = (it & 1) ? va : vb;
+        tmem_ld_fence(v);
+        if (it + 1 < NIT) tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32 + (it + 1) * 64), vn);
+        const int c0 = half * 32 + it * 64;
+        const float4* P = Pcol + (c0 >> 1);
+        uint32_t w[16];
+        uint32_t b[16];
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+            const float4 pp = P[jp];
+            const float2 a = make_float2(__int2float_rn((int)v[2 * jp] - __float_as_int(pp.z)),
+                                         __int2float_rn((int)v[2 * jp + 1] - __float_as_int(pp.w)));
+            float2 f = __ffma2_rn(a, cs2, make_float2(pp.x, pp.y));
+            f = act2<ACT>(f);
+            const float2 k = ctr2_t<FAST>(f, q);
+            if (OUT8) {
+                const float2 t = __fadd2_rn(k, off2);
+                b[2 * (jp & 7)] = __float_as_uint(t.x);
+                b[2 * (jp & 7) + 1] = __float_as_uint(t.y);
+                if ((jp & 7) == 7) {
+                    uint32_t w4[4];
+                    pack_bytes16(w4, b);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[(jp >> 3) * 4 + i] = w4[i];
+                }
+            } else {
+                w[jp] = pack_bf16(k);
+            }
+        }
+        if (row_ok) {
+            if (OUT8) {
+                stg256(o8 + c0, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+            } else {
+                stg256(oc + c0, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+                stg256(oc + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&w[8]));
+            }
+        }
+    }
+}
+
+// ---- residual + LayerNorm epilogue (one tile per CTA, cluster over the N tiles of a row panel) ----------
+//   loop 1   k = Q2( s1 * Q1(acc * cs + bias) + s_r * (r_int - zp_r) )  centred integers, parked as bf16 pairs in
+//            the accumulator columns just read; S1 += k, S2 += k * k  (exact: |k| <= 255, <= 128 columns per thread)
+//   exchange the two halves of a row -> every CTA of the cluster (DSMEM, int32) -> one cluster barrier
+//   mean = s2 * S1 / N, var = s2^2 * (S2 - S1^2 / N) / N  in fp64 from the exact totals, rounded once to fp32
+//   loop 2   z = Q3( (s2 * k - mean) * rstd * gamma + beta )
+// segment parameters sg[]: 0 cs, 1-4 q1 {s, r, clo, chi}, 6 exact, 7-10 q2 {s, r, clo, chi}, 11 res scale,
+// 12 2^23 + res zp, 13-16 q3 {s, r, clo, chi}, 17 (lo3 - clo3) + 1.5 * 2^23
+template <int BN, bool FAST>
+__device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restrict__ Pcol, const float4* __restrict__ Pgb,
+                                           const float* __restrict__ sg, int2* part, int2* xs, uint32_t tmem_tile, int half,
+                                           int quarter, int lane, int64_t row, bool row_ok, int64_t n0, int64_t N) {
+    constexpr int NIT = BN / 64;
+    const QReg q1 = qreg_of(sg[1], sg[2], sg[3], sg[4]);
+    const QReg q2 = qreg_of(sg[7], sg[8], sg[9], sg[10]);
+    const float2 cs2 = splat(sg[0]);
+    const float s1 = sg[1], rs = sg[11], roff = sg[12], s2 = sg[7];
+    const int rl = quarter * 32 + lane;
+    const unsigned char* rrow = ep.res_u8 + row * N + n0;
+    uint32_t va[32], vb[32];
+    uint32_t rw[8], rn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rn[i] = 0u;
+    tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32), va);
+    if (row_ok) ldg256(rrow + half * 32, rn);
+    float S1 = 0.0f, S2 = 0.0f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        uint32_t (&v)[32] = (it & 1) ? vb : va;
+        uint32_t (&vn)[32] = (it & 1) ? va : vb;
+        tmem_ld_fence(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rw[i] = rn[i];
+        const int c0 = half * 32 + it * 64;
+        if (it + 1 < NIT) {
+            tmem_ld32_nowait(tmem_tile + (uint32_t)(c0 + 64), vn);
+            if (row_ok) ldg256(rrow + c0 + 64, rn);
+        }
+        const float4* P = Pcol + (c0 >> 1);
+        uint32_t kp[16];
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+            const float4 pp = P[jp];
+            const float2 a = make_float2(__int2float_rn((int)v[2 * jp] - __float_as_int(pp.z)),
+                                         __int2float_rn((int)v[2 * jp + 1] - __float_as_int(pp.w)));
+            const float2 f = __ffma2_rn(a, cs2, make_float2(pp.x, pp.y));
+            const float2 c = ctr2_t<FAST>(f, q1);
+            // residual bytes -> floats without the conversion unit: 0x4B000000 | b = 2^23 + b, minus (2^23 + zp): exact
+            const uint32_t wd = rw[jp >> 1];
+            const uint32_t lo = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7652 : 0x7650);
+            const uint32_t hi = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7653 : 0x7651);
+            const float2 rc = make_float2(__fsub_rn(__uint_as_float(lo), roff), __fsub_rn(__uint_as_float(hi), roff));
+            // fl(s1 * c) + fl(s_r * r) as the reference materialises them: scalar multiplies (a packed multiply
+            // feeding a packed add would be contracted into FFMA2)
+            const float2 sum = __fadd2_rn(make_float2(__fmul_rn(s1, c.x), __fmul_rn(s1, c.y)),
+                                          make_float2(__fmul_rn(rs, rc.x), __fmul_rn(rs, rc.y)));
+            const float2 k = ctr2_t<FAST>(sum, q2);
+            S1 = __fadd_rn(S1, __fadd_rn(k.x, k.y));
+            S2 = __fmaf_rn(k.x, k.x, S2);
+            S2 = __fmaf_rn(k.y, k.y, S2);
+            kp[jp] = pack_bf16(k);
+        }
+        tmem_st16_nowait(tmem_tile + (uint32_t)c0, kp);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (threadIdx.x == 0) TQL_TRACE(11);
+    // ---- exchange ----
+    part[half * BM + rl] = make_int2(__float2int_rn(S1), __float2int_rn(S2));
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const uint32_t cn = cluster_nctarank(), my = cluster_ctarank();
+    if (half == 0) {
+        const int2 pa = part[rl], pb = part[BM + rl];
+        const int t1 = pa.x + pb.x, t2 = pa.y + pb.y;
+        const uint32_t dst = smem_u32(xs + (my * BM + rl));
+        for (uint32_t r = 0; r < cn; ++r) {
+            st_remote_f32(dst, r, __int_as_float(t1));
+            st_remote_f32(dst + 4, r, __int_as_float(t2));
+        }
+    }
+    cluster_sync_all();
+    if (threadIdx.x == 0) TQL_TRACE(12);
+    long long T1 = 0, T2 = 0;
+    for (uint32_t r = 0; r < cn; ++r) {
+        const int2 p = xs[r * BM + rl];
+        T1 += p.x;
+        T2 += p.y;
+    }
+    float mean, rstd;
+    ln_stats_from_sums(T1, T2, N, s2, ep.ln_eps, mean, rstd);
+    // ---- loop 2: normalise, affine, output quantizer ----
+    const QReg q3 = qreg_of(sg[13], sg[14], sg[15], sg[16]);
+    const float2 nmean = splat(-mean), rstd2 = splat(rstd), off3 = splat(sg[17]);
+    unsigned char* o8 = reinterpret_cast<unsigned char*>(ep.y_u8) + row * N + n0;
+    uint32_t ka[16], kb[16];
+    tmem_ld16_nowait(tmem_tile + (uint32_t)(half * 32), ka);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        uint32_t (&kq)[16] = (it & 1) ? kb : ka;
+        uint32_t (&kn)[16] = (it & 1) ? ka : kb;
+        tmem_ld_fence(kq);
+        const int c0 = half * 32 + it * 64;
+        if (it + 1 < NIT) tmem_ld16_nowait(tmem_tile + (uint32_t)(c0 + 64), kn);
+        const float4* G = Pgb + (c0 >> 1);
+        uint32_t w8[8], wc[16], b[16];
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+            const float2 v = make_float2(__fmul_rn(s2, __uint_as_float(kq[jp] << 16)),
+                                         __fmul_rn(s2, __uint_as_float(kq[jp] & 0xffff0000u)));
+            const float4 gb = G[jp];
+            float2 y = __fmul2_rn(__fadd2_rn(v, nmean), rstd2);
+            y = __ffma2_rn(y, make_float2(gb.x, gb.y), make_float2(gb.z, gb.w));
+            const float2 k3 = ctr2_t<FAST>(y, q3);
+            wc[jp] = pack_bf16(k3);
+            const float2 t = __fadd2_rn(k3, off3);
+            b[2 * (jp & 7)] = __float_as_uint(t.x);
+            b[2 * (jp & 7) + 1] = __float_as_uint(t.y);
+            if ((jp & 7) == 7) {
+                uint32_t w4[4];
+                pack_bytes16(w4, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w8[(jp >> 3) * 4 + i] = w4[i];
+            }
+        }
+        if (row_ok) {
+            stg256(o8 + c0, w8);
+            if (ep.y_ctr != nullptr) {
+                __nv_bfloat16* oc = ep.y_ctr + row * N + n0 + c0;
+                stg256(oc, *reinterpret_cast<uint32_t(*)[8]>(&wc[0]));
+                stg256(oc + 16, *reinterpret_cast<uint32_t(*)[8]>(&wc[8]));
+            }
+        }
+    }
+}
+
+template <int BN, int ACT, bool LNF, bool OUT8>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   int64_t M, int64_t N, int64_t K, int ring, Args ep) {
+    using C = Cfg<BN, LNF>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+    unsigned char* par_ptr = base_ptr + C::kStages * C::kStageBytes;
+    float4* Pcol = reinterpret_cast<float4*>(par_ptr);                       // [2][BN / 2]
+    float4* Pgb = reinterpret_cast<float4*>(par_ptr + C::kColBytes);         // LNF: [BN / 2] {gamma.x, gamma.y, beta.x, beta.y}
+    int2* part = reinterpret_cast<int2*>(par_ptr + C::kColBytes + (LNF ? (BN / 2) * 16 : 0));     // [2][BM]
+    int2* xs = part + 2 * BM;                                                 // [8][BM]
+    float* segp = reinterpret_cast<float*>(par_ptr + C::kColBytes + C::kLnBytes);   // [kMaxSeg][kSegFloats]
+    const uint32_t bar0 = base + C::kStages * C::kStageBytes + C::kParamBytes;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (C::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 2 + s); };
+    auto pfull_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 4 + s); };
+    auto pempty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 6 + s); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * C::kStages + 8);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+        base_ptr + C::kStages * C::kStageBytes + C::kParamBytes + 8 * (2 * C::kStages + 8));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
+    const int64_t tiles = m_tiles * n_tiles;
+    const int64_t tile0 = blockIdx.x, tile_step = gridDim.x;
+    const int num_kb = (int)(K / 128);
+
+    if (threadIdx.x == 0) TQL_TRACE(0);
+    int p_stage = 0, p_pre = 0;
+    uint32_t p_phase = 0;
+    if (warp == kProdWarp && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tile0 < tiles) {
+            pdl_wait();                               // A is produced by the previous kernel
+            const int32_t m0 = (int32_t)((tile0 / n_tiles) * BM), n0 = (int32_t)((tile0 % n_tiles) * BN);
+            p_pre = num_kb < ring ? num_kb : ring;
+            for (int kb = 0; kb < p_pre; ++kb) {      // ring slots are free: no empty-barrier wait
+                mbar_expect_tx(full_bar(p_stage), C::kStageBytes);
+                const uint32_t sa = base + p_stage * C::kStageBytes;
+                tma_load_2d<1>(sa, &map_a, kb * 128, m0, full_bar(p_stage));
+                tma_load_2d<1>(sa + C::kABytes, &map_w, kb * 128, n0, full_bar(p_stage));
+                if (++p_stage == ring) { p_stage = 0; p_phase ^= 1u; }
+            }
+        }
+    }
+    if (warp == kMmaWarp) {
+        if (lane == 0) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(tfull_bar(s), 1);
+                mbar_init(tempty_bar(s), kEpiWarps);
+                mbar_init(pfull_bar(s), 1);
+                mbar_init(pempty_bar(s), kEpiWarps);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();                       // A / residual tiles are produced by the previous kernel
+    if (threadIdx.x == 0) TQL_TRACE(1);
+
+    if (warp == kProdWarp) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = p_stage;
+            uint32_t phase = p_phase;
+            int tno = 0;
+            for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
+                const int32_t m0 = (int32_t)((t / n_tiles) * BM), n0 = (int32_t)((t % n_tiles) * BN);
+                for (int kb = (t == tile0 ? p_pre : 0); kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), C::kStageBytes);
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    tma_load_2d<1>(sa, &map_a, kb * 128, m0, full_bar(stage));
+                    tma_load_2d<1>(sa + C::kABytes, &map_w, kb * 128, n0, full_bar(stage));
+                    if (++stage == ring) { stage = 0; phase ^= 1u; }
+                }
+                TQL_TTRACE(tno, 7);
+            }
+        }
+        if (LNF) {                                    // the epilogue's cluster barrier counts every thread
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t a_s8 = (ep.a_q.zero_float == nullptr && ep.a_q.is_signed != nullptr && *ep.a_q.is_signed) ? 1u : 0u;
+            const uint32_t w_s8 = (ep.w_q.zero_float == nullptr && ep.w_q.is_signed != nullptr && *ep.w_q.is_signed) ? 1u : 0u;
+            const uint32_t idesc = (2u << 4) | (a_s8 << 7) | (w_s8 << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            int tno = 0;
+            for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                TQL_TTRACE(tno, 4);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    if (kb == 0) TQL_TTRACE(tno, 5);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    const uint64_t adesc = make_desc_sw128(sa), bdesc = make_desc_sw128(sa + C::kABytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    tc_commit<1>(empty_bar(stage));
+                    if (++stage == ring) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit<1>(tfull_bar(acc));
+                TQL_TTRACE(tno, 6);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        if (LNF) {
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else if (warp == kParWarp) {
+        // ===================== parameter warp =====================
+        float lo, hi;
+        grid_of(ep.a_q, lo, hi);
+        const QP aq = resolve(ep.a_q, 0, lo, hi);
+        const int a_zp = (int)aq.zp;
+        if (lane < ep.nseg && lane < kMaxSeg) {
+            float* sg = segp + lane * kSegFloats;
+            float wlo, whi, qlo, qhi;
+            grid_of(ep.w_q, wlo, whi);
+            grid_of(ep.out_q, qlo, qhi);
+            const QP wq = resolve(ep.w_q, lane, wlo, whi);
+            const QP oq = resolve(ep.out_q, lane, qlo, qhi);
+            int exact = oq.exact;
+            sg[0] = __fmul_rn(aq.scale, wq.scale);
+            sg[1] = oq.scale; sg[2] = oq.rcp; sg[3] = qlo - oq.zp; sg[4] = qhi - oq.zp;
+            sg[5] = __fadd_rn(oq.zp, 12582912.0f);               // x_int = k + zp, + 1.5 * 2^23
+            if (LNF) {
+                float l2, h2, l3, h3, lr, hr;
+                grid_of(ep.out2_q, l2, h2);
+                grid_of(ep.ln_q, l3, h3);
+                grid_of(ep.res_q, lr, hr);
+                const QP q2 = resolve(ep.out2_q, 0, l2, h2), q3 = resolve(ep.ln_q, 0, l3, h3), rq = resolve(ep.res_q, 0, lr, hr);
+                exact |= q2.exact | q3.exact;
+                sg[7] = q2.scale; sg[8] = q2.rcp; sg[9] = l2 - q2.zp; sg[10] = h2 - q2.zp;
+                sg[11] = rq.scale; sg[12] = __fadd_rn(8388608.0f, rq.zp);
+                sg[13] = q3.scale; sg[14] = q3.rcp; sg[15] = l3 - q3.zp; sg[16] = h3 - q3.zp;
+                sg[17] = __fadd_rn(q3.zp, 12582912.0f);
+            }
+            sg[6] = __int_as_float(exact);
+        }
+        if (LNF && tile0 < tiles) {
+            const int64_t n0 = (tile0 % n_tiles) * BN;
+            for (int jp = lane; jp < BN / 2; jp += 32) {
+                const int64_t n = n0 + 2 * jp;
+                Pgb[jp] = make_float4(ep.ln_gamma[n], ep.ln_gamma[n + 1], ep.ln_beta[n], ep.ln_beta[n + 1]);
+            }
+        }
+        int pb = 0;
+        uint32_t pphase = 0;
+        for (int64_t t = tile0; t < tiles; t += tile_step) {
+            const int64_t n0 = (t % n_tiles) * BN;
+            mbar_wait(pempty_bar(pb), pphase ^ 1u);
+            float4* P = Pcol + pb * (BN / 2);
+            for (int jp = lane; jp < BN / 2; jp += 32) {
+                const int64_t n = n0 + 2 * jp;
+                const float b0 = ep.bias != nullptr ? ep.bias[n] : 0.0f, b1 = ep.bias != nullptr ? ep.bias[n + 1] : 0.0f;
+                P[jp] = make_float4(b0, b1, __int_as_float(a_zp * ep.w_rowsum[n]), __int_as_float(a_zp * ep.w_rowsum[n + 1]));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pfull_bar(pb));
+            if (++pb == 2) { pb = 0; pphase ^= 1u; }
+        }
+        if (LNF) {
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else {
+        // ===================== epilogue (warps 0..7) =====================
+        const int quarter = warp & 3, half = warp >> 2;
+        int acc = 0, pb = 0;
+        uint32_t acc_phase = 0, pphase = 0;
+        int tno = 0;
+        for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
+            const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+            if (threadIdx.x == 0) TQL_TTRACE(tno, 0);
+            mbar_wait(pfull_bar(pb), pphase);
+            if (threadIdx.x == 0) TQL_TTRACE(tno, 1);
+            const float* sg = segp + (int)(n0 / ep.seg_width) * kSegFloats;
+            const int exact = __float_as_int(sg[6]);
+            const int64_t row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < M;
+            const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const float4* P = Pcol + pb * (BN / 2);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            if (threadIdx.x == 0) { TQL_TRACE(8); TQL_TTRACE(tno, 2); }
+            if (LNF) {
+                if (exact) epi_res_ln<BN, false>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N);
+                else epi_res_ln<BN, true>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N);
+            } else {
+                if (exact) epi_plain<BN, ACT, false, OUT8>(ep, P, sg, tmem_tile, half, row, row_ok, n0, N);
+                else epi_plain<BN, ACT, true, OUT8>(ep, P, sg, tmem_tile, half, row, row_ok, n0, N);
+            }
+            if (threadIdx.x == 0) { TQL_TRACE(9); TQL_TTRACE(tno, 3); }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tempty_bar(acc));
+                mbar_arrive(pempty_bar(pb));
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++pb == 2) { pb = 0; pphase ^= 1u; }
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) TQL_TRACE(10);
+    if (warp == kMmaWarp)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                     : "memory");
+}
+
+}  // namespace lean
+
 // hi | mid | lo bf16 split: x = hi + mid + lo up to 2^-24 relative (three 8-bit mantissa pieces)
 __global__ void __launch_bounds__(256, 4)
 split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t M, int64_t K) {
@@ -1367,6 +1895,50 @@ static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act
     return best;
 }
 
+
+template <int BN, int ACT, bool LNF, bool OUT8>
+static int launch_lean(const void* a, const void* w, int64_t M, int64_t N, int64_t K, const lean::Args& ep, cudaStream_t st) {
+    using C = lean::Cfg<BN, LNF>;
+    static_assert(C::kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(2 * BN <= kTmemCols && BN % 64 == 0, "TMEM budget / slice width");
+    CUtensorMap map_a, map_w;
+    if (int e = make_map(&map_a, a, M, K, BM, true)) return e;
+    if (int e = make_map(&map_w, w, N, K, BN, true)) return e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lean::linear_lean_kernel<BN, ACT, LNF, OUT8>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int64_t tiles = ((M + BM - 1) / BM) * (N / BN);
+    int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    int cluster = 1;
+    if (LNF) {
+        cluster = (int)(N / BN);
+        grid = (int)tiles;
+    }
+    int ring = C::kStages;
+    if (const char* e = getenv("TQ_LINEAR_STAGES")) {
+        const int f = atoi(e);
+        if (f >= 1 && f < ring) ring = f;
+    }
+    return launch_pdl(lean::linear_lean_kernel<BN, ACT, LNF, OUT8>, dim3(grid), dim3(lean::kThreads), C::kSmemBytes, st, cluster,
+                      map_a, map_w, M, N, K, ring, ep);
+}
+
+static void lean_trace(lean::Args& ep) {
+    ep.trace = nullptr;
+    ep.trace_tiles = nullptr;
+    if (const char* e = getenv("TQ_LINEAR_TRACE_PTR")) ep.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+    if (const char* e = getenv("TQ_LINEAR_TRACE_TILES")) ep.trace_tiles = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+}
+static bool lean_enabled() {          // TQ_LINEAR_LEAN=0: keep the general kernels (tools / A-B timing)
+    const char* e = getenv("TQ_LINEAR_LEAN");
+    return !(e != nullptr && e[0] == '0');
+}
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
 }  // namespace gemm
 }  // namespace tq
 
@@ -1462,6 +2034,24 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
             if (cost < best_cost) {
                 best_cost = cost;
                 best = bn;
+            }
+        }
+        if (i8 && lean_enabled() && y == nullptr && y_u8 != nullptr && w_q_params == 1 && out2_q.n_bits <= 8 &&
+            out_q.n_bits <= 8 && ln_q->n_bits <= 8 && (N & 31) == 0 && aligned32(y_u8) && aligned32(res_ctr_bf16) &&
+            (y_ctr_bf16 == nullptr || aligned32(y_ctr_bf16)) && (best == 256 || best == 192 || best == 128)) {
+            // lean int8 kernel: same arithmetic, parameter warp + 32-column epilogue slices (see namespace lean)
+            lean::Args la;
+            la.bias = bias; la.w_rowsum = w_rowsum; la.a_q = a_q; la.w_q = w_q; la.out_q = out_q;
+            la.seg_width = N; la.nseg = 1;
+            la.y_u8 = y_u8; la.y_ctr = reinterpret_cast<__nv_bfloat16*>(y_ctr_bf16);
+            la.res_u8 = reinterpret_cast<const unsigned char*>(res_ctr_bf16);
+            la.res_q = res_q; la.out2_q = out2_q; la.ln_q = *ln_q;
+            la.ln_gamma = ln_gamma; la.ln_beta = ln_beta; la.ln_eps = ln_eps;
+            lean_trace(la);
+            switch (best) {
+                case 256: return launch_lean<256, 0, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
+                case 192: return launch_lean<192, 0, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
+                default: return launch_lean<128, 0, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
             }
         }
         if (i8) {
@@ -1565,6 +2155,44 @@ int tq_linear_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w
     if (res_i8 == nullptr || ln_gamma_q == nullptr || ln_beta == nullptr) return TQ_EINVAL;
     return linear_impl(a_i8, w_i8, bias, z, z_ctr_bf16, M, N, K, 1, a_q, w_q, w_q_params, 0, out_q, 1, res_i8, res_q,
                        out2_q, 1, nullptr, nullptr, 0, stream, ln_gamma_q, ln_beta, ln_eps, &ln_q, true, w_rowsum, z_i8);
+}
+
+int tq_linear_seg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias, void* y_ctr_bf16,
+                         void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q, tq_qspec out_q,
+                         int32_t nseg, int32_t act_fn, void* stream) {
+    using namespace tq::gemm;
+    if (a_i8 == nullptr || w_i8 == nullptr || w_rowsum == nullptr || ((y_ctr_bf16 == nullptr) == (y_i8 == nullptr))) return TQ_EINVAL;
+    if (M < 1 || N < 1 || K < 1 || nseg < 1 || nseg > lean::kMaxSeg || N % nseg != 0) return TQ_EINVAL;
+    if (act_fn < 0 || act_fn > 1) return TQ_EUNSUPPORTED;
+    if (int e = tq::check_qspec(a_q)) return e;
+    if (int e = tq::check_qspec(w_q)) return e;
+    if (int e = tq::check_qspec(out_q)) return e;
+    if (a_q.n_bits > 8 || w_q.n_bits > 8 || out_q.n_bits > 8 || K % 128 != 0) return TQ_EUNSUPPORTED;
+    if (!tq::aligned16(a_i8) || !tq::aligned16(w_i8)) return TQ_EALIGN;
+    void* out = y_i8 != nullptr ? y_i8 : y_ctr_bf16;
+    if (!aligned32(out) || (N & 31) != 0) return TQ_EALIGN;
+    const int64_t seg = N / nseg;
+    const int bn = seg % 256 == 0 ? 256 : (seg % 192 == 0 ? 192 : (seg % 128 == 0 ? 128 : 0));
+    if (bn == 0) return TQ_EUNSUPPORTED;
+    lean::Args la = {};
+    la.bias = bias; la.w_rowsum = w_rowsum; la.a_q = a_q; la.w_q = w_q; la.out_q = out_q;
+    la.seg_width = seg; la.nseg = nseg;
+    la.y_u8 = y_i8; la.y_ctr = reinterpret_cast<__nv_bfloat16*>(y_ctr_bf16);
+    lean_trace(la);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool o8 = y_i8 != nullptr;
+#define TQ_LEAN_CASE(BN_)                                                                                          \
+    if (bn == BN_) {                                                                                               \
+        if (act_fn == 1) return o8 ? launch_lean<BN_, 1, false, true>(a_i8, w_i8, M, N, K, la, st)                 \
+                                   : launch_lean<BN_, 1, false, false>(a_i8, w_i8, M, N, K, la, st);                \
+        return o8 ? launch_lean<BN_, 0, false, true>(a_i8, w_i8, M, N, K, la, st)                                   \
+                  : launch_lean<BN_, 0, false, false>(a_i8, w_i8, M, N, K, la, st);                                 \
+    }
+    TQ_LEAN_CASE(256)
+    TQ_LEAN_CASE(192)
+    TQ_LEAN_CASE(128)
+#undef TQ_LEAN_CASE
+    return TQ_EUNSUPPORTED;
 }
 
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream) {

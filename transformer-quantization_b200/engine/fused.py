@@ -80,6 +80,16 @@ class _ColSite:
         if len({(q.n_bits, q.scale_domain, q.eps) for q in quantizers}) != 1:
             raise UnsupportedByEngine('fused sites must share n_bits / scale_domain / eps')
         self.n = int(sum(widths))
+        # one parameter slot per SEGMENT (= per fused quantizer) for tq_linear_seg_qdq_i8
+        self.nseg = len(quantizers)
+        self.equal_widths = len(set(widths)) == 1
+        self.seg_delta = torch.cat([q.delta.reshape(1) for q in quantizers]).contiguous()
+        if all(sym):
+            self.seg_zero_float = None
+            self.seg_spec = ops.spec(self.seg_delta, None, q0._signed, q0.n_bits, q0.scale_domain == 'log', q0.eps)
+        else:
+            self.seg_zero_float = torch.cat([q.zero_float.reshape(1) for q in quantizers]).contiguous()
+            self.seg_spec = ops.spec(self.seg_delta, self.seg_zero_float, None, q0.n_bits, q0.scale_domain == 'log', q0.eps)
 
 
 class _Weight:
@@ -117,6 +127,11 @@ class _Weight:
         self.N, self.K = self.grid.shape
         self._signed = q0._signed
         self.spec = ops.spec(self.delta, None, self._signed, q0.n_bits, q0.scale_domain == 'log', q0.eps)
+        # one scale per stacked layer (segment of output columns) for tq_linear_seg_qdq_i8 / the per-tensor form
+        self.nseg = len(layers)
+        self.seg_delta = torch.cat([lin.weight_quantizer.quantizer.delta.reshape(1) for lin in layers]).contiguous()
+        self.seg_spec = ops.spec(self.seg_delta, None, self._signed, q0.n_bits, q0.scale_domain == 'log', q0.eps)
+        self.equal_widths = len({lin.weight.shape[0] for lin in layers}) == 1 and pad_to is None
         # 8-bit operand mode: the same integers, one byte each (two's complement when the grid is signed),
         # and their row sums for the zero-point correction of the activations
         gi = self.grid.to(torch.int32)
@@ -199,6 +214,10 @@ class FusedBertEngine:
             self.first8 = torch.empty(batch, D, **u8)
             self.pooled8 = torch.empty(batch, D, **u8)
         self.ffn_in_bf16 = os.environ.get('TQ_ENGINE_FFN_IN_BF16', '1') != '0'
+        # lean int8 kernels (tq_linear_seg_qdq_i8 + the lean form of tq_linear_res_ln_qdq_i8): shapes they cover
+        self.lean = (self.i8 and os.environ.get('TQ_ENGINE_LEAN', '1') != '0' and D % 128 == 0
+                     and cfg.intermediate_size % 128 == 0
+                     and all(st.q.n_bits <= 8 for d in self.layers for st in (d['q'], d['k'], d['v'], d['f'])))
         self._last_i8 = False
 
     def _linear(self, a_ctr, a_site, w, act, out_spec, out_params, out_ctr=None, want_f32=False, M=None):
@@ -298,27 +317,36 @@ class FusedBertEngine:
         ops.embed_ln_qdq_i8(ids, tt, None, T, self.word_q, self.type_q, self.pos_q, self.e_tok.spec, 1, self.e_pos.spec, 1,
                             self.e_gamma, self.e_beta, self.e_eps, self.e_out.spec, 1, x)
         x_site = self.e_out
+        lean = self.lean
         for d in self.layers:
             w = d['wqkv']
-            ops.linear_i8(x, w.grid8, w.rowsum, w.bias, M, w.N, w.K, x_site.spec, w.spec, w.N, 0, d['qkv_out'].spec,
-                          d['qkv_out'].n, out_ctr=self.qkv)
+            if lean:     # per-segment quantizers (Q | K | V), lean int8 kernel
+                ops.linear_seg_i8(x, w.grid8, w.rowsum, w.bias, M, w.N, w.K, x_site.spec, w.seg_spec, d['qkv_out'].seg_spec,
+                                  3, 0, out_ctr=self.qkv)
+            else:
+                ops.linear_i8(x, w.grid8, w.rowsum, w.bias, M, w.N, w.K, x_site.spec, w.spec, w.N, 0, d['qkv_out'].spec,
+                              d['qkv_out'].n, out_ctr=self.qkv)
             ops.attention_i8(self.qkv, B, T, H, self.hd, d['q'].spec, d['k'].spec, d['v'].spec, d['s'].spec, d['p'].spec,
                              d['c'].spec, mask, c)
             w = d['wg']
             g1, b1, e1 = d['ln1']
             # FFN-in (K = hidden, GELU epilogue) measured faster with bf16 operands: the block before it writes
             # its output in both carrier formats
-            mixed = self.ffn_in_bf16
-            ops.linear_res_ln_i8(c, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['c'].spec, w.spec, w.N, d['g'].spec, x,
+            mixed = self.ffn_in_bf16 and not lean
+            ops.linear_res_ln_i8(c, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['c'].spec, w.seg_spec if lean else w.spec,
+                                 1 if lean else w.N, d['g'].spec, x,
                                  x_site.spec, d['u'].spec, g1, b1, e1, d['x'].spec, a, out_ctr=self.a if mixed else None)
             w = d['wf']
-            if mixed:
+            if lean:
+                ops.linear_seg_i8(a, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['x'].spec, w.seg_spec, d['f'].spec, 1, 1, out_i8=f)
+            elif mixed:
                 ops.linear_bf16_o8(self.a, w.grid, w.bias, M, w.N, w.K, d['x'].spec, w.spec, w.N, 1, d['f'].spec, 1, f)
             else:
                 ops.linear_i8(a, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['x'].spec, w.spec, w.N, 1, d['f'].spec, 1, out_i8=f)
             w = d['wh']
             g2, b2, e2 = d['ln2']
-            ops.linear_res_ln_i8(f, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['f'].spec, w.spec, w.N, d['h'].spec, a,
+            ops.linear_res_ln_i8(f, w.grid8, w.rowsum, w.bias, M, w.N, w.K, d['f'].spec, w.seg_spec if lean else w.spec,
+                                 1 if lean else w.N, d['h'].spec, a,
                                  d['x'].spec, d['y'].spec, g2, b2, e2, d['z'].spec, x)
             x_site = d['z']
         self.first8.copy_(x.view(B, T, D)[:, 0])                         # pooler input: first token
@@ -343,7 +371,7 @@ class FusedBertEngine:
         for d in self.layers:
             for key in ('wqkv', 'wg', 'wh'):
                 i8 += d[key].N * d[key].K
-            if self.ffn_in_bf16:
+            if self.ffn_in_bf16 and not self.lean:
                 bf += d['wf'].N * d['wf'].K
             else:
                 i8 += d['wf'].N * d['wf'].K

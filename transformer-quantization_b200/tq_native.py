@@ -93,6 +93,9 @@ SIGNATURES = {
     'tq_linear_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p,
                                         ctypes.c_void_p, ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, _i64, _i32,
                                         QSpec, _i64, ctypes.c_void_p]),
+    'tq_linear_seg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
+                                            ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, QSpec, _i32, _i32,
+                                            ctypes.c_void_p]),
     'tq_linear_qdq_bf16_o8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p, _i64, _i64, _i64,
                                              QSpec, QSpec, _i64, _i32, QSpec, _i64, ctypes.c_void_p]),
     'tq_linear_res_ln_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p,
@@ -116,7 +119,7 @@ SIGNATURES = {
                                            ctypes.c_float, ctypes.c_void_p]),
 }
 
-ABI_VERSION = 2          # tq_version() of the library this binding was written against
+ABI_VERSION = 3          # tq_version() of the library this binding was written against
 ADAROUND_MODE = {'learned_sigmoid': 0, 'learned_hard_sigmoid': 1, 'sigmoid_temp_decay': 2}
 
 
@@ -452,6 +455,15 @@ class CudaOps:
                   w_rowsum.data_ptr(), _ptr(bias), _ptr(y), _ptr(out_ctr), _ptr(out_i8), M, N, K, a_spec, w_spec,
                   int(w_params), int(act_fn), out_spec if out_spec is not None else null, int(out_params), _stream())
         return y
+
+    def linear_seg_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_seg_spec, out_seg_spec, nseg, act_fn,
+                      out_ctr=None, out_i8=None):
+        """tq_linear_seg_qdq_i8: per-segment weight / output quantizers (nseg slots each); fills out_ctr XOR out_i8"""
+        _chk_cuda(a_i8, w_i8, w_rowsum, bias, out_ctr, out_i8)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_seg_qdq_i8, a_i8.data_ptr(), w_i8.data_ptr(),
+                  w_rowsum.data_ptr(), _ptr(bias), _ptr(out_ctr), _ptr(out_i8), M, N, K, a_spec, w_seg_spec, out_seg_spec,
+                  int(nseg), int(act_fn), _stream())
+        return out_i8 if out_i8 is not None else out_ctr
 
     def linear_res_ln_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_spec, w_params, out_spec, res_i8, res_spec,
                          out2_spec, gamma_q, beta, eps, ln_spec, out_i8, want_f32=False, out_ctr=None):
