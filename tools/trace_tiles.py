@@ -34,7 +34,8 @@ def run(label, fn):
     torch.cuda.synchronize()
     t0 = trace.tolist()
     tt = tiles.view(8, 8).tolist()
-    print(f'{label}: setup_done={t0[1] - t0[0]} teardown={t0[10] - t0[0]}')
+    extra = f' ln_pass1_done={t0[11] - t0[0]} ln_stats_exchanged={t0[12] - t0[0]}' if 'LayerNorm' in label else ''
+    print(f'{label}: setup_done={t0[1] - t0[0]} teardown={t0[10] - t0[0]}{extra}')
     for i, row in enumerate(tt):
         if not any(row):
             continue
@@ -57,19 +58,23 @@ for N, K, label in [(2304, 768, 'qkv'), (768, 768, 'attn_out'), (3072, 768, 'ffn
         o_sp = spec(0.05, 120, None, N)
         run('i8 QKV 2304x768 per-column quantizers, bf16 out',
             lambda: ops.linear_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, 1, 0, o_sp, N, out_ctr=yc))
-        o1 = spec(0.05, 120)
-        run('i8 QKV 2304x768 per-tensor quantizer, bf16 out',
-            lambda: ops.linear_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, 1, 0, o1, 1, out_ctr=yc))
+        o3, w3 = spec(0.05, 120, None, 3), spec(0.001, None, True, 3)
+        run('LEAN i8 QKV 2304x768 three segments, bf16 out',
+            lambda: ops.linear_seg_i8(a8, w8, rsum, bias, M, N, K, a_sp, w3, o3, 3, 0, out_ctr=yc))
     elif label == 'ffn_in':
         o_sp = spec(0.05, 120)
         run('bf16 FFN-in 3072x768 GELU, u8 out',
             lambda: ops.linear_bf16_o8(a_bf, w_bf, bias, M, N, K, a_sp, w_sp, 1, 1, o_sp, 1, y8))
         run('i8 FFN-in 3072x768 GELU, u8 out',
             lambda: ops.linear_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, 1, 1, o_sp, 1, out_i8=y8))
-        run('i8 FFN-in 3072x768 no activation, u8 out',
-            lambda: ops.linear_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, 1, 0, o_sp, 1, out_i8=y8))
+        run('LEAN i8 FFN-in 3072x768 GELU, u8 out',
+            lambda: ops.linear_seg_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, o_sp, 1, 1, out_i8=y8))
+        run('LEAN i8 FFN-in 3072x768 no activation, u8 out',
+            lambda: ops.linear_seg_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, o_sp, 1, 0, out_i8=y8))
     else:
         o_sp, r_sp, u_sp, z_sp = spec(0.05, 120), spec(0.03, 128), spec(0.06, 125), spec(0.03, 128)
-        run(f'i8 {label} {N}x{K} residual + LayerNorm, u8 out',
-            lambda: ops.linear_res_ln_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, 1, o_sp, r8, r_sp, u_sp, gamma, beta, 1e-12,
-                                         z_sp, y8))
+        for lean_flag in ('0', '1'):
+            os.environ['TQ_LINEAR_LEAN'] = lean_flag
+            run(f'{"LEAN" if lean_flag == "1" else "general"} i8 {label} {N}x{K} residual + LayerNorm, u8 out',
+                lambda: ops.linear_res_ln_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, 1, o_sp, r8, r_sp, u_sp, gamma, beta, 1e-12,
+                                             z_sp, y8))

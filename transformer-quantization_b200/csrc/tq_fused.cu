@@ -261,7 +261,7 @@ constexpr int AT = 128, AD = 64;
 // score MMA has retired), <= 85 registers.
 constexpr int kAttnThreads = 256;
 constexpr int kAttnTmemCols = 128;      // S: [0,128)  then O: [0,64)
-constexpr int kAttnSmem = 16384 * 3 + 512 + 2048 + 64 + 1024;   // Q K (later P) V | mask | max/sum exchange | barriers
+constexpr int kAttnSmem = 16384 * 3 + 512 + 2048 + 64 + 192 + 1024;   // Q K (later P) V | mask | max/sum exchange | barriers | quantizers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -366,6 +366,12 @@ __device__ __forceinline__ float scale_of(const tq_qspec& q) {
     float lo, hi;
     grid_of(q, lo, hi);
     return resolve(q, 0, lo, hi).scale;
+}
+
+__device__ __forceinline__ QP load_qp(const float* o) {
+    QP p;
+    p.scale = o[0]; p.zp = o[1]; p.lo = o[2]; p.hi = o[3]; p.rcp = o[4]; p.exact = __float_as_int(o[5]);
+    return p;
 }
 
 // exact RN(e / d) for a per-thread divisor: Markstein corrections with r = RN(1/d) (see tq::div_rn_t);
@@ -553,6 +559,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
     unsigned char* pP = bp;
     float* smask = reinterpret_cast<float*>(bp + 49152);
     float* xchg = reinterpret_cast<float*>(bp + 49152 + 512);
+    float* qsm = reinterpret_cast<float*>(bp + 49152 + 512 + 2048 + 64);      // [6][8] resolved quantizers
     const uint32_t bar0 = base + 49152 + 512 + 2048;
     const uint32_t bar_qk = bar0, bar_v = bar0 + 8, bar_s = bar0 + 16, bar_p = bar0 + 24, bar_o = bar0 + 32;
     const uint32_t tmem_slot = bar0 + 40;
@@ -586,6 +593,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp == 1 && lane < 6) {
+        // quantizer parameters are calibration constants, not outputs of the previous kernel: no dependency wait
+        const tq_qspec& q = lane == 0 ? a.s_q : lane == 1 ? a.p_q : lane == 2 ? a.c_q : lane == 3 ? a.q_q : lane == 4 ? a.k_q : a.v_q;
+        float lo, hi;
+        grid_of(q, lo, hi);
+        const QP p = resolve(q, 0, lo, hi);
+        float* o = qsm + lane * 8;
+        o[0] = p.scale; o[1] = p.zp; o[2] = p.lo; o[3] = p.hi; o[4] = p.rcp; o[5] = __int_as_float(p.exact);
+    }
     pdl_trigger();
     pdl_wait();
     if (threadIdx.x < AT) smask[threadIdx.x] = a.mask != nullptr ? a.mask[(int64_t)b * AT + threadIdx.x] : 0.0f;
@@ -609,15 +625,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;                      // query index == TMEM lane
         const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-        float lo, hi;
-        grid_of(a.s_q, lo, hi);
-        const QP qs = resolve(a.s_q, 0, lo, hi);
-        grid_of(a.p_q, lo, hi);
-        const QP qp = resolve(a.p_q, 0, lo, hi);
-        grid_of(a.c_q, lo, hi);
-        const QP qc = resolve(a.c_q, 0, lo, hi);
-        const float sqk = scale_of(a.q_q) * scale_of(a.k_q);
-        const float spv = qp.scale * scale_of(a.v_q);
+        // the six quantizers were resolved by six lanes of warp 1 before the block barrier (qsm): one global round
+        // trip for the whole CTA instead of a chain of dependent loads in every thread
+        const QP qs = load_qp(qsm + 0 * 8), qp = load_qp(qsm + 1 * 8), qc = load_qp(qsm + 2 * 8);
+        const float sqk = qsm[3 * 8] * qsm[4 * 8];
+        const float spv = qp.scale * qsm[5 * 8];
 
         if (qs.exact | qp.exact | qc.exact)
             attn_rows<false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);

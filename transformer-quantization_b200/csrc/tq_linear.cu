@@ -246,7 +246,8 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
     const float2 z = __fmul2_rn(x, splat(0.70710678118654752440f));
     const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
     const float2 d = __ffma2_rn(splat(0.3275911f), az, splat(1.0f));
-    const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));      // (a Newton reciprocal on the FMA pipe measured slower:
+    // MUFU runs beside the FMA pipe, six more FFMA2 per pair do not -- tools/microbench/fp32_pipes.cu)
     float2 p = __ffma2_rn(splat(-1.061405429f), t, splat(1.453152027f));     // -(a5 t + a4) ...
     p = __ffma2_rn(p, t, splat(-1.421413741f));
     p = __ffma2_rn(p, t, splat(0.284496736f));
@@ -1331,11 +1332,20 @@ __device__ __forceinline__ void pack_bytes16(uint32_t (&w)[4], const uint32_t (&
         w[i] = __byte_perm(__byte_perm(b[4 * i], b[4 * i + 1], 0x0040), __byte_perm(b[4 * i + 2], b[4 * i + 3], 0x0040), 0x5410);
 }
 
+// Loop shape of both epilogues.  The ncu source view of the first version (32-column bodies, 1100 instructions in
+// the LayerNorm pass, each executed three times per warp) showed `no_instruction` -- instruction fetch -- as the top
+// stall of the hot loop: straight-line code that runs only a few times per CTA has to fit the instruction caches.
+// So: a 32-column slice is LOADED at once (tcgen05.ld.x32, the next slice in flight behind it), but PROCESSED as two
+// 16-column halves by one compact loop body (8 column pairs, ~200-400 instructions) that always works on registers
+// v[0..15]; the second half is rotated down by register moves.
+
 // ---- plain epilogue: y = Q(act(acc * cs + bias)) for one 128 x BN accumulator tile ---------------------
-// segment parameters sg[]: 0 cs, 1 s, 2 r, 3 clo, 4 chi, 5 (lo - clo) + 1.5 * 2^23, 6 exact flag
+// segment parameters sg[]: 0 cs, 1 s, 2 r, 3 clo, 4 chi, 5 zp + 1.5 * 2^23, 6 exact flag
 template <int BN, int ACT, bool FAST, bool OUT8>
 __device__ __forceinline__ void epi_plain(const Args& ep, const float4* __restrict__ Pcol, const float* __restrict__ sg,
                                           uint32_t tmem_tile, int half, int64_t row, bool row_ok, int64_t n0, int64_t N) {
+    // (persistent kernel, 2-3 tiles per CTA: here the fully unrolled slice loop with two register sets measured
+    // fastest -- 18.7 k cycles for the Q|K|V GEMM against 19.9 k for the compact forms, profiles/r2_trace_tiles_lean.txt)
     constexpr int NIT = BN / 64;
     const QReg q = qreg_of(sg[1], sg[2], sg[3], sg[4]);
     const float2 cs2 = splat(sg[0]), off2 = splat(sg[5]);
@@ -1348,11 +1358,10 @@ __device__ __forceinline__ void epi_plain(const Args& ep, const float4* __restri
         uint32_t (&v)[32] = (it & 1) ? vb : va;
         uint32_t (&vn)[32] = (it & 1) ? va : vb;
         tmem_ld_fence(v);
-        if (it + 1 < NIT) tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32 + (it + 1) * 64), vn);
         const int c0 = half * 32 + it * 64;
+        if (it + 1 < NIT) tmem_ld32_nowait(tmem_tile + (uint32_t)(c0 + 64), vn);
         const float4* P = Pcol + (c0 >> 1);
-        uint32_t w[16];
-        uint32_t b[16];
+        uint32_t w[16], b[16];
 #pragma unroll
         for (int jp = 0; jp < 16; ++jp) {
             const float4 pp = P[jp];
@@ -1387,17 +1396,19 @@ __device__ __forceinline__ void epi_plain(const Args& ep, const float4* __restri
 }
 
 // ---- residual + LayerNorm epilogue (one tile per CTA, cluster over the N tiles of a row panel) ----------
-//   loop 1   k = Q2( s1 * Q1(acc * cs + bias) + s_r * (r_int - zp_r) )  centred integers, parked as bf16 pairs in
+//   pass 1   k = Q2( s1 * Q1(acc * cs + bias) + s_r * (r_int - zp_r) )  centred integers, parked as bf16 pairs in
 //            the accumulator columns just read; S1 += k, S2 += k * k  (exact: |k| <= 255, <= 128 columns per thread)
 //   exchange the two halves of a row -> every CTA of the cluster (DSMEM, int32) -> one cluster barrier
 //   mean = s2 * S1 / N, var = s2^2 * (S2 - S1^2 / N) / N  in fp64 from the exact totals, rounded once to fp32
-//   loop 2   z = Q3( (s2 * k - mean) * rstd * gamma + beta )
+//   pass 2   z = Q3( (s2 * k - mean) * rstd * gamma + beta )
 // segment parameters sg[]: 0 cs, 1-4 q1 {s, r, clo, chi}, 6 exact, 7-10 q2 {s, r, clo, chi}, 11 res scale,
-// 12 2^23 + res zp, 13-16 q3 {s, r, clo, chi}, 17 (lo3 - clo3) + 1.5 * 2^23
+// 12 2^23 + res zp, 13-16 q3 {s, r, clo, chi}, 17 zp3 + 1.5 * 2^23
+// r0 / r1: the residual row pieces of the first two slices, requested before the accumulator was waited for
 template <int BN, bool FAST>
 __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restrict__ Pcol, const float4* __restrict__ Pgb,
                                            const float* __restrict__ sg, int2* part, int2* xs, uint32_t tmem_tile, int half,
-                                           int quarter, int lane, int64_t row, bool row_ok, int64_t n0, int64_t N) {
+                                           int quarter, int lane, int64_t row, bool row_ok, int64_t n0, int64_t N,
+                                           uint32_t (&rn)[8], uint32_t (&rn2)[8]) {
     constexpr int NIT = BN / 64;
     const QReg q1 = qreg_of(sg[1], sg[2], sg[3], sg[4]);
     const QReg q2 = qreg_of(sg[7], sg[8], sg[9], sg[10]);
@@ -1405,55 +1416,56 @@ __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restr
     const float s1 = sg[1], rs = sg[11], roff = sg[12], s2 = sg[7];
     const int rl = quarter * 32 + lane;
     const unsigned char* rrow = ep.res_u8 + row * N + n0;
-    uint32_t va[32], vb[32];
-    uint32_t rw[8], rn[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) rn[i] = 0u;
-    tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32), va);
-    if (row_ok) ldg256(rrow + half * 32, rn);
-    float S1 = 0.0f, S2 = 0.0f;
-#pragma unroll
+    uint32_t v[32], vn[32];
+    uint32_t rw[8];
+    tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32), vn);
+    float2 S1 = make_float2(0.0f, 0.0f), S2 = make_float2(0.0f, 0.0f);
+#pragma unroll 1
     for (int it = 0; it < NIT; ++it) {
-        uint32_t (&v)[32] = (it & 1) ? vb : va;
-        uint32_t (&vn)[32] = (it & 1) ? va : vb;
-        tmem_ld_fence(v);
+        tmem_ld_fence(vn);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rw[i] = rn[i];
+        for (int i = 0; i < 32; ++i) v[i] = vn[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rw[i] = rn[i]; rn[i] = rn2[i]; }
         const int c0 = half * 32 + it * 64;
-        if (it + 1 < NIT) {
-            tmem_ld32_nowait(tmem_tile + (uint32_t)(c0 + 64), vn);
-            if (row_ok) ldg256(rrow + c0 + 64, rn);
-        }
-        const float4* P = Pcol + (c0 >> 1);
-        uint32_t kp[16];
+        if (it + 1 < NIT) tmem_ld32_nowait(tmem_tile + (uint32_t)(c0 + 64), vn);
+        if (it + 2 < NIT && row_ok) ldg256(rrow + c0 + 128, rn2);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const float4* P = Pcol + (c0 >> 1) + 8 * h;
+            uint32_t kp[8];
 #pragma unroll
-        for (int jp = 0; jp < 16; ++jp) {
-            const float4 pp = P[jp];
-            const float2 a = make_float2(__int2float_rn((int)v[2 * jp] - __float_as_int(pp.z)),
-                                         __int2float_rn((int)v[2 * jp + 1] - __float_as_int(pp.w)));
-            const float2 f = __ffma2_rn(a, cs2, make_float2(pp.x, pp.y));
-            const float2 c = ctr2_t<FAST>(f, q1);
-            // residual bytes -> floats without the conversion unit: 0x4B000000 | b = 2^23 + b, minus (2^23 + zp): exact
-            const uint32_t wd = rw[jp >> 1];
-            const uint32_t lo = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7652 : 0x7650);
-            const uint32_t hi = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7653 : 0x7651);
-            const float2 rc = make_float2(__fsub_rn(__uint_as_float(lo), roff), __fsub_rn(__uint_as_float(hi), roff));
-            // fl(s1 * c) + fl(s_r * r) as the reference materialises them: scalar multiplies (a packed multiply
-            // feeding a packed add would be contracted into FFMA2)
-            const float2 sum = __fadd2_rn(make_float2(__fmul_rn(s1, c.x), __fmul_rn(s1, c.y)),
-                                          make_float2(__fmul_rn(rs, rc.x), __fmul_rn(rs, rc.y)));
-            const float2 k = ctr2_t<FAST>(sum, q2);
-            S1 = __fadd_rn(S1, __fadd_rn(k.x, k.y));
-            S2 = __fmaf_rn(k.x, k.x, S2);
-            S2 = __fmaf_rn(k.y, k.y, S2);
-            kp[jp] = pack_bf16(k);
+            for (int jp = 0; jp < 8; ++jp) {
+                const float4 pp = P[jp];
+                const float2 a = make_float2(__int2float_rn((int)v[2 * jp] - __float_as_int(pp.z)),
+                                             __int2float_rn((int)v[2 * jp + 1] - __float_as_int(pp.w)));
+                const float2 f = __ffma2_rn(a, cs2, make_float2(pp.x, pp.y));
+                const float2 c = ctr2_t<FAST>(f, q1);
+                // residual bytes -> floats without the conversion unit: 0x4B000000 | b = 2^23 + b, minus (2^23 + zp): exact
+                const uint32_t wd = rw[jp >> 1];
+                const uint32_t lo = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7652 : 0x7650);
+                const uint32_t hi = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7653 : 0x7651);
+                const float2 rc = make_float2(__fsub_rn(__uint_as_float(lo), roff), __fsub_rn(__uint_as_float(hi), roff));
+                // fl(s1 * c) + fl(s_r * r) as the reference materialises them: scalar multiplies (a packed multiply
+                // feeding a packed add would be contracted into FFMA2)
+                const float2 sum = __fadd2_rn(make_float2(__fmul_rn(s1, c.x), __fmul_rn(s1, c.y)),
+                                              make_float2(__fmul_rn(rs, rc.x), __fmul_rn(rs, rc.y)));
+                const float2 k = ctr2_t<FAST>(sum, q2);
+                S1 = __fadd2_rn(S1, k);                      // integers below 2^24: exact
+                S2 = __ffma2_rn(k, k, S2);
+                kp[jp] = pack_bf16(k);
+            }
+            tmem_st8_nowait(tmem_tile + (uint32_t)(c0 + 8 * h), kp);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i + 16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rw[i] = rw[i + 4];
         }
-        tmem_st16_nowait(tmem_tile + (uint32_t)c0, kp);
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tmem_st_wait();
     if (threadIdx.x == 0) TQL_TRACE(11);
     // ---- exchange ----
-    part[half * BM + rl] = make_int2(__float2int_rn(S1), __float2int_rn(S2));
+    part[half * BM + rl] = make_int2(__float2int_rn(S1.x) + __float2int_rn(S1.y), __float2int_rn(S2.x) + __float2int_rn(S2.y));
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const uint32_t cn = cluster_nctarank(), my = cluster_ctarank();
     if (half == 0) {
@@ -1475,47 +1487,49 @@ __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restr
     }
     float mean, rstd;
     ln_stats_from_sums(T1, T2, N, s2, ep.ln_eps, mean, rstd);
-    // ---- loop 2: normalise, affine, output quantizer ----
+    // ---- pass 2: normalise, affine, output quantizer ----
     const QReg q3 = qreg_of(sg[13], sg[14], sg[15], sg[16]);
     const float2 nmean = splat(-mean), rstd2 = splat(rstd), off3 = splat(sg[17]);
     unsigned char* o8 = reinterpret_cast<unsigned char*>(ep.y_u8) + row * N + n0;
-    uint32_t ka[16], kb[16];
-    tmem_ld16_nowait(tmem_tile + (uint32_t)(half * 32), ka);
-#pragma unroll
+    uint32_t kq[16], kn[16];
+    tmem_ld16_nowait(tmem_tile + (uint32_t)(half * 32), kn);
+#pragma unroll 1
     for (int it = 0; it < NIT; ++it) {
-        uint32_t (&kq)[16] = (it & 1) ? kb : ka;
-        uint32_t (&kn)[16] = (it & 1) ? ka : kb;
-        tmem_ld_fence(kq);
+        tmem_ld_fence(kn);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) kq[i] = kn[i];
         const int c0 = half * 32 + it * 64;
         if (it + 1 < NIT) tmem_ld16_nowait(tmem_tile + (uint32_t)(c0 + 64), kn);
-        const float4* G = Pgb + (c0 >> 1);
-        uint32_t w8[8], wc[16], b[16];
+        uint32_t held[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const float4* G = Pgb + (c0 >> 1) + 8 * h;
+            uint32_t wc[8], b[16];
 #pragma unroll
-        for (int jp = 0; jp < 16; ++jp) {
-            const float2 v = make_float2(__fmul_rn(s2, __uint_as_float(kq[jp] << 16)),
-                                         __fmul_rn(s2, __uint_as_float(kq[jp] & 0xffff0000u)));
-            const float4 gb = G[jp];
-            float2 y = __fmul2_rn(__fadd2_rn(v, nmean), rstd2);
-            y = __ffma2_rn(y, make_float2(gb.x, gb.y), make_float2(gb.z, gb.w));
-            const float2 k3 = ctr2_t<FAST>(y, q3);
-            wc[jp] = pack_bf16(k3);
-            const float2 t = __fadd2_rn(k3, off3);
-            b[2 * (jp & 7)] = __float_as_uint(t.x);
-            b[2 * (jp & 7) + 1] = __float_as_uint(t.y);
-            if ((jp & 7) == 7) {
-                uint32_t w4[4];
-                pack_bytes16(w4, b);
+            for (int jp = 0; jp < 8; ++jp) {
+                const float2 x = make_float2(__fmul_rn(s2, __uint_as_float(kq[jp] << 16)),
+                                             __fmul_rn(s2, __uint_as_float(kq[jp] & 0xffff0000u)));
+                const float4 gb = G[jp];
+                float2 y = __fmul2_rn(__fadd2_rn(x, nmean), rstd2);
+                y = __ffma2_rn(y, make_float2(gb.x, gb.y), make_float2(gb.z, gb.w));
+                const float2 k3 = ctr2_t<FAST>(y, q3);
+                wc[jp] = pack_bf16(k3);
+                const float2 t = __fadd2_rn(k3, off3);
+                b[2 * jp] = __float_as_uint(t.x);
+                b[2 * jp + 1] = __float_as_uint(t.y);
+            }
+            uint32_t w4[4];
+            pack_bytes16(w4, b);
+            if (h == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) w8[(jp >> 3) * 4 + i] = w4[i];
+                for (int i = 0; i < 4; ++i) held[i] = w4[i];
+            } else if (row_ok) {
+                const uint32_t o[8] = {held[0], held[1], held[2], held[3], w4[0], w4[1], w4[2], w4[3]};
+                stg256(o8 + c0, o);
             }
-        }
-        if (row_ok) {
-            stg256(o8 + c0, w8);
-            if (ep.y_ctr != nullptr) {
-                __nv_bfloat16* oc = ep.y_ctr + row * N + n0 + c0;
-                stg256(oc, *reinterpret_cast<uint32_t(*)[8]>(&wc[0]));
-                stg256(oc + 16, *reinterpret_cast<uint32_t(*)[8]>(&wc[8]));
-            }
+            if (row_ok && ep.y_ctr != nullptr) stg256(ep.y_ctr + row * N + n0 + c0 + 16 * h, wc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) kq[i] = kq[i + 8];
         }
     }
 }
@@ -1662,41 +1676,79 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     } else if (warp == kParWarp) {
         // ===================== parameter warp =====================
-        float lo, hi;
-        grid_of(ep.a_q, lo, hi);
-        const QP aq = resolve(ep.a_q, 0, lo, hi);
-        const int a_zp = (int)aq.zp;
-        if (lane < ep.nseg && lane < kMaxSeg) {
-            float* sg = segp + lane * kSegFloats;
-            float wlo, whi, qlo, qhi;
-            grid_of(ep.w_q, wlo, whi);
-            grid_of(ep.out_q, qlo, qhi);
-            const QP wq = resolve(ep.w_q, lane, wlo, whi);
-            const QP oq = resolve(ep.out_q, lane, qlo, qhi);
-            int exact = oq.exact;
-            sg[0] = __fmul_rn(aq.scale, wq.scale);
-            sg[1] = oq.scale; sg[2] = oq.rcp; sg[3] = qlo - oq.zp; sg[4] = qhi - oq.zp;
-            sg[5] = __fadd_rn(oq.zp, 12582912.0f);               // x_int = k + zp, + 1.5 * 2^23
-            if (LNF) {
-                float l2, h2, l3, h3, lr, hr;
-                grid_of(ep.out2_q, l2, h2);
-                grid_of(ep.ln_q, l3, h3);
-                grid_of(ep.res_q, lr, hr);
-                const QP q2 = resolve(ep.out2_q, 0, l2, h2), q3 = resolve(ep.ln_q, 0, l3, h3), rq = resolve(ep.res_q, 0, lr, hr);
-                exact |= q2.exact | q3.exact;
-                sg[7] = q2.scale; sg[8] = q2.rcp; sg[9] = l2 - q2.zp; sg[10] = h2 - q2.zp;
-                sg[11] = rq.scale; sg[12] = __fadd_rn(8388608.0f, rq.zp);
-                sg[13] = q3.scale; sg[14] = q3.rcp; sg[15] = l3 - q3.zp; sg[16] = h3 - q3.zp;
-                sg[17] = __fadd_rn(q3.zp, 12582912.0f);
+        // One lane per quantizer: lane 0 a_q, 1 res_q, 2 out2_q, 3 ln_q, 4.. w_q[j], 8.. out_q[j] -- their (independent)
+        // global loads are in flight together; the first tile's column loads are issued before any of them is used.
+        QP mine = make_qp(1.0f, 0.0f, 0.0f, 0.0f);
+        {
+            float lo = 0.0f, hi = 0.0f;
+            const tq_qspec* qs = nullptr;
+            int slot = 0;
+            if (lane == 0) qs = &ep.a_q;
+            else if (LNF && lane == 1) qs = &ep.res_q;
+            else if (LNF && lane == 2) qs = &ep.out2_q;
+            else if (LNF && lane == 3) qs = &ep.ln_q;
+            else if (lane >= 4 && lane < 4 + ep.nseg) { qs = &ep.w_q; slot = lane - 4; }
+            else if (lane >= 8 && lane < 8 + ep.nseg) { qs = &ep.out_q; slot = lane - 8; }
+            if (qs != nullptr) {
+                grid_of(*qs, lo, hi);
+                mine = resolve(*qs, slot, lo, hi);
             }
-            sg[6] = __int_as_float(exact);
+        }
+        float4 first[(BN / 2 + 31) / 32];
+        float4 gb[(BN / 2 + 31) / 32];
+        if (tile0 < tiles) {
+            const int64_t n0 = (tile0 % n_tiles) * BN;
+#pragma unroll
+            for (int i = 0; i < (BN / 2 + 31) / 32; ++i) {
+                const int jp = lane + 32 * i;
+                first[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                gb[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (jp < BN / 2) {
+                    const int64_t n = n0 + 2 * jp;
+                    first[i] = make_float4(ep.bias != nullptr ? ep.bias[n] : 0.0f, ep.bias != nullptr ? ep.bias[n + 1] : 0.0f,
+                                           __int_as_float(ep.w_rowsum[n]), __int_as_float(ep.w_rowsum[n + 1]));
+                    if (LNF) gb[i] = make_float4(ep.ln_gamma[n], ep.ln_gamma[n + 1], ep.ln_beta[n], ep.ln_beta[n + 1]);
+                }
+            }
+        }
+        // quantizers -> every lane (shuffles), segment parameters by lanes < nseg
+        const float a_scale = __shfl_sync(0xffffffffu, mine.scale, 0);
+        const int a_zp = (int)__shfl_sync(0xffffffffu, mine.zp, 0);
+        {
+            const int j = lane < ep.nseg ? lane : 0;
+            const float w_scale = __shfl_sync(0xffffffffu, mine.scale, 4 + j);
+            const float o_scale = __shfl_sync(0xffffffffu, mine.scale, 8 + j), o_rcp = __shfl_sync(0xffffffffu, mine.rcp, 8 + j);
+            const float o_zp = __shfl_sync(0xffffffffu, mine.zp, 8 + j), o_lo = __shfl_sync(0xffffffffu, mine.lo, 8 + j);
+            const float o_hi = __shfl_sync(0xffffffffu, mine.hi, 8 + j);
+            int exact = __shfl_sync(0xffffffffu, mine.exact, 8 + j);
+            const float r_scale = __shfl_sync(0xffffffffu, mine.scale, 1), r_zp = __shfl_sync(0xffffffffu, mine.zp, 1);
+            const float s2 = __shfl_sync(0xffffffffu, mine.scale, 2), r2 = __shfl_sync(0xffffffffu, mine.rcp, 2);
+            const float z2 = __shfl_sync(0xffffffffu, mine.zp, 2), l2 = __shfl_sync(0xffffffffu, mine.lo, 2);
+            const float h2 = __shfl_sync(0xffffffffu, mine.hi, 2);
+            const int e2 = __shfl_sync(0xffffffffu, mine.exact, 2);
+            const float s3 = __shfl_sync(0xffffffffu, mine.scale, 3), r3 = __shfl_sync(0xffffffffu, mine.rcp, 3);
+            const float z3 = __shfl_sync(0xffffffffu, mine.zp, 3), l3 = __shfl_sync(0xffffffffu, mine.lo, 3);
+            const float h3 = __shfl_sync(0xffffffffu, mine.hi, 3);
+            const int e3 = __shfl_sync(0xffffffffu, mine.exact, 3);
+            if (lane < ep.nseg && lane < kMaxSeg) {
+                float* sg = segp + lane * kSegFloats;
+                sg[0] = __fmul_rn(a_scale, w_scale);
+                sg[1] = o_scale; sg[2] = o_rcp; sg[3] = o_lo - o_zp; sg[4] = o_hi - o_zp;
+                sg[5] = __fadd_rn(o_zp, 12582912.0f);               // x_int = k + zp, + 1.5 * 2^23
+                if (LNF) {
+                    exact |= e2 | e3;
+                    sg[7] = s2; sg[8] = r2; sg[9] = l2 - z2; sg[10] = h2 - z2;
+                    sg[11] = r_scale; sg[12] = __fadd_rn(8388608.0f, r_zp);
+                    sg[13] = s3; sg[14] = r3; sg[15] = l3 - z3; sg[16] = h3 - z3;
+                    sg[17] = __fadd_rn(z3, 12582912.0f);
+                }
+                sg[6] = __int_as_float(exact);
+            }
         }
         if (LNF && tile0 < tiles) {
-            const int64_t n0 = (tile0 % n_tiles) * BN;
-            for (int jp = lane; jp < BN / 2; jp += 32) {
-                const int64_t n = n0 + 2 * jp;
-                Pgb[jp] = make_float4(ep.ln_gamma[n], ep.ln_gamma[n + 1], ep.ln_beta[n], ep.ln_beta[n + 1]);
-            }
+#pragma unroll
+            for (int i = 0; i < (BN / 2 + 31) / 32; ++i)
+                if (lane + 32 * i < BN / 2) Pgb[lane + 32 * i] = gb[i];
         }
         int pb = 0;
         uint32_t pphase = 0;
@@ -1704,10 +1756,18 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int64_t n0 = (t % n_tiles) * BN;
             mbar_wait(pempty_bar(pb), pphase ^ 1u);
             float4* P = Pcol + pb * (BN / 2);
-            for (int jp = lane; jp < BN / 2; jp += 32) {
-                const int64_t n = n0 + 2 * jp;
-                const float b0 = ep.bias != nullptr ? ep.bias[n] : 0.0f, b1 = ep.bias != nullptr ? ep.bias[n + 1] : 0.0f;
-                P[jp] = make_float4(b0, b1, __int_as_float(a_zp * ep.w_rowsum[n]), __int_as_float(a_zp * ep.w_rowsum[n + 1]));
+            if (t == tile0) {
+#pragma unroll
+                for (int i = 0; i < (BN / 2 + 31) / 32; ++i)
+                    if (lane + 32 * i < BN / 2)
+                        P[lane + 32 * i] = make_float4(first[i].x, first[i].y, __int_as_float(a_zp * __float_as_int(first[i].z)),
+                                                       __int_as_float(a_zp * __float_as_int(first[i].w)));
+            } else {
+                for (int jp = lane; jp < BN / 2; jp += 32) {
+                    const int64_t n = n0 + 2 * jp;
+                    const float b0 = ep.bias != nullptr ? ep.bias[n] : 0.0f, b1 = ep.bias != nullptr ? ep.bias[n + 1] : 0.0f;
+                    P[jp] = make_float4(b0, b1, __int_as_float(a_zp * ep.w_rowsum[n]), __int_as_float(a_zp * ep.w_rowsum[n + 1]));
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pfull_bar(pb));
@@ -1734,12 +1794,22 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const bool row_ok = row < M;
             const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             const float4* P = Pcol + pb * (BN / 2);
+            uint32_t r0[8], r1[8];
+            if (LNF) {                                 // the residual does not depend on the MMAs: request it now
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r0[i] = r1[i] = 0u;
+                if (row_ok) {
+                    const unsigned char* rrow = ep.res_u8 + row * N + n0 + half * 32;
+                    ldg256(rrow, r0);
+                    if (BN > 64) ldg256(rrow + 64, r1);
+                }
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             if (threadIdx.x == 0) { TQL_TRACE(8); TQL_TTRACE(tno, 2); }
             if (LNF) {
-                if (exact) epi_res_ln<BN, false>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N);
-                else epi_res_ln<BN, true>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N);
+                if (exact) epi_res_ln<BN, false>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+                else epi_res_ln<BN, true>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
             } else {
                 if (exact) epi_plain<BN, ACT, false, OUT8>(ep, P, sg, tmem_tile, half, row, row_ok, n0, N);
                 else epi_plain<BN, ACT, true, OUT8>(ep, P, sg, tmem_tile, half, row, row_ok, n0, N);
