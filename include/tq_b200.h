@@ -55,7 +55,7 @@ typedef struct tq_qspec {
 /* ---- library info ------------------------------------------------------------------------- */
 int         tq_version(void);              /* ABI version: 1 = inference path; 2 adds the training-time entry points
                                               * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 (current) adds
-                                              * tq_linear_seg_qdq_i8 */
+                                              * tq_linear_seg_qdq_i8 and the tq_*_peg_* entry points */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
 
@@ -246,6 +246,29 @@ int tq_linear_qdq_bf16_o8(const void* a_ctr_bf16, const void* w_ctr_bf16, const 
 int tq_linear_seg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
                          void* y_ctr_bf16, void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q,
                          tq_qspec w_q, tq_qspec out_q, int32_t nseg, int32_t act_fn, void* stream);
+/* Per-embedding-group (PEG) activations through the int8 pipeline (BASELINE config 3; reference
+ * utils/per_embd_quant_utils.py:54-68, quantization/range_estimators.py:82-112, quantizers.py:213-217).
+ * A operand: x_int bytes of a tensor whose (scale, zero point) change per group of K / a_groups CONTRACTION columns
+ * (a_q carries a_groups parameter slots; groups are contiguous; K / a_groups a multiple of 128).  The k-loop runs
+ * group by group into ping-pong TMEM accumulators and the epilogue keeps  sum_g s_a[g] s_w (acc_g - zp_g * rowsum_g)
+ * in registers, so every integer partial sum is exact.  w_grp_rowsum: int32 [a_groups][N], sum of w_int over the K
+ * columns of each group.  Output side: tiles are 128 columns wide and every quantizer is constant per SEGMENT of
+ * seg_width columns (a multiple of 128; N / seg_width segments): w_q / out_q [/ res_q / out2_q / ln_q] carry 1 or
+ * N / seg_width slots -- a per-embedding-group OUTPUT quantizer with groups of >= 128 columns is a per-segment one.
+ * tq_linear_peg_res_ln_qdq_i8 is the residual + LayerNorm block (cluster of N / 128 <= 8 CTAs; the row statistics
+ * combine every member's exact integer sums with its own output scale in fp64).  a_groups = 1 gives per-tensor A
+ * with per-group outputs (the FFN-out block).  Exactly one of y_ctr_bf16 / y_i8 for the plain form. */
+int tq_linear_peg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_grp_rowsum, const float* bias,
+                         void* y_ctr_bf16, void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q,
+                         int32_t a_groups, tq_qspec w_q, int32_t w_params, tq_qspec out_q, int32_t out_params,
+                         int64_t seg_width, int32_t act_fn, void* stream);
+int tq_linear_peg_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_grp_rowsum, const float* bias,
+                                void* z_ctr_bf16, void* z_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q,
+                                int32_t a_groups, tq_qspec w_q, int32_t w_params, tq_qspec out_q,
+                                int32_t out_params, const void* res_i8, tq_qspec res_q, int32_t res_params,
+                                tq_qspec out2_q, int32_t out2_params, const float* ln_gamma_q,
+                                const float* ln_beta, float ln_eps, tq_qspec ln_q, int32_t ln_params,
+                                int64_t seg_width, void* stream);
 int tq_linear_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
                             float* z, void* z_ctr_bf16, void* z_i8, int64_t M, int64_t N, int64_t K,
                             tq_qspec a_q, tq_qspec w_q, int64_t w_q_params, tq_qspec out_q,
@@ -271,6 +294,12 @@ int tq_attention_qdq_bf16(const void* qkv_ctr_bf16, void* c_ctr_bf16, int32_t B,
 int tq_attention_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H,
                         int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q,
                         tq_qspec p_q, tq_qspec c_q, const float* mask, void* stream);
+/* ... with per-embedding-group quantizers on Q / K / V and on the context whose groups hold whole heads: q_q, k_q,
+ * v_q carry qkv_params slots and c_q c_params slots (1 or a divisor of H); head h uses slot h / (H / params). */
+int tq_attention_peg_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H,
+                            int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, int32_t qkv_params,
+                            tq_qspec s_q, tq_qspec p_q, tq_qspec c_q, int32_t c_params, const float* mask,
+                            void* stream);
 
 /* QuantLayerNorm over a quantized input (reference autoquant_utils.py:55-66 applied to the output of
  * a residual quantizer): x = in_scale * x_ctr; y = LayerNorm(x; gamma_q, beta, eps); out_q QDQ.

@@ -49,16 +49,18 @@ def test_per_tensor_configs(name):
         assert {m.quantizer.n_bits for m in mgrs} == {4, 8}
 
 
-def test_peg_config():
-    """config 3: the PEG sites carry per-dim parameters with exactly K = 6 distinct groups, the others stay per-tensor"""
-    model, recipe, _ = _run('bert_w8a8_peg')
+@pytest.mark.parametrize('name', ['bert_w8a8_peg', 'bert_w8a8_pegp'])
+def test_peg_config(name):
+    """config 3 (contiguous groups, and the range-permuted variant): the PEG sites carry per-dim parameters with exactly
+    K = 6 distinct groups, the others stay per-tensor"""
+    model, recipe, _ = _run(name)
     peg = [s.activation_quantizer for s in model.peg_sites()]
     assert len(peg) == 3 + 10 * len(model.layers)
     for mgr in peg:
         d = mgr.quantizer._delta.detach().numpy().reshape(-1)
         assert d.size == model.config.hidden_size and mgr.n_groups == 6
         assert len(np.unique(d)) <= 6
-        assert mgr.range_estimator.ranges is not None          # permutation ranges were collected
+        assert (mgr.range_estimator.ranges is not None) == (name == 'bert_w8a8_pegp')     # permutation ranges collected?
     others = [m for m in _managers(model) if m.quantizer.is_initialized and all(m is not p for p in peg)]
     assert others and all(m.quantizer._delta.numel() == 1 for m in others)
 

@@ -73,10 +73,14 @@ def run(name, steps, warmup, use_graph=True, device='cuda:0', tiny=False, batch=
     ids = batches[2].to(dev)
     mask = torch.ones_like(ids)
     forward, kind = model, 'module path'
-    if on_gpu and recipe.family == 'bert' and recipe.peg is None:
+    if on_gpu and recipe.family == 'bert':
         from engine.fused import FusedBertEngine, UnsupportedByEngine
+        from engine.fused_peg import FusedBertPegEngine
         try:
-            forward, kind = FusedBertEngine(model, recipe.batch, recipe.seq), 'fused engine'
+            if recipe.peg is None:
+                forward, kind = FusedBertEngine(model, recipe.batch, recipe.seq), 'fused engine'
+            else:
+                forward, kind = FusedBertPegEngine(model, recipe.batch, recipe.seq), 'fused PEG engine (engine/fused_peg.py)'
         except UnsupportedByEngine as e:
             kind = f'module path ({e})'
     with torch.no_grad():
@@ -117,7 +121,14 @@ def run(name, steps, warmup, use_graph=True, device='cuda:0', tiny=False, batch=
         if profile and on_gpu:
             prof = _profile_live(forward, ids, mask, ops)
     extra = {'kernel_profile': prof} if prof is not None else {}
-    return dict(extra, config=name, forward=kind, batch=recipe.batch, seq=recipe.seq, ms_per_step=ms,
+    hid = None
+    if hasattr(forward, 'hidden_states') and on_gpu:
+        with torch.no_grad():
+            ref_h = model.encode(ids, mask)
+            hs = float(ref_h.abs().max()) / 128.0
+            dh = (forward.hidden_states().float() - ref_h).abs()
+            hid = {'max_abs_diff_in_approx_steps': float(dh.max()) / hs, 'share_off_by_half_a_step': float((dh > 0.5 * hs).float().mean())}
+    return dict(extra, last_hidden_vs_module_path=hid, config=name, forward=kind, batch=recipe.batch, seq=recipe.seq, ms_per_step=ms,
                 tokens_per_s=recipe.batch * recipe.seq / ms * 1e3, library_launches_per_step=launches,
                 calibration_s=t_cal, cuda_graph=use_graph, logits_finite=bool(torch.isfinite(out).all()),
                 graph_equals_eager=bool(torch.equal(out, ref)) if use_graph else None,

@@ -360,6 +360,8 @@ struct AttnArgs {
     __nv_bfloat16* c_ctr;         // [B * AT, H * AD] centred context grid (or null)
     unsigned char* c_u8;          // [B * AT, H * AD] context x_int, one byte each (8-bit operand mode; or null)
     float inv_sqrt_d;             // 1 / sqrt(head_dim)
+    int32_t qkv_params, c_params; // parameter slots of q_q / k_q / v_q and of c_q: 1, or a divisor of H (per-embedding-group
+                                  // quantizers whose groups hold whole heads: head h uses slot h / (H / params))
 };
 
 __device__ __forceinline__ float scale_of(const tq_qspec& q) {
@@ -598,7 +600,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
         const tq_qspec& q = lane == 0 ? a.s_q : lane == 1 ? a.p_q : lane == 2 ? a.c_q : lane == 3 ? a.q_q : lane == 4 ? a.k_q : a.v_q;
         float lo, hi;
         grid_of(q, lo, hi);
-        const QP p = resolve(q, 0, lo, hi);
+        const int np = lane == 2 ? a.c_params : (lane >= 3 ? a.qkv_params : 1);
+        const QP p = resolve(q, np > 1 ? h / (a.H / np) : 0, lo, hi);
         float* o = qsm + lane * 8;
         o[0] = p.scale; o[1] = p.zp; o[2] = p.lo; o[3] = p.hi; o[4] = p.rcp; o[5] = __int_as_float(p.exact);
     }
@@ -666,7 +669,7 @@ extern "C" {
 
 static int attention_impl(const void* qkv_ctr_bf16, void* c_ctr_bf16, void* c_u8, int32_t B, int32_t T, int32_t H,
                           int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q, tq_qspec p_q,
-                          tq_qspec c_q, const float* mask, void* stream) {
+                          tq_qspec c_q, const float* mask, void* stream, int32_t qkv_params = 1, int32_t c_params = 1) {
     using namespace tq::fused;
     if (qkv_ctr_bf16 == nullptr || (c_ctr_bf16 == nullptr && c_u8 == nullptr) || B < 1 || H < 1) return TQ_EINVAL;
     if (T != AT || head_dim != AD) return TQ_EUNSUPPORTED;
@@ -701,6 +704,9 @@ static int attention_impl(const void* qkv_ctr_bf16, void* c_ctr_bf16, void* c_u8
     a.c_ctr = reinterpret_cast<__nv_bfloat16*>(c_ctr_bf16);
     a.c_u8 = reinterpret_cast<unsigned char*>(c_u8);
     a.inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
+    if (qkv_params < 1 || c_params < 1 || H % qkv_params != 0 || H % c_params != 0) return TQ_EINVAL;
+    a.qkv_params = qkv_params;
+    a.c_params = c_params;
     return tq::launch_pdl(attention_kernel, dim3(B * H), dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, 1, map, a);
 }
 
@@ -716,6 +722,14 @@ int tq_attention_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t
                         const float* mask, void* stream) {
     if (c_i8 == nullptr) return TQ_EINVAL;
     return attention_impl(qkv_ctr_bf16, nullptr, c_i8, B, T, H, head_dim, q_q, k_q, v_q, s_q, p_q, c_q, mask, stream);
+}
+
+int tq_attention_peg_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H, int32_t head_dim,
+                            tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, int32_t qkv_params, tq_qspec s_q, tq_qspec p_q,
+                            tq_qspec c_q, int32_t c_params, const float* mask, void* stream) {
+    if (c_i8 == nullptr) return TQ_EINVAL;
+    return attention_impl(qkv_ctr_bf16, nullptr, c_i8, B, T, H, head_dim, q_q, k_q, v_q, s_q, p_q, c_q, mask, stream, qkv_params,
+                          c_params);
 }
 
 static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {

@@ -1834,6 +1834,500 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                      : "memory");
 }
 
+// =====================================================================================================
+// PEG kernels: per-embedding-group activations through the lean int8 pipeline (BASELINE config 3,
+// reference utils/per_embd_quant_utils.py:54-68, quantization/range_estimators.py:82-112, quantizers.py:213-217).
+// With K groups along the hidden dimension the A operand's scale and zero point change every d / K columns of the
+// CONTRACTION, so one integer accumulator per output element is not enough.  The k-loop runs GROUP BY GROUP into two
+// ping-pong TMEM accumulators (128 columns each); the epilogue warps drain group g while the tensor core works on
+// group g + 1 and keep the running fp32 sum  sum_g (s_a[g] s_w) * (acc_g[n] - zp_g * rowsum_g[n])  in registers
+// (every partial product sum is an exact integer; one fp32 FMA per group and element).  The OUTPUT side of PEG
+// (per-group quantizers of q / k / v / g / u / x / h / y / z, per-group residual) costs nothing extra: tiles are 128
+// columns wide = aligned to the groups, so every quantizer is a per-TILE constant ("segment").
+// =====================================================================================================
+namespace peg {
+
+
+constexpr int BN = 128;
+constexpr int kMaxGroups = 8;
+constexpr int kSegFloats = 24;
+constexpr int kTmemColsPeg = 256;
+
+template <bool LNF>
+struct Cfg {
+    static constexpr int kABytes = BM * 128;
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    // per-tile parameter buffer: bias pairs [BN / 2] float2 | corr [G][BN] int32 | segment parameters | cs per group
+    static constexpr int kTileParBytes = (BN / 2) * 8 + kMaxGroups * BN * 4 + kSegFloats * 4 + kMaxGroups * 4 + 32;
+    static constexpr int kLnBytes = LNF ? (BN / 2) * 16 + 2 * BM * 8 + 8 * BM * 8 + 64 : 0;   // gamma|beta, half partials, cluster partials, cluster scales
+    static constexpr int kParamBytes = 2 * kTileParBytes + kLnBytes;
+    static constexpr int kStagesFit = (227 * 1024 - 1024 - kParamBytes - 256) / kStageBytes;
+    static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + (2 * kStages + 8) * 8 + 16 + 1024;
+};
+
+struct Args {
+    const float* bias;              // [N] or null
+    const int32_t* w_grp_rowsum;    // [G][N] sum of w_int over the K columns of group g
+    tq_qspec a_q;                   // G parameter slots (delta[G], zero_float[G]); asymmetric / unsigned grid
+    int32_t a_groups;               // G >= 1, K / G a multiple of 128
+    tq_qspec w_q, out_q;            // w_params / out_params slots (1 or nseg)
+    int32_t w_params, out_params;
+    int64_t seg_width;              // columns per segment (a multiple of 128)
+    void* y_u8;
+    __nv_bfloat16* y_ctr;
+    const unsigned char* res_u8;    // LNF: residual x_int bytes [M, N]
+    tq_qspec res_q, out2_q, ln_q;   // LNF: res_params / out2_params / ln_params slots (1 or nseg)
+    int32_t res_params, out2_params, ln_params;
+    const float* ln_gamma;
+    const float* ln_beta;
+    float ln_eps;
+};
+
+// segment parameters sg[] as in the lean kernels: 0 (unused), 1-4 q1 {s, r, clo, chi}, 5 zp1 + 1.5 * 2^23, 6 exact,
+// 7-10 q2, 11 res scale, 12 2^23 + res zp, 13-16 q3, 17 zp3 + 1.5 * 2^23
+
+// drain one group's accumulator (this warp's 64 columns) into the running sums
+template <bool FIRST>
+__device__ __forceinline__ void drain_group(float (&run)[64], uint32_t tmem_buf, int half, const int32_t* __restrict__ corr,
+                                            float csg) {
+    uint32_t v[32];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int c0 = half * 32 + s * 64;
+        tmem_ld32_nowait(tmem_buf + (uint32_t)c0, v);
+        tmem_ld_fence(v);
+        const int4* cr = reinterpret_cast<const int4*>(corr + c0);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const int4 c = cr[j4];
+            const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = __int2float_rn((int)v[4 * j4 + j] - cc[j]);
+                run[s * 32 + 4 * j4 + j] = FIRST ? __fmul_rn(csg, a) : __fmaf_rn(csg, a, run[s * 32 + 4 * j4 + j]);
+            }
+        }
+    }
+}
+
+template <int ACT, bool FAST, bool OUT8>
+__device__ __forceinline__ void finish_plain(const Args& ep, const float (&run)[64], const float2* __restrict__ Pb,
+                                             const float* __restrict__ sg, int half, int64_t row, bool row_ok, int64_t n0,
+                                             int64_t N) {
+    const QReg q = qreg_of(sg[1], sg[2], sg[3], sg[4]);
+    const float2 off2 = splat(sg[5]);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int c0 = half * 32 + s * 64;
+        uint32_t w[16], b[16];
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+            float2 f = __fadd2_rn(make_float2(run[s * 32 + 2 * jp], run[s * 32 + 2 * jp + 1]), Pb[(c0 >> 1) + jp]);
+            f = act2<ACT>(f);
+            const float2 k = ctr2_t<FAST>(f, q);
+            if (OUT8) {
+                const float2 t = __fadd2_rn(k, off2);
+                b[2 * (jp & 7)] = __float_as_uint(t.x);
+                b[2 * (jp & 7) + 1] = __float_as_uint(t.y);
+                if ((jp & 7) == 7) {
+                    uint32_t w4[4];
+                    pack_bytes16(w4, b);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[(jp >> 3) * 4 + i] = w4[i];
+                }
+            } else {
+                w[jp] = pack_bf16(k);
+            }
+        }
+        if (row_ok) {
+            if (OUT8) {
+                stg256(reinterpret_cast<unsigned char*>(ep.y_u8) + row * N + n0 + c0, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+            } else {
+                __nv_bfloat16* oc = ep.y_ctr + row * N + n0 + c0;
+                stg256(oc, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+                stg256(oc + 16, *reinterpret_cast<uint32_t(*)[8]>(&w[8]));
+            }
+        }
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void finish_res_ln(const Args& ep, const float (&run)[64], const float2* __restrict__ Pb,
+                                              const float4* __restrict__ Pgb, const float* __restrict__ sg, int2* part, int2* xs,
+                                              const float* xscale, uint32_t tmem_park, int half, int quarter, int lane, int64_t row, bool row_ok,
+                                              int64_t n0, int64_t N, const uint32_t (&r0)[8], const uint32_t (&r1)[8]) {
+    const QReg q1 = qreg_of(sg[1], sg[2], sg[3], sg[4]);
+    const QReg q2 = qreg_of(sg[7], sg[8], sg[9], sg[10]);
+    const float s1 = sg[1], rs = sg[11], roff = sg[12], s2 = sg[7];
+    const int rl = quarter * 32 + lane;
+    float2 S1 = make_float2(0.0f, 0.0f), S2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int c0 = half * 32 + s * 64;
+        uint32_t kp[16];
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+            const float2 f = __fadd2_rn(make_float2(run[s * 32 + 2 * jp], run[s * 32 + 2 * jp + 1]), Pb[(c0 >> 1) + jp]);
+            const float2 c = ctr2_t<FAST>(f, q1);
+            const uint32_t wd = s == 0 ? r0[jp >> 1] : r1[jp >> 1];
+            const uint32_t lo = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7652 : 0x7650);
+            const uint32_t hi = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7653 : 0x7651);
+            const float2 rc = make_float2(__fsub_rn(__uint_as_float(lo), roff), __fsub_rn(__uint_as_float(hi), roff));
+            const float2 sum = __fadd2_rn(make_float2(__fmul_rn(s1, c.x), __fmul_rn(s1, c.y)),
+                                          make_float2(__fmul_rn(rs, rc.x), __fmul_rn(rs, rc.y)));
+            const float2 k = ctr2_t<FAST>(sum, q2);
+            S1 = __fadd2_rn(S1, k);
+            S2 = __ffma2_rn(k, k, S2);
+            kp[jp] = pack_bf16(k);
+        }
+        tmem_st16_nowait(tmem_park + (uint32_t)c0, kp);
+    }
+    tmem_st_wait();
+    part[half * BM + rl] = make_int2(__float2int_rn(S1.x) + __float2int_rn(S1.y), __float2int_rn(S2.x) + __float2int_rn(S2.y));
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const uint32_t cn = cluster_nctarank(), my = cluster_ctarank();
+    if (half == 0) {
+        const int2 pa = part[rl], pb = part[BM + rl];
+        const uint32_t dst = smem_u32(xs + (my * BM + rl));
+        for (uint32_t r = 0; r < cn; ++r) {
+            st_remote_f32(dst, r, __int_as_float(pa.x + pb.x));
+            st_remote_f32(dst + 4, r, __int_as_float(pa.y + pb.y));
+        }
+    }
+    cluster_sync_all();
+    // per-GROUP output scale s2: the LayerNorm input x = s2[g(n)] * k differs per cluster member, so the row statistics
+    // are combined from (S1, S2) of every member scaled by ITS s2 (exchanged with the sums)
+    double m = 0.0, e2 = 0.0;
+    for (uint32_t r = 0; r < cn; ++r) {
+        const int2 p = xs[r * BM + rl];
+        const double sr = (double)xscale[r];
+        m += sr * (double)p.x;
+        e2 += sr * sr * (double)p.y;
+    }
+    m /= (double)N;
+    double var = e2 / (double)N - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    const float mean = (float)m;
+    const float rstd = __fdiv_rn(1.0f, sqrtf(__fadd_rn((float)var, ep.ln_eps)));
+    const QReg q3 = qreg_of(sg[13], sg[14], sg[15], sg[16]);
+    const float2 nmean = splat(-mean), rstd2 = splat(rstd), off3 = splat(sg[17]);
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const int c0 = half * 32 + s * 64;
+        uint32_t kq[16];
+        tmem_ld16_nowait(tmem_park + (uint32_t)c0, kq);
+        tmem_ld_fence(kq);
+        const float4* G = Pgb + (c0 >> 1);
+        uint32_t w8[8], wc[16], b[16];
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+            const float2 x = make_float2(__fmul_rn(s2, __uint_as_float(kq[jp] << 16)),
+                                         __fmul_rn(s2, __uint_as_float(kq[jp] & 0xffff0000u)));
+            const float4 gb = G[jp];
+            float2 y = __fmul2_rn(__fadd2_rn(x, nmean), rstd2);
+            y = __ffma2_rn(y, make_float2(gb.x, gb.y), make_float2(gb.z, gb.w));
+            const float2 k3 = ctr2_t<FAST>(y, q3);
+            wc[jp] = pack_bf16(k3);
+            const float2 t = __fadd2_rn(k3, off3);
+            b[2 * (jp & 7)] = __float_as_uint(t.x);
+            b[2 * (jp & 7) + 1] = __float_as_uint(t.y);
+            if ((jp & 7) == 7) {
+                uint32_t w4[4];
+                pack_bytes16(w4, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w8[(jp >> 3) * 4 + i] = w4[i];
+            }
+        }
+        if (row_ok) {
+            stg256(reinterpret_cast<unsigned char*>(ep.y_u8) + row * N + n0 + c0, w8);
+            if (ep.y_ctr != nullptr) {
+                __nv_bfloat16* oc = ep.y_ctr + row * N + n0 + c0;
+                stg256(oc, *reinterpret_cast<uint32_t(*)[8]>(&wc[0]));
+                stg256(oc + 16, *reinterpret_cast<uint32_t(*)[8]>(&wc[8]));
+            }
+        }
+    }
+}
+
+template <int ACT, bool LNF, bool OUT8>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  int64_t M, int64_t N, int64_t K, int ring, Args ep) {
+    using C = Cfg<LNF>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+    unsigned char* par_ptr = base_ptr + C::kStages * C::kStageBytes;
+    auto tile_par = [&](int b) { return par_ptr + b * C::kTileParBytes; };
+    float4* Pgb = reinterpret_cast<float4*>(par_ptr + 2 * C::kTileParBytes);
+    int2* part = reinterpret_cast<int2*>(par_ptr + 2 * C::kTileParBytes + (BN / 2) * 16);
+    int2* xs = part + 2 * BM;                                                 // [8][BM] (S1, S2) of every cluster member
+    float* xscale = reinterpret_cast<float*>(xs + 8 * BM);                    // [8] output scale s2 of every cluster member
+    const uint32_t bar0 = base + C::kStages * C::kStageBytes + C::kParamBytes;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (C::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 2 + s); };
+    auto pfull_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 4 + s); };
+    auto pempty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 6 + s); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * C::kStages + 8);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+        base_ptr + C::kStages * C::kStageBytes + C::kParamBytes + 8 * (2 * C::kStages + 8));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
+    const int64_t tiles = m_tiles * n_tiles;
+    const int64_t tile0 = blockIdx.x, tile_step = gridDim.x;
+    const int G = ep.a_groups;
+    const int kb_per_group = (int)(K / 128) / G;
+    const int num_kb = kb_per_group * G;
+
+    int p_stage = 0, p_pre = 0;
+    uint32_t p_phase = 0;
+    if (warp == kProdWarp && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tile0 < tiles) {
+            pdl_wait();
+            const int32_t m0 = (int32_t)((tile0 / n_tiles) * BM), n0 = (int32_t)((tile0 % n_tiles) * BN);
+            p_pre = num_kb < ring ? num_kb : ring;
+            for (int kb = 0; kb < p_pre; ++kb) {
+                mbar_expect_tx(full_bar(p_stage), C::kStageBytes);
+                const uint32_t sa = base + p_stage * C::kStageBytes;
+                tma_load_2d<1>(sa, &map_a, kb * 128, m0, full_bar(p_stage));
+                tma_load_2d<1>(sa + C::kABytes, &map_w, kb * 128, n0, full_bar(p_stage));
+                if (++p_stage == ring) { p_stage = 0; p_phase ^= 1u; }
+            }
+        }
+    }
+    if (warp == kMmaWarp) {
+        if (lane == 0) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(tfull_bar(s), 1);
+                mbar_init(tempty_bar(s), kEpiWarps);
+                mbar_init(pfull_bar(s), 1);
+                mbar_init(pempty_bar(s), kEpiWarps);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)kTmemColsPeg)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp == kProdWarp) {
+        if (lane == 0) {
+            int stage = p_stage;
+            uint32_t phase = p_phase;
+            for (int64_t t = tile0; t < tiles; t += tile_step) {
+                const int32_t m0 = (int32_t)((t / n_tiles) * BM), n0 = (int32_t)((t % n_tiles) * BN);
+                for (int kb = (t == tile0 ? p_pre : 0); kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), C::kStageBytes);
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    tma_load_2d<1>(sa, &map_a, kb * 128, m0, full_bar(stage));
+                    tma_load_2d<1>(sa + C::kABytes, &map_w, kb * 128, n0, full_bar(stage));
+                    if (++stage == ring) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        if (LNF) {
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            const uint32_t w_s8 = (ep.w_q.zero_float == nullptr && ep.w_q.is_signed != nullptr && *ep.w_q.is_signed) ? 1u : 0u;
+            const uint32_t idesc = (2u << 4) | (w_s8 << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0, buf = 0;
+            uint32_t phase = 0, bphase = 0;
+            for (int64_t t = tile0; t < tiles; t += tile_step) {
+                for (int g = 0; g < G; ++g) {
+                    mbar_wait(tempty_bar(buf), bphase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    for (int kb = 0; kb < kb_per_group; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * C::kStageBytes;
+                        const uint64_t adesc = make_desc_sw128(sa), bdesc = make_desc_sw128(sa + C::kABytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        tc_commit<1>(empty_bar(stage));
+                        if (++stage == ring) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit<1>(tfull_bar(buf));
+                    if (++buf == 2) { buf = 0; bphase ^= 1u; }
+                }
+            }
+        }
+        if (LNF) {
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else if (warp == kParWarp) {
+        // lanes 0..4: w_q, out_q, out2_q, ln_q, res_q of the tile's segment; lanes 8..8+G-1: a_q of group g
+        int pb = 0;
+        uint32_t pphase = 0;
+        bool first = true;
+        for (int64_t t = tile0; t < tiles; t += tile_step) {
+            const int64_t n0 = (t % n_tiles) * BN;
+            const int seg = (int)(n0 / ep.seg_width);
+            QP mine = make_qp(1.0f, 0.0f, 0.0f, 0.0f);
+            {
+                const tq_qspec* qs = nullptr;
+                int slot = 0;
+                if (lane == 0) { qs = &ep.w_q; slot = ep.w_params > 1 ? seg : 0; }
+                else if (lane == 1) { qs = &ep.out_q; slot = ep.out_params > 1 ? seg : 0; }
+                else if (LNF && lane == 2) { qs = &ep.out2_q; slot = ep.out2_params > 1 ? seg : 0; }
+                else if (LNF && lane == 3) { qs = &ep.ln_q; slot = ep.ln_params > 1 ? seg : 0; }
+                else if (LNF && lane == 4) { qs = &ep.res_q; slot = ep.res_params > 1 ? seg : 0; }
+                else if (lane >= 8 && lane < 8 + G) { qs = &ep.a_q; slot = lane - 8; }
+                if (qs != nullptr) {
+                    float lo, hi;
+                    grid_of(*qs, lo, hi);
+                    mine = resolve(*qs, slot, lo, hi);
+                }
+            }
+            mbar_wait(pempty_bar(pb), pphase ^ 1u);
+            unsigned char* tp = tile_par(pb);
+            float2* Pb = reinterpret_cast<float2*>(tp);
+            int32_t* corr = reinterpret_cast<int32_t*>(tp + (BN / 2) * 8);
+            float* sg = reinterpret_cast<float*>(tp + (BN / 2) * 8 + kMaxGroups * BN * 4);
+            float* csg = sg + kSegFloats;
+            for (int jp = lane; jp < BN / 2; jp += 32) {
+                const int64_t n = n0 + 2 * jp;
+                Pb[jp] = make_float2(ep.bias != nullptr ? ep.bias[n] : 0.0f, ep.bias != nullptr ? ep.bias[n + 1] : 0.0f);
+                if (LNF && first) Pgb[jp] = make_float4(ep.ln_gamma[n], ep.ln_gamma[n + 1], ep.ln_beta[n], ep.ln_beta[n + 1]);
+            }
+            const float w_scale = __shfl_sync(0xffffffffu, mine.scale, 0);
+            for (int g = 0; g < G; ++g) {
+                const int zp_g = (int)__shfl_sync(0xffffffffu, mine.zp, 8 + g);
+                const float s_g = __shfl_sync(0xffffffffu, mine.scale, 8 + g);
+                for (int c = lane; c < BN; c += 32) corr[g * BN + c] = zp_g * ep.w_grp_rowsum[(int64_t)g * N + n0 + c];
+                if (lane == 0) csg[g] = __fmul_rn(s_g, w_scale);
+            }
+            {
+                const float o_s = __shfl_sync(0xffffffffu, mine.scale, 1), o_r = __shfl_sync(0xffffffffu, mine.rcp, 1);
+                const float o_z = __shfl_sync(0xffffffffu, mine.zp, 1), o_lo = __shfl_sync(0xffffffffu, mine.lo, 1);
+                const float o_hi = __shfl_sync(0xffffffffu, mine.hi, 1);
+                int exact = __shfl_sync(0xffffffffu, mine.exact, 1);
+                const float s2 = __shfl_sync(0xffffffffu, mine.scale, 2), r2 = __shfl_sync(0xffffffffu, mine.rcp, 2);
+                const float z2 = __shfl_sync(0xffffffffu, mine.zp, 2), l2 = __shfl_sync(0xffffffffu, mine.lo, 2);
+                const float h2 = __shfl_sync(0xffffffffu, mine.hi, 2);
+                const int e2 = __shfl_sync(0xffffffffu, mine.exact, 2);
+                const float s3 = __shfl_sync(0xffffffffu, mine.scale, 3), r3 = __shfl_sync(0xffffffffu, mine.rcp, 3);
+                const float z3 = __shfl_sync(0xffffffffu, mine.zp, 3), l3 = __shfl_sync(0xffffffffu, mine.lo, 3);
+                const float h3 = __shfl_sync(0xffffffffu, mine.hi, 3);
+                const int e3 = __shfl_sync(0xffffffffu, mine.exact, 3);
+                const float r_s = __shfl_sync(0xffffffffu, mine.scale, 4), r_z = __shfl_sync(0xffffffffu, mine.zp, 4);
+                if (lane == 0) {
+                    sg[1] = o_s; sg[2] = o_r; sg[3] = o_lo - o_z; sg[4] = o_hi - o_z;
+                    sg[5] = __fadd_rn(o_z, 12582912.0f);
+                    if (LNF) {
+                        exact |= e2 | e3;
+                        sg[7] = s2; sg[8] = r2; sg[9] = l2 - z2; sg[10] = h2 - z2;
+                        sg[11] = r_s; sg[12] = __fadd_rn(8388608.0f, r_z);
+                        sg[13] = s3; sg[14] = r3; sg[15] = l3 - z3; sg[16] = h3 - z3;
+                        sg[17] = __fadd_rn(z3, 12582912.0f);
+                    }
+                    sg[6] = __int_as_float(exact);
+                }
+            }
+            first = false;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pfull_bar(pb));
+            if (++pb == 2) { pb = 0; pphase ^= 1u; }
+        }
+        if (LNF) {
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else {
+        // ===================== epilogue (warps 0..7) =====================
+        const int quarter = warp & 3, half = warp >> 2;
+        int buf = 0, pb = 0;
+        uint32_t bphase = 0, pphase = 0;
+        for (int64_t t = tile0; t < tiles; t += tile_step) {
+            const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+            const int64_t row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < M;
+            uint32_t r0[8], r1[8];
+            if (LNF) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r0[i] = r1[i] = 0u;
+                if (row_ok) {
+                    const unsigned char* rrow = ep.res_u8 + row * N + n0 + half * 32;
+                    ldg256(rrow, r0);
+                    ldg256(rrow + 64, r1);
+                }
+            }
+            mbar_wait(pfull_bar(pb), pphase);
+            const unsigned char* tp = tile_par(pb);
+            const float2* Pb = reinterpret_cast<const float2*>(tp);
+            const int32_t* corr = reinterpret_cast<const int32_t*>(tp + (BN / 2) * 8);
+            const float* sg = reinterpret_cast<const float*>(tp + (BN / 2) * 8 + kMaxGroups * BN * 4);
+            const float* csg = sg + kSegFloats;
+            const int exact = __float_as_int(sg[6]);
+            float run[64];
+            uint32_t last_buf = 0;
+            for (int g = 0; g < G; ++g) {
+                mbar_wait(tfull_bar(buf), bphase);
+                tc_fence_after();
+                const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+                if (g == 0) drain_group<true>(run, tb, half, corr, csg[0]);
+                else drain_group<false>(run, tb, half, corr + g * BN, csg[g]);
+                last_buf = tb;
+                tc_fence_before();
+                __syncwarp();
+                // (LNF parks its intermediate in the LAST group's buffer: that one is released after the epilogue)
+                if (lane == 0 && !(LNF && g == G - 1)) mbar_arrive(tempty_bar(buf));
+                if (++buf == 2) { buf = 0; bphase ^= 1u; }
+            }
+            if (LNF) {
+                if (warp == 0 && lane == 0) {       // this CTA's output scale s2 travels with its sums (see finish_res_ln)
+                    const uint32_t my = cluster_ctarank(), cn = cluster_nctarank();
+                    const uint32_t dst = smem_u32(xscale + my);
+                    for (uint32_t r = 0; r < cn; ++r) st_remote_f32(dst, r, sg[7]);
+                }
+                if (exact) finish_res_ln<false>(ep, run, Pb, Pgb, sg, part, xs, xscale, last_buf, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+                else finish_res_ln<true>(ep, run, Pb, Pgb, sg, part, xs, xscale, last_buf, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+            } else {
+                if (exact) finish_plain<ACT, false, OUT8>(ep, run, Pb, sg, half, row, row_ok, n0, N);
+                else finish_plain<ACT, true, OUT8>(ep, run, Pb, sg, half, row, row_ok, n0, N);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pempty_bar(pb));
+            if (++pb == 2) { pb = 0; pphase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemColsPeg)
+                     : "memory");
+}
+
+}  // namespace peg
+
 }  // namespace lean
 
 // hi | mid | lo bf16 split: x = hi + mid + lo up to 2^-24 relative (three 8-bit mantissa pieces)
@@ -1995,6 +2489,32 @@ static int launch_lean(const void* a, const void* w, int64_t M, int64_t N, int64
     }
     return launch_pdl(lean::linear_lean_kernel<BN, ACT, LNF, OUT8>, dim3(grid), dim3(lean::kThreads), C::kSmemBytes, st, cluster,
                       map_a, map_w, M, N, K, ring, ep);
+}
+
+
+template <int ACT, bool LNF, bool OUT8>
+static int launch_peg(const void* a, const void* w, int64_t M, int64_t N, int64_t K, const lean::peg::Args& ep, cudaStream_t st) {
+    using C = lean::peg::Cfg<LNF>;
+    static_assert(C::kSmemBytes <= 227 * 1024, "shared memory budget");
+    CUtensorMap map_a, map_w;
+    if (int e = make_map(&map_a, a, M, K, BM, true)) return e;
+    if (int e = make_map(&map_w, w, N, K, lean::peg::BN, true)) return e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lean::peg::linear_peg_kernel<ACT, LNF, OUT8>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int64_t tiles = ((M + BM - 1) / BM) * (N / lean::peg::BN);
+    int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    int cluster = 1;
+    if (LNF) {
+        cluster = (int)(N / lean::peg::BN);
+        grid = (int)tiles;
+    }
+    return launch_pdl(lean::peg::linear_peg_kernel<ACT, LNF, OUT8>, dim3(grid), dim3(lean::kThreads), C::kSmemBytes, st, cluster,
+                      map_a, map_w, M, N, K, (int)C::kStages, ep);
 }
 
 static void lean_trace(lean::Args& ep) {
@@ -2263,6 +2783,68 @@ int tq_linear_seg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_ro
     TQ_LEAN_CASE(128)
 #undef TQ_LEAN_CASE
     return TQ_EUNSUPPORTED;
+}
+
+static int peg_common_checks(const void* a_i8, const void* w_i8, const int32_t* w_grp_rowsum, int64_t M, int64_t N, int64_t K,
+                             const tq_qspec& a_q, int32_t a_groups, const tq_qspec& w_q, int32_t w_params, const tq_qspec& out_q,
+                             int32_t out_params, int64_t seg_width) {
+    using namespace tq::gemm;
+    if (a_i8 == nullptr || w_i8 == nullptr || w_grp_rowsum == nullptr || M < 1 || N < 1 || K < 1) return TQ_EINVAL;
+    if (a_groups < 1 || a_groups > lean::peg::kMaxGroups || seg_width < 1) return TQ_EINVAL;
+    if (int e = tq::check_qspec(a_q)) return e;
+    if (int e = tq::check_qspec(w_q)) return e;
+    if (int e = tq::check_qspec(out_q)) return e;
+    if (a_q.zero_float == nullptr && a_q.is_signed == nullptr) return TQ_EINVAL;
+    if (a_q.n_bits > 8 || w_q.n_bits > 8 || out_q.n_bits > 8) return TQ_EUNSUPPORTED;
+    if (N % lean::peg::BN != 0 || seg_width % lean::peg::BN != 0 || N % seg_width != 0 || K % (128 * (int64_t)a_groups) != 0) return TQ_EUNSUPPORTED;
+    const int64_t nseg = N / seg_width;
+    if ((w_params != 1 && w_params != nseg) || (out_params != 1 && out_params != nseg)) return TQ_EINVAL;
+    if (!tq::aligned16(a_i8) || !tq::aligned16(w_i8)) return TQ_EALIGN;
+    return TQ_OK;
+}
+
+int tq_linear_peg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_grp_rowsum, const float* bias, void* y_ctr_bf16,
+                         void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q, int32_t a_groups, tq_qspec w_q,
+                         int32_t w_params, tq_qspec out_q, int32_t out_params, int64_t seg_width, int32_t act_fn, void* stream) {
+    using namespace tq::gemm;
+    if ((y_ctr_bf16 == nullptr) == (y_i8 == nullptr)) return TQ_EINVAL;
+    if (act_fn < 0 || act_fn > 1) return TQ_EUNSUPPORTED;
+    if (int e = peg_common_checks(a_i8, w_i8, w_grp_rowsum, M, N, K, a_q, a_groups, w_q, w_params, out_q, out_params, seg_width)) return e;
+    if (!aligned32(y_i8 != nullptr ? y_i8 : y_ctr_bf16)) return TQ_EALIGN;
+    lean::peg::Args pa = {};
+    pa.bias = bias; pa.w_grp_rowsum = w_grp_rowsum; pa.a_q = a_q; pa.a_groups = a_groups;
+    pa.w_q = w_q; pa.out_q = out_q; pa.w_params = w_params; pa.out_params = out_params; pa.seg_width = seg_width;
+    pa.y_u8 = y_i8; pa.y_ctr = reinterpret_cast<__nv_bfloat16*>(y_ctr_bf16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (y_i8 != nullptr) return act_fn == 1 ? launch_peg<1, false, true>(a_i8, w_i8, M, N, K, pa, st) : launch_peg<0, false, true>(a_i8, w_i8, M, N, K, pa, st);
+    return act_fn == 1 ? launch_peg<1, false, false>(a_i8, w_i8, M, N, K, pa, st) : launch_peg<0, false, false>(a_i8, w_i8, M, N, K, pa, st);
+}
+
+int tq_linear_peg_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_grp_rowsum, const float* bias,
+                                void* z_ctr_bf16, void* z_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q, int32_t a_groups,
+                                tq_qspec w_q, int32_t w_params, tq_qspec out_q, int32_t out_params, const void* res_i8,
+                                tq_qspec res_q, int32_t res_params, tq_qspec out2_q, int32_t out2_params,
+                                const float* ln_gamma_q, const float* ln_beta, float ln_eps, tq_qspec ln_q, int32_t ln_params,
+                                int64_t seg_width, void* stream) {
+    using namespace tq::gemm;
+    if (z_i8 == nullptr || res_i8 == nullptr || ln_gamma_q == nullptr || ln_beta == nullptr) return TQ_EINVAL;
+    if (int e = peg_common_checks(a_i8, w_i8, w_grp_rowsum, M, N, K, a_q, a_groups, w_q, w_params, out_q, out_params, seg_width)) return e;
+    if (int e = tq::check_qspec(res_q)) return e;
+    if (int e = tq::check_qspec(out2_q)) return e;
+    if (int e = tq::check_qspec(ln_q)) return e;
+    if (res_q.n_bits > 8 || out2_q.n_bits > 8 || ln_q.n_bits > 8 || N / lean::peg::BN > 8) return TQ_EUNSUPPORTED;
+    const int64_t nseg = N / seg_width;
+    if ((res_params != 1 && res_params != nseg) || (out2_params != 1 && out2_params != nseg) || (ln_params != 1 && ln_params != nseg)) return TQ_EINVAL;
+    if (!aligned32(z_i8) || !aligned32(res_i8) || (z_ctr_bf16 != nullptr && !aligned32(z_ctr_bf16))) return TQ_EALIGN;
+    lean::peg::Args pa = {};
+    pa.bias = bias; pa.w_grp_rowsum = w_grp_rowsum; pa.a_q = a_q; pa.a_groups = a_groups;
+    pa.w_q = w_q; pa.out_q = out_q; pa.w_params = w_params; pa.out_params = out_params; pa.seg_width = seg_width;
+    pa.y_u8 = z_i8; pa.y_ctr = reinterpret_cast<__nv_bfloat16*>(z_ctr_bf16);
+    pa.res_u8 = reinterpret_cast<const unsigned char*>(res_i8);
+    pa.res_q = res_q; pa.out2_q = out2_q; pa.ln_q = ln_q;
+    pa.res_params = res_params; pa.out2_params = out2_params; pa.ln_params = ln_params;
+    pa.ln_gamma = ln_gamma_q; pa.ln_beta = ln_beta; pa.ln_eps = ln_eps;
+    return launch_peg<0, true, true>(a_i8, w_i8, M, N, K, pa, (cudaStream_t)stream);
 }
 
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream) {

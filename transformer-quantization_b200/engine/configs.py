@@ -2,7 +2,8 @@
 
     bert_w8a8_sym      config 1  BERT-base W8A8 per-tensor symmetric, seq 128 batch 4 (plumbing check)
     bert_w8a8_asym     config 2  BERT-base W8A8 per-tensor asymmetric, seq 128 batch 32      <- bench.py's workload
-    bert_w8a8_peg      config 3  BERT-base W8A8 per-embedding-group activations (K = 6, range-permuted), batch 32
+    bert_w8a8_peg      config 3  BERT-base W8A8 per-embedding-group activations (K = 6 contiguous groups), batch 32
+    bert_w8a8_pegp               the same with range-based permutation of the groups (module path)
     mobilebert_w4a8    config 4  MobileBERT W4A8, seq 128 batch 64
     roberta_w8a8_mse   config 5  RoBERTa-base W8A8, MSE (grid) activation ranges; calibration batches shard over
                                  the ranks, statistics all-reduced in quantization/_dist.py
@@ -28,7 +29,8 @@ S, A = QMethods.symmetric_uniform, QMethods.asymmetric_uniform
 RECIPES = {
     'bert_w8a8_sym': Recipe('bert', S, 8, 8, RangeEstimators.running_minmax, {}, None, 4, 128),
     'bert_w8a8_asym': Recipe('bert', A, 8, 8, RangeEstimators.running_minmax, {}, None, 32, 128),
-    'bert_w8a8_peg': Recipe('bert', A, 8, 8, RangeEstimators.current_minmax, {}, ('ngp', 6), 32, 128),
+    'bert_w8a8_peg': Recipe('bert', A, 8, 8, RangeEstimators.current_minmax, {}, ('ng', 6), 32, 128),
+    'bert_w8a8_pegp': Recipe('bert', A, 8, 8, RangeEstimators.current_minmax, {}, ('ngp', 6), 32, 128),
     'mobilebert_w4a8': Recipe('mobilebert', A, 4, 8, RangeEstimators.running_minmax, {}, None, 64, 128),
     'roberta_w8a8_mse': Recipe('roberta', A, 8, 8, RangeEstimators.MSE,
                                dict(opt_method=OptMethod.grid, num_candidates=100), None, 32, 128),

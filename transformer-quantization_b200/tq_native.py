@@ -96,6 +96,15 @@ SIGNATURES = {
     'tq_linear_seg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
                                             ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, QSpec, _i32, _i32,
                                             ctypes.c_void_p]),
+    'tq_linear_peg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
+                                            ctypes.c_void_p, _i64, _i64, _i64, QSpec, _i32, QSpec, _i32, QSpec, _i32, _i64,
+                                            _i32, ctypes.c_void_p]),
+    'tq_linear_peg_res_ln_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
+                                                   ctypes.c_void_p, _i64, _i64, _i64, QSpec, _i32, QSpec, _i32, QSpec, _i32,
+                                                   ctypes.c_void_p, QSpec, _i32, QSpec, _i32, _c_f32p, _c_f32p,
+                                                   ctypes.c_float, QSpec, _i32, _i64, ctypes.c_void_p]),
+    'tq_attention_peg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _i32, QSpec, QSpec,
+                                               QSpec, _i32, QSpec, QSpec, QSpec, _i32, _c_f32p, ctypes.c_void_p]),
     'tq_linear_qdq_bf16_o8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p, _i64, _i64, _i64,
                                              QSpec, QSpec, _i64, _i32, QSpec, _i64, ctypes.c_void_p]),
     'tq_linear_res_ln_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, _c_f32p,
@@ -464,6 +473,34 @@ class CudaOps:
                   w_rowsum.data_ptr(), _ptr(bias), _ptr(out_ctr), _ptr(out_i8), M, N, K, a_spec, w_seg_spec, out_seg_spec,
                   int(nseg), int(act_fn), _stream())
         return out_i8 if out_i8 is not None else out_ctr
+
+    def linear_peg_i8(self, a_i8, w_i8, w_grp_rowsum, bias, M, N, K, a_spec, a_groups, w_spec, w_params, out_spec, out_params,
+                      seg_width, act_fn, out_ctr=None, out_i8=None):
+        """tq_linear_peg_qdq_i8: per-group A operand, per-segment output quantizers; fills out_ctr XOR out_i8"""
+        _chk_cuda(a_i8, w_i8, w_grp_rowsum, bias, out_ctr, out_i8)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_peg_qdq_i8, a_i8.data_ptr(), w_i8.data_ptr(),
+                  w_grp_rowsum.data_ptr(), _ptr(bias), _ptr(out_ctr), _ptr(out_i8), M, N, K, a_spec, int(a_groups), w_spec,
+                  int(w_params), out_spec, int(out_params), int(seg_width), int(act_fn), _stream())
+        return out_i8 if out_i8 is not None else out_ctr
+
+    def linear_peg_res_ln_i8(self, a_i8, w_i8, w_grp_rowsum, bias, M, N, K, a_spec, a_groups, w_spec, w_params, out_spec,
+                             out_params, res_i8, res_spec, res_params, out2_spec, out2_params, gamma_q, beta, eps, ln_spec,
+                             ln_params, seg_width, out_i8, out_ctr=None):
+        _chk_cuda(a_i8, w_i8, w_grp_rowsum, bias, res_i8, gamma_q, beta, out_i8, out_ctr)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_peg_res_ln_qdq_i8, a_i8.data_ptr(), w_i8.data_ptr(),
+                  w_grp_rowsum.data_ptr(), _ptr(bias), _ptr(out_ctr), out_i8.data_ptr(), M, N, K, a_spec, int(a_groups),
+                  w_spec, int(w_params), out_spec, int(out_params), res_i8.data_ptr(), res_spec, int(res_params), out2_spec,
+                  int(out2_params), gamma_q.data_ptr(), beta.data_ptr(), float(eps), ln_spec, int(ln_params), int(seg_width),
+                  _stream())
+        return out_i8
+
+    def attention_peg_i8(self, qkv_ctr, B, T, H, head_dim, q_spec, k_spec, v_spec, qkv_params, s_spec, p_spec, c_spec, c_params,
+                         mask, out_i8):
+        _chk_cuda(qkv_ctr, mask, out_i8)
+        self._run('attention', 4 * B * H * T * T * head_dim, 1, self.lib.tq_attention_peg_qdq_i8, qkv_ctr.data_ptr(),
+                  out_i8.data_ptr(), B, T, H, head_dim, q_spec, k_spec, v_spec, int(qkv_params), s_spec, p_spec, c_spec,
+                  int(c_params), _ptr(mask), _stream())
+        return out_i8
 
     def linear_res_ln_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_spec, w_params, out_spec, res_i8, res_spec,
                          out2_spec, gamma_q, beta, eps, ln_spec, out_i8, want_f32=False, out_ctr=None):
