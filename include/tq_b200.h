@@ -55,7 +55,7 @@ typedef struct tq_qspec {
 /* ---- library info ------------------------------------------------------------------------- */
 int         tq_version(void);              /* ABI version: 1 = inference path; 2 adds the training-time entry points
                                               * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 (current) adds
-                                              * tq_linear_seg_qdq_i8 and the tq_*_peg_* entry points */
+                                              * tq_linear_seg_qdq_i8, tq_linear_nonorm_qdq_i8 and the tq_*_peg_* entry points */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
 
@@ -241,11 +241,25 @@ int tq_linear_qdq_bf16_o8(const void* a_ctr_bf16, const void* w_ctr_bf16, const 
  * models/quantized_bert.py:135-151: three QuantLinear, each with its own per-tensor quantizers).  Same arithmetic
  * as tq_linear_qdq_i8 (bit-identical outputs), leaner kernel: a parameter warp resolves the quantizers once and
  * streams {bias, zero-point correction} per tile, the epilogue has no per-tile set-up and no run-time format
- * switches.  Exactly one of y_ctr_bf16 / y_i8; act_fn 0 (none) or 1 (GELU); K % 128 == 0, (N / nseg) a multiple of
- * 128, 192 or 256, outputs 32-byte aligned; else TQ_EUNSUPPORTED / TQ_EALIGN (callers use tq_linear_qdq_i8). */
+ * switches.  Exactly one of y_ctr_bf16 / y_i8; act_fn 0 (none), 1 (GELU) or 2 (ReLU); ldc: output row stride in
+ * elements (0: N; > N lets several GEMMs fill the column blocks of one buffer); K % 128 == 0, (N / nseg) a multiple
+ * of 128, 192 or 256, outputs 32-byte aligned; else TQ_EUNSUPPORTED / TQ_EALIGN (callers use tq_linear_qdq_i8). */
 int tq_linear_seg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
                          void* y_ctr_bf16, void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q,
-                         tq_qspec w_q, tq_qspec out_q, int32_t nseg, int32_t act_fn, void* stream);
+                         tq_qspec w_q, tq_qspec out_q, int32_t nseg, int32_t act_fn, int64_t ldc, void* stream);
+/* Hijacked nn.Linear followed by MobileBERT's QuantNoNorm (reference models/quantized_mobilebert.py:58-72: the
+ * elementwise affine y * weight + bias with fake-quantized parameters and a quantized output), optionally with the
+ * quantized residual sum in between (self-output / FFN-output / output-bottleneck blocks, :273-311, 327-404):
+ *     k = out_q(x @ Wq.T + bias)                                    [res_i8 == NULL]
+ *     k = out2_q( dequant(out_q(x @ Wq.T + bias)) + dequant(res) )  [res_i8 != NULL]
+ *     z = nn_q( dequant(k) * nn_weight_q + nn_bias_q )              -> x_int bytes
+ * nn_weight_q / nn_bias_q: the NoNorm parameters AFTER their (shared) weight quantizer, fp32 [N].  All quantizers
+ * per-tensor.  One pass in the GEMM epilogue: the two (three) intermediate tensors never leave the SM.
+ * ldc: output row stride in elements (0: N).  K % 128 == 0, N % 128 == 0. */
+int tq_linear_nonorm_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias, void* z_i8,
+                            int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q, tq_qspec out_q,
+                            const void* res_i8, tq_qspec res_q, tq_qspec out2_q, const float* nn_weight_q,
+                            const float* nn_bias_q, tq_qspec nn_q, int64_t ldc, void* stream);
 /* Per-embedding-group (PEG) activations through the int8 pipeline (BASELINE config 3; reference
  * utils/per_embd_quant_utils.py:54-68, quantization/range_estimators.py:82-112, quantizers.py:213-217).
  * A operand: x_int bytes of a tensor whose (scale, zero point) change per group of K / a_groups CONTRACTION columns

@@ -263,6 +263,7 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
 template <int ACT>
 __device__ __forceinline__ float2 act2(float2 f) {
     if (ACT == 1) return gelu2(f);
+    if (ACT == 2) return make_float2(fmaxf(f.x, 0.0f), fmaxf(f.y, 0.0f));      // nn.ReLU (finite inputs)
     return f;
 }
 
@@ -1247,13 +1248,17 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kMaxSeg = 4;
 constexpr int kSegFloats = 24;
 
-template <int BN, bool LNF>
+// MODE: 0 plain, 1 residual + LayerNorm (cluster), 2 NoNorm (elementwise affine), 3 residual + NoNorm
+template <int BN, int MODE>
 struct Cfg {
+    static constexpr bool LNF = MODE == 1;
+    static constexpr bool AFF = MODE >= 2;
     static constexpr int kABytes = BM * 128;
     static constexpr int kBBytes = BN * 128;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kColBytes = 2 * (BN / 2) * 16;                 // 2 x float4 {bias.x, bias.y, corr.x, corr.y} per column pair
-    static constexpr int kLnBytes = LNF ? (BN / 2) * 16 + 2 * BM * 8 + 8 * BM * 8 : 0;   // gamma|beta pairs, half partials, cluster partials
+    static constexpr int kLnBytes = LNF ? (BN / 2) * 16 + 2 * BM * 8 + 8 * BM * 8           // gamma|beta pairs, half partials, cluster partials
+                                        : (AFF ? 2 * (BN / 2) * 16 : 0);                    // NoNorm: gamma|beta pairs per tile (double-buffered)
     static constexpr int kSegBytes = kMaxSeg * kSegFloats * 4;
     static constexpr int kParamBytes = kColBytes + kLnBytes + kSegBytes;
     static constexpr int kStagesFit = (227 * 1024 - 1024 - kParamBytes - 256) / kStageBytes;
@@ -1271,6 +1276,7 @@ struct Args {
     int32_t nseg;
     void* y_u8;                     // [M, N] x_int bytes          (exactly one of the two outputs ...
     __nv_bfloat16* y_ctr;           // [M, N] centred bf16 grid     ... unless LNF, where y_ctr is optional)
+    int64_t ldc;                    // output row stride in elements (>= N: lets two GEMMs fill one [M, ldc] buffer)
     const unsigned char* res_u8;    // LNF: residual x_int bytes [M, N]
     tq_qspec res_q, out2_q, ln_q;   // LNF: per-tensor
     const float* ln_gamma;
@@ -1349,8 +1355,8 @@ __device__ __forceinline__ void epi_plain(const Args& ep, const float4* __restri
     constexpr int NIT = BN / 64;
     const QReg q = qreg_of(sg[1], sg[2], sg[3], sg[4]);
     const float2 cs2 = splat(sg[0]), off2 = splat(sg[5]);
-    unsigned char* o8 = OUT8 ? reinterpret_cast<unsigned char*>(ep.y_u8) + row * N + n0 : nullptr;
-    __nv_bfloat16* oc = OUT8 ? nullptr : ep.y_ctr + row * N + n0;
+    unsigned char* o8 = OUT8 ? reinterpret_cast<unsigned char*>(ep.y_u8) + row * ep.ldc + n0 : nullptr;
+    __nv_bfloat16* oc = OUT8 ? nullptr : ep.y_ctr + row * ep.ldc + n0;
     uint32_t va[32], vb[32];
     tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32), va);
 #pragma unroll
@@ -1534,17 +1540,92 @@ __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restr
     }
 }
 
-template <int BN, int ACT, bool LNF, bool OUT8>
+// ---- NoNorm epilogue (MobileBERT, reference models/quantized_mobilebert.py:58-72): QuantNoNorm is the elementwise
+// affine y * weight + bias with fake-quantized parameters and a quantized output, always applied to a quantized dense
+// output [+ quantized residual sum]:   z = Q3( s * k (*) gamma + beta ),  k = Q1(acc * cs + bias)  or, with the residual,
+// k = Q2( s1 * Q1(.) + s_r * (r_int - zp_r) ).  One pass, no statistics, no cluster.  Multiply and add are separate
+// roundings like the reference's two tensor ops.  Segment parameters as in epi_res_ln.
+template <int BN, bool FAST, bool RES>
+__device__ __forceinline__ void epi_affine(const Args& ep, const float4* __restrict__ Pcol, const float4* __restrict__ Pgb,
+                                           const float* __restrict__ sg, uint32_t tmem_tile, int half, int64_t row, bool row_ok,
+                                           int64_t n0, int64_t N) {
+    constexpr int NIT = BN / 64;
+    const QReg q1 = qreg_of(sg[1], sg[2], sg[3], sg[4]);
+    const QReg q2 = qreg_of(sg[7], sg[8], sg[9], sg[10]);
+    const QReg q3 = qreg_of(sg[13], sg[14], sg[15], sg[16]);
+    const float2 cs2 = splat(sg[0]), off3 = splat(sg[17]);
+    const float s1 = sg[1], rs = sg[11], roff = sg[12];
+    const float2 sk = splat(RES ? sg[7] : sg[1]);
+    const unsigned char* rrow = RES ? ep.res_u8 + row * N + n0 : nullptr;
+    unsigned char* o8 = reinterpret_cast<unsigned char*>(ep.y_u8) + row * ep.ldc + n0;
+    uint32_t va[32], vb[32], rw[8], rn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rn[i] = 0u;
+    tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32), va);
+    if (RES && row_ok) ldg256(rrow + half * 32, rn);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        uint32_t (&v)[32] = (it & 1) ? vb : va;
+        uint32_t (&vn)[32] = (it & 1) ? va : vb;
+        tmem_ld_fence(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rw[i] = rn[i];
+        const int c0 = half * 32 + it * 64;
+        if (it + 1 < NIT) {
+            tmem_ld32_nowait(tmem_tile + (uint32_t)(c0 + 64), vn);
+            if (RES && row_ok) ldg256(rrow + c0 + 64, rn);
+        }
+        const float4* P = Pcol + (c0 >> 1);
+        const float4* G = Pgb + (c0 >> 1);
+        uint32_t w[8], b[16];
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+            const float4 pp = P[jp];
+            const float2 a = make_float2(__int2float_rn((int)v[2 * jp] - __float_as_int(pp.z)),
+                                         __int2float_rn((int)v[2 * jp + 1] - __float_as_int(pp.w)));
+            const float2 f = __ffma2_rn(a, cs2, make_float2(pp.x, pp.y));
+            float2 k = ctr2_t<FAST>(f, q1);
+            if (RES) {
+                const uint32_t wd = rw[jp >> 1];
+                const uint32_t lo = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7652 : 0x7650);
+                const uint32_t hi = __byte_perm(wd, 0x4B000000u, (jp & 1) ? 0x7653 : 0x7651);
+                const float2 rc = make_float2(__fsub_rn(__uint_as_float(lo), roff), __fsub_rn(__uint_as_float(hi), roff));
+                const float2 sum = __fadd2_rn(make_float2(__fmul_rn(s1, k.x), __fmul_rn(s1, k.y)),
+                                              make_float2(__fmul_rn(rs, rc.x), __fmul_rn(rs, rc.y)));
+                k = ctr2_t<FAST>(sum, q2);
+            }
+            const float4 gb = G[jp];
+            const float2 x = __fmul2_rn(sk, k);                                        // dequantized NoNorm input
+            // x * weight, then + bias: scalar multiplies (a packed multiply feeding a packed add would be contracted)
+            const float2 y = __fadd2_rn(make_float2(__fmul_rn(x.x, gb.x), __fmul_rn(x.y, gb.y)), make_float2(gb.z, gb.w));
+            const float2 k3 = ctr2_t<FAST>(y, q3);
+            const float2 t = __fadd2_rn(k3, off3);
+            b[2 * (jp & 7)] = __float_as_uint(t.x);
+            b[2 * (jp & 7) + 1] = __float_as_uint(t.y);
+            if ((jp & 7) == 7) {
+                uint32_t w4[4];
+                pack_bytes16(w4, b);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[(jp >> 3) * 4 + i] = w4[i];
+            }
+        }
+        if (row_ok) stg256(o8 + c0, w);
+    }
+}
+
+template <int BN, int ACT, int MODE, bool OUT8>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                    int64_t M, int64_t N, int64_t K, int ring, Args ep) {
-    using C = Cfg<BN, LNF>;
+    using C = Cfg<BN, MODE>;
+    constexpr bool LNF = MODE == 1, AFF = MODE >= 2;
+    constexpr bool QX = LNF || AFF;               // three quantizers (+ residual) instead of one
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
     unsigned char* par_ptr = base_ptr + C::kStages * C::kStageBytes;
     float4* Pcol = reinterpret_cast<float4*>(par_ptr);                       // [2][BN / 2]
-    float4* Pgb = reinterpret_cast<float4*>(par_ptr + C::kColBytes);         // LNF: [BN / 2] {gamma.x, gamma.y, beta.x, beta.y}
+    float4* Pgb = reinterpret_cast<float4*>(par_ptr + C::kColBytes);         // LNF: [BN / 2] {gamma.x, gamma.y, beta.x, beta.y}; AFF: [2][BN / 2]
     int2* part = reinterpret_cast<int2*>(par_ptr + C::kColBytes + (LNF ? (BN / 2) * 16 : 0));     // [2][BM]
     int2* xs = part + 2 * BM;                                                 // [8][BM]
     float* segp = reinterpret_cast<float*>(par_ptr + C::kColBytes + C::kLnBytes);   // [kMaxSeg][kSegFloats]
@@ -1684,9 +1765,9 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const tq_qspec* qs = nullptr;
             int slot = 0;
             if (lane == 0) qs = &ep.a_q;
-            else if (LNF && lane == 1) qs = &ep.res_q;
-            else if (LNF && lane == 2) qs = &ep.out2_q;
-            else if (LNF && lane == 3) qs = &ep.ln_q;
+            else if ((LNF || MODE == 3) && lane == 1) qs = &ep.res_q;
+            else if ((LNF || MODE == 3) && lane == 2) qs = &ep.out2_q;
+            else if (QX && lane == 3) qs = &ep.ln_q;
             else if (lane >= 4 && lane < 4 + ep.nseg) { qs = &ep.w_q; slot = lane - 4; }
             else if (lane >= 8 && lane < 8 + ep.nseg) { qs = &ep.out_q; slot = lane - 8; }
             if (qs != nullptr) {
@@ -1735,8 +1816,8 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 sg[0] = __fmul_rn(a_scale, w_scale);
                 sg[1] = o_scale; sg[2] = o_rcp; sg[3] = o_lo - o_zp; sg[4] = o_hi - o_zp;
                 sg[5] = __fadd_rn(o_zp, 12582912.0f);               // x_int = k + zp, + 1.5 * 2^23
-                if (LNF) {
-                    exact |= e2 | e3;
+                if (QX) {
+                    exact |= (MODE == 2 ? 0 : e2) | e3;
                     sg[7] = s2; sg[8] = r2; sg[9] = l2 - z2; sg[10] = h2 - z2;
                     sg[11] = r_scale; sg[12] = __fadd_rn(8388608.0f, r_zp);
                     sg[13] = s3; sg[14] = r3; sg[15] = l3 - z3; sg[16] = h3 - z3;
@@ -1767,6 +1848,13 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const int64_t n = n0 + 2 * jp;
                     const float b0 = ep.bias != nullptr ? ep.bias[n] : 0.0f, b1 = ep.bias != nullptr ? ep.bias[n + 1] : 0.0f;
                     P[jp] = make_float4(b0, b1, __int_as_float(a_zp * ep.w_rowsum[n]), __int_as_float(a_zp * ep.w_rowsum[n + 1]));
+                }
+            }
+            if (AFF) {
+                float4* Gt = Pgb + pb * (BN / 2);
+                for (int jp = lane; jp < BN / 2; jp += 32) {
+                    const int64_t n = n0 + 2 * jp;
+                    Gt[jp] = make_float4(ep.ln_gamma[n], ep.ln_gamma[n + 1], ep.ln_beta[n], ep.ln_beta[n + 1]);
                 }
             }
             __syncwarp();
@@ -1810,6 +1898,10 @@ linear_lean_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (LNF) {
                 if (exact) epi_res_ln<BN, false>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
                 else epi_res_ln<BN, true>(ep, P, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+            } else if (AFF) {
+                const float4* Gt = Pgb + pb * (BN / 2);
+                if (exact) epi_affine<BN, false, MODE == 3>(ep, P, Gt, sg, tmem_tile, half, row, row_ok, n0, N);
+                else epi_affine<BN, true, MODE == 3>(ep, P, Gt, sg, tmem_tile, half, row, row_ok, n0, N);
             } else {
                 if (exact) epi_plain<BN, ACT, false, OUT8>(ep, P, sg, tmem_tile, half, row, row_ok, n0, N);
                 else epi_plain<BN, ACT, true, OUT8>(ep, P, sg, tmem_tile, half, row, row_ok, n0, N);
@@ -2460,9 +2552,10 @@ static TileShape pick_tile(int64_t M, int64_t N, int64_t K, int k_split, int act
 }
 
 
-template <int BN, int ACT, bool LNF, bool OUT8>
+template <int BN, int ACT, int MODE, bool OUT8>
 static int launch_lean(const void* a, const void* w, int64_t M, int64_t N, int64_t K, const lean::Args& ep, cudaStream_t st) {
-    using C = lean::Cfg<BN, LNF>;
+    using C = lean::Cfg<BN, MODE>;
+    constexpr bool LNF = MODE == 1;
     static_assert(C::kSmemBytes <= 227 * 1024, "shared memory budget");
     static_assert(2 * BN <= kTmemCols && BN % 64 == 0, "TMEM budget / slice width");
     CUtensorMap map_a, map_w;
@@ -2470,7 +2563,7 @@ static int launch_lean(const void* a, const void* w, int64_t M, int64_t N, int64
     if (int e = make_map(&map_w, w, N, K, BN, true)) return e;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(lean::linear_lean_kernel<BN, ACT, LNF, OUT8>,
+        cudaError_t e = cudaFuncSetAttribute(lean::linear_lean_kernel<BN, ACT, MODE, OUT8>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
@@ -2487,7 +2580,7 @@ static int launch_lean(const void* a, const void* w, int64_t M, int64_t N, int64
         const int f = atoi(e);
         if (f >= 1 && f < ring) ring = f;
     }
-    return launch_pdl(lean::linear_lean_kernel<BN, ACT, LNF, OUT8>, dim3(grid), dim3(lean::kThreads), C::kSmemBytes, st, cluster,
+    return launch_pdl(lean::linear_lean_kernel<BN, ACT, MODE, OUT8>, dim3(grid), dim3(lean::kThreads), C::kSmemBytes, st, cluster,
                       map_a, map_w, M, N, K, ring, ep);
 }
 
@@ -2636,12 +2729,12 @@ static int linear_impl(const void* a_ctr_bf16, const void* w_ctr_bf16, const flo
             la.y_u8 = y_u8; la.y_ctr = reinterpret_cast<__nv_bfloat16*>(y_ctr_bf16);
             la.res_u8 = reinterpret_cast<const unsigned char*>(res_ctr_bf16);
             la.res_q = res_q; la.out2_q = out2_q; la.ln_q = *ln_q;
-            la.ln_gamma = ln_gamma; la.ln_beta = ln_beta; la.ln_eps = ln_eps;
+            la.ln_gamma = ln_gamma; la.ln_beta = ln_beta; la.ln_eps = ln_eps; la.ldc = N;
             lean_trace(la);
             switch (best) {
-                case 256: return launch_lean<256, 0, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
-                case 192: return launch_lean<192, 0, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
-                default: return launch_lean<128, 0, true, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
+                case 256: return launch_lean<256, 0, 1, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
+                case 192: return launch_lean<192, 0, 1, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
+                default: return launch_lean<128, 0, 1, true>(a_ctr_bf16, w_ctr_bf16, M, N, K, la, st);
             }
         }
         if (i8) {
@@ -2749,40 +2842,81 @@ int tq_linear_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w
 
 int tq_linear_seg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias, void* y_ctr_bf16,
                          void* y_i8, int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q, tq_qspec out_q,
-                         int32_t nseg, int32_t act_fn, void* stream) {
+                         int32_t nseg, int32_t act_fn, int64_t ldc, void* stream) {
     using namespace tq::gemm;
     if (a_i8 == nullptr || w_i8 == nullptr || w_rowsum == nullptr || ((y_ctr_bf16 == nullptr) == (y_i8 == nullptr))) return TQ_EINVAL;
     if (M < 1 || N < 1 || K < 1 || nseg < 1 || nseg > lean::kMaxSeg || N % nseg != 0) return TQ_EINVAL;
-    if (act_fn < 0 || act_fn > 1) return TQ_EUNSUPPORTED;
+    if (act_fn < 0 || act_fn > 2) return TQ_EUNSUPPORTED;
     if (int e = tq::check_qspec(a_q)) return e;
     if (int e = tq::check_qspec(w_q)) return e;
     if (int e = tq::check_qspec(out_q)) return e;
     if (a_q.n_bits > 8 || w_q.n_bits > 8 || out_q.n_bits > 8 || K % 128 != 0) return TQ_EUNSUPPORTED;
     if (!tq::aligned16(a_i8) || !tq::aligned16(w_i8)) return TQ_EALIGN;
+    if (ldc == 0) ldc = N;
     void* out = y_i8 != nullptr ? y_i8 : y_ctr_bf16;
-    if (!aligned32(out) || (N & 31) != 0) return TQ_EALIGN;
+    if (ldc < N || !aligned32(out) || (N & 31) != 0 || (ldc & 31) != 0) return TQ_EALIGN;
     const int64_t seg = N / nseg;
     const int bn = seg % 256 == 0 ? 256 : (seg % 192 == 0 ? 192 : (seg % 128 == 0 ? 128 : 0));
     if (bn == 0) return TQ_EUNSUPPORTED;
     lean::Args la = {};
     la.bias = bias; la.w_rowsum = w_rowsum; la.a_q = a_q; la.w_q = w_q; la.out_q = out_q;
-    la.seg_width = seg; la.nseg = nseg;
+    la.seg_width = seg; la.nseg = nseg; la.ldc = ldc;
     la.y_u8 = y_i8; la.y_ctr = reinterpret_cast<__nv_bfloat16*>(y_ctr_bf16);
     lean_trace(la);
     cudaStream_t st = (cudaStream_t)stream;
     const bool o8 = y_i8 != nullptr;
+#define TQ_LEAN_ACT(BN_, ACT_)                                                                                     \
+    return o8 ? launch_lean<BN_, ACT_, 0, true>(a_i8, w_i8, M, N, K, la, st)                                        \
+              : launch_lean<BN_, ACT_, 0, false>(a_i8, w_i8, M, N, K, la, st);
 #define TQ_LEAN_CASE(BN_)                                                                                          \
     if (bn == BN_) {                                                                                               \
-        if (act_fn == 1) return o8 ? launch_lean<BN_, 1, false, true>(a_i8, w_i8, M, N, K, la, st)                 \
-                                   : launch_lean<BN_, 1, false, false>(a_i8, w_i8, M, N, K, la, st);                \
-        return o8 ? launch_lean<BN_, 0, false, true>(a_i8, w_i8, M, N, K, la, st)                                   \
-                  : launch_lean<BN_, 0, false, false>(a_i8, w_i8, M, N, K, la, st);                                 \
+        if (act_fn == 1) { TQ_LEAN_ACT(BN_, 1) }                                                                   \
+        if (act_fn == 2) { TQ_LEAN_ACT(BN_, 2) }                                                                   \
+        TQ_LEAN_ACT(BN_, 0)                                                                                        \
     }
     TQ_LEAN_CASE(256)
     TQ_LEAN_CASE(192)
     TQ_LEAN_CASE(128)
 #undef TQ_LEAN_CASE
+#undef TQ_LEAN_ACT
     return TQ_EUNSUPPORTED;
+}
+
+int tq_linear_nonorm_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias, void* z_i8,
+                            int64_t M, int64_t N, int64_t K, tq_qspec a_q, tq_qspec w_q, tq_qspec out_q, const void* res_i8,
+                            tq_qspec res_q, tq_qspec out2_q, const float* nn_weight_q, const float* nn_bias_q, tq_qspec nn_q,
+                            int64_t ldc, void* stream) {
+    using namespace tq::gemm;
+    if (a_i8 == nullptr || w_i8 == nullptr || w_rowsum == nullptr || z_i8 == nullptr || nn_weight_q == nullptr || nn_bias_q == nullptr) return TQ_EINVAL;
+    if (M < 1 || N < 1 || K < 1) return TQ_EINVAL;
+    const tq_qspec* need[4] = {&a_q, &w_q, &out_q, &nn_q};
+    for (int i = 0; i < 4; ++i) {
+        if (int e = tq::check_qspec(*need[i])) return e;
+        if (need[i]->n_bits > 8) return TQ_EUNSUPPORTED;
+    }
+    if (res_i8 != nullptr) {
+        if (int e = tq::check_qspec(res_q)) return e;
+        if (int e = tq::check_qspec(out2_q)) return e;
+        if (res_q.n_bits > 8 || out2_q.n_bits > 8) return TQ_EUNSUPPORTED;
+        if (!aligned32(res_i8)) return TQ_EALIGN;
+    }
+    if (K % 128 != 0) return TQ_EUNSUPPORTED;
+    if (ldc == 0) ldc = N;
+    if (ldc < N || !aligned32(z_i8) || (N & 31) != 0 || (ldc & 31) != 0 || !tq::aligned16(a_i8) || !tq::aligned16(w_i8)) return TQ_EALIGN;
+    const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 0);
+    if (bn == 0) return TQ_EUNSUPPORTED;
+    lean::Args la = {};
+    la.bias = bias; la.w_rowsum = w_rowsum; la.a_q = a_q; la.w_q = w_q; la.out_q = out_q;
+    la.seg_width = N; la.nseg = 1; la.ldc = ldc;
+    la.y_u8 = z_i8; la.y_ctr = nullptr;
+    la.res_u8 = reinterpret_cast<const unsigned char*>(res_i8);
+    la.res_q = res_q; la.out2_q = out2_q; la.ln_q = nn_q;
+    la.ln_gamma = nn_weight_q; la.ln_beta = nn_bias_q; la.ln_eps = 0.0f;
+    lean_trace(la);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (res_i8 != nullptr)
+        return bn == 256 ? launch_lean<256, 0, 3, true>(a_i8, w_i8, M, N, K, la, st) : launch_lean<128, 0, 3, true>(a_i8, w_i8, M, N, K, la, st);
+    return bn == 256 ? launch_lean<256, 0, 2, true>(a_i8, w_i8, M, N, K, la, st) : launch_lean<128, 0, 2, true>(a_i8, w_i8, M, N, K, la, st);
 }
 
 static int peg_common_checks(const void* a_i8, const void* w_i8, const int32_t* w_grp_rowsum, int64_t M, int64_t N, int64_t K,

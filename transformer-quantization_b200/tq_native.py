@@ -94,8 +94,11 @@ SIGNATURES = {
                                         ctypes.c_void_p, ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, _i64, _i32,
                                         QSpec, _i64, ctypes.c_void_p]),
     'tq_linear_seg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
-                                            ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, QSpec, _i32, _i32,
+                                            ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, QSpec, _i32, _i32, _i64,
                                             ctypes.c_void_p]),
+    'tq_linear_nonorm_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
+                                               _i64, _i64, _i64, QSpec, QSpec, QSpec, ctypes.c_void_p, QSpec, QSpec, _c_f32p,
+                                               _c_f32p, QSpec, _i64, ctypes.c_void_p]),
     'tq_linear_peg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
                                             ctypes.c_void_p, _i64, _i64, _i64, QSpec, _i32, QSpec, _i32, QSpec, _i32, _i64,
                                             _i32, ctypes.c_void_p]),
@@ -466,13 +469,25 @@ class CudaOps:
         return y
 
     def linear_seg_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_seg_spec, out_seg_spec, nseg, act_fn,
-                      out_ctr=None, out_i8=None):
-        """tq_linear_seg_qdq_i8: per-segment weight / output quantizers (nseg slots each); fills out_ctr XOR out_i8"""
+                      out_ctr=None, out_i8=None, ldc=0):
+        """tq_linear_seg_qdq_i8: per-segment weight / output quantizers (nseg slots each); fills out_ctr XOR out_i8
+        (``ldc``: output row stride in elements when the output is a column block of a wider buffer)"""
         _chk_cuda(a_i8, w_i8, w_rowsum, bias, out_ctr, out_i8)
         self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_seg_qdq_i8, a_i8.data_ptr(), w_i8.data_ptr(),
                   w_rowsum.data_ptr(), _ptr(bias), _ptr(out_ctr), _ptr(out_i8), M, N, K, a_spec, w_seg_spec, out_seg_spec,
-                  int(nseg), int(act_fn), _stream())
+                  int(nseg), int(act_fn), int(ldc), _stream())
         return out_i8 if out_i8 is not None else out_ctr
+
+    def linear_nonorm_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_spec, out_spec, res_i8, res_spec, out2_spec,
+                         nn_weight_q, nn_bias_q, nn_spec, out_i8, ldc=0):
+        """tq_linear_nonorm_qdq_i8: dense -> QDQ [-> + residual -> QDQ] -> NoNorm -> QDQ in one GEMM epilogue"""
+        _chk_cuda(a_i8, w_i8, w_rowsum, bias, res_i8, nn_weight_q, nn_bias_q, out_i8)
+        null = QSpec(None, None, None, 8, 0, 1e-8)
+        self._run('linear_qdq', 2 * M * N * K, 1, self.lib.tq_linear_nonorm_qdq_i8, a_i8.data_ptr(), w_i8.data_ptr(),
+                  w_rowsum.data_ptr(), _ptr(bias), out_i8.data_ptr(), M, N, K, a_spec, w_spec, out_spec, _ptr(res_i8),
+                  res_spec if res_spec is not None else null, out2_spec if out2_spec is not None else null,
+                  nn_weight_q.data_ptr(), nn_bias_q.data_ptr(), nn_spec, int(ldc), _stream())
+        return out_i8
 
     def linear_peg_i8(self, a_i8, w_i8, w_grp_rowsum, bias, M, N, K, a_spec, a_groups, w_spec, w_params, out_spec, out_params,
                       seg_width, act_fn, out_ctr=None, out_i8=None):
