@@ -310,6 +310,13 @@ int tq_attention_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t
                         tq_qspec p_q, tq_qspec c_q, const float* mask, void* stream);
 /* ... with per-embedding-group quantizers on Q / K / V and on the context whose groups hold whole heads: q_q, k_q,
  * v_q carry qkv_params slots and c_q c_params slots (1 or a divisor of H); head h uses slot h / (H / params). */
+/* ... for heads narrower than the kernel's 64: every head occupies a 64-column slot of qkv whose upper columns are
+ * ZERO (the projections are run with zero-padded weight rows, so the padding is exact), the scores are divided by
+ * sqrt(true_head_dim) -- a true division unless that is a power of two -- and the padded context columns come out
+ * as the zero point.  MobileBERT: 4 heads x 32 (reference models/quantized_mobilebert.py:166-270). */
+int tq_attention_pad_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H,
+                            int32_t head_dim, int32_t true_head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q,
+                            tq_qspec s_q, tq_qspec p_q, tq_qspec c_q, const float* mask, void* stream);
 int tq_attention_peg_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H,
                             int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, int32_t qkv_params,
                             tq_qspec s_q, tq_qspec p_q, tq_qspec c_q, int32_t c_params, const float* mask,

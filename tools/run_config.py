@@ -83,6 +83,13 @@ def run(name, steps, warmup, use_graph=True, device='cuda:0', tiny=False, batch=
                 forward, kind = FusedBertPegEngine(model, recipe.batch, recipe.seq), 'fused PEG engine (engine/fused_peg.py)'
         except UnsupportedByEngine as e:
             kind = f'module path ({e})'
+    elif on_gpu and recipe.family == 'mobilebert':
+        from engine.fused import UnsupportedByEngine
+        from engine.fused_mobilebert import FusedMobileBertEngine
+        try:
+            forward, kind = FusedMobileBertEngine(model, recipe.batch, recipe.seq), 'fused MobileBERT engine (engine/fused_mobilebert.py)'
+        except UnsupportedByEngine as e:
+            kind = f'module path ({e})'
     with torch.no_grad():
         for _ in range(2):
             ref = forward(ids, mask)

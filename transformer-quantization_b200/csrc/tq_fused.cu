@@ -360,6 +360,7 @@ struct AttnArgs {
     __nv_bfloat16* c_ctr;         // [B * AT, H * AD] centred context grid (or null)
     unsigned char* c_u8;          // [B * AT, H * AD] context x_int, one byte each (8-bit operand mode; or null)
     float inv_sqrt_d;             // 1 / sqrt(head_dim)
+    float sqrt_d;                 // != 0: scores are DIVIDED by this value (true head_dim not a power of 4: 1 / sqrt(d) is not exact)
     int32_t qkv_params, c_params; // parameter slots of q_q / k_q / v_q and of c_q: 1, or a divisor of H (per-embedding-group
                                   // quantizers whose groups hold whole heads: head h uses slot h / (H / params))
 };
@@ -387,7 +388,7 @@ __device__ __forceinline__ float div_by(float e, float d, float r, bool ieee) {
 
 // per-row work of the softmax / epilogue warps: TWO threads per query row (warps w and w+4 of the
 // eight share a TMEM lane quarter), each owns one 64-key half of the row = one swizzle span of P
-template <bool FAST>
+template <bool FAST, bool DIVD>
 __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const QP& qp, const QP& qc, float sqk,
                                           float spv, uint32_t trow, int row, int quarter, int lane, int warp, int b,
                                           int h, int32_t dmodel, const float* smask, unsigned char* pP, float* xchg,
@@ -411,7 +412,9 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
             float2 t;                                                               // quantized_bert.py:153-154
             if (FAST) t = dequant2(quant_int2_finite(sc, qs2), qs2);
             else t = make_float2(qdq_t<false>(sc.x, qs), qdq_t<false>(sc.y, qs));
-            t = __fadd2_rn(__fmul2_rn(t, inv2), *reinterpret_cast<const float2*>(smask + c0 + j));   // :190-194
+            if (DIVD) t = make_float2(__fdiv_rn(t.x, a.sqrt_d), __fdiv_rn(t.y, a.sqrt_d));           // scores / math.sqrt(d)
+            else t = __fmul2_rn(t, inv2);                                                             // (exact for d = 4^n)
+            t = __fadd2_rn(t, *reinterpret_cast<const float2*>(smask + c0 + j));                      // :190-194
             vmax = fmaxf(vmax, fmaxf(t.x, t.y));
             v[j] = __float_as_uint(t.x);
             v[j + 1] = __float_as_uint(t.y);
@@ -634,10 +637,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
         const float sqk = qsm[3 * 8] * qsm[4 * 8];
         const float spv = qp.scale * qsm[5 * 8];
 
-        if (qs.exact | qp.exact | qc.exact)
-            attn_rows<false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
+        if (a.sqrt_d != 0.0f) {
+            if (qs.exact | qp.exact | qc.exact)
+                attn_rows<false, true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
+            else
+                attn_rows<true, true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
+        } else if (qs.exact | qp.exact | qc.exact)
+            attn_rows<false, false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
         else
-            attn_rows<true>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
+            attn_rows<true, false>(a, qs, qp, qc, sqk, spv, trow, row, quarter, lane, warp, b, h, dmodel, smask, pP, xchg, bar_s, bar_p, bar_o, bar_v, sP, sV, tmem);
     }
     tc_fence_before();
     __syncthreads();
@@ -669,7 +677,8 @@ extern "C" {
 
 static int attention_impl(const void* qkv_ctr_bf16, void* c_ctr_bf16, void* c_u8, int32_t B, int32_t T, int32_t H,
                           int32_t head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q, tq_qspec p_q,
-                          tq_qspec c_q, const float* mask, void* stream, int32_t qkv_params = 1, int32_t c_params = 1) {
+                          tq_qspec c_q, const float* mask, void* stream, int32_t qkv_params = 1, int32_t c_params = 1,
+                          int32_t true_head_dim = 0) {
     using namespace tq::fused;
     if (qkv_ctr_bf16 == nullptr || (c_ctr_bf16 == nullptr && c_u8 == nullptr) || B < 1 || H < 1) return TQ_EINVAL;
     if (T != AT || head_dim != AD) return TQ_EUNSUPPORTED;
@@ -703,7 +712,11 @@ static int attention_impl(const void* qkv_ctr_bf16, void* c_ctr_bf16, void* c_u8
     a.mask = mask;
     a.c_ctr = reinterpret_cast<__nv_bfloat16*>(c_ctr_bf16);
     a.c_u8 = reinterpret_cast<unsigned char*>(c_u8);
-    a.inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
+    if (true_head_dim < 0 || true_head_dim > head_dim) return TQ_EINVAL;
+    const int32_t dd = true_head_dim > 0 ? true_head_dim : head_dim;
+    a.inv_sqrt_d = 1.0f / sqrtf((float)dd);
+    const float sq = sqrtf((float)dd);                 // math.sqrt(d) in the reference (float64 there; the tensor is fp32)
+    a.sqrt_d = (sq * sq == (float)dd && (dd & (dd - 1)) == 0) ? 0.0f : sq;      // power of 4: multiply by the exact reciprocal
     if (qkv_params < 1 || c_params < 1 || H % qkv_params != 0 || H % c_params != 0) return TQ_EINVAL;
     a.qkv_params = qkv_params;
     a.c_params = c_params;
@@ -730,6 +743,14 @@ int tq_attention_peg_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int
     if (c_i8 == nullptr) return TQ_EINVAL;
     return attention_impl(qkv_ctr_bf16, nullptr, c_i8, B, T, H, head_dim, q_q, k_q, v_q, s_q, p_q, c_q, mask, stream, qkv_params,
                           c_params);
+}
+
+int tq_attention_pad_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int32_t T, int32_t H, int32_t head_dim,
+                            int32_t true_head_dim, tq_qspec q_q, tq_qspec k_q, tq_qspec v_q, tq_qspec s_q, tq_qspec p_q,
+                            tq_qspec c_q, const float* mask, void* stream) {
+    if (c_i8 == nullptr) return TQ_EINVAL;
+    return attention_impl(qkv_ctr_bf16, nullptr, c_i8, B, T, H, head_dim, q_q, k_q, v_q, s_q, p_q, c_q, mask, stream, 1, 1,
+                          true_head_dim);
 }
 
 static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {

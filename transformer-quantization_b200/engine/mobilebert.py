@@ -248,6 +248,10 @@ class QuantMobileBertForSequenceClassification(QuantizedModel):
                 if isinstance(m, nn.Linear) and m.bias is not None:
                     m.bias.data.zero_()
             elif isinstance(m, QuantNoNorm):
-                m.weight.data.fill_(1.0)
-                m.bias.data.zero_()
+                # NOT the (1, 0) of an untrained NoNorm: both parameters go through ONE quantizer whose fixed range is
+                # the one seen last -- the bias's (reference quantized_mobilebert.py:58-72).  An all-zero bias would give
+                # a degenerate range that clamps the weight to ~0 and with it every activation of the network; trained
+                # checkpoints have biases of the weights' magnitude, so the synthetic model gets them too.
+                m.weight.data = (1.0 + 0.1 * torch.randn(m.weight.shape, generator=g)).to(m.weight.device)
+                m.bias.data = (0.5 * torch.randn(m.bias.shape, generator=g)).to(m.bias.device)
         return self

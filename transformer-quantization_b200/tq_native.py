@@ -106,6 +106,8 @@ SIGNATURES = {
                                                    ctypes.c_void_p, _i64, _i64, _i64, QSpec, _i32, QSpec, _i32, QSpec, _i32,
                                                    ctypes.c_void_p, QSpec, _i32, QSpec, _i32, _c_f32p, _c_f32p,
                                                    ctypes.c_float, QSpec, _i32, _i64, ctypes.c_void_p]),
+    'tq_attention_pad_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _i32, _i32, QSpec, QSpec,
+                                               QSpec, QSpec, QSpec, QSpec, _c_f32p, ctypes.c_void_p]),
     'tq_attention_peg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _i32, QSpec, QSpec,
                                                QSpec, _i32, QSpec, QSpec, QSpec, _i32, _c_f32p, ctypes.c_void_p]),
     'tq_linear_qdq_bf16_o8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p, _i64, _i64, _i64,
@@ -507,6 +509,15 @@ class CudaOps:
                   w_spec, int(w_params), out_spec, int(out_params), res_i8.data_ptr(), res_spec, int(res_params), out2_spec,
                   int(out2_params), gamma_q.data_ptr(), beta.data_ptr(), float(eps), ln_spec, int(ln_params), int(seg_width),
                   _stream())
+        return out_i8
+
+    def attention_pad_i8(self, qkv_ctr, B, T, H, head_dim, true_head_dim, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec, mask,
+                         out_i8):
+        """tq_attention_pad_qdq_i8: heads of `true_head_dim` < 64 dims in zero-padded 64-column slots"""
+        _chk_cuda(qkv_ctr, mask, out_i8)
+        self._run('attention', 4 * B * H * T * T * true_head_dim, 1, self.lib.tq_attention_pad_qdq_i8, qkv_ctr.data_ptr(),
+                  out_i8.data_ptr(), B, T, H, head_dim, true_head_dim, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec,
+                  _ptr(mask), _stream())
         return out_i8
 
     def attention_peg_i8(self, qkv_ctr, B, T, H, head_dim, q_spec, k_spec, v_spec, qkv_params, s_spec, p_spec, c_spec, c_params,
