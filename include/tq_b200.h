@@ -55,7 +55,8 @@ typedef struct tq_qspec {
 /* ---- library info ------------------------------------------------------------------------- */
 int         tq_version(void);              /* ABI version: 1 = inference path; 2 adds the training-time entry points
                                               * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 (current) adds
-                                              * tq_linear_seg_qdq_i8, tq_linear_nonorm_qdq_i8 and the tq_*_peg_* entry points */
+                                              * tq_linear_seg_qdq_i8, tq_linear_nonorm_qdq_i8, tq_calib_finalize_f32,
+                                              * tq_attention_pad_qdq_i8 and the tq_*_peg_* entry points */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
 
@@ -141,6 +142,16 @@ int tq_set_range_asym_f32(const float* x_min, const float* x_max, int64_t k, int
 int tq_set_range_sym_f32(const float* x_min, const float* x_max, int64_t k, int32_t n_bits,
                          float eps, int32_t log_domain, float* delta, uint8_t* is_signed,
                          void* stream);
+
+/* Calibration-time fused GEMM, second half (reference quantization_manager.py:99-106 after hijacker.py:98-116):
+ * tq_linear_qdq_bf16(..., tile_minmax) reduced min / max of its own output into tile_minmax (two ordered-int words,
+ * zero-initialised by the caller once); this single launch decodes them, applies the estimator update in place on
+ * cur_min / cur_max (mode 0 current, 1 running EMA with `momentum`, 2 all-time min/max; `first`: initialise) and sets the
+ * per-tensor quantizer range (asymmetric: delta + zero_float; symmetric: delta + is_signed) -- no min/max pass over
+ * the tensor, no separate range_update / set_range launches.  The two words are reset to zero. */
+int tq_calib_finalize_f32(void* tile_minmax, float* cur_min, float* cur_max, int32_t mode, double momentum,
+                          int32_t first, int32_t symmetric, int32_t n_bits, float eps, int32_t log_domain,
+                          float* delta, float* zero_float, void* is_signed, void* stream);
 
 /* ---- MSE range estimator --------------------------------------------------------------------
  * a9: MSE_Estimator.loss_fx (range_estimators.py:248-256) for a whole table of candidate

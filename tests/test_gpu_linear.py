@@ -200,3 +200,56 @@ def test_fused_linear_declines_while_autograd_records():
     assert lin.weight.grad is not None and lin.weight.grad.abs().sum().item() > 0
     with torch.no_grad():
         assert lin(x).grad_fn is None
+
+
+@pytest.mark.parametrize('est_name', ['running_minmax', 'current_minmax', 'allminmax'])
+@pytest.mark.parametrize('sym', [False, True])
+@torch.no_grad()
+def test_calibration_time_fused_gemm(est_name, sym):
+    """QuantLinear in estimate_ranges state: min/max out of the GEMM epilogue + tq_calib_finalize_f32 (one launch) must
+    give exactly the ranges and outputs of the GEMM -> min/max kernel -> range update -> set_quant_range -> QDQ chain,
+    over several calibration batches (EMA / all-time rules included)."""
+    from quantization import fused_linear
+    from quantization.autoquant_utils import QuantLinear
+    from quantization.quantizers import QMethods
+    from quantization.range_estimators import RangeEstimators
+    act_m = QMethods.symmetric_uniform if sym else QMethods.asymmetric_uniform
+
+    def make():
+        torch.manual_seed(0)
+        lin = QuantLinear(256, 384, bias=True, method=QMethods.symmetric_uniform, act_method=act_m, n_bits=8, n_bits_act=8,
+                          act_range_method=RangeEstimators[est_name]).to(DEV)
+        lin.weight.data.normal_(0, 0.05)
+        lin.bias.data.normal_(0, 0.05)
+        lin.quantized()
+        lin.eval()
+        return lin
+
+    q_in = QMethods.asymmetric_uniform.cls(n_bits=8)
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(4, 64, 256, generator=g) * (1 + i)).to(DEV) for i in range(3)]
+    q_in.set_quant_range(-8.0, 8.0)
+    a, b = make(), make()
+    launches = {}
+    for flag, lin in ((True, a), (False, b)):
+        fused_linear.CALIBRATION_FUSION = flag
+        l0 = tq_native.ops().launches
+        try:
+            outs = [lin(q_in(x)) for x in batches]
+        finally:
+            fused_linear.CALIBRATION_FUSION = True
+        launches[flag] = tq_native.ops().launches - l0
+        lin._outs = outs
+    torch.cuda.synchronize()
+    qa, qb = a.activation_quantizer.quantizer, b.activation_quantizer.quantizer
+    assert torch.equal(qa._delta.reshape(-1), qb._delta.reshape(-1))
+    if not sym:
+        assert torch.equal(qa._zero_float.reshape(-1), qb._zero_float.reshape(-1))
+    else:
+        assert bool(qa._signed) == bool(qb._signed)
+    ea, eb = a.activation_quantizer.range_estimator, b.activation_quantizer.range_estimator
+    assert torch.equal(ea.current_xmin.reshape(-1), eb.current_xmin.reshape(-1))
+    assert torch.equal(ea.current_xmax.reshape(-1), eb.current_xmax.reshape(-1))
+    for ya, yb in zip(a._outs, b._outs):
+        assert torch.equal(ya, yb)
+    assert launches[True] < launches[False]          # two launches and one pass over the tensor fewer per batch

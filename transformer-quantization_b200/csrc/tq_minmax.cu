@@ -387,6 +387,51 @@ static int64_t slab_rows(int64_t rows, int64_t col_blocks, int unit) {
     return rps;
 }
 
+
+// Calibration-time fused GEMM (SURVEY.md section 7 "hard parts", reference quantization_manager.py:99-106 after
+// hijacker.py:98-116): the GEMM epilogue reduced min / max of its own output into two ordered-int words
+// (tile_minmax); this ONE single-thread launch decodes them, applies the estimator update (current / running EMA /
+// all-time min-max, range_estimators.py:142-143, 166-167, 205-214), and sets the per-tensor quantizer range
+// (quantizers.py:263-282 asymmetric, 334-344 symmetric) -- the min/max pass over the tensor and two scalar launches
+// are gone.  The two words are reset for the next calibration batch.
+__global__ void calib_finalize_kernel(uint32_t* __restrict__ tile_mm, float* __restrict__ cmin, float* __restrict__ cmax,
+                                      int mode, float m_new, float m_old, int first, int symmetric, int n_bits, float eps,
+                                      int log_domain, float* __restrict__ delta, float* __restrict__ zero_float,
+                                      uint8_t* __restrict__ is_signed) {
+    const float a0 = ord2f(~tile_mm[0]), b0 = ord2f(tile_mm[1]);
+    tile_mm[0] = 0u;
+    tile_mm[1] = 0u;
+    float mn, mx;
+    if (mode == 0 || first) {
+        mn = a0;
+        mx = b0;
+    } else if (mode == 1) {
+        mn = __fadd_rn(__fmul_rn(m_new, a0), __fmul_rn(m_old, cmin[0]));
+        mx = __fadd_rn(__fmul_rn(m_new, b0), __fmul_rn(m_old, cmax[0]));
+    } else {
+        const float c0 = cmin[0], c1 = cmax[0];
+        mn = (a0 != a0 || c0 != c0) ? __int_as_float(0x7fc00000) : fminf(c0, a0);
+        mx = (b0 != b0 || c1 != c1) ? __int_as_float(0x7fc00000) : fmaxf(c1, b0);
+    }
+    cmin[0] = mn;
+    cmax[0] = mx;
+    const float a = tmin0(mn), b = tmaxe(mx, eps);
+    if (!symmetric) {
+        const float int_max = (float)(1u << n_bits) - 1.0f;
+        const float d = __fdiv_rn(__fsub_rn(b, a), int_max);
+        zero_float[0] = __fdiv_rn(-a, d);
+        delta[0] = log_domain ? logf(d) : d;
+    } else {
+        const int sg = a < 0.0f;
+        const float int_max = (float)(1u << (n_bits - (sg ? 1 : 0))) - 1.0f;
+        const float fa = fabsf(a);
+        const float am = (fa != fa || b != b) ? __int_as_float(0x7fc00000) : fmaxf(fa, b);
+        const float d = __fdiv_rn(am, int_max);
+        delta[0] = log_domain ? logf(d) : d;
+        *is_signed = sg ? 1 : 0;
+    }
+}
+
 }  // namespace tq
 
 extern "C" {
@@ -497,6 +542,20 @@ int tq_set_range_sym_f32(const float* x_min, const float* x_max, int64_t k, int3
     if (n_bits < 1 || n_bits > 16) return TQ_EINVAL;
     tq::set_range_sym_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x_min, x_max, k, n_bits, eps, log_domain,
                                                                   delta, is_signed);
+    return tq::launch_status();
+}
+
+
+int tq_calib_finalize_f32(void* tile_minmax, float* cur_min, float* cur_max, int32_t mode, double momentum, int32_t first,
+                          int32_t symmetric, int32_t n_bits, float eps, int32_t log_domain, float* delta, float* zero_float,
+                          void* is_signed, void* stream) {
+    if (tile_minmax == nullptr || cur_min == nullptr || cur_max == nullptr || delta == nullptr) return TQ_EINVAL;
+    if (mode < 0 || mode > 2 || n_bits < 1 || n_bits > 16) return TQ_EINVAL;
+    if (symmetric ? is_signed == nullptr : zero_float == nullptr) return TQ_EINVAL;
+    const float m_new = (float)(1.0 - momentum), m_old = (float)momentum;
+    tq::calib_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint32_t*>(tile_minmax), cur_min, cur_max, mode,
+                                                                m_new, m_old, first, symmetric, n_bits, eps, log_domain, delta,
+                                                                zero_float, reinterpret_cast<uint8_t*>(is_signed));
     return tq::launch_status();
 }
 

@@ -22,6 +22,7 @@ from torch.nn import functional as F
 import tq_native
 
 ENABLED = True          # tests flip this to compare against the unfused path
+CALIBRATION_FUSION = True      # min/max of a calibrating layer from its GEMM epilogue (tests flip it)
 
 _ACT_CODES = ((nn.GELU, 1), (nn.ReLU, 2), (nn.Tanh, 3))
 
@@ -109,6 +110,17 @@ def _wants_grad(layer, weight, bias):
     return False
 
 
+def _fused_calibration(mgr):
+    """range estimation by a per-tensor min/max rule on a per-tensor quantizer whose range is not being trained:
+    the min/max can come out of the GEMM epilogue (tq_linear_qdq_bf16 tile_minmax + tq_calib_finalize_f32)"""
+    est, qz = mgr.range_estimator, mgr.quantizer
+    if not CALIBRATION_FUSION or est is None or est.per_group_range_estimation or not mgr._updates_ranges():
+        return False
+    if qz.axis is not None or qz.per_channel or est.fused_minmax_mode() is None:
+        return False
+    return not any(isinstance(getattr(qz, n, None), nn.Parameter) for n in ('_delta', '_zero_float'))
+
+
 def try_fused(layer, x, weight, bias):
     """Fused QuantLinear forward or None.  ``weight`` is what get_params() returned."""
     if not ENABLED or layer.training or not layer._quant_w or not x.is_cuda or x.dtype != torch.float32:
@@ -165,9 +177,19 @@ def try_fused(layer, x, weight, bias):
     else:
         a_ctr, k_split = ops.split3(x2), 3
 
+    tile_mm = None
+    if calibrate and _fused_calibration(mgr):
+        # calibration-time fused GEMM: the epilogue reduces min / max of its own output, ONE launch turns them into the
+        # estimator update + quantizer range -- no min/max pass over y, no scalar launches; the QDQ then reads y from L2
+        tile_mm = getattr(layer, '_tq_tile_mm', None)
+        if tile_mm is None or tile_mm.device != x.device:
+            tile_mm = layer._tq_tile_mm = torch.zeros(2, dtype=torch.int32, device=x.device)
     y, _ = ops.linear(a_ctr, w_ctr, bias, M, N, K, k_split, a_spec, w_spec, w_params, act, out_spec,
-                      out_params, want_f32=True, want_ctr=False)
+                      out_params, want_f32=True, want_ctr=False, tile_minmax=tile_mm)
     y = y.view(*x.shape[:-1], N)
+    if tile_mm is not None:
+        mgr.range_estimator.update_from_tile(tile_mm, mgr.quantizer)
+        return mgr.quantizer(y)
     if calibrate:
         return mgr(y)                              # estimator update + set_quant_range + QDQ kernels
     if out_spec is not None and out_params == 1 and mgr.quantizer.n_bits <= 8:

@@ -317,6 +317,16 @@ class AsymmetricUniformQuantizer(QuantizerBase):
         self._zero_float = zero_float
         self._range_epoch = getattr(self, '_range_epoch', 0) + 1     # invalidates grid tags of earlier outputs
 
+    def _range_from_tile(self, tile_mm, cur_min, cur_max, mode, momentum, first):
+        """set_quant_range fused with the estimator update, fed by a GEMM epilogue's min/max words (tq_calib_finalize_f32)"""
+        delta = self._alloc_like('_delta', cur_min)
+        zero_float = self._alloc_like('_zero_float', cur_min)
+        tq_native.ops().calib_finalize(tile_mm, cur_min, cur_max, mode, momentum, first, False, self.n_bits, self.eps,
+                                       self.scale_domain == 'log', delta, zero_float, None)
+        self._delta = delta
+        self._zero_float = zero_float
+        self._range_epoch = getattr(self, '_range_epoch', 0) + 1
+
     def make_range_trainable(self):
         if self.delta not in self.parameters():
             self._delta = torch.nn.Parameter(self._delta)
@@ -369,6 +379,17 @@ class SymmetricUniformQuantizer(AsymmetricUniformQuantizer):
             signed = torch.empty((), dtype=torch.bool, device=x_min.device)
         tq_native.ops().set_range_sym(x_min, x_max, self.n_bits, self.eps, self.scale_domain == 'log',
                                       delta, signed)
+        self._delta = delta
+        self._signed = signed
+        self._range_epoch = getattr(self, '_range_epoch', 0) + 1
+
+    def _range_from_tile(self, tile_mm, cur_min, cur_max, mode, momentum, first):
+        delta = self._alloc_like('_delta', cur_min)
+        signed = self._signed
+        if signed is None or signed.device != cur_min.device:
+            signed = torch.empty((), dtype=torch.bool, device=cur_min.device)
+        tq_native.ops().calib_finalize(tile_mm, cur_min, cur_max, mode, momentum, first, True, self.n_bits, self.eps,
+                                       self.scale_domain == 'log', delta, None, signed)
         self._delta = delta
         self._signed = signed
         self._range_epoch = getattr(self, '_range_epoch', 0) + 1

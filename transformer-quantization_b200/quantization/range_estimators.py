@@ -92,6 +92,25 @@ class RangeEstimatorBase(nn.Module):
         mn, mx = _dist.allreduce_minmax(mm[0], mm[1])
         return mn, mx
 
+    # ---- calibration-time fused GEMM: the producer's epilogue already reduced min / max (tile_minmax) ----
+    def fused_minmax_mode(self):
+        """(mode, momentum) if this estimator's update is a per-tensor min/max rule tq_calib_finalize_f32 implements
+        (0 current, 1 running EMA, 2 all-time), else None"""
+        return None
+
+    def _per_tensor_minmax_rule(self):
+        return (self.axis is None and not self.per_channel and not self.per_group_range_estimation
+                and not getattr(self, 'percentile', None) and not _dist.enabled())
+
+    def update_from_tile(self, tile_mm, quantizer):
+        """estimator update + quantizer.set_quant_range from the GEMM epilogue's ordered-int min/max words, one launch"""
+        mode, momentum = self.fused_minmax_mode()
+        first = self.current_xmin is None or self.current_xmin.dim() != 0 or self.current_xmin.device != tile_mm.device
+        if first:
+            self.current_xmin = torch.empty((), dtype=torch.float32, device=tile_mm.device)
+            self.current_xmax = torch.empty((), dtype=torch.float32, device=tile_mm.device)
+        quantizer._range_from_tile(tile_mm, self.current_xmin, self.current_xmax, mode, momentum, first)
+
     def _grouped(self, mn, mx, ranges=None):
         ng = self.n_groups
         assert ng > 0 and mn.numel() % ng == 0
@@ -114,6 +133,9 @@ class CurrentMinMaxEstimator(RangeEstimatorBase):
     def __init__(self, percentile=None, *args, **kwargs):
         self.percentile = percentile
         super().__init__(*args, **kwargs)
+
+    def fused_minmax_mode(self):
+        return (0, 0.0) if self._per_tensor_minmax_rule() else None
 
     def _ranges_pass(self, x):
         # FP32 pass that records per-dim dynamic ranges for the PEG permutation (reference :68-80;
@@ -179,6 +201,9 @@ class AllMinMaxEstimator(RangeEstimatorBase):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
 
+    def fused_minmax_mode(self):
+        return (2, 0.0) if self._per_tensor_minmax_rule() else None
+
     def forward(self, x):
         mn, mx = self._channel_minmax(x) if self.per_channel else self._tensor_minmax(x)
         return self._store(mn, mx, mode=2)
@@ -190,6 +215,9 @@ class RunningMinMaxEstimator(RangeEstimatorBase):
     def __init__(self, momentum=0.9, *args, **kwargs):
         self.momentum = momentum
         super().__init__(*args, **kwargs)
+
+    def fused_minmax_mode(self):
+        return (1, self.momentum) if self._per_tensor_minmax_rule() else None
 
     def forward(self, x):
         if self.axis is not None:

@@ -65,6 +65,8 @@ SIGNATURES = {
                                              _c_f32p, _c_f32p, ctypes.c_void_p]),
     'tq_set_range_sym_f32': (ctypes.c_int, [_c_f32p, _c_f32p, _i64, _i32, ctypes.c_float, _i32,
                                             _c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
+    'tq_calib_finalize_f32': (ctypes.c_int, [ctypes.c_void_p, _c_f32p, _c_f32p, _i32, ctypes.c_double, _i32, _i32, _i32,
+                                             ctypes.c_float, _i32, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
     'tq_mse_workspace_bytes': (ctypes.c_size_t, [_i32]),
     'tq_mse_sse_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i32, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_void_p]),
@@ -352,6 +354,14 @@ class CudaOps:
         self._run('set_range', 12 * x_min.numel(), 1, self.lib.tq_set_range_sym_f32, x_min.data_ptr(),
                   x_max.data_ptr(), x_min.numel(), int(n_bits), float(eps), int(bool(log_domain)),
                   delta.data_ptr(), is_signed.data_ptr(), _stream())
+
+    def calib_finalize(self, tile_mm, cur_min, cur_max, mode, momentum, first, symmetric, n_bits, eps, log_domain, delta,
+                       zero_float, is_signed):
+        """tq_calib_finalize_f32: GEMM-epilogue min/max -> estimator update -> quantizer range, one launch"""
+        _chk_cuda(tile_mm, cur_min, cur_max, delta, zero_float, is_signed)
+        self._run('set_range', 32, 1, self.lib.tq_calib_finalize_f32, tile_mm.data_ptr(), cur_min.data_ptr(), cur_max.data_ptr(),
+                  int(mode), float(momentum), int(bool(first)), int(bool(symmetric)), int(n_bits), float(eps),
+                  int(bool(log_domain)), delta.data_ptr(), _ptr(zero_float), _ptr(is_signed), _stream())
 
     # -- MSE ------------------------------------------------------------------------------------
     def mse_sse(self, x, cand, n_cand, loss_accum):
