@@ -466,3 +466,24 @@ def test_linear_residual_layernorm_lean_matches_general_kernel(M, N, K, monkeypa
         zc2, _ = ops.ln_qdq(uc, u_sp, 1, gt, bt, 1e-12, z_sp, 1)
         torch.cuda.synchronize()
         assert torch.equal(zc2, zc_l)
+
+
+def test_engine_detects_reallocated_quantizer_buffers():
+    """the engine's specs hold raw device pointers; a recalibration that re-allocates a quantizer's
+    buffers must be detected instead of reading freed memory"""
+    from engine.fused import FusedBertEngine
+    model = _model(DEV)
+    model.set_quant_state(True, True)
+    ids = torch.randint(0, 2000, (4, 128), generator=torch.Generator().manual_seed(5)).to(DEV)
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        model(ids, mask)
+        model.fix_ranges()
+        eng = FusedBertEngine(model, 4, 128)
+        eng(ids, mask)
+        site = model.layers[0].c.activation_quantizer
+        site.reset_ranges()                       # buffers dropped ...
+        model(ids, mask)                          # ... and re-allocated by the next calibration forward
+        model.fix_ranges()
+        with pytest.raises(RuntimeError, match='re-allocated'):
+            eng(ids, mask)

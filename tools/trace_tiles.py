@@ -24,7 +24,7 @@ trace = torch.zeros(16, dtype=torch.int64, device=dev)
 tiles = torch.zeros(64, dtype=torch.int64, device=dev)
 os.environ['TQ_LINEAR_TRACE_PTR'] = hex(trace.data_ptr())
 os.environ['TQ_LINEAR_TRACE_TILES'] = hex(tiles.data_ptr())
-names = ['par0', 'par1', 'acc', 'epiE', 'mmaS', 'ld1', 'mmaE', 'prodE']
+names = ['par0', 'par1', 'acc', 'epiE', 'mmaS', 'ld1|drained', 'mmaE', 'prodE']
 
 
 def run(label, fn):
@@ -78,3 +78,26 @@ for N, K, label in [(2304, 768, 'qkv'), (768, 768, 'attn_out'), (3072, 768, 'ffn
             run(f'{"LEAN" if lean_flag == "1" else "general"} i8 {label} {N}x{K} residual + LayerNorm, u8 out',
                 lambda: ops.linear_res_ln_i8(a8, w8, rsum, bias, M, N, K, a_sp, w_sp, 1, o_sp, r8, r_sp, u_sp, gamma, beta, 1e-12,
                                              z_sp, y8))
+
+
+# ---- PEG kernels (group-by-group accumulation): slot 5 = all groups drained
+os.environ['TQ_LINEAR_LEAN'] = '1'
+G = 6
+for N, K, label, ln in [(2304, 768, 'PEG qkv', False), (3072, 768, 'PEG ffn_in', False), (768, 768, 'PEG attn_out + LN', True), (768, 3072, 'PEG ffn_out + LN (A per-tensor)', True)]:
+    g = 1 if K == 3072 else G
+    a8 = torch.randint(0, 256, (M, K), device=dev).to(torch.uint8)
+    w8 = torch.randint(-128, 128, (N, K), device=dev).to(torch.int8)
+    grs = w8.to(torch.int32).view(N, g, K // g).sum(dim=2, dtype=torch.int32).t().contiguous()
+    bias = torch.randn(N, device=dev) * 0.1
+    r8 = torch.randint(0, 256, (M, N), device=dev).to(torch.uint8)
+    gamma, beta = torch.ones(N, device=dev), torch.zeros(N, device=dev)
+    nseg = N // 128
+    a_sp, w_sp = spec(0.02, 128, None, g), spec(0.001, None, True)
+    o_sp, r_sp, u_sp, z_sp = spec(0.05, 120, None, nseg), spec(0.03, 128, None, nseg), spec(0.06, 125, None, nseg), spec(0.03, 128, None, nseg)
+    y8 = torch.empty(M, N, device=dev, dtype=torch.uint8)
+    if ln:
+        run(f'{label} {N}x{K}', lambda: ops.linear_peg_res_ln_i8(a8, w8, grs, bias, M, N, K, a_sp, g, w_sp, 1, o_sp, nseg, r8, r_sp, nseg,
+                                                                 u_sp, nseg, gamma, beta, 1e-12, z_sp, nseg, 128, y8))
+    else:
+        run(f'{label} {N}x{K}', lambda: ops.linear_peg_i8(a8, w8, grs, bias, M, N, K, a_sp, g, w_sp, 1, o_sp, nseg, 128, 1 if N == 3072 else 0,
+                                                          out_i8=y8))

@@ -398,6 +398,7 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
     const int k0 = hs * 64;
     const QP2 qs2 = pair_of(qs), qp2 = pair_of(qp), qc2 = pair_of(qc);
     const float2 sqk2 = make_float2(sqk, sqk), inv2 = make_float2(a.inv_sqrt_d, a.inv_sqrt_d), spv2 = make_float2(spv, spv);
+    const float2 sinv2 = make_float2(__fmul_rn(qs.scale, a.inv_sqrt_d), __fmul_rn(qs.scale, a.inv_sqrt_d));
     mbar_wait(bar_s, 0);
     tc_fence_after();
     // pass 1: scores -> QDQ -> / sqrt(d) + mask, written back to TMEM; row max
@@ -410,10 +411,16 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
         for (int j = 0; j < 16; j += 2) {
             const float2 sc = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sqk2);
             float2 t;                                                               // quantized_bert.py:153-154
-            if (FAST) t = dequant2(quant_int2_finite(sc, qs2), qs2);
-            else t = make_float2(qdq_t<false>(sc.x, qs), qdq_t<false>(sc.y, qs));
-            if (DIVD) t = make_float2(__fdiv_rn(t.x, a.sqrt_d), __fdiv_rn(t.y, a.sqrt_d));           // scores / math.sqrt(d)
-            else t = __fmul2_rn(t, inv2);                                                             // (exact for d = 4^n)
+            if (FAST && !DIVD) {
+                // centred integers, then ONE multiply by scale / sqrt(d): 1 / sqrt(d) is a power of two here, so
+                // fl(fl(scale * c) / sqrt(d)) == fl((scale / sqrt(d)) * c) bit for bit -- three packed FP32 ops fewer
+                t = __fmul2_rn(quant_ctr2_finite(sc, qs2), sinv2);
+            } else {
+                if (FAST) t = dequant2(quant_int2_finite(sc, qs2), qs2);
+                else t = make_float2(qdq_t<false>(sc.x, qs), qdq_t<false>(sc.y, qs));
+                if (DIVD) t = make_float2(__fdiv_rn(t.x, a.sqrt_d), __fdiv_rn(t.y, a.sqrt_d));       // scores / math.sqrt(d)
+                else t = __fmul2_rn(t, inv2);                                                         // (exact for d = 4^n)
+            }
             t = __fadd2_rn(t, *reinterpret_cast<const float2*>(smask + c0 + j));                      // :190-194
             vmax = fmaxf(vmax, fmaxf(t.x, t.y));
             v[j] = __float_as_uint(t.x);

@@ -1975,30 +1975,37 @@ struct Args {
     const float* ln_gamma;
     const float* ln_beta;
     float ln_eps;
+    long long* trace;
+    long long* trace_tiles;
 };
 
 // segment parameters sg[] as in the lean kernels: 0 (unused), 1-4 q1 {s, r, clo, chi}, 5 zp1 + 1.5 * 2^23, 6 exact,
 // 7-10 q2, 11 res scale, 12 2^23 + res zp, 13-16 q3, 17 zp3 + 1.5 * 2^23
 
 // drain one group's accumulator (this warp's 64 columns) into the running sums
-template <bool FIRST>
 __device__ __forceinline__ void drain_group(float (&run)[64], uint32_t tmem_buf, int half, const int32_t* __restrict__ corr,
                                             float csg) {
-    uint32_t v[32];
+    // four 16-column chunks, the next one in flight during the arithmetic of the current one (two 16-register sets:
+    // with the 64 running sums a 32-column double buffer spilled)
+    uint32_t va[16], vb[16];
+    tmem_ld16_nowait(tmem_buf + (uint32_t)(half * 32), va);
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int c0 = half * 32 + s * 64;
-        tmem_ld32_nowait(tmem_buf + (uint32_t)c0, v);
+    for (int i = 0; i < 4; ++i) {
+        uint32_t (&v)[16] = (i & 1) ? vb : va;
+        uint32_t (&vn)[16] = (i & 1) ? va : vb;
         tmem_ld_fence(v);
+        const int c0 = half * 32 + (i >> 1) * 64 + (i & 1) * 16;
+        if (i + 1 < 4) tmem_ld16_nowait(tmem_buf + (uint32_t)(half * 32 + ((i + 1) >> 1) * 64 + ((i + 1) & 1) * 16), vn);
         const int4* cr = reinterpret_cast<const int4*>(corr + c0);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < 4; ++j4) {
             const int4 c = cr[j4];
             const int cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float a = __int2float_rn((int)v[4 * j4 + j] - cc[j]);
-                run[s * 32 + 4 * j4 + j] = FIRST ? __fmul_rn(csg, a) : __fmaf_rn(csg, a, run[s * 32 + 4 * j4 + j]);
+                const int r = (i >> 1) * 32 + (i & 1) * 16 + 4 * j4 + j;
+                run[r] = __fmaf_rn(csg, a, run[r]);
             }
         }
     }
@@ -2176,6 +2183,7 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int kb_per_group = (int)(K / 128) / G;
     const int num_kb = kb_per_group * G;
 
+    if (threadIdx.x == 0) TQL_TRACE(0);
     int p_stage = 0, p_pre = 0;
     uint32_t p_phase = 0;
     if (warp == kProdWarp && lane == 0) {
@@ -2222,6 +2230,7 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_trigger();
     pdl_wait();
+    if (threadIdx.x == 0) TQL_TRACE(1);
 
     if (warp == kProdWarp) {
         if (lane == 0) {
@@ -2249,10 +2258,12 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t idesc = (2u << 4) | (w_s8 << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int stage = 0, buf = 0;
             uint32_t phase = 0, bphase = 0;
-            for (int64_t t = tile0; t < tiles; t += tile_step) {
+            int tno = 0;
+            for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
                 for (int g = 0; g < G; ++g) {
                     mbar_wait(tempty_bar(buf), bphase ^ 1u);
                     tc_fence_after();
+                    if (g == 0) TQL_TTRACE(tno, 4);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                     for (int kb = 0; kb < kb_per_group; ++kb) {
                         mbar_wait(full_bar(stage), phase);
@@ -2266,6 +2277,7 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (++stage == ring) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit<1>(tfull_bar(buf));
+                    if (g == G - 1) TQL_TTRACE(tno, 6);
                     if (++buf == 2) { buf = 0; bphase ^= 1u; }
                 }
             }
@@ -2310,11 +2322,23 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (LNF && first) Pgb[jp] = make_float4(ep.ln_gamma[n], ep.ln_gamma[n + 1], ep.ln_beta[n], ep.ln_beta[n + 1]);
             }
             const float w_scale = __shfl_sync(0xffffffffu, mine.scale, 0);
-            for (int g = 0; g < G; ++g) {
-                const int zp_g = (int)__shfl_sync(0xffffffffu, mine.zp, 8 + g);
-                const float s_g = __shfl_sync(0xffffffffu, mine.scale, 8 + g);
-                for (int c = lane; c < BN; c += 32) corr[g * BN + c] = zp_g * ep.w_grp_rowsum[(int64_t)g * N + n0 + c];
-                if (lane == 0) csg[g] = __fmul_rn(s_g, w_scale);
+            // all row sums of the tile first (independent loads in flight together), then the stores: a load -> store
+            // per element made every one of the G * 4 loads of a lane wait for the previous one (12 k cycles per tile)
+            int32_t rsv[kMaxGroups][BN / 32];
+#pragma unroll
+            for (int g = 0; g < kMaxGroups; ++g)
+#pragma unroll
+                for (int i = 0; i < BN / 32; ++i)
+                    rsv[g][i] = g < G ? __ldg(ep.w_grp_rowsum + (int64_t)g * N + n0 + lane + 32 * i) : 0;
+#pragma unroll
+            for (int g = 0; g < kMaxGroups; ++g) {
+                if (g < G) {
+                    const int zp_g = (int)__shfl_sync(0xffffffffu, mine.zp, 8 + g);
+                    const float s_g = __shfl_sync(0xffffffffu, mine.scale, 8 + g);
+#pragma unroll
+                    for (int i = 0; i < BN / 32; ++i) corr[g * BN + lane + 32 * i] = zp_g * rsv[g][i];
+                    if (lane == 0) csg[g] = __fmul_rn(s_g, w_scale);
+                }
             }
             {
                 const float o_s = __shfl_sync(0xffffffffu, mine.scale, 1), o_r = __shfl_sync(0xffffffffu, mine.rcp, 1);
@@ -2357,8 +2381,10 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int quarter = warp & 3, half = warp >> 2;
         int buf = 0, pb = 0;
         uint32_t bphase = 0, pphase = 0;
-        for (int64_t t = tile0; t < tiles; t += tile_step) {
+        int tno = 0;
+        for (int64_t t = tile0; t < tiles; t += tile_step, ++tno) {
             const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+            if (threadIdx.x == 0) TQL_TTRACE(tno, 0);
             const int64_t row = m0 + quarter * 32 + lane;
             const bool row_ok = row < M;
             uint32_t r0[8], r1[8];
@@ -2372,20 +2398,24 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
             mbar_wait(pfull_bar(pb), pphase);
+            if (threadIdx.x == 0) TQL_TTRACE(tno, 1);
             const unsigned char* tp = tile_par(pb);
             const float2* Pb = reinterpret_cast<const float2*>(tp);
             const int32_t* corr = reinterpret_cast<const int32_t*>(tp + (BN / 2) * 8);
             const float* sg = reinterpret_cast<const float*>(tp + (BN / 2) * 8 + kMaxGroups * BN * 4);
             const float* csg = sg + kSegFloats;
             const int exact = __float_as_int(sg[6]);
-            float run[64];
+            float run[64];                    // (one drain body for every group: two inlined copies cost ~100 register moves per group)
+#pragma unroll
+            for (int i = 0; i < 64; ++i) run[i] = 0.0f;
             uint32_t last_buf = 0;
+#pragma unroll 1
             for (int g = 0; g < G; ++g) {
                 mbar_wait(tfull_bar(buf), bphase);
                 tc_fence_after();
+                if (threadIdx.x == 0 && g == 0) TQL_TTRACE(tno, 2);
                 const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
-                if (g == 0) drain_group<true>(run, tb, half, corr, csg[0]);
-                else drain_group<false>(run, tb, half, corr + g * BN, csg[g]);
+                drain_group(run, tb, half, corr + g * BN, csg[g]);
                 last_buf = tb;
                 tc_fence_before();
                 __syncwarp();
@@ -2393,6 +2423,7 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0 && !(LNF && g == G - 1)) mbar_arrive(tempty_bar(buf));
                 if (++buf == 2) { buf = 0; bphase ^= 1u; }
             }
+            if (threadIdx.x == 0) TQL_TTRACE(tno, 5);          // all groups drained
             if (LNF) {
                 if (warp == 0 && lane == 0) {       // this CTA's output scale s2 travels with its sums (see finish_res_ln)
                     const uint32_t my = cluster_ctarank(), cn = cluster_nctarank();
@@ -2405,6 +2436,7 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (exact) finish_plain<ACT, false, OUT8>(ep, run, Pb, sg, half, row, row_ok, n0, N);
                 else finish_plain<ACT, true, OUT8>(ep, run, Pb, sg, half, row, row_ok, n0, N);
             }
+            if (threadIdx.x == 0) TQL_TTRACE(tno, 3);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pempty_bar(pb));
@@ -2413,6 +2445,7 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TQL_TRACE(10);
     if (warp == kMmaWarp)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemColsPeg)
                      : "memory");
@@ -2946,6 +2979,8 @@ int tq_linear_peg_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_gr
     if (int e = peg_common_checks(a_i8, w_i8, w_grp_rowsum, M, N, K, a_q, a_groups, w_q, w_params, out_q, out_params, seg_width)) return e;
     if (!aligned32(y_i8 != nullptr ? y_i8 : y_ctr_bf16)) return TQ_EALIGN;
     lean::peg::Args pa = {};
+    if (const char* e = getenv("TQ_LINEAR_TRACE_PTR")) pa.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+    if (const char* e = getenv("TQ_LINEAR_TRACE_TILES")) pa.trace_tiles = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
     pa.bias = bias; pa.w_grp_rowsum = w_grp_rowsum; pa.a_q = a_q; pa.a_groups = a_groups;
     pa.w_q = w_q; pa.out_q = out_q; pa.w_params = w_params; pa.out_params = out_params; pa.seg_width = seg_width;
     pa.y_u8 = y_i8; pa.y_ctr = reinterpret_cast<__nv_bfloat16*>(y_ctr_bf16);
@@ -2971,6 +3006,8 @@ int tq_linear_peg_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_
     if ((res_params != 1 && res_params != nseg) || (out2_params != 1 && out2_params != nseg) || (ln_params != 1 && ln_params != nseg)) return TQ_EINVAL;
     if (!aligned32(z_i8) || !aligned32(res_i8) || (z_ctr_bf16 != nullptr && !aligned32(z_ctr_bf16))) return TQ_EALIGN;
     lean::peg::Args pa = {};
+    if (const char* e = getenv("TQ_LINEAR_TRACE_PTR")) pa.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+    if (const char* e = getenv("TQ_LINEAR_TRACE_TILES")) pa.trace_tiles = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
     pa.bias = bias; pa.w_grp_rowsum = w_grp_rowsum; pa.a_q = a_q; pa.a_groups = a_groups;
     pa.w_q = w_q; pa.out_q = out_q; pa.w_params = w_params; pa.out_params = out_params; pa.seg_width = seg_width;
     pa.y_u8 = z_i8; pa.y_ctr = reinterpret_cast<__nv_bfloat16*>(z_ctr_bf16);

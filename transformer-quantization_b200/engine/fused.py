@@ -50,11 +50,23 @@ def _unsigned_grid(q):
 
 
 class _Site:
-    """per-tensor quantizer -> tq_qspec (keeps the buffers alive)"""
+    """per-tensor quantizer -> tq_qspec.  The spec holds RAW device pointers into the quantizer's buffers: the tensors
+    are kept here (so the memory cannot be freed under the engine) and ``check()`` detects a quantizer whose buffers
+    were re-allocated since (reset_ranges + recalibration, model.to(), make_range_trainable, a shape-changing
+    set_quant_range) -- the engine must be rebuilt then."""
 
     def __init__(self, quantizer):
         self.q = quantizer
         self.spec = quantizer._spec()
+        self.keep = (quantizer._delta, getattr(quantizer, '_zero_float', None), getattr(quantizer, '_signed', None))
+
+    def check(self):
+        q = self.q
+        now = (q._delta, getattr(q, '_zero_float', None), getattr(q, '_signed', None))
+        for a, b in zip(self.keep, now):
+            if (a is None) != (b is None) or (a is not None and a.data_ptr() != b.data_ptr()):
+                raise RuntimeError('fused engine: a quantizer\'s range buffers were re-allocated after the engine was built '
+                                   '(recalibration / .to() / trainable ranges) -- build a new engine from the model')
 
 
 class _ColSite:
@@ -248,6 +260,7 @@ class FusedBertEngine:
 
         B, T, D, H = self.B, self.T, self.D, self.H
         assert tuple(input_ids.shape) == (B, T)
+        self.validate()
         # the pre-LayerNorm sums (sites u / y) only exist in the unfused chain: tracing keeps it
         fuse_ln = self.fuse_ln and trace is None
         self._last_i8 = self.i8 and fuse_ln
@@ -362,6 +375,17 @@ class FusedBertEngine:
         return logits
 
     __call__ = forward
+
+    def validate(self):
+        """the raw pointers baked into the specs still point at the model's live quantizer buffers?"""
+        for st in self._all_sites():
+            st.check()
+
+    def _all_sites(self):
+        yield from (self.e_tok, self.e_pos, self.e_out, self.pool_out, self.cls_out)
+        for d in self.layers:
+            for k in ('q', 'k', 'v', 's', 'p', 'c', 'g', 'u', 'x', 'f', 'h', 'y', 'z'):
+                yield d[k]
 
     def i8_flop_share(self):
         """share of the GEMM flops of one forward that runs on kind::i8 (bench.py: flop-weighted tensor peak)"""
