@@ -468,6 +468,52 @@ def test_linear_residual_layernorm_lean_matches_general_kernel(M, N, K, monkeypa
         assert torch.equal(zc2, zc_l)
 
 
+def _wide_model(device, hidden, heads, inter, layers, seed=0):
+    from engine.bert import BertConfig, QuantBertForSequenceClassification
+    from quantization.quantizers import QMethods
+    cfg = BertConfig(vocab_size=2000, hidden_size=hidden, num_hidden_layers=layers, num_attention_heads=heads,
+                     intermediate_size=inter, max_position_embeddings=128)
+    m = QuantBertForSequenceClassification(cfg, method=QMethods.symmetric_uniform,
+                                           act_method=QMethods.asymmetric_uniform, n_bits=8, n_bits_act=8)
+    m.init_weights(seed=seed, std=0.05)
+    g = torch.Generator().manual_seed(1)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Linear):
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.05
+        elif isinstance(mod, torch.nn.LayerNorm):
+            mod.weight.data = 1 + torch.randn(mod.weight.shape, generator=g) * 0.1
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.05
+    return m.to(device).eval()
+
+
+@pytest.mark.parametrize('hidden,heads,inter,layers,B', [(768, 12, 3072, 3, 3), (768, 12, 3072, 2, 5)])
+def test_engine_chain_kernel_matches_separate_kernels(hidden, heads, inter, layers, B, monkeypatch):
+    """tq_linear_chain_i8 (attention-output + LN -> FFN-in -> FFN-out + LN -> next Q | K | V in one launch, a cluster per
+    128-row panel) vs the same stages as separate lean kernels: identical arithmetic, so every buffer is bit-identical"""
+    from engine.fused import FusedBertEngine
+    model = _wide_model(DEV, hidden, heads, inter, layers)
+    g = torch.Generator().manual_seed(11)
+    ids = [torch.randint(0, 2000, (B, 128), generator=g).to(DEV) for _ in range(2)]
+    mask = torch.ones(B, 128, dtype=torch.int64, device=DEV)
+    mask[B - 1, 100:] = 0
+    model.set_quant_state(True, True)
+    with torch.no_grad():
+        model(ids[0], mask)
+        model.fix_ranges()
+    out = {}
+    for chain in ('0', '1'):
+        monkeypatch.setenv('TQ_ENGINE_CHAIN', chain)
+        eng = FusedBertEngine(model, B, 128)
+        assert eng.lean and eng.chain == (chain == '1')
+        n0 = eng.ops.launches
+        logits = eng(ids[1], mask)
+        torch.cuda.synchronize()
+        out[chain] = (logits.clone(), eng.x8.clone(), eng.a8.clone(), eng.f8.clone(), eng.qkv.clone(), eng.ops.launches - n0)
+    for k in range(5):
+        assert torch.equal(out['0'][k], out['1'][k]), k
+    assert out['1'][5] == out['0'][5] - 3 * layers + 1            # four launches per layer become one (the last: three)
+
+
 def test_engine_detects_reallocated_quantizer_buffers():
     """the engine's specs hold raw device pointers; a recalibration that re-allocates a quantizer's
     buffers must be detected instead of reading freed memory"""

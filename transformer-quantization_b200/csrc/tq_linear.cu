@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstring>
 
 namespace tq {
 namespace gemm {
@@ -2453,6 +2454,336 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
 }  // namespace peg
 
+// =====================================================================================================
+// CHAIN kernel: a sequence of int8 GEMM stages of one encoder layer in ONE launch.
+// A sequence of 128 tokens never interacts with another sequence outside attention, so a 128-row panel can be
+// carried through  attention-out + LN -> FFN-in + GELU -> FFN-out + LN -> next layer's Q | K | V  by one cluster of
+// N_hidden / 192 CTAs with cluster-level synchronisation only: every stage's A operand is the panel its own cluster
+// wrote in the stage before (global memory, L2 resident).  What this removes per stage is the dependent-launch cost
+// of the one-kernel-per-GEMM form (pipeline fill after a grid-wide dependency, tail of the slowest CTA, TMEM
+// allocation, barrier set-up: ~4.5 us per launch, ~20 % of the BERT-base step).
+// Roles, pipelines and epilogues are those of the lean kernels (same functions -> bit-identical results).
+//   stage kinds   0  plain, per-segment quantizers, bf16 centred output, tiles of 192      (Q | K | V)
+//                 1  plain + GELU, byte output, tiles of 256                               (FFN-in)
+//                 2  residual + LayerNorm, byte output, one 192-column tile per CTA        (attention-out, FFN-out)
+// Between stages: every epilogue thread fences its global stores (gpu scope + async proxy), then one cluster
+// barrier; the producer issues the next stage's TMA loads after it.
+// =====================================================================================================
+namespace chain {
+
+constexpr int kMaxStages = 4;
+constexpr int BNL = 192;                 // LayerNorm / segment stages
+constexpr int BNF = 256;                 // GELU stage
+constexpr int kStageBytes = BM * 128 + BNF * 128;
+constexpr int kRing = 4;
+constexpr int kColBytes = 2 * (BNF / 2) * 16;
+constexpr int kGbBytes = (BNL / 2) * 16;
+constexpr int kXchgBytes = 2 * BM * 8 + 8 * BM * 8;
+constexpr int kSegBytes = kMaxStages * kMaxSeg * kSegFloats * 4;
+constexpr int kParamBytes = kColBytes + kGbBytes + kXchgBytes + kSegBytes;
+constexpr int kSmemBytes = kRing * kStageBytes + kParamBytes + (2 * kRing + 8) * 8 + 16 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "chain kernel shared memory budget");
+
+struct alignas(64) StageDesc {
+    CUtensorMap map_a, map_w;
+    Args ep;
+    int64_t N, K;
+    int32_t kind, tiles;                 // tiles of this stage per CTA
+};
+struct alignas(64) Params {
+    StageDesc st[kMaxStages];
+    int64_t M;
+    int32_t n;
+    long long* trace;                    // tools: [CTA][stage][4] clock64 stamps (stage top, first accumulator, epilogue end, past barrier)
+};
+
+__device__ __forceinline__ int bn_of(int kind) { return kind == 1 ? BNF : BNL; }
+
+__global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_constant__ Params P) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+    unsigned char* par_ptr = base_ptr + kRing * kStageBytes;
+    float4* Pcol = reinterpret_cast<float4*>(par_ptr);                                  // [2][BNF / 2]
+    float4* Pgb = reinterpret_cast<float4*>(par_ptr + kColBytes);                       // [BNL / 2]
+    int2* part = reinterpret_cast<int2*>(par_ptr + kColBytes + kGbBytes);               // [2][BM]
+    int2* xs = part + 2 * BM;                                                           // [8][BM]
+    float* segp = reinterpret_cast<float*>(par_ptr + kColBytes + kGbBytes + kXchgBytes); // [stage][kMaxSeg][kSegFloats]
+    const uint32_t bar0 = base + kRing * kStageBytes + kParamBytes;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kRing + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 2 + s); };
+    auto pfull_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 4 + s); };
+    auto pempty_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 6 + s); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * kRing + 8);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+        base_ptr + kRing * kStageBytes + kParamBytes + 8 * (2 * kRing + 8));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    const int64_t m0 = (int64_t)(blockIdx.x / csize) * BM;        // this cluster's row panel
+    const int nst = P.n;
+
+    if (warp == kProdWarp && lane == 0) {
+        for (int s = 0; s < nst; ++s) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&P.st[s].map_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&P.st[s].map_w) : "memory");
+        }
+        for (int s = 0; s < kRing; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        if (lane == 0) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(tfull_bar(s), 1);
+                mbar_init(tempty_bar(s), kEpiWarps);
+                mbar_init(pfull_bar(s), 1);
+                mbar_init(pempty_bar(s), kEpiWarps);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();                                       // the first stage's A / residual come from the previous kernel
+    if (warp == kProdWarp) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int s = 0; s < nst; ++s) {
+            const StageDesc& S = P.st[s];
+            if (lane == 0) {
+                const int bn = bn_of(S.kind);
+                const int num_kb = (int)(S.K / 128);
+                const uint32_t bytes = (uint32_t)(BM * 128 + bn * 128);
+                for (int j = 0; j < S.tiles; ++j) {
+                    const int32_t n0 = (int32_t)((crank * S.tiles + j) * bn);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), bytes);
+                        const uint32_t sa = base + stage * kStageBytes;
+                        tma_load_2d<1>(sa, &S.map_a, kb * 128, (int32_t)m0, full_bar(stage));
+                        tma_load_2d<1>(sa + BM * 128, &S.map_w, kb * 128, n0, full_bar(stage));
+                        if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+            __syncwarp();
+            if (S.kind == 2) cluster_sync_all();              // the stage's LayerNorm statistics exchange
+            if (s + 1 < nst) {
+                cluster_sync_all();                           // stage boundary: the panel of stage s is complete
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int s = 0; s < nst; ++s) {
+            const StageDesc& S = P.st[s];
+            if (lane == 0) {
+                const int bn = bn_of(S.kind);
+                const int num_kb = (int)(S.K / 128);
+                const uint32_t a_s8 = (S.ep.a_q.zero_float == nullptr && S.ep.a_q.is_signed != nullptr && *S.ep.a_q.is_signed) ? 1u : 0u;
+                const uint32_t w_s8 = (S.ep.w_q.zero_float == nullptr && S.ep.w_q.is_signed != nullptr && *S.ep.w_q.is_signed) ? 1u : 0u;
+                const uint32_t idesc = (2u << 4) | (a_s8 << 7) | (w_s8 << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                for (int j = 0; j < S.tiles; ++j) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BNF);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * kStageBytes;
+                        const uint64_t adesc = make_desc_sw128(sa), bdesc = make_desc_sw128(sa + BM * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        tc_commit<1>(empty_bar(stage));
+                        if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit<1>(tfull_bar(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+            }
+            __syncwarp();
+            if (S.kind == 2) cluster_sync_all();
+            if (s + 1 < nst) cluster_sync_all();
+        }
+    } else if (warp == kParWarp) {
+        // ===================== parameter warp =====================
+        int pb = 0;
+        uint32_t pphase = 0;
+        bool pending = false;                         // arrived at a stage-end cluster barrier, not yet waited
+        for (int s = 0; s < nst; ++s) {
+            const StageDesc& S = P.st[s];
+            const Args& ep = S.ep;
+            const bool lnf = S.kind == 2;
+            const int bn = bn_of(S.kind);
+            QP mine = make_qp(1.0f, 0.0f, 0.0f, 0.0f);
+            {
+                float lo = 0.0f, hi = 0.0f;
+                const tq_qspec* qs = nullptr;
+                int slot = 0;
+                if (lane == 0) qs = &ep.a_q;
+                else if (lnf && lane == 1) qs = &ep.res_q;
+                else if (lnf && lane == 2) qs = &ep.out2_q;
+                else if (lnf && lane == 3) qs = &ep.ln_q;
+                else if (lane >= 4 && lane < 4 + ep.nseg) { qs = &ep.w_q; slot = lane - 4; }
+                else if (lane >= 8 && lane < 8 + ep.nseg) { qs = &ep.out_q; slot = lane - 8; }
+                if (qs != nullptr) {
+                    grid_of(*qs, lo, hi);
+                    mine = resolve(*qs, slot, lo, hi);
+                }
+            }
+            const float a_scale = __shfl_sync(0xffffffffu, mine.scale, 0);
+            const int a_zp = (int)__shfl_sync(0xffffffffu, mine.zp, 0);
+            {
+                const int j = lane < ep.nseg ? lane : 0;
+                const float w_scale = __shfl_sync(0xffffffffu, mine.scale, 4 + j);
+                const float o_scale = __shfl_sync(0xffffffffu, mine.scale, 8 + j), o_rcp = __shfl_sync(0xffffffffu, mine.rcp, 8 + j);
+                const float o_zp = __shfl_sync(0xffffffffu, mine.zp, 8 + j), o_lo = __shfl_sync(0xffffffffu, mine.lo, 8 + j);
+                const float o_hi = __shfl_sync(0xffffffffu, mine.hi, 8 + j);
+                int exact = __shfl_sync(0xffffffffu, mine.exact, 8 + j);
+                const float r_scale = __shfl_sync(0xffffffffu, mine.scale, 1), r_zp = __shfl_sync(0xffffffffu, mine.zp, 1);
+                const float s2 = __shfl_sync(0xffffffffu, mine.scale, 2), r2 = __shfl_sync(0xffffffffu, mine.rcp, 2);
+                const float z2 = __shfl_sync(0xffffffffu, mine.zp, 2), l2 = __shfl_sync(0xffffffffu, mine.lo, 2);
+                const float h2 = __shfl_sync(0xffffffffu, mine.hi, 2);
+                const int e2 = __shfl_sync(0xffffffffu, mine.exact, 2);
+                const float s3 = __shfl_sync(0xffffffffu, mine.scale, 3), r3 = __shfl_sync(0xffffffffu, mine.rcp, 3);
+                const float z3 = __shfl_sync(0xffffffffu, mine.zp, 3), l3 = __shfl_sync(0xffffffffu, mine.lo, 3);
+                const float h3 = __shfl_sync(0xffffffffu, mine.hi, 3);
+                const int e3 = __shfl_sync(0xffffffffu, mine.exact, 3);
+                if (lane < ep.nseg && lane < kMaxSeg) {
+                    float* sg = segp + (s * kMaxSeg + lane) * kSegFloats;
+                    sg[0] = __fmul_rn(a_scale, w_scale);
+                    sg[1] = o_scale; sg[2] = o_rcp; sg[3] = o_lo - o_zp; sg[4] = o_hi - o_zp;
+                    sg[5] = __fadd_rn(o_zp, 12582912.0f);
+                    if (lnf) {
+                        exact |= e2 | e3;
+                        sg[7] = s2; sg[8] = r2; sg[9] = l2 - z2; sg[10] = h2 - z2;
+                        sg[11] = r_scale; sg[12] = __fadd_rn(8388608.0f, r_zp);
+                        sg[13] = s3; sg[14] = r3; sg[15] = l3 - z3; sg[16] = h3 - z3;
+                        sg[17] = __fadd_rn(z3, 12582912.0f);
+                    }
+                    sg[6] = __int_as_float(exact);
+                }
+            }
+            if (pending) {
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                pending = false;
+            }
+            for (int j = 0; j < S.tiles; ++j) {
+                const int64_t n0 = (int64_t)(crank * S.tiles + j) * bn;
+                mbar_wait(pempty_bar(pb), pphase ^ 1u);
+                float4* Pt = Pcol + pb * (BNF / 2);
+                for (int jp = lane; jp < bn / 2; jp += 32) {
+                    const int64_t n = n0 + 2 * jp;
+                    const float b0 = ep.bias != nullptr ? __ldg(ep.bias + n) : 0.0f, b1 = ep.bias != nullptr ? __ldg(ep.bias + n + 1) : 0.0f;
+                    const int r0 = __ldg(ep.w_rowsum + n), r1 = __ldg(ep.w_rowsum + n + 1);
+                    float4 gb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (lnf) gb = make_float4(__ldg(ep.ln_gamma + n), __ldg(ep.ln_gamma + n + 1), __ldg(ep.ln_beta + n), __ldg(ep.ln_beta + n + 1));
+                    Pt[jp] = make_float4(b0, b1, __int_as_float(a_zp * r0), __int_as_float(a_zp * r1));
+                    if (lnf) Pgb[jp] = gb;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pfull_bar(pb));
+                if (++pb == 2) { pb = 0; pphase ^= 1u; }
+            }
+            __syncwarp();
+            if (lnf) cluster_sync_all();
+            if (s + 1 < nst) {
+                // arrive now, wait at the top of the next stage's tile loop: the next stage's quantizers are resolved
+                // while the epilogue warps finish this stage
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                pending = true;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 0..7) =====================
+        const int quarter = warp & 3, half = warp >> 2;
+        int acc = 0, pb = 0;
+        uint32_t acc_phase = 0, pphase = 0;
+        const int64_t row = m0 + quarter * 32 + lane;
+        const bool row_ok = row < P.M;
+        long long* tr = (P.trace != nullptr && threadIdx.x == 0) ? P.trace + (int64_t)blockIdx.x * kMaxStages * 4 : nullptr;
+        for (int s = 0; s < nst; ++s) {
+            const StageDesc& S = P.st[s];
+            const Args& ep = S.ep;
+            const int bn = bn_of(S.kind);
+            const int64_t N = S.N;
+            if (tr != nullptr) tr[s * 4 + 0] = clock64();
+            for (int j = 0; j < S.tiles; ++j) {
+                const int64_t n0 = (int64_t)(crank * S.tiles + j) * bn;
+                uint32_t r0[8], r1[8];
+                if (S.kind == 2) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r0[i] = r1[i] = 0u;
+                    if (row_ok) {
+                        const unsigned char* rrow = ep.res_u8 + row * N + n0 + half * 32;
+                        ldg256(rrow, r0);
+                        ldg256(rrow + 64, r1);
+                    }
+                }
+                mbar_wait(pfull_bar(pb), pphase);
+                const float* sg = segp + (s * kMaxSeg + (int)(n0 / ep.seg_width)) * kSegFloats;
+                const int exact = __float_as_int(sg[6]);
+                const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNF);
+                const float4* Pt = Pcol + pb * (BNF / 2);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                if (tr != nullptr && j == 0) tr[s * 4 + 1] = clock64();
+                if (S.kind == 2) {
+                    if (exact) epi_res_ln<BNL, false>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+                    else epi_res_ln<BNL, true>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+                } else if (S.kind == 1) {
+                    if (exact) epi_plain<BNF, 1, false, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                    else epi_plain<BNF, 1, true, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                } else {
+                    if (exact) epi_plain<BNL, 0, false, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                    else epi_plain<BNL, 0, true, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(tempty_bar(acc));
+                    mbar_arrive(pempty_bar(pb));
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++pb == 2) { pb = 0; pphase ^= 1u; }
+            }
+            if (tr != nullptr) tr[s * 4 + 2] = clock64();
+            if (s + 1 < nst) {
+                // the next stage reads this stage's panel through TMA (async proxy): make the stores visible first
+                __threadfence();
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                cluster_sync_all();
+            }
+            if (tr != nullptr) tr[s * 4 + 3] = clock64();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                     : "memory");
+}
+
+}  // namespace chain
+
 }  // namespace lean
 
 // hi | mid | lo bf16 split: x = hi + mid + lo up to 2^-24 relative (three 8-bit mantissa pieces)
@@ -2643,6 +2974,74 @@ static int launch_peg(const void* a, const void* w, int64_t M, int64_t N, int64_
                       map_a, map_w, M, N, K, (int)C::kStages, ep);
 }
 
+
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
+static int launch_chain(const tq_chain_stage* stages, int32_t n, int64_t M, cudaStream_t st) {
+    using namespace lean::chain;
+    if (stages == nullptr || n < 1 || n > kMaxStages || M < 1) return TQ_EINVAL;
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.M = M;
+    P.n = n;
+    int64_t csize = 0;
+    for (int i = 0; i < n; ++i)
+        if (stages[i].kind == 2) {
+            const int64_t c = stages[i].N / BNL;
+            if (stages[i].N % BNL != 0 || c < 1 || c > 8 || (csize != 0 && c != csize)) return TQ_EUNSUPPORTED;
+            csize = c;
+        }
+    if (csize == 0) return TQ_EUNSUPPORTED;            // (a chain without a LayerNorm stage: use the single kernels)
+    for (int i = 0; i < n; ++i) {
+        const tq_chain_stage& g = stages[i];
+        StageDesc& S = P.st[i];
+        if (g.kind < 0 || g.kind > 2 || g.a_i8 == nullptr || g.w_i8 == nullptr || g.w_rowsum == nullptr || g.out == nullptr) return TQ_EINVAL;
+        if (g.N < 1 || g.K < 1 || g.K % 128 != 0 || g.nseg < 1 || g.nseg > lean::kMaxSeg || g.N % g.nseg != 0) return TQ_EUNSUPPORTED;
+        const int bn = g.kind == 1 ? BNF : BNL;
+        if (g.N % bn != 0 || (g.N / bn) % csize != 0 || (g.N / g.nseg) % bn != 0) return TQ_EUNSUPPORTED;
+        if (g.kind == 2 && (g.N / bn != csize || g.res_i8 == nullptr || g.ln_gamma_q == nullptr || g.ln_beta == nullptr || g.nseg != 1)) return TQ_EINVAL;
+        const tq_qspec* need[3] = {&g.a_q, &g.w_q, &g.out_q};
+        for (int k = 0; k < 3; ++k) {
+            if (int e = tq::check_qspec(*need[k])) return e;
+            if (need[k]->n_bits > 8) return TQ_EUNSUPPORTED;
+        }
+        if (g.kind == 2) {
+            const tq_qspec* more[3] = {&g.res_q, &g.out2_q, &g.ln_q};
+            for (int k = 0; k < 3; ++k) {
+                if (int e = tq::check_qspec(*more[k])) return e;
+                if (more[k]->n_bits > 8) return TQ_EUNSUPPORTED;
+            }
+        }
+        if (!tq::aligned16(g.a_i8) || !tq::aligned16(g.w_i8) || !aligned32(g.out) || (g.res_i8 != nullptr && !aligned32(g.res_i8)) || (g.N & 31) != 0) return TQ_EALIGN;
+        if (int e = make_map(&S.map_a, g.a_i8, M, g.K, BM, true)) return e;
+        if (int e = make_map(&S.map_w, g.w_i8, g.N, g.K, bn, true)) return e;
+        S.N = g.N;
+        S.K = g.K;
+        S.kind = g.kind;
+        S.tiles = (int32_t)((g.N / bn) / csize);
+        lean::Args& a = S.ep;
+        a.bias = g.bias; a.w_rowsum = g.w_rowsum; a.a_q = g.a_q; a.w_q = g.w_q; a.out_q = g.out_q;
+        a.seg_width = g.N / g.nseg; a.nseg = g.nseg; a.ldc = g.N;
+        a.y_u8 = g.kind == 0 ? nullptr : g.out;
+        a.y_ctr = g.kind == 0 ? reinterpret_cast<__nv_bfloat16*>(g.out) : nullptr;
+        a.res_u8 = reinterpret_cast<const unsigned char*>(g.res_i8);
+        a.res_q = g.res_q; a.out2_q = g.out2_q; a.ln_q = g.ln_q;
+        a.ln_gamma = g.ln_gamma_q; a.ln_beta = g.ln_beta; a.ln_eps = g.ln_eps;
+        a.trace = nullptr; a.trace_tiles = nullptr;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int64_t panels = (M + BM - 1) / BM;
+    if (const char* env = getenv("TQ_LINEAR_TRACE_CHAIN")) {       // tools/trace_chain.py: device pointer of a zeroed int64 buffer
+        P.trace = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
+    }
+    return launch_pdl(linear_chain_kernel, dim3((unsigned)(panels * csize)), dim3(lean::kThreads), kSmemBytes, st, (int)csize, P);
+}
+
 static void lean_trace(lean::Args& ep) {
     ep.trace = nullptr;
     ep.trace_tiles = nullptr;
@@ -2653,7 +3052,6 @@ static bool lean_enabled() {          // TQ_LINEAR_LEAN=0: keep the general kern
     const char* e = getenv("TQ_LINEAR_LEAN");
     return !(e != nullptr && e[0] == '0');
 }
-static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 }  // namespace gemm
 }  // namespace tq
@@ -3016,6 +3414,10 @@ int tq_linear_peg_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_
     pa.res_params = res_params; pa.out2_params = out2_params; pa.ln_params = ln_params;
     pa.ln_gamma = ln_gamma_q; pa.ln_beta = ln_beta; pa.ln_eps = ln_eps;
     return launch_peg<0, true, true>(a_i8, w_i8, M, N, K, pa, (cudaStream_t)stream);
+}
+
+int tq_linear_chain_i8(const tq_chain_stage* stages, int32_t n_stages, int64_t M, void* stream) {
+    return tq::gemm::launch_chain(stages, n_stages, M, (cudaStream_t)stream);
 }
 
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream) {

@@ -230,7 +230,34 @@ class FusedBertEngine:
         self.lean = (self.i8 and os.environ.get('TQ_ENGINE_LEAN', '1') != '0' and D % 128 == 0
                      and cfg.intermediate_size % 128 == 0
                      and all(st.q.n_bits <= 8 for d in self.layers for st in (d['q'], d['k'], d['v'], d['f'])))
+        # chain kernel: the four GEMM stages between two attention kernels in ONE launch (a cluster per 128-row panel)
+        I = cfg.intermediate_size
+        self.chain = (self.lean and os.environ.get('TQ_ENGINE_CHAIN', '1') != '0' and D % 192 == 0 and D // 192 <= 8
+                      and I % 256 == 0 and (I // 256) % (D // 192) == 0)
+        if self.chain:
+            self._build_chains()
         self._last_i8 = False
+
+    def _build_chains(self):
+        cs = self.ops.chain_stage
+        D, x, c, a, f = self.D, self.x8, self.c8, self.a8, self.f8
+        self.chains = []
+        x_site = self.e_out
+        for li, d in enumerate(self.layers):
+            wg, wf, wh = d['wg'], d['wf'], d['wh']
+            g1, b1, e1 = d['ln1']
+            g2, b2, e2 = d['ln2']
+            st = [cs(2, c, wg.grid8, wg.rowsum, wg.bias, a, wg.N, wg.K, d['c'].spec, wg.seg_spec, d['g'].spec, 1, x, x_site.spec,
+                     d['u'].spec, d['x'].spec, g1, b1, e1),
+                  cs(1, a, wf.grid8, wf.rowsum, wf.bias, f, wf.N, wf.K, d['x'].spec, wf.seg_spec, d['f'].spec),
+                  cs(2, f, wh.grid8, wh.rowsum, wh.bias, x, wh.N, wh.K, d['f'].spec, wh.seg_spec, d['h'].spec, 1, a, d['x'].spec,
+                     d['y'].spec, d['z'].spec, g2, b2, e2)]
+            if li + 1 < len(self.layers):
+                n = self.layers[li + 1]
+                w = n['wqkv']
+                st.append(cs(0, x, w.grid8, w.rowsum, w.bias, self.qkv, w.N, w.K, d['z'].spec, w.seg_spec, n['qkv_out'].seg_spec, 3))
+            self.chains.append(st)
+            x_site = d['z']
 
     def _linear(self, a_ctr, a_site, w, act, out_spec, out_params, out_ctr=None, want_f32=False, M=None):
         M = a_ctr.shape[0] if M is None else M
@@ -331,7 +358,17 @@ class FusedBertEngine:
                             self.e_gamma, self.e_beta, self.e_eps, self.e_out.spec, 1, x)
         x_site = self.e_out
         lean = self.lean
-        for d in self.layers:
+        if self.chain:   # QKV(0), then per layer: attention + one chain launch (attn-out + LN, FFN-in, FFN-out + LN, next QKV)
+            d = self.layers[0]
+            w = d['wqkv']
+            ops.linear_seg_i8(x, w.grid8, w.rowsum, w.bias, M, w.N, w.K, x_site.spec, w.seg_spec, d['qkv_out'].seg_spec, 3, 0,
+                              out_ctr=self.qkv)
+            for d, st in zip(self.layers, self.chains):
+                ops.attention_i8(self.qkv, B, T, H, self.hd, d['q'].spec, d['k'].spec, d['v'].spec, d['s'].spec, d['p'].spec,
+                                 d['c'].spec, mask, c)
+                ops.linear_chain_i8(st, M)
+            x_site = self.layers[-1]['z']
+        for d in (() if self.chain else self.layers):
             w = d['wqkv']
             if lean:     # per-segment quantizers (Q | K | V), lean int8 kernel
                 ops.linear_seg_i8(x, w.grid8, w.rowsum, w.bias, M, w.N, w.K, x_site.spec, w.seg_spec, d['qkv_out'].seg_spec,

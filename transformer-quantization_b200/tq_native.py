@@ -34,6 +34,17 @@ class QSpec(ctypes.Structure):
     ]
 
 
+class ChainStage(ctypes.Structure):
+    """struct tq_chain_stage (include/tq_b200.h)."""
+    _fields_ = [
+        ('a_i8', ctypes.c_void_p), ('w_i8', ctypes.c_void_p), ('w_rowsum', ctypes.c_void_p), ('bias', ctypes.c_void_p),
+        ('out', ctypes.c_void_p), ('N', ctypes.c_int64), ('K', ctypes.c_int64),
+        ('a_q', QSpec), ('w_q', QSpec), ('out_q', QSpec), ('nseg', ctypes.c_int32), ('kind', ctypes.c_int32),
+        ('res_i8', ctypes.c_void_p), ('res_q', QSpec), ('out2_q', QSpec), ('ln_q', QSpec),
+        ('ln_gamma_q', ctypes.c_void_p), ('ln_beta', ctypes.c_void_p), ('ln_eps', ctypes.c_float),
+    ]
+
+
 class TQError(RuntimeError):
     pass
 
@@ -98,6 +109,7 @@ SIGNATURES = {
     'tq_linear_seg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
                                             ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, QSpec, _i32, _i32, _i64,
                                             ctypes.c_void_p]),
+    'tq_linear_chain_i8': (ctypes.c_int, [ctypes.POINTER(ChainStage), _i32, _i64, ctypes.c_void_p]),
     'tq_linear_nonorm_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
                                                _i64, _i64, _i64, QSpec, QSpec, QSpec, ctypes.c_void_p, QSpec, QSpec, _c_f32p,
                                                _c_f32p, QSpec, _i64, ctypes.c_void_p]),
@@ -489,6 +501,26 @@ class CudaOps:
                   w_rowsum.data_ptr(), _ptr(bias), _ptr(out_ctr), _ptr(out_i8), M, N, K, a_spec, w_seg_spec, out_seg_spec,
                   int(nseg), int(act_fn), int(ldc), _stream())
         return out_i8 if out_i8 is not None else out_ctr
+
+    @staticmethod
+    def chain_stage(kind, a_i8, w_i8, w_rowsum, bias, out, N, K, a_spec, w_spec, out_spec, nseg=1, res_i8=None, res_spec=None,
+                    out2_spec=None, ln_spec=None, ln_gamma_q=None, ln_beta=None, ln_eps=0.0):
+        """one struct tq_chain_stage; kind 0 plain segments (out bf16 centred grid), 1 GELU (bytes), 2 residual + LayerNorm"""
+        _chk_cuda(a_i8, w_i8, w_rowsum, bias, out, res_i8, ln_gamma_q, ln_beta)
+        st = ChainStage()
+        st.a_i8, st.w_i8, st.w_rowsum, st.bias, st.out = a_i8.data_ptr(), w_i8.data_ptr(), w_rowsum.data_ptr(), _ptr(bias), out.data_ptr()
+        st.N, st.K, st.nseg, st.kind = int(N), int(K), int(nseg), int(kind)
+        st.a_q, st.w_q, st.out_q = a_spec, w_spec, out_spec
+        if kind == 2:
+            st.res_i8, st.res_q, st.out2_q, st.ln_q = res_i8.data_ptr(), res_spec, out2_spec, ln_spec
+            st.ln_gamma_q, st.ln_beta, st.ln_eps = ln_gamma_q.data_ptr(), ln_beta.data_ptr(), float(ln_eps)
+        return st
+
+    def linear_chain_i8(self, stages, M):
+        """tq_linear_chain_i8: consecutive GEMM stages of an encoder layer in one launch (clusters own 128-row panels)"""
+        arr = (ChainStage * len(stages))(*stages)
+        flops = sum(2 * M * s.N * s.K for s in stages)
+        self._run('linear_qdq', flops, 1, self.lib.tq_linear_chain_i8, arr, len(stages), int(M), _stream())
 
     def linear_nonorm_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_spec, out_spec, res_i8, res_spec, out2_spec,
                          nn_weight_q, nn_bias_q, nn_spec, out_i8, ldc=0):
