@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_engine.py tests/test_gpu_fullsize_parity.py -q --tb=short -p no:cacheprovider -x > gpurun_out/c24_engine.log 2>&1; echo "exit $?" >> gpurun_out/c24_engine.log
+tail -8 gpurun_out/c24_engine.log | cut -c1-250
+timeout 120 python tools/trace_chain.py > gpurun_out/c24_trace_chain.txt 2>&1; echo "exit $?" >> gpurun_out/c24_trace_chain.txt
+cat gpurun_out/c24_trace_chain.txt | cut -c1-300
+TQ_BENCH_OTHER_CONFIGS=0 TQ_BENCH_CALIBRATION=0 timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/c24_bench.json 2> gpurun_out/c24_bench.err
+python -c "
+import json;p=json.load(open('gpurun_out/c24_bench.json'));print({k:p.get(k) for k in ('value','ms_per_step','kernels','e2e')})"
+tail -2 gpurun_out/c24_bench.err

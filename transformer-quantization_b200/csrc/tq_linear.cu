@@ -2499,6 +2499,12 @@ struct alignas(64) Params {
 
 __device__ __forceinline__ int bn_of(int kind) { return kind == 1 ? BNF : BNL; }
 
+// Measured and dropped (profiles/r2_trace_chain_mcast.txt, r2_trace_chain_12warps.txt): (a) TMA-multicasting the A
+// k-blocks across the cluster (each member loads 128 / cluster rows) leaves every main loop unchanged -- the bound is the
+// bytes LANDING in an SM's shared memory per clock (~60 B/clk: 16 KB + 24 KB per k-block in ~670 cycles), which multicast
+// does not reduce; (b) twelve epilogue warps (three per scheduler, setmaxnreg 152 / 48) leave every epilogue unchanged --
+// the epilogues are bound by the FMA + ALU pipe time of their instruction mix (packed FP32 2.1-2.3 cycles, FMNMX / PRMT
+// 2 cycles, MUFU 8 cycles per warp instruction), not by latency.
 __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_constant__ Params P) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -2558,11 +2564,31 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_trigger();
+    // The WEIGHT halves of a stage's first ring slots do not depend on the stage before: they are requested while the
+    // previous stage (or the previous kernel) is still in its epilogue; only the A halves wait for the boundary.
+    int p_stage = 0, p_pre = 0;
+    uint32_t p_phase = 0;
+    auto preissue_w = [&](int s) {                    // producer lane 0: W of the first k-blocks of stage s
+        const StageDesc& S = P.st[s];
+        const int bn = bn_of(S.kind);
+        const int num_kb = (int)(S.K / 128);
+        const uint32_t bytes = (uint32_t)(BM * 128 + bn * 128);
+        const int32_t n0 = (int32_t)((crank * S.tiles) * bn);
+        int st = p_stage;
+        uint32_t ph = p_phase;
+        p_pre = num_kb < kRing ? num_kb : kRing;
+        for (int kb = 0; kb < p_pre; ++kb) {
+            mbar_wait(empty_bar(st), ph ^ 1u);
+            mbar_expect_tx(full_bar(st), bytes);
+            tma_load_2d<1>(base + st * kStageBytes + BM * 128, &S.map_w, kb * 128, n0, full_bar(st));
+            if (++st == kRing) { st = 0; ph ^= 1u; }
+        }
+    };
+    if (warp == kProdWarp && lane == 0) preissue_w(0);
     pdl_wait();                                       // the first stage's A / residual come from the previous kernel
+
     if (warp == kProdWarp) {
         // ===================== TMA producer =====================
-        int stage = 0;
-        uint32_t phase = 0;
         for (int s = 0; s < nst; ++s) {
             const StageDesc& S = P.st[s];
             if (lane == 0) {
@@ -2572,14 +2598,17 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
                 for (int j = 0; j < S.tiles; ++j) {
                     const int32_t n0 = (int32_t)((crank * S.tiles + j) * bn);
                     for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), bytes);
-                        const uint32_t sa = base + stage * kStageBytes;
-                        tma_load_2d<1>(sa, &S.map_a, kb * 128, (int32_t)m0, full_bar(stage));
-                        tma_load_2d<1>(sa + BM * 128, &S.map_w, kb * 128, n0, full_bar(stage));
-                        if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                        const uint32_t sa = base + p_stage * kStageBytes;
+                        if (j > 0 || kb >= p_pre) {
+                            mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
+                            mbar_expect_tx(full_bar(p_stage), bytes);
+                            tma_load_2d<1>(sa + BM * 128, &S.map_w, kb * 128, n0, full_bar(p_stage));
+                        }
+                        tma_load_2d<1>(sa, &S.map_a, kb * 128, (int32_t)m0, full_bar(p_stage));
+                        if (++p_stage == kRing) { p_stage = 0; p_phase ^= 1u; }
                     }
                 }
+                if (s + 1 < nst) preissue_w(s + 1);
             }
             __syncwarp();
             if (S.kind == 2) cluster_sync_all();              // the stage's LayerNorm statistics exchange
