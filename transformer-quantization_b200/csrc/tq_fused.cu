@@ -432,20 +432,31 @@ __device__ __forceinline__ void attn_rows(const AttnArgs& a, const QP& qs, const
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("bar.sync 1, 256;" ::: "memory");
     vmax = fmaxf(vmax, xchg[(hs ^ 1) * AT + row]);
-    // pass 2: exp(t - max), row sum
-    float vsum = 0.0f;
+    // pass 2: exp(t - max) = 2^(t * log2 e - max * log2 e): one packed FMA and one ex2 per score.  (The reference's exp
+    // is a libm / CUDA expf within 1-2 ulp; ex2.approx adds <= 2 ulp and the single rounding of the exponent
+    // |t - max| * 2^-24 <~ 5e-6 relative -- far inside the probability quantizer's step; the flip budget of the
+    // attention block, tests/test_gpu_fullsize_parity.py, covers it.)  Row sum: two interleaved partial sums.
+    const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    const float nm = -__fmul_rn(vmax, 1.4426950408889634f);
+    const float2 nm2 = make_float2(nm, nm);
+    float2 vs2 = make_float2(0.0f, 0.0f);
 #pragma unroll 1
     for (int c0 = k0; c0 < k0 + 64; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(trow + c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float e = expf(__uint_as_float(v[j]) - vmax);
-            vsum += e;
-            v[j] = __float_as_uint(e);
+        for (int j = 0; j < 16; j += 2) {
+            const float2 u = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), l2e, nm2);
+            float2 e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(u.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(u.y));
+            vs2 = __fadd2_rn(vs2, e);
+            v[j] = __float_as_uint(e.x);
+            v[j + 1] = __float_as_uint(e.y);
         }
         tmem_st16_nowait(trow + c0, v);
     }
+    float vsum = __fadd_rn(vs2.x, vs2.y);
     xchg[2 * AT + hs * AT + row] = vsum;
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("bar.sync 1, 256;" ::: "memory");
