@@ -510,7 +510,7 @@ def run_other_config(args):
     roof = None
     if prof:
         name, st = max(prof.items(), key=lambda kv: kv[1]['seconds'])
-        tensor = name in ('linear_qdq', 'attention')
+        tensor = name in ('linear_qdq', 'attention', 'chain')
         ach = st['work'] / st['seconds'] / (1e12 if tensor else 1e9)
         roof = {'kernel': name, 'bound': 'tensor' if tensor else 'hbm', 'achieved': ach, 'peak': tf_peak if tensor else hbm_peak,
                 'unit': 'TFLOP/s' if tensor else 'GB/s', 'frac': ach / (tf_peak if tensor else hbm_peak), 'traffic': None,
@@ -653,17 +653,22 @@ def run_ours(args):
     top = max(prof.items(), key=lambda kv: kv[1]['seconds'])
     name, st = top
     per_launch_s = st['seconds'] / st['launches']
-    flops_kernels = ('linear_qdq', 'attention')
+    flops_kernels = ('linear_qdq', 'attention', 'chain')
     if name in flops_kernels:
-        roof = {'kernel': 'tq_linear_qdq_i8 / tq_linear_res_ln_qdq_i8 / tq_linear_qdq_bf16_o8 (tcgen05 GEMM + fused QDQ / GELU / residual / '
-                          'LayerNorm epilogue)' if name == 'linear_qdq' else 'tq_attention_qdq_i8', 'bound': 'tensor',
+        kname = {'linear_qdq': 'tq_linear_qdq_i8 / tq_linear_res_ln_qdq_i8 / tq_linear_qdq_bf16_o8 (tcgen05 GEMM + fused QDQ / GELU / residual / '
+                               'LayerNorm epilogue)',
+                 'chain': 'tq_chain_plan_run (linear_chain_kernel: the whole encoder in one launch -- per layer attention, attention-output + '
+                          'LayerNorm, FFN-in + GELU, FFN-out + LayerNorm, next Q|K|V; tcgen05 kind::i8 GEMMs + kind::f16 attention products, '
+                          'fused QDQ epilogues)',
+                 'attention': 'tq_attention_qdq_i8'}[name]
+        roof = {'kernel': kname, 'bound': 'tensor',
                 'achieved': st['work'] / st['seconds'] / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',
                 'peak_kind': 'bf16 dense BURST (cuBLAS 8192^3, best of 10) -- the timed region is tens of ms at full clocks',
                 'frac_of_sustained_bf16_peak': st['work'] / st['seconds'] / 1e12 / tf_sustained}
-        if name == 'linear_qdq' and getattr(forward, 'i8', False):
+        if name in ('linear_qdq', 'chain') and getattr(forward, 'i8', False):
             # 2/3 of the GEMM flops of a layer run as kind::i8 (QKV, attention-out, FFN-out), whose pipe rate is 2x
             # bf16 (tools/mainloop_probe_i8.py: 133 cycles per M128 x N256 x K32 MMA alone = K16 bf16): flop-weighted peak
-            share_i8 = forward.i8_flop_share()
+            share_i8 = forward.i8_flop_share(name)
             roof['i8_flop_share'] = share_i8
             roof['peak_i8_weighted'] = tf_peak / (1.0 - share_i8 / 2.0)
             roof['frac_of_i8_weighted_peak'] = roof['achieved'] / roof['peak_i8_weighted']

@@ -55,7 +55,7 @@ typedef struct tq_qspec {
 /* ---- library info ------------------------------------------------------------------------- */
 int         tq_version(void);              /* ABI version: 1 = inference path; 2 adds the training-time entry points
                                               * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 (current) adds
-                                              * tq_linear_seg_qdq_i8, tq_linear_chain_i8, tq_linear_nonorm_qdq_i8, tq_calib_finalize_f32,
+                                              * tq_linear_seg_qdq_i8, tq_chain_plan_create / _run / _destroy, tq_linear_nonorm_qdq_i8, tq_calib_finalize_f32,
                                               * tq_attention_pad_qdq_i8 and the tq_*_peg_* entry points */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
@@ -294,22 +294,27 @@ int tq_linear_peg_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_
                                 tq_qspec out2_q, int32_t out2_params, const float* ln_gamma_q,
                                 const float* ln_beta, float ln_eps, tq_qspec ln_q, int32_t ln_params,
                                 int64_t seg_width, void* stream);
-/* A SEQUENCE of int8 GEMM stages of one encoder layer in one launch (reference models/quantized_bert.py:238-291 followed
- * by the next layer's :135-151): attention-output + residual + LayerNorm -> FFN-in + GELU -> FFN-out + residual + LayerNorm
- * -> next layer's Q | K | V.  A cluster of N_hidden / 192 CTAs carries one 128-row panel (= one sequence of 128 tokens)
- * through all stages: every stage's A operand is the panel its own cluster wrote in the stage before (a_i8 of stage
- * i + 1 = out of stage i), so only cluster barriers separate the stages.  Same arithmetic as tq_linear_seg_qdq_i8 /
- * tq_linear_res_ln_qdq_i8 (bit-identical outputs).
- *   kind 0  plain, nseg segments, out = bf16 centred grid       kind 1  plain + GELU, out = x_int bytes
- *   kind 2  residual + LayerNorm, out = x_int bytes (N / 192 <= 8 CTAs per cluster; res_i8, res_q, out2_q, ln_*)
- * At least one kind-2 stage (it fixes the cluster size); (N / tile) divisible by the cluster size in every stage;
- * K % 128 == 0; else TQ_EUNSUPPORTED and callers launch the stages one by one. */
+/* The ENCODER CHAIN: a list of stages executed by ONE launch (reference models/quantized_bert.py:135-291, all layers).
+ * A cluster of N_hidden / 192 CTAs carries one 128-row panel (= one sequence of 128 tokens) through every stage: the A
+ * operand of stage i + 1 is what the same cluster wrote in stage i, so only cluster barriers separate the stages -- the
+ * whole encoder (Q | K | V of layer 0, then per layer: attention, attention-output + residual + LayerNorm, FFN-in + GELU,
+ * FFN-out + residual + LayerNorm, the next layer's Q | K | V) is one kernel.  Same arithmetic as the single kernels
+ * (tq_linear_seg_qdq_i8 / tq_linear_res_ln_qdq_i8 / tq_attention_qdq_i8): bit-identical outputs.
+ *   kind 0  int8 GEMM, nseg segments, out = bf16 centred grid       kind 1  int8 GEMM + GELU, out = x_int bytes
+ *   kind 2  int8 GEMM + residual + LayerNorm, out = x_int bytes (N / 192 <= 8 CTAs per cluster; res_i8, res_q, out2_q, ln_*)
+ *   kind 3  attention: a_i8 = the Q | K | V buffer [M, 3 N] bf16 centred grids, N = hidden size, K = heads (N == 64 K,
+ *           K divisible by the cluster size, M % 128 == 0), bias = additive mask [M / 128, 128] or NULL, out = context
+ *           x_int bytes [M, N]; quantizers: a_q / w_q / res_q = Q / K / V projections, out2_q = scores, ln_q =
+ *           probabilities, out_q = context (all per-tensor)
+ * At least one kind-2 stage (it fixes the cluster size); (N / tile) divisible by the cluster size in every GEMM stage;
+ * K % 128 == 0; else TQ_EUNSUPPORTED and callers launch the stages one by one.  A plan holds the stage descriptors
+ * (tensor maps, pointers, quantizer specs) in device memory: create once for fixed buffers, run per forward. */
 typedef struct tq_chain_stage {
-    const void*    a_i8;        /* [M, K] x_int bytes */
+    const void*    a_i8;        /* [M, K] x_int bytes (kind 3: [M, 3 N] bf16) */
     const void*    w_i8;        /* [N, K] */
     const int32_t* w_rowsum;    /* [N] */
-    const float*   bias;        /* [N] or NULL */
-    void*          out;         /* [M, N] bf16 centred grid (kind 0) or x_int bytes (kinds 1, 2) */
+    const float*   bias;        /* [N] or NULL (kind 3: the mask) */
+    void*          out;         /* [M, N] bf16 centred grid (kind 0) or x_int bytes (kinds 1, 2, 3) */
     int64_t        N, K;
     tq_qspec       a_q, w_q, out_q;   /* w_q / out_q: nseg slots */
     int32_t        nseg;
@@ -320,7 +325,9 @@ typedef struct tq_chain_stage {
     const float*   ln_beta;
     float          ln_eps;
 } tq_chain_stage;
-int tq_linear_chain_i8(const tq_chain_stage* stages, int32_t n_stages, int64_t M, void* stream);
+int tq_chain_plan_create(const tq_chain_stage* stages, int32_t n_stages, int64_t M, void** plan);
+int tq_chain_plan_run(const void* plan, void* stream);
+int tq_chain_plan_destroy(void* plan);
 int tq_linear_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_t* w_rowsum, const float* bias,
                             float* z, void* z_ctr_bf16, void* z_i8, int64_t M, int64_t N, int64_t K,
                             tq_qspec a_q, tq_qspec w_q, int64_t w_q_params, tq_qspec out_q,

@@ -486,32 +486,37 @@ def _wide_model(device, hidden, heads, inter, layers, seed=0):
     return m.to(device).eval()
 
 
-@pytest.mark.parametrize('hidden,heads,inter,layers,B', [(768, 12, 3072, 3, 3), (768, 12, 3072, 2, 5)])
-def test_engine_chain_kernel_matches_separate_kernels(hidden, heads, inter, layers, B, monkeypatch):
-    """tq_linear_chain_i8 (attention-output + LN -> FFN-in -> FFN-out + LN -> next Q | K | V in one launch, a cluster per
-    128-row panel) vs the same stages as separate lean kernels: identical arithmetic, so every buffer is bit-identical"""
+@pytest.mark.parametrize('hidden,heads,inter,layers,B,use_mask', [(768, 12, 3072, 3, 3, True), (768, 12, 3072, 2, 5, False)])
+def test_engine_chain_kernel_matches_separate_kernels(hidden, heads, inter, layers, B, use_mask, monkeypatch):
+    """the encoder chain (tq_chain_plan_*: a cluster per 128-row panel carries a sequence through the stages) vs the same
+    stages as separate kernels -- mode 1: the four GEMM stages of a layer in one launch; mode 2: the whole encoder incl.
+    attention in ONE launch.  Identical arithmetic, so every buffer is bit-identical"""
     from engine.fused import FusedBertEngine
     model = _wide_model(DEV, hidden, heads, inter, layers)
     g = torch.Generator().manual_seed(11)
     ids = [torch.randint(0, 2000, (B, 128), generator=g).to(DEV) for _ in range(2)]
     mask = torch.ones(B, 128, dtype=torch.int64, device=DEV)
-    mask[B - 1, 100:] = 0
+    if use_mask:
+        mask[B - 1, 100:] = 0
+        mask[0, 5:9] = 0
     model.set_quant_state(True, True)
     with torch.no_grad():
         model(ids[0], mask)
         model.fix_ranges()
     out = {}
-    for chain in ('0', '1'):
+    for chain in ('0', '1', '2'):
         monkeypatch.setenv('TQ_ENGINE_CHAIN', chain)
         eng = FusedBertEngine(model, B, 128)
-        assert eng.lean and eng.chain == (chain == '1')
+        assert eng.lean and eng.chain == int(chain)
         n0 = eng.ops.launches
-        logits = eng(ids[1], mask)
+        logits = eng(ids[1], mask if use_mask else None)
         torch.cuda.synchronize()
-        out[chain] = (logits.clone(), eng.x8.clone(), eng.a8.clone(), eng.f8.clone(), eng.qkv.clone(), eng.ops.launches - n0)
-    for k in range(5):
-        assert torch.equal(out['0'][k], out['1'][k]), k
-    assert out['1'][5] == out['0'][5] - 3 * layers + 1            # four launches per layer become one (the last: three)
+        out[chain] = (logits.clone(), eng.x8.clone(), eng.a8.clone(), eng.f8.clone(), eng.qkv.clone(), eng.c8.clone(), eng.ops.launches - n0)
+    for chain in ('1', '2'):
+        for k in range(6):
+            assert torch.equal(out['0'][k], out[chain][k]), (chain, k)
+    assert out['1'][6] == out['0'][6] - 3 * layers + 1            # four launches per layer become one (the last: three)
+    assert out['2'][6] == out['0'][6] - 5 * layers + 1            # embedding + ONE encoder launch + pooler + classifier
 
 
 def test_engine_detects_reallocated_quantizer_buffers():

@@ -17,10 +17,12 @@
 // Persistent: grid = min(#tiles, #SMs); tile order keeps the A row-panel hot in L2.  Three
 // pipelines (smem full/empty, TMEM full/empty, tile loop) synchronised with mbarriers only.
 #include "tq_common.cuh"
+#include "tq_attn.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace tq {
 namespace gemm {
@@ -2471,33 +2473,60 @@ linear_peg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // =====================================================================================================
 namespace chain {
 
-constexpr int kMaxStages = 4;
-constexpr int BNL = 192;                 // LayerNorm / segment stages
-constexpr int BNF = 256;                 // GELU stage
-constexpr int kStageBytes = BM * 128 + BNF * 128;
+// One launch carries every 128-row panel (= one sequence of 128 tokens) through a LIST of stages; a cluster of
+// hidden / 192 CTAs owns the panel, so stage i + 1 reads what the same cluster wrote in stage i and only cluster barriers
+// separate the stages.  Stage kinds:
+//   0  int8 GEMM, per-segment quantizers, bf16 centred-grid output (Q | K | V)           tile 128 x 192
+//   1  int8 GEMM + GELU, x_int byte output (FFN-in)                                       tile 128 x 256
+//   2  int8 GEMM + residual + LayerNorm over the cluster, byte output                     tile 128 x 192, one per CTA
+//   3  attention of heads / cluster heads per CTA (bf16 tensor-core products, tq_attn.cuh), byte output
+// The stage descriptors live in global memory (a plan built once per engine): the whole encoder -- Q|K|V of layer 0, then
+// per layer attention, attention-output + LN, FFN-in, FFN-out + LN, next Q|K|V -- is ONE launch.
+struct alignas(16) StageTail {           // everything but the tensor maps: copied to shared memory one stage ahead
+    Args ep;                             // kind 3: a_q / w_q / res_q = Q / K / V, out2_q = scores, ln_q = probs, out_q = context, bias = mask
+    int64_t N, K;                        // kind 3: N = hidden size, K = heads
+    int32_t kind, tiles;                 // tiles (kind 3: heads) of this stage per CTA
+    uint32_t idesc;                      // kinds 0-2: the kind::i8 instruction descriptor (operand signedness resolved by the host)
+    int32_t pad;
+};
+static_assert(sizeof(StageTail) % 16 == 0, "stage tail is copied in 16-byte pieces");
+struct alignas(64) StageDesc {
+    CUtensorMap map_a, map_w;            // kind 3: map_a = the Q | K | V buffer [M, 3 hidden] bf16, box 64 x 128
+    StageTail t;
+};
+constexpr int BNL = 192;
+constexpr int BNF = 256;
+constexpr int kStageBytes = BM * 128 + BNF * 128;        // 48 KB: a GEMM k-block (A 16 KB | W <= 32 KB) or one head's Q | K | V
 constexpr int kRing = 4;
 constexpr int kColBytes = 2 * (BNF / 2) * 16;
-constexpr int kGbBytes = (BNL / 2) * 16;
-constexpr int kXchgBytes = 2 * BM * 8 + 8 * BM * 8;
-constexpr int kSegBytes = kMaxStages * kMaxSeg * kSegFloats * 4;
-constexpr int kParamBytes = kColBytes + kGbBytes + kXchgBytes + kSegBytes;
-constexpr int kSmemBytes = kRing * kStageBytes + kParamBytes + (2 * kRing + 8) * 8 + 16 + 1024;
+constexpr int kGbBytes = (BNL / 2) * 16;                 // LayerNorm gamma | beta pairs; attention: the sequence's additive mask
+constexpr int kXchgBytes = 2 * BM * 8 + 8 * BM * 8;      // LayerNorm partial sums; attention: row max / sum exchange
+constexpr int kSegBytes = 2 * kMaxSeg * kSegFloats * 4;  // two stages in flight; attention: [6][8] resolved quantizers
+constexpr int kTailBytes = 2 * ((int)sizeof(StageTail) + 15) / 16 * 16;
+constexpr int kParamBytes = kColBytes + kGbBytes + kXchgBytes + kSegBytes + kTailBytes;
+constexpr int kNumBars = 2 * kRing + 8 + 4;
+constexpr int kSmemBytes = kRing * kStageBytes + kParamBytes + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "chain kernel shared memory budget");
+static_assert(6 * 8 <= kMaxSeg * kSegFloats, "attention quantizer table fits a segment-parameter slot");
 
-struct alignas(64) StageDesc {
-    CUtensorMap map_a, map_w;
-    Args ep;
-    int64_t N, K;
-    int32_t kind, tiles;                 // tiles of this stage per CTA
-};
-struct alignas(64) Params {
-    StageDesc st[kMaxStages];
+struct Params {
+    const StageDesc* st;                 // [n] in global memory
     int64_t M;
     int32_t n;
     long long* trace;                    // tools: [CTA][stage][4] clock64 stamps (stage top, first accumulator, epilogue end, past barrier)
 };
 
 __device__ __forceinline__ int bn_of(int kind) { return kind == 1 ? BNF : BNL; }
+// MN-major SWIZZLE_128B operand (V of the PV product): 64 MN elements (128 B) contiguous per K row, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ QP load_qp(const float* o) {
+    QP p;
+    p.scale = o[0]; p.zp = o[1]; p.lo = o[2]; p.hi = o[3]; p.rcp = o[4]; p.exact = __float_as_int(o[5]);
+    return p;
+}
 
 // Measured and dropped (profiles/r2_trace_chain_mcast.txt, r2_trace_chain_12warps.txt): (a) TMA-multicasting the A
 // k-blocks across the cluster (each member loads 128 / cluster rows) leaves every main loop unchanged -- the bound is the
@@ -2505,7 +2534,9 @@ __device__ __forceinline__ int bn_of(int kind) { return kind == 1 ? BNF : BNL; }
 // does not reduce; (b) twelve epilogue warps (three per scheduler, setmaxnreg 152 / 48) leave every epilogue unchanged --
 // the epilogues are bound by the FMA + ALU pipe time of their instruction mix (packed FP32 2.1-2.3 cycles, FMNMX / PRMT
 // 2 cycles, MUFU 8 cycles per warp instruction), not by latency.
-__global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_constant__ Params P) {
+// ATT: the plan has attention stages (kind 3); plans of GEMM stages only run the instantiation without that code
+template <bool ATT>
+__global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params P) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
@@ -2513,8 +2544,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
     float4* Pcol = reinterpret_cast<float4*>(par_ptr);                                  // [2][BNF / 2]
     float4* Pgb = reinterpret_cast<float4*>(par_ptr + kColBytes);                       // [BNL / 2]
     int2* part = reinterpret_cast<int2*>(par_ptr + kColBytes + kGbBytes);               // [2][BM]
-    int2* xs = part + 2 * BM;                                                           // [8][BM]
-    float* segp = reinterpret_cast<float*>(par_ptr + kColBytes + kGbBytes + kXchgBytes); // [stage][kMaxSeg][kSegFloats]
+    int2* xs = part + 2 * BM;                                                            // [8][BM]
+    float* segp = reinterpret_cast<float*>(par_ptr + kColBytes + kGbBytes + kXchgBytes); // [2][kMaxSeg][kSegFloats]
+    const StageTail* tails = reinterpret_cast<const StageTail*>(par_ptr + kColBytes + kGbBytes + kXchgBytes + kSegBytes);   // [2]
+    float* smask = reinterpret_cast<float*>(Pgb);                                        // attention stages
+    float* xchg = reinterpret_cast<float*>(xs);
     const uint32_t bar0 = base + kRing * kStageBytes + kParamBytes;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
@@ -2522,20 +2556,19 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 2 + s); };
     auto pfull_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 4 + s); };
     auto pempty_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 6 + s); };
-    const uint32_t tmem_slot = bar0 + 8u * (2 * kRing + 8);
+    auto pready_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 8 + s); };           // attention: P tile written
+    auto oready_bar = [&](int s) { return bar0 + 8u * (2 * kRing + 10 + s); };          // attention: O accumulated
+    const uint32_t tmem_slot = bar0 + 8u * kNumBars;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-        base_ptr + kRing * kStageBytes + kParamBytes + 8 * (2 * kRing + 8));
+        base_ptr + kRing * kStageBytes + kParamBytes + 8 * kNumBars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const int64_t m0 = (int64_t)(blockIdx.x / csize) * BM;        // this cluster's row panel
     const int nst = P.n;
+    const StageDesc* __restrict__ ST = P.st;
 
     if (warp == kProdWarp && lane == 0) {
-        for (int s = 0; s < nst; ++s) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&P.st[s].map_a) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&P.st[s].map_w) : "memory");
-        }
         for (int s = 0; s < kRing; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -2550,6 +2583,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
                 mbar_init(tempty_bar(s), kEpiWarps);
                 mbar_init(pfull_bar(s), 1);
                 mbar_init(pempty_bar(s), kEpiWarps);
+                mbar_init(pready_bar(s), kEpiThreads);
+                mbar_init(oready_bar(s), 1);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -2559,6 +2594,16 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // Stage descriptors: the tensor maps are used from global memory, everything else is copied into one of two shared
+    // slots by the parameter warp ONE STAGE AHEAD (before it arrives at the stage-end barrier) -- reading them from
+    // global memory at every use costs an L2 round trip per 128-byte line per warp per stage (measured: +3-4 k cycles
+    // on every stage).
+    auto copy_tail = [&](int s) {                     // parameter warp
+        const uint4* src = reinterpret_cast<const uint4*>(&ST[s].t);
+        uint4* dst = reinterpret_cast<uint4*>(const_cast<StageTail*>(tails + (s & 1)));
+        for (int i = lane; i < (int)(sizeof(StageTail) / 16); i += 32) dst[i] = __ldg(src + i);
+    };
+    if (warp == kParWarp) copy_tail(0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -2569,11 +2614,14 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
     int p_stage = 0, p_pre = 0;
     uint32_t p_phase = 0;
     auto preissue_w = [&](int s) {                    // producer lane 0: W of the first k-blocks of stage s
-        const StageDesc& S = P.st[s];
-        const int bn = bn_of(S.kind);
-        const int num_kb = (int)(S.K / 128);
+        const StageDesc& S = ST[s];                   // (ahead of the shared copy: global memory, off the critical path)
+        p_pre = 0;
+        const int kind = S.t.kind;
+        if (ATT && kind == 3) return;
+        const int bn = bn_of(kind);
+        const int num_kb = (int)(S.t.K / 128);
         const uint32_t bytes = (uint32_t)(BM * 128 + bn * 128);
-        const int32_t n0 = (int32_t)((crank * S.tiles) * bn);
+        const int32_t n0 = (int32_t)((crank * S.t.tiles) * bn);
         int st = p_stage;
         uint32_t ph = p_phase;
         p_pre = num_kb < kRing ? num_kb : kRing;
@@ -2590,28 +2638,44 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
     if (warp == kProdWarp) {
         // ===================== TMA producer =====================
         for (int s = 0; s < nst; ++s) {
-            const StageDesc& S = P.st[s];
+            const StageDesc& G = ST[s];
+            const StageTail& S = tails[s & 1];
+            const int kind = S.kind;
             if (lane == 0) {
-                const int bn = bn_of(S.kind);
-                const int num_kb = (int)(S.K / 128);
-                const uint32_t bytes = (uint32_t)(BM * 128 + bn * 128);
-                for (int j = 0; j < S.tiles; ++j) {
-                    const int32_t n0 = (int32_t)((crank * S.tiles + j) * bn);
-                    for (int kb = 0; kb < num_kb; ++kb) {
+                if (ATT && kind == 3) {
+                    const int32_t D = (int32_t)S.N;
+                    for (int j = 0; j < S.tiles; ++j) {                 // one ring slot per head: Q | K | V, 16 KB each
+                        const int32_t h = (int32_t)(crank * S.tiles + j);
+                        mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
+                        mbar_expect_tx(full_bar(p_stage), 3u * 16384u);
                         const uint32_t sa = base + p_stage * kStageBytes;
-                        if (j > 0 || kb >= p_pre) {
-                            mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
-                            mbar_expect_tx(full_bar(p_stage), bytes);
-                            tma_load_2d<1>(sa + BM * 128, &S.map_w, kb * 128, n0, full_bar(p_stage));
-                        }
-                        tma_load_2d<1>(sa, &S.map_a, kb * 128, (int32_t)m0, full_bar(p_stage));
+                        tma_load_2d<1>(sa, &G.map_a, h * 64, (int32_t)m0, full_bar(p_stage));
+                        tma_load_2d<1>(sa + 16384, &G.map_a, D + h * 64, (int32_t)m0, full_bar(p_stage));
+                        tma_load_2d<1>(sa + 32768, &G.map_a, 2 * D + h * 64, (int32_t)m0, full_bar(p_stage));
                         if (++p_stage == kRing) { p_stage = 0; p_phase ^= 1u; }
+                    }
+                } else {
+                    const int bn = bn_of(kind);
+                    const int num_kb = (int)(S.K / 128);
+                    const uint32_t bytes = (uint32_t)(BM * 128 + bn * 128);
+                    for (int j = 0; j < S.tiles; ++j) {
+                        const int32_t n0 = (int32_t)((crank * S.tiles + j) * bn);
+                        for (int kb = 0; kb < num_kb; ++kb) {
+                            const uint32_t sa = base + p_stage * kStageBytes;
+                            if (j > 0 || kb >= p_pre) {
+                                mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
+                                mbar_expect_tx(full_bar(p_stage), bytes);
+                                tma_load_2d<1>(sa + BM * 128, &G.map_w, kb * 128, n0, full_bar(p_stage));
+                            }
+                            tma_load_2d<1>(sa, &G.map_a, kb * 128, (int32_t)m0, full_bar(p_stage));
+                            if (++p_stage == kRing) { p_stage = 0; p_phase ^= 1u; }
+                        }
                     }
                 }
                 if (s + 1 < nst) preissue_w(s + 1);
             }
             __syncwarp();
-            if (S.kind == 2) cluster_sync_all();              // the stage's LayerNorm statistics exchange
+            if (kind == 2) cluster_sync_all();                // the stage's LayerNorm statistics exchange
             if (s + 1 < nst) {
                 cluster_sync_all();                           // stage boundary: the panel of stage s is complete
                 asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -2621,14 +2685,51 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
         // ===================== MMA issuer =====================
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
+        uint32_t att_ph0 = 0, att_ph1 = 0;                    // phases of pready[0 / 1]
         for (int s = 0; s < nst; ++s) {
-            const StageDesc& S = P.st[s];
-            if (lane == 0) {
-                const int bn = bn_of(S.kind);
+            const StageTail& S = tails[s & 1];
+            const int kind = S.kind;
+            if (ATT && lane == 0 && kind == 3) {
+                // per head: S = Q K^T (K-major operands, 4 x k16), then -- once the softmax warps have written P over
+                // Q | K -- O = P V (V MN-major, 8 x k16) into the first 64 score columns.  The scores of head j + 1 are
+                // issued BEFORE waiting for P of head j: its softmax overlaps the next head's loads and products.
+                constexpr uint32_t idS = make_idesc(128, 128), idO = make_idesc(128, 64) | (1u << 16);
+                auto issue_scores = [&]() {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * kStageBytes;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BNF);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_bf16<1>(d_tmem, make_desc_sw128(sa) + (uint64_t)(2 * k), make_desc_sw128(sa + 16384) + (uint64_t)(2 * k), idS, (uint32_t)(k != 0));
+                    tc_commit<1>(tfull_bar(acc));
+                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                };
+                int sj = stage, aj = acc;
+                issue_scores();
+                for (int j = 0; j < S.tiles; ++j) {
+                    const int sn = stage, an = acc;
+                    if (j + 1 < S.tiles) issue_scores();
+                    mbar_wait(pready_bar(aj), aj ? att_ph1 : att_ph0);
+                    tc_fence_after();
+                    const uint32_t sa = base + sj * kStageBytes;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(aj * BNF);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        tc_mma_bf16<1>(d_tmem, make_desc_sw128(sa + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3)), desc_mn_sw128(sa + 32768 + k * 2048), idO,
+                                       (uint32_t)(k != 0));
+                    tc_commit<1>(oready_bar(aj));
+                    tc_commit<1>(empty_bar(sj));
+                    if (aj) att_ph1 ^= 1u; else att_ph0 ^= 1u;
+                    sj = sn;
+                    aj = an;
+                }
+            } else if (lane == 0) {
+                const int bn = bn_of(kind);
                 const int num_kb = (int)(S.K / 128);
-                const uint32_t a_s8 = (S.ep.a_q.zero_float == nullptr && S.ep.a_q.is_signed != nullptr && *S.ep.a_q.is_signed) ? 1u : 0u;
-                const uint32_t w_s8 = (S.ep.w_q.zero_float == nullptr && S.ep.w_q.is_signed != nullptr && *S.ep.w_q.is_signed) ? 1u : 0u;
-                const uint32_t idesc = (2u << 4) | (a_s8 << 7) | (w_s8 << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                const uint32_t idesc = S.idesc;
                 for (int j = 0; j < S.tiles; ++j) {
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     tc_fence_after();
@@ -2648,8 +2749,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                 }
             }
+            // (the other lanes follow the ring / accumulator counters: they do not use them)
             __syncwarp();
-            if (S.kind == 2) cluster_sync_all();
+            if (kind == 2) cluster_sync_all();
             if (s + 1 < nst) cluster_sync_all();
         }
     } else if (warp == kParWarp) {
@@ -2658,12 +2760,24 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
         uint32_t pphase = 0;
         bool pending = false;                         // arrived at a stage-end cluster barrier, not yet waited
         for (int s = 0; s < nst; ++s) {
-            const StageDesc& S = P.st[s];
+            const StageTail& S = tails[s & 1];
             const Args& ep = S.ep;
-            const bool lnf = S.kind == 2;
-            const int bn = bn_of(S.kind);
+            const int kind = S.kind;
+            const bool lnf = kind == 2;
+            const int bn = bn_of(kind);
+            float* sgs = segp + (s & 1) * kMaxSeg * kSegFloats;
             QP mine = make_qp(1.0f, 0.0f, 0.0f, 0.0f);
-            {
+            int a_zp = 0;
+            if (ATT && kind == 3) {
+                if (lane < 6) {
+                    const tq_qspec& q = lane == 0 ? ep.out2_q : lane == 1 ? ep.ln_q : lane == 2 ? ep.out_q : lane == 3 ? ep.a_q : lane == 4 ? ep.w_q : ep.res_q;
+                    float lo, hi;
+                    grid_of(q, lo, hi);
+                    const QP p = resolve(q, 0, lo, hi);
+                    float* o = sgs + lane * 8;
+                    o[0] = p.scale; o[1] = p.zp; o[2] = p.lo; o[3] = p.hi; o[4] = p.rcp; o[5] = __int_as_float(p.exact);
+                }
+            } else {
                 float lo = 0.0f, hi = 0.0f;
                 const tq_qspec* qs = nullptr;
                 int slot = 0;
@@ -2677,10 +2791,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
                     grid_of(*qs, lo, hi);
                     mine = resolve(*qs, slot, lo, hi);
                 }
-            }
-            const float a_scale = __shfl_sync(0xffffffffu, mine.scale, 0);
-            const int a_zp = (int)__shfl_sync(0xffffffffu, mine.zp, 0);
-            {
+                const float a_scale = __shfl_sync(0xffffffffu, mine.scale, 0);
+                a_zp = (int)__shfl_sync(0xffffffffu, mine.zp, 0);
                 const int j = lane < ep.nseg ? lane : 0;
                 const float w_scale = __shfl_sync(0xffffffffu, mine.scale, 4 + j);
                 const float o_scale = __shfl_sync(0xffffffffu, mine.scale, 8 + j), o_rcp = __shfl_sync(0xffffffffu, mine.rcp, 8 + j);
@@ -2697,7 +2809,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
                 const float h3 = __shfl_sync(0xffffffffu, mine.hi, 3);
                 const int e3 = __shfl_sync(0xffffffffu, mine.exact, 3);
                 if (lane < ep.nseg && lane < kMaxSeg) {
-                    float* sg = segp + (s * kMaxSeg + lane) * kSegFloats;
+                    float* sg = sgs + lane * kSegFloats;
                     sg[0] = __fmul_rn(a_scale, w_scale);
                     sg[1] = o_scale; sg[2] = o_rcp; sg[3] = o_lo - o_zp; sg[4] = o_hi - o_zp;
                     sg[5] = __fadd_rn(o_zp, 12582912.0f);
@@ -2715,84 +2827,141 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const __grid_
                 asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
                 pending = false;
             }
-            for (int j = 0; j < S.tiles; ++j) {
-                const int64_t n0 = (int64_t)(crank * S.tiles + j) * bn;
-                mbar_wait(pempty_bar(pb), pphase ^ 1u);
-                float4* Pt = Pcol + pb * (BNF / 2);
-                for (int jp = lane; jp < bn / 2; jp += 32) {
-                    const int64_t n = n0 + 2 * jp;
-                    const float b0 = ep.bias != nullptr ? __ldg(ep.bias + n) : 0.0f, b1 = ep.bias != nullptr ? __ldg(ep.bias + n + 1) : 0.0f;
-                    const int r0 = __ldg(ep.w_rowsum + n), r1 = __ldg(ep.w_rowsum + n + 1);
-                    float4 gb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (lnf) gb = make_float4(__ldg(ep.ln_gamma + n), __ldg(ep.ln_gamma + n + 1), __ldg(ep.ln_beta + n), __ldg(ep.ln_beta + n + 1));
-                    Pt[jp] = make_float4(b0, b1, __int_as_float(a_zp * r0), __int_as_float(a_zp * r1));
-                    if (lnf) Pgb[jp] = gb;
+            if (ATT && kind == 3) {
+                const float* mask = ep.bias;                             // [sequences][128] additive mask or null
+                for (int i = lane; i < BM; i += 32) smask[i] = mask != nullptr ? __ldg(mask + m0 + i) : 0.0f;
+                for (int j = 0; j < S.tiles; ++j) {
+                    mbar_wait(pempty_bar(pb), pphase ^ 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pfull_bar(pb));
+                    if (++pb == 2) { pb = 0; pphase ^= 1u; }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(pfull_bar(pb));
-                if (++pb == 2) { pb = 0; pphase ^= 1u; }
+            } else {
+                for (int j = 0; j < S.tiles; ++j) {
+                    const int64_t n0 = (int64_t)(crank * S.tiles + j) * bn;
+                    mbar_wait(pempty_bar(pb), pphase ^ 1u);
+                    float4* Pt = Pcol + pb * (BNF / 2);
+                    for (int jp = lane; jp < bn / 2; jp += 32) {
+                        const int64_t n = n0 + 2 * jp;
+                        const float b0 = ep.bias != nullptr ? __ldg(ep.bias + n) : 0.0f, b1 = ep.bias != nullptr ? __ldg(ep.bias + n + 1) : 0.0f;
+                        const int r0 = __ldg(ep.w_rowsum + n), r1 = __ldg(ep.w_rowsum + n + 1);
+                        float4 gb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (lnf) gb = make_float4(__ldg(ep.ln_gamma + n), __ldg(ep.ln_gamma + n + 1), __ldg(ep.ln_beta + n), __ldg(ep.ln_beta + n + 1));
+                        Pt[jp] = make_float4(b0, b1, __int_as_float(a_zp * r0), __int_as_float(a_zp * r1));
+                        if (lnf) Pgb[jp] = gb;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pfull_bar(pb));
+                    if (++pb == 2) { pb = 0; pphase ^= 1u; }
+                }
             }
             __syncwarp();
             if (lnf) cluster_sync_all();
             if (s + 1 < nst) {
-                // arrive now, wait at the top of the next stage's tile loop: the next stage's quantizers are resolved
-                // while the epilogue warps finish this stage
+                // the next stage's descriptor goes to the other shared slot BEFORE this warp arrives at the stage-end barrier
+                // (every warp reads it after the barrier); arrive now, wait at the top of the next stage's tile loop: the next
+                // stage's quantizers are resolved while the epilogue warps finish this stage
+                copy_tail(s + 1);
+                __syncwarp();
                 asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
                 pending = true;
             }
         }
     } else {
-        // ===================== epilogue (warps 0..7) =====================
+        // ===================== epilogue / softmax (warps 0..7) =====================
         const int quarter = warp & 3, half = warp >> 2;
-        int acc = 0, pb = 0;
-        uint32_t acc_phase = 0, pphase = 0;
-        const int64_t row = m0 + quarter * 32 + lane;
+        int acc = 0, pb = 0, e_ring = 0;
+        uint32_t acc_phase = 0, pphase = 0, att_ph0 = 0, att_ph1 = 0;
+        const int rl = quarter * 32 + lane;
+        const int64_t row = m0 + rl;
         const bool row_ok = row < P.M;
-        long long* tr = (P.trace != nullptr && threadIdx.x == 0) ? P.trace + (int64_t)blockIdx.x * kMaxStages * 4 : nullptr;
+        long long* tr = (P.trace != nullptr && threadIdx.x == 0) ? P.trace + (int64_t)blockIdx.x * nst * 4 : nullptr;
         for (int s = 0; s < nst; ++s) {
-            const StageDesc& S = P.st[s];
+            const StageTail& S = tails[s & 1];
             const Args& ep = S.ep;
-            const int bn = bn_of(S.kind);
+            const int kind = S.kind;
+            const int bn = bn_of(kind);
             const int64_t N = S.N;
+            const float* sgs = segp + (s & 1) * kMaxSeg * kSegFloats;
             if (tr != nullptr) tr[s * 4 + 0] = clock64();
-            for (int j = 0; j < S.tiles; ++j) {
-                const int64_t n0 = (int64_t)(crank * S.tiles + j) * bn;
-                uint32_t r0[8], r1[8];
-                if (S.kind == 2) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) r0[i] = r1[i] = 0u;
-                    if (row_ok) {
-                        const unsigned char* rrow = ep.res_u8 + row * N + n0 + half * 32;
-                        ldg256(rrow, r0);
-                        ldg256(rrow + 64, r1);
+            if (ATT && kind == 3) {
+                attn::RowArgs ra;
+                ra.inv_sqrt_d = 0.125f; ra.sqrt_d = 0.0f; ra.c_ctr = nullptr; ra.c_u8 = reinterpret_cast<unsigned char*>(ep.y_u8);
+                for (int j = 0; j < S.tiles; ++j) {
+                    const int h = (int)(crank * S.tiles) + j;
+                    int slot = e_ring + j;
+                    slot -= slot >= kRing ? kRing : 0;
+                    mbar_wait(pfull_bar(pb), pphase);
+                    const QP qs = load_qp(sgs), qp = load_qp(sgs + 8), qc = load_qp(sgs + 16);
+                    const float sqk = sgs[24] * sgs[32], spv = qp.scale * sgs[40];
+                    const bool exact = (qs.exact | qp.exact | qc.exact) != 0;
+                    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNF);
+                    unsigned char* pP = base_ptr + slot * kStageBytes;
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    tc_fence_after();
+                    if (tr != nullptr && j == 0) tr[s * 4 + 1] = clock64();
+                    if (exact) attn::softmax_rows<false, false>(ra, qs, qp, sqk, trow, rl, half, smask, pP, xchg);
+                    else attn::softmax_rows<true, false>(ra, qs, qp, sqk, trow, rl, half, smask, pP, xchg);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
+                    tc_fence_before();
+                    mbar_arrive(pready_bar(acc));
+                    mbar_wait(oready_bar(acc), acc ? att_ph1 : att_ph0);
+                    tc_fence_after();
+                    const int64_t ooff = row * N + h * 64 + half * 32;
+                    if (exact) attn::context_rows<false>(ra, qc, spv, trow, half, ooff, (int32_t)N);
+                    else attn::context_rows<true>(ra, qc, spv, trow, half, ooff, (int32_t)N);
+                    if (acc) att_ph1 ^= 1u; else att_ph0 ^= 1u;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(tempty_bar(acc));
+                        mbar_arrive(pempty_bar(pb));
                     }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                    if (++pb == 2) { pb = 0; pphase ^= 1u; }
                 }
-                mbar_wait(pfull_bar(pb), pphase);
-                const float* sg = segp + (s * kMaxSeg + (int)(n0 / ep.seg_width)) * kSegFloats;
-                const int exact = __float_as_int(sg[6]);
-                const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNF);
-                const float4* Pt = Pcol + pb * (BNF / 2);
-                mbar_wait(tfull_bar(acc), acc_phase);
-                tc_fence_after();
-                if (tr != nullptr && j == 0) tr[s * 4 + 1] = clock64();
-                if (S.kind == 2) {
-                    if (exact) epi_res_ln<BNL, false>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
-                    else epi_res_ln<BNL, true>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
-                } else if (S.kind == 1) {
-                    if (exact) epi_plain<BNF, 1, false, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
-                    else epi_plain<BNF, 1, true, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
-                } else {
-                    if (exact) epi_plain<BNL, 0, false, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
-                    else epi_plain<BNL, 0, true, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                e_ring = (e_ring + S.tiles) % kRing;
+            } else {
+                for (int j = 0; j < S.tiles; ++j) {
+                    const int64_t n0 = (int64_t)(crank * S.tiles + j) * bn;
+                    uint32_t r0[8], r1[8];
+                    if (kind == 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) r0[i] = r1[i] = 0u;
+                        if (row_ok) {
+                            const unsigned char* rrow = ep.res_u8 + row * N + n0 + half * 32;
+                            ldg256(rrow, r0);
+                            ldg256(rrow + 64, r1);
+                        }
+                    }
+                    mbar_wait(pfull_bar(pb), pphase);
+                    const float* sg = sgs + (int)(n0 / ep.seg_width) * kSegFloats;
+                    const int exact = __float_as_int(sg[6]);
+                    const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNF);
+                    const float4* Pt = Pcol + pb * (BNF / 2);
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    tc_fence_after();
+                    if (tr != nullptr && j == 0) tr[s * 4 + 1] = clock64();
+                    if (kind == 2) {
+                        if (exact) epi_res_ln<BNL, false>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+                        else epi_res_ln<BNL, true>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
+                    } else if (kind == 1) {
+                        if (exact) epi_plain<BNF, 1, false, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                        else epi_plain<BNF, 1, true, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                    } else {
+                        if (exact) epi_plain<BNL, 0, false, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                        else epi_plain<BNL, 0, true, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(tempty_bar(acc));
+                        mbar_arrive(pempty_bar(pb));
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                    if (++pb == 2) { pb = 0; pphase ^= 1u; }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(tempty_bar(acc));
-                    mbar_arrive(pempty_bar(pb));
-                }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                if (++pb == 2) { pb = 0; pphase ^= 1u; }
+                e_ring = (e_ring + S.tiles * (int)(S.K / 128)) % kRing;
             }
             if (tr != nullptr) tr[s * 4 + 2] = clock64();
             if (s + 1 < nst) {
@@ -3006,13 +3175,18 @@ static int launch_peg(const void* a, const void* w, int64_t M, int64_t N, int64_
 
 static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
-static int launch_chain(const tq_chain_stage* stages, int32_t n, int64_t M, cudaStream_t st) {
+struct ChainPlan {
+    lean::chain::StageDesc* d_st;
+    int32_t n, csize;
+    int64_t M;
+    bool attention;                       // any kind-3 stage
+};
+constexpr int kMaxPlanStages = 256;
+
+static int chain_plan_create(const tq_chain_stage* stages, int32_t n, int64_t M, void** out) {
     using namespace lean::chain;
-    if (stages == nullptr || n < 1 || n > kMaxStages || M < 1) return TQ_EINVAL;
-    Params P;
-    memset(&P, 0, sizeof(P));
-    P.M = M;
-    P.n = n;
+    if (stages == nullptr || out == nullptr || n < 1 || n > kMaxPlanStages || M < 1) return TQ_EINVAL;
+    *out = nullptr;
     int64_t csize = 0;
     for (int i = 0; i < n; ++i)
         if (stages[i].kind == 2) {
@@ -3021,10 +3195,35 @@ static int launch_chain(const tq_chain_stage* stages, int32_t n, int64_t M, cuda
             csize = c;
         }
     if (csize == 0) return TQ_EUNSUPPORTED;            // (a chain without a LayerNorm stage: use the single kernels)
+    std::vector<StageDesc> host((size_t)n);
+    memset(host.data(), 0, sizeof(StageDesc) * (size_t)n);
     for (int i = 0; i < n; ++i) {
         const tq_chain_stage& g = stages[i];
-        StageDesc& S = P.st[i];
-        if (g.kind < 0 || g.kind > 2 || g.a_i8 == nullptr || g.w_i8 == nullptr || g.w_rowsum == nullptr || g.out == nullptr) return TQ_EINVAL;
+        StageDesc& S = host[(size_t)i];
+        if (g.kind < 0 || g.kind > 3 || g.a_i8 == nullptr || g.out == nullptr) return TQ_EINVAL;
+        lean::Args& a = S.t.ep;
+        a.a_q = g.a_q; a.w_q = g.w_q; a.out_q = g.out_q; a.res_q = g.res_q; a.out2_q = g.out2_q; a.ln_q = g.ln_q;
+        a.bias = g.bias;
+        a.trace = nullptr; a.trace_tiles = nullptr;
+        S.t.N = g.N;
+        S.t.K = g.K;
+        S.t.kind = g.kind;
+        if (g.kind == 3) {
+            // attention of K heads of 64 dimensions over [M, 3 N] bf16 centred grids, one sequence = one 128-row panel
+            const tq_qspec* need[6] = {&g.a_q, &g.w_q, &g.res_q, &g.out2_q, &g.ln_q, &g.out_q};
+            for (int k = 0; k < 6; ++k) {
+                if (int e = tq::check_qspec(*need[k])) return e;
+                if (need[k]->n_bits > 8) return TQ_EUNSUPPORTED;
+            }
+            if (g.K < 1 || g.N != g.K * 64 || g.K % csize != 0 || M % BM != 0 || g.N != csize * BNL) return TQ_EUNSUPPORTED;
+            if (!tq::aligned16(g.a_i8) || !aligned32(g.out) || (g.N & 31) != 0) return TQ_EALIGN;
+            if (int e = make_map(&S.map_a, g.a_i8, M, 3 * g.N, BM, false)) return e;
+            S.t.tiles = (int32_t)(g.K / csize);
+            a.y_u8 = g.out;
+            a.ldc = g.N;
+            continue;
+        }
+        if (g.w_i8 == nullptr || g.w_rowsum == nullptr) return TQ_EINVAL;
         if (g.N < 1 || g.K < 1 || g.K % 128 != 0 || g.nseg < 1 || g.nseg > lean::kMaxSeg || g.N % g.nseg != 0) return TQ_EUNSUPPORTED;
         const int bn = g.kind == 1 ? BNF : BNL;
         if (g.N % bn != 0 || (g.N / bn) % csize != 0 || (g.N / g.nseg) % bn != 0) return TQ_EUNSUPPORTED;
@@ -3044,31 +3243,61 @@ static int launch_chain(const tq_chain_stage* stages, int32_t n, int64_t M, cuda
         if (!tq::aligned16(g.a_i8) || !tq::aligned16(g.w_i8) || !aligned32(g.out) || (g.res_i8 != nullptr && !aligned32(g.res_i8)) || (g.N & 31) != 0) return TQ_EALIGN;
         if (int e = make_map(&S.map_a, g.a_i8, M, g.K, BM, true)) return e;
         if (int e = make_map(&S.map_w, g.w_i8, g.N, g.K, bn, true)) return e;
-        S.N = g.N;
-        S.K = g.K;
-        S.kind = g.kind;
-        S.tiles = (int32_t)((g.N / bn) / csize);
-        lean::Args& a = S.ep;
-        a.bias = g.bias; a.w_rowsum = g.w_rowsum; a.a_q = g.a_q; a.w_q = g.w_q; a.out_q = g.out_q;
+        S.t.tiles = (int32_t)((g.N / bn) / csize);
+        {   // operand signedness of the kind::i8 products (symmetric quantizers carry a device-side flag): resolved once, here
+            auto is_s8 = [](const tq_qspec& q, uint32_t& out) -> int {
+                out = 0u;
+                if (q.zero_float != nullptr || q.is_signed == nullptr) return TQ_OK;
+                unsigned char flag = 0;
+                if (cudaMemcpy(&flag, q.is_signed, 1, cudaMemcpyDeviceToHost) != cudaSuccess) return TQ_EINVAL;
+                out = flag ? 1u : 0u;
+                return TQ_OK;
+            };
+            uint32_t a_s8 = 0u, w_s8 = 0u;
+            if (int e = is_s8(g.a_q, a_s8)) return e;
+            if (int e = is_s8(g.w_q, w_s8)) return e;
+            S.t.idesc = (2u << 4) | (a_s8 << 7) | (w_s8 << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        }
+        a.w_rowsum = g.w_rowsum;
         a.seg_width = g.N / g.nseg; a.nseg = g.nseg; a.ldc = g.N;
         a.y_u8 = g.kind == 0 ? nullptr : g.out;
         a.y_ctr = g.kind == 0 ? reinterpret_cast<__nv_bfloat16*>(g.out) : nullptr;
         a.res_u8 = reinterpret_cast<const unsigned char*>(g.res_i8);
-        a.res_q = g.res_q; a.out2_q = g.out2_q; a.ln_q = g.ln_q;
         a.ln_gamma = g.ln_gamma_q; a.ln_beta = g.ln_beta; a.ln_eps = g.ln_eps;
-        a.trace = nullptr; a.trace_tiles = nullptr;
     }
+    StageDesc* dev = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dev), sizeof(StageDesc) * (size_t)n);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(dev, host.data(), sizeof(StageDesc) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); return (int)e; }
+    bool att = false;
+    for (int i = 0; i < n; ++i) att = att || stages[i].kind == 3;
+    ChainPlan* plan = new ChainPlan{dev, n, (int32_t)csize, M, att};
+    *out = plan;
+    return TQ_OK;
+}
+
+static int chain_plan_run(const ChainPlan* plan, cudaStream_t st) {
+    using namespace lean::chain;
+    if (plan == nullptr || plan->d_st == nullptr) return TQ_EINVAL;
+    Params P;
+    P.st = plan->d_st;
+    P.M = plan->M;
+    P.n = plan->n;
+    P.trace = nullptr;
+    if (const char* env = getenv("TQ_LINEAR_TRACE_CHAIN"))         // tools/trace_chain.py: device pointer of a zeroed int64 buffer
+        P.trace = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(linear_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int64_t panels = (M + BM - 1) / BM;
-    if (const char* env = getenv("TQ_LINEAR_TRACE_CHAIN")) {       // tools/trace_chain.py: device pointer of a zeroed int64 buffer
-        P.trace = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
-    }
-    return launch_pdl(linear_chain_kernel, dim3((unsigned)(panels * csize)), dim3(lean::kThreads), kSmemBytes, st, (int)csize, P);
+    const int64_t panels = (plan->M + BM - 1) / BM;
+    const dim3 grid((unsigned)(panels * plan->csize)), block(lean::kThreads);
+    if (plan->attention) return launch_pdl(linear_chain_kernel<true>, grid, block, kSmemBytes, st, plan->csize, P);
+    return launch_pdl(linear_chain_kernel<false>, grid, block, kSmemBytes, st, plan->csize, P);
 }
 
 static void lean_trace(lean::Args& ep) {
@@ -3445,8 +3674,18 @@ int tq_linear_peg_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_
     return launch_peg<0, true, true>(a_i8, w_i8, M, N, K, pa, (cudaStream_t)stream);
 }
 
-int tq_linear_chain_i8(const tq_chain_stage* stages, int32_t n_stages, int64_t M, void* stream) {
-    return tq::gemm::launch_chain(stages, n_stages, M, (cudaStream_t)stream);
+int tq_chain_plan_create(const tq_chain_stage* stages, int32_t n_stages, int64_t M, void** plan) {
+    return tq::gemm::chain_plan_create(stages, n_stages, M, plan);
+}
+int tq_chain_plan_run(const void* plan, void* stream) {
+    return tq::gemm::chain_plan_run(static_cast<const tq::gemm::ChainPlan*>(plan), (cudaStream_t)stream);
+}
+int tq_chain_plan_destroy(void* plan) {
+    if (plan == nullptr) return TQ_OK;
+    tq::gemm::ChainPlan* p = static_cast<tq::gemm::ChainPlan*>(plan);
+    cudaFree(p->d_st);
+    delete p;
+    return TQ_OK;
 }
 
 int tq_split3_bf16(const float* x, void* out_bf16, int64_t M, int64_t K, void* stream) {

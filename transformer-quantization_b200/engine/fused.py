@@ -230,23 +230,40 @@ class FusedBertEngine:
         self.lean = (self.i8 and os.environ.get('TQ_ENGINE_LEAN', '1') != '0' and D % 128 == 0
                      and cfg.intermediate_size % 128 == 0
                      and all(st.q.n_bits <= 8 for d in self.layers for st in (d['q'], d['k'], d['v'], d['f'])))
-        # chain kernel: the four GEMM stages between two attention kernels in ONE launch (a cluster per 128-row panel)
+        # chain kernel (tq_chain_plan_*): a cluster of D / 192 CTAs carries one sequence through a list of stages.
+        #   TQ_ENGINE_CHAIN=1 (default)  one launch per layer for the four GEMM stages (attention-output + LN, FFN-in, FFN-out
+        #                                + LN, next Q|K|V), attention as its own kernel (three CTAs per SM hide its latencies)
+        #   TQ_ENGINE_CHAIN=2            the whole encoder in ONE launch, attention as a chain stage (bit-identical; measured
+        #                                1.13 ms against 1.07 ms per step: with the attention code in the same kernel every
+        #                                GEMM epilogue runs 15-20 % slower and three heads per CTA run one after the other)
+        #   TQ_ENGINE_CHAIN=0            every stage its own kernel
         I = cfg.intermediate_size
-        self.chain = (self.lean and os.environ.get('TQ_ENGINE_CHAIN', '1') != '0' and D % 192 == 0 and D // 192 <= 8
-                      and I % 256 == 0 and (I // 256) % (D // 192) == 0)
+        mode = int(os.environ.get('TQ_ENGINE_CHAIN', '1'))
+        ok = (self.lean and D % 192 == 0 and D // 192 <= 8 and I % 256 == 0 and (I // 256) % (D // 192) == 0
+              and (3 * D // 192) % (D // 192) == 0)
+        self.chain = mode if ok else 0
+        if self.chain == 2 and self.H % (D // 192) != 0:
+            self.chain = 1
         if self.chain:
+            self.mask_buf = torch.zeros(batch, seq, dtype=torch.float32, device=dev)
             self._build_chains()
         self._last_i8 = False
 
     def _build_chains(self):
-        cs = self.ops.chain_stage
-        D, x, c, a, f = self.D, self.x8, self.c8, self.a8, self.f8
-        self.chains = []
+        ops = self.ops
+        cs = ops.chain_stage
+        D, M, x, c, a, f = self.D, self.M, self.x8, self.c8, self.a8, self.f8
+        per_layer, whole = [], []
         x_site = self.e_out
+        d0 = self.layers[0]
+        w = d0['wqkv']
+        whole.append(cs(0, x, w.grid8, w.rowsum, w.bias, self.qkv, w.N, w.K, x_site.spec, w.seg_spec, d0['qkv_out'].seg_spec, 3))
         for li, d in enumerate(self.layers):
             wg, wf, wh = d['wg'], d['wf'], d['wh']
             g1, b1, e1 = d['ln1']
             g2, b2, e2 = d['ln2']
+            att = ops.chain_attention_stage(self.qkv, c, D, self.H, d['q'].spec, d['k'].spec, d['v'].spec, d['s'].spec, d['p'].spec,
+                                            d['c'].spec, self.mask_buf)
             st = [cs(2, c, wg.grid8, wg.rowsum, wg.bias, a, wg.N, wg.K, d['c'].spec, wg.seg_spec, d['g'].spec, 1, x, x_site.spec,
                      d['u'].spec, d['x'].spec, g1, b1, e1),
                   cs(1, a, wf.grid8, wf.rowsum, wf.bias, f, wf.N, wf.K, d['x'].spec, wf.seg_spec, d['f'].spec),
@@ -256,8 +273,14 @@ class FusedBertEngine:
                 n = self.layers[li + 1]
                 w = n['wqkv']
                 st.append(cs(0, x, w.grid8, w.rowsum, w.bias, self.qkv, w.N, w.K, d['z'].spec, w.seg_spec, n['qkv_out'].seg_spec, 3))
-            self.chains.append(st)
+            per_layer.append(st)
+            whole.append(att)
+            whole.extend(st)
             x_site = d['z']
+        if self.chain == 2:
+            self.plan = ops.chain_plan(whole, M)
+        else:
+            self.plans = [ops.chain_plan(st, M) for st in per_layer]
 
     def _linear(self, a_ctr, a_site, w, act, out_spec, out_params, out_ctr=None, want_f32=False, M=None):
         M = a_ctr.shape[0] if M is None else M
@@ -358,15 +381,23 @@ class FusedBertEngine:
                             self.e_gamma, self.e_beta, self.e_eps, self.e_out.spec, 1, x)
         x_site = self.e_out
         lean = self.lean
-        if self.chain:   # QKV(0), then per layer: attention + one chain launch (attn-out + LN, FFN-in, FFN-out + LN, next QKV)
+        if self.chain:
+            if attention_mask is not None:
+                self.mask_buf.copy_(mask.view(B, T))
+            else:
+                self.mask_buf.zero_()
+        if self.chain == 2:          # the whole encoder in one launch
+            ops.chain_run(self.plan)
+            x_site = self.layers[-1]['z']
+        elif self.chain == 1:        # QKV(0), then per layer: attention + one chain launch (attn-out + LN, FFN-in, FFN-out + LN, next QKV)
             d = self.layers[0]
             w = d['wqkv']
             ops.linear_seg_i8(x, w.grid8, w.rowsum, w.bias, M, w.N, w.K, x_site.spec, w.seg_spec, d['qkv_out'].seg_spec, 3, 0,
                               out_ctr=self.qkv)
-            for d, st in zip(self.layers, self.chains):
+            for d, plan in zip(self.layers, self.plans):
                 ops.attention_i8(self.qkv, B, T, H, self.hd, d['q'].spec, d['k'].spec, d['v'].spec, d['s'].spec, d['p'].spec,
-                                 d['c'].spec, mask, c)
-                ops.linear_chain_i8(st, M)
+                                 d['c'].spec, self.mask_buf, c)
+                ops.chain_run(plan)
             x_site = self.layers[-1]['z']
         for d in (() if self.chain else self.layers):
             w = d['wqkv']
@@ -424,11 +455,14 @@ class FusedBertEngine:
             for k in ('q', 'k', 'v', 's', 'p', 'c', 'g', 'u', 'x', 'f', 'h', 'y', 'z'):
                 yield d[k]
 
-    def i8_flop_share(self):
-        """share of the GEMM flops of one forward that runs on kind::i8 (bench.py: flop-weighted tensor peak)"""
+    def i8_flop_share(self, kernel_class='linear_qdq'):
+        """share of the tensor-core flops of one forward (of the given bench kernel class) that runs on kind::i8
+        (bench.py: flop-weighted tensor peak); the chain class of the one-launch encoder includes the bf16 attention products"""
         if not self.i8:
             return 0.0
         i8 = bf = 0
+        if kernel_class == 'chain' and self.chain == 2:
+            bf += len(self.layers) * 2 * self.T * self.D          # per row: QK^T and PV over T keys (x 2 flops, as N * K below)
         for d in self.layers:
             for key in ('wqkv', 'wg', 'wh'):
                 i8 += d[key].N * d[key].K

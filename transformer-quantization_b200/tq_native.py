@@ -49,6 +49,31 @@ class TQError(RuntimeError):
     pass
 
 
+class ChainPlan:
+    """owner of one tq_chain_plan (device-side stage descriptors); keeps the stage structs alive for inspection"""
+
+    def __init__(self, ops, stages, M):
+        self._ops = ops
+        self.stages = list(stages)
+        self.M = int(M)
+        self.flops = sum(self.M * getattr(s, '_flops', 0) for s in self.stages)
+        arr = (ChainStage * len(self.stages))(*self.stages)
+        h = ctypes.c_void_p()
+        ops._check(ops.lib.tq_chain_plan_create(arr, len(self.stages), self.M, ctypes.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            self._ops.lib.tq_chain_plan_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 ACT_FN = {'none': 0, 'gelu': 1, 'relu': 2, 'tanh': 3}
 
 # exported symbol -> (restype, argtypes); also used by the CPU-side export test
@@ -109,7 +134,9 @@ SIGNATURES = {
     'tq_linear_seg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
                                             ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, QSpec, _i32, _i32, _i64,
                                             ctypes.c_void_p]),
-    'tq_linear_chain_i8': (ctypes.c_int, [ctypes.POINTER(ChainStage), _i32, _i64, ctypes.c_void_p]),
+    'tq_chain_plan_create': (ctypes.c_int, [ctypes.POINTER(ChainStage), _i32, _i64, ctypes.POINTER(ctypes.c_void_p)]),
+    'tq_chain_plan_run': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'tq_chain_plan_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'tq_linear_nonorm_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
                                                _i64, _i64, _i64, QSpec, QSpec, QSpec, ctypes.c_void_p, QSpec, QSpec, _c_f32p,
                                                _c_f32p, QSpec, _i64, ctypes.c_void_p]),
@@ -514,13 +541,27 @@ class CudaOps:
         if kind == 2:
             st.res_i8, st.res_q, st.out2_q, st.ln_q = res_i8.data_ptr(), res_spec, out2_spec, ln_spec
             st.ln_gamma_q, st.ln_beta, st.ln_eps = ln_gamma_q.data_ptr(), ln_beta.data_ptr(), float(ln_eps)
+        st._flops = 2 * int(N) * int(K)                 # per row
         return st
 
-    def linear_chain_i8(self, stages, M):
-        """tq_linear_chain_i8: consecutive GEMM stages of an encoder layer in one launch (clusters own 128-row panels)"""
-        arr = (ChainStage * len(stages))(*stages)
-        flops = sum(2 * M * s.N * s.K for s in stages)
-        self._run('linear_qdq', flops, 1, self.lib.tq_linear_chain_i8, arr, len(stages), int(M), _stream())
+    @staticmethod
+    def chain_attention_stage(qkv_ctr, out_i8, hidden, heads, q_spec, k_spec, v_spec, s_spec, p_spec, c_spec, mask=None):
+        """kind 3: attention over the Q | K | V buffer [M, 3 hidden] (bf16 centred grids) -> context bytes [M, hidden]"""
+        _chk_cuda(qkv_ctr, out_i8, mask)
+        st = ChainStage()
+        st.a_i8, st.out, st.bias = qkv_ctr.data_ptr(), out_i8.data_ptr(), _ptr(mask)
+        st.N, st.K, st.nseg, st.kind = int(hidden), int(heads), 1, 3
+        st.a_q, st.w_q, st.res_q, st.out2_q, st.ln_q, st.out_q = q_spec, k_spec, v_spec, s_spec, p_spec, c_spec
+        st._flops = 4 * 128 * int(hidden)               # per row: QK^T and PV over 128 keys
+        return st
+
+    def chain_plan(self, stages, M):
+        """tq_chain_plan_create: descriptors of a stage list in device memory (fixed buffers); run with chain_run"""
+        return ChainPlan(self, stages, M)
+
+    def chain_run(self, plan):
+        """tq_chain_plan_run: every stage of the plan in ONE launch (a cluster per 128-row panel)"""
+        self._run('chain', plan.flops, 1, self.lib.tq_chain_plan_run, plan.handle, _stream())
 
     def linear_nonorm_i8(self, a_i8, w_i8, w_rowsum, bias, M, N, K, a_spec, w_spec, out_spec, res_i8, res_spec, out2_spec,
                          nn_weight_q, nn_bias_q, nn_spec, out_i8, ldc=0):
