@@ -54,9 +54,11 @@ typedef struct tq_qspec {
 
 /* ---- library info ------------------------------------------------------------------------- */
 int         tq_version(void);              /* ABI version: 1 = inference path; 2 adds the training-time entry points
-                                              * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 (current) adds
-                                              * tq_linear_seg_qdq_i8, tq_chain_plan_create / _run / _destroy, tq_linear_nonorm_qdq_i8, tq_calib_finalize_f32,
-                                              * tq_attention_pad_qdq_i8 and the tq_*_peg_* entry points */
+                                              * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 adds
+                                              * tq_linear_seg_qdq_i8, tq_linear_nonorm_qdq_i8, tq_calib_finalize_f32,
+                                              * tq_attention_pad_qdq_i8 and the tq_*_peg_* entry points; 4 (current) adds the
+                                              * encoder chain (tq_chain_plan_create / _run / _destroy) and the packed-path
+                                              * counters of tq_selftest_div (uint64[5]) */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
 
@@ -65,7 +67,8 @@ int         tq_device_sm_count(void);      /* SM count of the current device (14
  * bit with the IEEE division instruction.  mismatches[0] += #quotient mismatches with
  * 2^-60 <= |x/s| < 2^22, mismatches[1] += #integer-grid mismatches (both must stay 0),
  * mismatches[2] += #quotient mismatches below 2^-60 (residual underflow; they round to 0 either
- * way).  Device uint64[3], caller-zeroed. */
+ * way); mismatches[3] / [4] += the same two counts for the PACKED forms the fused epilogues use (quot2,
+ * quant_int2_finite, quant_ctr2_finite on FFMA2; both must stay 0).  Device uint64[5], caller-zeroed. */
 int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mismatches, void* stream);
 
 /* Copy-bandwidth probe with this library's streaming access pattern (128-bit grid-stride loop of the

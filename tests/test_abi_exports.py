@@ -23,7 +23,7 @@ def test_library_exports_every_symbol():
         import __graft_entry__
         __graft_entry__.build()
     lib = tq_native.load_library()      # getattr() on every declared symbol; no CUDA call
-    assert lib.tq_version() == tq_native.ABI_VERSION == 3
+    assert lib.tq_version() == tq_native.ABI_VERSION == 4
     assert b'invalid' in lib.tq_error_string(-1)
 
 
@@ -71,7 +71,7 @@ def test_argument_errors_are_reported_before_any_device_work():
     Q = tq_native.QSpec
     fake = 0x1000                                  # a non-NULL "device pointer" that is never dereferenced
     good = Q(fake, fake, None, 8, 0, 1e-8)
-    assert lib.tq_version() == tq_native.ABI_VERSION == 3
+    assert lib.tq_version() == tq_native.ABI_VERSION == 4
     assert lib.tq_error_string(-1) == b'tq: invalid argument' and lib.tq_error_string(0) == b'ok'
     assert lib.tq_error_string(-3) == b'tq: workspace too small'
     # quantize-dequantize

@@ -55,13 +55,15 @@ def test_quant_linear_golden(case, golden):
 def test_division_free_quotient_is_exact(ops):
     """tq::div_rn (two FMA corrections of x * RN(1/s)) == IEEE division, bit for bit, on 1.2e10
     adversarial pairs (ties of the integer grid +- 4 ulp, random floats, random scales, 2-16 bits)."""
-    out = torch.zeros(3, dtype=torch.int64, device=DEV)
+    out = torch.zeros(5, dtype=torch.int64, device=DEV)
     for seed in range(3):
         code = ops.lib.tq_selftest_div(1234 + seed, 148 * 16, 4096 * 4, out.data_ptr(), None)
         assert code == 0
     torch.cuda.synchronize()
     assert out.tolist()[:2] == [0, 0], (f'quotient mismatches {out[0].item()}, grid mismatches {out[1].item()}, '
                                         f'sub-2^-60 quotient mismatches {out[2].item()}')
+    # the packed (FFMA2) forms the fused epilogues use: quot2 bit for bit, quant_int2_finite / quant_ctr2_finite integers
+    assert out.tolist()[3:] == [0, 0], f'packed quotient mismatches {out[3].item()}, packed grid mismatches {out[4].item()}'
 
 
 # ---- 2. kernels vs oracle on random inputs ------------------------------------------------------

@@ -22,7 +22,7 @@ __device__ __forceinline__ float quant_int_ref(float x, float s, float zp, float
 // IEEE division instruction on adversarial inputs: x near (k + 1/2) * s ties, random x, random s.
 __global__ void selftest_div_kernel(uint64_t seed, int iters, unsigned long long* out) {
     uint64_t st = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1B54A32D192ED03ULL);
-    unsigned long long bad_div = 0, bad_q = 0, bad_tiny = 0;
+    unsigned long long bad_div = 0, bad_q = 0, bad_tiny = 0, bad_div2 = 0, bad_q2 = 0;
     for (int it = 0; it < iters; ++it) {
         const uint64_t r0 = splitmix(st), r1 = splitmix(st);
         // scale: random significand, exponent so that s in ~[1e-8, 1e4]
@@ -53,10 +53,25 @@ __global__ void selftest_div_kernel(uint64_t seed, int iters, unsigned long long
         }
         const float qa = quant_int(x, p), qb = quant_int_ref(x, s, zp, 0.0f, hi);
         if (!(qa == qb) && !(qa != qa && qb != qb)) ++bad_q;
+        // the PACKED path the fused epilogues use (quot2 / quant_int2_finite / quant_ctr2_finite on FFMA2): both components,
+        // the second one a neighbour of x, finite inputs with |x / s| < 2^22 (what the epilogues guarantee)
+        const float x2 = __uint_as_float(__float_as_uint(x) ^ (uint32_t)((r1 >> 20) & 7u));
+        const float b2 = __fdiv_rn(x2, s);
+        if (fabsf(b) < 4194304.0f && fabsf(b2) < 4194304.0f && fabsf(b) >= 8.67361737988e-19f && fabsf(b2) >= 8.67361737988e-19f) {
+            const QP2 p2 = pair_of(p);
+            const float2 xx = make_float2(x, x2);
+            const float2 qq = quot2(xx, p2);
+            if (__float_as_uint(qq.x) != __float_as_uint(b) || __float_as_uint(qq.y) != __float_as_uint(b2)) ++bad_div2;
+            const float2 ki = quant_int2_finite(xx, p2), kc = quant_ctr2_finite(xx, p2);
+            const float rb2 = quant_int_ref(x2, s, zp, 0.0f, hi);
+            if (ki.x != qb || ki.y != rb2 || kc.x != qb - zp || kc.y != rb2 - zp) ++bad_q2;
+        }
     }
     if (bad_div) atomicAdd(out, bad_div);
     if (bad_q) atomicAdd(out + 1, bad_q);
     if (bad_tiny) atomicAdd(out + 2, bad_tiny);
+    if (bad_div2) atomicAdd(out + 3, bad_div2);
+    if (bad_q2) atomicAdd(out + 4, bad_q2);
 }
 
 // ---- copy-bandwidth probe with this library's access patterns ---------------------------------------------
@@ -115,7 +130,7 @@ int tq_selftest_div(uint64_t seed, int32_t blocks, int32_t iters, uint64_t* mism
     return tq::launch_status();
 }
 
-int tq_version(void) { return 3; }
+int tq_version(void) { return 4; }
 
 const char* tq_error_string(int code) {
     switch (code) {

@@ -174,7 +174,7 @@ SIGNATURES = {
                                            ctypes.c_float, ctypes.c_void_p]),
 }
 
-ABI_VERSION = 3          # tq_version() of the library this binding was written against
+ABI_VERSION = 4          # tq_version() of the library this binding was written against
 ADAROUND_MODE = {'learned_sigmoid': 0, 'learned_hard_sigmoid': 1, 'sigmoid_temp_decay': 2}
 
 
