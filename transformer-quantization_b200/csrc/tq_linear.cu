@@ -1495,12 +1495,11 @@ __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restr
         const int c0 = half * 32 + it * 64;
         if (it + 1 < NIT) tmem_ld32_nowait(tmem_tile + (uint32_t)(c0 + 64), vn);
         if (it + 2 < NIT && row_ok) ldg256(rrow + c0 + 128, rn2);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const float4* P = Pcol + (c0 >> 1) + 8 * h;
-            uint32_t kp[8];
+        {
+            const float4* P = Pcol + (c0 >> 1);
+            uint32_t kp[16];
 #pragma unroll
-            for (int jp = 0; jp < 8; ++jp) {
+            for (int jp = 0; jp < 16; ++jp) {
                 const float4 pp = P[jp];
                 const float2 a = make_float2(__int2float_rn((int)v[2 * jp] - __float_as_int(pp.z)),
                                              __int2float_rn((int)v[2 * jp + 1] - __float_as_int(pp.w)));
@@ -1520,11 +1519,7 @@ __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restr
                 S2 = __ffma2_rn(k, k, S2);
                 kp[jp] = pack_bf16(k);
             }
-            tmem_st8_nowait(tmem_tile + (uint32_t)(c0 + 8 * h), kp);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = v[i + 16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rw[i] = rw[i + 4];
+            tmem_st16_nowait(tmem_tile + (uint32_t)c0, kp);
         }
     }
     tmem_st_wait();
@@ -1565,13 +1560,11 @@ __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restr
         for (int i = 0; i < 16; ++i) kq[i] = kn[i];
         const int c0 = half * 32 + it * 64;
         if (it + 1 < NIT) tmem_ld16_nowait(tmem_tile + (uint32_t)(c0 + 64), kn);
-        uint32_t held[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const float4* G = Pgb + (c0 >> 1) + 8 * h;
-            uint32_t wc[8], b[16];
+        {
+            const float4* G = Pgb + (c0 >> 1);
+            uint32_t wc[16], b[32];
 #pragma unroll
-            for (int jp = 0; jp < 8; ++jp) {
+            for (int jp = 0; jp < 16; ++jp) {
                 const float2 x = make_float2(__fmul_rn(s2, __uint_as_float(kq[jp] << 16)),
                                              __fmul_rn(s2, __uint_as_float(kq[jp] & 0xffff0000u)));
                 const float4 gb = G[jp];
@@ -1583,18 +1576,17 @@ __device__ __forceinline__ void epi_res_ln(const Args& ep, const float4* __restr
                 b[2 * jp] = __float_as_uint(t.x);
                 b[2 * jp + 1] = __float_as_uint(t.y);
             }
-            uint32_t w4[4];
-            pack_bytes16(w4, b);
-            if (h == 0) {
+            if (row_ok) {
+                uint32_t o[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) held[i] = w4[i];
-            } else if (row_ok) {
-                const uint32_t o[8] = {held[0], held[1], held[2], held[3], w4[0], w4[1], w4[2], w4[3]};
+                for (int i = 0; i < 8; ++i)
+                    o[i] = __byte_perm(__byte_perm(b[4 * i], b[4 * i + 1], 0x0040), __byte_perm(b[4 * i + 2], b[4 * i + 3], 0x0040), 0x5410);
                 stg256(o8 + c0, o);
+                if (ep.y_ctr != nullptr) {
+                    stg256(ep.y_ctr + row * N + n0 + c0, *reinterpret_cast<uint32_t(*)[8]>(&wc[0]));
+                    stg256(ep.y_ctr + row * N + n0 + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&wc[8]));
+                }
             }
-            if (row_ok && ep.y_ctr != nullptr) stg256(ep.y_ctr + row * N + n0 + c0 + 16 * h, wc);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) kq[i] = kq[i + 8];
         }
     }
 }
