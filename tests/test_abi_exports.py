@@ -116,3 +116,19 @@ def test_argument_errors_are_reported_before_any_device_work():
     assert lib.tq_probe_copy_f32(None, fake, 16, 0, None) == -1
     assert lib.tq_probe_copy_f32(fake, fake, 18, 0, None) == -1
     assert lib.tq_selftest_div(1, 0, 1, fake, None) == -1
+    # encoder chain plans: argument errors are reported before any CUDA call
+    import ctypes
+    handle = ctypes.c_void_p()
+    stage = tq_native.ChainStage()
+    stage.kind, stage.N, stage.K, stage.nseg = 1, 3072, 768, 1
+    arr = (tq_native.ChainStage * 1)(stage)
+    assert lib.tq_chain_plan_create(None, 1, 128, ctypes.byref(handle)) == -1
+    assert lib.tq_chain_plan_create(arr, 0, 128, ctypes.byref(handle)) == -1
+    assert lib.tq_chain_plan_create(arr, 1, 0, ctypes.byref(handle)) == -1
+    assert lib.tq_chain_plan_create(arr, 1, 128, ctypes.byref(handle)) == -4    # no LayerNorm stage: nothing fixes the cluster size
+    stage.kind, stage.N = 2, 1000                                                # LayerNorm stage: N must be a multiple of 192, <= 1536
+    arr = (tq_native.ChainStage * 1)(stage)
+    assert lib.tq_chain_plan_create(arr, 1, 128, ctypes.byref(handle)) == -4
+    assert handle.value is None
+    assert lib.tq_chain_plan_run(None, None) == -1
+    assert lib.tq_chain_plan_destroy(None) == 0

@@ -519,6 +519,60 @@ def test_engine_chain_kernel_matches_separate_kernels(hidden, heads, inter, laye
     assert out['2'][6] == out['0'][6] - 5 * layers + 1            # embedding + ONE encoder launch + pooler + classifier
 
 
+@pytest.mark.parametrize('M', [200, 384])
+def test_chain_plan_matches_single_kernels(M):
+    """tq_chain_plan_* through the binding on synthetic BERT-base stages, incl. a ragged last panel (M = 200: TMA zero-fills
+    the missing rows, stores are masked): every stage output bit-identical to the single-kernel entry points"""
+    ops = tq_native.ops()
+    g = torch.Generator(device='cpu').manual_seed(M)
+    D, I = 768, 3072
+    keep = []
+
+    def spec(scale, zp=None, signed=None, n=1):
+        d = torch.full((n,), scale, device=DEV)
+        z = None if zp is None else torch.full((n,), float(zp), device=DEV)
+        sg = None if signed is None else torch.tensor(signed, device=DEV)
+        keep.extend([d, z, sg])
+        return ops.spec(d, z, sg, 8)
+
+    def weight(N, K):
+        w8 = torch.randint(-128, 128, (N, K), generator=g).to(torch.int8).to(DEV)
+        return w8, w8.to(torch.int32).sum(dim=1, dtype=torch.int32).contiguous(), (torch.randn(N, generator=g) * 0.1).to(DEV)
+
+    u8 = lambda *sh: torch.randint(0, 256, sh, generator=g).to(torch.uint8).to(DEV)          # noqa: E731
+    c, x0 = u8(M, D), u8(M, D)
+    wg, wf, wh, wq = weight(D, D), weight(I, D), weight(D, I), weight(3 * D, D)
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.05 * torch.randn(D, generator=g)).to(DEV)
+    a_sp, w_sp, w3_sp = spec(0.02, 128), spec(0.001, None, True), spec(0.001, None, True, 3)
+    g_sp, u_sp, x_sp, f_sp, o3_sp = spec(0.06, 125), spec(0.07, 131), spec(0.03, 120), spec(0.04, 9), spec(0.05, 120, None, 3)
+    outs = []
+    for chained in (False, True):
+        x = x0.clone()
+        a, f = torch.zeros(M, D, dtype=torch.uint8, device=DEV), torch.zeros(M, I, dtype=torch.uint8, device=DEV)
+        qkv = torch.zeros(M, 3 * D, dtype=torch.bfloat16, device=DEV)
+        if chained:
+            cs = ops.chain_stage
+            plan = ops.chain_plan([
+                cs(2, c, wg[0], wg[1], wg[2], a, D, D, a_sp, w_sp, g_sp, 1, x, a_sp, u_sp, x_sp, gamma, beta, 1e-12),
+                cs(1, a, wf[0], wf[1], wf[2], f, I, D, x_sp, w_sp, f_sp),
+                cs(2, f, wh[0], wh[1], wh[2], x, D, I, f_sp, w_sp, g_sp, 1, a, x_sp, u_sp, a_sp, gamma, beta, 1e-12),
+                cs(0, x, wq[0], wq[1], wq[2], qkv, 3 * D, D, a_sp, w3_sp, o3_sp, 3)], M)
+            ops.chain_run(plan)
+            ops.chain_run(plan)                     # a plan is reusable (x is both residual of stage 1 and output of stage 3: run twice on
+            torch.cuda.synchronize()                # the single-kernel side too)
+            plan.close()
+        else:
+            for _ in range(2):
+                ops.linear_res_ln_i8(c, wg[0], wg[1], wg[2], M, D, D, a_sp, w_sp, 1, g_sp, x, a_sp, u_sp, gamma, beta, 1e-12, x_sp, a)
+                ops.linear_seg_i8(a, wf[0], wf[1], wf[2], M, I, D, x_sp, w_sp, f_sp, 1, 1, out_i8=f)
+                ops.linear_res_ln_i8(f, wh[0], wh[1], wh[2], M, D, I, f_sp, w_sp, 1, g_sp, a, x_sp, u_sp, gamma, beta, 1e-12, a_sp, x)
+                ops.linear_seg_i8(x, wq[0], wq[1], wq[2], M, 3 * D, D, a_sp, w3_sp, o3_sp, 3, 0, out_ctr=qkv)
+            torch.cuda.synchronize()
+        outs.append((a, f, x, qkv))
+    for k in range(4):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
 def test_engine_detects_reallocated_quantizer_buffers():
     """the engine's specs hold raw device pointers; a recalibration that re-allocates a quantizer's
     buffers must be detected instead of reading freed memory"""

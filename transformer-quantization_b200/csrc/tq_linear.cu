@@ -1350,66 +1350,13 @@ __device__ __forceinline__ void pack_bytes16(uint32_t (&w)[4], const uint32_t (&
 
 // ---- plain epilogue: y = Q(act(acc * cs + bias)) for one 128 x BN accumulator tile ---------------------
 // segment parameters sg[]: 0 cs, 1 s, 2 r, 3 clo, 4 chi, 5 zp + 1.5 * 2^23, 6 exact flag
+// Loop shape: a ROLLED loop over the 32-column slices of this warp's half of the tile, one 16-pair body, the next slice's
+// tcgen05.ld in flight behind it.  History (all measured): fully unrolled over the tile (2400 instructions = 39 KB with
+// GELU) 40-60 % of the samples stalled on `no_instruction` (profiles/r2_ncu_chain_layer0.json, first capture); an 8-pair
+// body lost 20 % on the GELU stage (too little independent work for the 12-deep dependent FFMA2 chain of a quantizer);
+// this form keeps the ILP of the unrolled one with a quarter of the code.
 template <int BN, int ACT, bool FAST, bool OUT8>
 __device__ __forceinline__ void epi_plain(const Args& ep, const float4* __restrict__ Pcol, const float* __restrict__ sg,
-                                          uint32_t tmem_tile, int half, int64_t row, bool row_ok, int64_t n0, int64_t N) {
-    // (persistent kernel, 2-3 tiles per CTA: here the fully unrolled slice loop with two register sets measured
-    // fastest -- 18.7 k cycles for the Q|K|V GEMM against 19.9 k for the compact forms, profiles/r2_trace_tiles_lean.txt)
-    constexpr int NIT = BN / 64;
-    const QReg q = qreg_of(sg[1], sg[2], sg[3], sg[4]);
-    const float2 cs2 = splat(sg[0]), off2 = splat(sg[5]);
-    unsigned char* o8 = OUT8 ? reinterpret_cast<unsigned char*>(ep.y_u8) + row * ep.ldc + n0 : nullptr;
-    __nv_bfloat16* oc = OUT8 ? nullptr : ep.y_ctr + row * ep.ldc + n0;
-    uint32_t va[32], vb[32];
-    tmem_ld32_nowait(tmem_tile + (uint32_t)(half * 32), va);
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        uint32_t (&v)[32] = (it & 1) ? vb : va;
-        uint32_t (&vn)[32] = (it & 1) ? va : vb;
-        tmem_ld_fence(v);
-        const int c0 = half * 32 + it * 64;
-        if (it + 1 < NIT) tmem_ld32_nowait(tmem_tile + (uint32_t)(c0 + 64), vn);
-        const float4* P = Pcol + (c0 >> 1);
-        uint32_t w[16], b[16];
-#pragma unroll
-        for (int jp = 0; jp < 16; ++jp) {
-            const float4 pp = P[jp];
-            const float2 a = make_float2(__int2float_rn((int)v[2 * jp] - __float_as_int(pp.z)),
-                                         __int2float_rn((int)v[2 * jp + 1] - __float_as_int(pp.w)));
-            float2 f = __ffma2_rn(a, cs2, make_float2(pp.x, pp.y));
-            f = act2<ACT>(f);
-            const float2 k = ctr2_t<FAST>(f, q);
-            if (OUT8) {
-                const float2 t = __fadd2_rn(k, off2);
-                b[2 * (jp & 7)] = __float_as_uint(t.x);
-                b[2 * (jp & 7) + 1] = __float_as_uint(t.y);
-                if ((jp & 7) == 7) {
-                    uint32_t w4[4];
-                    pack_bytes16(w4, b);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) w[(jp >> 3) * 4 + i] = w4[i];
-                }
-            } else {
-                w[jp] = pack_bf16(k);
-            }
-        }
-        if (row_ok) {
-            if (OUT8) {
-                stg256(o8 + c0, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
-            } else {
-                stg256(oc + c0, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
-                stg256(oc + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&w[8]));
-            }
-        }
-    }
-}
-
-// The same epilogue as a COMPACT loop: one body of 8 column pairs (~300 instructions with GELU) runs over the tile, the
-// next 32-column slice in flight behind it.  The ncu source view of the chain kernel (profiles/r2_ncu_chain_layer0.json)
-// shows 40-60 % of the samples of the unrolled GELU epilogue (2400 instructions = 39 KB per tile, streamed by eight
-// warps) stalled on `no_instruction`: straight-line code of that size does not fit the instruction caches.
-template <int BN, int ACT, bool FAST, bool OUT8>
-__device__ __forceinline__ void epi_plain_compact(const Args& ep, const float4* __restrict__ Pcol, const float* __restrict__ sg,
                                                   uint32_t tmem_tile, int half, int64_t row, bool row_ok, int64_t n0, int64_t N) {
     constexpr int NIT = BN / 64;
     const QReg q = qreg_of(sg[1], sg[2], sg[3], sg[4]);
@@ -2994,11 +2941,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
                         if (exact) epi_res_ln<BNL, false>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
                         else epi_res_ln<BNL, true>(ep, Pt, Pgb, sg, part, xs, tmem_tile, half, quarter, lane, row, row_ok, n0, N, r0, r1);
                     } else if (kind == 1) {
-                        if (exact) epi_plain_compact<BNF, 1, false, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
-                        else epi_plain_compact<BNF, 1, true, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                        if (exact) epi_plain<BNF, 1, false, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                        else epi_plain<BNF, 1, true, true>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
                     } else {
-                        if (exact) epi_plain_compact<BNL, 0, false, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
-                        else epi_plain_compact<BNL, 0, true, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                        if (exact) epi_plain<BNL, 0, false, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
+                        else epi_plain<BNL, 0, true, false>(ep, Pt, sg, tmem_tile, half, row, row_ok, n0, N);
                     }
                     tc_fence_before();
                     __syncwarp();
