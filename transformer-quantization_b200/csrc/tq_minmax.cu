@@ -64,6 +64,34 @@ __device__ void finalize(const MMWs& w, int64_t C, float* mn, float* mx, int64_t
     if (tid == 0) *w.ticket = 0u;
 }
 
+// Column kernels: ONE TICKET PER COLUMN BLOCK instead of one per launch -- the last CTA of a block's slabs decodes that
+// block's columns.  (A launch-wide ticket made 768 CTAs queue on one address: ~27 cycles per same-address atomic =
+// 10 us of a 25 us launch.)  The ticket lives in bits 8.. of the block's first NaN-flag word (bit 0 stays the flag), so
+// the workspace layout and size are unchanged; the decoding pass re-zeroes it with the flags.
+__device__ void finalize_colblock(const MMWs& w, int64_t c0, int64_t c1, float* mn, float* mx, uint32_t slabs) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        const uint32_t t = atomicAdd(w.nanf + c0, 256u) >> 8;
+        is_last = (t == slabs - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int nthr = blockDim.x * blockDim.y;
+    for (int64_t c = c0 + tid; c < c1; c += nthr) {
+        const uint32_t a = atomicExch(w.emin + c, 0u);
+        const uint32_t b = atomicExch(w.emax + c, 0u);
+        const uint32_t f = atomicExch(w.nanf + c, 0u) & 1u;
+        float vmin = ord2f(~a), vmax = ord2f(b);
+        if (f) vmin = vmax = __int_as_float(0x7fc00000);
+        mn[c] = vmin;
+        mx[c] = vmax;
+    }
+}
+
 __device__ __forceinline__ void acc4(const float4& v, float& mn, float& mx, bool& nan) {
     mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
     mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
@@ -159,6 +187,19 @@ minmax_cols_vec_kernel(const float* __restrict__ x, int64_t rows, int32_t C, int
         int64_t r1 = r0 + rows_per_slab;
         if (r1 > rows) r1 = rows;
         int64_t r = r0 + threadIdx.y;
+        for (; r + 28 < r1; r += 32) {                 // eight 16-byte loads in flight per thread (~35 KB per SM needed)
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ld_stream(xv + (r + 4 * u) * CV + vc);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                mn.x = fminf(mn.x, v[u].x); mn.y = fminf(mn.y, v[u].y);
+                mn.z = fminf(mn.z, v[u].z); mn.w = fminf(mn.w, v[u].w);
+                mx.x = fmaxf(mx.x, v[u].x); mx.y = fmaxf(mx.y, v[u].y);
+                mx.z = fmaxf(mx.z, v[u].z); mx.w = fmaxf(mx.w, v[u].w);
+                nan |= (v[u].x != v[u].x) | (v[u].y != v[u].y) | (v[u].z != v[u].z) | (v[u].w != v[u].w);
+            }
+        }
         for (; r + 12 < r1; r += 16) {
             float4 v[4];
 #pragma unroll
@@ -220,7 +261,8 @@ minmax_cols_vec_kernel(const float* __restrict__ x, int64_t rows, int32_t C, int
             if (n3) atomicOr(w.nanf + c + 3, 1u);
         }
     }
-    finalize(w, C, mn_out, mx_out, 1, gridDim.x * gridDim.y);
+    const int64_t c0 = (int64_t)blockIdx.x * 256;
+    finalize_colblock(w, c0, c0 + 256 < C ? c0 + 256 : C, mn_out, mx_out, gridDim.y);
 }
 
 // ---- per-axis, general [outer, C, inner]: one CTA per (channel, outer-split) --------------------
@@ -377,8 +419,14 @@ set_range_sym_kernel(const float* __restrict__ xmin, const float* __restrict__ x
     if (threadIdx.x == 0) *is_signed = sg ? 1 : 0;
 }
 
-static int64_t slab_rows(int64_t rows, int64_t col_blocks, int unit) {
-    const int64_t target_ctas = (int64_t)sm_count() * 8;
+// Rows per CTA of the column kernels.  Every CTA ends with one atomic on the shared ticket and two on each of its
+// columns' words, and same-address L2 atomics serialise (~27 cycles each): 768 CTAs on a 12.6 MB activation spent
+// ~10 us queueing on the ticket alone (22.5 us per launch).  So the CTA count follows the tensor size -- >= 128 KB of
+// input per CTA, between one CTA per SM and eight (and the vector kernel keeps one ticket per column block).
+static int64_t slab_rows(int64_t rows, int64_t col_blocks, int unit, int64_t total_bytes) {
+    int64_t target_ctas = total_bytes / 131072;
+    const int64_t lo = sm_count(), hi = (int64_t)sm_count() * 8;
+    target_ctas = target_ctas < lo ? lo : (target_ctas > hi ? hi : target_ctas);
     int64_t slabs = target_ctas / (col_blocks > 0 ? col_blocks : 1);
     if (slabs < 1) slabs = 1;
     int64_t rps = (rows + slabs - 1) / slabs;
@@ -447,7 +495,11 @@ int tq_minmax_f32(const float* x, int64_t n, float* out, void* ws, size_t ws_byt
     const int vec_ok = tq::aligned16(x) ? 1 : 0;
     const int64_t per_block = (int64_t)tq::kRThreads * (vec_ok ? 4 * tq::kRUnroll : 1);
     int64_t blocks = (n + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)tq::sm_count() * 4;
+    // CTA count by tensor size (>= 64 KB per CTA, one to four CTAs per SM): every CTA queues on the shared ticket and on
+    // the two result words with same-address atomics (see slab_rows)
+    int64_t cap = n * 4 / 65536;
+    const int64_t lo = tq::sm_count(), hi = (int64_t)tq::sm_count() * 4;
+    cap = cap < lo ? lo : (cap > hi ? hi : cap);
     if (blocks > cap) blocks = cap;
     tq::minmax_tensor_kernel<<<(int)blocks, tq::kRThreads, 0, (cudaStream_t)stream>>>(x, n, vec_ok, out, ws);
     return tq::launch_status();
@@ -463,12 +515,12 @@ int tq_minmax_axis_f32(const float* x, int64_t outer, int64_t C, int64_t inner, 
         const int64_t rows = outer;
         if (tq::aligned16(x) && (C & 3) == 0) {
             const int64_t colb = ((C >> 2) + 63) / 64;
-            const int64_t rps = tq::slab_rows(rows, colb, 16);
+            const int64_t rps = tq::slab_rows(rows, colb, 32, rows * C * 4);
             dim3 grid((unsigned)colb, (unsigned)((rows + rps - 1) / rps));
             tq::minmax_cols_vec_kernel<<<grid, dim3(64, 4), 0, st>>>(x, rows, (int32_t)C, rps, mn, mx, ws);
         } else {
             const int64_t colb = (C + tq::kRThreads - 1) / tq::kRThreads;
-            const int64_t rps = tq::slab_rows(rows, colb, 8);
+            const int64_t rps = tq::slab_rows(rows, colb, 8, rows * C * 4);
             dim3 grid((unsigned)colb, (unsigned)((rows + rps - 1) / rps));
             tq::minmax_cols_scalar_kernel<<<grid, tq::kRThreads, 0, st>>>(x, rows, C, rps, mn, mx, ws);
         }
