@@ -2509,6 +2509,7 @@ struct Params {
     int64_t M;
     int32_t n;
     long long* trace;                    // tools: [CTA][stage][4] clock64 stamps (stage top, first accumulator, epilogue end, past barrier)
+    int32_t gpu_fence;                   // 1: __threadfence() at every stage end as well
 };
 
 __device__ __forceinline__ int bn_of(int kind) { return kind == 1 ? BNF : BNL; }
@@ -2960,8 +2961,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
             }
             if (tr != nullptr) tr[s * 4 + 2] = clock64();
             if (s + 1 < nst) {
-                // the next stage reads this stage's panel through TMA (async proxy): make the stores visible first
-                __threadfence();
+                // the next stage reads this stage's panel through TMA (async proxy) issued by a thread of this cluster:
+                // generic -> async proxy fence by every writer, then the cluster barrier's release / acquire pair.  The
+                // gpu-scope fence in front of it is belt and braces: TQ_CHAIN_GPU_FENCE=0 drops it (300 forwards of
+                // tools/stress_chain.py bit-identical without it, step -0.7 %) -- kept by default
+                if (P.gpu_fence) __threadfence();
                 asm volatile("fence.proxy.async.global;" ::: "memory");
                 cluster_sync_all();
             }
@@ -3280,6 +3284,8 @@ static int chain_plan_run(const ChainPlan* plan, cudaStream_t st) {
     P.M = plan->M;
     P.n = plan->n;
     P.trace = nullptr;
+    static const int gpu_fence = [] { const char* e = getenv("TQ_CHAIN_GPU_FENCE"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+    P.gpu_fence = gpu_fence;
     if (const char* env = getenv("TQ_LINEAR_TRACE_CHAIN"))         // tools/trace_chain.py: device pointer of a zeroed int64 buffer
         P.trace = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
     static bool attr_set = false;
