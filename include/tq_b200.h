@@ -57,7 +57,7 @@ int         tq_version(void);              /* ABI version: 1 = inference path; 2
                                               * (tq_qdq_bwd_f32, tq_adaround_*) and tq_probe_copy_f32; 3 adds
                                               * tq_linear_seg_qdq_i8, tq_linear_nonorm_qdq_i8, tq_calib_finalize_f32,
                                               * tq_attention_pad_qdq_i8 and the tq_*_peg_* entry points; 4 (current) adds the
-                                              * encoder chain (tq_chain_plan_create / _run / _destroy) and the packed-path
+                                              * encoder chain (tq_chain_plan_create / _run / _destroy), tq_head_qdq_i8 and the packed-path
                                               * counters of tq_selftest_div (uint64[5]) */
 const char* tq_error_string(int code);     /* static string for TQ_E* / cudaError_t */
 int         tq_device_sm_count(void);      /* SM count of the current device (148 on B200) */
@@ -297,6 +297,15 @@ int tq_linear_peg_res_ln_qdq_i8(const void* a_i8, const void* w_i8, const int32_
                                 tq_qspec out2_q, int32_t out2_params, const float* ln_gamma_q,
                                 const float* ln_beta, float ln_eps, tq_qspec ln_q, int32_t ln_params,
                                 int64_t seg_width, void* stream);
+/* Classification head in one launch (reference models/quantized_bert.py:525-560 -- QuantizedBertPooler on the first token,
+ * then the classifier QuantLinear): row b of the input = x_i8 + b * row_stride (x_int bytes, hidden size D, D % 128 == 0,
+ * D <= 1024); pooler [D, D] int8 + tanh + QDQ(pool_q), classifier [>= L, D] int8 + QDQ(cls_q); logits [B, ldl] receive the
+ * DEQUANTIZED classifier outputs.  a_q / pool_q must be unsigned grids (zero_float != NULL).  Same arithmetic as two
+ * tq_linear_qdq_i8 calls (activation 3, then 0): bit-identical. */
+int tq_head_qdq_i8(const void* x_i8, int64_t row_stride, int32_t B, int32_t D, int32_t L, const void* wp_i8, const int32_t* wp_rowsum,
+                   const float* bp, tq_qspec a_q, tq_qspec wp_q, tq_qspec pool_q, const void* wc_i8, const int32_t* wc_rowsum,
+                   const float* bc, tq_qspec wc_q, tq_qspec cls_q, float* logits, int64_t ldl, void* stream);
+
 /* The ENCODER CHAIN: a list of stages executed by ONE launch (reference models/quantized_bert.py:135-291, all layers).
  * A cluster of N_hidden / 192 CTAs carries one 128-row panel (= one sequence of 128 tokens) through every stage: the A
  * operand of stage i + 1 is what the same cluster wrote in stage i, so only cluster barriers separate the stages -- the

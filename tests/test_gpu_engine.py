@@ -386,7 +386,7 @@ def test_engine_matches_module_path(n_bits, use_mask):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, eager)
-        assert n_launch == 1 + per_layer * 2 + 2
+        assert n_launch == 1 + per_layer * 2 + (1 if (eng.head and i8) else 2)      # embedding, layers, head (int8 mode: one launch, tq_head_qdq_i8)
 
 
 # ---- lean int8 kernels (tq_linear_seg_qdq_i8, lean form of tq_linear_res_ln_qdq_i8) ------------------------------
@@ -517,6 +517,29 @@ def test_engine_chain_kernel_matches_separate_kernels(hidden, heads, inter, laye
             assert torch.equal(out['0'][k], out[chain][k]), (chain, k)
     assert out['1'][6] == out['0'][6] - 3 * layers + 1            # four launches per layer become one (the last: three)
     assert out['2'][6] == out['0'][6] - 5 * layers + 1            # embedding + ONE encoder launch + pooler + classifier
+
+
+@pytest.mark.parametrize('hidden,heads,inter', [(256, 4, 512), (768, 12, 3072)])
+def test_engine_head_kernel_matches_gemm_path(hidden, heads, inter, monkeypatch):
+    """tq_head_qdq_i8 (first token -> pooler + tanh + QDQ -> classifier + QDQ, one dp4a launch) vs the same two layers through
+    tq_linear_qdq_i8: identical arithmetic, bit-identical logits"""
+    from engine.fused import FusedBertEngine
+    model = _wide_model(DEV, hidden, heads, inter, 1)
+    g = torch.Generator().manual_seed(4)
+    ids = [torch.randint(0, 2000, (6, 128), generator=g).to(DEV) for _ in range(2)]
+    mask = torch.ones(6, 128, dtype=torch.int64, device=DEV)
+    model.set_quant_state(True, True)
+    with torch.no_grad():
+        model(ids[0], mask)
+        model.fix_ranges()
+    out = {}
+    for head in ('0', '1'):
+        monkeypatch.setenv('TQ_ENGINE_HEAD', head)
+        eng = FusedBertEngine(model, 6, 128)
+        assert eng.head == (head == '1')
+        out[head] = eng(ids[1], mask).clone()
+    assert torch.equal(out['0'], out['1'])
+    assert float(out['1'].abs().max()) > 0.0
 
 
 @pytest.mark.parametrize('M', [200, 384])

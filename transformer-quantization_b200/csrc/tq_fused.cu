@@ -518,6 +518,129 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// classification head: first token -> pooler (dense + tanh + QDQ) -> classifier (dense + QDQ)   (reference
+// models/quantized_bert.py:525-560: QuantizedBertPooler, then the classifier QuantLinear).  B x hidden x hidden
+// int8 products: two launches of the persistent GEMM (TMEM allocation, TMA ring, 128-row tiles for 32 rows) and a
+// gather kernel took ~27 us of a 1 ms step; this is one CTA per sequence on the CUDA cores (dp4a), a warp per output
+// column with coalesced weight rows.  Same arithmetic as tq_linear_qdq_i8's generic epilogue: exact integer
+// accumulation, fma(acc - zp * rowsum, s_a * s_w, bias), tanhf, clamp(rint(RN(. / s))).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kHeadThreads = 1024;
+constexpr int kHeadIlp = 4;              // output columns per warp iteration: their weight rows are requested together (L2 latency)
+constexpr int kHeadMaxWords = 8;            // hidden <= 1024: <= 8 packed words of the input row per lane
+
+struct HeadArgs {
+    const unsigned char* x;       // x_int bytes; row b of the head input = x + b * row_stride
+    int64_t row_stride;
+    int32_t D, L;                 // hidden size, classifier outputs
+    const int8_t* wp; const int32_t* wp_rowsum; const float* bp;     // pooler [D, D]
+    tq_qspec a_q, wp_q, pool_q;
+    const int8_t* wc; const int32_t* wc_rowsum; const float* bc;     // classifier [>= L, D]
+    tq_qspec wc_q, cls_q;
+    float* logits;                // [B, ldl] dequantized classifier outputs
+    int64_t ldl;
+};
+
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8, uint32_t b_s8, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8), "r"(b_s8), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_uu(uint32_t a_u8, uint32_t b_u8, int c) {
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8), "r"(b_u8), "r"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a) {
+    __shared__ __align__(16) uint32_t xs[kHeadMaxWords * 32], ps[kHeadMaxWords * 32];
+    __shared__ float qsm[5][8];
+    __shared__ int wsigned[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kHeadThreads / 32;
+    const int words = a.D >> 2, per_lane = words >> 5;
+    if (warp == 0 && lane < 5) {                      // quantizers are calibration constants: resolved before the dependency wait
+        const tq_qspec& q = lane == 0 ? a.a_q : lane == 1 ? a.wp_q : lane == 2 ? a.pool_q : lane == 3 ? a.wc_q : a.cls_q;
+        float lo, hi;
+        grid_of(q, lo, hi);
+        const QP p = resolve(q, 0, lo, hi);
+        float* o = qsm[lane];
+        o[0] = p.scale; o[1] = p.zp; o[2] = p.lo; o[3] = p.hi; o[4] = p.rcp; o[5] = __int_as_float(p.exact);
+        if (lane == 1 || lane == 3) wsigned[lane >> 1] = (q.zero_float == nullptr && q.is_signed != nullptr && *q.is_signed) ? 1 : 0;
+    }
+    pdl_trigger();
+    pdl_wait();                                       // x is produced by the previous kernel
+    const uint32_t* xrow = reinterpret_cast<const uint32_t*>(a.x + (int64_t)blockIdx.x * a.row_stride);
+    for (int i = threadIdx.x; i < words; i += kHeadThreads) xs[i] = xrow[i];
+    __syncthreads();
+    const QP qa = load_qp(qsm[0]), qwp = load_qp(qsm[1]), qpool = load_qp(qsm[2]), qwc = load_qp(qsm[3]), qcls = load_qp(qsm[4]);
+    uint32_t xw[kHeadMaxWords];
+#pragma unroll
+    for (int i = 0; i < kHeadMaxWords; ++i) xw[i] = i < per_lane ? xs[lane + 32 * i] : 0u;
+    {   // pooler: tanh(dense(x)) -> QDQ -> x_int bytes in shared memory
+        const float cs = __fmul_rn(qa.scale, qwp.scale);
+        const int zp = (int)qa.zp;
+        const bool sg = wsigned[0] != 0;
+        unsigned char* pb = reinterpret_cast<unsigned char*>(ps);
+        for (int n0 = warp * kHeadIlp; n0 < a.D; n0 += nwarps * kHeadIlp) {
+            uint32_t w[kHeadIlp][kHeadMaxWords];
+#pragma unroll
+            for (int u = 0; u < kHeadIlp; ++u) {
+                const int n = n0 + u < a.D ? n0 + u : a.D - 1;
+                const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.wp + (int64_t)n * a.D);
+#pragma unroll
+                for (int i = 0; i < kHeadMaxWords; ++i)
+                    if (i < per_lane) w[u][i] = __ldg(wrow + lane + 32 * i);
+            }
+            int acc[kHeadIlp];
+#pragma unroll
+            for (int u = 0; u < kHeadIlp; ++u) {
+                acc[u] = 0;
+#pragma unroll
+                for (int i = 0; i < kHeadMaxWords; ++i)
+                    if (i < per_lane) acc[u] = sg ? dp4a_us(xw[i], w[u][i], acc[u]) : dp4a_uu(xw[i], w[u][i], acc[u]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < kHeadIlp; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            if (lane < kHeadIlp && n0 + lane < a.D) {         // lane u finishes output n0 + u
+                const int n = n0 + lane;
+                int mine = acc[0];
+#pragma unroll
+                for (int u = 1; u < kHeadIlp; ++u) mine = lane == u ? acc[u] : mine;
+                const float pre = __fmaf_rn(__int2float_rn(mine - zp * __ldg(a.wp_rowsum + n)), cs, a.bp != nullptr ? __ldg(a.bp + n) : 0.0f);
+                pb[n] = (unsigned char)(int)quant_int(tanhf(pre), qpool);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kHeadMaxWords; ++i) xw[i] = i < per_lane ? ps[lane + 32 * i] : 0u;
+    {   // classifier: dense(pooled) -> QDQ -> dequantized logits
+        const float cs = __fmul_rn(qpool.scale, qwc.scale);
+        const int zp = (int)qpool.zp;
+        const bool sg = wsigned[1] != 0;
+        for (int n = warp; n < a.L; n += nwarps) {
+            const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.wc + (int64_t)n * a.D);
+            int acc = 0;
+#pragma unroll
+            for (int i = 0; i < kHeadMaxWords; ++i)
+                if (i < per_lane) {
+                    const uint32_t w = __ldg(wrow + lane + 32 * i);
+                    acc = sg ? dp4a_us(xw[i], w, acc) : dp4a_uu(xw[i], w, acc);
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                const float pre = __fmaf_rn(__int2float_rn(acc - zp * __ldg(a.wc_rowsum + n)), cs, a.bc != nullptr ? __ldg(a.bc + n) : 0.0f);
+                a.logits[(int64_t)blockIdx.x * a.ldl + n] = __fmul_rn(qcls.scale, __fsub_rn(quant_int(pre, qcls), qcls.zp));
+            }
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -614,6 +737,31 @@ int tq_attention_pad_qdq_i8(const void* qkv_ctr_bf16, void* c_i8, int32_t B, int
     if (c_i8 == nullptr) return TQ_EINVAL;
     return attention_impl(qkv_ctr_bf16, nullptr, c_i8, B, T, H, head_dim, q_q, k_q, v_q, s_q, p_q, c_q, mask, stream, 1, 1,
                           true_head_dim);
+}
+
+int tq_head_qdq_i8(const void* x_i8, int64_t row_stride, int32_t B, int32_t D, int32_t L, const void* wp_i8, const int32_t* wp_rowsum,
+                   const float* bp, tq_qspec a_q, tq_qspec wp_q, tq_qspec pool_q, const void* wc_i8, const int32_t* wc_rowsum,
+                   const float* bc, tq_qspec wc_q, tq_qspec cls_q, float* logits, int64_t ldl, void* stream) {
+    using namespace tq::fused;
+    if (x_i8 == nullptr || wp_i8 == nullptr || wp_rowsum == nullptr || wc_i8 == nullptr || wc_rowsum == nullptr || logits == nullptr) return TQ_EINVAL;
+    if (B < 1 || L < 1 || ldl < L || row_stride < D) return TQ_EINVAL;
+    if (D < 128 || (D & 127) != 0 || D > 128 * kHeadMaxWords) return TQ_EUNSUPPORTED;
+    const tq_qspec* all[5] = {&a_q, &wp_q, &pool_q, &wc_q, &cls_q};
+    for (int i = 0; i < 5; ++i) {
+        if (int e = tq::check_qspec(*all[i])) return e;
+        if (all[i]->n_bits > 8) return TQ_EUNSUPPORTED;
+    }
+    if (a_q.zero_float == nullptr || pool_q.zero_float == nullptr) return TQ_EUNSUPPORTED;      // x_int bytes: unsigned activation grids
+    if ((reinterpret_cast<uintptr_t>(x_i8) & 3u) != 0 || (row_stride & 3) != 0 || (reinterpret_cast<uintptr_t>(wp_i8) & 3u) != 0 ||
+        (reinterpret_cast<uintptr_t>(wc_i8) & 3u) != 0)
+        return TQ_EALIGN;
+    HeadArgs a;
+    a.x = static_cast<const unsigned char*>(x_i8); a.row_stride = row_stride; a.D = D; a.L = L;
+    a.wp = static_cast<const int8_t*>(wp_i8); a.wp_rowsum = wp_rowsum; a.bp = bp;
+    a.a_q = a_q; a.wp_q = wp_q; a.pool_q = pool_q;
+    a.wc = static_cast<const int8_t*>(wc_i8); a.wc_rowsum = wc_rowsum; a.bc = bc;
+    a.wc_q = wc_q; a.cls_q = cls_q; a.logits = logits; a.ldl = ldl;
+    return tq::launch_pdl(head_kernel, dim3((unsigned)B), dim3(kHeadThreads), 0, (cudaStream_t)stream, 1, a);
 }
 
 static int ln_common(tq::fused::LnArgs& a, bool embed, void* stream) {

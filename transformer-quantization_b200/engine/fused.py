@@ -225,11 +225,15 @@ class FusedBertEngine:
             self.f8 = torch.empty(M, cfg.intermediate_size, **u8)
             self.first8 = torch.empty(batch, D, **u8)
             self.pooled8 = torch.empty(batch, D, **u8)
+            self.logits32 = torch.empty(batch, self.w_cls.N, dtype=torch.float32, device=dev)
         self.ffn_in_bf16 = os.environ.get('TQ_ENGINE_FFN_IN_BF16', '1') != '0'
         # lean int8 kernels (tq_linear_seg_qdq_i8 + the lean form of tq_linear_res_ln_qdq_i8): shapes they cover
         self.lean = (self.i8 and os.environ.get('TQ_ENGINE_LEAN', '1') != '0' and D % 128 == 0
                      and cfg.intermediate_size % 128 == 0
                      and all(st.q.n_bits <= 8 for d in self.layers for st in (d['q'], d['k'], d['v'], d['f'])))
+        # classification head (first token -> pooler -> classifier) as one dp4a kernel; needs per-tensor weight quantizers
+        self.head = (self.i8 and os.environ.get('TQ_ENGINE_HEAD', '1') != '0' and D % 128 == 0 and D <= 1024
+                     and self.w_pool.nseg == 1 and self.w_cls.nseg == 1)
         # chain kernel (tq_chain_plan_*): a cluster of D / 192 CTAs carries one sequence through a list of stages.
         #   TQ_ENGINE_CHAIN=1 (default)  one launch per layer for the four GEMM stages (attention-output + LN, FFN-in, FFN-out
         #                                + LN, next Q|K|V), attention as its own kernel (three CTAs per SM hide its latencies)
@@ -430,13 +434,18 @@ class FusedBertEngine:
                                  1 if lean else w.N, d['h'].spec, a,
                                  d['x'].spec, d['y'].spec, g2, b2, e2, d['z'].spec, x)
             x_site = d['z']
-        self.first8.copy_(x.view(B, T, D)[:, 0])                         # pooler input: first token
-        w = self.w_pool
-        ops.linear_i8(self.first8, w.grid8, w.rowsum, w.bias, B, w.N, w.K, x_site.spec, w.spec, w.N, 3, self.pool_out.spec,
-                      1, out_i8=self.pooled8)
-        w = self.w_cls
-        logits = ops.linear_i8(self.pooled8, w.grid8, w.rowsum, w.bias, B, w.N, w.K, self.pool_out.spec, w.spec, w.N, 0,
-                               self.cls_out.spec, 1, want_f32=True)
+        if self.head:            # first token -> pooler -> classifier in one launch
+            wp, wc = self.w_pool, self.w_cls
+            logits = ops.head_i8(x, T * D, B, D, wc.N, wp.grid8, wp.rowsum, wp.bias, x_site.spec, wp.seg_spec, self.pool_out.spec,
+                                 wc.grid8, wc.rowsum, wc.bias, wc.seg_spec, self.cls_out.spec, self.logits32)
+        else:
+            self.first8.copy_(x.view(B, T, D)[:, 0])                     # pooler input: first token
+            w = self.w_pool
+            ops.linear_i8(self.first8, w.grid8, w.rowsum, w.bias, B, w.N, w.K, x_site.spec, w.spec, w.N, 3, self.pool_out.spec,
+                          1, out_i8=self.pooled8)
+            w = self.w_cls
+            logits = ops.linear_i8(self.pooled8, w.grid8, w.rowsum, w.bias, B, w.N, w.K, self.pool_out.spec, w.spec, w.N, 0,
+                                   self.cls_out.spec, 1, want_f32=True)
         logits = logits[:, :self.num_labels]
         if self.num_labels == 1:
             logits = torch.clamp(logits, 0.0, 5.0)

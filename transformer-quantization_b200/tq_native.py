@@ -134,6 +134,8 @@ SIGNATURES = {
     'tq_linear_seg_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p,
                                             ctypes.c_void_p, _i64, _i64, _i64, QSpec, QSpec, QSpec, _i32, _i32, _i64,
                                             ctypes.c_void_p]),
+    'tq_head_qdq_i8': (ctypes.c_int, [ctypes.c_void_p, _i64, _i32, _i32, _i32, ctypes.c_void_p, ctypes.c_void_p, _c_f32p, QSpec, QSpec, QSpec,
+                                      ctypes.c_void_p, ctypes.c_void_p, _c_f32p, QSpec, QSpec, ctypes.c_void_p, _i64, ctypes.c_void_p]),
     'tq_chain_plan_create': (ctypes.c_int, [ctypes.POINTER(ChainStage), _i32, _i64, ctypes.POINTER(ctypes.c_void_p)]),
     'tq_chain_plan_run': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'tq_chain_plan_destroy': (ctypes.c_int, [ctypes.c_void_p]),
@@ -554,6 +556,15 @@ class CudaOps:
         st.a_q, st.w_q, st.res_q, st.out2_q, st.ln_q, st.out_q = q_spec, k_spec, v_spec, s_spec, p_spec, c_spec
         st._flops = 4 * 128 * int(hidden)               # per row: QK^T and PV over 128 keys
         return st
+
+    def head_i8(self, x_i8, row_stride, B, D, L, wp_i8, wp_rowsum, bp, a_spec, wp_spec, pool_spec, wc_i8, wc_rowsum, bc, wc_spec,
+                cls_spec, logits):
+        """tq_head_qdq_i8: first token -> pooler (tanh, QDQ) -> classifier (QDQ) in one launch; logits [B, ldl] fp32"""
+        _chk_cuda(x_i8, wp_i8, wp_rowsum, bp, wc_i8, wc_rowsum, bc, logits)
+        self._run('linear_qdq', 2 * B * D * (D + L), 1, self.lib.tq_head_qdq_i8, x_i8.data_ptr(), int(row_stride), int(B), int(D), int(L),
+                  wp_i8.data_ptr(), wp_rowsum.data_ptr(), _ptr(bp), a_spec, wp_spec, pool_spec, wc_i8.data_ptr(), wc_rowsum.data_ptr(),
+                  _ptr(bc), wc_spec, cls_spec, logits.data_ptr(), logits.shape[1], _stream())
+        return logits
 
     def chain_plan(self, stages, M):
         """tq_chain_plan_create: descriptors of a stage list in device memory (fixed buffers); run with chain_run"""
