@@ -2482,7 +2482,8 @@ struct alignas(16) StageTail {           // everything but the tensor maps: copi
     int64_t N, K;                        // kind 3: N = hidden size, K = heads
     int32_t kind, tiles;                 // tiles (kind 3: heads) of this stage per CTA
     uint32_t idesc;                      // kinds 0-2: the kind::i8 instruction descriptor (operand signedness resolved by the host)
-    int32_t pad;
+    int32_t ovl;                         // 1: GELU stage whose successor (ovl == 2, a LayerNorm stage with K = this N) starts its
+                                         // main loop on the columns of this stage's first tiles while the last tile is in its epilogue
 };
 static_assert(sizeof(StageTail) % 16 == 0, "stage tail is copied in 16-byte pieces");
 struct alignas(64) StageDesc {
@@ -2522,6 +2523,26 @@ __device__ __forceinline__ QP load_qp(const float* o) {
     QP p;
     p.scale = o[0]; p.zp = o[1]; p.lo = o[2]; p.hi = o[3]; p.rcp = o[4]; p.exact = __float_as_int(o[5]);
     return p;
+}
+
+// Overlapped pair (FFN-in + GELU -> FFN-out + LayerNorm): CTA c, tile j of the GELU stage produces the k-blocks
+// (c T + j) * 2 + {0, 1} of the next stage's A operand.  Consumption order of the next stage: first the k-blocks of every
+// member's tiles 0 .. T - 2 (ready at the MID barrier, after the epilogue of tile T - 2), then those of the last tiles.
+__device__ __forceinline__ int ovl_kb(int i, int T, int n_early) {
+    int cc, j, h;
+    if (i < n_early) {
+        const int per = (T - 1) * 2;
+        cc = i / per;
+        const int r = i - cc * per;
+        j = r >> 1;
+        h = r & 1;
+    } else {
+        const int r = i - n_early;
+        cc = r >> 1;
+        j = T - 1;
+        h = r & 1;
+    }
+    return (cc * T + j) * 2 + h;
 }
 
 // Measured and dropped (profiles/r2_trace_chain_mcast.txt, r2_trace_chain_12warps.txt): (a) TMA-multicasting the A
@@ -2614,6 +2635,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
         p_pre = 0;
         const int kind = S.t.kind;
         if (ATT && kind == 3) return;
+        if (S.t.ovl == 2) return;                     // its first k-blocks were requested whole inside the stage before
         const int bn = bn_of(kind);
         const int num_kb = (int)(S.t.K / 128);
         const uint32_t bytes = (uint32_t)(BM * 128 + bn * 128);
@@ -2650,6 +2672,21 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
                         tma_load_2d<1>(sa + 32768, &G.map_a, 2 * D + h * 64, (int32_t)m0, full_bar(p_stage));
                         if (++p_stage == kRing) { p_stage = 0; p_phase ^= 1u; }
                     }
+                } else if (S.ovl == 2) {
+                    // second part of an overlapped pair: the k-blocks of the predecessor's LAST tiles (the early ones went
+                    // out before the stage boundary, see below)
+                    const int Tp = tails[(s - 1) & 1].tiles, total = (int)(S.K / 128), n_early = (int)csize * (Tp - 1) * 2;
+                    const uint32_t bytes = (uint32_t)(BM * 128 + BNL * 128);
+                    const int32_t n0 = (int32_t)(crank * BNL);
+                    for (int i = n_early; i < total; ++i) {
+                        const int kb = ovl_kb(i, Tp, n_early);
+                        const uint32_t sa = base + p_stage * kStageBytes;
+                        mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
+                        mbar_expect_tx(full_bar(p_stage), bytes);
+                        tma_load_2d<1>(sa + BM * 128, &G.map_w, kb * 128, n0, full_bar(p_stage));
+                        tma_load_2d<1>(sa, &G.map_a, kb * 128, (int32_t)m0, full_bar(p_stage));
+                        if (++p_stage == kRing) { p_stage = 0; p_phase ^= 1u; }
+                    }
                 } else {
                     const int bn = bn_of(kind);
                     const int num_kb = (int)(S.K / 128);
@@ -2668,9 +2705,32 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
                         }
                     }
                 }
-                if (s + 1 < nst) preissue_w(s + 1);
+                if (s + 1 < nst && S.ovl != 1) preissue_w(s + 1);
             }
             __syncwarp();
+            if (S.ovl == 1) {
+                // overlapped pair, first part: after the MID barrier (every member has written its tiles 0 .. T - 2) the
+                // successor's main loop starts on those columns -- under the epilogue of this stage's last tile
+                cluster_sync_all();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    const StageDesc& GN = ST[s + 1];
+                    const int n_early = (int)csize * (S.tiles - 1) * 2;
+                    const uint32_t bytes = (uint32_t)(BM * 128 + BNL * 128);
+                    const int32_t n0 = (int32_t)(crank * BNL);
+                    for (int i = 0; i < n_early; ++i) {
+                        const int kb = ovl_kb(i, S.tiles, n_early);
+                        const uint32_t sa = base + p_stage * kStageBytes;
+                        mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
+                        mbar_expect_tx(full_bar(p_stage), bytes);
+                        tma_load_2d<1>(sa + BM * 128, &GN.map_w, kb * 128, n0, full_bar(p_stage));
+                        tma_load_2d<1>(sa, &GN.map_a, kb * 128, (int32_t)m0, full_bar(p_stage));
+                        if (++p_stage == kRing) { p_stage = 0; p_phase ^= 1u; }
+                    }
+                    p_pre = 0;
+                }
+                __syncwarp();
+            }
             if (kind == 2) cluster_sync_all();                // the stage's LayerNorm statistics exchange
             if (s + 1 < nst) {
                 cluster_sync_all();                           // stage boundary: the panel of stage s is complete
@@ -2722,6 +2782,23 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
                     sj = sn;
                     aj = an;
                 }
+            } else if (lane == 0 && S.ovl == 2) {
+                // second part of an overlapped pair: the accumulator already holds the early k-blocks
+                const int Tp = tails[(s - 1) & 1].tiles, total = (int)(S.K / 128), n_early = (int)csize * (Tp - 1) * 2;
+                const uint32_t idesc = S.idesc;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BNF);
+                for (int i = n_early; i < total; ++i) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * kStageBytes;
+                    const uint64_t adesc = make_desc_sw128(sa), bdesc = make_desc_sw128(sa + BM * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                    tc_commit<1>(empty_bar(stage));
+                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit<1>(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             } else if (lane == 0) {
                 const int bn = bn_of(kind);
                 const int num_kb = (int)(S.K / 128);
@@ -2747,6 +2824,28 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
             }
             // (the other lanes follow the ring / accumulator counters: they do not use them)
             __syncwarp();
+            if (S.ovl == 1) {
+                cluster_sync_all();                           // MID barrier of an overlapped pair
+                if (lane == 0) {                              // the successor's early k-blocks into the free accumulator
+                    const int n_early = (int)csize * (S.tiles - 1) * 2;
+                    const uint32_t idesc = ST[s + 1].t.idesc;
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BNF);
+                    for (int i = 0; i < n_early; ++i) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * kStageBytes;
+                        const uint64_t adesc = make_desc_sw128(sa), bdesc = make_desc_sw128(sa + BM * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+                        tc_commit<1>(empty_bar(stage));
+                        if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                __syncwarp();
+            }
             if (kind == 2) cluster_sync_all();
             if (s + 1 < nst) cluster_sync_all();
         }
@@ -2852,6 +2951,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
                 }
             }
             __syncwarp();
+            if (S.ovl == 1) cluster_sync_all();               // MID barrier of an overlapped pair
             if (lnf) cluster_sync_all();
             if (s + 1 < nst) {
                 // the next stage's descriptor goes to the other shared slot BEFORE this warp arrives at the stage-end barrier
@@ -2956,6 +3056,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_chain_kernel(const Params 
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                     if (++pb == 2) { pb = 0; pphase ^= 1u; }
+                    if (S.ovl == 1 && j == S.tiles - 2) {
+                        // MID barrier of an overlapped pair: tiles 0 .. T - 2 of every member are in memory, the successor's
+                        // main loop may read them (same fence protocol as a stage end)
+                        if (P.gpu_fence) __threadfence();
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                        cluster_sync_all();
+                    }
                 }
                 e_ring = (e_ring + S.tiles * (int)(S.K / 128)) % kRing;
             }
@@ -3263,6 +3370,16 @@ static int chain_plan_create(const tq_chain_stage* stages, int32_t n, int64_t M,
         a.y_ctr = g.kind == 0 ? reinterpret_cast<__nv_bfloat16*>(g.out) : nullptr;
         a.res_u8 = reinterpret_cast<const unsigned char*>(g.res_i8);
         a.ln_gamma = g.ln_gamma_q; a.ln_beta = g.ln_beta; a.ln_eps = g.ln_eps;
+    }
+    // overlapped pairs: a GELU stage with >= 2 tiles per CTA followed by the LayerNorm stage that consumes its output
+    static const bool ovl_on = [] { const char* e = getenv("TQ_CHAIN_OVERLAP"); return e == nullptr || e[0] != '0'; }();
+    for (int i = 0; ovl_on && i + 1 < n; ++i) {
+        StageTail &b = host[(size_t)i].t, &c = host[(size_t)i + 1].t;
+        if (b.kind == 1 && c.kind == 2 && c.K == b.N && b.tiles >= 2 && stages[i + 1].a_i8 == stages[i].out &&
+            (int64_t)csize * b.tiles * 2 == c.K / 128) {
+            b.ovl = 1;
+            c.ovl = 2;
+        }
     }
     StageDesc* dev = nullptr;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dev), sizeof(StageDesc) * (size_t)n);
