@@ -540,6 +540,11 @@ def test_engine_head_kernel_matches_gemm_path(hidden, heads, inter, monkeypatch)
         out[head] = eng(ids[1], mask).clone()
     assert torch.equal(out['0'], out['1'])
     assert float(out['1'].abs().max()) > 0.0
+    first = eng(ids[1], mask)                       # the engine returns a fresh tensor per call: a later forward must not overwrite it
+    keep = first.clone()
+    eng(ids[0], mask)
+    torch.cuda.synchronize()
+    assert torch.equal(first, keep)
 
 
 @pytest.mark.parametrize('M', [200, 384])

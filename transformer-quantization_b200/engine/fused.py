@@ -225,7 +225,6 @@ class FusedBertEngine:
             self.f8 = torch.empty(M, cfg.intermediate_size, **u8)
             self.first8 = torch.empty(batch, D, **u8)
             self.pooled8 = torch.empty(batch, D, **u8)
-            self.logits32 = torch.empty(batch, self.w_cls.N, dtype=torch.float32, device=dev)
         self.ffn_in_bf16 = os.environ.get('TQ_ENGINE_FFN_IN_BF16', '1') != '0'
         # lean int8 kernels (tq_linear_seg_qdq_i8 + the lean form of tq_linear_res_ln_qdq_i8): shapes they cover
         self.lean = (self.i8 and os.environ.get('TQ_ENGINE_LEAN', '1') != '0' and D % 128 == 0
@@ -436,8 +435,10 @@ class FusedBertEngine:
             x_site = d['z']
         if self.head:            # first token -> pooler -> classifier in one launch
             wp, wc = self.w_pool, self.w_cls
+            # (a fresh output tensor per call, like every other forward path: callers may keep the logits of several batches)
             logits = ops.head_i8(x, T * D, B, D, wc.N, wp.grid8, wp.rowsum, wp.bias, x_site.spec, wp.seg_spec, self.pool_out.spec,
-                                 wc.grid8, wc.rowsum, wc.bias, wc.seg_spec, self.cls_out.spec, self.logits32)
+                                 wc.grid8, wc.rowsum, wc.bias, wc.seg_spec, self.cls_out.spec,
+                                 torch.empty(B, wc.N, dtype=torch.float32, device=x.device))
         else:
             self.first8.copy_(x.view(B, T, D)[:, 0])                     # pooler input: first token
             w = self.w_pool
