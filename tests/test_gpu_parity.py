@@ -76,6 +76,7 @@ def _asym(ops, xmin, xmax, n_bits, dev=DEV):
 
 
 @pytest.mark.parametrize('shape', [(32, 128, 768), (8, 12, 128, 128), (1000003,), (5,), (4, 7, 13),
+                                   (32, 128, 3072), (32, 12, 128, 128), (64, 128, 512),   # the other BASELINE activation shapes, full size
                                    (8 * 1024 * 1024 + 4096 + 13,),      # bulk-copy staged kernel, ragged
                                    (20 * 1024 * 1024 + 4096 + 13,)])    # one-chunk-per-CTA kernel, ragged
 @pytest.mark.parametrize('n_bits', [8, 4])
@@ -180,6 +181,17 @@ def test_minmax_nan_propagates(ops):
     mn, mx = ops.minmax_axis(xa, 64, 96, 1)
     nan_cols = torch.isnan(mn).nonzero().flatten().tolist()
     assert nan_cols == [17] and torch.isnan(mx[17])
+    # several column blocks and slabs: the per-column-block ticket shares the first flag word of a block with that
+    # column's NaN flag (bit 0) -- NaNs in block-leading columns, twice in a row (the workspace must come back clean)
+    xb = torch.randn(4096, 768, device=DEV)
+    xb[100, 0] = xb[4000, 256] = xb[7, 300] = xb[2222, 767] = float('nan')
+    for _ in range(2):
+        mn, mx = ops.minmax_axis(xb, 4096, 768, 1)
+        assert torch.isnan(mn).nonzero().flatten().tolist() == [0, 256, 300, 767]
+        assert torch.isnan(mx).nonzero().flatten().tolist() == [0, 256, 300, 767]
+    clean = torch.nan_to_num(xb, nan=0.0)
+    mn, mx = ops.minmax_axis(clean, 4096, 768, 1)
+    assert torch.equal(mn, clean.min(dim=0).values) and torch.equal(mx, clean.max(dim=0).values)
 
 
 def test_misaligned_views(ops):
