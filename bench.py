@@ -560,10 +560,18 @@ def run_ours(args):
         # ---- the public forward: fused engine built from the calibrated model (module path if the
         #      configuration is outside the engine's support) ----
         from engine.fused import FusedBertEngine, UnsupportedByEngine
-        engine_kind = ('fused (engine/fused.py: 5 kernels per encoder layer -- QKV GEMM, attention, attention-out GEMM + residual + '
-                       'LayerNorm, FFN-in GEMM + GELU, FFN-out GEMM + residual + LayerNorm -- bf16 integer-grid carriers)')
         try:
             forward = FusedBertEngine(model, BATCH, SEQ)
+            engine_kind = ('fused (engine/fused.py, x_int byte carriers, int8 tensor cores: per encoder layer the attention kernel + '
+                           + {0: 'four GEMM kernels (attention-out + residual + LayerNorm, FFN-in + GELU, FFN-out + residual + LayerNorm, '
+                                 'next Q|K|V)',
+                              1: 'ONE encoder-chain launch (attention-out + residual + LayerNorm -> FFN-in + GELU -> FFN-out + residual + '
+                                 'LayerNorm -> next Q|K|V, a 4-CTA cluster per sequence)',
+                              2: 'everything in ONE encoder-chain launch for all layers'}[getattr(forward, 'chain', 0)]
+                           + ('; one-launch classification head)' if getattr(forward, 'head', False) else ')'))
+            if not getattr(forward, 'i8', False):
+                engine_kind = ('fused (engine/fused.py: 5 kernels per encoder layer -- QKV GEMM, attention, attention-out GEMM + residual + '
+                               'LayerNorm, FFN-in GEMM + GELU, FFN-out GEMM + residual + LayerNorm -- bf16 integer-grid carriers)')
         except UnsupportedByEngine as e:
             forward = model
             engine_kind = f'module path (one kernel per quantizer site): {e}'

@@ -16,6 +16,14 @@ layer, every tensor between them carried as the centred integer grid in bf16 (2 
 (``TQ_ENGINE_FUSE_LN=0`` or a ``trace`` request splits the two residual blocks back into
 tq_linear_res_qdq_bf16 + tq_ln_qdq_bf16: 7 kernels per layer.)
 
+8-bit operand mode (the default whenever every activation grid is unsigned, i.e. the BASELINE configuration): the
+tensors between the kernels are x_int BYTES, every GEMM runs on the int8 tensor cores with exact int32 accumulation,
+and the launches are merged further -- per layer the attention kernel plus ONE encoder-chain launch
+(``tq_chain_plan_*``: attention-output + LayerNorm -> FFN-in + GELU -> FFN-out + LayerNorm -> the next layer's Q | K | V,
+a 4-CTA cluster per sequence; ``TQ_ENGINE_CHAIN`` = 0 / 1 / 2 selects separate kernels / per-layer chains / the whole
+encoder in one launch), and one launch for the classification head (``tq_head_qdq_i8``): 27 launches per forward of
+BERT-base.  Every merged form is bit-identical to the separate kernels (tests/test_gpu_engine.py).
+
 The module-level path (quantization.* classes, one kernel per site + library ops) stays the
 reference-facing API and the calibration path; this engine is what the throughput benchmark runs.
 Supported: per-tensor quantizers with n_bits <= 8 at every site, seq 128, head_dim 64, hidden % 256
@@ -371,7 +379,7 @@ class FusedBertEngine:
         return logits
 
     def _forward_i8(self, input_ids, attention_mask, token_type_ids):
-        """the same chain with x_int byte carriers and int8 tensor-core GEMMs (5 kernels per layer)"""
+        """the same chain with x_int byte carriers and int8 tensor-core GEMMs (per layer: attention + one encoder-chain launch)"""
         ops = self.ops
         B, T, D, H, M = self.B, self.T, self.D, self.H, self.M
         mask = None
