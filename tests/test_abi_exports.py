@@ -132,3 +132,28 @@ def test_argument_errors_are_reported_before_any_device_work():
     assert handle.value is None
     assert lib.tq_chain_plan_run(None, None) == -1
     assert lib.tq_chain_plan_destroy(None) == 0
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """struct tq_qspec / tq_chain_stage: size and every field offset of the ctypes mirrors vs the C header (gcc)"""
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    structs = {'tq_qspec': tq_native.QSpec, 'tq_chain_stage': tq_native.ChainStage}
+    lines = ['#include "tq_b200.h"', '#include <stdio.h>', '#include <stddef.h>', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f'{cname}.{fname}']) == getattr(cls, fname).offset, (cname, fname)
